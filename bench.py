@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- p121 EBE-PCG throughput on B200 (BASELINE.json metric).
+
+A *step* is one PCG iteration of p121.f90:91-103 (gather -> storkm mat-vec -> scatter ->
+dot products / vector updates -> checon_par) over the whole mesh.  Workload at any N:
+BASELINE config C, the 125^3 20-node-hexahedra cube (1 953 125 elements, 23 531 000
+equations, 56.25 GB of storkm), partitioned over the N ranks with ParaFEM's own partition
+(strong scaling).  `value` = MDOF*iterations/s = neq * K / t / 1e6 with everything resident
+in HBM; `e2e` = the same through pf_pcg_solve with pinned HOST buffers for r_pp and xnew_pp.
+
+  python bench.py [--gpus N --steps K --warmup W]            this repo's CUDA path
+  python bench.py --impl reference [...]                     the CPU restatement of the reference
+                                                              (oracle/, all host threads)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "p121 EBE-PCG MDOF-iters/s"
+UNIT = "MDOF*iterations/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=125, help="cube edge in elements (125 = BASELINE config C)")
+    ap.add_argument("--nod", type=int, default=20, choices=[8, 20])
+    ap.add_argument("--cpu-n", type=int, default=40, help="cube edge of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=60)
+    ap.add_argument("--no-solve", action="store_true", help="skip the solve to convergence (time-to-solution)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            return None
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_leg(n, nod, steps, warmup):
+    """The oracle (CPU restatement of the reference, kind 'port') on a bounded sample."""
+    import oracle
+    from parafem_b200 import host
+    prob = host.cube_p121(n, n, n, nod)
+    t = time.time()
+    km = oracle.form_km_elastic(prob.g_coord_pp, prob.nod, prob.nip, prob.e, prob.v)
+    t_km = time.time() - t
+    cores = oracle.max_threads()
+    if warmup > 0:
+        oracle.pcg(km, prob.g_g_pp, prob.neq, prob.r_pp, -1.0, warmup, npes=cores, red_mode=0)
+    res = oracle.pcg(km, prob.g_g_pp, prob.neq, prob.r_pp, -1.0, steps, npes=cores, red_mode=0)
+    secs = res["seconds"]
+    val = prob.neq * res["iters"] / secs / 1e6
+    return {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{res['iters']} PCG iterations of p121 on a {n}^3 hex{nod} cube ({prob.nels} elements, "
+                      f"{prob.neq} equations, storkm {km.nbytes / 1e9:.2f} GB) after {warmup} warm-up iterations; "
+                      f"C restatement of the reference (oracle/pf_oracle.c, OpenMP over {cores} emulated ranks); "
+                      f"the Fortran+MPI reference itself cannot be built in this image",
+            "seconds": secs, "ms_per_step": 1e3 * secs / res["iters"], "storkm_form_seconds": t_km,
+            "neq": prob.neq, "steps": res["iters"]}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    c = cpu_leg(args.cpu_n, args.nod, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": c["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": c["steps"], "warmup": args.warmup, "ms_per_step": c["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"p121 {args.n}^3 hex{args.nod} cube (BASELINE config C), timed on the bounded sample "
+                                   f"named in cpu_baseline.sample", "step": "one PCG iteration"},
+            "cpu_baseline": {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": c["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from parafem_b200 import host, solver
+
+    if world > 1:
+        # control plane only (id broadcast, barriers, max over ranks); the data path is the
+        # library's own NCCL communicator
+        dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+    nranks = world
+
+    def barrier():
+        if nranks > 1:
+            dist.barrier()
+
+    def maxf(x):
+        if nranks == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    nccl_id = None
+    if nranks > 1:
+        idt = torch.from_numpy(solver.nccl_unique_id().copy()) if rank == 0 else torch.zeros(128, dtype=torch.uint8)
+        dist.broadcast(idt, src=0)
+        nccl_id = idt.numpy()
+
+    t_setup0 = time.time()
+    n = args.n
+    prob = host.cube_p121(n, n, n, args.nod, limit=20000, npes=nranks, numpe=rank + 1)
+    t_mesh = time.time() - t_setup0
+    s = solver.Solver(rank, nranks, local, nccl_id)
+    t0 = time.time()
+    solver.setup_problem(s, prob)
+    barrier()
+    t_dev_setup = time.time() - t0
+    ntot = prob.ntot
+    storkm_bytes_pp = prob.nels_pp * ntot * ntot * 8
+
+    K, W = args.steps, max(args.warmup, 3)
+    # ---- device-resident arm: `value` --------------------------------------------------------
+    s.pcg_load_rhs(prob.r_pp)
+    s.pcg_run(-1.0, W)                       # W untimed warm-up steps (tol < 0: never converges)
+    s.set_profile(True)
+    s.reset_profile()
+    sampler = ClockSampler(local)
+    barrier()
+    launches0 = s.kernel_launches()
+    if rank == 0:
+        sampler.start()
+    iters, _, ms = s.pcg_run(-1.0, K)        # exactly K steps, CUDA events on the solver stream
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = s.kernel_launches() - launches0
+    assert iters == K
+    ms = maxf(ms)
+    mv_ms, mv_n = s.kernel_ms(0)
+    sc_ms, sc_n = s.kernel_ms(1)
+    vec_ms, vec_n = s.kernel_ms(2)
+    halo_ms, halo_n = s.kernel_ms(3)
+    s.set_profile(False)
+    value = prob.neq * K / (ms / 1e3) / 1e6
+
+    # ---- end-to-end arm: host buffers through pf_pcg_solve ----------------------------------
+    r_pin = torch.empty(prob.neq_pp, dtype=torch.float64).pin_memory()
+    x_pin = torch.empty(prob.neq_pp, dtype=torch.float64).pin_memory()
+    r_np, x_np = r_pin.numpy(), x_pin.numpy()
+    r_np[:] = prob.r_pp
+    import ctypes as C
+    from parafem_b200._lib import lib, ptr
+    it_c, cv_c = C.c_int(), C.c_int()
+
+    def e2e_once(k):
+        barrier()
+        t = time.perf_counter()
+        rc = lib().pf_pcg_solve(s._h, ptr(r_np), -1.0, k, ptr(x_np), C.byref(it_c), C.byref(cv_c))
+        assert rc == 0 and it_c.value == k
+        chk = float(x_np[0])                 # the step's result is read on the host
+        dt = time.perf_counter() - t
+        return maxf(dt), chk
+
+    e2e_once(W)
+    e2e_s, _ = e2e_once(K)
+    e2e_value = prob.neq * K / e2e_s / 1e6
+
+    # ---- solve to convergence: time-to-solution, iteration count ---------------------------
+    tts = None
+    if not args.no_solve:
+        s.pcg_load_rhs(prob.r_pp)
+        barrier()
+        it_full, conv, ms_full = s.pcg_run(prob.tol, prob.limit)
+        ms_full = maxf(ms_full)
+        x = s.pcg_get_x()
+        tts = {"iters": it_full, "converged": bool(conv), "solve_s": ms_full / 1e3,
+               "mdof_iters_per_s": prob.neq * it_full / (ms_full / 1e3) / 1e6,
+               "x1": float(x[0]) if rank == 0 else None, "tol": prob.tol}
+
+    pk, pk_kind = peaks()
+    mv_avg_ms = mv_ms / max(mv_n, 1)
+    achieved = storkm_bytes_pp / (mv_avg_ms / 1e3) / 1e9 if mv_n else None
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = f"hex{args.nod}_n{n}_gpus{nranks}"
+        traffic = tj.get(key, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    cpu = None
+    if rank == 0 and nranks == 1 and not args.no_cpu:
+        cpu = cpu_leg(args.cpu_n, args.nod, args.cpu_steps, 3)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": nranks, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"p121 {n}^3 hex{args.nod} cube, p12meshgen geometry (BASELINE config "
+                                   f"{'C' if (n, args.nod) == (125, 20) else 'custom'}): {prob.nels} elements, "
+                                   f"{prob.neq} equations, storkm {prob.nels * ntot * ntot * 8 / 1e9:.2f} GB",
+                       "step": "one PCG iteration (gather, storkm mat-vec, scatter, dots/updates, checon_par)",
+                       "partition": f"ParaFEM calc_nels_pp/calc_neq_pp over {nranks} rank(s)",
+                       "l2": "inputs larger than L2 (storkm stream per rank >> 126 MB), no flush needed",
+                       "nels": prob.nels, "neq": prob.neq, "nod": args.nod, "nip": prob.nip},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": prob.neq_pp * 8 / K,
+                    "d2h_bytes_per_step": prob.neq_pp * 8 / K, "seconds": e2e_s,
+                    "note": "pf_pcg_solve with pinned host r_pp in / xnew_pp out, K iterations per call"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": traffic,
+                         "kernel": "k_matvec (storkm stream; gather fused)", "peak_kind": pk_kind,
+                         "algorithmic_bytes_per_launch": storkm_bytes_pp, "avg_launch_ms": mv_avg_ms,
+                         "launches_timed": int(mv_n)},
+            "kernel_ms_per_step": {"matvec": mv_ms / K, "scatter": sc_ms / K, "vector_and_reductions": vec_ms / K,
+                                   "halo": halo_ms / K},
+            "clocks": clocks,
+            "time_to_solution": tts,
+            "setup_s": {"mesh_host": t_mesh, "device_setup_incl_storkm": t_dev_setup},
+            "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+        }
+        print(json.dumps(line), flush=True)
+    s.close()
+    if nranks > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

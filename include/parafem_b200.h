@@ -1,0 +1,228 @@
+/*
+ * parafem_b200.h -- C-ABI of libparafem_b200.so
+ *
+ * B200-native (sm_100a) replacement for the EBE-PCG hot path of ParaFEM programs
+ * p121 (3-D elasticity, 20-/8-node hexahedra) and p123 (steady heat conduction,
+ * 8-node hexahedra).  It is, in the reference's own terms, the missing
+ * "modules/gpu" platform library (parafem/src/modules/readme.txt:9-40).
+ *
+ * Conventions (same as the reference's existing CUDA boundary,
+ * parafem/src/programs/dev/xx3/cuda_helpers.cu:183-368 and the
+ * `interface ... bind(C)` block at xx3.f90:56-148):
+ *   - plain C symbols, callable from Fortran through ISO_C_BINDING
+ *     (see fortran/parafem_gpu.f90) -- no torch / C++ types in any signature;
+ *   - every function returns 0 on success and >0 on error; it never calls
+ *     exit().  pf_last_error() returns the message (xx3 prints it with printf);
+ *   - all host arrays are the caller's, in Fortran (column-major) layout with
+ *     1-based CONTENTS (node numbers, equation numbers; 0 = restrained);
+ *     the library never keeps a host pointer after a call returns;
+ *   - reals are REAL(iwp) = double (precision.f90:19); node and equation numbers
+ *     are default INTEGER = int32 as in the reference; SIZES are int64 because
+ *     xx3's int*int byte counts overflow past 596 523 hex20 elements
+ *     (cuda_helpers.cu:205,242,264);
+ *   - one MPI rank <-> one process <-> one GPU; rank = numpe-1.
+ *
+ * Section A is the device API (needs a B200).  Section B are host-side helpers
+ * that restate the ParaFEM library routines the Fortran driver would call
+ * between read_p121 and make_ggl; they exist because this image has no Fortran
+ * compiler and the host driver (parafem_b200/csrc/p121_b200.cpp and the Python
+ * mirror parafem_b200/driver.py) has to be written in C++/Python.  They run on
+ * the CPU and do not need a GPU.
+ */
+#ifndef PARAFEM_B200_H
+#define PARAFEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pf_ctx *pf_handle;
+
+/* ===================================================================== */
+/* A. Device API                                                          */
+/* ===================================================================== */
+
+/* --- process / device / communicator ---------------------------------
+ * Replaces set_gpu (xx3/cuda_helpers.cu:183-192) and find_pe_procs' device
+ * side (mp_interface.f90:42-91).  For nranks > 1 rank 0 calls
+ * pf_nccl_unique_id(), the driver broadcasts the 128 bytes (MPI_BCAST in
+ * Fortran, torch.distributed in bench.py) and every rank passes them to
+ * pf_init.  id128 may be NULL when nranks == 1.                          */
+int pf_nccl_unique_id(void *id128);
+int pf_init(int rank, int nranks, int device, const void *id128, pf_handle *h);
+int pf_finalize(pf_handle h);
+int pf_last_error(pf_handle h, char *buf, int len);  /* h may be NULL: last global error */
+int pf_version(void);
+
+/* --- mesh setup --------------------------------------------------------
+ * Called once between make_ggl (p121.f90:49) and DEALLOCATE(g_g_pp)
+ * (p121.f90:86).  Replaces allocate_memory_on_gpu + copy_*_data_to_gpu
+ * (xx3.f90:409-463).  The gather/scatter tables (ggl_pp, toget/toput of
+ * gather_scatter.f90:50-70, PRIVATE there) are rebuilt inside the library
+ * from g_g_pp and the closed-form owner map of calc_neq_pp
+ * (gather_scatter.f90:319-339), so the Fortran module needs no accessor.
+ *   nod          nodes per element (8 or 20), nodof dof per node (3 or 1)
+ *   nip          Gauss points (1, 8)
+ *   nels_pp      elements of this rank
+ *   g_coord_pp   (nod, ndim=3, nels_pp) coordinates        [p121.f90:33]
+ *   g_g_pp       (ntot, nels_pp) global equation numbers, 0 = restrained
+ *   neq          global equation count; ieq_start 1-based; neq_pp owned   */
+int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp,
+                  const double *g_coord_pp, const int32_t *g_g_pp,
+                  int64_t neq, int64_t ieq_start, int64_t neq_pp);
+
+/* --- element matrices --------------------------------------------------
+ * pf_form_km_elastic: elements_1/gauss_pts_1 of p121.f90:54-64 (deemat,
+ * sample, shape_der, invert, beemat, BtDB*det*w) formed ON the device into
+ * storkm_pp(ntot,ntot,nels_pp), which never crosses PCIe.
+ * pf_form_kc_laplace: p123.f90:70-84 (kcx,kcy,kcz -> storkc_pp).
+ * pf_set_storkm uploads a host storkm_pp instead (xx3's
+ * copy_3d_data_to_gpu, xx3.f90:440-452); pf_get_storkm reads n elements
+ * starting at 0-based local element iel0 back (parity tests).
+ * pf_set_matrix_free(1): do not store storkm; recompute km inside the
+ * mat-vec kernel every iteration (BASELINE config E).                     */
+int pf_form_km_elastic(pf_handle h, double e, double v);
+int pf_form_kc_laplace(pf_handle h, double kx, double ky, double kz);
+int pf_set_storkm(pf_handle h, const double *storkm_pp);
+int pf_get_storkm(pf_handle h, int64_t iel0, int64_t n, double *out);
+int pf_set_matrix_free(pf_handle h, int on);
+
+/* --- diagonal preconditioner -------------------------------------------
+ * p121.f90:65-69,86 / p123.f90:86-92,120-125.  no_f_pp are the GLOBAL
+ * 1-based equation numbers of this rank's fixed freedoms (p123's no_f_pp),
+ * nfixed_pp may be 0.  After the call the device holds 1/diag; store_pp
+ * (p123.f90:123) can be fetched with pf_get_store.  pf_get_diag_precon
+ * returns the INVERTED diagonal (diag_precon_pp after p121.f90:86).       */
+int pf_build_precon(pf_handle h, int64_t nfixed_pp, const int32_t *no_f_pp,
+                    double penalty);
+int pf_get_diag_precon(pf_handle h, double *diag_precon_pp);
+int pf_get_store(pf_handle h, double *store_pp);
+
+/* --- the solve -----------------------------------------------------------
+ * pf_pcg_solve = p121.f90:87-104 / p123.f90:132-151: d=M^-1 r, p=d, x=0,
+ * then the PCG loop with checon_par's stopping rule evaluated every
+ * iteration.  r_pp in (host, neq_pp), xnew_pp out (host, neq_pp).
+ * The three-call form keeps the vectors resident (bench `value`):
+ * pf_pcg_load_rhs (H2D) / pf_pcg_run (device only; elapsed_ms from CUDA
+ * events on the solver stream) / pf_pcg_get_x (D2H).                      */
+int pf_pcg_solve(pf_handle h, const double *r_pp, double tol, int limit,
+                 double *xnew_pp, int *iters, int *converged);
+int pf_pcg_load_rhs(pf_handle h, const double *r_pp);
+int pf_pcg_run(pf_handle h, double tol, int limit, int *iters, int *converged,
+               double *elapsed_ms);
+int pf_pcg_get_x(pf_handle h, double *xnew_pp);
+/* checon_par ratio max|xnew-x|/max|xnew| of every iteration of the last run */
+int pf_get_ratio_history(pf_handle h, double *out, int maxn, int *n);
+
+/* --- fine-grained entry points (kernel-level parity tests) --------------
+ * Same argument meaning as the reference routines they replace:
+ *   pf_gather  = gather(p_pp,pmul_pp)            gather_scatter.f90:547-688
+ *   pf_matvec  = elements_3 loop                 p121.f90:93-97
+ *   pf_scatter = scatter(u_pp,utemp_pp), u_pp zeroed first  :694-850
+ *   pf_apply   = the three fused as the solver runs them (u = A p)
+ *   pf_dot     = dot_product_p                   maths.f90:168-216
+ *   pf_norm    = norm_p                          maths.f90:222-265
+ * All pointers are host arrays.                                           */
+int pf_gather(pf_handle h, const double *p_pp, double *pmul_pp);
+int pf_matvec(pf_handle h, const double *pmul_pp, double *utemp_pp);
+int pf_scatter(pf_handle h, const double *utemp_pp, double *u_pp);
+int pf_apply(pf_handle h, const double *p_pp, double *u_pp);
+int pf_dot(pf_handle h, const double *a_pp, const double *b_pp, double *result);
+int pf_norm(pf_handle h, const double *a_pp, double *result);
+
+/* --- post-solve ---------------------------------------
+ * pf_centroid_stress: p121.f90:113-123 for local 0-based element iel
+ * (gather of xnew into eld, one shape_der/beemat at the centroid,
+ * sigma = dee*bee*eld).  Uses the x of the last solve.                    */
+int pf_centroid_stress(pf_handle h, int64_t iel, double e, double v, double *sigma6);
+
+/* --- measurement ---------------------------------------------------------
+ * pf_set_profile(1) brackets every launch of the named kernels with CUDA
+ * events on the solver stream; pf_get_kernel_ms returns the sum and the
+ * count since the last pf_pcg_run/pf_reset_profile.
+ * which: 0 mat-vec (storkm stream), 1 scatter, 2 vector updates+reductions,
+ *        3 halo exchange.                                                 */
+int pf_set_profile(pf_handle h, int on);
+int pf_reset_profile(pf_handle h);
+int pf_get_kernel_ms(pf_handle h, int which, double *total_ms, int64_t *launches);
+int64_t pf_kernel_launches(pf_handle h); /* all kernel launches since pf_init */
+int pf_device_info(pf_handle h, int *sm_count, int64_t *free_bytes, int64_t *total_bytes);
+
+/* ===================================================================== */
+/* B. Host helpers (CPU; restate ParaFEM library routines)                */
+/* ===================================================================== */
+
+/* calc_nels_pp partitioner 1 (gather_scatter.f90:217-238) and calc_neq_pp
+ * (gather_scatter.f90:319-339).  numpe is 1-based; *_start 1-based.       */
+void pf_calc_nels_pp(int64_t nels, int npes, int numpe, int64_t *nels_pp, int64_t *iel_start);
+void pf_calc_neq_pp(int64_t neq, int npes, int numpe, int64_t *neq_pp, int64_t *ieq_start);
+
+/* p12meshgen cubes (tools/preprocessing/p12meshgen/p12meshgen.f90:118-236,
+ * 658-701; geometry.f90 geometry_20bxz :175-286, geometry_8bxz :70-169,
+ * cube_bc20 :425-500, cube_bc8 :589-650, box_bc8 :652-696; loading.f90
+ * load_p121 :386-546).
+ * round_mode 0: full-precision values; 1: values as they survive the deck
+ * text formats (coordinates E14.6, loads E16.8).                          */
+int pf_p121_sizes(int nxe, int nye, int nze, int nod,
+                  int64_t *nn, int64_t *nr, int64_t *loaded_nodes);
+int pf_p123_sizes(int nxe, int nye, int nze, int64_t *nn, int64_t *nr, int64_t *nres);
+/* elements iel_start .. iel_start+nels_pp-1 (1-based) in S&G node order:
+ * g_num_pp(nod,nels_pp), g_coord_pp(nod,3,nels_pp)                         */
+int pf_cube_elements(int nxe, int nze, int nod, double aa, double bb, double cc,
+                     int64_t iel_start, int64_t nels_pp, int round_mode,
+                     int32_t *g_num_pp, double *g_coord_pp);
+/* rest(nr,nodof+1) column-major: kind 0 = cube_bc20/cube_bc8 (p121),
+ * kind 1 = box_bc8 (p123)                                                 */
+int pf_cube_rest(int kind, int nxe, int nye, int nze, int nod, int64_t nr, int32_t *rest);
+/* load_p121 scaled as p12meshgen does; node(loaded), val(3,loaded)        */
+int pf_p121_loads(int nxe, int nze, int nod, double aa, double bb, int round_mode,
+                  int32_t *node, double *val);
+
+/* rearrange + find_g3 (new_library.f90:3059-3112, 3130-3212) and
+ * rearrange_2 + find_g4 (:3118-3124, 3249-3271) restated as "number the free
+ * freedoms in ascending node order": nf(nodof,nn), 0 = restrained.         */
+int pf_form_nf(int64_t nn, int nodof, int64_t nr, const int32_t *rest,
+               int32_t *nf, int64_t *neq);
+int pf_find_g(int nod, int nodof, int64_t nels_pp, const int32_t *g_num_pp,
+              const int32_t *nf, int32_t *g_g_pp);
+/* load + scatter_noadd (loading.f90:36-142): r_pp(neq_pp) from nodal loads */
+int pf_load(int nodof, int64_t loaded_nodes, const int32_t *node, const double *val,
+            const int32_t *nf, int64_t ieq_start, int64_t neq_pp, double *r_pp);
+/* abaqus2sg (new_library.f90:3515-3682) for hexahedra, in place            */
+int pf_abaqus2sg(int nod, int64_t nels, int32_t *g_num);
+
+/* deck readers (formats: SURVEY Appendix A; input.f90:3234-3396 read_p121,
+ * :3620-3806 read_p123, :288-445 read_g_coord_pp, :935-1080 read_g_num_pp,
+ * :2570-2632 read_rest, :2350-2411 read_loads).  job = path without suffix */
+typedef struct {
+  int program;      /* 121 or 123 */
+  int meshgen, partitioner, nip, nod, limit;
+  int64_t nels, nn, nr, loaded, fixed, nres;
+  double e, v, kx, ky, kz, tol;
+} pf_deck_info;
+int pf_read_dat(const char *job, int program, pf_deck_info *info);
+int pf_read_d(const char *job, int64_t nn, int64_t nels, int nod,
+              double *g_coord /*(3,nn)*/, int32_t *g_num /*(nod,nels)*/);
+int pf_read_bnd(const char *job, int64_t nr, int nodof, int32_t *rest);
+int pf_read_lds(const char *job, int64_t loaded, int nodof, int32_t *node, double *val);
+/* g_coord_pp(nod,3,nels_pp) from g_coord(3,nn) and g_num_pp                */
+int pf_coords_pp(int nod, int64_t nels_pp, const int32_t *g_num_pp,
+                 const double *g_coord, double *g_coord_pp);
+
+/* Halo tables (make_ggl, gather_scatter.f90:1387-1780, rebuilt from g_g_pp).
+ * Local numbering of this rank's gather buffer: slot 0 = restrained dump
+ * slot, 1..neq_pp = owned equations, then the remote equations the local
+ * elements touch, grouped by owner rank ascending, ascending inside a group.
+ * ggl_pp(ntot,nels_pp) receives slot numbers; halo_eq receives the global
+ * numbers of the remote slots (capacity cap); halo_cnt[npes] per owner.
+ * Returns the number of remote slots in *nhalo (call with cap = 0 to size). */
+int pf_make_ggl(int ntot, int64_t nels_pp, const int32_t *g_g_pp, int64_t neq,
+                int npes, int numpe, int32_t *ggl_pp, int64_t cap,
+                int32_t *halo_eq, int64_t *halo_cnt, int64_t *nhalo);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,175 @@
+"""ctypes wrapper of the CPU oracle (oracle/pf_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs -- never by parafem_b200/.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpf_oracle.so")
+_lib = None
+
+vp, i64, cint, dbl = C.c_void_p, C.c_int64, C.c_int, C.c_double
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "pf_oracle.c")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "CC=gcc"] + (["-B"] if force else []), check=True,
+                       stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        L.orc_dot_blocked.restype = dbl
+        L.orc_dot_blocked.argtypes = [vp, vp, i64]
+        L.orc_dot_ranks.restype = dbl
+        L.orc_dot_ranks.argtypes = [vp, vp, i64, cint, cint]
+        L.orc_determinant3.restype = dbl
+        L.orc_form_km_elastic.argtypes = [i64, cint, cint, vp, dbl, dbl, vp]
+        L.orc_form_kc_laplace.argtypes = [i64, cint, cint, vp, dbl, dbl, dbl, vp]
+        L.orc_centroid_stress.argtypes = [cint, vp, vp, dbl, dbl, vp]
+        L.orc_gather.argtypes = [cint, i64, vp, vp, vp]
+        L.orc_matvec.argtypes = [cint, i64, vp, vp, vp]
+        L.orc_scatter.argtypes = [cint, i64, vp, i64, cint, vp, vp]
+        L.orc_rearrange.argtypes = [i64, cint, vp]
+        L.orc_rearrange_2.argtypes = [i64, vp]
+        L.orc_find_g3.argtypes = [cint, cint, vp, vp, i64, vp]
+        L.orc_find_g4.argtypes = [cint, vp, vp, i64, vp]
+        L.orc_partition.argtypes = [i64, cint, cint, C.POINTER(i64), C.POINTER(i64)]
+        L.orc_pcg.argtypes = [cint, i64, vp, vp, i64, vp, i64, vp, vp, dbl, cint, cint, dbl, cint, vp,
+                              C.POINTER(cint), C.POINTER(cint), vp, vp, C.POINTER(dbl)]
+        L.orc_sample_hex.argtypes = [cint, vp, vp]
+        L.orc_shape_der.argtypes = [cint, vp, cint, cint, vp]
+        L.orc_set_threads.argtypes = [cint]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(vp)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def set_threads(n):
+    lib().orc_set_threads(int(n))
+
+
+def max_threads():
+    return lib().orc_max_threads()
+
+
+def form_km_elastic(g_coord_pp, nod, nip, e, v):
+    """g_coord_pp (nels,3,nod) -> storkm (nels, ntot, ntot) [Fortran storkm_pp(i,j,iel) = out[iel,j,i]]."""
+    g = _f64(g_coord_pp)
+    nels = g.shape[0]
+    out = np.empty((nels, 3 * nod, 3 * nod))
+    rc = lib().orc_form_km_elastic(nels, nod, nip, _p(g), e, v, _p(out))
+    assert rc == 0
+    return out
+
+
+def form_kc_laplace(g_coord_pp, nip, kx, ky, kz):
+    g = _f64(g_coord_pp)
+    nels = g.shape[0]
+    out = np.empty((nels, 8, 8))
+    rc = lib().orc_form_kc_laplace(nels, 8, nip, _p(g), kx, ky, kz, _p(out))
+    assert rc == 0
+    return out
+
+
+def centroid_stress(nod, coord, eld, e, v):
+    sig = np.empty(6)
+    rc = lib().orc_centroid_stress(nod, _p(_f64(coord)), _p(_f64(eld)), e, v, _p(sig))
+    assert rc == 0
+    return sig
+
+
+def gather(g_g, p):
+    g = _i32(g_g)
+    out = np.empty(g.shape)
+    lib().orc_gather(g.shape[1], g.shape[0], _p(g), _p(_f64(p)), _p(out))
+    return out
+
+
+def matvec(storkm, pmul):
+    k = _f64(storkm)
+    out = np.empty((k.shape[0], k.shape[1]))
+    lib().orc_matvec(k.shape[1], k.shape[0], _p(k), _p(_f64(pmul)), _p(out))
+    return out
+
+
+def scatter(g_g, utemp, neq, npes=1):
+    g = _i32(g_g)
+    u = np.zeros(neq)
+    lib().orc_scatter(g.shape[1], g.shape[0], _p(g), neq, npes, _p(_f64(utemp)), _p(u))
+    return u
+
+
+def dot_blocked(a, b):
+    a, b = _f64(a), _f64(b)
+    return lib().orc_dot_blocked(_p(a), _p(b), a.size)
+
+
+def dot_ranks(a, b, npes=1, red_mode=1):
+    a, b = _f64(a), _f64(b)
+    return lib().orc_dot_ranks(_p(a), _p(b), a.size, npes, red_mode)
+
+
+def find_g3(g_num, rest, nodof=3):
+    """rearrange + find_g3 over all elements; rest (nodof+1, nr) as read from .bnd (copied)."""
+    rest = _i32(rest).copy()
+    nr = rest.shape[1]
+    lib().orc_rearrange(nr, nodof, _p(rest))
+    g_num = _i32(g_num)
+    nels, nod = g_num.shape
+    g = np.zeros((nels, nod * nodof), np.int32)
+    for e in range(nels):
+        lib().orc_find_g3(nod, nodof, _p(g_num[e]), _p(g[e]), nr, _p(rest))
+    return g
+
+
+def find_g4(g_num, rest):
+    rest = _i32(rest).copy()
+    nr = rest.shape[1]
+    lib().orc_rearrange_2(nr, _p(rest))
+    g_num = _i32(g_num)
+    nels, nod = g_num.shape
+    g = np.zeros((nels, nod), np.int32)
+    for e in range(nels):
+        lib().orc_find_g4(nod, _p(g_num[e]), _p(g[e]), nr, _p(rest))
+    return g
+
+
+def pcg(storkm, g_g, neq, r, tol, limit, npes=1, red_mode=0, no_f=None, val_f=None, penalty=1e20):
+    """p121.f90:65-104 / p123.f90:86-151 on global arrays.  Returns dict(x, iters, converged,
+    ratio, diag, seconds)."""
+    k, g, r = _f64(storkm), _i32(g_g), _f64(r)
+    nels, ntot = g.shape
+    nfixed = 0 if no_f is None else len(no_f)
+    no_f = _i32(no_f) if nfixed else None
+    val_f = _f64(val_f) if nfixed else None
+    x = np.empty(neq)
+    diag = np.empty(neq)
+    ratio = np.zeros(limit)
+    it, conv, secs = cint(), cint(), dbl()
+    rc = lib().orc_pcg(ntot, nels, _p(g), _p(k), neq, _p(r), nfixed, _p(no_f), _p(val_f), penalty, npes,
+                       red_mode, tol, limit, _p(x), C.byref(it), C.byref(conv), _p(ratio), _p(diag),
+                       C.byref(secs))
+    assert rc == 0
+    return dict(x=x, iters=it.value, converged=bool(conv.value), ratio=ratio[:it.value], diag=diag,
+                seconds=secs.value)

@@ -1,0 +1,635 @@
+/*
+ * pf_oracle.c -- CPU ORACLE for the EBE-PCG hot path of ParaFEM p121 / p123.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, the
+ * __graft_entry__.smoke() check and bench.py's cpu_baseline / --impl reference
+ * legs may load it.  Nothing under parafem_b200/ links, imports or calls it.
+ *
+ * It is a plain-C restatement (not a copy) of the reference's algorithm; the
+ * reference itself is Fortran 90 + MPI and cannot be compiled in this image
+ * (no gfortran, no MPI -- see DESIGN.md), so there is no oracle/_ref binary.
+ * Parity is pinned against the reference's own golden outputs instead
+ * (tests/golden/, tests/test_oracle_golden.py): xx3-tiny 79 iterations +
+ * 756x3 displacements, p121_demo 98 360 equations / 295 iterations / x(1) /
+ * centroid stresses / EnSight displacement field, p121 book 777 520 equations,
+ * p123 potentials.
+ *
+ * Reference files followed (under /root/reference/parafem/src):
+ *   programs/5th_ed/p121/p121.f90 (whole), programs/5th_ed/p123/p123.f90 (whole)
+ *   modules/shared/new_library.f90: shape_der :745-896, beemat :918-1000,
+ *       sample :1397-1520, deemat :1604-1691, rearrange :3059-3112,
+ *       rearrange_2 :3118-3124, find_g3 :3130-3212, find_g4 :3249-3271
+ *   modules/mpi/maths.f90: dot_product_p :168-216, invert :490-565,
+ *       determinant :571-629, checon_par :999-1069
+ *   modules/mpi/gather_scatter.f90: calc_nels_pp :146-257, calc_neq_pp :263-343,
+ *       gather :547-688, scatter :694-850
+ *
+ * Arithmetic contract (compile with -O2 -ffp-contract=off, never -ffast-math):
+ *   - every MATMUL is C(i,j) = sum_k A(i,k)*B(k,j), k ascending, separate
+ *     multiply and add (what gfortran's inlined MATMUL does without FMA);
+ *   - scatter adds element contributions in ascending element order inside a
+ *     rank (gather_scatter.f90:759-761), the owner adds its own partial sum
+ *     first and then the other ranks' partial sums in ASCENDING RANK ORDER (the
+ *     reference adds them in arrival order, :829-832 -- any order is a legal
+ *     reference execution, this one is reproducible);
+ *   - reductions: red_mode 0 = sequential DOT_PRODUCT per rank then ranks
+ *     ascending (one legal MPI_ALLREDUCE order); red_mode 1 = the fixed blocked
+ *     tree documented at orc_dot_blocked (another legal order, and the one the
+ *     CUDA path uses, so GPU-vs-oracle comparisons can be exact).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* element library                                                            */
+/* ------------------------------------------------------------------------- */
+
+/* sample('hexahedron'), new_library.f90:1397-1433.  points(nip,3) col-major. */
+int orc_sample_hex(int nip, double *points, double *weights) {
+  if (nip == 1) {
+    points[0] = points[1] = points[2] = 0.0; weights[0] = 8.0; return 0;
+  }
+  if (nip == 8) {
+    const double r = 1.0 / sqrt(3.0);
+    /* sign pattern of the 8 points in the reference's order */
+    static const int sx[8] = {1, 1, 1, 1, -1, -1, -1, -1};
+    static const int sy[8] = {1, 1, -1, -1, 1, -1, 1, -1};
+    static const int sz[8] = {1, -1, 1, -1, 1, 1, -1, -1};
+    for (int i = 0; i < 8; ++i) {
+      points[0 * 8 + i] = sx[i] > 0 ? r : -r;
+      points[1 * 8 + i] = sy[i] > 0 ? r : -r;
+      points[2 * 8 + i] = sz[i] > 0 ? r : -r;
+      weights[i] = 1.0;
+    }
+    return 0;
+  }
+  return 1;
+}
+
+/* shape_der for 3-D nod = 8 / 20 at Gauss point i (0-based); der(3,nod) col-major,
+ * new_library.f90:745-755, 769-794, 865-896 */
+int orc_shape_der(int nod, const double *points, int nip, int i, double *der) {
+  const double xi = points[0 * nip + i], eta = points[1 * nip + i], zeta = points[2 * nip + i];
+#define DER(a, l) der[((l)-1) * 3 + ((a)-1)]
+  if (nod == 8) {
+    const double etam = 1.0 - eta, xim = 1.0 - xi, zetam = 1.0 - zeta;
+    const double etap = eta + 1.0, xip = xi + 1.0, zetap = zeta + 1.0;
+    DER(1, 1) = -0.125 * etam * zetam; DER(1, 2) = -0.125 * etam * zetap;
+    DER(1, 3) = 0.125 * etam * zetap;  DER(1, 4) = 0.125 * etam * zetam;
+    DER(1, 5) = -0.125 * etap * zetam; DER(1, 6) = -0.125 * etap * zetap;
+    DER(1, 7) = 0.125 * etap * zetap;  DER(1, 8) = 0.125 * etap * zetam;
+    DER(2, 1) = -0.125 * xim * zetam;  DER(2, 2) = -0.125 * xim * zetap;
+    DER(2, 3) = -0.125 * xip * zetap;  DER(2, 4) = -0.125 * xip * zetam;
+    DER(2, 5) = 0.125 * xim * zetam;   DER(2, 6) = 0.125 * xim * zetap;
+    DER(2, 7) = 0.125 * xip * zetap;   DER(2, 8) = 0.125 * xip * zetam;
+    DER(3, 1) = -0.125 * xim * etam;   DER(3, 2) = 0.125 * xim * etam;
+    DER(3, 3) = 0.125 * xip * etam;    DER(3, 4) = -0.125 * xip * etam;
+    DER(3, 5) = -0.125 * xim * etap;   DER(3, 6) = 0.125 * xim * etap;
+    DER(3, 7) = 0.125 * xip * etap;    DER(3, 8) = -0.125 * xip * etap;
+    return 0;
+  }
+  if (nod == 20) {
+    static const int xii[20] = {-1, -1, -1, 0, 1, 1, 1, 0, -1, -1, 1, 1, -1, -1, -1, 0, 1, 1, 1, 0};
+    static const int etai[20] = {-1, -1, -1, -1, -1, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1};
+    static const int zetai[20] = {-1, 0, 1, 1, 1, 0, -1, -1, -1, 1, 1, -1, -1, 0, 1, 1, 1, 0, -1, -1};
+    for (int l = 1; l <= 20; ++l) {
+      const double xl = xii[l - 1], el = etai[l - 1], zl = zetai[l - 1];
+      const double xi0 = xi * xl, eta0 = eta * el, zeta0 = zeta * zl;
+      if (l == 4 || l == 8 || l == 16 || l == 20) {
+        DER(1, l) = -.5 * xi * (1. + eta0) * (1. + zeta0);
+        DER(2, l) = .25 * el * (1. - xi * xi) * (1. + zeta0);
+        DER(3, l) = .25 * zl * (1. - xi * xi) * (1. + eta0);
+      } else if (l >= 9 && l <= 12) {
+        DER(1, l) = .25 * xl * (1. - eta * eta) * (1. + zeta0);
+        DER(2, l) = -.5 * eta * (1. + xi0) * (1. + zeta0);
+        DER(3, l) = .25 * zl * (1. + xi0) * (1. - eta * eta);
+      } else if (l == 2 || l == 6 || l == 14 || l == 18) {
+        DER(1, l) = .25 * xl * (1. + eta0) * (1. - zeta * zeta);
+        DER(2, l) = .25 * el * (1. + xi0) * (1. - zeta * zeta);
+        DER(3, l) = -.5 * zeta * (1. + xi0) * (1. + eta0);
+      } else {
+        DER(1, l) = .125 * xl * (1. + eta0) * (1. + zeta0) * (2. * xi0 + eta0 + zeta0 - 1.);
+        DER(2, l) = .125 * el * (1. + xi0) * (1. + zeta0) * (xi0 + 2. * eta0 + zeta0 - 1.);
+        DER(3, l) = .125 * zl * (1. + xi0) * (1. + eta0) * (xi0 + eta0 + 2. * zeta0 - 1.);
+      }
+    }
+    return 0;
+  }
+#undef DER
+  return 1;
+}
+
+#define M3(m, r, c) (m)[((c)-1) * 3 + ((r)-1)]
+
+/* determinant, 3x3 branch, maths.f90:617-619 */
+double orc_determinant3(const double *jac) {
+  double det = M3(jac, 1, 1) * (M3(jac, 2, 2) * M3(jac, 3, 3) - M3(jac, 3, 2) * M3(jac, 2, 3));
+  det = det - M3(jac, 1, 2) * (M3(jac, 2, 1) * M3(jac, 3, 3) - M3(jac, 3, 1) * M3(jac, 2, 3));
+  det = det + M3(jac, 1, 3) * (M3(jac, 2, 1) * M3(jac, 3, 2) - M3(jac, 3, 1) * M3(jac, 2, 2));
+  return det;
+}
+
+/* invert, 3x3 branch (adjugate / det), maths.f90:526-547 */
+void orc_invert3(double *m) {
+  double det = orc_determinant3(m);
+  double j11 = M3(m, 2, 2) * M3(m, 3, 3) - M3(m, 3, 2) * M3(m, 2, 3);
+  double j21 = -(M3(m, 2, 1) * M3(m, 3, 3)) + M3(m, 3, 1) * M3(m, 2, 3);
+  double j31 = M3(m, 2, 1) * M3(m, 3, 2) - M3(m, 3, 1) * M3(m, 2, 2);
+  double j12 = -(M3(m, 1, 2) * M3(m, 3, 3)) + M3(m, 3, 2) * M3(m, 1, 3);
+  double j22 = M3(m, 1, 1) * M3(m, 3, 3) - M3(m, 3, 1) * M3(m, 1, 3);
+  double j32 = -(M3(m, 1, 1) * M3(m, 3, 2)) + M3(m, 3, 1) * M3(m, 1, 2);
+  double j13 = M3(m, 1, 2) * M3(m, 2, 3) - M3(m, 2, 2) * M3(m, 1, 3);
+  double j23 = -(M3(m, 1, 1) * M3(m, 2, 3)) + M3(m, 2, 1) * M3(m, 1, 3);
+  double j33 = M3(m, 1, 1) * M3(m, 2, 2) - M3(m, 2, 1) * M3(m, 1, 2);
+  M3(m, 1, 1) = j11 / det; M3(m, 1, 2) = j12 / det; M3(m, 1, 3) = j13 / det;
+  M3(m, 2, 1) = j21 / det; M3(m, 2, 2) = j22 / det; M3(m, 2, 3) = j23 / det;
+  M3(m, 3, 1) = j31 / det; M3(m, 3, 2) = j32 / det; M3(m, 3, 3) = j33 / det;
+}
+
+/* deemat, nst = 6 branch, new_library.f90:1671-1686; dee(6,6) col-major */
+void orc_deemat6(double *dee, double e, double v) {
+  const double v2 = v / (1.0 - v);
+  const double vv = (1.0 - 2.0 * v) / (1.0 - v) * 0.5;
+  memset(dee, 0, 36 * sizeof(double));
+  for (int i = 0; i < 3; ++i) dee[i * 6 + i] = 1.0;
+  for (int i = 3; i < 6; ++i) dee[i * 6 + i] = vv;
+  dee[1 * 6 + 0] = v2; dee[0 * 6 + 1] = v2; dee[2 * 6 + 0] = v2;
+  dee[0 * 6 + 2] = v2; dee[2 * 6 + 1] = v2; dee[1 * 6 + 2] = v2;
+  const double den = 2.0 * (1.0 + v) * vv;
+  for (int i = 0; i < 36; ++i) dee[i] = dee[i] * e / den;
+}
+
+/* beemat, nst = 6 branch, new_library.f90:976-993; bee(6,3*nod) col-major */
+void orc_beemat6(double *bee, const double *deriv, int nod) {
+  memset(bee, 0, (size_t)6 * 3 * nod * sizeof(double));
+#define BEE(r, c) bee[((c)-1) * 6 + ((r)-1)]
+  for (int m = 1; m <= nod; ++m) {
+    const int n = 3 * m, k = n - 1, l = k - 1;
+    const double x = deriv[(m - 1) * 3 + 0], y = deriv[(m - 1) * 3 + 1], z = deriv[(m - 1) * 3 + 2];
+    BEE(1, l) = x; BEE(4, k) = x; BEE(6, n) = x;
+    BEE(2, k) = y; BEE(4, l) = y; BEE(5, n) = y;
+    BEE(3, n) = z; BEE(5, k) = z; BEE(6, l) = z;
+  }
+#undef BEE
+}
+
+/* Cartesian derivatives at one Gauss point: shape_der, jac = der*coord,
+ * det, invert, deriv = jac^-1 * der  (p121.f90:58-59).  coord(nod,3). */
+static double gauss_point(int nod, const double *points, int nip, int ig, const double *coord,
+                          double *der, double *deriv) {
+  double jac[9];
+  orc_shape_der(nod, points, nip, ig, der);
+  for (int b = 0; b < 3; ++b)
+    for (int a = 0; a < 3; ++a) {
+      double s = 0.0;
+      for (int m = 0; m < nod; ++m) s += der[m * 3 + a] * coord[b * nod + m];
+      jac[b * 3 + a] = s;
+    }
+  double det = orc_determinant3(jac);
+  orc_invert3(jac);
+  for (int m = 0; m < nod; ++m)
+    for (int a = 0; a < 3; ++a) {
+      double s = 0.0;
+      for (int b = 0; b < 3; ++b) s += jac[b * 3 + a] * der[m * 3 + b];
+      deriv[m * 3 + a] = s;
+    }
+  return det;
+}
+
+/* elements_1 / gauss_pts_1 of p121.f90:54-64.
+ * g_coord_pp(nod,3,nels), storkm_pp(ntot,ntot,nels), ntot = 3*nod. */
+int orc_form_km_elastic(int64_t nels, int nod, int nip, const double *g_coord_pp, double e,
+                        double v, double *storkm_pp) {
+  if ((nod != 8 && nod != 20) || (nip != 1 && nip != 8)) return 1;
+  const int ntot = 3 * nod;
+  double points[24], weights[8], dee[36];
+  orc_sample_hex(nip, points, weights);
+  orc_deemat6(dee, e, v);
+#pragma omp parallel
+  {
+    double der[60], deriv[60];
+    double *bee = malloc(sizeof(double) * 6 * ntot);
+    double *btd = malloc(sizeof(double) * ntot * 6);
+#pragma omp for schedule(static)
+    for (int64_t iel = 0; iel < nels; ++iel) {
+      double *km = storkm_pp + iel * ntot * ntot;
+      memset(km, 0, sizeof(double) * ntot * ntot);
+      for (int ig = 0; ig < nip; ++ig) {
+        const double det = gauss_point(nod, points, nip, ig, g_coord_pp + iel * nod * 3, der, deriv);
+        orc_beemat6(bee, deriv, nod);
+        /* btd = MATMUL(TRANSPOSE(bee),dee): (ntot,6) col-major */
+        for (int k = 0; k < 6; ++k)
+          for (int i = 0; i < ntot; ++i) {
+            double s = 0.0;
+            for (int l = 0; l < 6; ++l) s += bee[i * 6 + l] * dee[k * 6 + l];
+            btd[k * ntot + i] = s;
+          }
+        /* km += MATMUL(btd,bee)*det*weights(ig) */
+        for (int j = 0; j < ntot; ++j)
+          for (int i = 0; i < ntot; ++i) {
+            double s = 0.0;
+            for (int k = 0; k < 6; ++k) s += btd[k * ntot + i] * bee[j * 6 + k];
+            km[j * ntot + i] = km[j * ntot + i] + s * det * weights[ig];
+          }
+      }
+    }
+    free(bee); free(btd);
+  }
+  return 0;
+}
+
+/* elements_1 of p123.f90:70-84: kcx,kcy,kcz outer products; storkc_pp(8,8,nels) */
+int orc_form_kc_laplace(int64_t nels, int nod, int nip, const double *g_coord_pp, double kx,
+                        double ky, double kz, double *storkc_pp) {
+  if (nod != 8 || (nip != 1 && nip != 8)) return 1;
+  double points[24], weights[8];
+  orc_sample_hex(nip, points, weights);
+#pragma omp parallel for schedule(static)
+  for (int64_t iel = 0; iel < nels; ++iel) {
+    double der[24], deriv[24], kc[3][64];
+    memset(kc, 0, sizeof kc);
+    for (int ig = 0; ig < nip; ++ig) {
+      const double det = gauss_point(nod, points, nip, ig, g_coord_pp + iel * nod * 3, der, deriv);
+      for (int a = 0; a < 3; ++a)
+        for (int j = 0; j < 8; ++j)
+          for (int i = 0; i < 8; ++i)
+            kc[a][j * 8 + i] = kc[a][j * 8 + i] + deriv[i * 3 + a] * deriv[j * 3 + a] * det * weights[ig];
+    }
+    double *out = storkc_pp + iel * 64;
+    for (int q = 0; q < 64; ++q) out[q] = kc[0][q] * kx + kc[1][q] * ky + kc[2][q] * kz;
+  }
+  return 0;
+}
+
+/* centroid stresses, p121.f90:113-123: one point at (0,0,0); sigma = dee*(bee*eld) */
+int orc_centroid_stress(int nod, const double *coord, const double *eld, double e, double v,
+                        double *sigma) {
+  if (nod != 8 && nod != 20) return 1;
+  const int ntot = 3 * nod;
+  double points[3] = {0, 0, 0}, der[60], deriv[60], dee[36], eps[6];
+  double *bee = malloc(sizeof(double) * 6 * ntot);
+  gauss_point(nod, points, 1, 0, coord, der, deriv);
+  orc_beemat6(bee, deriv, nod);
+  orc_deemat6(dee, e, v);
+  for (int r = 0; r < 6; ++r) {
+    double s = 0.0;
+    for (int c = 0; c < ntot; ++c) s += bee[c * 6 + r] * eld[c];
+    eps[r] = s;
+  }
+  for (int r = 0; r < 6; ++r) {
+    double s = 0.0;
+    for (int c = 0; c < 6; ++c) s += dee[c * 6 + r] * eps[c];
+    sigma[r] = s;
+  }
+  free(bee);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* steering: rearrange + find_g3, rearrange_2 + find_g4                       */
+/* ------------------------------------------------------------------------- */
+
+/* rest(nr,nodof+1) col-major, modified in place (new_library.f90:3059-3112) */
+void orc_rearrange(int64_t nr, int nodof, int32_t *rest) {
+#define REST(i, k) rest[(int64_t)((k)-1) * nr + ((i)-1)]
+  int32_t m = 0;
+  for (int64_t i = 1; i <= nr; ++i)
+    for (int k = 2; k <= nodof + 1; ++k)
+      if (REST(i, k) != 0) { m = m + 1; REST(i, k) = m; }
+  for (int64_t i = 1; i <= nr; ++i) {
+    int64_t k = REST(i, 1);
+    for (int c = 2; c <= nodof + 1; ++c)
+      if (REST(i, c) != 0) REST(i, c) = (int32_t)(REST(i, c) + nodof * (k - i));
+  }
+}
+
+static int64_t rest_bsearch(int64_t nr, const int32_t *rest, int64_t l) {
+  int64_t first = 1, last = nr;
+  while (first != last) {
+    int64_t half = (first + last) / 2;
+    if (l <= REST(half, 1)) last = half; else first = half + 1;
+  }
+  return first;
+}
+
+/* find_g3 (new_library.f90:3130-3212) for one element; rest already rearranged */
+void orc_find_g3(int nod, int nodof, const int32_t *num, int32_t *g, int64_t nr, const int32_t *rest) {
+  for (int i = 1; i <= nod; ++i) {
+    const int64_t l = num[i - 1];
+    const int64_t only = rest_bsearch(nr, rest, l);
+    if (l == REST(only, 1)) {
+      for (int j = 1; j <= nodof; ++j) g[nodof * i - nodof + j - 1] = REST(only, j + 1);
+    } else {
+      int64_t k = (only == nr) ? 0 : 1, s1;
+      for (;;) {
+        s1 = only - k;
+        int64_t sum = 0;
+        for (int c = 2; c <= nodof + 1; ++c) sum += REST(s1, c);
+        if (sum != 0 || s1 == 1) break;
+        k = k + 1;
+      }
+      int64_t s2 = REST(s1, 2);
+      for (int c = 3; c <= nodof + 1; ++c) if (REST(s1, c) > s2) s2 = REST(s1, c);
+      int64_t s3 = (only == nr) ? l - REST(s1, 1) - k : l - REST(s1, 1) - (k - 1);
+      for (int j = 1; j <= nodof; ++j) g[nodof * i - nodof + j - 1] = (int32_t)(s2 + nodof * s3 - (nodof - j));
+    }
+  }
+}
+
+/* rearrange_2 (new_library.f90:3118-3124); rest(nr,2) */
+void orc_rearrange_2(int64_t nr, int32_t *rest) {
+  int64_t m = 0;
+  for (int64_t i = 1; i <= nr; ++i) REST(i, 2) = (int32_t)(REST(i, 1) - i);
+  for (int64_t i = 1; i <= nr; ++i) if (REST(i, 2) != 0) { m = i - 1; break; }
+  for (int64_t i = (m < 1 ? 1 : m); i <= nr; ++i) REST(i, 2) = REST(i, 2) + 1;
+}
+
+/* find_g4 (new_library.f90:3249-3271) for one element */
+void orc_find_g4(int nod, const int32_t *num, int32_t *g, int64_t nr, const int32_t *rest) {
+  for (int i = 1; i <= nod; ++i) {
+    const int64_t l = num[i - 1];
+    const int64_t only = rest_bsearch(nr, rest, l);
+    if (l == REST(only, 1)) g[i - 1] = 0;
+    else {
+      int64_t s1 = only - 1;
+      g[i - 1] = (int32_t)(REST(s1, 2) + (l - REST(s1, 1)) - 1);
+    }
+  }
+}
+#undef REST
+
+/* ------------------------------------------------------------------------- */
+/* partition (calc_nels_pp / calc_neq_pp, gather_scatter.f90:217-238,319-339) */
+/* ------------------------------------------------------------------------- */
+void orc_partition(int64_t n, int npes, int numpe /*1-based*/, int64_t *cnt, int64_t *start /*1-based*/) {
+  if (npes == 1) { *cnt = n; *start = 1; return; }
+  int64_t pp2 = n / npes, num1 = n - pp2 * npes, pp1 = num1 == 0 ? pp2 : pp2 + 1;
+  if (numpe <= num1 || num1 == 0) { *cnt = pp1; *start = (int64_t)(numpe - 1) * pp1 + 1; }
+  else { *cnt = pp2; *start = num1 * pp1 + (numpe - num1 - 1) * (pp1 - 1) + 1; }
+}
+
+/* ------------------------------------------------------------------------- */
+/* per-iteration kernels                                                      */
+/* ------------------------------------------------------------------------- */
+
+/* gather: pmul(:,e) = p(g(:,e)), restrained (0) -> 0  (gather_scatter.f90:663-665) */
+void orc_gather(int ntot, int64_t nels, const int32_t *g_g, const double *p /*1-based eq -> p[eq-1]*/,
+                double *pmul) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < nels * ntot; ++i) pmul[i] = g_g[i] > 0 ? p[g_g[i] - 1] : 0.0;
+}
+
+/* elements_3: utemp(:,e) = MATMUL(km(:,:,e), pmul(:,e))  (p121.f90:93-97) */
+void orc_matvec(int ntot, int64_t nels, const double *storkm, const double *pmul, double *utemp) {
+#pragma omp parallel for schedule(static)
+  for (int64_t e = 0; e < nels; ++e) {
+    const double *km = storkm + e * ntot * ntot, *pm = pmul + e * ntot;
+    double *ut = utemp + e * ntot;
+    for (int i = 0; i < ntot; ++i) ut[i] = 0.0;
+    for (int j = 0; j < ntot; ++j) {
+      const double pj = pm[j];
+      for (int i = 0; i < ntot; ++i) ut[i] = ut[i] + km[j * ntot + i] * pj;
+    }
+  }
+}
+
+typedef struct {
+  int npes;
+  int64_t *el0, *el1;   /* element range [el0,el1) per rank (0-based) */
+  int64_t *eq0, *eq1;   /* owned equation range [eq0,eq1) per rank (0-based eq index) */
+  int64_t *lo, *hi;     /* bounding range of equations touched by the rank's elements */
+  double **ul;          /* per-rank partial-sum buffers over [lo,hi) */
+} orc_ranks;
+
+static orc_ranks *ranks_new(int npes, int ntot, int64_t nels, const int32_t *g_g, int64_t neq) {
+  orc_ranks *R = calloc(1, sizeof *R);
+  R->npes = npes;
+  R->el0 = malloc(sizeof(int64_t) * npes); R->el1 = malloc(sizeof(int64_t) * npes);
+  R->eq0 = malloc(sizeof(int64_t) * npes); R->eq1 = malloc(sizeof(int64_t) * npes);
+  R->lo = malloc(sizeof(int64_t) * npes);  R->hi = malloc(sizeof(int64_t) * npes);
+  R->ul = calloc(npes, sizeof(double *));
+  for (int r = 0; r < npes; ++r) {
+    int64_t c, s;
+    orc_partition(nels, npes, r + 1, &c, &s); R->el0[r] = s - 1; R->el1[r] = s - 1 + c;
+    orc_partition(neq, npes, r + 1, &c, &s);  R->eq0[r] = s - 1; R->eq1[r] = s - 1 + c;
+    int64_t lo = neq, hi = 0;
+    for (int64_t i = R->el0[r] * ntot; i < R->el1[r] * ntot; ++i)
+      if (g_g[i] > 0) { if (g_g[i] - 1 < lo) lo = g_g[i] - 1; if (g_g[i] > hi) hi = g_g[i]; }
+    if (hi < lo) { lo = 0; hi = 0; }
+    R->lo[r] = lo; R->hi[r] = hi;
+    R->ul[r] = malloc(sizeof(double) * (size_t)(hi - lo + 1));
+  }
+  return R;
+}
+
+static void ranks_free(orc_ranks *R) {
+  for (int r = 0; r < R->npes; ++r) free(R->ul[r]);
+  free(R->ul); free(R->el0); free(R->el1); free(R->eq0); free(R->eq1); free(R->lo); free(R->hi); free(R);
+}
+
+/* scatter(u,utemp) over emulated ranks, u zeroed first (p121.f90:91) */
+static void ranks_scatter(orc_ranks *R, int ntot, const int32_t *g_g, const double *utemp, double *u) {
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int r = 0; r < R->npes; ++r) {
+    double *ul = R->ul[r];
+    const int64_t lo = R->lo[r];
+    memset(ul, 0, sizeof(double) * (size_t)(R->hi[r] - lo));
+    for (int64_t i = R->el0[r] * ntot; i < R->el1[r] * ntot; ++i)
+      if (g_g[i] > 0) ul[g_g[i] - 1 - lo] = ul[g_g[i] - 1 - lo] + utemp[i];
+  }
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int o = 0; o < R->npes; ++o) {
+    for (int64_t q = R->eq0[o]; q < R->eq1[o]; ++q)
+      u[q] = (q >= R->lo[o] && q < R->hi[o]) ? 0.0 + R->ul[o][q - R->lo[o]] : 0.0;
+    for (int r = 0; r < R->npes; ++r) {
+      if (r == o) continue;
+      int64_t a = R->lo[r] > R->eq0[o] ? R->lo[r] : R->eq0[o];
+      int64_t b = R->hi[r] < R->eq1[o] ? R->hi[r] : R->eq1[o];
+      for (int64_t q = a; q < b; ++q) u[q] = u[q] + R->ul[r][q - R->lo[r]];
+    }
+  }
+}
+
+/* public single-call scatter for kernel-level parity tests */
+int orc_scatter(int ntot, int64_t nels, const int32_t *g_g, int64_t neq, int npes, const double *utemp,
+                double *u) {
+  orc_ranks *R = ranks_new(npes, ntot, nels, g_g, neq);
+  ranks_scatter(R, ntot, g_g, utemp, u);
+  ranks_free(R);
+  return 0;
+}
+
+/*
+ * The fixed blocked reduction tree (red_mode 1).  For a local vector of n
+ * entries:
+ *   chunk c   = entries [2048c, 2048c+2048)
+ *   lane sum  : thread t (0..255) adds, in this order, the products at
+ *               2048c + 512k + 2t and 2048c + 512k + 2t + 1 for k = 0..3,
+ *               skipping indices >= n, starting from 0.0
+ *   warp tree : for off = 16,8,4,2,1: v[i] = v[i] + v[i ^ off] within each
+ *               group of 32 lanes
+ *   block sum : s = w0; s = s + w1; ... + w7 over the 8 warps
+ *   final     : thread t adds the chunk sums t, t+256, t+512, ... in order
+ *               from 0.0, then the same warp tree and block sum
+ * This is exactly what parafem_b200/csrc/kernels.cu's reductions compute.
+ */
+static double block_tree(double *v /*256*/) {
+  for (int off = 16; off >= 1; off >>= 1) {
+    double t[256];
+    for (int i = 0; i < 256; ++i) t[i] = v[i] + v[i ^ off];
+    memcpy(v, t, sizeof t);
+  }
+  double s = v[0];
+  for (int w = 1; w < 8; ++w) s = s + v[32 * w];
+  return s;
+}
+
+double orc_dot_blocked(const double *a, const double *b, int64_t n) {
+  const int64_t nchunks = (n + 2047) / 2048;
+  double *part = malloc(sizeof(double) * (size_t)(nchunks > 0 ? nchunks : 1));
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < nchunks; ++c) {
+    double v[256];
+    for (int t = 0; t < 256; ++t) {
+      double acc = 0.0;
+      for (int k = 0; k < 4; ++k)
+        for (int h = 0; h < 2; ++h) {
+          int64_t i = 2048 * c + 512 * k + 2 * t + h;
+          if (i < n) acc = acc + a[i] * b[i];
+        }
+      v[t] = acc;
+    }
+    part[c] = block_tree(v);
+  }
+  double v[256];
+  for (int t = 0; t < 256; ++t) {
+    double acc = 0.0;
+    for (int64_t c = t; c < nchunks; c += 256) acc = acc + part[c];
+    v[t] = acc;
+  }
+  free(part);
+  return block_tree(v);
+}
+
+static double dot_seq(const double *a, const double *b, int64_t n) {
+  double s = 0.0;
+  for (int64_t i = 0; i < n; ++i) s = s + a[i] * b[i];
+  return s;
+}
+
+/* dot_product_p over emulated ranks: local dot, then ranks ascending */
+double orc_dot_ranks(const double *a, const double *b, int64_t neq, int npes, int red_mode) {
+  double s = 0.0;
+  for (int r = 0; r < npes; ++r) {
+    int64_t c, st;
+    orc_partition(neq, npes, r + 1, &c, &st);
+    double part = red_mode ? orc_dot_blocked(a + st - 1, b + st - 1, c) : dot_seq(a + st - 1, b + st - 1, c);
+    s = (r == 0) ? part : s + part;
+  }
+  return s;
+}
+
+/* ------------------------------------------------------------------------- */
+/* the solver: p121.f90:65-69,86-104 / p123.f90:86-92,120-151                 */
+/* ------------------------------------------------------------------------- */
+/*
+ * storkm(ntot,ntot,nels), g_g(ntot,nels) global; r(neq) the starting residual
+ * (loads); fixed equations (p123): no_f[nfixed] global 1-based, val_f values,
+ * penalty; npes emulated ranks (also the OpenMP width of the element loops).
+ * Outputs: x(neq), *iters, *converged, ratio[limit] (may be NULL),
+ * diag_out(neq) (may be NULL) = inverted preconditioner.
+ * Returns seconds spent in the iteration loop (the reference's timest(3)
+ * window, p121.f90:89,107-108) through *solve_seconds.
+ */
+int orc_pcg(int ntot, int64_t nels, const int32_t *g_g, const double *storkm, int64_t neq,
+            const double *r_in, int64_t nfixed, const int32_t *no_f, const double *val_f,
+            double penalty, int npes, int red_mode, double tol, int limit, double *x_out,
+            int *iters_out, int *converged_out, double *ratio, double *diag_out,
+            double *solve_seconds) {
+  orc_ranks *R = ranks_new(npes, ntot, nels, g_g, neq);
+  double *pmul = malloc(sizeof(double) * (size_t)(nels * ntot));
+  double *utemp = malloc(sizeof(double) * (size_t)(nels * ntot));
+  double *diag = calloc((size_t)neq, sizeof(double)), *p = calloc((size_t)neq, sizeof(double));
+  double *r = malloc(sizeof(double) * (size_t)neq), *x = calloc((size_t)neq, sizeof(double));
+  double *xnew = calloc((size_t)neq, sizeof(double)), *u = calloc((size_t)neq, sizeof(double));
+  double *d = calloc((size_t)neq, sizeof(double));
+  double *store = nfixed > 0 ? malloc(sizeof(double) * (size_t)nfixed) : NULL;
+  memcpy(r, r_in, sizeof(double) * (size_t)neq);
+
+  /* diag_precon_tmp(i,iel) = storkm(i,i,iel); scatter (p121.f90:65-69) */
+#pragma omp parallel for schedule(static)
+  for (int64_t e = 0; e < nels; ++e)
+    for (int i = 0; i < ntot; ++i) utemp[e * ntot + i] = storkm[e * ntot * ntot + i * ntot + i];
+  ranks_scatter(R, ntot, g_g, utemp, diag);
+  for (int64_t i = 0; i < nfixed; ++i) {      /* p123.f90:120-125 */
+    int64_t j = no_f[i] - 1;
+    diag[j] = diag[j] + penalty; store[i] = diag[j];
+  }
+  for (int64_t i = 0; i < neq; ++i) diag[i] = 1.0 / diag[i];
+  for (int64_t i = 0; i < nfixed; ++i) r[no_f[i] - 1] = store[i] * val_f[i];   /* p123.f90:127-131 */
+  for (int64_t i = 0; i < neq; ++i) { d[i] = diag[i] * r[i]; p[i] = d[i]; }
+  if (diag_out) memcpy(diag_out, diag, sizeof(double) * (size_t)neq);
+
+  int iters = 0, converged = 0;
+  double t0 = 0.0;
+#ifdef _OPENMP
+  t0 = omp_get_wtime();
+#endif
+  for (;;) {
+    iters = iters + 1;
+    orc_gather(ntot, nels, g_g, p, pmul);
+    orc_matvec(ntot, nels, storkm, pmul, utemp);
+    ranks_scatter(R, ntot, g_g, utemp, u);
+    for (int64_t i = 0; i < nfixed; ++i) u[no_f[i] - 1] = p[no_f[i] - 1] * store[i];  /* p123.f90:141-145 */
+    const double up = orc_dot_ranks(r, d, neq, npes, red_mode);
+    const double alpha = up / orc_dot_ranks(p, u, neq, npes, red_mode);
+    double maxloads = 0.0, maxdiff = 0.0;
+#pragma omp parallel for schedule(static) reduction(max : maxloads, maxdiff)
+    for (int64_t i = 0; i < neq; ++i) {
+      xnew[i] = x[i] + p[i] * alpha;
+      r[i] = r[i] - u[i] * alpha;
+      d[i] = diag[i] * r[i];
+      const double al = fabs(xnew[i]), ad = fabs(xnew[i] - x[i]);
+      if (al > maxloads) maxloads = al;
+      if (ad > maxdiff) maxdiff = ad;
+    }
+    const double beta = orc_dot_ranks(r, d, neq, npes, red_mode) / up;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < neq; ++i) { p[i] = d[i] + p[i] * beta; x[i] = xnew[i]; }
+    /* checon_par, maths.f90:1052-1061 */
+    const double rat = maxdiff / maxloads;
+    if (ratio) ratio[iters - 1] = rat;
+    converged = rat <= tol;
+    if (converged || iters == limit) break;
+  }
+#ifdef _OPENMP
+  if (solve_seconds) *solve_seconds = omp_get_wtime() - t0;
+#else
+  if (solve_seconds) *solve_seconds = 0.0;
+#endif
+  memcpy(x_out, xnew, sizeof(double) * (size_t)neq);
+  *iters_out = iters; *converged_out = converged;
+  free(pmul); free(utemp); free(diag); free(p); free(r); free(x); free(xnew); free(u); free(d); free(store);
+  ranks_free(R);
+  return 0;
+}
+
+int orc_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}

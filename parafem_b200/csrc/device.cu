@@ -1,0 +1,937 @@
+// device.cu -- section A of include/parafem_b200.h: the device side of the
+// p121 / p123 EBE-PCG path (context, setup, solver loop, halo exchange, C-ABI).
+// Kernels live in kernels.cuh.  Built for sm_100a only; there is no CPU path:
+// every entry point returns an error when no CUDA device is usable.
+#include "kernels.cuh"
+#include "parafem_b200.h"
+
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+using namespace pf;
+
+namespace {
+
+std::string g_last_error;
+
+// ---- NCCL through dlopen: the library stays loadable on a CPU-only box and picks
+// up whichever libnccl.so.2 the process already has (torch's bundled one under
+// torchrun, the system one for the C++ driver) ----
+struct Nccl {
+  void *so = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string &err) {
+    if (so) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) { so = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (so) break; }
+    if (!so) { err = std::string("dlopen libnccl.so.2 failed: ") + dlerror(); return false; }
+#define L(name) name = reinterpret_cast<decltype(name)>(dlsym(so, "nccl" #name)); if (!name) { err = "missing nccl" #name; return false; }
+    L(GetUniqueId) L(CommInitRank) L(CommDestroy) L(GroupStart) L(GroupEnd) L(Send) L(Recv) L(AllGather) L(GetErrorString)
+#undef L
+    return true;
+  }
+} g_nccl;
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr; size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    release(); n = count;
+    return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+enum { K_MATVEC = 0, K_SCATTER = 1, K_VECTOR = 2, K_HALO = 3, K_NKINDS = 4 };
+
+}  // namespace
+
+struct pf_ctx {
+  int rank = 0, nranks = 1, device = 0, sm_count = 0;
+  cudaStream_t stream = nullptr;
+  ncclComm_t comm = nullptr;
+  std::string err;
+  int64_t launches = 0;
+
+  // mesh
+  int nod = 0, nodof = 0, nip = 0, ntot = 0;
+  int64_t nels = 0, neq = 0, ieq_start = 0, neq_pp = 0, nhalo = 0, nslots = 0;
+  bool have_mesh = false, have_km = false, have_precon = false, matrix_free = false;
+  DevBuf<double> coord, km, utemp;
+  DevBuf<int> ggl;
+  DevBuf<unsigned int> csr_ptr, csr_pos;
+
+  // halo tables (sizes per peer rank)
+  std::vector<int64_t> get_cnt, get_off, put_cnt, put_off;
+  int64_t nput = 0;
+  DevBuf<int> put_slot;                 // owned slots wanted by peers, grouped by peer
+  DevBuf<double> sendbuf, recvbuf;      // nput each
+  int nacc = 0;
+  DevBuf<int> acc_slot;
+  DevBuf<unsigned int> acc_ptr, acc_pos;
+
+  // vectors (p_ext/u_ext/diag_ext are slot-indexed: [0] dump, 1..neq_pp owned, then halo)
+  DevBuf<double> p_ext, u_ext, diag_ext, r, x, d, part, gath;
+  DevBuf<State> state;
+  DevBuf<double> ratio_hist;
+  int ratio_cap = 0, last_iters = 0;
+
+  // p123 fixed freedoms
+  int nfixed = 0;
+  DevBuf<int> fix_slot;
+  DevBuf<double> store;
+
+  // profiling
+  bool profile = false;
+  struct Span { cudaEvent_t a, b; int kind; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> pool;
+  double kind_ms[K_NKINDS] = {0, 0, 0, 0};
+  int64_t kind_n[K_NKINDS] = {0, 0, 0, 0};
+};
+
+namespace {
+
+int fail(pf_handle h, int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  g_last_error = buf;
+  if (h) h->err = buf;
+  return code;
+}
+
+#define CU(call)                                                                           \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) return fail(h, 10, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define NC(call)                                                                           \
+  do {                                                                                     \
+    ncclResult_t r_ = (call);                                                              \
+    if (r_ != ncclSuccess) return fail(h, 11, "%s: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
+  } while (0)
+#define NEED(cond, msg) do { if (!(cond)) return fail(h, 2, "%s: %s", __func__, msg); } while (0)
+
+// ---- profiling spans: CUDA events on the solver stream around a group of launches ----
+struct Scope {
+  pf_handle h; int kind; cudaEvent_t a = nullptr, b = nullptr;
+  Scope(pf_handle h_, int kind_) : h(h_), kind(kind_) {
+    if (!h->profile) return;
+    auto get = [&]() { cudaEvent_t e; if (h->pool.empty()) cudaEventCreate(&e); else { e = h->pool.back(); h->pool.pop_back(); } return e; };
+    a = get(); b = get();
+    cudaEventRecord(a, h->stream);
+  }
+  ~Scope() {
+    if (!h->profile) return;
+    cudaEventRecord(b, h->stream);
+    h->spans.push_back({a, b, kind});
+  }
+};
+
+void collect_spans(pf_handle h) {
+  for (auto &s : h->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) { h->kind_ms[s.kind] += ms; h->kind_n[s.kind] += 1; }
+    h->pool.push_back(s.a); h->pool.push_back(s.b);
+  }
+  h->spans.clear();
+}
+
+int grid_for(pf_handle h, int64_t n, int threads, int per_sm = 8) {
+  int64_t blocks = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)h->sm_count * per_sm;
+  return (int)std::max<int64_t>(1, std::min(blocks, cap));
+}
+
+// ---- host restatement of the element tables (product code; the oracle has its own) ----
+// sample('hexahedron') new_library.f90:1397-1433; shape_der :745-794, :865-896; deemat :1671-1686
+int fill_tables(int nod, int nip, double e, double v, double kx, double ky, double kz, ElemTables &T) {
+  memset(&T, 0, sizeof T);
+  double pts[8][3];
+  if (nip == 1) { pts[0][0] = pts[0][1] = pts[0][2] = 0.0; T.weights[0] = 8.0; }
+  else if (nip == 8) {
+    const double r3 = 1.0 / std::sqrt(3.0);
+    for (int i = 0; i < 8; ++i) {
+      pts[i][0] = (i < 4) ? r3 : -r3;
+      pts[i][1] = (i == 0 || i == 1 || i == 4 || i == 6) ? r3 : -r3;
+      pts[i][2] = (i == 0 || i == 2 || i == 4 || i == 5) ? r3 : -r3;
+      T.weights[i] = 1.0;
+    }
+  } else return 1;
+  T.nip = nip;
+  for (int ig = 0; ig < nip; ++ig) {
+    const double xi = pts[ig][0], eta = pts[ig][1], zeta = pts[ig][2];
+    double *D = T.der + ig * 60;  // D[a*20+m]
+    if (nod == 8) {
+      const double em = 1.0 - eta, xm = 1.0 - xi, zm = 1.0 - zeta, ep = eta + 1.0, xp = xi + 1.0, zp = zeta + 1.0;
+      const double dx[8] = {-0.125 * em * zm, -0.125 * em * zp, 0.125 * em * zp, 0.125 * em * zm,
+                            -0.125 * ep * zm, -0.125 * ep * zp, 0.125 * ep * zp, 0.125 * ep * zm};
+      const double dy[8] = {-0.125 * xm * zm, -0.125 * xm * zp, -0.125 * xp * zp, -0.125 * xp * zm,
+                            0.125 * xm * zm, 0.125 * xm * zp, 0.125 * xp * zp, 0.125 * xp * zm};
+      const double dz[8] = {-0.125 * xm * em, 0.125 * xm * em, 0.125 * xp * em, -0.125 * xp * em,
+                            -0.125 * xm * ep, 0.125 * xm * ep, 0.125 * xp * ep, -0.125 * xp * ep};
+      for (int m = 0; m < 8; ++m) { D[m] = dx[m]; D[20 + m] = dy[m]; D[40 + m] = dz[m]; }
+    } else if (nod == 20) {
+      // corner / mid-edge classes of the 20-node brick in S&G order
+      const int sx[20] = {-1, -1, -1, 0, 1, 1, 1, 0, -1, -1, 1, 1, -1, -1, -1, 0, 1, 1, 1, 0};
+      const int sy[20] = {-1, -1, -1, -1, -1, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1};
+      const int sz[20] = {-1, 0, 1, 1, 1, 0, -1, -1, -1, 1, 1, -1, -1, 0, 1, 1, 1, 0, -1, -1};
+      for (int m = 0; m < 20; ++m) {
+        const double a = sx[m], b = sy[m], c = sz[m];
+        const double x0 = xi * a, e0 = eta * b, z0 = zeta * c;
+        double gx, gy, gz;
+        if (sx[m] == 0) {         // mid-edge along xi
+          gx = -.5 * xi * (1. + e0) * (1. + z0);
+          gy = .25 * b * (1. - xi * xi) * (1. + z0);
+          gz = .25 * c * (1. - xi * xi) * (1. + e0);
+        } else if (sy[m] == 0) {  // mid-edge along eta
+          gx = .25 * a * (1. - eta * eta) * (1. + z0);
+          gy = -.5 * eta * (1. + x0) * (1. + z0);
+          gz = .25 * c * (1. + x0) * (1. - eta * eta);
+        } else if (sz[m] == 0) {  // mid-edge along zeta
+          gx = .25 * a * (1. + e0) * (1. - zeta * zeta);
+          gy = .25 * b * (1. + x0) * (1. - zeta * zeta);
+          gz = -.5 * zeta * (1. + x0) * (1. + e0);
+        } else {                  // corner
+          gx = .125 * a * (1. + e0) * (1. + z0) * (2. * x0 + e0 + z0 - 1.);
+          gy = .125 * b * (1. + x0) * (1. + z0) * (x0 + 2. * e0 + z0 - 1.);
+          gz = .125 * c * (1. + x0) * (1. + e0) * (x0 + e0 + 2. * z0 - 1.);
+        }
+        D[m] = gx; D[20 + m] = gy; D[40 + m] = gz;
+      }
+    } else return 2;
+  }
+  // deemat, 6x6
+  const double v2 = v / (1.0 - v), vv = (1.0 - 2.0 * v) / (1.0 - v) * 0.5;
+  for (int i = 0; i < 3; ++i) T.dee[i * 6 + i] = 1.0;
+  for (int i = 3; i < 6; ++i) T.dee[i * 6 + i] = vv;
+  T.dee[1 * 6 + 0] = T.dee[0 * 6 + 1] = T.dee[2 * 6 + 0] = T.dee[0 * 6 + 2] = T.dee[2 * 6 + 1] = T.dee[1 * 6 + 2] = v2;
+  if (e != 0.0) { const double den = 2.0 * (1.0 + v) * vv; for (int i = 0; i < 36; ++i) T.dee[i] = T.dee[i] * e / den; }
+  T.kxyz[0] = kx; T.kxyz[1] = ky; T.kxyz[2] = kz;
+  return 0;
+}
+
+// ---- mat-vec dispatch ----
+template <int NTOT, int EPT, int STAGES, bool GATHER>
+int launch_matvec_t(pf_handle h, const double *pvec, const State *st) {
+  using Cfg = MatvecCfg<NTOT, EPT, STAGES>;
+  auto kern = k_matvec<NTOT, EPT, STAGES, GATHER>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+    attr_set = true;
+  }
+  const int64_t ntiles = (h->nels + EPT - 1) / EPT;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, ntiles));
+  kern<<<grid, Cfg::kThreads, Cfg::kSmem, h->stream>>>(h->km.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <bool GATHER>
+int launch_matvec(pf_handle h, const double *pvec, const State *st) {
+  Scope sc(h, K_MATVEC);
+  switch (h->ntot) {
+    case 60: return launch_matvec_t<60, 1, 7, GATHER>(h, pvec, st);
+    case 24: return launch_matvec_t<24, 8, 5, GATHER>(h, pvec, st);
+    case 8: return launch_matvec_t<8, 64, 6, GATHER>(h, pvec, st);
+  }
+  return fail(h, 3, "unsupported ntot %d (supported: 60, 24, 8)", h->ntot);
+}
+
+int launch_scatter(pf_handle h, const State *st, bool diag, double *dst) {
+  Scope sc(h, K_SCATTER);
+  const int grid = grid_for(h, h->nslots, 256, 16);
+  if (diag) k_scatter<true><<<grid, 256, 0, h->stream>>>(h->csr_ptr.p, h->csr_pos.p, h->km.p, dst, (long long)h->nslots, h->ntot, st);
+  else k_scatter<false><<<grid, 256, 0, h->stream>>>(h->csr_ptr.p, h->csr_pos.p, h->utemp.p, dst, (long long)h->nslots, h->ntot, st);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// forward halo exchange: owners send the p values their peers' elements need
+int halo_forward(pf_handle h, double *vec_ext, const State *st) {
+  if (h->nranks == 1) return 0;
+  Scope sc(h, K_HALO);
+  if (h->nput > 0) {
+    k_halo_pack<<<(int)((h->nput + 255) / 256), 256, 0, h->stream>>>(h->put_slot.p, vec_ext, h->sendbuf.p, (int)h->nput, st);
+    h->launches++;
+  }
+  NC(g_nccl.GroupStart());
+  for (int r = 0; r < h->nranks; ++r) {
+    if (r == h->rank) continue;
+    if (h->put_cnt[r] > 0) NC(g_nccl.Send(h->sendbuf.p + h->put_off[r], (size_t)h->put_cnt[r], ncclDouble, r, h->comm, h->stream));
+    if (h->get_cnt[r] > 0) NC(g_nccl.Recv(vec_ext + 1 + h->neq_pp + h->get_off[r], (size_t)h->get_cnt[r], ncclDouble, r, h->comm, h->stream));
+  }
+  NC(g_nccl.GroupEnd());
+  return 0;
+}
+
+// reverse halo exchange: partial sums of remote equations go to their owners, which add
+// them after their own partial sum, sources in ascending rank order
+int halo_reverse(pf_handle h, double *vec_ext, const State *st) {
+  if (h->nranks == 1) return 0;
+  Scope sc(h, K_HALO);
+  NC(g_nccl.GroupStart());
+  for (int r = 0; r < h->nranks; ++r) {
+    if (r == h->rank) continue;
+    if (h->get_cnt[r] > 0) NC(g_nccl.Send(vec_ext + 1 + h->neq_pp + h->get_off[r], (size_t)h->get_cnt[r], ncclDouble, r, h->comm, h->stream));
+    if (h->put_cnt[r] > 0) NC(g_nccl.Recv(h->recvbuf.p + h->put_off[r], (size_t)h->put_cnt[r], ncclDouble, r, h->comm, h->stream));
+  }
+  NC(g_nccl.GroupEnd());
+  if (h->nacc > 0) {
+    k_halo_accumulate<<<(h->nacc + 255) / 256, 256, 0, h->stream>>>(h->acc_slot.p, h->acc_ptr.p, h->acc_pos.p, h->recvbuf.p, vec_ext, h->nacc, st);
+    h->launches++;
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// all-gather of the ranks' [dot, max, max, 0] partials + fixed-order combine
+int combine_scalars(pf_handle h, int mode) {
+  if (h->nranks == 1) return 0;
+  State *st = h->state.p;
+  NC(g_nccl.AllGather(st->loc, h->gath.p, 4, ncclDouble, h->comm, h->stream));
+  k_scalars<<<1, 32, 0, h->stream>>>(st, h->gath.p, h->nranks, mode, h->ratio_hist.p);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int vec_grid(pf_handle h) {
+  const int64_t nchunks = (h->neq_pp + kChunk - 1) / kChunk;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(nchunks, (int64_t)h->sm_count * 8));
+}
+
+// u_ext = A p_ext over this rank's elements + halo exchanges (gather, mat-vec, scatter)
+int apply_operator(pf_handle h, const State *st) {
+  int rc;
+  if ((rc = halo_forward(h, h->p_ext.p, st))) return rc;
+  if ((rc = launch_matvec<true>(h, h->p_ext.p, st))) return rc;
+  if ((rc = launch_scatter(h, st, false, h->u_ext.p))) return rc;
+  if ((rc = halo_reverse(h, h->u_ext.p, st))) return rc;
+  if (h->nfixed > 0) {
+    k_fixed_u<<<(h->nfixed + 255) / 256, 256, 0, h->stream>>>(h->fix_slot.p, h->store.p, h->p_ext.p, h->u_ext.p, h->nfixed, st);
+    h->launches++;
+  }
+  return 0;
+}
+
+int one_iteration(pf_handle h) {
+  State *st = h->state.p;
+  const int single = h->nranks == 1;
+  const long long n = h->neq_pp;
+  int rc;
+  if ((rc = apply_operator(h, st))) return rc;
+  {
+    Scope sc(h, K_VECTOR);
+    k_dot<<<vec_grid(h), kRedThreads, 0, h->stream>>>(h->p_ext.p + 1, h->u_ext.p + 1, n, h->part.p, st, single, 1);
+    h->launches++;
+    if ((rc = combine_scalars(h, 1))) return rc;
+    k_pcg_update<<<vec_grid(h), kRedThreads, 0, h->stream>>>(h->diag_ext.p + 1, h->p_ext.p + 1, h->u_ext.p + 1, h->x.p, h->r.p,
+                                                              h->d.p, n, h->part.p, st, single, h->ratio_hist.p);
+    h->launches++;
+    if ((rc = combine_scalars(h, 2))) return rc;
+    k_pupdate<<<grid_for(h, (n + 1) / 2, 256, 8), 256, 0, h->stream>>>(h->d.p, h->p_ext.p + 1, n, st);
+    k_exit_test<<<1, 1, 0, h->stream>>>(st);
+    h->launches += 2;
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int need_device(pf_handle h) {
+  if (!h) return fail(nullptr, 1, "null handle");
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return fail(h, 10, "cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pf_version(void) { return 100; }
+
+int pf_last_error(pf_handle h, char *buf, int len) {
+  const std::string &s = h ? h->err : g_last_error;
+  if (buf && len > 0) { strncpy(buf, s.c_str(), (size_t)len - 1); buf[len - 1] = 0; }
+  return (int)s.size();
+}
+
+int pf_nccl_unique_id(void *id128) {
+  pf_handle h = nullptr;
+  std::string err;
+  if (!g_nccl.load(err)) return fail(h, 12, "%s", err.c_str());
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  NC(g_nccl.GetUniqueId(reinterpret_cast<ncclUniqueId *>(id128)));
+  return 0;
+}
+
+int pf_init(int rank, int nranks, int device, const void *id128, pf_handle *out) {
+  pf_handle h = nullptr;
+  if (!out || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, 2, "pf_init: bad arguments");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(h, 10, "pf_init: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(h, 2, "pf_init: device %d out of range (%d devices)", device, ndev);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(h, 13, "pf_init: device is sm_%d%d; this build targets sm_100a (B200) only", prop.major, prop.minor);
+  h = new pf_ctx();
+  h->rank = rank; h->nranks = nranks; h->device = device; h->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CU(h->state.alloc(1));
+  CU(cudaMemset(h->state.p, 0, sizeof(State)));
+  CU(h->gath.alloc((size_t)4 * nranks));
+  if (nranks > 1) {
+    std::string err;
+    if (!g_nccl.load(err)) { int rc = fail(h, 12, "%s", err.c_str()); delete h; return rc; }
+    if (!id128) { delete h; return fail(nullptr, 2, "pf_init: nranks > 1 needs the 128-byte NCCL id"); }
+    ncclUniqueId id; memcpy(&id, id128, sizeof id);
+    NC(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+  }
+  *out = h;
+  return 0;
+}
+
+int pf_finalize(pf_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  collect_spans(h);
+  for (auto e : h->pool) cudaEventDestroy(e);
+  if (h->comm) g_nccl.CommDestroy(h->comm);
+  h->coord.release(); h->km.release(); h->utemp.release(); h->ggl.release(); h->csr_ptr.release(); h->csr_pos.release();
+  h->put_slot.release(); h->sendbuf.release(); h->recvbuf.release(); h->acc_slot.release(); h->acc_ptr.release(); h->acc_pos.release();
+  h->p_ext.release(); h->u_ext.release(); h->diag_ext.release(); h->r.release(); h->x.release(); h->d.release();
+  h->part.release(); h->gath.release(); h->state.release(); h->ratio_hist.release(); h->fix_slot.release(); h->store.release();
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int pf_device_info(pf_handle h, int *sm_count, int64_t *free_bytes, int64_t *total_bytes) {
+  int rc = need_device(h); if (rc) return rc;
+  size_t f = 0, t = 0;
+  CU(cudaMemGetInfo(&f, &t));
+  if (sm_count) *sm_count = h->sm_count;
+  if (free_bytes) *free_bytes = (int64_t)f;
+  if (total_bytes) *total_bytes = (int64_t)t;
+  return 0;
+}
+
+int64_t pf_kernel_launches(pf_handle h) { return h ? h->launches : 0; }
+
+int pf_set_profile(pf_handle h, int on) { if (!h) return 1; h->profile = on != 0; return 0; }
+int pf_reset_profile(pf_handle h) {
+  if (!h) return 1;
+  cudaStreamSynchronize(h->stream);
+  collect_spans(h);
+  for (int k = 0; k < K_NKINDS; ++k) { h->kind_ms[k] = 0; h->kind_n[k] = 0; }
+  return 0;
+}
+int pf_get_kernel_ms(pf_handle h, int which, double *total_ms, int64_t *launches) {
+  if (!h || which < 0 || which >= K_NKINDS) return fail(h, 2, "pf_get_kernel_ms: bad arguments");
+  CU(cudaStreamSynchronize(h->stream));
+  collect_spans(h);
+  if (total_ms) *total_ms = h->kind_ms[which];
+  if (launches) *launches = h->kind_n[which];
+  return 0;
+}
+
+int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp, const double *g_coord_pp,
+                  const int32_t *g_g_pp, int64_t neq, int64_t ieq_start, int64_t neq_pp) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED((nod == 8 || nod == 20) && (nodof == 1 || nodof == 3), "nod must be 8 or 20, nodof 1 or 3");
+  NEED(nip == 1 || nip == 8, "nip must be 1 or 8");
+  NEED(nels_pp >= 1 && neq >= 1 && neq_pp >= 0 && ieq_start >= 1, "bad sizes");
+  const int ntot = nod * nodof;
+  NEED(ntot == 60 || ntot == 24 || ntot == 8, "supported element types: hex20/hex8 elastic, hex8 scalar");
+  NEED(nels_pp * ntot < (int64_t)0xffffffffu, "nels_pp*ntot exceeds 32-bit table range; use more ranks");
+  {
+    int64_t c, s;
+    pf_calc_neq_pp(neq, h->nranks, h->rank + 1, &c, &s);
+    NEED(c == neq_pp && s == ieq_start, "neq_pp/ieq_start do not match calc_neq_pp for this rank");
+  }
+  h->nod = nod; h->nodof = nodof; h->nip = nip; h->ntot = ntot;
+  h->nels = nels_pp; h->neq = neq; h->ieq_start = ieq_start; h->neq_pp = neq_pp;
+  h->have_km = h->have_precon = false;
+
+  // gather table (make_ggl rebuilt from g_g_pp)
+  const int64_t total = nels_pp * ntot;
+  std::vector<int32_t> ggl((size_t)total), halo;
+  std::vector<int64_t> halo_cnt((size_t)h->nranks, 0);
+  int64_t nhalo = 0;
+  if (pf_make_ggl(ntot, nels_pp, g_g_pp, neq, h->nranks, h->rank + 1, nullptr, 0, nullptr, halo_cnt.data(), &nhalo))
+    return fail(h, 4, "pf_setup_mesh: g_g_pp holds equation numbers outside [0, neq]");
+  halo.resize((size_t)std::max<int64_t>(nhalo, 1));
+  if (pf_make_ggl(ntot, nels_pp, g_g_pp, neq, h->nranks, h->rank + 1, ggl.data(), (int64_t)halo.size(), halo.data(),
+                  halo_cnt.data(), &nhalo))
+    return fail(h, 4, "pf_setup_mesh: gather table construction failed");
+  h->nhalo = nhalo;
+  h->nslots = 1 + neq_pp + nhalo;
+  NEED(h->nslots < (int64_t)0x7fffffff, "slot count exceeds int32");
+
+  // CSR of contributions per slot, ascending element order (counting sort keeps it)
+  std::vector<unsigned int> ptr((size_t)h->nslots + 1, 0), pos;
+  for (int64_t i = 0; i < total; ++i) if (ggl[i] > 0) ptr[(size_t)ggl[i] + 1]++;
+  for (int64_t s = 0; s < h->nslots; ++s) ptr[(size_t)s + 1] += ptr[(size_t)s];
+  pos.resize(std::max<size_t>(ptr[(size_t)h->nslots], 1));
+  {
+    std::vector<unsigned int> cur(ptr.begin(), ptr.end() - 1);
+    for (int64_t i = 0; i < total; ++i) if (ggl[i] > 0) pos[cur[(size_t)ggl[i]]++] = (unsigned int)i;
+  }
+
+  CU(h->coord.alloc((size_t)nels_pp * nod * 3));
+  CU(cudaMemcpy(h->coord.p, g_coord_pp, h->coord.bytes(), cudaMemcpyHostToDevice));
+  CU(h->ggl.alloc((size_t)total));
+  CU(cudaMemcpy(h->ggl.p, ggl.data(), h->ggl.bytes(), cudaMemcpyHostToDevice));
+  CU(h->csr_ptr.alloc(ptr.size()));
+  CU(cudaMemcpy(h->csr_ptr.p, ptr.data(), h->csr_ptr.bytes(), cudaMemcpyHostToDevice));
+  CU(h->csr_pos.alloc(pos.size()));
+  CU(cudaMemcpy(h->csr_pos.p, pos.data(), pos.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
+  CU(h->utemp.alloc((size_t)total));
+
+  const size_t ns = (size_t)h->nslots, nq = (size_t)std::max<int64_t>(neq_pp, 1);
+  CU(h->p_ext.alloc(ns)); CU(h->u_ext.alloc(ns)); CU(h->diag_ext.alloc(ns));
+  CU(h->r.alloc(nq)); CU(h->x.alloc(nq)); CU(h->d.alloc(nq));
+  CU(cudaMemset(h->p_ext.p, 0, ns * 8)); CU(cudaMemset(h->u_ext.p, 0, ns * 8)); CU(cudaMemset(h->diag_ext.p, 0, ns * 8));
+  CU(cudaMemset(h->x.p, 0, nq * 8));
+  const size_t nchunks = (size_t)((neq_pp + kChunk - 1) / kChunk);
+  CU(h->part.alloc(3 * std::max<size_t>(nchunks, 1)));
+
+  // halo tables: what I get from each owner is known; tell each owner what to put
+  h->get_cnt.assign((size_t)h->nranks, 0); h->get_off.assign((size_t)h->nranks, 0);
+  h->put_cnt.assign((size_t)h->nranks, 0); h->put_off.assign((size_t)h->nranks, 0);
+  h->nput = 0; h->nacc = 0;
+  if (h->nranks > 1) {
+    const int R = h->nranks;
+    int64_t off = 0;
+    for (int r = 0; r < R; ++r) { h->get_cnt[r] = halo_cnt[r]; h->get_off[r] = off; off += halo_cnt[r]; }
+    // counts matrix via all-gather (int64 as 8-byte doubles would mangle; use ncclInt64)
+    DevBuf<int64_t> d_cnt, d_all;
+    CU(d_cnt.alloc((size_t)R)); CU(d_all.alloc((size_t)R * R));
+    CU(cudaMemcpy(d_cnt.p, h->get_cnt.data(), (size_t)R * 8, cudaMemcpyHostToDevice));
+    NC(g_nccl.AllGather(d_cnt.p, d_all.p, (size_t)R, ncclInt64, h->comm, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<int64_t> all((size_t)R * R);
+    CU(cudaMemcpy(all.data(), d_all.p, all.size() * 8, cudaMemcpyDeviceToHost));
+    d_cnt.release(); d_all.release();
+    off = 0;
+    for (int r = 0; r < R; ++r) { h->put_cnt[r] = all[(size_t)r * R + h->rank]; h->put_off[r] = off; off += h->put_cnt[r]; }
+    h->nput = off;
+    NEED(h->put_cnt[h->rank] == 0, "a rank lists its own equations as remote");
+    // exchange the wanted global equation numbers
+    DevBuf<int> d_want, d_asked;
+    CU(d_want.alloc((size_t)std::max<int64_t>(nhalo, 1))); CU(d_asked.alloc((size_t)std::max<int64_t>(h->nput, 1)));
+    CU(cudaMemcpy(d_want.p, halo.data(), (size_t)nhalo * 4, cudaMemcpyHostToDevice));
+    NC(g_nccl.GroupStart());
+    for (int r = 0; r < R; ++r) {
+      if (r == h->rank) continue;
+      if (h->get_cnt[r] > 0) NC(g_nccl.Send(d_want.p + h->get_off[r], (size_t)h->get_cnt[r], ncclInt32, r, h->comm, h->stream));
+      if (h->put_cnt[r] > 0) NC(g_nccl.Recv(d_asked.p + h->put_off[r], (size_t)h->put_cnt[r], ncclInt32, r, h->comm, h->stream));
+    }
+    NC(g_nccl.GroupEnd());
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<int> asked((size_t)std::max<int64_t>(h->nput, 1));
+    CU(cudaMemcpy(asked.data(), d_asked.p, (size_t)h->nput * 4, cudaMemcpyDeviceToHost));
+    d_want.release(); d_asked.release();
+    for (int64_t k = 0; k < h->nput; ++k) {
+      const int64_t g = asked[(size_t)k];
+      NEED(g >= ieq_start && g < ieq_start + neq_pp, "peer asked for an equation this rank does not own");
+      asked[(size_t)k] = (int)(g - ieq_start + 1);  // -> slot
+    }
+    CU(h->put_slot.alloc(asked.size()));
+    CU(cudaMemcpy(h->put_slot.p, asked.data(), asked.size() * 4, cudaMemcpyHostToDevice));
+    CU(h->sendbuf.alloc(asked.size())); CU(h->recvbuf.alloc(asked.size()));
+    // accumulate table: per owned slot, receive-buffer positions in ascending source rank
+    // (recvbuf is grouped by source rank ascending, so ascending position == ascending rank)
+    std::vector<std::pair<int, unsigned int>> pairs((size_t)h->nput);
+    for (int64_t k = 0; k < h->nput; ++k) pairs[(size_t)k] = {asked[(size_t)k], (unsigned int)k};
+    std::sort(pairs.begin(), pairs.end());
+    std::vector<int> aslot; std::vector<unsigned int> aptr, apos;
+    for (size_t k = 0; k < pairs.size(); ++k) {
+      if (k == 0 || pairs[k].first != pairs[k - 1].first) { aslot.push_back(pairs[k].first); aptr.push_back((unsigned int)k); }
+      apos.push_back(pairs[k].second);
+    }
+    aptr.push_back((unsigned int)pairs.size());
+    h->nacc = (int)aslot.size();
+    CU(h->acc_slot.alloc(std::max<size_t>(aslot.size(), 1))); CU(h->acc_ptr.alloc(aptr.size())); CU(h->acc_pos.alloc(std::max<size_t>(apos.size(), 1)));
+    CU(cudaMemcpy(h->acc_slot.p, aslot.data(), aslot.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->acc_ptr.p, aptr.data(), aptr.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->acc_pos.p, apos.data(), apos.size() * 4, cudaMemcpyHostToDevice));
+  }
+  h->have_mesh = true;
+  return 0;
+}
+
+static int alloc_km(pf_handle h) {
+  if (h->km.n != (size_t)h->nels * h->ntot * h->ntot) CU(h->km.alloc((size_t)h->nels * h->ntot * h->ntot));
+  return 0;
+}
+
+int pf_form_km_elastic(pf_handle h, double e, double v) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_mesh && h->nodof == 3, "needs pf_setup_mesh with nodof = 3");
+  ElemTables T;
+  if (fill_tables(h->nod, h->nip, e, v, 0, 0, 0, T)) return fail(h, 3, "unsupported nod/nip");
+  CU(cudaMemcpyToSymbol(c_tab, &T, sizeof T));
+  if ((rc = alloc_km(h))) return rc;
+  const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 16);
+  if (h->nod == 20) k_form_km_elastic<20, 128><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels);
+  else k_form_km_elastic<8, 64><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  h->have_km = true; h->have_precon = false;
+  return 0;
+}
+
+int pf_form_kc_laplace(pf_handle h, double kx, double ky, double kz) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_mesh && h->nodof == 1 && h->nod == 8, "needs pf_setup_mesh with nod = 8, nodof = 1");
+  ElemTables T;
+  if (fill_tables(h->nod, h->nip, 0, 0, kx, ky, kz, T)) return fail(h, 3, "unsupported nod/nip");
+  CU(cudaMemcpyToSymbol(c_tab, &T, sizeof T));
+  if ((rc = alloc_km(h))) return rc;
+  const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 32);
+  k_form_kc_laplace<<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  h->have_km = true; h->have_precon = false;
+  return 0;
+}
+
+int pf_set_storkm(pf_handle h, const double *storkm_pp) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_mesh && storkm_pp, "needs pf_setup_mesh");
+  if ((rc = alloc_km(h))) return rc;
+  CU(cudaMemcpy(h->km.p, storkm_pp, h->km.bytes(), cudaMemcpyHostToDevice));
+  h->have_km = true; h->have_precon = false;
+  return 0;
+}
+
+int pf_get_storkm(pf_handle h, int64_t iel0, int64_t n, double *out) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_km && iel0 >= 0 && n >= 0 && iel0 + n <= h->nels, "range outside the local elements");
+  const size_t per = (size_t)h->ntot * h->ntot;
+  CU(cudaMemcpy(out, h->km.p + (size_t)iel0 * per, (size_t)n * per * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int pf_set_matrix_free(pf_handle h, int on) {
+  if (!h) return 1;
+  if (on) return fail(h, 5, "matrix-free variant not built yet");
+  h->matrix_free = false;
+  return 0;
+}
+
+int pf_build_precon(pf_handle h, int64_t nfixed_pp, const int32_t *no_f_pp, double penalty) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_km, "needs element matrices (pf_form_km_elastic / pf_form_kc_laplace / pf_set_storkm)");
+  NEED(nfixed_pp >= 0 && nfixed_pp < (1 << 30), "bad nfixed_pp");
+  // diag_precon_tmp(i,iel) = storkm(i,i,iel); scatter  (p121.f90:65-69)
+  if ((rc = launch_scatter(h, nullptr, true, h->diag_ext.p))) return rc;
+  if ((rc = halo_reverse(h, h->diag_ext.p, nullptr))) return rc;
+  h->nfixed = (int)nfixed_pp;
+  if (h->nfixed > 0) {
+    std::vector<int> slots((size_t)h->nfixed);
+    for (int i = 0; i < h->nfixed; ++i) {
+      const int64_t g = no_f_pp[i];
+      NEED(g >= h->ieq_start && g < h->ieq_start + h->neq_pp, "fixed equation not owned by this rank");
+      slots[(size_t)i] = (int)(g - h->ieq_start + 1);
+    }
+    CU(h->fix_slot.alloc(slots.size())); CU(h->store.alloc(slots.size()));
+    CU(cudaMemcpy(h->fix_slot.p, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice));
+    k_fixed_penalty<<<(h->nfixed + 255) / 256, 256, 0, h->stream>>>(h->fix_slot.p, h->diag_ext.p, h->store.p, penalty, h->nfixed);
+    h->launches++;
+  }
+  if (h->neq_pp > 0) {
+    k_invert<<<grid_for(h, h->neq_pp, 256), 256, 0, h->stream>>>(h->diag_ext.p + 1, (long long)h->neq_pp);
+    h->launches++;
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  h->have_precon = true;
+  return 0;
+}
+
+int pf_get_diag_precon(pf_handle h, double *out) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_precon, "needs pf_build_precon");
+  CU(cudaMemcpy(out, h->diag_ext.p + 1, (size_t)h->neq_pp * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int pf_get_store(pf_handle h, double *store_pp) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_precon, "needs pf_build_precon");
+  if (h->nfixed > 0) CU(cudaMemcpy(store_pp, h->store.p, (size_t)h->nfixed * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int pf_pcg_load_rhs(pf_handle h, const double *r_pp) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_mesh, "needs pf_setup_mesh");
+  CU(cudaMemcpyAsync(h->r.p, r_pp, (size_t)h->neq_pp * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int pf_pcg_run(pf_handle h, double tol, int limit, int *iters, int *converged, double *elapsed_ms) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_precon, "needs pf_build_precon");
+  NEED(limit >= 1, "limit must be >= 1");
+  if (h->ratio_cap < limit) { CU(h->ratio_hist.alloc((size_t)limit)); h->ratio_cap = limit; }
+  State init; memset(&init, 0, sizeof init);
+  init.tol = tol; init.limit = limit;
+  CU(cudaMemcpyAsync(h->state.p, &init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+  // d = M^-1 r, p = d, x = 0 (p121.f90:87; p123.f90:132)
+  k_pcg_init<<<vec_grid(h), kRedThreads, 0, h->stream>>>(h->diag_ext.p + 1, h->r.p, h->d.p, h->p_ext.p + 1, h->x.p,
+                                                          (long long)h->neq_pp, h->part.p, h->state.p, h->nranks == 1);
+  h->launches++;
+  if ((rc = combine_scalars(h, 0))) return rc;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, h->stream));  // timest(3), p121.f90:89
+  State snap;
+  const int batch = 8;
+  int queued = 0;
+  for (;;) {
+    const int nb = std::min(batch, limit - queued);
+    for (int k = 0; k < nb; ++k) if ((rc = one_iteration(h))) return rc;
+    queued += nb;
+    CU(cudaMemcpyAsync(&snap, h->state.p, sizeof snap, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (snap.done || queued >= limit) break;
+  }
+  CU(cudaEventRecord(e1, h->stream));
+  CU(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  collect_spans(h);
+  h->last_iters = snap.iters;
+  if (iters) *iters = snap.iters;
+  if (converged) *converged = snap.converged;
+  if (elapsed_ms) *elapsed_ms = ms;
+  return 0;
+}
+
+int pf_pcg_get_x(pf_handle h, double *xnew_pp) {
+  int rc = need_device(h); if (rc) return rc;
+  CU(cudaMemcpyAsync(xnew_pp, h->x.p, (size_t)h->neq_pp * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int pf_pcg_solve(pf_handle h, const double *r_pp, double tol, int limit, double *xnew_pp, int *iters,
+                 int *converged) {
+  int rc;
+  if ((rc = pf_pcg_load_rhs(h, r_pp))) return rc;
+  if ((rc = pf_pcg_run(h, tol, limit, iters, converged, nullptr))) return rc;
+  return pf_pcg_get_x(h, xnew_pp);
+}
+
+int pf_get_ratio_history(pf_handle h, double *out, int maxn, int *n) {
+  int rc = need_device(h); if (rc) return rc;
+  const int m = std::min(maxn, h->last_iters);
+  if (m > 0) CU(cudaMemcpy(out, h->ratio_hist.p, (size_t)m * 8, cudaMemcpyDeviceToHost));
+  if (n) *n = m;
+  return 0;
+}
+
+// ---- fine-grained entry points ----
+static int upload_owned(pf_handle h, double *ext, const double *host) {
+  CU(cudaMemcpyAsync(ext + 1, host, (size_t)h->neq_pp * 8, cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+int pf_gather(pf_handle h, const double *p_pp, double *pmul_pp) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_mesh, "needs pf_setup_mesh");
+  if ((rc = upload_owned(h, h->p_ext.p, p_pp))) return rc;
+  if ((rc = halo_forward(h, h->p_ext.p, nullptr))) return rc;
+  const int64_t n = h->nels * h->ntot;
+  k_gather<<<grid_for(h, n, 256), 256, 0, h->stream>>>(h->ggl.p, h->p_ext.p, h->utemp.p, (long long)n);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(pmul_pp, h->utemp.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int pf_matvec(pf_handle h, const double *pmul_pp, double *utemp_pp) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_km, "needs element matrices");
+  const size_t n = (size_t)h->nels * h->ntot;
+  DevBuf<double> pm;
+  CU(pm.alloc(n));
+  CU(cudaMemcpyAsync(pm.p, pmul_pp, n * 8, cudaMemcpyHostToDevice, h->stream));
+  rc = launch_matvec<false>(h, pm.p, nullptr);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(utemp_pp, h->utemp.p, n * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = fail(h, 10, "pf_matvec: %s", cudaGetErrorString(e));
+  }
+  cudaStreamSynchronize(h->stream);
+  pm.release();
+  return rc;
+}
+
+int pf_scatter(pf_handle h, const double *utemp_pp, double *u_pp) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_mesh, "needs pf_setup_mesh");
+  const size_t n = (size_t)h->nels * h->ntot;
+  CU(cudaMemcpyAsync(h->utemp.p, utemp_pp, n * 8, cudaMemcpyHostToDevice, h->stream));
+  if ((rc = launch_scatter(h, nullptr, false, h->u_ext.p))) return rc;
+  if ((rc = halo_reverse(h, h->u_ext.p, nullptr))) return rc;
+  CU(cudaMemcpyAsync(u_pp, h->u_ext.p + 1, (size_t)h->neq_pp * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int pf_apply(pf_handle h, const double *p_pp, double *u_pp) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_km, "needs element matrices");
+  if ((rc = upload_owned(h, h->p_ext.p, p_pp))) return rc;
+  const int nfixed = h->nfixed;
+  if (!h->have_precon) h->nfixed = 0;
+  rc = apply_operator(h, nullptr);
+  h->nfixed = nfixed;
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(u_pp, h->u_ext.p + 1, (size_t)h->neq_pp * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int pf_dot(pf_handle h, const double *a_pp, const double *b_pp, double *result) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_mesh, "needs pf_setup_mesh");
+  // p_ext / u_ext double as staging for the two operands
+  if ((rc = upload_owned(h, h->p_ext.p, a_pp))) return rc;
+  if ((rc = upload_owned(h, h->u_ext.p, b_pp))) return rc;
+  k_dot<<<vec_grid(h), kRedThreads, 0, h->stream>>>(h->p_ext.p + 1, h->u_ext.p + 1, (long long)h->neq_pp, h->part.p, h->state.p,
+                                                     h->nranks == 1, -1);
+  h->launches++;
+  CU(cudaGetLastError());
+  std::vector<double> all((size_t)4 * h->nranks, 0.0);
+  if (h->nranks > 1) {
+    NC(g_nccl.AllGather(h->state.p->loc, h->gath.p, 4, ncclDouble, h->comm, h->stream));
+    CU(cudaMemcpyAsync(all.data(), h->gath.p, all.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    CU(cudaMemcpyAsync(all.data(), h->state.p->loc, 4 * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  double s = all[0];
+  for (int r = 1; r < h->nranks; ++r) s = s + all[(size_t)4 * r];  // ranks ascending
+  *result = s;
+  return 0;
+}
+
+int pf_norm(pf_handle h, const double *a_pp, double *result) {
+  double s = 0.0;
+  int rc = pf_dot(h, a_pp, a_pp, &s);
+  if (rc) return rc;
+  *result = std::sqrt(s);  // norm_p, maths.f90:258-261
+  return 0;
+}
+
+int pf_centroid_stress(pf_handle h, int64_t iel, double e, double v, double *sigma6) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_mesh && h->nodof == 3 && iel >= 0 && iel < h->nels, "needs an elastic mesh and a local element index");
+  // gather xnew into eld (p121.f90:114) for this one element, then one point at the centroid
+  const int ntot = h->ntot, nod = h->nod;
+  std::vector<int> g((size_t)ntot);
+  std::vector<double> co((size_t)nod * 3), eld((size_t)ntot, 0.0);
+  CU(cudaMemcpy(g.data(), h->ggl.p + iel * ntot, (size_t)ntot * 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(co.data(), h->coord.p + iel * nod * 3, co.size() * 8, cudaMemcpyDeviceToHost));
+  if (h->nranks > 1) {
+    // x lives in h->x (owned only): stage it through p_ext so halo values arrive
+    CU(cudaMemcpyAsync(h->p_ext.p + 1, h->x.p, (size_t)h->neq_pp * 8, cudaMemcpyDeviceToDevice, h->stream));
+    if ((rc = halo_forward(h, h->p_ext.p, nullptr))) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  for (int k = 0; k < ntot; ++k) {
+    if (g[(size_t)k] == 0) continue;
+    const double *src = (h->nranks > 1) ? h->p_ext.p + g[(size_t)k] : h->x.p + (g[(size_t)k] - 1);
+    if (h->nranks == 1 && g[(size_t)k] > h->neq_pp) return fail(h, 6, "slot outside owned range");
+    CU(cudaMemcpy(&eld[(size_t)k], src, 8, cudaMemcpyDeviceToHost));
+  }
+  ElemTables T;
+  if (fill_tables(nod, 1, e, v, 0, 0, 0, T)) return fail(h, 3, "unsupported nod");
+  // jac, inverse, deriv with the same operation order as the kernels
+  double jac[9], inv[9], deriv[60];
+  for (int b = 0; b < 3; ++b)
+    for (int a = 0; a < 3; ++a) {
+      double s = 0.0;
+      for (int m = 0; m < nod; ++m) s = s + T.der[a * 20 + m] * co[(size_t)b * nod + m];
+      jac[b * 3 + a] = s;
+    }
+#define A(r, c) jac[(c - 1) * 3 + (r - 1)]
+  double det = A(1, 1) * (A(2, 2) * A(3, 3) - A(3, 2) * A(2, 3));
+  det = det - A(1, 2) * (A(2, 1) * A(3, 3) - A(3, 1) * A(2, 3));
+  det = det + A(1, 3) * (A(2, 1) * A(3, 2) - A(3, 1) * A(2, 2));
+  inv[0] = (A(2, 2) * A(3, 3) - A(3, 2) * A(2, 3)) / det;
+  inv[1] = (-(A(2, 1) * A(3, 3)) + A(3, 1) * A(2, 3)) / det;
+  inv[2] = (A(2, 1) * A(3, 2) - A(3, 1) * A(2, 2)) / det;
+  inv[3] = (-(A(1, 2) * A(3, 3)) + A(3, 2) * A(1, 3)) / det;
+  inv[4] = (A(1, 1) * A(3, 3) - A(3, 1) * A(1, 3)) / det;
+  inv[5] = (-(A(1, 1) * A(3, 2)) + A(3, 1) * A(1, 2)) / det;
+  inv[6] = (A(1, 2) * A(2, 3) - A(2, 2) * A(1, 3)) / det;
+  inv[7] = (-(A(1, 1) * A(2, 3)) + A(2, 1) * A(1, 3)) / det;
+  inv[8] = (A(1, 1) * A(2, 2) - A(2, 1) * A(1, 2)) / det;
+#undef A
+  for (int m = 0; m < nod; ++m)
+    for (int a = 0; a < 3; ++a) {
+      double s = 0.0;
+      for (int b = 0; b < 3; ++b) s = s + inv[b * 3 + a] * T.der[b * 20 + m];
+      deriv[m * 3 + a] = s;
+    }
+  // eps = bee*eld, rows of bee from beemat (new_library.f90:976-993)
+  double eps[6];
+  for (int row = 0; row < 6; ++row) {
+    double s = 0.0;
+    for (int c = 0; c < ntot; ++c) {
+      const int m = c / 3, comp = c % 3;
+      const double x = deriv[m * 3], y = deriv[m * 3 + 1], z = deriv[m * 3 + 2];
+      double b = 0.0;
+      if (comp == 0) b = row == 0 ? x : row == 3 ? y : row == 5 ? z : 0.0;
+      else if (comp == 1) b = row == 1 ? y : row == 3 ? x : row == 4 ? z : 0.0;
+      else b = row == 2 ? z : row == 4 ? y : row == 5 ? x : 0.0;
+      s = s + b * eld[(size_t)c];
+    }
+    eps[row] = s;
+  }
+  for (int row = 0; row < 6; ++row) {
+    double s = 0.0;
+    for (int c = 0; c < 6; ++c) s = s + T.dee[c * 6 + row] * eps[c];
+    sigma6[row] = s;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,494 @@
+// host.cpp -- section B of include/parafem_b200.h: CPU-side helpers that
+// restate the ParaFEM library routines a p121/p123 host driver calls around
+// the device path (partition arithmetic, p12meshgen cubes, steering arrays,
+// deck readers, gather-table construction).  No CUDA in this file.
+//
+// Reference files followed (all under /root/reference/parafem/src):
+//   modules/mpi/gather_scatter.f90  calc_nels_pp :146-257, calc_neq_pp :263-343,
+//                                   make_ggl :1387-1780
+//   modules/shared/geometry.f90     geometry_8bxz :70-169, geometry_20bxz :175-286,
+//                                   cube_bc20 :425-500, cube_bc8 :589-650, box_bc8 :652-696
+//   modules/mpi/loading.f90         load :36-142, load_p121 :386-546
+//   modules/shared/new_library.f90  rearrange :3059-3112, find_g3 :3130-3212,
+//                                   rearrange_2 :3118-3124, find_g4 :3249-3271,
+//                                   abaqus2sg :3515-3682
+//   modules/mpi/input.f90           read_p121 :3234-3396, read_p123 :3620-3806,
+//                                   read_g_coord_pp :288-445, read_g_num_pp :935-1080,
+//                                   read_rest :2570-2632, read_loads :2350-2411
+//   tools/preprocessing/p12meshgen/p12meshgen.f90 :118-364 (p121), :658-819 (p123)
+#include "parafem_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+// even split used for both elements and equations: the first `rem` ranks get
+// one extra item (gather_scatter.f90:217-238 and :319-339 are the same formula)
+void even_split(int64_t n, int npes, int numpe, int64_t *cnt, int64_t *start) {
+  if (npes <= 1) { *cnt = n; *start = 1; return; }
+  int64_t lo = n / npes, rem = n - lo * npes;
+  int64_t hi = rem == 0 ? lo : lo + 1;
+  if (numpe <= rem || rem == 0) {
+    *cnt = hi; *start = (int64_t)(numpe - 1) * hi + 1;
+  } else {
+    *cnt = lo; *start = rem * hi + (int64_t)(numpe - rem - 1) * (hi - 1) + 1;
+  }
+}
+
+// value as it survives a Fortran Ew.d text field (d significant digits)
+double through_text(double x, int digits) {
+  char buf[64];
+  snprintf(buf, sizeof buf, "%.*E", digits - 1, x);
+  return strtod(buf, nullptr);
+}
+
+inline bool divisible(int64_t a, int64_t m) { return a % m == 0; }
+
+void hex8_element(int64_t iel, int nxe, int nze, double aa, double bb, double cc,
+                  int32_t *num, double *coord /* (8,3) col-major */) {
+  // geometry_8bxz: elements run x fastest, then z (downwards), then y planes
+  int64_t plane = (int64_t)nxe * nze;
+  int64_t iq = (iel - 1) / plane + 1;
+  int64_t ipl = iel - (iq - 1) * plane;
+  int64_t is = (ipl - 1) / nxe + 1;
+  int64_t ip = ipl - (is - 1) * nxe;
+  int64_t row = nxe + 1, layer = (int64_t)(nxe + 1) * (nze + 1);
+  int64_t n1 = (iq - 1) * layer + is * row + ip;
+  int64_t n[8];
+  n[0] = n1; n[1] = n1 - row; n[2] = n[1] + 1; n[3] = n1 + 1;
+  n[4] = n1 + layer; n[5] = n[4] - row; n[6] = n[5] + 1; n[7] = n[4] + 1;
+  for (int m = 0; m < 8; ++m) num[m] = (int32_t)n[m];
+  double x0 = (ip - 1) * aa, x1 = ip * aa;
+  double y0 = (iq - 1) * bb, y1 = iq * bb;
+  double zb = -(double)is * cc, zt = -(double)(is - 1) * cc;
+  const int xhi[8] = {0, 0, 1, 1, 0, 0, 1, 1};
+  const int yhi[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+  const int ztop[8] = {0, 1, 1, 0, 0, 1, 1, 0};
+  for (int m = 0; m < 8; ++m) {
+    coord[0 * 8 + m] = xhi[m] ? x1 : x0;
+    coord[1 * 8 + m] = yhi[m] ? y1 : y0;
+    coord[2 * 8 + m] = ztop[m] ? zt : zb;
+  }
+}
+
+void hex20_element(int64_t iel, int nxe, int nze, double aa, double bb, double cc,
+                   int32_t *num, double *coord /* (20,3) col-major */) {
+  // geometry_20bxz: a "full" plane of corner+mid-edge nodes followed by a
+  // mid-plane holding only the y-mid-edge nodes
+  int64_t plane = (int64_t)nxe * nze;
+  int64_t iq = (iel - 1) / plane + 1;
+  int64_t ipl = iel - (iq - 1) * plane;
+  int64_t is = (ipl - 1) / nxe + 1;
+  int64_t ip = ipl - (is - 1) * nxe;
+  int64_t per_y = (int64_t)(2 * nxe + 1) * (nze + 1) + (int64_t)(2 * nze + 1) * (nxe + 1);
+  int64_t f1 = per_y * (iq - 1), f2 = per_y * iq;
+  int64_t band = 3 * nxe + 2, mid = (int64_t)(nxe + 1) * (nze + 1);
+  int64_t n[21];
+  n[1] = f1 + band * is + 2 * ip - 1;
+  n[2] = f1 + band * is - nxe + ip - 1;
+  n[3] = n[1] - band;
+  n[4] = n[3] + 1; n[5] = n[4] + 1; n[6] = n[2] + 1; n[7] = n[1] + 2; n[8] = n[1] + 1;
+  n[9] = f2 - mid + (nxe + 1) * is + ip;
+  n[10] = n[9] - nxe - 1; n[11] = n[10] + 1; n[12] = n[9] + 1;
+  n[13] = f2 + band * is + 2 * ip - 1;
+  n[14] = f2 + band * is - nxe + ip - 1;
+  n[15] = n[13] - band;
+  n[16] = n[15] + 1; n[17] = n[16] + 1; n[18] = n[14] + 1; n[19] = n[13] + 2; n[20] = n[13] + 1;
+  for (int m = 0; m < 20; ++m) num[m] = (int32_t)n[m + 1];
+  double *X = coord, *Y = coord + 20, *Z = coord + 40;
+  auto c = [](double *a, int k) -> double & { return a[k - 1]; };  // 1-based view
+  double x0 = (ip - 1) * aa, x1 = ip * aa;
+  for (int k : {1, 2, 3, 9, 10, 13, 14, 15}) c(X, k) = x0;
+  for (int k : {5, 6, 7, 11, 12, 17, 18, 19}) c(X, k) = x1;
+  c(X, 4) = .5 * (c(X, 3) + c(X, 5)); c(X, 8) = .5 * (c(X, 1) + c(X, 7));
+  c(X, 16) = .5 * (c(X, 15) + c(X, 17)); c(X, 20) = .5 * (c(X, 13) + c(X, 19));
+  double y0 = (iq - 1) * bb, y1 = iq * bb;
+  for (int k = 1; k <= 8; ++k) c(Y, k) = y0;
+  for (int k = 13; k <= 20; ++k) c(Y, k) = y1;
+  c(Y, 9) = .5 * (c(Y, 1) + c(Y, 13)); c(Y, 10) = .5 * (c(Y, 3) + c(Y, 15));
+  c(Y, 11) = .5 * (c(Y, 5) + c(Y, 17)); c(Y, 12) = .5 * (c(Y, 7) + c(Y, 19));
+  double zb = -(double)is * cc, zt = -(double)(is - 1) * cc;
+  for (int k : {1, 7, 8, 9, 12, 13, 19, 20}) c(Z, k) = zb;
+  for (int k : {3, 4, 5, 10, 11, 15, 16, 17}) c(Z, k) = zt;
+  c(Z, 2) = .5 * (c(Z, 1) + c(Z, 3)); c(Z, 6) = .5 * (c(Z, 5) + c(Z, 7));
+  c(Z, 14) = .5 * (c(Z, 13) + c(Z, 15)); c(Z, 18) = .5 * (c(Z, 17) + c(Z, 19));
+}
+
+struct RestWriter {
+  int32_t *rest; int64_t nr; int ncol; int64_t count = 0; bool overflow = false;
+  void add(int64_t node, int a, int b, int c) {
+    if (count >= nr) { overflow = true; ++count; return; }
+    rest[count] = (int32_t)node;
+    int v[3] = {a, b, c};
+    for (int k = 1; k < ncol; ++k) rest[(int64_t)k * nr + count] = v[k - 1];
+    ++count;
+  }
+};
+
+// tokenizer for list-directed decks: whitespace/comma separated, quotes kept off
+bool read_tokens(const std::string &path, std::vector<std::string> &tok) {
+  FILE *f = fopen(path.c_str(), "r");
+  if (!f) return false;
+  std::string cur; int ch; bool inq = false;
+  auto flush = [&]() { if (!cur.empty()) { tok.push_back(cur); cur.clear(); } };
+  while ((ch = fgetc(f)) != EOF) {
+    if (ch == '\'' || ch == '"') { inq = !inq; if (!inq) { tok.push_back(cur); cur.clear(); } continue; }
+    if (!inq && (ch == ' ' || ch == '\t' || ch == '\n' || ch == '\r' || ch == ',')) { flush(); continue; }
+    cur.push_back((char)ch);
+  }
+  flush(); fclose(f);
+  return true;
+}
+
+bool is_number(const std::string &s) {
+  if (s.empty()) return false;
+  char *end = nullptr; strtod(s.c_str(), &end);
+  return end && *end == '\0';
+}
+
+}  // namespace
+
+extern "C" {
+
+void pf_calc_nels_pp(int64_t nels, int npes, int numpe, int64_t *nels_pp, int64_t *iel_start) {
+  even_split(nels, npes, numpe, nels_pp, iel_start);
+}
+void pf_calc_neq_pp(int64_t neq, int npes, int numpe, int64_t *neq_pp, int64_t *ieq_start) {
+  even_split(neq, npes, numpe, neq_pp, ieq_start);
+}
+
+int pf_p121_sizes(int nxe, int nye, int nze, int nod, int64_t *nn, int64_t *nr, int64_t *loaded) {
+  int64_t X = nxe, Y = nye, Z = nze, nle = nxe / 5;
+  if (nod == 20) {
+    *nr = ((2 * X + 1) * (Z + 1) + (X + 1) * Z) * 2 + ((2 * Y - 1) * Z + (Y - 1) * Z) * 2 +
+          (2 * Y - 1) * (X + 1) + (Y - 1) * X;
+    *nn = (((2 * X + 1) * (Z + 1)) + ((X + 1) * Z)) * (Y + 1) + (X + 1) * (Z + 1) * Y;
+    *loaded = 3 * nle * nle + 4 * nle + 1;
+  } else if (nod == 8) {
+    // p12meshgen.f90:181 writes ((nxe+1)*(nze+1))*2 + ((nye-1)*(nze+1))*2 + (nxe-1)*(nze-1), which equals
+    // the number of rows cube_bc8 emits only when nxe == nye; count what cube_bc8 emits instead
+    *nr = ((X + 1) * (Z + 1)) * 2 + (Y - 1) * (2 * Z + X + 1);
+    *nn = (X + 1) * (Y + 1) * (Z + 1);
+    *loaded = (nle + 1) * (nle + 1);
+  } else return 1;
+  return 0;
+}
+
+int pf_p123_sizes(int nxe, int nye, int nze, int64_t *nn, int64_t *nr, int64_t *nres) {
+  int64_t X = nxe, Y = nye, Z = nze;
+  *nr = (X + 1) * (Y + 1) + (X + 1) * Z + Y * Z;
+  *nn = (X + 1) * (Y + 1) * (Z + 1);
+  *nres = X * (Z - 1) + 1;
+  return 0;
+}
+
+int pf_cube_elements(int nxe, int nze, int nod, double aa, double bb, double cc,
+                     int64_t iel_start, int64_t nels_pp, int round_mode,
+                     int32_t *g_num_pp, double *g_coord_pp) {
+  if (nod != 8 && nod != 20) return 1;
+#pragma omp parallel for schedule(static)
+  for (int64_t e = 0; e < nels_pp; ++e) {
+    int32_t *num = g_num_pp + e * nod;
+    double *co = g_coord_pp + e * nod * 3;
+    if (nod == 20) hex20_element(iel_start + e, nxe, nze, aa, bb, cc, num, co);
+    else hex8_element(iel_start + e, nxe, nze, aa, bb, cc, num, co);
+    if (round_mode == 1)
+      for (int k = 0; k < nod * 3; ++k) co[k] = through_text(co[k], 6);
+  }
+  return 0;
+}
+
+int pf_cube_rest(int kind, int nxe, int nye, int nze, int nod, int64_t nr, int32_t *rest) {
+  int64_t X = nxe, Z = nze;
+  if (kind == 1) {  // box_bc8 (p123): one column of flags, all zero
+    RestWriter w{rest, nr, 2};
+    int64_t face = (X + 1) * (Z + 1);
+    for (int64_t i = 0; i < nye; ++i)
+      for (int64_t j = i * face + 1; j <= (i + 1) * face; ++j)
+        if (divisible(j, X + 1) || j < i * face + X + 1) w.add(j, 0, 0, 0);
+    for (int64_t j = nye * face + 1; j <= (nye + 1) * face; ++j) w.add(j, 0, 0, 0);
+    return (w.overflow || w.count != nr) ? 2 : 0;
+  }
+  RestWriter w{rest, nr, 4};
+  if (nod == 20) {
+    int64_t face1 = 3 * X * Z + 2 * (X + Z) + 1, face2 = (X + 1) * (Z + 1);
+    int64_t face = face1 + face2, l = Z * (X + 1), m = 3 * X + 2, n = 3 * X * Z + 2 * Z;
+    for (int64_t i = 0; i <= nye; ++i) {
+      bool endplane = (i == 0 || i == nye);
+      for (int64_t j = i * face + 1; j <= i * face + face1; ++j) {
+        int64_t k = j - i * face;
+        bool side = k <= n && (divisible(k + m - 1, m) || divisible(k + X + 1, m) ||
+                               divisible(k + X, m) || divisible(k, m));
+        if (endplane) {
+          if (side) w.add(j, 0, 0, 1);
+          else if (k <= n) w.add(j, 1, 0, 1);
+          else w.add(j, 0, 0, 0);
+        } else {
+          if (side) w.add(j, 0, 1, 1);
+          else if (k > n) w.add(j, 0, 0, 0);
+        }
+      }
+      if (i < nye)
+        for (int64_t j = i * face + face1 + 1; j <= (i + 1) * face; ++j) {
+          int64_t k = j - (face1 + i * face);
+          if (k <= l && (divisible(k + X, X + 1) || divisible(k, X + 1))) w.add(j, 0, 1, 1);
+          else if (k > l) w.add(j, 0, 0, 0);
+        }
+    }
+  } else if (nod == 8) {
+    int64_t face = (X + 1) * (Z + 1), m = 2 * X + 2, n = (X + 1) * Z;
+    for (int64_t i = 0; i <= nye; ++i) {
+      bool endplane = (i == 0 || i == nye);
+      for (int64_t j = i * face + 1; j <= i * face + face; ++j) {
+        int64_t k = j - i * face;
+        bool side = k <= n && (divisible(k + m - 1, m) || divisible(k + X + 1, m) ||
+                               divisible(k + X, m) || divisible(k, m));
+        if (endplane) {
+          if (side) w.add(j, 0, 0, 1);
+          else if (k <= n) w.add(j, 1, 0, 1);
+          else w.add(j, 0, 0, 0);
+        } else {
+          if (side) w.add(j, 0, 1, 1);
+          else if (k > n) w.add(j, 0, 0, 0);
+        }
+      }
+    }
+  } else return 1;
+  return (w.overflow || w.count != nr) ? 2 : 0;
+}
+
+int pf_p121_loads(int nxe, int nze, int nod, double aa, double bb, int round_mode,
+                  int32_t *node, double *val) {
+  int64_t X = nxe, Z = nze, nle = nxe / 5, c = 0;
+  std::vector<double> v;
+  if (nod == 20) {
+    int64_t f1 = (2 * X + 1) * (Z + 1) + (X + 1) * Z, f2 = (X + 1) * (Z + 1);
+    auto edge_row = [&](int64_t base, double w_end, double w_even, double w_odd) {
+      for (int64_t i = 1; i <= 2 * nle + 1; ++i) {
+        node[c++] = (int32_t)(base + i);
+        v.push_back((i == 1 || i == 2 * nle + 1) ? w_end : (i % 2 == 0 ? w_even : w_odd));
+      }
+    };
+    edge_row(0, -1., 4., -2.);
+    for (int64_t j = 0; j < nle; ++j) {
+      for (int64_t i = 1; i <= nle + 1; ++i) {
+        node[c++] = (int32_t)(i + f1 + j * (f1 + f2));
+        v.push_back((i == 1 || i == nle + 1) ? 4. : 8.);
+      }
+      if (j != nle - 1) edge_row(f1 + (j + 1) * f2 + j * f1, -2., 8., -4.);
+      else edge_row(f1 + (j + 1) * f2 + j * f1, -1., 4., -2.);
+    }
+    for (auto &x : v) x = -x * aa * bb * (25. / 12.);
+  } else if (nod == 8) {
+    int64_t f1 = (X + 1) * (Z + 1);
+    for (int64_t i = 1; i <= nle + 1; ++i) {
+      node[c++] = (int32_t)i;
+      v.push_back((i == 1 || i == nle + 1) ? -6.25 : -12.5);
+    }
+    for (int64_t j = 0; j < nle; ++j)
+      for (int64_t i = 1; i <= nle + 1; ++i) {
+        node[c++] = (int32_t)(i + (j + 1) * f1);
+        bool end = (i == 1 || i == nle + 1);
+        if (j != nle - 1) v.push_back(end ? -12.5 : -25.);
+        else v.push_back(end ? -6.25 : -12.5);
+      }
+    for (auto &x : v) x = x * aa * bb;
+  } else return 1;
+  for (int64_t i = 0; i < c; ++i) {
+    val[3 * i + 0] = 0.; val[3 * i + 1] = 0.;
+    val[3 * i + 2] = round_mode == 1 ? through_text(v[i], 8) : v[i];
+  }
+  return 0;
+}
+
+int pf_form_nf(int64_t nn, int nodof, int64_t nr, const int32_t *rest, int32_t *nf, int64_t *neq) {
+  // free = 1 everywhere, then the rest rows overwrite; number free dofs in node order
+  for (int64_t i = 0; i < nn * nodof; ++i) nf[i] = 1;
+  for (int64_t i = 0; i < nr; ++i) {
+    int64_t node = rest[i];
+    if (node < 1 || node > nn) return 2;
+    for (int k = 0; k < nodof; ++k) nf[(node - 1) * nodof + k] = rest[(int64_t)(k + 1) * nr + i];
+  }
+  int64_t m = 0;
+  for (int64_t i = 0; i < nn * nodof; ++i)
+    if (nf[i] != 0) nf[i] = (int32_t)(++m);
+  *neq = m;
+  return 0;
+}
+
+int pf_find_g(int nod, int nodof, int64_t nels_pp, const int32_t *g_num_pp, const int32_t *nf,
+              int32_t *g_g_pp) {
+  int ntot = nod * nodof;
+#pragma omp parallel for schedule(static)
+  for (int64_t e = 0; e < nels_pp; ++e)
+    for (int m = 0; m < nod; ++m) {
+      int64_t node = g_num_pp[e * nod + m];
+      for (int k = 0; k < nodof; ++k) g_g_pp[e * ntot + m * nodof + k] = nf[(node - 1) * nodof + k];
+    }
+  return 0;
+}
+
+int pf_load(int nodof, int64_t loaded, const int32_t *node, const double *val, const int32_t *nf,
+            int64_t ieq_start, int64_t neq_pp, double *r_pp) {
+  for (int64_t i = 0; i < neq_pp; ++i) r_pp[i] = 0.;
+  for (int64_t i = 0; i < loaded; ++i)
+    for (int k = 0; k < nodof; ++k) {
+      int64_t eq = nf[(int64_t)(node[i] - 1) * nodof + k];
+      if (eq >= ieq_start && eq < ieq_start + neq_pp) r_pp[eq - ieq_start] = val[i * nodof + k];
+    }
+  return 0;
+}
+
+int pf_abaqus2sg(int nod, int64_t nels, int32_t *g_num) {
+  // new position m (0-based) takes old position perm[m] (0-based)
+  static const int p20[20] = {3, 11, 0, 8, 1, 9, 2, 10, 19, 16, 17, 18, 7, 15, 4, 12, 5, 13, 6, 14};
+  static const int p8[8] = {0, 4, 5, 1, 3, 7, 6, 2};
+  const int *p = nod == 20 ? p20 : nod == 8 ? p8 : nullptr;
+  if (!p) return 1;
+  for (int64_t e = 0; e < nels; ++e) {
+    int32_t t[20];
+    for (int m = 0; m < nod; ++m) t[m] = g_num[e * nod + m];
+    for (int m = 0; m < nod; ++m) g_num[e * nod + m] = t[p[m]];
+  }
+  return 0;
+}
+
+int pf_read_dat(const char *job, int program, pf_deck_info *info) {
+  std::vector<std::string> t;
+  if (!read_tokens(std::string(job) + ".dat", t)) return 1;
+  memset(info, 0, sizeof *info);
+  info->program = program;
+  size_t k = 0;
+  // xx3-style decks carry a leading program tag ('gpu') before 'hexahedron'
+  while (k < t.size() && !is_number(t[k])) ++k;
+  std::vector<double> v;
+  for (; k < t.size(); ++k) if (is_number(t[k])) v.push_back(strtod(t[k].c_str(), nullptr));
+  if (program == 121) {
+    if (v.size() < 12) return 2;
+    info->meshgen = (int)v[0]; info->partitioner = (int)v[1];
+    info->nels = (int64_t)v[2]; info->nn = (int64_t)v[3]; info->nr = (int64_t)v[4];
+    info->nip = (int)v[5]; info->nod = (int)v[6]; info->loaded = (int64_t)v[7];
+    info->e = v[8]; info->v = v[9]; info->tol = v[10]; info->limit = (int)v[11];
+  } else if (program == 123) {
+    if (v.size() < 15) return 2;
+    info->meshgen = (int)v[0]; info->partitioner = (int)v[1];
+    info->nels = (int64_t)v[2]; info->nn = (int64_t)v[3]; info->nr = (int64_t)v[4];
+    info->nip = (int)v[5]; info->nod = (int)v[6]; info->loaded = (int64_t)v[7];
+    info->fixed = (int64_t)v[8];
+    info->kx = v[9]; info->ky = v[10]; info->kz = v[11]; info->tol = v[12];
+    info->limit = (int)v[13]; info->nres = (int64_t)v[14];
+  } else return 3;
+  return 0;
+}
+
+int pf_read_d(const char *job, int64_t nn, int64_t nels, int nod, double *g_coord, int32_t *g_num) {
+  FILE *f = fopen((std::string(job) + ".d").c_str(), "r");
+  if (!f) return 1;
+  char word[256];
+  int rc = 0;
+  if (fscanf(f, "%255s", word) != 1 || fscanf(f, "%255s", word) != 1) rc = 2;  // *THREE_DIMENSIONAL *NODES
+  for (int64_t i = 0; i < nn && !rc; ++i) {
+    long long id; double x, y, z;
+    if (fscanf(f, "%lld %lf %lf %lf", &id, &x, &y, &z) != 4 || id < 1 || id > nn) { rc = 3; break; }
+    g_coord[(id - 1) * 3 + 0] = x; g_coord[(id - 1) * 3 + 1] = y; g_coord[(id - 1) * 3 + 2] = z;
+  }
+  if (!rc && fscanf(f, "%255s", word) != 1) rc = 4;  // *ELEMENTS
+  for (int64_t e = 0; e < nels && !rc; ++e) {
+    long long id, a, b, c, v;
+    if (fscanf(f, "%lld %lld %lld %lld", &id, &a, &b, &c) != 4 || b != nod) { rc = 5; break; }
+    for (int m = 0; m < nod; ++m) {
+      if (fscanf(f, "%lld", &v) != 1) { rc = 6; break; }
+      g_num[e * nod + m] = (int32_t)v;
+    }
+    if (!rc && fscanf(f, "%lld", &v) != 1) rc = 7;  // material id
+  }
+  fclose(f);
+  return rc;
+}
+
+int pf_read_bnd(const char *job, int64_t nr, int nodof, int32_t *rest) {
+  FILE *f = fopen((std::string(job) + ".bnd").c_str(), "r");
+  if (!f) return 1;
+  int rc = 0;
+  for (int64_t i = 0; i < nr && !rc; ++i)
+    for (int k = 0; k <= nodof; ++k) {
+      long long v;
+      if (fscanf(f, "%lld", &v) != 1) { rc = 2; break; }
+      rest[(int64_t)k * nr + i] = (int32_t)v;
+    }
+  fclose(f);
+  return rc;
+}
+
+int pf_read_lds(const char *job, int64_t loaded, int nodof, int32_t *node, double *val) {
+  FILE *f = fopen((std::string(job) + ".lds").c_str(), "r");
+  if (!f) return 1;
+  int rc = 0;
+  for (int64_t i = 0; i < loaded && !rc; ++i) {
+    long long n;
+    if (fscanf(f, "%lld", &n) != 1) { rc = 2; break; }
+    node[i] = (int32_t)n;
+    for (int k = 0; k < nodof; ++k)
+      if (fscanf(f, "%lf", &val[i * nodof + k]) != 1) { rc = 3; break; }
+  }
+  fclose(f);
+  return rc;
+}
+
+int pf_coords_pp(int nod, int64_t nels_pp, const int32_t *g_num_pp, const double *g_coord,
+                 double *g_coord_pp) {
+#pragma omp parallel for schedule(static)
+  for (int64_t e = 0; e < nels_pp; ++e)
+    for (int m = 0; m < nod; ++m) {
+      int64_t node = g_num_pp[e * nod + m] - 1;
+      for (int d = 0; d < 3; ++d) g_coord_pp[e * nod * 3 + d * nod + m] = g_coord[node * 3 + d];
+    }
+  return 0;
+}
+
+int pf_make_ggl(int ntot, int64_t nels_pp, const int32_t *g_g_pp, int64_t neq, int npes, int numpe,
+                int32_t *ggl_pp, int64_t cap, int32_t *halo_eq, int64_t *halo_cnt, int64_t *nhalo) {
+  int64_t neq_pp, ieq_start;
+  even_split(neq, npes, numpe, &neq_pp, &ieq_start);
+  int64_t lo = ieq_start, hi = ieq_start + neq_pp;  // owned: [lo, hi)
+  int64_t total = nels_pp * ntot;
+  // remote equations referenced by local elements, sorted unique; ascending
+  // global number == ascending owner rank because ownership is contiguous
+  std::vector<int32_t> remote;
+  for (int64_t i = 0; i < total; ++i) {
+    int64_t g = g_g_pp[i];
+    if (g < 0 || g > neq) return 2;
+    if (g != 0 && (g < lo || g >= hi)) remote.push_back((int32_t)g);
+  }
+  std::sort(remote.begin(), remote.end());
+  remote.erase(std::unique(remote.begin(), remote.end()), remote.end());
+  *nhalo = (int64_t)remote.size();
+  if (halo_cnt) {
+    for (int r = 0; r < npes; ++r) halo_cnt[r] = 0;
+    int r = 1; int64_t cnt_r, st_r; even_split(neq, npes, r, &cnt_r, &st_r);
+    for (int32_t g : remote) {
+      while (g >= st_r + cnt_r) { ++r; even_split(neq, npes, r, &cnt_r, &st_r); }
+      halo_cnt[r - 1]++;
+    }
+  }
+  if (cap < (int64_t)remote.size() || !ggl_pp || !halo_eq) return cap == 0 ? 0 : 3;
+  std::copy(remote.begin(), remote.end(), halo_eq);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < total; ++i) {
+    int64_t g = g_g_pp[i];
+    if (g == 0) ggl_pp[i] = 0;
+    else if (g >= lo && g < hi) ggl_pp[i] = (int32_t)(g - lo + 1);
+    else {
+      auto it = std::lower_bound(remote.begin(), remote.end(), (int32_t)g);
+      ggl_pp[i] = (int32_t)(neq_pp + 1 + (it - remote.begin()));
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,631 @@
+// kernels.cuh -- sm_100a kernels of the EBE-PCG hot path.
+//
+// Everything here is FP64 and HBM-bound; nothing is tensor-core work.  The file
+// is compiled with --fmad=false so that every a*b+c is a separate IEEE multiply
+// and add: the kernels then produce the same bits as oracle/pf_oracle.c
+// (-ffp-contract=off) because they also use the same summation orders:
+//   mat-vec     u_i = sum_j K(i,j) p_j, j ascending        (p121.f90:93-97)
+//   scatter     contributions in ascending element order    (gather_scatter.f90:759-761)
+//   reductions  the fixed blocked tree described at block_tree() below
+// The kernels are bandwidth-bound, so the lost FMA throughput costs nothing.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pf {
+
+// ----------------------------------------------------------------------------
+// device-resident solver state (one per handle)
+// ----------------------------------------------------------------------------
+struct State {
+  double up;         // r.d at the top of the iteration (p121.f90:99)
+  double pu;         // p.u
+  double alpha, beta;
+  double rd_new;     // r.d after the update (numerator of beta)
+  double maxloads, maxdiff, ratio;
+  double loc[4];     // this rank's partials: [0] dot, [1] max|xnew|, [2] max|xnew-x|
+  double tol;
+  int iters, limit;
+  int done, converged;
+  unsigned int ticket[4];  // "last block" counters, one per reducing kernel
+};
+
+// ----------------------------------------------------------------------------
+// small PTX wrappers: mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// global -> shared bulk copy completing on an mbarrier; streaming data: L2 evict_first
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar,
+                                         uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+// ----------------------------------------------------------------------------
+// a7+a8 fused: pmul = p(ggl) gathered into shared memory, utemp = K_e * pmul
+// ----------------------------------------------------------------------------
+// One persistent CTA per SM.  Warp w owns ring slot w: it issues a 1-D bulk copy
+// of the next tile of EPT element matrices (the Fortran layout
+// storkm_pp(ntot,ntot,iel) is already contiguous per element), gathers the tile's
+// p values while the copy is in flight, waits on the slot's mbarrier, multiplies,
+// stores utemp and re-arms the slot.  Every byte of storkm is read once; lanes
+// hold two rows each so shared-memory reads are conflict-free 128-bit loads.
+template <int NTOT, int EPT, int STAGES>
+struct MatvecCfg {
+  static constexpr int kTileDoubles = EPT * NTOT * NTOT;
+  static constexpr int kTileBytes = kTileDoubles * 8;
+  static constexpr int kPmDoubles = EPT * NTOT;
+  static constexpr int kThreads = STAGES * 32;
+  static constexpr size_t kSmem = (size_t)STAGES * kTileBytes + (size_t)STAGES * kPmDoubles * 8 + STAGES * 8;
+};
+
+template <int NTOT, int EPT, int STAGES, bool GATHER>
+__global__ void __launch_bounds__(STAGES * 32, 1)
+k_matvec(const double *__restrict__ km, const int *__restrict__ ggl, const double *__restrict__ pvec,
+         double *__restrict__ utemp, long long nels, const State *st) {
+  using Cfg = MatvecCfg<NTOT, EPT, STAGES>;
+  if (st && *(volatile const int *)&st->done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *tiles = reinterpret_cast<double *>(smem_raw);
+  double *pm_all = tiles + (size_t)STAGES * Cfg::kTileDoubles;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(pm_all + STAGES * Cfg::kPmDoubles);
+
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ntiles = (nels + EPT - 1) / EPT;
+  const long long t0 = ntiles * blockIdx.x / gridDim.x;
+  const long long t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
+  double *tile = tiles + (size_t)w * Cfg::kTileDoubles;
+  double *pm = pm_all + w * Cfg::kPmDoubles;
+  const uint32_t bar = smem_u32(&bars[w]);
+  const uint32_t tile_s = smem_u32(tile);
+  uint64_t policy = 0;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    policy = policy_evict_first();
+  }
+  __syncwarp();
+
+  auto issue = [&](long long t) {
+    const long long e0 = t * EPT;
+    const int ne = (int)((nels - e0) < EPT ? (nels - e0) : EPT);
+    const uint32_t bytes = (uint32_t)ne * NTOT * NTOT * 8;
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(tile_s, km + e0 * (long long)(NTOT * NTOT), bytes, bar, policy);
+  };
+
+  long long t = t0 + w;
+  if (t < t1 && lane == 0) issue(t);
+  uint32_t phase = 0;
+  constexpr int RP = NTOT / 2;  // row pairs per element
+  for (; t < t1; t += STAGES) {
+    const long long e0 = t * EPT;
+    const int ne = (int)((nels - e0) < EPT ? (nels - e0) : EPT);
+    // gather (or copy) the tile's right-hand sides while the bulk copy flies
+    for (int s = lane; s < ne * NTOT; s += 32) {
+      if (GATHER) pm[s] = pvec[ggl[e0 * NTOT + s]];
+      else pm[s] = pvec[e0 * NTOT + s];
+    }
+    __syncwarp();
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    for (int s = lane; s < ne * RP; s += 32) {
+      const int el = s / RP, rp = s - el * RP;
+      const double *K = tile + el * (NTOT * NTOT) + 2 * rp;
+      const double *pv = pm + el * NTOT;
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < NTOT; j += 2) {
+        const double2 pj = *reinterpret_cast<const double2 *>(pv + j);
+        const double2 k0 = *reinterpret_cast<const double2 *>(K + j * NTOT);
+        const double2 k1 = *reinterpret_cast<const double2 *>(K + (j + 1) * NTOT);
+        a0 = a0 + k0.x * pj.x; a1 = a1 + k0.y * pj.x;
+        a0 = a0 + k1.x * pj.y; a1 = a1 + k1.y * pj.y;
+      }
+      *reinterpret_cast<double2 *>(utemp + (e0 + el) * NTOT + 2 * rp) = make_double2(a0, a1);
+    }
+    __syncwarp();
+    const long long tn = t + STAGES;
+    if (tn < t1 && lane == 0) {
+      fence_proxy_async();  // order this warp's generic reads of the slot before the async overwrite
+      issue(tn);
+    }
+  }
+}
+
+// pmul materialised (pf_gather only; the solver never does this)
+__global__ void k_gather(const int *__restrict__ ggl, const double *__restrict__ p_ext,
+                         double *__restrict__ pmul, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) pmul[i] = p_ext[ggl[i]];
+}
+
+// ----------------------------------------------------------------------------
+// a9: deterministic scatter as a slot-centric gather.  csr_ptr/csr_pos list, for
+// every slot >= 1 of the local gather buffer, the positions e*ntot+k in utemp of
+// its contributions in ascending element order.  DIAG: read K_e(k,k) instead.
+// ----------------------------------------------------------------------------
+template <bool DIAG>
+__global__ void k_scatter(const unsigned int *__restrict__ csr_ptr, const unsigned int *__restrict__ csr_pos,
+                          const double *__restrict__ src, double *__restrict__ u_ext, long long nslots,
+                          int ntot, const State *st) {
+  if (st && *(volatile const int *)&st->done) return;
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; s < nslots; s += stride) {
+    const unsigned int a = csr_ptr[s], b = csr_ptr[s + 1];
+    double acc = 0.0;
+    for (unsigned int k = a; k < b; ++k) {
+      const unsigned int pos = csr_pos[k];
+      if (DIAG) {
+        const unsigned int e = pos / ntot, d = pos - e * ntot;
+        acc = acc + src[(size_t)e * ntot * ntot + (size_t)d * ntot + d];
+      } else {
+        acc = acc + src[pos];
+      }
+    }
+    u_ext[s] = acc;
+  }
+}
+
+// owner side of the reverse halo exchange: add received partial sums, sources in
+// ascending rank order (acc_pos is sorted that way per equation)
+__global__ void k_halo_accumulate(const int *__restrict__ acc_slot, const unsigned int *__restrict__ acc_ptr,
+                                  const unsigned int *__restrict__ acc_pos, const double *__restrict__ recv,
+                                  double *__restrict__ u_ext, int n, const State *st) {
+  if (st && *(volatile const int *)&st->done) return;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double acc = u_ext[acc_slot[i]];
+  for (unsigned int k = acc_ptr[i]; k < acc_ptr[i + 1]; ++k) acc = acc + recv[acc_pos[k]];
+  u_ext[acc_slot[i]] = acc;
+}
+
+// pack owned values wanted by other ranks (forward halo exchange)
+__global__ void k_halo_pack(const int *__restrict__ put_slot, const double *__restrict__ p_ext,
+                            double *__restrict__ sendbuf, int n, const State *st) {
+  if (st && *(volatile const int *)&st->done) return;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sendbuf[i] = p_ext[put_slot[i]];
+}
+
+// ----------------------------------------------------------------------------
+// the fixed blocked reduction tree (mirrored by orc_dot_blocked in the oracle)
+//   chunk c = entries [2048c, 2048c+2048); thread t adds the entries
+//   2048c+512k+2t and +1 for k = 0..3 in order from 0.0; warp xor-tree
+//   off = 16,8,4,2,1; then warps 0..7 in order.  Chunk sums are combined by the
+//   last block to finish: thread t adds chunks t, t+256, ... in order, same tree.
+// ----------------------------------------------------------------------------
+constexpr int kChunk = 2048;
+constexpr int kRedThreads = 256;
+
+__device__ __forceinline__ double warp_tree_sum(double v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+__device__ __forceinline__ double warp_tree_max(double v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+// all 256 threads call; result valid in thread 0
+__device__ __forceinline__ double block_tree(double v, double *sh /*8*/) {
+  v = warp_tree_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0) {
+    s = sh[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) s = s + sh[w];
+  }
+  return s;
+}
+__device__ __forceinline__ double block_max(double v, double *sh /*8*/) {
+  v = warp_tree_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0) {
+    s = sh[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) s = fmax(s, sh[w]);
+  }
+  return s;
+}
+// true in every thread of exactly one block: the last to arrive
+__device__ __forceinline__ bool last_block(unsigned int *ticket, int *sh_flag) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(ticket, 1u);
+    *sh_flag = (prev == gridDim.x - 1);
+    if (*sh_flag) *ticket = 0;
+  }
+  __syncthreads();
+  const bool last = *sh_flag != 0;
+  if (last) __threadfence();
+  return last;
+}
+__device__ __forceinline__ double final_sum(const double *part, long long nchunks, double *sh) {
+  double acc = 0.0;
+  for (long long c = threadIdx.x; c < nchunks; c += kRedThreads) acc = acc + __ldcg(part + c);
+  return block_tree(acc, sh);
+}
+__device__ __forceinline__ double final_max(const double *part, long long nchunks, double *sh) {
+  double acc = 0.0;
+  for (long long c = threadIdx.x; c < nchunks; c += kRedThreads) acc = fmax(acc, __ldcg(part + c));
+  return block_max(acc, sh);
+}
+
+// scalar epilogues; run by one thread, either inside the last block (1 rank) or
+// in k_scalars after the all-gather of the ranks' partials
+__device__ __forceinline__ void finish_init(State *st, double rd) { st->up = rd; }
+__device__ __forceinline__ void finish_pu(State *st, double pu) {
+  st->pu = pu;
+  st->alpha = st->up / pu;
+}
+__device__ __forceinline__ void finish_update(State *st, double rd, double maxloads, double maxdiff,
+                                              double *ratio_hist) {
+  st->rd_new = rd;
+  st->beta = rd / st->up;
+  st->up = rd;  // p121.f90:99 recomputes r.d next iteration: same operands, same order, same bits
+  st->maxloads = maxloads; st->maxdiff = maxdiff;
+  const double ratio = maxdiff / maxloads;  // checon_par, maths.f90:1060
+  st->ratio = ratio;
+  st->iters = st->iters + 1;
+  if (ratio_hist) ratio_hist[st->iters - 1] = ratio;
+  const int conv = ratio <= st->tol;
+  st->converged = conv;
+  // p = d + p*beta of the converging iteration still runs (p121.f90:102-103); `done` is
+  // raised by k_pupdate after it
+}
+
+// mode: 0 init (up), 1 p.u, 2 update
+__global__ void k_scalars(State *st, const double *all /*nranks x 4*/, int nranks, int mode,
+                          double *ratio_hist) {
+  if (*(volatile const int *)&st->done) return;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s = all[0], m1 = all[1], m2 = all[2];
+  for (int r = 1; r < nranks; ++r) {
+    s = s + all[4 * r];
+    m1 = fmax(m1, all[4 * r + 1]);
+    m2 = fmax(m2, all[4 * r + 2]);
+  }
+  if (mode == 0) finish_init(st, s);
+  else if (mode == 1) finish_pu(st, s);
+  else finish_update(st, s, m1, m2, ratio_hist);
+}
+
+// d = diag*r, p = d, x = 0, up = r.d     (p121.f90:87; p_ext/u_ext slot 0 stays 0)
+__global__ void __launch_bounds__(kRedThreads)
+k_pcg_init(const double *__restrict__ diag, const double *__restrict__ r, double *__restrict__ d,
+           double *__restrict__ p, double *__restrict__ x, long long n, double *part, State *st,
+           int single_rank) {
+  __shared__ double sh[8];
+  __shared__ int flag;
+  const long long nchunks = (n + kChunk - 1) / kChunk;
+  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long i = c * kChunk + 512 * k + 2 * threadIdx.x;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (i + h < n) {
+          const double rr = r[i + h], dd = diag[i + h] * rr;
+          d[i + h] = dd; p[i + h] = dd; x[i + h] = 0.0;
+          acc = acc + rr * dd;
+        }
+    }
+    const double s = block_tree(acc, sh);
+    if (threadIdx.x == 0) part[c] = s;
+  }
+  if (last_block(&st->ticket[0], &flag)) {
+    const double s = final_sum(part, nchunks, sh);
+    if (threadIdx.x == 0) {
+      st->loc[0] = s; st->loc[1] = 0.0; st->loc[2] = 0.0; st->loc[3] = 0.0;
+      if (single_rank) finish_init(st, s);
+    }
+  }
+}
+
+// p123 fixed freedoms: u(j) = p(j)*store(i)   (p123.f90:141-145)
+__global__ void k_fixed_u(const int *__restrict__ fix_slot, const double *__restrict__ store,
+                          const double *__restrict__ p_ext, double *__restrict__ u_ext, int n, const State *st) {
+  if (st && *(volatile const int *)&st->done) return;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) u_ext[fix_slot[i]] = p_ext[fix_slot[i]] * store[i];
+}
+
+// pu = p.u over the owned equations
+__global__ void __launch_bounds__(kRedThreads)
+k_dot(const double *__restrict__ a, const double *__restrict__ b, long long n, double *part, State *st,
+      int single_rank, int mode /*1: p.u epilogue, -1: plain dot into loc[0]*/) {
+  if (mode == 1 && *(volatile const int *)&st->done) return;
+  __shared__ double sh[8];
+  __shared__ int flag;
+  const long long nchunks = (n + kChunk - 1) / kChunk;
+  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long i = c * kChunk + 512 * k + 2 * threadIdx.x;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (i + h < n) acc = acc + a[i + h] * b[i + h];
+    }
+    const double s = block_tree(acc, sh);
+    if (threadIdx.x == 0) part[c] = s;
+  }
+  if (last_block(&st->ticket[1], &flag)) {
+    const double s = final_sum(part, nchunks, sh);
+    if (threadIdx.x == 0) {
+      st->loc[0] = s; st->loc[1] = 0.0; st->loc[2] = 0.0; st->loc[3] = 0.0;
+      if (single_rank && mode == 1) finish_pu(st, s);
+    }
+  }
+}
+
+// xnew = x + p*alpha; r = r - u*alpha; d = diag*r; partial r.d, max|xnew|, max|xnew-x|; x = xnew
+// (p121.f90:100-102 and checon_par maths.f90:1048-1061)
+__global__ void __launch_bounds__(kRedThreads)
+k_pcg_update(const double *__restrict__ diag, const double *__restrict__ p, const double *__restrict__ u,
+             double *__restrict__ x, double *__restrict__ r, double *__restrict__ d, long long n,
+             double *part /*3*nchunks*/, State *st, int single_rank, double *ratio_hist) {
+  if (*(volatile const int *)&st->done) return;
+  __shared__ double sh[8];
+  __shared__ int flag;
+  const double alpha = st->alpha;
+  const long long nchunks = (n + kChunk - 1) / kChunk;
+  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    double acc = 0.0, ml = 0.0, md = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long i = c * kChunk + 512 * k + 2 * threadIdx.x;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (i + h < n) {
+          const double xo = x[i + h];
+          const double xn = xo + p[i + h] * alpha;
+          const double rr = r[i + h] - u[i + h] * alpha;
+          const double dd = diag[i + h] * rr;
+          x[i + h] = xn; r[i + h] = rr; d[i + h] = dd;
+          acc = acc + rr * dd;
+          ml = fmax(ml, fabs(xn));
+          md = fmax(md, fabs(xn - xo));
+        }
+    }
+    const double s = block_tree(acc, sh);
+    const double m1 = block_max(ml, sh);
+    const double m2 = block_max(md, sh);
+    if (threadIdx.x == 0) { part[c] = s; part[nchunks + c] = m1; part[2 * nchunks + c] = m2; }
+  }
+  if (last_block(&st->ticket[2], &flag)) {
+    const double s = final_sum(part, nchunks, sh);
+    const double m1 = final_max(part + nchunks, nchunks, sh);
+    const double m2 = final_max(part + 2 * nchunks, nchunks, sh);
+    if (threadIdx.x == 0) {
+      st->loc[0] = s; st->loc[1] = m1; st->loc[2] = m2; st->loc[3] = 0.0;
+      if (single_rank) finish_update(st, s, m1, m2, ratio_hist);
+    }
+  }
+}
+
+// p = d + p*beta (p121.f90:102), then the exit test of p121.f90:103
+__global__ void k_pupdate(const double *__restrict__ d, double *__restrict__ p, long long n, State *st) {
+  if (*(volatile const int *)&st->done) return;
+  const double beta = st->beta;
+  long long i = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+  const long long stride = 2 * (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    p[i] = d[i] + p[i] * beta;
+    if (i + 1 < n) p[i + 1] = d[i + 1] + p[i + 1] * beta;
+  }
+}
+// separate 1-thread launch after k_pupdate so no block can observe `done` early
+__global__ void k_exit_test(State *st) {
+  if (st->done) return;
+  if (st->converged || st->iters == st->limit) st->done = 1;
+}
+
+// diag = 1/diag (+ penalty on fixed equations first; p123.f90:120-125, p121.f90:86)
+__global__ void k_fixed_penalty(const int *__restrict__ fix_slot, double *__restrict__ diag_ext,
+                                double *__restrict__ store, double penalty, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double v = diag_ext[fix_slot[i]] + penalty;
+    diag_ext[fix_slot[i]] = v;
+    store[i] = v;
+  }
+}
+__global__ void k_invert(double *__restrict__ v, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) v[i] = 1.0 / v[i];
+}
+
+// ----------------------------------------------------------------------------
+// a3-a5: element matrices.  One CTA per element, Gauss points in sequence.
+// Tables (shape-function derivatives at the Gauss points, weights, dee) are
+// computed on the host with the reference's formulas and held in constant memory.
+// ----------------------------------------------------------------------------
+struct ElemTables {
+  double der[8 * 3 * 20];  // [ig][a][m]  = der(a,m) at Gauss point ig   (shape_der)
+  double weights[8];       // sample
+  double dee[36];          // dee(l,k) at [k*6+l]                        (deemat)
+  double kxyz[3];          // p123 conductivities
+  int nip;
+};
+__constant__ ElemTables c_tab;  // single translation unit (device.cu)
+
+// 3x3 determinant and adjugate inverse with the reference's operation order
+// (maths.f90:617-619, 526-547)
+__device__ __forceinline__ double det3(const double *m /*col-major*/) {
+#define A(r, c) m[(c - 1) * 3 + (r - 1)]
+  double det = A(1, 1) * (A(2, 2) * A(3, 3) - A(3, 2) * A(2, 3));
+  det = det - A(1, 2) * (A(2, 1) * A(3, 3) - A(3, 1) * A(2, 3));
+  det = det + A(1, 3) * (A(2, 1) * A(3, 2) - A(3, 1) * A(2, 2));
+  return det;
+}
+__device__ __forceinline__ void inv3(const double *m, double det, double *o) {
+  o[0] = (A(2, 2) * A(3, 3) - A(3, 2) * A(2, 3)) / det;      // (1,1)
+  o[1] = (-(A(2, 1) * A(3, 3)) + A(3, 1) * A(2, 3)) / det;   // (2,1)
+  o[2] = (A(2, 1) * A(3, 2) - A(3, 1) * A(2, 2)) / det;      // (3,1)
+  o[3] = (-(A(1, 2) * A(3, 3)) + A(3, 2) * A(1, 3)) / det;   // (1,2)
+  o[4] = (A(1, 1) * A(3, 3) - A(3, 1) * A(1, 3)) / det;      // (2,2)
+  o[5] = (-(A(1, 1) * A(3, 2)) + A(3, 1) * A(1, 2)) / det;   // (3,2)
+  o[6] = (A(1, 2) * A(2, 3) - A(2, 2) * A(1, 3)) / det;      // (1,3)
+  o[7] = (-(A(1, 1) * A(2, 3)) + A(2, 1) * A(1, 3)) / det;   // (2,3)
+  o[8] = (A(1, 1) * A(2, 2) - A(2, 1) * A(1, 2)) / det;      // (3,3)
+#undef A
+}
+
+// jac = der*coord, det, deriv = jac^-1 * der for Gauss point ig; coord(nod,3) in smem.
+// Leaves deriv(a,m) at s_deriv[m*3+a]; returns det in every thread.
+template <int NOD>
+__device__ __forceinline__ double gauss_point(int ig, const double *s_coord, double *s_jac, double *s_deriv) {
+  const double *der = c_tab.der + ig * 3 * 20;
+  if (threadIdx.x < 9) {
+    const int a = threadIdx.x % 3, b = threadIdx.x / 3;
+    double s = 0.0;
+#pragma unroll
+    for (int m = 0; m < NOD; ++m) s = s + der[a * 20 + m] * s_coord[b * NOD + m];
+    s_jac[b * 3 + a] = s;
+  }
+  __syncthreads();
+  double jac[9], inv[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) jac[q] = s_jac[q];
+  const double det = det3(jac);
+  inv3(jac, det, inv);
+  if (threadIdx.x < 3 * NOD) {
+    const int m = threadIdx.x / 3, a = threadIdx.x - 3 * m;
+    double s = 0.0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) s = s + inv[b * 3 + a] * der[b * 20 + m];
+    s_deriv[m * 3 + a] = s;
+  }
+  __syncthreads();
+  return det;
+}
+
+// elements_1 of p121.f90:56-64.  km(i,j) += (sum_k btd(i,k)*bee(k,j)) * det * w
+template <int NOD, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_form_km_elastic(const double *__restrict__ g_coord, double *__restrict__ km, long long nels) {
+  constexpr int NTOT = 3 * NOD, NENT = NTOT * NTOT, PER = (NENT + THREADS - 1) / THREADS;
+  __shared__ double s_coord[NOD * 3], s_jac[9], s_deriv[NOD * 3];
+  __shared__ double s_bee[6 * NTOT];  // bee(l,c) at [c*6+l]
+  __shared__ double s_btd[6 * NTOT];  // btd(i,k) at [k*NTOT+i]
+  for (long long e = blockIdx.x; e < nels; e += gridDim.x) {
+    __syncthreads();
+    for (int q = threadIdx.x; q < NOD * 3; q += THREADS) s_coord[q] = g_coord[e * NOD * 3 + q];
+    double acc[PER];
+#pragma unroll
+    for (int n = 0; n < PER; ++n) acc[n] = 0.0;
+    __syncthreads();
+    for (int ig = 0; ig < c_tab.nip; ++ig) {
+      const double det = gauss_point<NOD>(ig, s_coord, s_jac, s_deriv);
+      const double wt = c_tab.weights[ig];
+      // beemat (new_library.f90:976-993)
+      for (int c = threadIdx.x; c < NTOT; c += THREADS) {
+        const int m = c / 3, comp = c - 3 * m;
+        const double x = s_deriv[m * 3 + 0], y = s_deriv[m * 3 + 1], z = s_deriv[m * 3 + 2];
+        double b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
+        if (comp == 0) { b0 = x; b3 = y; b5 = z; }
+        else if (comp == 1) { b1 = y; b3 = x; b4 = z; }
+        else { b2 = z; b4 = y; b5 = x; }
+        double *bc = s_bee + c * 6;
+        bc[0] = b0; bc[1] = b1; bc[2] = b2; bc[3] = b3; bc[4] = b4; bc[5] = b5;
+      }
+      __syncthreads();
+      // btd = MATMUL(TRANSPOSE(bee),dee)
+      for (int q = threadIdx.x; q < 6 * NTOT; q += THREADS) {
+        const int k = q / NTOT, i = q - k * NTOT;
+        double s = 0.0;
+#pragma unroll
+        for (int l = 0; l < 6; ++l) s = s + s_bee[i * 6 + l] * c_tab.dee[k * 6 + l];
+        s_btd[k * NTOT + i] = s;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int n = 0; n < PER; ++n) {
+        const int idx = threadIdx.x + n * THREADS;
+        if (idx < NENT) {
+          const int j = idx / NTOT, i = idx - j * NTOT;
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) s = s + s_btd[k * NTOT + i] * s_bee[j * 6 + k];
+          acc[n] = acc[n] + s * det * wt;
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int n = 0; n < PER; ++n) {
+      const int idx = threadIdx.x + n * THREADS;
+      if (idx < NENT) km[e * (long long)NENT + idx] = acc[n];
+    }
+  }
+}
+
+// elements_1 of p123.f90:71-84; 8-node bricks, 64 threads = one per entry
+__global__ void __launch_bounds__(64)
+k_form_kc_laplace(const double *__restrict__ g_coord, double *__restrict__ kc, long long nels) {
+  constexpr int NOD = 8;
+  __shared__ double s_coord[NOD * 3], s_jac[9], s_deriv[NOD * 3];
+  const int j = threadIdx.x / 8, i = threadIdx.x % 8;
+  for (long long e = blockIdx.x; e < nels; e += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x < NOD * 3) s_coord[threadIdx.x] = g_coord[e * NOD * 3 + threadIdx.x];
+    __syncthreads();
+    double kx = 0.0, ky = 0.0, kz = 0.0;
+    for (int ig = 0; ig < c_tab.nip; ++ig) {
+      const double det = gauss_point<NOD>(ig, s_coord, s_jac, s_deriv);
+      const double wt = c_tab.weights[ig];
+      kx = kx + s_deriv[i * 3 + 0] * s_deriv[j * 3 + 0] * det * wt;
+      ky = ky + s_deriv[i * 3 + 1] * s_deriv[j * 3 + 1] * det * wt;
+      kz = kz + s_deriv[i * 3 + 2] * s_deriv[j * 3 + 2] * det * wt;
+      __syncthreads();
+    }
+    kc[e * 64 + threadIdx.x] = kx * c_tab.kxyz[0] + ky * c_tab.kxyz[1] + kz * c_tab.kxyz[2];
+  }
+}
+
+}  // namespace pf

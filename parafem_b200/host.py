@@ -1,0 +1,210 @@
+"""Host-side mirror of the ParaFEM library calls a p121 / p123 driver makes before
+the device path (section B of include/parafem_b200.h, implemented in
+csrc/host.cpp).  numpy arrays hold the Fortran arrays with axes reversed, i.e.
+``g_num_pp(nod, nels_pp)`` is a C-contiguous ``(nels_pp, nod)`` array, so the raw
+memory is exactly what the Fortran driver would pass.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from ._lib import DeckInfo, PfError, c_i64, check, f64, i32, lib, ptr
+
+
+def calc_nels_pp(nels, npes, numpe):
+    """calc_nels_pp, partitioner 1 (gather_scatter.f90:217-238) -> (nels_pp, iel_start)."""
+    a, b = c_i64(), c_i64()
+    lib().pf_calc_nels_pp(nels, npes, numpe, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def calc_neq_pp(neq, npes, numpe):
+    """calc_neq_pp (gather_scatter.f90:319-339) -> (neq_pp, ieq_start)."""
+    a, b = c_i64(), c_i64()
+    lib().pf_calc_neq_pp(neq, npes, numpe, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+@dataclass
+class Problem:
+    """Everything one rank of a p121 / p123 run holds after make_ggl (p121.f90:49)."""
+    program: int
+    nod: int
+    nodof: int
+    nip: int
+    nels: int
+    nn: int
+    nr: int
+    neq: int
+    npes: int
+    numpe: int
+    nels_pp: int
+    iel_start: int
+    neq_pp: int
+    ieq_start: int
+    g_num_pp: np.ndarray      # (nels_pp, nod) int32, S&G node order
+    g_coord_pp: np.ndarray    # (nels_pp, 3, nod) float64
+    g_g_pp: np.ndarray        # (nels_pp, ntot) int32, 0 = restrained
+    nf: np.ndarray            # (nn, nodof) int32
+    r_pp: np.ndarray          # (neq_pp,) starting residual (loads)
+    e: float = 0.0
+    v: float = 0.0
+    kx: float = 0.0
+    ky: float = 0.0
+    kz: float = 0.0
+    tol: float = 1e-5
+    limit: int = 2000
+    nres: int = 0
+    no_f: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))   # fixed eq (global)
+    val_f: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float64))
+    total_load: float = 0.0
+
+    @property
+    def ntot(self):
+        return self.nod * self.nodof
+
+
+def _steer(nn, nodof, rest, g_num_pp, nod):
+    nr = rest.shape[1]
+    nf = np.empty((nn, nodof), np.int32)
+    neq = c_i64()
+    check(lib().pf_form_nf(nn, nodof, nr, ptr(rest), ptr(nf), C.byref(neq)), what="pf_form_nf")
+    nels_pp = g_num_pp.shape[0]
+    g_g = np.empty((nels_pp, nod * nodof), np.int32)
+    check(lib().pf_find_g(nod, nodof, nels_pp, ptr(g_num_pp), ptr(nf), ptr(g_g)), what="pf_find_g")
+    return nf, g_g, neq.value
+
+
+def cube_p121(nxe, nye, nze, nod=20, aa=None, bb=None, cc=None, e=100.0, v=0.3, tol=1e-5,
+              limit=2000, nip=8, npes=1, numpe=1, round_mode=0, distort=0.0, seed=12345):
+    """In-memory p12meshgen cube for p121 (p12meshgen.f90:118-236): this rank's share.
+
+    ``distort`` > 0 perturbs interior node coordinates by up to distort*h (uniform,
+    deterministic per node number) -- not in the reference, kernel parity only.
+    """
+    aa = 10.0 / nxe if aa is None else aa
+    bb = 10.0 / nye if bb is None else bb
+    cc = 10.0 / nze if cc is None else cc
+    L = lib()
+    nn, nr, loaded = c_i64(), c_i64(), c_i64()
+    check(L.pf_p121_sizes(nxe, nye, nze, nod, C.byref(nn), C.byref(nr), C.byref(loaded)), what="pf_p121_sizes")
+    nn, nr, loaded = nn.value, nr.value, loaded.value
+    nels = nxe * nye * nze
+    nels_pp, iel_start = calc_nels_pp(nels, npes, numpe)
+    g_num = np.empty((nels_pp, nod), np.int32)
+    g_coord = np.empty((nels_pp, 3, nod), np.float64)
+    check(L.pf_cube_elements(nxe, nze, nod, aa, bb, cc, iel_start, nels_pp, round_mode, ptr(g_num), ptr(g_coord)),
+          what="pf_cube_elements")
+    rest = np.zeros((4, nr), np.int32)
+    check(L.pf_cube_rest(0, nxe, nye, nze, nod, nr, ptr(rest)), what="pf_cube_rest")
+    if distort > 0.0:
+        g_coord = _distort(g_coord, g_num, rest, nn, distort * min(aa, bb, cc), seed)
+    nf, g_g, neq = _steer(nn, 3, rest, g_num, nod)
+    neq_pp, ieq_start = calc_neq_pp(neq, npes, numpe)
+    node = np.empty(loaded, np.int32)
+    val = np.empty((loaded, 3), np.float64)
+    check(L.pf_p121_loads(nxe, nze, nod, aa, bb, round_mode, ptr(node), ptr(val)), what="pf_p121_loads")
+    r = np.empty(neq_pp, np.float64)
+    check(L.pf_load(3, loaded, ptr(node), ptr(val), ptr(nf), ieq_start, neq_pp, ptr(r)), what="pf_load")
+    return Problem(121, nod, 3, nip, nels, nn, nr, neq, npes, numpe, nels_pp, iel_start, neq_pp, ieq_start,
+                   g_num, g_coord, g_g, nf, r, e=e, v=v, tol=tol, limit=limit,
+                   total_load=float(val[:, 2].sum()))
+
+
+def _distort(g_coord, g_num, rest, nn, amp, seed):
+    """Deterministic per-node jitter; nodes listed in rest (boundary) stay put so BCs hold."""
+    rng = np.random.RandomState(seed)
+    jit = (rng.rand(nn, 3) * 2.0 - 1.0) * amp
+    jit[rest[0] - 1] = 0.0
+    out = g_coord.copy()
+    out += np.transpose(jit[g_num - 1], (0, 2, 1))
+    return out
+
+
+def cube_p123(nxe, nye, nze, aa=None, bb=None, cc=None, kx=2.0, ky=2.0, kz=2.0, tol=1e-5, limit=500,
+              nip=8, npes=1, numpe=1, round_mode=0, source=10.0, fixed=False, fixed_value=100.0):
+    """In-memory p12meshgen box for p123 (p12meshgen.f90:658-701)."""
+    aa = 1.0 / nxe if aa is None else aa
+    bb = 1.0 / nye if bb is None else bb
+    cc = 1.0 / nze if cc is None else cc
+    L = lib()
+    nn, nr, nres = c_i64(), c_i64(), c_i64()
+    check(L.pf_p123_sizes(nxe, nye, nze, C.byref(nn), C.byref(nr), C.byref(nres)), what="pf_p123_sizes")
+    nn, nr, nres = nn.value, nr.value, nres.value
+    nels = nxe * nye * nze
+    nels_pp, iel_start = calc_nels_pp(nels, npes, numpe)
+    g_num = np.empty((nels_pp, 8), np.int32)
+    g_coord = np.empty((nels_pp, 3, 8), np.float64)
+    check(L.pf_cube_elements(nxe, nze, 8, aa, bb, cc, iel_start, nels_pp, round_mode, ptr(g_num), ptr(g_coord)),
+          what="pf_cube_elements")
+    rest = np.zeros((2, nr), np.int32)
+    check(L.pf_cube_rest(1, nxe, nye, nze, 8, nr, ptr(rest)), what="pf_cube_rest")
+    nf, g_g, neq = _steer(nn, 1, rest, g_num, 8)
+    neq_pp, ieq_start = calc_neq_pp(neq, npes, numpe)
+    r = np.zeros(neq_pp, np.float64)
+    no_f = np.zeros(0, np.int32)
+    val_f = np.zeros(0, np.float64)
+    total = 0.0
+    if fixed:
+        # p12meshgen's fixed_freedoms branch (p12meshgen.f90:770-781): freedom nres held at a value
+        if ieq_start <= nres < ieq_start + neq_pp:
+            no_f = np.array([nres], np.int32)
+            val_f = np.array([fixed_value], np.float64)
+    else:
+        # the .lds column is used directly as a global equation number (p123.f90:111-116)
+        if ieq_start <= nres < ieq_start + neq_pp:
+            r[nres - ieq_start] = source
+        total = source
+    return Problem(123, 8, 1, nip, nels, nn, nr, neq, npes, numpe, nels_pp, iel_start, neq_pp, ieq_start,
+                   g_num, g_coord, g_g, nf, r, kx=kx, ky=ky, kz=kz, tol=tol, limit=limit, nres=nres,
+                   no_f=no_f, val_f=val_f, total_load=total)
+
+
+def read_deck_p121(job, npes=1, numpe=1):
+    """read_p121 + read_g_num_pp + abaqus2sg + read_g_coord_pp + read_rest + steering +
+    read_loads + load (p121.f90:28-49, 79-85) for one rank."""
+    L = lib()
+    info = DeckInfo()
+    check(L.pf_read_dat(job.encode(), 121, C.byref(info)), what="pf_read_dat")
+    nod, nn, nels, nr, loaded = info.nod, info.nn, info.nels, info.nr, info.loaded
+    g_coord = np.empty((nn, 3), np.float64)
+    g_num = np.empty((nels, nod), np.int32)
+    check(L.pf_read_d(job.encode(), nn, nels, nod, ptr(g_coord), ptr(g_num)), what="pf_read_d")
+    if info.meshgen == 2:
+        check(L.pf_abaqus2sg(nod, nels, ptr(g_num)), what="pf_abaqus2sg")
+    if info.partitioner != 1:
+        raise PfError("only partitioner 1 (internal) decks are supported")
+    nels_pp, iel_start = calc_nels_pp(nels, npes, numpe)
+    g_num_pp = np.ascontiguousarray(g_num[iel_start - 1:iel_start - 1 + nels_pp])
+    g_coord_pp = np.empty((nels_pp, 3, nod), np.float64)
+    check(L.pf_coords_pp(nod, nels_pp, ptr(g_num_pp), ptr(g_coord), ptr(g_coord_pp)), what="pf_coords_pp")
+    rest = np.zeros((4, nr), np.int32)
+    check(L.pf_read_bnd(job.encode(), nr, 3, ptr(rest)), what="pf_read_bnd")
+    nf, g_g, neq = _steer(nn, 3, rest, g_num_pp, nod)
+    neq_pp, ieq_start = calc_neq_pp(neq, npes, numpe)
+    node = np.empty(loaded, np.int32)
+    val = np.empty((loaded, 3), np.float64)
+    check(L.pf_read_lds(job.encode(), loaded, 3, ptr(node), ptr(val)), what="pf_read_lds")
+    r = np.empty(neq_pp, np.float64)
+    check(L.pf_load(3, loaded, ptr(node), ptr(val), ptr(nf), ieq_start, neq_pp, ptr(r)), what="pf_load")
+    p = Problem(121, nod, 3, info.nip, nels, nn, nr, neq, npes, numpe, nels_pp, iel_start, neq_pp, ieq_start,
+                g_num_pp, g_coord_pp, g_g, nf, r, e=info.e, v=info.v, tol=info.tol, limit=info.limit,
+                total_load=float(val.sum()))
+    p.rest = rest
+    p.g_coord = g_coord
+    return p
+
+
+def make_ggl(prob):
+    """Gather tables of one rank (pf_make_ggl): (ggl_pp, halo_eq, halo_cnt)."""
+    L = lib()
+    nh = c_i64()
+    cnt = np.zeros(prob.npes, np.int64)
+    check(L.pf_make_ggl(prob.ntot, prob.nels_pp, ptr(prob.g_g_pp), prob.neq, prob.npes, prob.numpe,
+                        None, 0, None, ptr(cnt), C.byref(nh)), what="pf_make_ggl(size)")
+    ggl = np.empty_like(prob.g_g_pp)
+    halo = np.empty(max(nh.value, 1), np.int32)
+    check(L.pf_make_ggl(prob.ntot, prob.nels_pp, ptr(prob.g_g_pp), prob.neq, prob.npes, prob.numpe,
+                        ptr(ggl), halo.size, ptr(halo), ptr(cnt), C.byref(nh)), what="pf_make_ggl")
+    return ggl, halo[:nh.value], cnt

@@ -1,0 +1,191 @@
+"""Python mirror of the device API (section A of include/parafem_b200.h).
+
+``Solver`` holds one pf_handle = one rank = one B200.  Every method is a thin
+ctypes call into libparafem_b200.so; there is no PyTorch or CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import PfError, c_i64, check, f64, i32, lib, ptr
+
+
+def nccl_unique_id():
+    """128-byte NCCL id created by rank 0; broadcast it and pass it to every Solver."""
+    buf = np.zeros(128, np.uint8)
+    check(lib().pf_nccl_unique_id(ptr(buf)), what="pf_nccl_unique_id")
+    return buf
+
+
+class Solver:
+    def __init__(self, rank=0, nranks=1, device=0, nccl_id=None):
+        self._h = C.c_void_p()
+        self.rank, self.nranks = rank, nranks
+        idp = ptr(np.ascontiguousarray(nccl_id, np.uint8)) if nccl_id is not None else None
+        check(lib().pf_init(rank, nranks, device, idp, C.byref(self._h)), what="pf_init")
+        self.prob = None
+
+    # -- lifetime ---------------------------------------------------------------
+    def close(self):
+        if self._h:
+            lib().pf_finalize(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        check(rc, self._h, what)
+
+    # -- setup ------------------------------------------------------------------
+    def setup_mesh(self, prob):
+        """pf_setup_mesh from a host.Problem (this rank's g_coord_pp / g_g_pp)."""
+        self.prob = prob
+        self._ck(lib().pf_setup_mesh(self._h, prob.nod, prob.nodof, prob.nip, prob.nels_pp,
+                                     ptr(f64(prob.g_coord_pp)), ptr(i32(prob.g_g_pp)), prob.neq,
+                                     prob.ieq_start, prob.neq_pp), "pf_setup_mesh")
+
+    def form_km_elastic(self, e, v):
+        self._ck(lib().pf_form_km_elastic(self._h, e, v), "pf_form_km_elastic")
+
+    def form_kc_laplace(self, kx, ky, kz):
+        self._ck(lib().pf_form_kc_laplace(self._h, kx, ky, kz), "pf_form_kc_laplace")
+
+    def set_storkm(self, storkm):
+        k = f64(storkm)
+        assert k.size == self.prob.nels_pp * self.prob.ntot ** 2
+        self._ck(lib().pf_set_storkm(self._h, ptr(k)), "pf_set_storkm")
+
+    def get_storkm(self, iel0=0, n=None):
+        n = self.prob.nels_pp - iel0 if n is None else n
+        nt = self.prob.ntot
+        out = np.empty((n, nt, nt))
+        self._ck(lib().pf_get_storkm(self._h, iel0, n, ptr(out)), "pf_get_storkm")
+        return out
+
+    def build_precon(self, no_f=None, penalty=1e20):
+        no_f = np.zeros(0, np.int32) if no_f is None else i32(no_f)
+        self._nfixed = no_f.size
+        self._ck(lib().pf_build_precon(self._h, no_f.size, ptr(no_f) if no_f.size else None, penalty),
+                 "pf_build_precon")
+
+    def diag_precon(self):
+        out = np.empty(self.prob.neq_pp)
+        self._ck(lib().pf_get_diag_precon(self._h, ptr(out)), "pf_get_diag_precon")
+        return out
+
+    def store(self):
+        out = np.empty(self._nfixed)
+        self._ck(lib().pf_get_store(self._h, ptr(out)), "pf_get_store")
+        return out
+
+    # -- solve --------------------------------------------------------------------
+    def pcg_solve(self, r_pp, tol, limit):
+        """p121.f90:87-104 through one C-ABI call with host buffers. -> (xnew_pp, iters, converged)"""
+        r = f64(r_pp)
+        x = np.empty(self.prob.neq_pp)
+        it, cv = C.c_int(), C.c_int()
+        self._ck(lib().pf_pcg_solve(self._h, ptr(r), tol, limit, ptr(x), C.byref(it), C.byref(cv)), "pf_pcg_solve")
+        return x, it.value, bool(cv.value)
+
+    def pcg_load_rhs(self, r_pp):
+        self._ck(lib().pf_pcg_load_rhs(self._h, ptr(f64(r_pp))), "pf_pcg_load_rhs")
+
+    def pcg_run(self, tol, limit):
+        """Device-resident solve. -> (iters, converged, elapsed_ms on the solver stream)"""
+        it, cv, ms = C.c_int(), C.c_int(), C.c_double()
+        self._ck(lib().pf_pcg_run(self._h, tol, limit, C.byref(it), C.byref(cv), C.byref(ms)), "pf_pcg_run")
+        return it.value, bool(cv.value), ms.value
+
+    def pcg_get_x(self):
+        x = np.empty(self.prob.neq_pp)
+        self._ck(lib().pf_pcg_get_x(self._h, ptr(x)), "pf_pcg_get_x")
+        return x
+
+    def ratio_history(self, maxn=100000):
+        out = np.zeros(maxn)
+        n = C.c_int()
+        self._ck(lib().pf_get_ratio_history(self._h, ptr(out), maxn, C.byref(n)), "pf_get_ratio_history")
+        return out[:n.value].copy()
+
+    # -- fine-grained -----------------------------------------------------------------
+    def gather(self, p_pp):
+        out = np.empty((self.prob.nels_pp, self.prob.ntot))
+        self._ck(lib().pf_gather(self._h, ptr(f64(p_pp)), ptr(out)), "pf_gather")
+        return out
+
+    def matvec(self, pmul_pp):
+        out = np.empty((self.prob.nels_pp, self.prob.ntot))
+        self._ck(lib().pf_matvec(self._h, ptr(f64(pmul_pp)), ptr(out)), "pf_matvec")
+        return out
+
+    def scatter(self, utemp_pp):
+        out = np.empty(self.prob.neq_pp)
+        self._ck(lib().pf_scatter(self._h, ptr(f64(utemp_pp)), ptr(out)), "pf_scatter")
+        return out
+
+    def apply(self, p_pp):
+        out = np.empty(self.prob.neq_pp)
+        self._ck(lib().pf_apply(self._h, ptr(f64(p_pp)), ptr(out)), "pf_apply")
+        return out
+
+    def dot(self, a_pp, b_pp):
+        res = C.c_double()
+        self._ck(lib().pf_dot(self._h, ptr(f64(a_pp)), ptr(f64(b_pp)), C.byref(res)), "pf_dot")
+        return res.value
+
+    def norm(self, a_pp):
+        res = C.c_double()
+        self._ck(lib().pf_norm(self._h, ptr(f64(a_pp)), C.byref(res)), "pf_norm")
+        return res.value
+
+    def centroid_stress(self, iel, e, v):
+        out = np.empty(6)
+        self._ck(lib().pf_centroid_stress(self._h, iel, e, v, ptr(out)), "pf_centroid_stress")
+        return out
+
+    # -- measurement -----------------------------------------------------------------
+    def set_profile(self, on):
+        self._ck(lib().pf_set_profile(self._h, int(on)), "pf_set_profile")
+
+    def reset_profile(self):
+        self._ck(lib().pf_reset_profile(self._h), "pf_reset_profile")
+
+    def kernel_ms(self, which):
+        ms, n = C.c_double(), c_i64()
+        self._ck(lib().pf_get_kernel_ms(self._h, which, C.byref(ms), C.byref(n)), "pf_get_kernel_ms")
+        return ms.value, n.value
+
+    def kernel_launches(self):
+        return lib().pf_kernel_launches(self._h)
+
+    def device_info(self):
+        sm, fr, tot = C.c_int(), c_i64(), c_i64()
+        self._ck(lib().pf_device_info(self._h, C.byref(sm), C.byref(fr), C.byref(tot)), "pf_device_info")
+        return sm.value, fr.value, tot.value
+
+
+def setup_problem(solver, prob):
+    """The device part of p121.f90:49-69,86 / p123.f90:57-92,120-125 for one rank."""
+    solver.setup_mesh(prob)
+    if prob.program == 121:
+        solver.form_km_elastic(prob.e, prob.v)
+        solver.build_precon()
+    else:
+        solver.form_kc_laplace(prob.kx, prob.ky, prob.kz)
+        solver.build_precon(prob.no_f, 1e20)
+        if prob.no_f.size:
+            # r_pp(j) = store_pp(i)*val_f(k)   (p123.f90:127-131)
+            st = solver.store()
+            prob.r_pp[prob.no_f - prob.ieq_start] = st * prob.val_f
+    return solver

@@ -1,0 +1,192 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI
+(libparafem_b200.so via ctypes), against the CPU oracle on identical inputs.
+
+Bar: FP64 results EQUAL the oracle's (==, i.e. bit-exact up to the sign of zero) because
+the kernels use the oracle's summation orders and no FMA contraction; north_star's
+tolerance (iteration count +-1, 1e-9 relative L2) is asserted as well, with the number
+written in the test."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from parafem_b200 import host, solver
+
+pytestmark = pytest.mark.gpu
+TOL_L2 = 1e-9        # north_star: converged field within 1e-9 relative L2
+
+
+def rel_l2(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    s = solver.Solver(0, 1, 0)
+    yield s
+    s.close()
+
+
+def km_oracle(p):
+    if p.program == 121:
+        return oracle.form_km_elastic(p.g_coord_pp, p.nod, p.nip, p.e, p.v)
+    return oracle.form_kc_laplace(p.g_coord_pp, p.nip, p.kx, p.ky, p.kz)
+
+
+PROBLEMS = {
+    "tiny_hex20": lambda: host.cube_p121(5, 5, 5, 20, aa=2., bb=2., cc=2., limit=200),
+    "ragged_hex20": lambda: host.cube_p121(5, 3, 4, 20, aa=1., bb=2., cc=.5, limit=400),
+    "distorted_hex20": lambda: host.cube_p121(5, 5, 5, 20, aa=2., bb=2., cc=2., limit=400, distort=0.2),
+    "hex8_elastic": lambda: host.cube_p121(10, 7, 5, 8, aa=1., bb=1., cc=1., limit=400),
+    "hex8_nip1": lambda: host.cube_p121(5, 5, 5, 8, aa=1., bb=1., cc=1., nip=1, limit=50),
+    "p123_box": lambda: host.cube_p123(12, 9, 10, limit=500),
+    "p123_one_element_tile_tail": lambda: host.cube_p123(5, 5, 5, limit=200),
+}
+
+
+@pytest.mark.parametrize("name", list(PROBLEMS))
+def test_element_matrices_equal_oracle(gpu, name):
+    """pf_form_km_elastic / pf_form_kc_laplace == elements_1 of p121.f90:56-64 / p123.f90:71-84."""
+    p = PROBLEMS[name]()
+    solver.setup_problem(gpu, p)
+    km = gpu.get_storkm()
+    ref = km_oracle(p)
+    assert km.shape == ref.shape
+    assert np.array_equal(km, ref)
+    gpu.build_precon()
+    r = oracle.pcg(ref, p.g_g_pp, p.neq, p.r_pp, 1.0, 1, npes=1, red_mode=1)
+    assert np.array_equal(gpu.diag_precon(), r["diag"])
+
+
+@pytest.mark.parametrize("name", list(PROBLEMS))
+def test_gather_matvec_scatter_dot_equal_oracle(gpu, name):
+    p = PROBLEMS[name]()
+    solver.setup_problem(gpu, p)
+    rng = np.random.RandomState(7)
+    pv = rng.randn(p.neq)
+    km = km_oracle(p)
+    pmul = gpu.gather(pv)
+    assert np.array_equal(pmul, oracle.gather(p.g_g_pp, pv))           # gather_scatter.f90:663-665
+    ut = gpu.matvec(pmul)
+    ut_ref = oracle.matvec(km, pmul)
+    assert np.array_equal(ut, ut_ref)                                   # p121.f90:93-97
+    u = gpu.scatter(ut)
+    u_ref = oracle.scatter(p.g_g_pp, ut_ref, p.neq)
+    assert np.array_equal(u, u_ref)                                     # gather_scatter.f90:758-773
+    assert np.array_equal(gpu.apply(pv), u_ref)                         # fused path the solver runs
+    q = rng.randn(p.neq)
+    assert gpu.dot(pv, q) == oracle.dot_blocked(pv, q)                  # maths.f90:210-214, blocked order
+    assert gpu.norm(pv) == np.sqrt(oracle.dot_blocked(pv, pv))
+
+
+def test_operator_properties(gpu):
+    """Size-independent properties of u = A p: linearity (exact for power-of-two scaling),
+    symmetry p.Aq == q.Ap to rounding, rigid-body translations in the null space of the
+    unconstrained rows."""
+    p = host.cube_p121(8, 8, 8, 20, aa=1.25, bb=1.25, cc=1.25)
+    solver.setup_problem(gpu, p)
+    rng = np.random.RandomState(3)
+    a, b = rng.randn(p.neq), rng.randn(p.neq)
+    Aa, Ab = gpu.apply(a), gpu.apply(b)
+    assert np.array_equal(gpu.apply(4.0 * a), 4.0 * Aa)
+    assert rel_l2(gpu.apply(a + b), Aa + Ab) < 1e-13
+    assert abs(np.dot(b, Aa) - np.dot(a, Ab)) < 1e-11 * np.abs(np.dot(b, Aa))
+    assert np.array_equal(gpu.apply(np.zeros(p.neq)), np.zeros(p.neq))
+
+
+@pytest.mark.parametrize("name", ["tiny_hex20", "ragged_hex20", "distorted_hex20", "hex8_elastic", "p123_box"])
+def test_pcg_equals_oracle(gpu, name):
+    p = PROBLEMS[name]()
+    solver.setup_problem(gpu, p)
+    x, iters, conv = gpu.pcg_solve(p.r_pp, p.tol, p.limit)
+    ref = oracle.pcg(km_oracle(p), p.g_g_pp, p.neq, p.r_pp, p.tol, p.limit, npes=1, red_mode=1)
+    assert conv == ref["converged"]
+    assert abs(iters - ref["iters"]) <= 1 and iters == ref["iters"]      # north_star: +-1; achieved: equal
+    assert rel_l2(x, ref["x"]) <= TOL_L2
+    assert np.array_equal(x, ref["x"])
+    assert np.array_equal(gpu.ratio_history(), ref["ratio"])             # checon_par trajectory, every iteration
+
+
+def test_pcg_limit_exit(gpu):
+    """IF(converged .OR. iters==limit) EXIT (p121.f90:103): limit reached without convergence."""
+    p = PROBLEMS["tiny_hex20"]()
+    solver.setup_problem(gpu, p)
+    x, iters, conv = gpu.pcg_solve(p.r_pp, 1e-30, 13)
+    ref = oracle.pcg(km_oracle(p), p.g_g_pp, p.neq, p.r_pp, 1e-30, 13, npes=1, red_mode=1)
+    assert (iters, conv) == (13, False) == (ref["iters"], ref["converged"])
+    assert np.array_equal(x, ref["x"])
+
+
+def test_p123_fixed_freedom(gpu):
+    """penalty path of p123.f90:120-131,141-145."""
+    p = host.cube_p123(8, 8, 8, fixed=True, limit=500)
+    r0 = p.r_pp.copy()
+    solver.setup_problem(gpu, p)
+    x, iters, conv = gpu.pcg_solve(p.r_pp, p.tol, p.limit)
+    kc = km_oracle(p)
+    ref = oracle.pcg(kc, p.g_g_pp, p.neq, r0, p.tol, p.limit, npes=1, red_mode=1, no_f=p.no_f, val_f=p.val_f)
+    assert iters == ref["iters"] and conv
+    assert np.array_equal(x, ref["x"])
+    assert abs(x[p.nres - 1] - 100.0) < 1e-6                              # the fixed freedom holds its value
+
+
+def test_xx3_tiny_deck_golden(gpu, tiny, golden):
+    """The reference's own tiny deck through the device path: 79 iterations (xx3-tiny.res) and
+    the 756x3 golden displacements (xx3-tiny.dis, 5 significant digits)."""
+    solver.setup_problem(gpu, tiny)
+    x, iters, conv = gpu.pcg_solve(tiny.r_pp, tiny.tol, tiny.limit)
+    gold = int(re.search(r"Number of PCG iterations\s+(\d+)", open(os.path.join(golden, "xx3-tiny.res")).read()).group(1))
+    assert conv and abs(iters - gold) <= 1
+    dis = np.loadtxt(os.path.join(golden, "xx3-tiny.dis"), skiprows=2)[:, 1:]
+    u = np.zeros((tiny.nn, 3))
+    m = tiny.nf > 0
+    u[m] = x[tiny.nf[m] - 1]
+    assert np.abs(u - dis).max() < 2e-5
+    ref = oracle.pcg(oracle.form_km_elastic(tiny.g_coord_pp, 20, 8, tiny.e, tiny.v), tiny.g_g_pp, tiny.neq, tiny.r_pp,
+                     tiny.tol, tiny.limit, npes=1, red_mode=1)
+    assert iters == ref["iters"] and np.array_equal(x, ref["x"])
+
+
+def test_p121_demo_golden(gpu, demo, golden):
+    """BASELINE config A (p121 demo, 8000 hex20, 98 360 equations): golden .res lines and the
+    EnSight displacement field, plus equality with the oracle."""
+    solver.setup_problem(gpu, demo)
+    x, iters, conv = gpu.pcg_solve(demo.r_pp, demo.tol, demo.limit)
+    assert conv and abs(iters - 295) <= 2                                 # p121_demo.res: 295
+    assert abs(x[0] + 0.8571) < 5e-5                                      # "central nodal displacement"
+    sig = gpu.centroid_stress(0, demo.e, demo.v)
+    gold_sig = np.array([-0.1572E+02, -0.1572E+02, -0.2486E+02, 0.2659E-01, 0.7671E-01, 0.7671E-01])
+    assert np.abs(sig[:3] - gold_sig[:3]).max() < 5e-3 and np.abs(sig[3:] - gold_sig[3:]).max() < 2e-4
+    displ = np.load(os.path.join(golden, "p121_demo_displ.npz"))["displ"].astype(np.float64)
+    u = np.zeros((demo.nn, 3))
+    m = demo.nf > 0
+    u[m] = x[demo.nf[m] - 1]
+    assert np.abs(u - displ).max() < 1e-4
+    km = oracle.form_km_elastic(demo.g_coord_pp, 20, 8, demo.e, demo.v)
+    ref = oracle.pcg(km, demo.g_g_pp, demo.neq, demo.r_pp, demo.tol, demo.limit, npes=1, red_mode=1)
+    assert iters == ref["iters"] and np.array_equal(x, ref["x"])
+    g0 = demo.g_g_pp[0]
+    eld = np.where(g0 > 0, x[np.maximum(g0, 1) - 1], 0.0)
+    assert np.allclose(sig, oracle.centroid_stress(20, demo.g_coord_pp[0], eld, demo.e, demo.v), rtol=0, atol=1e-12)
+
+
+def test_tight_tolerance_vs_sequential_reference_order(gpu):
+    """Against the oracle in its *sequential* reduction order (a different legal summation
+    order): with the solve driven to tol 1e-13 both land on the same solution within 1e-9."""
+    p = PROBLEMS["tiny_hex20"]()
+    solver.setup_problem(gpu, p)
+    x, iters, conv = gpu.pcg_solve(p.r_pp, 1e-13, 2000)
+    ref = oracle.pcg(km_oracle(p), p.g_g_pp, p.neq, p.r_pp, 1e-13, 2000, npes=4, red_mode=0)
+    assert conv and ref["converged"]
+    assert rel_l2(x, ref["x"]) <= TOL_L2
+
+
+def test_errors_are_codes_not_exits(gpu):
+    from parafem_b200 import PfError
+    s = solver.Solver(0, 1, 0)
+    with pytest.raises(PfError):
+        s.prob = PROBLEMS["tiny_hex20"]()
+        s.build_precon()          # no mesh yet -> status > 0 + message, never exit()
+    s.close()
