@@ -1,0 +1,87 @@
+"""Multi-rank parity worker, launched by torchrun (one process per GPU) from
+tests/test_gpu_multirank.py:  N-GPU solve through the C-ABI == the oracle emulating the same
+N ranks (same partition, same rank-ordered partial sums, same blocked reductions)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import oracle  # noqa: E402
+from parafem_b200 import host, solver  # noqa: E402
+
+
+def problem(name, npes, numpe):
+    if name == "hex20":
+        return host.cube_p121(6, 7, 5, 20, aa=1., bb=1., cc=1., limit=500, npes=npes, numpe=numpe)
+    if name == "hex20_thin":   # element and equation cuts badly misaligned -> +-2 neighbours
+        return host.cube_p121(5, 9, 2, 20, aa=1., bb=.5, cc=1., limit=500, npes=npes, numpe=numpe)
+    if name == "hex8":
+        return host.cube_p121(10, 9, 6, 8, aa=1., bb=1., cc=1., limit=500, npes=npes, numpe=numpe)
+    if name == "p123":
+        return host.cube_p123(9, 11, 8, limit=500, npes=npes, numpe=numpe)
+    if name == "p123_fixed":
+        return host.cube_p123(9, 11, 8, limit=500, npes=npes, numpe=numpe, fixed=True)
+    raise KeyError(name)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+    idt = torch.from_numpy(solver.nccl_unique_id().copy()) if rank == 0 else torch.zeros(128, dtype=torch.uint8)
+    dist.broadcast(idt, src=0)
+    s = solver.Solver(rank, world, local, idt.numpy())
+    failures = []
+    for name in sys.argv[1:]:
+        p = problem(name, world, rank + 1)
+        full = problem(name, 1, 1)
+        r0 = p.r_pp.copy()
+        solver.setup_problem(s, p)
+        lo = p.ieq_start - 1
+        # operator pieces
+        rng = np.random.RandomState(11)
+        pv = rng.randn(p.neq)
+        qv = rng.randn(p.neq)
+        km = (oracle.form_km_elastic(full.g_coord_pp, full.nod, full.nip, full.e, full.v) if p.program == 121
+              else oracle.form_kc_laplace(full.g_coord_pp, full.nip, full.kx, full.ky, full.kz))
+        pm_ref = oracle.gather(full.g_g_pp, pv)
+        e0 = p.iel_start - 1
+        ok_g = np.array_equal(s.gather(pv[lo:lo + p.neq_pp]), pm_ref[e0:e0 + p.nels_pp])
+        u_ref = oracle.scatter(full.g_g_pp, oracle.matvec(km, pm_ref), p.neq, npes=world)
+        s.nfixed_saved = None
+        u = s.apply(pv[lo:lo + p.neq_pp])
+        if p.no_f.size:   # fixed freedom rows are overridden by u = p*store in the solver path
+            mask = np.ones(p.neq_pp, bool); mask[p.no_f - p.ieq_start] = False
+            ok_u = np.array_equal(u[mask], u_ref[lo:lo + p.neq_pp][mask])
+        else:
+            ok_u = np.array_equal(u, u_ref[lo:lo + p.neq_pp])
+        ok_d = s.dot(pv[lo:lo + p.neq_pp], qv[lo:lo + p.neq_pp]) == oracle.dot_ranks(pv, qv, npes=world, red_mode=1)
+        # full solve
+        x, iters, conv = s.pcg_solve(p.r_pp, p.tol, p.limit)
+        no_f = full.no_f if full.no_f.size else None
+        ref = oracle.pcg(km, full.g_g_pp, p.neq, full.r_pp if no_f is None else np.zeros(p.neq), p.tol, p.limit,
+                         npes=world, red_mode=1, no_f=no_f, val_f=full.val_f if no_f is not None else None)
+        ok_x = np.array_equal(x, ref["x"][lo:lo + p.neq_pp])
+        ok_i = iters == ref["iters"] and conv == ref["converged"]
+        rel = np.linalg.norm(x - ref["x"][lo:lo + p.neq_pp]) / max(np.linalg.norm(ref["x"][lo:lo + p.neq_pp]), 1e-300)
+        line = f"[rank {rank}] {name}: gather={ok_g} apply={ok_u} dot={ok_d} iters={iters}/{ref['iters']} x_equal={ok_x} rel={rel:.2e}"
+        print(line, flush=True)
+        if not (ok_g and ok_u and ok_d and ok_x and ok_i):
+            failures.append(line)
+    s.close()
+    flag = torch.tensor([len(failures)], dtype=torch.int64)
+    dist.all_reduce(flag)
+    dist.destroy_process_group()
+    if flag.item():
+        sys.exit(1)
+    if rank == 0:
+        print("MRANK_OK", flush=True)
+
+
+if __name__ == "__main__":
+    main()

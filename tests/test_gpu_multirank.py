@@ -1,0 +1,29 @@
+"""N-GPU parity (needs >= 2 visible B200s; skipped otherwise): torchrun launches
+tests/mrank_worker.py, one process per GPU, NCCL halo exchange inside the library."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def ngpus():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).stdout
+        return sum(1 for l in out.splitlines() if l.startswith("GPU "))
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_multirank_equals_oracle(n):
+    if ngpus() < n:
+        pytest.skip(f"needs {n} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+           "127.0.0.1", "--master-port", str(29500 + n), os.path.join(ROOT, "tests", "mrank_worker.py"),
+           "hex20", "hex20_thin", "hex8", "p123", "p123_fixed"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert res.returncode == 0 and "MRANK_OK" in res.stdout, res.stdout[-4000:] + res.stderr[-4000:]
