@@ -1,0 +1,73 @@
+"""p121 / p123 program flow (p121.f90, p123.f90) on top of host.py + solver.py.
+
+`run(prob, solver)` performs, for one rank, what the Fortran driver does between make_ggl and
+the output section, and returns the quantities the reference prints to <job>.res; `write_res`
+emits those lines in the reference's formats (p121.f90:72-76,83,106-109,115,121,139).
+"""
+import time
+
+import numpy as np
+
+from . import solver as _solver
+
+
+def _fe(x, w=12, d=4):
+    """Fortran Ew.d: 0.dddd E+xx"""
+    if x == 0.0:
+        s = "0." + "0" * d + "E+00"
+    else:
+        e = int(np.floor(np.log10(abs(x)))) + 1
+        m = x / 10.0 ** e
+        if abs(round(m, d)) >= 1.0:
+            m /= 10.0
+            e += 1
+        s = f"{m:.{d}f}E{e:+03d}"
+        if s.startswith("-0."):
+            s = "-0." + s[3:]
+    return s.rjust(w)
+
+
+def run(prob, s):
+    """-> dict(iters, converged, x, solve_s, setup_s, sigma, total_load)."""
+    t0 = time.time()
+    _solver.setup_problem(s, prob)
+    t_setup = time.time() - t0
+    t1 = time.time()
+    x, iters, conv = s.pcg_solve(prob.r_pp, prob.tol, prob.limit)
+    t_solve = time.time() - t1
+    out = dict(iters=iters, converged=conv, x=x, solve_s=t_solve, setup_s=t_setup, total_load=prob.total_load)
+    if prob.program == 121:
+        out["sigma"] = s.centroid_stress(0, prob.e, prob.v) if prob.numpe == 1 else None
+    return out
+
+
+def write_res(path, prob, res, t_read=0.0, t_total=0.0):
+    """<job>.res as rank 1 writes it."""
+    with open(path, "w") as f:
+        if prob.program == 121:
+            f.write(f"This job ran on {prob.npes:7d} processes\n")
+            f.write(f"There are {prob.nn:12d} nodes{prob.nr:12d} restrained and {prob.neq:12d} equations\n")
+            f.write(f"Time to read input is:{t_read:10.4f}\n")
+            f.write(f"Time after setup is:{t_read + res['setup_s']:10.4f}\n")
+            f.write(f"The total load is:{_fe(res['total_load'])}\n")
+            f.write(f"The number of iterations to convergence was {res['iters']:6d}\n")
+            f.write(f"Time to solve equations was  :{res['solve_s']:10.4f}\n")
+            f.write(f"The central nodal displacement is :{_fe(res['x'][0])}\n")
+            if res.get("sigma") is not None:
+                f.write("The Centroid point stresses for element 1 are\n")
+                f.write(f"Point {1:5d}\n")
+                f.write("".join(_fe(v) for v in res["sigma"]) + "\n")
+            f.write(f"This analysis took  :{t_total:10.4f}\n")
+        else:
+            f.write(f"This job ran on {prob.npes:5d}  processes\n")
+            f.write(f"There are {prob.nn:12d} nodes{prob.nr:12d} restrained and   {prob.neq:12d} equations\n")
+            f.write(f"Time after setup is {res['setup_s']:10.4f}\n")
+            f.write(f"The number of iterations to convergence was {res['iters']:5d}\n")
+            f.write(f"The total load is {_fe(res['total_load'])}\n")
+            f.write("The potentials are:\n Freedom       Potential\n")
+            lo = prob.ieq_start
+            for i in range(4):
+                q = prob.nres + i
+                if lo <= q < lo + prob.neq_pp:
+                    f.write(f"{q:8d}     {_fe(res['x'][q - lo])}\n")
+            f.write(f"Time spent in the solver was {res['solve_s']:10.4f}\n")

@@ -1,0 +1,68 @@
+"""The host drivers above the C-ABI (C++ p121_b200, Python driver.py) reproduce the text lines
+the reference's own regression test greps from <job>.res
+(programs/5th_ed/p121/test.sh:7-35 with the patterns in programs/5th_ed/p121/tests:24-29)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from parafem_b200 import driver, host, solver
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def golden_lines(golden):
+    return open(os.path.join(golden, "p121_demo.res")).read().splitlines()
+
+
+def test_cpp_driver_on_demo_cube(golden, tmp_path):
+    exe = os.path.join(ROOT, "parafem_b200", "p121_b200")
+    res = subprocess.run([exe, "--cube", "20", "20"], capture_output=True, text=True, cwd=tmp_path, timeout=300)
+    assert res.returncode == 0, res.stderr
+    out = res.stdout.splitlines()
+    gold = golden_lines(golden)
+    # identical text lines, as test.sh requires
+    assert gold[1] in out                                   # "There are 35721 nodes 6081 restrained and 98360 equations"
+    assert gold[4] in out                                   # "The total load is: -0.1000E+03"
+    assert gold[7] in out                                   # "The central nodal displacement is : -0.8571E+00"
+    it = int(re.search(r"iterations to convergence was\s+(\d+)", res.stdout).group(1))
+    assert abs(it - 295) <= 2                                # golden 295; see DESIGN.md section 2
+    sig = [float(v) for v in out[out.index("Point     1") + 1].split()]
+    gold_sig = [float(v) for v in gold[10].split()]
+    assert all(abs(a - b) < 6e-3 for a, b in zip(sig[:3], gold_sig[:3]))
+
+
+def test_cpp_driver_reads_the_tiny_deck(golden, tmp_path):
+    exe = os.path.join(ROOT, "parafem_b200", "p121_b200")
+    res = subprocess.run([exe, os.path.join(golden, "xx3-tiny")], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    assert "restrained and         1640 equations" in res.stdout
+    it = int(re.search(r"iterations to convergence was\s+(\d+)", res.stdout).group(1))
+    assert abs(it - 79) <= 1
+    assert "The total load is: -0.1000E+03" in res.stdout
+    os.remove(os.path.join(golden, "xx3-tiny.b200.res"))
+
+
+def test_python_driver_res_file(golden, tmp_path, demo):
+    with solver.Solver(0, 1, 0) as s:
+        res = driver.run(demo, s)
+    path = tmp_path / "p121_demo.res"
+    driver.write_res(path, demo, res)
+    out = open(path).read().splitlines()
+    gold = golden_lines(golden)
+    for k in (1, 4, 7):
+        assert gold[k] in out, (gold[k], out)
+    assert abs(res["iters"] - 295) <= 2
+
+
+def test_python_driver_p123(tmp_path):
+    p = host.cube_p123(10, 10, 10)
+    with solver.Solver(0, 1, 0) as s:
+        res = driver.run(p, s)
+    path = tmp_path / "p123.res"
+    driver.write_res(path, p, res)
+    txt = open(path).read()
+    assert "The total load is   0.1000E+02" in txt             # p123.res line format
+    assert res["converged"]

@@ -1,0 +1,110 @@
+"""Host-side logic (section B of the C-ABI): partition arithmetic, mesh generators, steering,
+deck readers, gather tables.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from parafem_b200 import host
+
+
+@pytest.mark.parametrize("n,npes", [(8000, 1), (8000, 3), (98360, 7), (5, 8), (1953125, 8)])
+def test_partition_matches_reference_formula(n, npes):
+    """calc_nels_pp / calc_neq_pp (gather_scatter.f90:217-238, 319-339): host.cpp's single
+    even_split against the oracle's literal restatement; ranges tile [1, n]."""
+    import ctypes as C
+    nxt = 1
+    for numpe in range(1, npes + 1):
+        cnt, start = host.calc_nels_pp(n, npes, numpe)
+        a, b = C.c_int64(), C.c_int64()
+        oracle.lib().orc_partition(n, npes, numpe, C.byref(a), C.byref(b))
+        assert (cnt, start) == (a.value, b.value) == host.calc_neq_pp(n, npes, numpe)
+        assert start == nxt
+        nxt += cnt
+    assert nxt == n + 1
+
+
+def test_hex20_steering_equals_find_g3_on_generated_cube():
+    p = host.cube_p121(4, 3, 5, 20, aa=1., bb=1., cc=1.)
+    import ctypes as C
+    from parafem_b200._lib import lib, ptr
+    rest = np.zeros((4, p.nr), np.int32)
+    assert lib().pf_cube_rest(0, 4, 3, 5, 20, p.nr, ptr(rest)) == 0
+    assert np.all(np.diff(rest[0]) > 0)                    # ascending nodes: find_g3's binary search needs it
+    assert np.array_equal(oracle.find_g3(p.g_num_pp, rest), p.g_g_pp)
+
+
+def test_hex8_steering_equals_find_g3():
+    p = host.cube_p121(6, 4, 5, 8, aa=1., bb=1., cc=1.)
+    from parafem_b200._lib import lib, ptr
+    rest = np.zeros((4, p.nr), np.int32)
+    assert lib().pf_cube_rest(0, 6, 4, 5, 8, p.nr, ptr(rest)) == 0
+    assert np.array_equal(oracle.find_g3(p.g_num_pp, rest), p.g_g_pp)
+
+
+def test_p121_total_load_is_minus_100():
+    """load_p121 scaling (p12meshgen.f90:176-177, 218-219): 'The total load is: -0.1000E+03'."""
+    for nod in (20, 8):
+        for n in (5, 10, 20):
+            p = host.cube_p121(n, n, n, nod)
+            assert abs(p.total_load + 100.0) < 1e-9
+            assert abs(p.r_pp.sum() + 100.0) < 1e-9
+
+
+def test_tiny_mg_equals_xx3_tiny_deck(tiny, golden):
+    """p121_tiny.mg (5^3, aa=2) generated in memory == the shipped xx3-tiny deck's connectivity
+    and steering (the .d file lists nodes in its own coordinate frame)."""
+    p = host.cube_p121(5, 5, 5, 20, aa=2., bb=2., cc=2.)
+    assert (p.nn, p.nr, p.neq) == (tiny.nn, tiny.nr, tiny.neq)
+    assert np.array_equal(p.g_num_pp, tiny.g_num_pp)
+    assert np.array_equal(p.g_g_pp, tiny.g_g_pp)
+
+
+def test_slices_of_a_partitioned_cube_tile_the_serial_cube():
+    full = host.cube_p121(6, 5, 4, 20)
+    parts = [host.cube_p121(6, 5, 4, 20, npes=3, numpe=k) for k in (1, 2, 3)]
+    assert np.array_equal(np.concatenate([q.g_g_pp for q in parts]), full.g_g_pp)
+    assert np.array_equal(np.concatenate([q.g_coord_pp for q in parts]), full.g_coord_pp)
+    assert np.array_equal(np.concatenate([q.r_pp for q in parts]), full.r_pp)
+
+
+def test_make_ggl_single_rank_is_identity_plus_dump_slot():
+    p = host.cube_p121(4, 4, 4, 20)
+    ggl, halo, cnt = host.make_ggl(p)
+    assert halo.size == 0 and cnt.sum() == 0
+    assert np.array_equal(ggl, p.g_g_pp)                   # slot = equation number, 0 = restrained
+
+
+def test_make_ggl_multi_rank_tables():
+    npes = 4
+    full = host.cube_p121(5, 8, 3, 20)
+    for numpe in range(1, npes + 1):
+        p = host.cube_p121(5, 8, 3, 20, npes=npes, numpe=numpe)
+        ggl, halo, cnt = host.make_ggl(p)
+        lo, hi = p.ieq_start, p.ieq_start + p.neq_pp
+        g = p.g_g_pp
+        own = (g >= lo) & (g < hi)
+        assert np.array_equal(ggl[own], g[own] - lo + 1)
+        assert np.all(ggl[g == 0] == 0)
+        rem = (g != 0) & ~own
+        assert np.array_equal(halo[ggl[rem] - p.neq_pp - 1], g[rem])
+        assert np.all(np.diff(halo) > 0) and cnt[numpe - 1] == 0 and cnt.sum() == halo.size
+        # owner of each halo equation from the closed form
+        owners = np.array([next(r for r in range(1, npes + 1)
+                                if host.calc_neq_pp(full.neq, npes, r)[1] <= q < sum(host.calc_neq_pp(full.neq, npes, r)))
+                           for q in halo])
+        assert np.array_equal(np.bincount(owners - 1, minlength=npes), cnt)
+
+
+def test_deck_reader_roundtrip(tmp_path, tiny, golden):
+    """read_p121-family readers on the shipped tiny deck: sizes from the .dat, Abaqus->S&G
+    permutation applied, loads placed on z freedoms."""
+    assert (tiny.nels, tiny.nn, tiny.nr, tiny.nod, tiny.nip) == (125, 756, 396, 20, 8)
+    assert (tiny.e, tiny.v, tiny.tol, tiny.limit) == (100.0, 0.3, 1e-5, 200)
+    assert np.count_nonzero(tiny.r_pp) == 8
+    # S&G ordering puts the 8 corner nodes at local positions 1,3,5,7,13,15,17,19: their
+    # coordinates span the element's bounding box
+    c = tiny.g_coord_pp[0]
+    corners = c[:, [0, 2, 4, 6, 12, 14, 16, 18]]
+    assert np.allclose(corners.min(axis=1), c.min(axis=1)) and np.allclose(corners.max(axis=1), c.max(axis=1))

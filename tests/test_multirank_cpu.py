@@ -1,0 +1,128 @@
+"""N>1 host logic on CPU: two gloo processes run the halo protocol of device.cu (tables from
+pf_make_ggl, wanted-list exchange, forward exchange, reverse exchange with owner-first then
+ascending-rank accumulation, all-gather + rank-ordered scalar sum) in numpy and must reproduce
+the serial oracle's emulated-rank results exactly."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import oracle
+    from parafem_b200 import host
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = host.cube_p121(5, 6, 4, 20, aa=1., bb=1., cc=1.)
+        p = host.cube_p121(5, 6, 4, 20, aa=1., bb=1., cc=1., npes=world, numpe=rank + 1)
+        ggl, halo, get_cnt = host.make_ggl(p)
+        # counts matrix, then the wanted equation lists (pf_setup_mesh does this over NCCL)
+        cnts = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(cnts, torch.from_numpy(get_cnt.copy()))
+        put_cnt = np.array([int(cnts[r][rank]) for r in range(world)])
+        get_off = np.concatenate([[0], np.cumsum(get_cnt)])
+        put_off = np.concatenate([[0], np.cumsum(put_cnt)])
+        reqs, asked = [], [None] * world
+        for r in range(world):
+            if r == rank:
+                continue
+            if get_cnt[r]:
+                reqs.append(dist.isend(torch.from_numpy(halo[get_off[r]:get_off[r + 1]].copy()), r))
+            if put_cnt[r]:
+                asked[r] = torch.zeros(int(put_cnt[r]), dtype=torch.int32)
+                reqs.append(dist.irecv(asked[r], r))
+        for w in reqs:
+            w.wait()
+        put_slot = [None if a is None else a.numpy().astype(np.int64) - p.ieq_start + 1 for a in asked]
+
+        km = oracle.form_km_elastic(full.g_coord_pp, 20, 8, full.e, full.v)
+        rng = np.random.RandomState(5)
+        pv = rng.randn(full.neq)
+        lo = p.ieq_start - 1
+        # forward exchange -> p_ext, then gather
+        p_ext = np.zeros(1 + p.neq_pp + halo.size)
+        p_ext[1:1 + p.neq_pp] = pv[lo:lo + p.neq_pp]
+        reqs, bufs = [], {}
+        for r in range(world):
+            if r == rank:
+                continue
+            if put_cnt[r]:
+                reqs.append(dist.isend(torch.from_numpy(p_ext[put_slot[r]].copy()), r))
+            if get_cnt[r]:
+                bufs[r] = torch.zeros(int(get_cnt[r]), dtype=torch.float64)
+                reqs.append(dist.irecv(bufs[r], r))
+        for w in reqs:
+            w.wait()
+        for r, b in bufs.items():
+            p_ext[1 + p.neq_pp + get_off[r]:1 + p.neq_pp + get_off[r + 1]] = b.numpy()
+        pmul = p_ext[ggl]
+        e0 = p.iel_start - 1
+        ok_gather = np.array_equal(pmul, oracle.gather(full.g_g_pp, pv)[e0:e0 + p.nels_pp])
+        # local mat-vec + slot-centric scatter in ascending element order
+        ut = oracle.matvec(km[e0:e0 + p.nels_pp], pmul)
+        u_ext = np.zeros_like(p_ext)
+        for e in range(p.nels_pp):                       # ascending element order
+            for k in range(p.ntot):
+                if ggl[e, k]:
+                    u_ext[ggl[e, k]] += ut[e, k]
+        # reverse exchange; owner adds after its own partial sum, sources ascending
+        reqs, bufs = [], {}
+        for r in range(world):
+            if r == rank:
+                continue
+            if get_cnt[r]:
+                reqs.append(dist.isend(torch.from_numpy(u_ext[1 + p.neq_pp + get_off[r]:1 + p.neq_pp + get_off[r + 1]].copy()), r))
+            if put_cnt[r]:
+                bufs[r] = torch.zeros(int(put_cnt[r]), dtype=torch.float64)
+                reqs.append(dist.irecv(bufs[r], r))
+        for w in reqs:
+            w.wait()
+        for r in sorted(bufs):
+            np.add.at(u_ext, put_slot[r], bufs[r].numpy())
+        u_ref = oracle.scatter(full.g_g_pp, oracle.matvec(km, oracle.gather(full.g_g_pp, pv)), full.neq, npes=world)
+        ok_scatter = np.array_equal(u_ext[1:1 + p.neq_pp], u_ref[lo:lo + p.neq_pp])
+        # dot: blocked local partial, all-gather, ranks ascending
+        part = torch.tensor([oracle.dot_blocked(pv[lo:lo + p.neq_pp], u_ref[lo:lo + p.neq_pp])], dtype=torch.float64)
+        parts = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts, part)
+        s = float(parts[0])
+        for r in range(1, world):
+            s = s + float(parts[r])
+        ok_dot = s == oracle.dot_ranks(pv, u_ref, npes=world, red_mode=1)
+        q.put((rank, bool(ok_gather), bool(ok_scatter), bool(ok_dot), int(halo.size), int(put_cnt.sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_protocol_over_gloo(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, okg, oks, okd, nh, npu in sorted(res):
+        assert okg and oks and okd, (rank, okg, oks, okd)
+        assert nh > 0 and npu > 0
