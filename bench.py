@@ -147,6 +147,8 @@ def main():
     import torch.distributed as dist
     from parafem_b200 import host, solver
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"    # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     if world > 1:
         # control plane only (id broadcast, barriers, max over ranks); the data path is the
         # library's own NCCL communicator
