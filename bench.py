@@ -37,8 +37,12 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=125, help="cube edge in elements (125 = BASELINE config C)")
     ap.add_argument("--nod", type=int, default=20, choices=[8, 20])
+    ap.add_argument("--program", default="p121", choices=["p121", "p123"],
+                    help="p123 = steady heat conduction, 8-node bricks (BASELINE config B at --n 100)")
     ap.add_argument("--cpu-n", type=int, default=40, help="cube edge of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=60)
+    ap.add_argument("--matrix-free", action="store_true",
+                    help="BASELINE config E: recompute the element operator every iteration (FP64-pipe roofline)")
     ap.add_argument("--no-solve", action="store_true", help="skip the solve to convergence (time-to-solution)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     return ap.parse_args()
@@ -175,13 +179,18 @@ def main():
 
     t_setup0 = time.time()
     n = args.n
-    prob = host.cube_p121(n, n, n, args.nod, limit=20000, npes=nranks, numpe=rank + 1)
+    if args.program == "p123":
+        args.nod = 8
+        prob = host.cube_p123(n, n, n, limit=20000, npes=nranks, numpe=rank + 1)
+    else:
+        prob = host.cube_p121(n, n, n, args.nod, limit=20000, npes=nranks, numpe=rank + 1)
     t_mesh = time.time() - t_setup0
     s = solver.Solver(rank, nranks, local, nccl_id)
     t0 = time.time()
-    solver.setup_problem(s, prob)
+    solver.setup_problem(s, prob, matrix_free=args.matrix_free)
     barrier()
     t_dev_setup = time.time() - t0
+    fp64_tflops = s.measure_fp64() if args.matrix_free else None
     ntot = prob.ntot
     storkm_bytes_pp = prob.nels_pp * ntot * ntot * 8
 
@@ -246,6 +255,12 @@ def main():
     pk, pk_kind = peaks()
     mv_avg_ms = mv_ms / max(mv_n, 1)
     achieved = storkm_bytes_pp / (mv_avg_ms / 1e3) / 1e9 if mv_n else None
+    # matrix-free: flops of the operator form per element (k_apply_mf), fma = 2 flop:
+    # per Gauss point 9*nod (jac) + 2*(9+12)*nod... counted from the kernel source:
+    #   jac 9 fma/node, deriv 9 fma/node twice, eps 9 fma/node, B^T sigma 9 fma/node  -> 45*nod fma
+    #   + determinant/adjugate (~45 flop) + sigma (36 fma + 7 mul); 8 points; + 7 adds per dof
+    nodn = args.nod
+    mf_flops_per_el = 8 * (2 * 45 * nodn + 45 + 2 * 36 + 7) + 7 * 3 * nodn
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -255,15 +270,15 @@ def main():
         pass
 
     cpu = None
-    if rank == 0 and nranks == 1 and not args.no_cpu:
+    if rank == 0 and nranks == 1 and not args.no_cpu and args.program == "p121":
         cpu = cpu_leg(args.cpu_n, args.nod, args.cpu_steps, 3)
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": nranks, "steps": K, "warmup": W,
+            "metric": METRIC if args.program == "p121" else "p123 EBE-PCG MDOF-iters/s", "value": value, "unit": UNIT, "n_gpus": nranks, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"p121 {n}^3 hex{args.nod} cube, p12meshgen geometry (BASELINE config "
+            "config": {"workload": f"{args.program} {n}^3 hex{args.nod} cube, p12meshgen geometry (BASELINE config "
                                    f"{'C' if (n, args.nod) == (125, 20) else 'custom'}): {prob.nels} elements, "
                                    f"{prob.neq} equations, storkm {prob.nels * ntot * ntot * 8 / 1e9:.2f} GB",
                        "step": "one PCG iteration (gather, storkm mat-vec, scatter, dots/updates, checon_par)",
@@ -274,11 +289,20 @@ def main():
                     "d2h_bytes_per_step": prob.neq_pp * 8 / K, "seconds": e2e_s,
                     "note": "pf_pcg_solve with pinned host r_pp in / xnew_pp out, K iterations per call"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": traffic,
-                         "kernel": "k_matvec (storkm stream; gather fused)", "peak_kind": pk_kind,
-                         "algorithmic_bytes_per_launch": storkm_bytes_pp, "avg_launch_ms": mv_avg_ms,
-                         "launches_timed": int(mv_n)},
+            "roofline": ({"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                          "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": traffic,
+                          "kernel": "k_matvec (storkm stream; gather fused)", "peak_kind": pk_kind,
+                          "algorithmic_bytes_per_launch": storkm_bytes_pp, "avg_launch_ms": mv_avg_ms,
+                          "launches_timed": int(mv_n)} if not args.matrix_free else
+                         {"bound": "fp64", "achieved": prob.nels_pp * mf_flops_per_el / (mv_avg_ms / 1e3) / 1e12,
+                          "peak": fp64_tflops, "unit": "TFLOP/s",
+                          "frac": prob.nels_pp * mf_flops_per_el / (mv_avg_ms / 1e3) / 1e12 / fp64_tflops,
+                          "traffic": None, "kernel": "k_apply_mf (matrix-free operator form, gather fused)",
+                          "peak_kind": "DFMA micro-benchmark on this device (pf_measure_fp64), fma = 2 flop",
+                          "algorithmic_flops_per_launch": prob.nels_pp * mf_flops_per_el,
+                          "flops_per_element": mf_flops_per_el, "avg_launch_ms": mv_avg_ms,
+                          "launches_timed": int(mv_n)}),
+            "variant": "matrix-free (config E)" if args.matrix_free else "stored storkm",
             "kernel_ms_per_step": {"matvec": mv_ms / K, "scatter": sc_ms / K, "vector_and_reductions": vec_ms / K,
                                    "halo": halo_ms / K},
             "clocks": clocks,

@@ -81,8 +81,10 @@ int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp,
  * pf_set_storkm uploads a host storkm_pp instead (xx3's
  * copy_3d_data_to_gpu, xx3.f90:440-452); pf_get_storkm reads n elements
  * starting at 0-based local element iel0 back (parity tests).
- * pf_set_matrix_free(1): do not store storkm; recompute km inside the
- * mat-vec kernel every iteration (BASELINE config E).                     */
+ * pf_set_matrix_free(1) (call before pf_form_km_elastic): BASELINE config E.
+ * storkm is never stored; every iteration recomputes the element operator
+ * from g_coord_pp as sum_gp B^T (D (B p)) det w (p121 elements, nip = 8).
+ * Only the diagonal of km is formed once, for the preconditioner.          */
 int pf_form_km_elastic(pf_handle h, double e, double v);
 int pf_form_kc_laplace(pf_handle h, double kx, double ky, double kz);
 int pf_set_storkm(pf_handle h, const double *storkm_pp);
@@ -148,6 +150,9 @@ int pf_set_profile(pf_handle h, int on);
 int pf_reset_profile(pf_handle h);
 int pf_get_kernel_ms(pf_handle h, int which, double *total_ms, int64_t *launches);
 int64_t pf_kernel_launches(pf_handle h); /* all kernel launches since pf_init */
+/* DFMA micro-benchmark on this device: the FP64 roofline denominator of the
+ * matrix-free variant ("FP64 peak is not in MEASURED_PEAKS.json").  */
+int pf_measure_fp64(pf_handle h, double *tflops);
 int pf_device_info(pf_handle h, int *sm_count, int64_t *free_bytes, int64_t *total_bytes);
 
 /* ===================================================================== */

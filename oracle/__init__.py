@@ -45,7 +45,8 @@ def lib():
         L.orc_find_g4.argtypes = [cint, vp, vp, i64, vp]
         L.orc_partition.argtypes = [i64, cint, cint, C.POINTER(i64), C.POINTER(i64)]
         L.orc_pcg.argtypes = [cint, i64, vp, vp, i64, vp, i64, vp, vp, dbl, cint, cint, dbl, cint, vp,
-                              C.POINTER(cint), C.POINTER(cint), vp, vp, C.POINTER(dbl)]
+                              C.POINTER(cint), C.POINTER(cint), vp, vp, C.POINTER(dbl), vp, cint, cint, dbl, dbl]
+        L.orc_apply_mf.argtypes = [i64, cint, cint, vp, dbl, dbl, vp, vp]
         L.orc_sample_hex.argtypes = [cint, vp, vp]
         L.orc_shape_der.argtypes = [cint, vp, cint, cint, vp]
         L.orc_set_threads.argtypes = [cint]
@@ -155,7 +156,16 @@ def find_g4(g_num, rest):
     return g
 
 
-def pcg(storkm, g_g, neq, r, tol, limit, npes=1, red_mode=0, no_f=None, val_f=None, penalty=1e20):
+def apply_mf(g_coord_pp, nod, nip, e, v, pmul):
+    """Matrix-free element products (config E): utemp = sum_gp B^T D B p det w, oracle order."""
+    g, pm = _f64(g_coord_pp), _f64(pmul)
+    out = np.empty(pm.shape)
+    rc = lib().orc_apply_mf(g.shape[0], nod, nip, _p(g), e, v, _p(pm), _p(out))
+    assert rc == 0
+    return out
+
+
+def pcg(storkm, g_g, neq, r, tol, limit, npes=1, red_mode=0, no_f=None, val_f=None, penalty=1e20, mf=None):
     """p121.f90:65-104 / p123.f90:86-151 on global arrays.  Returns dict(x, iters, converged,
     ratio, diag, seconds)."""
     k, g, r = _f64(storkm), _i32(g_g), _f64(r)
@@ -167,9 +177,11 @@ def pcg(storkm, g_g, neq, r, tol, limit, npes=1, red_mode=0, no_f=None, val_f=No
     diag = np.empty(neq)
     ratio = np.zeros(limit)
     it, conv, secs = cint(), cint(), dbl()
+    mfc = _f64(mf["g_coord_pp"]) if mf else None     # mf = dict(g_coord_pp, nod, nip, e, v): matrix-free products
     rc = lib().orc_pcg(ntot, nels, _p(g), _p(k), neq, _p(r), nfixed, _p(no_f), _p(val_f), penalty, npes,
                        red_mode, tol, limit, _p(x), C.byref(it), C.byref(conv), _p(ratio), _p(diag),
-                       C.byref(secs))
+                       C.byref(secs), _p(mfc), mf["nod"] if mf else 0, mf["nip"] if mf else 0,
+                       mf["e"] if mf else 0.0, mf["v"] if mf else 0.0)
     assert rc == 0
     return dict(x=x, iters=it.value, converged=bool(conv.value), ratio=ratio[:it.value], diag=diag,
                 seconds=secs.value)

@@ -398,6 +398,97 @@ void orc_matvec(int ntot, int64_t nels, const double *storkm, const double *pmul
   }
 }
 
+
+/* ------------------------------------------------------------------------- */
+/* matrix-free variant (BASELINE config E): utemp(:,e) = sum_gp B^T (D (B p)) det w   */
+/* ------------------------------------------------------------------------- */
+/*
+ * Operator form of elements_3 without storkm: per element and Gauss point (ascending) the
+ * Jacobian, its inverse and the Cartesian derivatives are recomputed as in gauss_point()
+ * but with fused multiply-adds (fma chains from 0.0), then
+ *   eps   = B p      node-ascending fma chains, rows in beemat's order
+ *   sigma = D eps    c-ascending fma chain per row, then sigma *= det*w
+ *   ug    = B^T sigma   per dof three fmas from 0.0 in row order
+ * and the eight per-point vectors are added in Gauss-point order.  This is the operation
+ * order of k_apply_mf in parafem_b200/csrc/kernels.cuh.  It is a different rounding of
+ * the same operator as MATMUL(storkm,pmul) (p121.f90:94), hence its own oracle.
+ */
+static void mf_point(int nod, const double *der /*(3,20) at [a*20+m]*/, const double *coord, const double *dee,
+                     double wt, const double *pm, double *ug) {
+  double jac[9], inv[9];
+  for (int b = 0; b < 3; ++b)
+    for (int a = 0; a < 3; ++a) {
+      double s = 0.0;
+      for (int m = 0; m < nod; ++m) s = fma(der[a * 20 + m], coord[b * nod + m], s);
+      jac[b * 3 + a] = s;
+    }
+  const double det = orc_determinant3(jac);
+  memcpy(inv, jac, sizeof inv);
+  orc_invert3(inv);
+  double eps[6] = {0, 0, 0, 0, 0, 0}, sig[6];
+  for (int m = 0; m < nod; ++m) {
+    double d[3];
+    for (int a = 0; a < 3; ++a) {
+      double s = 0.0;
+      for (int b = 0; b < 3; ++b) s = fma(inv[b * 3 + a], der[b * 20 + m], s);
+      d[a] = s;
+    }
+    const double px = pm[3 * m], py = pm[3 * m + 1], pz = pm[3 * m + 2];
+    eps[0] = fma(d[0], px, eps[0]);
+    eps[1] = fma(d[1], py, eps[1]);
+    eps[2] = fma(d[2], pz, eps[2]);
+    eps[3] = fma(d[1], px, eps[3]); eps[3] = fma(d[0], py, eps[3]);
+    eps[4] = fma(d[2], py, eps[4]); eps[4] = fma(d[1], pz, eps[4]);
+    eps[5] = fma(d[2], px, eps[5]); eps[5] = fma(d[0], pz, eps[5]);
+  }
+  const double f = det * wt;
+  for (int r = 0; r < 6; ++r) {
+    double s = 0.0;
+    for (int c = 0; c < 6; ++c) s = fma(dee[c * 6 + r], eps[c], s);
+    sig[r] = s * f;
+  }
+  for (int m = 0; m < nod; ++m) {
+    double d[3];
+    for (int a = 0; a < 3; ++a) {
+      double s = 0.0;
+      for (int b = 0; b < 3; ++b) s = fma(inv[b * 3 + a], der[b * 20 + m], s);
+      d[a] = s;
+    }
+    double ux = 0.0, uy = 0.0, uz = 0.0;
+    ux = fma(d[0], sig[0], ux); ux = fma(d[1], sig[3], ux); ux = fma(d[2], sig[5], ux);
+    uy = fma(d[1], sig[1], uy); uy = fma(d[0], sig[3], uy); uy = fma(d[2], sig[4], uy);
+    uz = fma(d[2], sig[2], uz); uz = fma(d[1], sig[4], uz); uz = fma(d[0], sig[5], uz);
+    ug[3 * m] = ux; ug[3 * m + 1] = uy; ug[3 * m + 2] = uz;
+  }
+}
+
+int orc_apply_mf(int64_t nels, int nod, int nip, const double *g_coord_pp, double e, double v,
+                 const double *pmul, double *utemp) {
+  if ((nod != 8 && nod != 20) || nip != 8) return 1;
+  const int ntot = 3 * nod;
+  double points[24], weights[8], dee[36], der[8][60], d3[60];
+  orc_sample_hex(nip, points, weights);
+  orc_deemat6(dee, e, v);
+  for (int ig = 0; ig < nip; ++ig) {
+    orc_shape_der(nod, points, nip, ig, d3);
+    memset(der[ig], 0, sizeof der[ig]);
+    for (int m = 0; m < nod; ++m)
+      for (int a = 0; a < 3; ++a) der[ig][a * 20 + m] = d3[m * 3 + a];
+  }
+#pragma omp parallel for schedule(static)
+  for (int64_t iel = 0; iel < nels; ++iel) {
+    double ug[8][60];
+    for (int ig = 0; ig < nip; ++ig)
+      mf_point(nod, der[ig], g_coord_pp + iel * nod * 3, dee, weights[ig], pmul + iel * ntot, ug[ig]);
+    for (int k = 0; k < ntot; ++k) {
+      double s = ug[0][k];
+      for (int ig = 1; ig < nip; ++ig) s = s + ug[ig][k];
+      utemp[iel * ntot + k] = s;
+    }
+  }
+  return 0;
+}
+
 typedef struct {
   int npes;
   int64_t *el0, *el1;   /* element range [el0,el1) per rank (0-based) */
@@ -543,6 +634,8 @@ double orc_dot_ranks(const double *a, const double *b, int64_t neq, int npes, in
  * penalty; npes emulated ranks (also the OpenMP width of the element loops).
  * Outputs: x(neq), *iters, *converged, ratio[limit] (may be NULL),
  * diag_out(neq) (may be NULL) = inverted preconditioner.
+ * mf_coord != NULL: the element products use orc_apply_mf (matrix-free variant) instead of
+ * storkm, which is then only read for the preconditioner diagonal.
  * Returns seconds spent in the iteration loop (the reference's timest(3)
  * window, p121.f90:89,107-108) through *solve_seconds.
  */
@@ -550,7 +643,7 @@ int orc_pcg(int ntot, int64_t nels, const int32_t *g_g, const double *storkm, in
             const double *r_in, int64_t nfixed, const int32_t *no_f, const double *val_f,
             double penalty, int npes, int red_mode, double tol, int limit, double *x_out,
             int *iters_out, int *converged_out, double *ratio, double *diag_out,
-            double *solve_seconds) {
+            double *solve_seconds, const double *mf_coord, int mf_nod, int mf_nip, double mf_e, double mf_v) {
   orc_ranks *R = ranks_new(npes, ntot, nels, g_g, neq);
   double *pmul = malloc(sizeof(double) * (size_t)(nels * ntot));
   double *utemp = malloc(sizeof(double) * (size_t)(nels * ntot));
@@ -583,7 +676,8 @@ int orc_pcg(int ntot, int64_t nels, const int32_t *g_g, const double *storkm, in
   for (;;) {
     iters = iters + 1;
     orc_gather(ntot, nels, g_g, p, pmul);
-    orc_matvec(ntot, nels, storkm, pmul, utemp);
+    if (mf_coord) orc_apply_mf(nels, mf_nod, mf_nip, mf_coord, mf_e, mf_v, pmul, utemp);
+    else orc_matvec(ntot, nels, storkm, pmul, utemp);
     ranks_scatter(R, ntot, g_g, utemp, u);
     for (int64_t i = 0; i < nfixed; ++i) u[no_f[i] - 1] = p[no_f[i] - 1] * store[i];  /* p123.f90:141-145 */
     const double up = orc_dot_ranks(r, d, neq, npes, red_mode);

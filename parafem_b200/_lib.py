@@ -65,6 +65,7 @@ SIGNATURES = {
     "pf_reset_profile": (c_int, [vp]),
     "pf_get_kernel_ms": (c_int, [vp, c_int, P(c_dbl), P(c_i64)]),
     "pf_kernel_launches": (c_i64, [vp]),
+    "pf_measure_fp64": (c_int, [vp, P(c_dbl)]),
     "pf_device_info": (c_int, [vp, P(c_int), P(c_i64), P(c_i64)]),
     # B. host helpers
     "pf_calc_nels_pp": (None, [c_i64, c_int, c_int, P(c_i64), P(c_i64)]),

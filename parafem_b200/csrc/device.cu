@@ -74,7 +74,7 @@ struct pf_ctx {
   int nod = 0, nodof = 0, nip = 0, ntot = 0;
   int64_t nels = 0, neq = 0, ieq_start = 0, neq_pp = 0, nhalo = 0, nslots = 0;
   bool have_mesh = false, have_km = false, have_precon = false, matrix_free = false;
-  DevBuf<double> coord, km, utemp;
+  DevBuf<double> coord, km, utemp, diag_tmp;
   DevBuf<int> ggl;
   DevBuf<unsigned int> csr_ptr, csr_pos;
 
@@ -246,9 +246,31 @@ int launch_matvec_t(pf_handle h, const double *pvec, const State *st) {
   return 0;
 }
 
+template <int NOD, bool GATHER>
+int launch_mf_t(pf_handle h, const double *pvec, const State *st) {
+  using Cfg = MfCfg<NOD>;
+  constexpr int kWarps = 10;
+  auto kern = k_apply_mf<NOD, GATHER>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem(kWarps)));
+    attr_set = true;
+  }
+  const int64_t ngroups = (h->nels + 3) / 4;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (ngroups + kWarps - 1) / kWarps));
+  kern<<<grid, kWarps * 32, Cfg::smem(kWarps), h->stream>>>(h->coord.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
 template <bool GATHER>
 int launch_matvec(pf_handle h, const double *pvec, const State *st) {
   Scope sc(h, K_MATVEC);
+  if (h->matrix_free) {
+    if (h->nod == 20) return launch_mf_t<20, GATHER>(h, pvec, st);
+    return launch_mf_t<8, GATHER>(h, pvec, st);
+  }
   switch (h->ntot) {
     case 60: return launch_matvec_t<60, 1, 7, GATHER>(h, pvec, st);
     case 24: return launch_matvec_t<24, 8, 5, GATHER>(h, pvec, st);
@@ -422,7 +444,7 @@ int pf_finalize(pf_handle h) {
   collect_spans(h);
   for (auto e : h->pool) cudaEventDestroy(e);
   if (h->comm) g_nccl.CommDestroy(h->comm);
-  h->coord.release(); h->km.release(); h->utemp.release(); h->ggl.release(); h->csr_ptr.release(); h->csr_pos.release();
+  h->coord.release(); h->km.release(); h->diag_tmp.release(); h->utemp.release(); h->ggl.release(); h->csr_ptr.release(); h->csr_pos.release();
   h->put_slot.release(); h->sendbuf.release(); h->recvbuf.release(); h->acc_slot.release(); h->acc_ptr.release(); h->acc_pos.release();
   h->p_ext.release(); h->u_ext.release(); h->diag_ext.release(); h->r.release(); h->x.release(); h->d.release();
   h->part.release(); h->gath.release(); h->state.release(); h->ratio_hist.release(); h->fix_slot.release(); h->store.release();
@@ -442,6 +464,27 @@ int pf_device_info(pf_handle h, int *sm_count, int64_t *free_bytes, int64_t *tot
 }
 
 int64_t pf_kernel_launches(pf_handle h) { return h ? h->launches : 0; }
+
+int pf_measure_fp64(pf_handle h, double *tflops) {
+  int rc = need_device(h); if (rc) return rc;
+  DevBuf<double> out; CU(out.alloc(1));
+  const int iters = 20000, threads = 256, blocks = h->sm_count * 8;
+  cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CU(cudaEventRecord(e0, h->stream));
+    k_fp64_peak<<<blocks, threads, 0, h->stream>>>(out.p, iters, 1.0000001, 1e-9);
+    CU(cudaEventRecord(e1, h->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f; CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 2.0 * 8.0 * iters * (double)threads * blocks / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  h->launches += 4;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); out.release();
+  *tflops = best;
+  return 0;
+}
 
 int pf_set_profile(pf_handle h, int on) { if (!h) return 1; h->profile = on != 0; return 0; }
 int pf_reset_profile(pf_handle h) {
@@ -597,10 +640,17 @@ int pf_form_km_elastic(pf_handle h, double e, double v) {
   ElemTables T;
   if (fill_tables(h->nod, h->nip, e, v, 0, 0, 0, T)) return fail(h, 3, "unsupported nod/nip");
   CU(cudaMemcpyToSymbol(c_tab, &T, sizeof T));
-  if ((rc = alloc_km(h))) return rc;
+  double *diag_only = nullptr;
+  if (h->matrix_free) {
+    // config E: storkm is never stored; only its diagonal is formed (for the preconditioner)
+    NEED(h->nip == 8, "the matrix-free variant supports nip = 8");
+    h->km.release();
+    CU(h->diag_tmp.alloc((size_t)h->nels * h->ntot));
+    diag_only = h->diag_tmp.p;
+  } else if ((rc = alloc_km(h))) return rc;
   const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 16);
-  if (h->nod == 20) k_form_km_elastic<20, 128><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels);
-  else k_form_km_elastic<8, 64><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels);
+  if (h->nod == 20) k_form_km_elastic<20, 128><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, diag_only);
+  else k_form_km_elastic<8, 64><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, diag_only);
   h->launches++;
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));
@@ -627,6 +677,7 @@ int pf_form_kc_laplace(pf_handle h, double kx, double ky, double kz) {
 int pf_set_storkm(pf_handle h, const double *storkm_pp) {
   int rc = need_device(h); if (rc) return rc;
   NEED(h->have_mesh && storkm_pp, "needs pf_setup_mesh");
+  NEED(!h->matrix_free, "matrix-free variant: storkm is not stored");
   if ((rc = alloc_km(h))) return rc;
   CU(cudaMemcpy(h->km.p, storkm_pp, h->km.bytes(), cudaMemcpyHostToDevice));
   h->have_km = true; h->have_precon = false;
@@ -635,6 +686,7 @@ int pf_set_storkm(pf_handle h, const double *storkm_pp) {
 
 int pf_get_storkm(pf_handle h, int64_t iel0, int64_t n, double *out) {
   int rc = need_device(h); if (rc) return rc;
+  NEED(!h->matrix_free, "matrix-free variant: storkm is not stored");
   NEED(h->have_km && iel0 >= 0 && n >= 0 && iel0 + n <= h->nels, "range outside the local elements");
   const size_t per = (size_t)h->ntot * h->ntot;
   CU(cudaMemcpy(out, h->km.p + (size_t)iel0 * per, (size_t)n * per * 8, cudaMemcpyDeviceToHost));
@@ -643,8 +695,9 @@ int pf_get_storkm(pf_handle h, int64_t iel0, int64_t n, double *out) {
 
 int pf_set_matrix_free(pf_handle h, int on) {
   if (!h) return 1;
-  if (on) return fail(h, 5, "matrix-free variant not built yet");
-  h->matrix_free = false;
+  NEED(!on || !h->have_mesh || h->nodof == 3, "the matrix-free variant exists for the elastic elements (p121) only");
+  if ((on != 0) != h->matrix_free) { h->have_km = false; h->have_precon = false; }
+  h->matrix_free = on != 0;
   return 0;
 }
 
@@ -653,7 +706,13 @@ int pf_build_precon(pf_handle h, int64_t nfixed_pp, const int32_t *no_f_pp, doub
   NEED(h->have_km, "needs element matrices (pf_form_km_elastic / pf_form_kc_laplace / pf_set_storkm)");
   NEED(nfixed_pp >= 0 && nfixed_pp < (1 << 30), "bad nfixed_pp");
   // diag_precon_tmp(i,iel) = storkm(i,i,iel); scatter  (p121.f90:65-69)
-  if ((rc = launch_scatter(h, nullptr, true, h->diag_ext.p))) return rc;
+  if (h->matrix_free) {
+    NEED(h->diag_tmp.n == (size_t)h->nels * h->ntot, "matrix-free: call pf_form_km_elastic first");
+    Scope sc(h, K_SCATTER);
+    k_scatter<false><<<grid_for(h, h->nslots, 256, 16), 256, 0, h->stream>>>(h->csr_ptr.p, h->csr_pos.p, h->diag_tmp.p, h->diag_ext.p,
+                                                                              (long long)h->nslots, h->ntot, nullptr);
+    h->launches++;
+  } else if ((rc = launch_scatter(h, nullptr, true, h->diag_ext.p))) return rc;
   if ((rc = halo_reverse(h, h->diag_ext.p, nullptr))) return rc;
   h->nfixed = (int)nfixed_pp;
   if (h->nfixed > 0) {
@@ -674,6 +733,7 @@ int pf_build_precon(pf_handle h, int64_t nfixed_pp, const int32_t *no_f_pp, doub
   }
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));
+  h->diag_tmp.release();
   h->have_precon = true;
   return 0;
 }

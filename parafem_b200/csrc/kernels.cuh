@@ -548,7 +548,8 @@ __device__ __forceinline__ double gauss_point(int ig, const double *s_coord, dou
 // elements_1 of p121.f90:56-64.  km(i,j) += (sum_k btd(i,k)*bee(k,j)) * det * w
 template <int NOD, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-k_form_km_elastic(const double *__restrict__ g_coord, double *__restrict__ km, long long nels) {
+k_form_km_elastic(const double *__restrict__ g_coord, double *__restrict__ km, long long nels,
+                  double *__restrict__ diag_only /* matrix-free: (ntot,nels) diagonal instead of km */) {
   constexpr int NTOT = 3 * NOD, NENT = NTOT * NTOT, PER = (NENT + THREADS - 1) / THREADS;
   __shared__ double s_coord[NOD * 3], s_jac[9], s_deriv[NOD * 3];
   __shared__ double s_bee[6 * NTOT];  // bee(l,c) at [c*6+l]
@@ -600,7 +601,143 @@ k_form_km_elastic(const double *__restrict__ g_coord, double *__restrict__ km, l
 #pragma unroll
     for (int n = 0; n < PER; ++n) {
       const int idx = threadIdx.x + n * THREADS;
-      if (idx < NENT) km[e * (long long)NENT + idx] = acc[n];
+      if (idx < NENT) {
+        if (diag_only) {
+          const int j = idx / NTOT, i = idx - j * NTOT;
+          if (i == j) diag_only[e * (long long)NTOT + i] = acc[n];
+        } else {
+          km[e * (long long)NENT + idx] = acc[n];
+        }
+      }
+    }
+  }
+}
+
+
+// ----------------------------------------------------------------------------
+// BASELINE config E: matrix-free element products, utemp(:,e) = sum_gp B^T (D (B p)) det w
+// ----------------------------------------------------------------------------
+// One thread per (element, Gauss point); a warp owns 4 elements x 8 points and works out of
+// its own slice of shared memory, so there is no block-wide barrier.  Per point the thread
+// rebuilds jac, its inverse and the Cartesian derivatives (fused multiply-adds), forms
+// eps = B p, sigma = D eps * det * w and the 3 nodal products B^T sigma, writes them to a
+// per-point row and the warp then adds the 8 rows in point order.  Same operation order as
+// orc_apply_mf in the oracle.  FP64-pipe bound (~14 kflop per hex20 element), not HBM bound.
+template <int NOD>
+struct MfCfg {
+  static constexpr int NTOT = 3 * NOD;
+  static constexpr int kNodeStride = 4;                   // doubles per node: x,y,z,pad
+  static constexpr int kRow = NOD * kNodeStride + 2;      // +16 B: rows land in distinct 16 B bank groups
+  static constexpr int kPart = NTOT + 1;                  // odd stride: conflict-free per-point rows
+  static constexpr int kWarpDoubles = 4 * kRow * 2 + 32 * kPart;   // coords, p, 32 partial rows
+  static constexpr int kDerDoubles = 8 * kRow;
+  static constexpr size_t smem(int warps) { return (size_t)(kDerDoubles + warps * kWarpDoubles) * 8; }
+};
+
+template <int NOD, bool GATHER>
+__global__ void __launch_bounds__(320, 1)
+k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, const double *__restrict__ pvec,
+           double *__restrict__ utemp, long long nels, const State *st) {
+  using Cfg = MfCfg<NOD>;
+  constexpr int NTOT = Cfg::NTOT;
+  if (st && *(volatile const int *)&st->done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *s_der = reinterpret_cast<double *>(smem_raw);            // [ig][m][4]
+  const int nwarps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *s_co = s_der + Cfg::kDerDoubles + (size_t)w * Cfg::kWarpDoubles;   // [el][m][4]
+  double *s_p = s_co + 4 * Cfg::kRow;                                         // [el][m][4]
+  double *s_part = s_p + 4 * Cfg::kRow;                                       // [el*8+ig][kPart]
+  for (int q = threadIdx.x; q < 8 * NOD * 3; q += blockDim.x) {
+    const int ig = q / (NOD * 3), r = q - ig * NOD * 3, a = r / NOD, m = r - a * NOD;
+    s_der[ig * Cfg::kRow + m * 4 + a] = c_tab.der[ig * 60 + a * 20 + m];
+  }
+  __syncthreads();
+  const int el = lane >> 3, ig = lane & 7;
+  const double *der = s_der + ig * Cfg::kRow;
+  const double *co = s_co + el * Cfg::kRow;
+  const double *pp = s_p + el * Cfg::kRow;
+  double *part = s_part + lane * Cfg::kPart;
+  const double wt = c_tab.weights[ig];
+  const long long ngroups = (nels + 3) / 4;
+  for (long long grp = (long long)blockIdx.x * nwarps + w; grp < ngroups; grp += (long long)gridDim.x * nwarps) {
+    const long long e0 = grp * 4;
+    const int ne = (int)((nels - e0) < 4 ? (nels - e0) : 4);
+    __syncwarp();
+    for (int s = lane; s < ne * NTOT; s += 32) {
+      const int le = s / NTOT, k = s - le * NTOT;
+      // coordinates: g_coord_pp(nod,3,nels) -> [m][d]; p: dof k = 3m+c -> [m][c]
+      const int d = k / NOD, m = k - d * NOD;
+      s_co[le * Cfg::kRow + m * 4 + d] = g_coord[(e0 + le) * NTOT + k];
+      const double pv = GATHER ? pvec[ggl[(e0 + le) * NTOT + k]] : pvec[(e0 + le) * NTOT + k];
+      s_p[le * Cfg::kRow + (k / 3) * 4 + (k % 3)] = pv;
+    }
+    __syncwarp();
+    if (el < ne) {
+      double jac[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) jac[q] = 0.0;
+#pragma unroll
+      for (int m = 0; m < NOD; ++m) {
+        const double2 dxy = *reinterpret_cast<const double2 *>(der + m * 4);
+        const double dz = der[m * 4 + 2];
+        const double2 cxy = *reinterpret_cast<const double2 *>(co + m * 4);
+        const double cz = co[m * 4 + 2];
+        // jac(a,b) at [b*3+a], node-ascending fma chains
+        jac[0] = fma(dxy.x, cxy.x, jac[0]); jac[1] = fma(dxy.y, cxy.x, jac[1]); jac[2] = fma(dz, cxy.x, jac[2]);
+        jac[3] = fma(dxy.x, cxy.y, jac[3]); jac[4] = fma(dxy.y, cxy.y, jac[4]); jac[5] = fma(dz, cxy.y, jac[5]);
+        jac[6] = fma(dxy.x, cz, jac[6]);    jac[7] = fma(dxy.y, cz, jac[7]);    jac[8] = fma(dz, cz, jac[8]);
+      }
+      const double det = det3(jac);
+      double inv[9];
+      inv3(jac, det, inv);
+      double e0_ = 0.0, e1_ = 0.0, e2_ = 0.0, e3_ = 0.0, e4_ = 0.0, e5_ = 0.0;
+#pragma unroll
+      for (int m = 0; m < NOD; ++m) {
+        const double2 dxy = *reinterpret_cast<const double2 *>(der + m * 4);
+        const double dz = der[m * 4 + 2];
+        // deriv(a,m) = sum_b inv(a,b) der(b,m), b ascending from 0
+        const double gx = fma(inv[6], dz, fma(inv[3], dxy.y, fma(inv[0], dxy.x, 0.0)));
+        const double gy = fma(inv[7], dz, fma(inv[4], dxy.y, fma(inv[1], dxy.x, 0.0)));
+        const double gz = fma(inv[8], dz, fma(inv[5], dxy.y, fma(inv[2], dxy.x, 0.0)));
+        const double2 pxy = *reinterpret_cast<const double2 *>(pp + m * 4);
+        const double pz = pp[m * 4 + 2];
+        e0_ = fma(gx, pxy.x, e0_);
+        e1_ = fma(gy, pxy.y, e1_);
+        e2_ = fma(gz, pz, e2_);
+        e3_ = fma(gy, pxy.x, e3_); e3_ = fma(gx, pxy.y, e3_);
+        e4_ = fma(gz, pxy.y, e4_); e4_ = fma(gy, pz, e4_);
+        e5_ = fma(gz, pxy.x, e5_); e5_ = fma(gx, pz, e5_);
+      }
+      const double eps[6] = {e0_, e1_, e2_, e3_, e4_, e5_};
+      const double f = det * wt;
+      double sig[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) s = fma(c_tab.dee[c * 6 + r], eps[c], s);
+        sig[r] = s * f;
+      }
+#pragma unroll
+      for (int m = 0; m < NOD; ++m) {
+        const double2 dxy = *reinterpret_cast<const double2 *>(der + m * 4);
+        const double dz = der[m * 4 + 2];
+        const double gx = fma(inv[6], dz, fma(inv[3], dxy.y, fma(inv[0], dxy.x, 0.0)));
+        const double gy = fma(inv[7], dz, fma(inv[4], dxy.y, fma(inv[1], dxy.x, 0.0)));
+        const double gz = fma(inv[8], dz, fma(inv[5], dxy.y, fma(inv[2], dxy.x, 0.0)));
+        part[3 * m] = fma(gz, sig[5], fma(gy, sig[3], fma(gx, sig[0], 0.0)));
+        part[3 * m + 1] = fma(gz, sig[4], fma(gx, sig[3], fma(gy, sig[1], 0.0)));
+        part[3 * m + 2] = fma(gx, sig[5], fma(gy, sig[4], fma(gz, sig[2], 0.0)));
+      }
+    }
+    __syncwarp();
+    for (int s = lane; s < ne * NTOT; s += 32) {
+      const int le = s / NTOT, k = s - le * NTOT;
+      const double *row = s_part + (le * 8) * Cfg::kPart + k;
+      double acc = row[0];
+#pragma unroll
+      for (int g = 1; g < 8; ++g) acc = acc + row[g * Cfg::kPart];
+      utemp[(e0 + le) * NTOT + k] = acc;
     }
   }
 }
@@ -626,6 +763,19 @@ k_form_kc_laplace(const double *__restrict__ g_coord, double *__restrict__ kc, l
     }
     kc[e * 64 + threadIdx.x] = kx * c_tab.kxyz[0] + ky * c_tab.kxyz[1] + kz * c_tab.kxyz[2];
   }
+}
+
+
+// DFMA micro-benchmark: the FP64 denominator for the matrix-free variant ("of measured").
+// 8 independent fma chains per thread, `iters` rounds; 2 flop per fma.
+__global__ void k_fp64_peak(double *out, int iters, double a, double b) {
+  double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+    v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+  }
+  const double s = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+  if (s == 12345.678) out[0] = s;  // keep the chains alive
 }
 
 }  // namespace pf

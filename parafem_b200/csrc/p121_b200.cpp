@@ -19,6 +19,24 @@ static double now() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// Fortran Ew.d edit descriptor: 0.dddd E+xx (C's %E prints d.dddE+xx)
+static std::string fe(double x, int w = 12, int d = 4) {
+  char buf[64];
+  if (x == 0.0) snprintf(buf, sizeof buf, "0.%0*dE+00", d, 0);
+  else {
+    snprintf(buf, sizeof buf, "%.*E", d - 1, x);          // d.ddd E+xx with d significant digits
+    std::string m(buf);
+    const size_t epos = m.find('E');
+    int ex = atoi(m.c_str() + epos + 1) + 1;
+    std::string digits;
+    for (char c : m.substr(0, epos)) if (c >= '0' && c <= '9') digits.push_back(c);
+    snprintf(buf, sizeof buf, "%s0.%sE%c%02d", x < 0 ? "-" : "", digits.c_str(), ex < 0 ? '-' : '+', ex < 0 ? -ex : ex);
+  }
+  std::string s(buf);
+  if ((int)s.size() < w) s.insert(0, (size_t)w - s.size(), ' ');
+  return s;
+}
+
 #define CHECK(call)                                                        \
   do {                                                                     \
     int st_ = (call);                                                      \
@@ -111,12 +129,12 @@ int main(int argc, char **argv) {
     fprintf(o, "There are %12lld nodes%12lld restrained and %12lld equations\n", (long long)nn, (long long)nr, (long long)neq);
     fprintf(o, "Time to read input is:%10.4f\n", t_read);
     fprintf(o, "Time after setup is:%10.4f\n", t_setup);
-    fprintf(o, "The total load is:%12.4E\n", q);
+    fprintf(o, "The total load is:%s\n", fe(q).c_str());
     fprintf(o, "The number of iterations to convergence was %6d\n", iters);
     fprintf(o, "Time to solve equations was  :%10.4f\n", t_solve);
-    fprintf(o, "The central nodal displacement is :%12.4E\n", x[0]);
+    fprintf(o, "The central nodal displacement is :%s\n", fe(x[0]).c_str());
     fprintf(o, "The Centroid point stresses for element 1 are\nPoint %5d\n", 1);
-    for (double s : sigma) fprintf(o, "%12.4E", s);
+    for (double s : sigma) fprintf(o, "%s", fe(s).c_str());
     fprintf(o, "\nThis analysis took  :%10.4f\n", now() - t_start);
   }
   if (f) fclose(f);

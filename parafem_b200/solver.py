@@ -66,6 +66,15 @@ class Solver:
         assert k.size == self.prob.nels_pp * self.prob.ntot ** 2
         self._ck(lib().pf_set_storkm(self._h, ptr(k)), "pf_set_storkm")
 
+    def set_matrix_free(self, on=True):
+        """BASELINE config E: call before form_km_elastic."""
+        self._ck(lib().pf_set_matrix_free(self._h, int(on)), "pf_set_matrix_free")
+
+    def measure_fp64(self):
+        t = C.c_double()
+        self._ck(lib().pf_measure_fp64(self._h, C.byref(t)), "pf_measure_fp64")
+        return t.value
+
     def get_storkm(self, iel0=0, n=None):
         n = self.prob.nels_pp - iel0 if n is None else n
         nt = self.prob.ntot
@@ -175,9 +184,10 @@ class Solver:
         return sm.value, fr.value, tot.value
 
 
-def setup_problem(solver, prob):
+def setup_problem(solver, prob, matrix_free=False):
     """The device part of p121.f90:49-69,86 / p123.f90:57-92,120-125 for one rank."""
     solver.setup_mesh(prob)
+    solver.set_matrix_free(matrix_free)
     if prob.program == 121:
         solver.form_km_elastic(prob.e, prob.v)
         solver.build_precon()

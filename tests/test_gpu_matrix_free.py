@@ -1,0 +1,79 @@
+"""BASELINE config E: the matrix-free variant (km never stored; the element operator
+sum_gp B^T D B p det w is recomputed every iteration) against its own oracle mirror
+(orc_apply_mf, same fma chains) and against the stored-km path."""
+import numpy as np
+import pytest
+
+import oracle
+from parafem_b200 import PfError, host, solver
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "hex20": lambda: host.cube_p121(5, 5, 5, 20, aa=2., bb=2., cc=2., limit=200),
+    "hex20_distorted_ragged": lambda: host.cube_p121(5, 3, 4, 20, aa=1., bb=2., cc=.5, limit=400, distort=0.2),
+    "hex8": lambda: host.cube_p121(10, 7, 5, 8, aa=1., bb=1., cc=1., limit=400),
+}
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    s = solver.Solver(0, 1, 0)
+    yield s
+    s.close()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_matrix_free_products_equal_oracle(gpu, name):
+    p = CASES[name]()
+    solver.setup_problem(gpu, p, matrix_free=True)
+    rng = np.random.RandomState(2)
+    pm = rng.randn(p.nels, p.ntot)
+    ut = gpu.matvec(pm)
+    ref = oracle.apply_mf(p.g_coord_pp, p.nod, p.nip, p.e, p.v, pm)
+    assert np.array_equal(ut, ref)
+    # and it is the same operator as the stored matrices, to rounding
+    km = oracle.form_km_elastic(p.g_coord_pp, p.nod, p.nip, p.e, p.v)
+    stored = oracle.matvec(km, pm)
+    assert np.abs(ut - stored).max() <= 1e-13 * np.abs(stored).max()
+    # the preconditioner diagonal is km's diagonal, bit for bit
+    r = oracle.pcg(km, p.g_g_pp, p.neq, p.r_pp, 1.0, 1, npes=1, red_mode=1)
+    assert np.array_equal(gpu.diag_precon(), r["diag"])
+    with pytest.raises(PfError):
+        gpu.get_storkm()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_matrix_free_pcg_equals_oracle(gpu, name):
+    p = CASES[name]()
+    solver.setup_problem(gpu, p, matrix_free=True)
+    x, iters, conv = gpu.pcg_solve(p.r_pp, p.tol, p.limit)
+    km = oracle.form_km_elastic(p.g_coord_pp, p.nod, p.nip, p.e, p.v)
+    mf = dict(g_coord_pp=p.g_coord_pp, nod=p.nod, nip=p.nip, e=p.e, v=p.v)
+    ref = oracle.pcg(km, p.g_g_pp, p.neq, p.r_pp, p.tol, p.limit, npes=1, red_mode=1, mf=mf)
+    assert conv and iters == ref["iters"]
+    assert np.array_equal(x, ref["x"])
+    assert np.array_equal(gpu.ratio_history(), ref["ratio"])
+    # against the stored-km solve: same count +-1, solution within the stopping tolerance
+    stored = oracle.pcg(km, p.g_g_pp, p.neq, p.r_pp, p.tol, p.limit, npes=1, red_mode=1)
+    assert abs(iters - stored["iters"]) <= 1
+    assert np.linalg.norm(x - stored["x"]) <= 1e-4 * np.linalg.norm(stored["x"])
+
+
+def test_matrix_free_tight_tolerance_matches_stored_path(gpu):
+    """Driven to tol 1e-13 the two operator roundings land on the same field within 1e-9."""
+    p = CASES["hex20"]()
+    solver.setup_problem(gpu, p, matrix_free=True)
+    x_mf, _, c1 = gpu.pcg_solve(p.r_pp, 1e-13, 2000)
+    solver.setup_problem(gpu, p, matrix_free=False)
+    x_st, _, c2 = gpu.pcg_solve(p.r_pp, 1e-13, 2000)
+    assert c1 and c2
+    assert np.linalg.norm(x_mf - x_st) <= 1e-9 * np.linalg.norm(x_st)
+
+
+def test_matrix_free_rejects_p123(gpu):
+    p = host.cube_p123(5, 5, 5)
+    gpu.setup_mesh(p)
+    with pytest.raises(PfError):
+        gpu.set_matrix_free(True)
+    gpu.set_matrix_free(False)
