@@ -35,14 +35,19 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=125, help="cube edge in elements (125 = BASELINE config C)")
-    ap.add_argument("--nod", type=int, default=20, choices=[8, 20])
+    # (option names must not be prefixes of torchrun's own options: argparse abbreviation matching
+    #  rejects e.g. --n / --nod even after the script name)
+    ap.add_argument("--cube", dest="n", type=int, default=125, help="cube edge in elements (125 = BASELINE config C)")
+    ap.add_argument("--hex", dest="nod", type=int, default=20, choices=[8, 20], help="nodes per brick")
     ap.add_argument("--program", default="p121", choices=["p121", "p123"],
                     help="p123 = steady heat conduction, 8-node bricks (BASELINE config B at --n 100)")
     ap.add_argument("--cpu-n", type=int, default=40, help="cube edge of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=60)
-    ap.add_argument("--matrix-free", action="store_true",
-                    help="BASELINE config E: recompute the element operator every iteration (FP64-pipe roofline)")
+    ap.add_argument("--matrix-free", type=int, default=0, choices=[0, 1, 2],
+                    help="BASELINE config E: 1 = rebuild the element operator from coordinates every iteration, "
+                         "2 = same with stored geometric factors (FP64-pipe roofline)")
+    ap.add_argument("--weak", action="store_true",
+                    help="weak scaling: n x (n*N) x n elements, i.e. one n^3 slab of y-planes per GPU")
     ap.add_argument("--no-solve", action="store_true", help="skip the solve to convergence (time-to-solution)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     return ap.parse_args()
@@ -179,11 +184,13 @@ def main():
 
     t_setup0 = time.time()
     n = args.n
+    nye = n * nranks if args.weak else n
     if args.program == "p123":
         args.nod = 8
-        prob = host.cube_p123(n, n, n, limit=20000, npes=nranks, numpe=rank + 1)
+        prob = host.cube_p123(n, nye, n, aa=1.0 / n, bb=1.0 / n, cc=1.0 / n, limit=20000, npes=nranks, numpe=rank + 1)
     else:
-        prob = host.cube_p121(n, n, n, args.nod, limit=20000, npes=nranks, numpe=rank + 1)
+        prob = host.cube_p121(n, nye, n, args.nod, aa=10.0 / n, bb=10.0 / n, cc=10.0 / n, limit=20000, npes=nranks,
+                              numpe=rank + 1)
     t_mesh = time.time() - t_setup0
     s = solver.Solver(rank, nranks, local, nccl_id)
     t0 = time.time()
@@ -261,6 +268,8 @@ def main():
     #   + determinant/adjugate (~45 flop) + sigma (36 fma + 7 mul); 8 points; + 7 adds per dof
     nodn = args.nod
     mf_flops_per_el = 8 * (2 * 45 * nodn + 45 + 2 * 36 + 7) + 7 * 3 * nodn
+    if args.matrix_free == 2:   # no Jacobian pass (9 fma/node) and no determinant / adjugate
+        mf_flops_per_el = 8 * (2 * 36 * nodn + 2 * 36 + 7) + 7 * 3 * nodn
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -276,9 +285,10 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC if args.program == "p121" else "p123 EBE-PCG MDOF-iters/s", "value": value, "unit": UNIT, "n_gpus": nranks, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak" if args.weak else "strong",
+            "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.program} {n}^3 hex{args.nod} cube, p12meshgen geometry (BASELINE config "
+            "config": {"workload": f"{args.program} {n}x{nye}x{n} hex{args.nod} cube, p12meshgen geometry (BASELINE config "
                                    f"{'C' if (n, args.nod) == (125, 20) else 'custom'}): {prob.nels} elements, "
                                    f"{prob.neq} equations, storkm {prob.nels * ntot * ntot * 8 / 1e9:.2f} GB",
                        "step": "one PCG iteration (gather, storkm mat-vec, scatter, dots/updates, checon_par)",
@@ -302,7 +312,8 @@ def main():
                           "algorithmic_flops_per_launch": prob.nels_pp * mf_flops_per_el,
                           "flops_per_element": mf_flops_per_el, "avg_launch_ms": mv_avg_ms,
                           "launches_timed": int(mv_n)}),
-            "variant": "matrix-free (config E)" if args.matrix_free else "stored storkm",
+            "variant": {0: "stored storkm", 1: "matrix-free, rebuilt from coordinates (config E)",
+                        2: "matrix-free, stored geometric factors"}[args.matrix_free],
             "kernel_ms_per_step": {"matvec": mv_ms / K, "scatter": sc_ms / K, "vector_and_reductions": vec_ms / K,
                                    "halo": halo_ms / K},
             "clocks": clocks,

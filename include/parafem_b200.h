@@ -84,7 +84,11 @@ int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp,
  * pf_set_matrix_free(1) (call before pf_form_km_elastic): BASELINE config E.
  * storkm is never stored; every iteration recomputes the element operator
  * from g_coord_pp as sum_gp B^T (D (B p)) det w (p121 elements, nip = 8).
- * Only the diagonal of km is formed once, for the preconditioner.          */
+ * Only the diagonal of km is formed once, for the preconditioner.
+ * pf_set_matrix_free(2): as 1, but the inverse Jacobian and det*w of every
+ * Gauss point (10 doubles, 640 B per element) are stored at setup and read
+ * back instead of being rebuilt -- same bits as mode 1, no FP64 divisions
+ * in the loop ("partial assembly").                                        */
 int pf_form_km_elastic(pf_handle h, double e, double v);
 int pf_form_kc_laplace(pf_handle h, double kx, double ky, double kz);
 int pf_set_storkm(pf_handle h, const double *storkm_pp);

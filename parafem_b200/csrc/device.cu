@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <string>
@@ -74,7 +75,8 @@ struct pf_ctx {
   int nod = 0, nodof = 0, nip = 0, ntot = 0;
   int64_t nels = 0, neq = 0, ieq_start = 0, neq_pp = 0, nhalo = 0, nslots = 0;
   bool have_mesh = false, have_km = false, have_precon = false, matrix_free = false;
-  DevBuf<double> coord, km, utemp, diag_tmp;
+  DevBuf<double> coord, km, utemp, diag_tmp, geom;
+  int mf_mode = 0;
   DevBuf<int> ggl;
   DevBuf<unsigned int> csr_ptr, csr_pos;
 
@@ -86,6 +88,13 @@ struct pf_ctx {
   int nacc = 0;
   DevBuf<int> acc_slot;
   DevBuf<unsigned int> acc_ptr, acc_pos;
+
+  // peer-memory collectives (CUDA IPC mappings of the peers' p_ext / receive buffer / sync block)
+  bool peer_ok = false, use_peer = true, ptab_valid = false;
+  DevBuf<PeerSync> sync;
+  DevBuf<PeerTable> ptab;
+  PeerTable host_tab;
+  std::vector<void *> imports;
 
   // vectors (p_ext/u_ext/diag_ext are slot-indexed: [0] dump, 1..neq_pp owned, then halo)
   DevBuf<double> p_ext, u_ext, diag_ext, r, x, d, part, gath;
@@ -246,11 +255,10 @@ int launch_matvec_t(pf_handle h, const double *pvec, const State *st) {
   return 0;
 }
 
-template <int NOD, bool GATHER>
-int launch_mf_t(pf_handle h, const double *pvec, const State *st) {
+template <int NOD, bool GATHER, int GEOM, int kWarps>
+int launch_mf_w(pf_handle h, const double *pvec, const State *st) {
   using Cfg = MfCfg<NOD>;
-  constexpr int kWarps = 10;
-  auto kern = k_apply_mf<NOD, GATHER>;
+  auto kern = k_apply_mf<NOD, GATHER, GEOM, kWarps>;
   static bool attr_set = false;
   if (!attr_set) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem(kWarps)));
@@ -258,23 +266,49 @@ int launch_mf_t(pf_handle h, const double *pvec, const State *st) {
   }
   const int64_t ngroups = (h->nels + 3) / 4;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (ngroups + kWarps - 1) / kWarps));
-  kern<<<grid, kWarps * 32, Cfg::smem(kWarps), h->stream>>>(h->coord.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st);
+  kern<<<grid, kWarps * 32, Cfg::smem(kWarps), h->stream>>>(h->coord.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st,
+                                                            h->geom.p);
   h->launches++;
   CU(cudaGetLastError());
   return 0;
+}
+
+template <int NOD, bool GATHER, int GEOM>
+int launch_mf_t(pf_handle h, const double *pvec, const State *st) {
+  // hex20 keeps ~200 live registers with the prefetch pipeline: 8 warps (255 regs) avoid spills,
+  // 10 warps (168 regs) spill ~0.5 KB per thread; PF_TUNE=1 selects the 10-warp build
+  static const int tune = getenv("PF_TUNE") ? atoi(getenv("PF_TUNE")) : 0;
+  if (NOD == 20 && tune != 1) return launch_mf_w<NOD, GATHER, GEOM, 8>(h, pvec, st);
+  return launch_mf_w<NOD, GATHER, GEOM, 10>(h, pvec, st);
 }
 
 template <bool GATHER>
 int launch_matvec(pf_handle h, const double *pvec, const State *st) {
   Scope sc(h, K_MATVEC);
   if (h->matrix_free) {
-    if (h->nod == 20) return launch_mf_t<20, GATHER>(h, pvec, st);
-    return launch_mf_t<8, GATHER>(h, pvec, st);
+    if (h->mf_mode == 2) {
+      if (h->nod == 20) return launch_mf_t<20, GATHER, 2>(h, pvec, st);
+      return launch_mf_t<8, GATHER, 2>(h, pvec, st);
+    }
+    if (h->nod == 20) return launch_mf_t<20, GATHER, 0>(h, pvec, st);
+    return launch_mf_t<8, GATHER, 0>(h, pvec, st);
   }
+  // PF_TUNE selects an alternative tile shape (elements per tile x ring slots) for experiments
+  static const int tune = getenv("PF_TUNE") ? atoi(getenv("PF_TUNE")) : 0;
   switch (h->ntot) {
     case 60: return launch_matvec_t<60, 1, 7, GATHER>(h, pvec, st);
-    case 24: return launch_matvec_t<24, 8, 5, GATHER>(h, pvec, st);
-    case 8: return launch_matvec_t<8, 64, 6, GATHER>(h, pvec, st);
+    // measured on B200 (profiles/r01_tile_tuning.md): small tiles on many ring slots win --
+    // hex8 8x5 -> 0.90 of HBM peak, 2x16 -> 0.99; p123 64x6 -> 0.67, 16x16 -> 0.85
+    case 24:
+      if (tune == 1) return launch_matvec_t<24, 8, 5, GATHER>(h, pvec, st);
+      if (tune == 2) return launch_matvec_t<24, 1, 32, GATHER>(h, pvec, st);
+      if (tune == 3) return launch_matvec_t<24, 2, 24, GATHER>(h, pvec, st);
+      return launch_matvec_t<24, 2, 16, GATHER>(h, pvec, st);
+    case 8:
+      if (tune == 1) return launch_matvec_t<8, 64, 6, GATHER>(h, pvec, st);
+      if (tune == 2) return launch_matvec_t<8, 8, 32, GATHER>(h, pvec, st);
+      if (tune == 3) return launch_matvec_t<8, 16, 24, GATHER>(h, pvec, st);
+      return launch_matvec_t<8, 16, 16, GATHER>(h, pvec, st);
   }
   return fail(h, 3, "unsupported ntot %d (supported: 60, 24, 8)", h->ntot);
 }
@@ -289,10 +323,95 @@ int launch_scatter(pf_handle h, const State *st, bool diag, double *dst) {
   return 0;
 }
 
+
+void close_imports(pf_handle h) {
+  for (void *p : h->imports) if (p) cudaIpcCloseMemHandle(p);
+  h->imports.clear();
+  h->peer_ok = false;
+}
+
+// map the peers' buffers and fill the PeerTable; `all` = counts matrix, all[r*R+o] = number of
+// equations rank r gathers from owner o.  Every rank must reach the same verdict.
+int setup_peer(pf_handle h, const std::vector<int64_t> &all) {
+  const int R = h->nranks, me = h->rank;
+  h->peer_ok = false;
+  if (!h->use_peer || R > kMaxRanks) return 0;
+  struct Handles { cudaIpcMemHandle_t sync, pext, recv; };
+  Handles mine;
+  int ok = 1;
+  if (cudaIpcGetMemHandle(&mine.sync, h->sync.p) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine.pext, h->p_ext.p) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine.recv, h->recvbuf.p) != cudaSuccess) ok = 0;
+  cudaGetLastError();
+  DevBuf<char> d_mine, d_all;
+  CU(d_mine.alloc(sizeof(Handles))); CU(d_all.alloc(sizeof(Handles) * (size_t)R));
+  CU(cudaMemcpy(d_mine.p, &mine, sizeof mine, cudaMemcpyHostToDevice));
+  NC(g_nccl.AllGather(d_mine.p, d_all.p, sizeof(Handles), ncclChar, h->comm, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  std::vector<Handles> hs((size_t)R);
+  CU(cudaMemcpy(hs.data(), d_all.p, sizeof(Handles) * (size_t)R, cudaMemcpyDeviceToHost));
+  d_mine.release(); d_all.release();
+
+  PeerTable T;
+  if (h->ptab_valid) CU(cudaMemcpy(&T, h->ptab.p, sizeof T, cudaMemcpyDeviceToHost));  // keep the sequence counters
+  else memset(&T, 0, sizeof T);
+  T.rank = me; T.nranks = R; T.ticket[0] = T.ticket[1] = 0;
+  for (int r = 0; r < kMaxRanks; ++r) { T.sync[r] = nullptr; T.p_ext[r] = nullptr; T.recv[r] = nullptr; T.fwd_dst_off[r] = T.rev_dst_off[r] = 0; }
+  for (int r = 0; r < R && ok; ++r) {
+    if (r == me) { T.sync[r] = h->sync.p; T.p_ext[r] = h->p_ext.p; T.recv[r] = h->recvbuf.p; continue; }
+    void *ps = nullptr, *pp = nullptr, *pr = nullptr;
+    if (cudaIpcOpenMemHandle(&ps, hs[(size_t)r].sync, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+    h->imports.push_back(ps);
+    if (cudaIpcOpenMemHandle(&pp, hs[(size_t)r].pext, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+    h->imports.push_back(pp);
+    if (cudaIpcOpenMemHandle(&pr, hs[(size_t)r].recv, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+    h->imports.push_back(pr);
+    T.sync[r] = (PeerSync *)ps; T.p_ext[r] = (double *)pp; T.recv[r] = (double *)pr;
+    int64_t neq_pp_r, st_r;
+    pf_calc_neq_pp(h->neq, R, r + 1, &neq_pp_r, &st_r);
+    int64_t goff = 0; for (int o = 0; o < me; ++o) goff += all[(size_t)r * R + o];     // peer r's halo offset of owner `me`
+    int64_t poff = 0; for (int q = 0; q < me; ++q) poff += all[(size_t)q * R + r];     // owner r's receive offset of source `me`
+    T.fwd_dst_off[r] = 1 + neq_pp_r + goff;
+    T.rev_dst_off[r] = poff;
+  }
+  cudaGetLastError();
+  for (int r = 0; r < R; ++r) { T.put_off[r] = h->put_off[r]; T.get_off[r] = h->get_off[r]; }
+  T.put_off[R] = h->nput; T.get_off[R] = h->nhalo;
+  for (int r = R + 1; r <= kMaxRanks; ++r) { T.put_off[r] = h->nput; T.get_off[r] = h->nhalo; }
+  // unanimous verdict
+  DevBuf<int> d_ok, d_oks;
+  CU(d_ok.alloc(1)); CU(d_oks.alloc((size_t)R));
+  CU(cudaMemcpy(d_ok.p, &ok, sizeof ok, cudaMemcpyHostToDevice));
+  NC(g_nccl.AllGather(d_ok.p, d_oks.p, 1, ncclInt32, h->comm, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  std::vector<int> oks((size_t)R);
+  CU(cudaMemcpy(oks.data(), d_oks.p, (size_t)R * 4, cudaMemcpyDeviceToHost));
+  d_ok.release(); d_oks.release();
+  for (int v : oks) ok = ok && v;
+  if (!ok) {
+    close_imports(h);
+    if (me == 0) fprintf(stderr, "parafem_b200: CUDA IPC peer mapping unavailable, halo exchange stays on NCCL send/recv\n");
+    return 0;
+  }
+  CU(cudaMemcpy(h->ptab.p, &T, sizeof T, cudaMemcpyHostToDevice));
+  h->host_tab = T;
+  h->ptab_valid = true;
+  h->peer_ok = true;
+  return 0;
+}
+
 // forward halo exchange: owners send the p values their peers' elements need
-int halo_forward(pf_handle h, double *vec_ext, const State *st) {
+int halo_forward(pf_handle h, double *vec_ext, const State *st, bool peer = false) {
   if (h->nranks == 1) return 0;
   Scope sc(h, K_HALO);
+  if (peer && vec_ext == h->p_ext.p) {
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((h->nput + 255) / 256, 2 * h->sm_count));
+    k_halo_put_peer<<<grid, 256, 0, h->stream>>>(h->ptab.p, h->put_slot.p, vec_ext, (long long)h->nput, st);
+    k_halo_wait<<<1, 32, 0, h->stream>>>(h->ptab.p, 0, st);
+    h->launches += 2;
+    CU(cudaGetLastError());
+    return 0;
+  }
   if (h->nput > 0) {
     k_halo_pack<<<(int)((h->nput + 255) / 256), 256, 0, h->stream>>>(h->put_slot.p, vec_ext, h->sendbuf.p, (int)h->nput, st);
     h->launches++;
@@ -309,9 +428,21 @@ int halo_forward(pf_handle h, double *vec_ext, const State *st) {
 
 // reverse halo exchange: partial sums of remote equations go to their owners, which add
 // them after their own partial sum, sources in ascending rank order
-int halo_reverse(pf_handle h, double *vec_ext, const State *st) {
+int halo_reverse(pf_handle h, double *vec_ext, const State *st, bool peer = false) {
   if (h->nranks == 1) return 0;
   Scope sc(h, K_HALO);
+  if (peer) {
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((h->nhalo + 255) / 256, 2 * h->sm_count));
+    k_halo_rev_peer<<<grid, 256, 0, h->stream>>>(h->ptab.p, vec_ext, (long long)h->neq_pp, (long long)h->nhalo, st);
+    k_halo_wait<<<1, 32, 0, h->stream>>>(h->ptab.p, 1, st);
+    h->launches += 2;
+    if (h->nacc > 0) {
+      k_halo_accumulate<<<(h->nacc + 255) / 256, 256, 0, h->stream>>>(h->acc_slot.p, h->acc_ptr.p, h->acc_pos.p, h->recvbuf.p, vec_ext, h->nacc, st);
+      h->launches++;
+    }
+    CU(cudaGetLastError());
+    return 0;
+  }
   NC(g_nccl.GroupStart());
   for (int r = 0; r < h->nranks; ++r) {
     if (r == h->rank) continue;
@@ -344,12 +475,12 @@ int vec_grid(pf_handle h) {
 }
 
 // u_ext = A p_ext over this rank's elements + halo exchanges (gather, mat-vec, scatter)
-int apply_operator(pf_handle h, const State *st) {
+int apply_operator(pf_handle h, const State *st, bool peer = false) {
   int rc;
-  if ((rc = halo_forward(h, h->p_ext.p, st))) return rc;
+  if ((rc = halo_forward(h, h->p_ext.p, st, peer))) return rc;
   if ((rc = launch_matvec<true>(h, h->p_ext.p, st))) return rc;
   if ((rc = launch_scatter(h, st, false, h->u_ext.p))) return rc;
-  if ((rc = halo_reverse(h, h->u_ext.p, st))) return rc;
+  if ((rc = halo_reverse(h, h->u_ext.p, st, peer))) return rc;
   if (h->nfixed > 0) {
     k_fixed_u<<<(h->nfixed + 255) / 256, 256, 0, h->stream>>>(h->fix_slot.p, h->store.p, h->p_ext.p, h->u_ext.p, h->nfixed, st);
     h->launches++;
@@ -361,17 +492,19 @@ int one_iteration(pf_handle h) {
   State *st = h->state.p;
   const int single = h->nranks == 1;
   const long long n = h->neq_pp;
+  const bool peer = h->peer_ok && h->use_peer;
+  PeerTable *T = peer ? h->ptab.p : nullptr;
   int rc;
-  if ((rc = apply_operator(h, st))) return rc;
+  if ((rc = apply_operator(h, st, peer))) return rc;
   {
     Scope sc(h, K_VECTOR);
-    k_dot<<<vec_grid(h), kRedThreads, 0, h->stream>>>(h->p_ext.p + 1, h->u_ext.p + 1, n, h->part.p, st, single, 1);
+    k_dot<<<vec_grid(h), kRedThreads, 0, h->stream>>>(h->p_ext.p + 1, h->u_ext.p + 1, n, h->part.p, st, single, 1, T);
     h->launches++;
-    if ((rc = combine_scalars(h, 1))) return rc;
+    if (!peer && (rc = combine_scalars(h, 1))) return rc;
     k_pcg_update<<<vec_grid(h), kRedThreads, 0, h->stream>>>(h->diag_ext.p + 1, h->p_ext.p + 1, h->u_ext.p + 1, h->x.p, h->r.p,
-                                                              h->d.p, n, h->part.p, st, single, h->ratio_hist.p);
+                                                              h->d.p, n, h->part.p, st, single, h->ratio_hist.p, T);
     h->launches++;
-    if ((rc = combine_scalars(h, 2))) return rc;
+    if (!peer && (rc = combine_scalars(h, 2))) return rc;
     k_pupdate<<<grid_for(h, (n + 1) / 2, 256, 8), 256, 0, h->stream>>>(h->d.p, h->p_ext.p + 1, n, st);
     k_exit_test<<<1, 1, 0, h->stream>>>(st);
     h->launches += 2;
@@ -432,6 +565,10 @@ int pf_init(int rank, int nranks, int device, const void *id128, pf_handle *out)
     if (!id128) { delete h; return fail(nullptr, 2, "pf_init: nranks > 1 needs the 128-byte NCCL id"); }
     ncclUniqueId id; memcpy(&id, id128, sizeof id);
     NC(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+    CU(h->sync.alloc(1)); CU(cudaMemset(h->sync.p, 0, sizeof(PeerSync)));
+    CU(h->ptab.alloc(1)); CU(cudaMemset(h->ptab.p, 0, sizeof(PeerTable)));
+    const char *mode = getenv("PF_HALO");     // "nccl": keep every exchange on NCCL send/recv + all-gather
+    h->use_peer = !(mode && !strcmp(mode, "nccl"));
   }
   *out = h;
   return 0;
@@ -443,8 +580,19 @@ int pf_finalize(pf_handle h) {
   cudaStreamSynchronize(h->stream);
   collect_spans(h);
   for (auto e : h->pool) cudaEventDestroy(e);
-  if (h->comm) g_nccl.CommDestroy(h->comm);
-  h->coord.release(); h->km.release(); h->diag_tmp.release(); h->utemp.release(); h->ggl.release(); h->csr_ptr.release(); h->csr_pos.release();
+  close_imports(h);
+  if (h->comm) {
+    // peers must have closed their mappings of my buffers before I free them
+    DevBuf<int> a, b;
+    if (a.alloc(1) == cudaSuccess && b.alloc((size_t)h->nranks) == cudaSuccess) {
+      g_nccl.AllGather(a.p, b.p, 1, ncclInt32, h->comm, h->stream);
+      cudaStreamSynchronize(h->stream);
+    }
+    a.release(); b.release();
+    g_nccl.CommDestroy(h->comm);
+  }
+  h->sync.release(); h->ptab.release();
+  h->coord.release(); h->km.release(); h->diag_tmp.release(); h->geom.release(); h->utemp.release(); h->ggl.release(); h->csr_ptr.release(); h->csr_pos.release();
   h->put_slot.release(); h->sendbuf.release(); h->recvbuf.release(); h->acc_slot.release(); h->acc_ptr.release(); h->acc_pos.release();
   h->p_ext.release(); h->u_ext.release(); h->diag_ext.release(); h->r.release(); h->x.release(); h->d.release();
   h->part.release(); h->gath.release(); h->state.release(); h->ratio_hist.release(); h->fix_slot.release(); h->store.release();
@@ -516,6 +664,16 @@ int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp, con
     int64_t c, s;
     pf_calc_neq_pp(neq, h->nranks, h->rank + 1, &c, &s);
     NEED(c == neq_pp && s == ieq_start, "neq_pp/ieq_start do not match calc_neq_pp for this rank");
+  }
+  if (h->nranks > 1) {
+    // re-setup: drop the mappings of the peers' old buffers, and make sure every peer has
+    // dropped its mappings of mine, before anything is freed
+    close_imports(h);
+    DevBuf<int> a, b;
+    CU(a.alloc(1)); CU(b.alloc((size_t)h->nranks));
+    NC(g_nccl.AllGather(a.p, b.p, 1, ncclInt32, h->comm, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    a.release(); b.release();
   }
   h->nod = nod; h->nodof = nodof; h->nip = nip; h->ntot = ntot;
   h->nels = nels_pp; h->neq = neq; h->ieq_start = ieq_start; h->neq_pp = neq_pp;
@@ -624,6 +782,7 @@ int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp, con
     CU(cudaMemcpy(h->acc_slot.p, aslot.data(), aslot.size() * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->acc_ptr.p, aptr.data(), aptr.size() * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->acc_pos.p, apos.data(), apos.size() * 4, cudaMemcpyHostToDevice));
+    if ((rc = setup_peer(h, all))) return rc;
   }
   h->have_mesh = true;
   return 0;
@@ -647,6 +806,13 @@ int pf_form_km_elastic(pf_handle h, double e, double v) {
     h->km.release();
     CU(h->diag_tmp.alloc((size_t)h->nels * h->ntot));
     diag_only = h->diag_tmp.p;
+    if (h->mf_mode == 2) {
+      // geometric factors: inverse Jacobian (9) + det*w (1) per element and Gauss point
+      CU(h->geom.alloc((size_t)h->nels * 80));
+      if (h->nod == 20) rc = launch_mf_t<20, false, 1>(h, nullptr, nullptr);
+      else rc = launch_mf_t<8, false, 1>(h, nullptr, nullptr);
+      if (rc) return rc;
+    } else h->geom.release();
   } else if ((rc = alloc_km(h))) return rc;
   const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 16);
   if (h->nod == 20) k_form_km_elastic<20, 128><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, diag_only);
@@ -696,8 +862,10 @@ int pf_get_storkm(pf_handle h, int64_t iel0, int64_t n, double *out) {
 int pf_set_matrix_free(pf_handle h, int on) {
   if (!h) return 1;
   NEED(!on || !h->have_mesh || h->nodof == 3, "the matrix-free variant exists for the elastic elements (p121) only");
-  if ((on != 0) != h->matrix_free) { h->have_km = false; h->have_precon = false; }
+  NEED(on >= 0 && on <= 2, "mode must be 0 (stored), 1 (recompute from coordinates) or 2 (stored geometric factors)");
+  if ((on != 0) != h->matrix_free || on != h->mf_mode) { h->have_km = false; h->have_precon = false; }
   h->matrix_free = on != 0;
+  h->mf_mode = on;
   return 0;
 }
 
@@ -770,9 +938,10 @@ int pf_pcg_run(pf_handle h, double tol, int limit, int *iters, int *converged, d
   CU(cudaMemcpyAsync(h->state.p, &init, sizeof init, cudaMemcpyHostToDevice, h->stream));
   // d = M^-1 r, p = d, x = 0 (p121.f90:87; p123.f90:132)
   k_pcg_init<<<vec_grid(h), kRedThreads, 0, h->stream>>>(h->diag_ext.p + 1, h->r.p, h->d.p, h->p_ext.p + 1, h->x.p,
-                                                          (long long)h->neq_pp, h->part.p, h->state.p, h->nranks == 1);
+                                                          (long long)h->neq_pp, h->part.p, h->state.p, h->nranks == 1,
+                                                          (h->peer_ok && h->use_peer) ? h->ptab.p : nullptr);
   h->launches++;
-  if ((rc = combine_scalars(h, 0))) return rc;
+  if (!(h->peer_ok && h->use_peer) && (rc = combine_scalars(h, 0))) return rc;
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
   CU(cudaEventRecord(e0, h->stream));  // timest(3), p121.f90:89
@@ -895,7 +1064,7 @@ int pf_dot(pf_handle h, const double *a_pp, const double *b_pp, double *result) 
   if ((rc = upload_owned(h, h->p_ext.p, a_pp))) return rc;
   if ((rc = upload_owned(h, h->u_ext.p, b_pp))) return rc;
   k_dot<<<vec_grid(h), kRedThreads, 0, h->stream>>>(h->p_ext.p + 1, h->u_ext.p + 1, (long long)h->neq_pp, h->part.p, h->state.p,
-                                                     h->nranks == 1, -1);
+                                                     h->nranks == 1, -1, nullptr);
   h->launches++;
   CU(cudaGetLastError());
   std::vector<double> all((size_t)4 * h->nranks, 0.0);

@@ -221,6 +221,140 @@ __global__ void k_halo_pack(const int *__restrict__ put_slot, const double *__re
   if (i < n) sendbuf[i] = p_ext[put_slot[i]];
 }
 
+
+// ----------------------------------------------------------------------------
+// peer-memory collectives over NVLink/NVSwitch (one process per GPU, buffers mapped
+// with CUDA IPC).  Inside the PCG loop the halo exchanges and the scalar reductions are
+// plain st.global / ld.global on peer pointers plus release/acquire flags, issued from
+// the same kernels that produce / consume the data -- no NCCL launch, no host round trip.
+// Safety of buffer reuse: every PCG iteration passes two all-rank reductions, so a rank
+// cannot overwrite a peer's halo segment or receive buffer of iteration k+1 before that
+// peer has consumed iteration k.
+// ----------------------------------------------------------------------------
+constexpr int kMaxRanks = 16;
+struct PeerSync {                       // lives in every rank's exported buffer; written by peers
+  unsigned long long fwd_flag[kMaxRanks];
+  unsigned long long rev_flag[kMaxRanks];
+  unsigned long long red_flag[3][kMaxRanks];
+  double red_val[3][2][kMaxRanks][4];   // [reduction][seq parity][source rank][dot,max,max,-]
+};
+struct PeerTable {                      // local; pointers into the peers' address ranges
+  int rank, nranks;
+  PeerSync *sync[kMaxRanks];
+  double *p_ext[kMaxRanks];
+  double *recv[kMaxRanks];
+  long long fwd_dst_off[kMaxRanks];     // where my owned values land in peer r's p_ext
+  long long rev_dst_off[kMaxRanks];     // where my partial sums land in owner r's receive buffer
+  long long put_off[kMaxRanks + 1];     // my put list, segmented by destination rank
+  long long get_off[kMaxRanks + 1];     // my halo slots, segmented by owner rank
+  unsigned long long seq_fwd, seq_rev, seq_red[3];
+  unsigned int ticket[2];
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// all threads of ONE block call; loc[4] in shared memory; result (rank-ordered sum, maxima)
+// valid in thread 0.  Writes my partials into every peer, waits for theirs.
+__device__ __forceinline__ void peer_allreduce(PeerTable *T, int which, const double *loc, double *out) {
+  const unsigned long long seq = T->seq_red[which] + 1;
+  const int t = threadIdx.x, me = T->rank, n = T->nranks;
+  const int par = (int)(seq & 1);
+  if (t < n && t != me) {
+    volatile double *dst = T->sync[t]->red_val[which][par][me];
+    dst[0] = loc[0]; dst[1] = loc[1]; dst[2] = loc[2]; dst[3] = loc[3];
+    __threadfence_system();
+    st_release_sys(&T->sync[t]->red_flag[which][me], seq);
+    while (ld_acquire_sys(&T->sync[me]->red_flag[which][t]) < seq) { }
+  }
+  __syncthreads();
+  if (t == 0) {
+    double s = 0.0, m1 = 0.0, m2 = 0.0;
+    for (int r = 0; r < n; ++r) {
+      const volatile double *v = T->sync[me]->red_val[which][par][r];
+      const double a = (r == me) ? loc[0] : v[0];
+      const double b = (r == me) ? loc[1] : v[1];
+      const double c = (r == me) ? loc[2] : v[2];
+      s = (r == 0) ? a : s + a;      // ranks ascending, as k_scalars and the oracle
+      m1 = fmax(m1, b); m2 = fmax(m2, c);
+    }
+    out[0] = s; out[1] = m1; out[2] = m2;
+    T->seq_red[which] = seq;
+  }
+}
+
+// forward halo exchange by peer stores: owned values straight into the peers' p_ext halo segments
+__global__ void k_halo_put_peer(PeerTable *T, const int *__restrict__ put_slot, const double *__restrict__ p_ext,
+                                long long nput, const State *st) {
+  if (st && *(volatile const int *)&st->done) return;
+  __shared__ int flag;
+  const unsigned long long seq = T->seq_fwd + 1;
+  const int me = T->rank, n = T->nranks;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nput; k += (long long)gridDim.x * blockDim.x) {
+    int r = 0;
+    while (k >= T->put_off[r + 1]) ++r;
+    T->p_ext[r][T->fwd_dst_off[r] + (k - T->put_off[r])] = p_ext[put_slot[k]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(&T->ticket[0], 1u);
+    flag = (prev == gridDim.x - 1);
+    if (flag) T->ticket[0] = 0;
+  }
+  __syncthreads();
+  if (flag) {
+    __threadfence_system();
+    const int t = threadIdx.x;
+    if (t < n && t != me && T->put_off[t + 1] > T->put_off[t]) st_release_sys(&T->sync[t]->fwd_flag[me], seq);
+    __syncthreads();
+    if (t == 0) T->seq_fwd = seq;
+  }
+}
+// reverse: partial sums of remote equations straight into their owners' receive buffers
+__global__ void k_halo_rev_peer(PeerTable *T, const double *__restrict__ vec_ext, long long neq_pp, long long nhalo,
+                                const State *st) {
+  if (st && *(volatile const int *)&st->done) return;
+  __shared__ int flag;
+  const unsigned long long seq = T->seq_rev + 1;
+  const int me = T->rank, n = T->nranks;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nhalo; k += (long long)gridDim.x * blockDim.x) {
+    int r = 0;
+    while (k >= T->get_off[r + 1]) ++r;
+    T->recv[r][T->rev_dst_off[r] + (k - T->get_off[r])] = vec_ext[1 + neq_pp + k];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(&T->ticket[1], 1u);
+    flag = (prev == gridDim.x - 1);
+    if (flag) T->ticket[1] = 0;
+  }
+  __syncthreads();
+  if (flag) {
+    __threadfence_system();
+    const int t = threadIdx.x;
+    if (t < n && t != me && T->get_off[t + 1] > T->get_off[t]) st_release_sys(&T->sync[t]->rev_flag[me], seq);
+    __syncthreads();
+    if (t == 0) T->seq_rev = seq;
+  }
+}
+// dir 0: wait for the owners I gather from; dir 1: wait for the ranks that send me partial sums
+__global__ void k_halo_wait(PeerTable *T, int dir, const State *st) {
+  if (st && *(volatile const int *)&st->done) return;
+  const int t = threadIdx.x, me = T->rank;
+  if (t < T->nranks && t != me) {
+    const bool need = dir == 0 ? (T->get_off[t + 1] > T->get_off[t]) : (T->put_off[t + 1] > T->put_off[t]);
+    const unsigned long long seq = dir == 0 ? T->seq_fwd : T->seq_rev;
+    const unsigned long long *f = dir == 0 ? &T->sync[me]->fwd_flag[t] : &T->sync[me]->rev_flag[t];
+    if (need) while (ld_acquire_sys(f) < seq) { }
+  }
+}
+
 // ----------------------------------------------------------------------------
 // the fixed blocked reduction tree (mirrored by orc_dot_blocked in the oracle)
 //   chunk c = entries [2048c, 2048c+2048); thread t adds the entries
@@ -336,8 +470,9 @@ __global__ void k_scalars(State *st, const double *all /*nranks x 4*/, int nrank
 __global__ void __launch_bounds__(kRedThreads)
 k_pcg_init(const double *__restrict__ diag, const double *__restrict__ r, double *__restrict__ d,
            double *__restrict__ p, double *__restrict__ x, long long n, double *part, State *st,
-           int single_rank) {
+           int single_rank, PeerTable *T) {
   __shared__ double sh[8];
+  __shared__ double sh_loc[4], sh_out[3];
   __shared__ int flag;
   const long long nchunks = (n + kChunk - 1) / kChunk;
   for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
@@ -360,7 +495,13 @@ k_pcg_init(const double *__restrict__ diag, const double *__restrict__ r, double
     const double s = final_sum(part, nchunks, sh);
     if (threadIdx.x == 0) {
       st->loc[0] = s; st->loc[1] = 0.0; st->loc[2] = 0.0; st->loc[3] = 0.0;
+      sh_loc[0] = s; sh_loc[1] = 0.0; sh_loc[2] = 0.0; sh_loc[3] = 0.0;
       if (single_rank) finish_init(st, s);
+    }
+    if (T) {
+      __syncthreads();
+      peer_allreduce(T, 0, sh_loc, sh_out);
+      if (threadIdx.x == 0) finish_init(st, sh_out[0]);
     }
   }
 }
@@ -376,9 +517,10 @@ __global__ void k_fixed_u(const int *__restrict__ fix_slot, const double *__rest
 // pu = p.u over the owned equations
 __global__ void __launch_bounds__(kRedThreads)
 k_dot(const double *__restrict__ a, const double *__restrict__ b, long long n, double *part, State *st,
-      int single_rank, int mode /*1: p.u epilogue, -1: plain dot into loc[0]*/) {
+      int single_rank, int mode /*1: p.u epilogue, -1: plain dot into loc[0]*/, PeerTable *T) {
   if (mode == 1 && *(volatile const int *)&st->done) return;
   __shared__ double sh[8];
+  __shared__ double sh_loc[4], sh_out[3];
   __shared__ int flag;
   const long long nchunks = (n + kChunk - 1) / kChunk;
   for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
@@ -397,7 +539,13 @@ k_dot(const double *__restrict__ a, const double *__restrict__ b, long long n, d
     const double s = final_sum(part, nchunks, sh);
     if (threadIdx.x == 0) {
       st->loc[0] = s; st->loc[1] = 0.0; st->loc[2] = 0.0; st->loc[3] = 0.0;
+      sh_loc[0] = s; sh_loc[1] = 0.0; sh_loc[2] = 0.0; sh_loc[3] = 0.0;
       if (single_rank && mode == 1) finish_pu(st, s);
+    }
+    if (T && mode == 1) {
+      __syncthreads();
+      peer_allreduce(T, 1, sh_loc, sh_out);
+      if (threadIdx.x == 0) finish_pu(st, sh_out[0]);
     }
   }
 }
@@ -407,9 +555,10 @@ k_dot(const double *__restrict__ a, const double *__restrict__ b, long long n, d
 __global__ void __launch_bounds__(kRedThreads)
 k_pcg_update(const double *__restrict__ diag, const double *__restrict__ p, const double *__restrict__ u,
              double *__restrict__ x, double *__restrict__ r, double *__restrict__ d, long long n,
-             double *part /*3*nchunks*/, State *st, int single_rank, double *ratio_hist) {
+             double *part /*3*nchunks*/, State *st, int single_rank, double *ratio_hist, PeerTable *T) {
   if (*(volatile const int *)&st->done) return;
   __shared__ double sh[8];
+  __shared__ double sh_loc[4], sh_out[3];
   __shared__ int flag;
   const double alpha = st->alpha;
   const long long nchunks = (n + kChunk - 1) / kChunk;
@@ -442,7 +591,13 @@ k_pcg_update(const double *__restrict__ diag, const double *__restrict__ p, cons
     const double m2 = final_max(part + 2 * nchunks, nchunks, sh);
     if (threadIdx.x == 0) {
       st->loc[0] = s; st->loc[1] = m1; st->loc[2] = m2; st->loc[3] = 0.0;
+      sh_loc[0] = s; sh_loc[1] = m1; sh_loc[2] = m2; sh_loc[3] = 0.0;
       if (single_rank) finish_update(st, s, m1, m2, ratio_hist);
+    }
+    if (T) {
+      __syncthreads();
+      peer_allreduce(T, 2, sh_loc, sh_out);
+      if (threadIdx.x == 0) finish_update(st, sh_out[0], sh_out[1], sh_out[2], ratio_hist);
     }
   }
 }
@@ -634,10 +789,14 @@ struct MfCfg {
   static constexpr size_t smem(int warps) { return (size_t)(kDerDoubles + warps * kWarpDoubles) * 8; }
 };
 
-template <int NOD, bool GATHER>
-__global__ void __launch_bounds__(320, 1)
+// GEOM 0: rebuild jac / inverse / det at every point from the coordinates (config E as named);
+// GEOM 1: only write the 10 geometric factors per (element, point) -- inverse Jacobian and det*w;
+// GEOM 2: read those factors (640 B per hex element instead of 28 800 B of storkm) and skip the
+//         Jacobian pass and its 9 FP64 divisions.  Modes 0 and 2 produce identical bits.
+template <int NOD, bool GATHER, int GEOM, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
 k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, const double *__restrict__ pvec,
-           double *__restrict__ utemp, long long nels, const State *st) {
+           double *__restrict__ utemp, long long nels, const State *st, double *__restrict__ geom) {
   using Cfg = MfCfg<NOD>;
   constexpr int NTOT = Cfg::NTOT;
   if (st && *(volatile const int *)&st->done) return;
@@ -659,37 +818,96 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
   double *part = s_part + lane * Cfg::kPart;
   const double wt = c_tab.weights[ig];
   const long long ngroups = (nels + 3) / 4;
-  for (long long grp = (long long)blockIdx.x * nwarps + w; grp < ngroups; grp += (long long)gridDim.x * nwarps) {
+  // software pipeline: while group n is being computed, the coordinates / right-hand sides /
+  // geometric factors of group n+1 and the gather indices of group n+2 are in flight in registers
+  constexpr int NS = (4 * NTOT + 31) / 32;
+  double cr[NS], pr[NS];
+  int ir[NS];
+  double2 gr[5];
+  const long long gstride = (long long)gridDim.x * nwarps;
+  auto load_idx = [&](long long g) {
+    const long long e0 = g * 4;
+    const int ne = (int)((nels - e0) < 4 ? (nels - e0) : 4);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      const int s = lane + 32 * i;
+      ir[i] = (GATHER && GEOM != 1 && s < ne * NTOT) ? ggl[e0 * NTOT + s] : 0;
+    }
+  };
+  auto load_vals = [&](long long g) {
+    const long long e0 = g * 4;
+    const int ne = (int)((nels - e0) < 4 ? (nels - e0) : 4);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      const int s = lane + 32 * i;
+      if (s < ne * NTOT) {
+        if (GEOM != 2) cr[i] = g_coord[e0 * NTOT + s];
+        if (GEOM != 1) pr[i] = GATHER ? pvec[ir[i]] : pvec[e0 * NTOT + s];
+      }
+    }
+    if (GEOM == 2 && el < ne) {
+      const double2 *gf = reinterpret_cast<const double2 *>(geom + ((e0 + el) * 8 + ig) * 10);
+#pragma unroll
+      for (int q = 0; q < 5; ++q) gr[q] = gf[q];
+    }
+  };
+  long long grp = (long long)blockIdx.x * nwarps + w;
+  if (grp < ngroups) { load_idx(grp); load_vals(grp); }
+  if (grp + gstride < ngroups) load_idx(grp + gstride);
+  for (; grp < ngroups; grp += gstride) {
     const long long e0 = grp * 4;
     const int ne = (int)((nels - e0) < 4 ? (nels - e0) : 4);
     __syncwarp();
-    for (int s = lane; s < ne * NTOT; s += 32) {
-      const int le = s / NTOT, k = s - le * NTOT;
-      // coordinates: g_coord_pp(nod,3,nels) -> [m][d]; p: dof k = 3m+c -> [m][c]
-      const int d = k / NOD, m = k - d * NOD;
-      s_co[le * Cfg::kRow + m * 4 + d] = g_coord[(e0 + le) * NTOT + k];
-      const double pv = GATHER ? pvec[ggl[(e0 + le) * NTOT + k]] : pvec[(e0 + le) * NTOT + k];
-      s_p[le * Cfg::kRow + (k / 3) * 4 + (k % 3)] = pv;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      const int s = lane + 32 * i;
+      if (s < ne * NTOT) {
+        const int le = s / NTOT, k = s - le * NTOT;
+        // coordinates: g_coord_pp(nod,3,nels) -> [m][d]; p: dof k = 3m+c -> [m][c]
+        if (GEOM != 2) {
+          const int d = k / NOD, m = k - d * NOD;
+          s_co[le * Cfg::kRow + m * 4 + d] = cr[i];
+        }
+        if (GEOM != 1) s_p[le * Cfg::kRow + (k / 3) * 4 + (k % 3)] = pr[i];
+      }
+    }
+    double inv[9], f = 0.0;
+    if (GEOM == 2) {
+      inv[0] = gr[0].x; inv[1] = gr[0].y; inv[2] = gr[1].x; inv[3] = gr[1].y; inv[4] = gr[2].x; inv[5] = gr[2].y;
+      inv[6] = gr[3].x; inv[7] = gr[3].y; inv[8] = gr[4].x; f = gr[4].y;
     }
     __syncwarp();
+    if (grp + gstride < ngroups) {
+      load_vals(grp + gstride);
+      if (grp + 2 * gstride < ngroups) load_idx(grp + 2 * gstride);
+    }
     if (el < ne) {
-      double jac[9];
+      if (GEOM != 2) {
+        double jac[9];
 #pragma unroll
-      for (int q = 0; q < 9; ++q) jac[q] = 0.0;
+        for (int q = 0; q < 9; ++q) jac[q] = 0.0;
 #pragma unroll
-      for (int m = 0; m < NOD; ++m) {
-        const double2 dxy = *reinterpret_cast<const double2 *>(der + m * 4);
-        const double dz = der[m * 4 + 2];
-        const double2 cxy = *reinterpret_cast<const double2 *>(co + m * 4);
-        const double cz = co[m * 4 + 2];
-        // jac(a,b) at [b*3+a], node-ascending fma chains
-        jac[0] = fma(dxy.x, cxy.x, jac[0]); jac[1] = fma(dxy.y, cxy.x, jac[1]); jac[2] = fma(dz, cxy.x, jac[2]);
-        jac[3] = fma(dxy.x, cxy.y, jac[3]); jac[4] = fma(dxy.y, cxy.y, jac[4]); jac[5] = fma(dz, cxy.y, jac[5]);
-        jac[6] = fma(dxy.x, cz, jac[6]);    jac[7] = fma(dxy.y, cz, jac[7]);    jac[8] = fma(dz, cz, jac[8]);
+        for (int m = 0; m < NOD; ++m) {
+          const double2 dxy = *reinterpret_cast<const double2 *>(der + m * 4);
+          const double dz = der[m * 4 + 2];
+          const double2 cxy = *reinterpret_cast<const double2 *>(co + m * 4);
+          const double cz = co[m * 4 + 2];
+          // jac(a,b) at [b*3+a], node-ascending fma chains
+          jac[0] = fma(dxy.x, cxy.x, jac[0]); jac[1] = fma(dxy.y, cxy.x, jac[1]); jac[2] = fma(dz, cxy.x, jac[2]);
+          jac[3] = fma(dxy.x, cxy.y, jac[3]); jac[4] = fma(dxy.y, cxy.y, jac[4]); jac[5] = fma(dz, cxy.y, jac[5]);
+          jac[6] = fma(dxy.x, cz, jac[6]);    jac[7] = fma(dxy.y, cz, jac[7]);    jac[8] = fma(dz, cz, jac[8]);
+        }
+        const double det = det3(jac);
+        inv3(jac, det, inv);
+        f = det * wt;
+        if (GEOM == 1) {
+          double *gf = geom + ((e0 + el) * 8 + ig) * 10;
+#pragma unroll
+          for (int q = 0; q < 9; ++q) gf[q] = inv[q];
+          gf[9] = f;
+        }
       }
-      const double det = det3(jac);
-      double inv[9];
-      inv3(jac, det, inv);
+      if (GEOM != 1) {
       double e0_ = 0.0, e1_ = 0.0, e2_ = 0.0, e3_ = 0.0, e4_ = 0.0, e5_ = 0.0;
 #pragma unroll
       for (int m = 0; m < NOD; ++m) {
@@ -709,7 +927,6 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
         e5_ = fma(gz, pxy.x, e5_); e5_ = fma(gx, pz, e5_);
       }
       const double eps[6] = {e0_, e1_, e2_, e3_, e4_, e5_};
-      const double f = det * wt;
       double sig[6];
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
@@ -729,15 +946,18 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
         part[3 * m + 1] = fma(gz, sig[4], fma(gx, sig[3], fma(gy, sig[1], 0.0)));
         part[3 * m + 2] = fma(gx, sig[5], fma(gy, sig[4], fma(gz, sig[2], 0.0)));
       }
+      }
     }
     __syncwarp();
-    for (int s = lane; s < ne * NTOT; s += 32) {
-      const int le = s / NTOT, k = s - le * NTOT;
-      const double *row = s_part + (le * 8) * Cfg::kPart + k;
-      double acc = row[0];
+    if (GEOM != 1) {
+      for (int s = lane; s < ne * NTOT; s += 32) {
+        const int le = s / NTOT, k = s - le * NTOT;
+        const double *row = s_part + (le * 8) * Cfg::kPart + k;
+        double acc = row[0];
 #pragma unroll
-      for (int g = 1; g < 8; ++g) acc = acc + row[g * Cfg::kPart];
-      utemp[(e0 + le) * NTOT + k] = acc;
+        for (int g = 1; g < 8; ++g) acc = acc + row[g * Cfg::kPart];
+        utemp[(e0 + le) * NTOT + k] = acc;
+      }
     }
   }
 }

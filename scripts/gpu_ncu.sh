@@ -8,8 +8,8 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 tail -3 gpurun_out/ncu_launch_bench.log | cut -c1-400
 # the mat-vec kernel, full set, on an 80^3 cube (storkm 14.7 GB >> L2) so the ~40 replays stay cheap
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_matvec -s 4 -c 2 -f -o gpurun_out/prof_matvec_n80 \
-    python bench.py --n 80 --steps 4 --warmup 3 --no-cpu --no-solve > gpurun_out/ncu_full_bench.log 2>&1
+    python bench.py --cube 80 --steps 4 --warmup 3 --no-cpu --no-solve > gpurun_out/ncu_full_bench.log 2>&1
 tail -3 gpurun_out/ncu_full_bench.log | cut -c1-400
 ls -la gpurun_out
 # other element types, device-resident bench only (hex8 200^3 = BASELINE config D on one GPU)
-timeout 600 python bench.py --nod 8 --n 200 --steps 50 --no-cpu > gpurun_out/bench_hex8_n200.json 2> gpurun_out/bench_hex8_n200.err; cut -c1-1500 gpurun_out/bench_hex8_n200.json; tail -3 gpurun_out/bench_hex8_n200.err
+timeout 600 python bench.py --hex 8 --cube 200 --steps 50 --no-cpu > gpurun_out/bench_hex8_n200.json 2> gpurun_out/bench_hex8_n200.err; cut -c1-1500 gpurun_out/bench_hex8_n200.json; tail -3 gpurun_out/bench_hex8_n200.err

@@ -23,10 +23,11 @@ def gpu():
     s.close()
 
 
+@pytest.mark.parametrize("mode", [1, 2])      # 1: rebuild from coordinates; 2: stored geometric factors
 @pytest.mark.parametrize("name", list(CASES))
-def test_matrix_free_products_equal_oracle(gpu, name):
+def test_matrix_free_products_equal_oracle(gpu, name, mode):
     p = CASES[name]()
-    solver.setup_problem(gpu, p, matrix_free=True)
+    solver.setup_problem(gpu, p, matrix_free=mode)
     rng = np.random.RandomState(2)
     pm = rng.randn(p.nels, p.ntot)
     ut = gpu.matvec(pm)
@@ -43,10 +44,11 @@ def test_matrix_free_products_equal_oracle(gpu, name):
         gpu.get_storkm()
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("name", list(CASES))
-def test_matrix_free_pcg_equals_oracle(gpu, name):
+def test_matrix_free_pcg_equals_oracle(gpu, name, mode):
     p = CASES[name]()
-    solver.setup_problem(gpu, p, matrix_free=True)
+    solver.setup_problem(gpu, p, matrix_free=mode)
     x, iters, conv = gpu.pcg_solve(p.r_pp, p.tol, p.limit)
     km = oracle.form_km_elastic(p.g_coord_pp, p.nod, p.nip, p.e, p.v)
     mf = dict(g_coord_pp=p.g_coord_pp, nod=p.nod, nip=p.nip, e=p.e, v=p.v)
