@@ -220,6 +220,18 @@ int pf_read_lds(const char *job, int64_t loaded, int nodof, int32_t *node, doubl
 int pf_coords_pp(int nod, int64_t nels_pp, const int32_t *g_num_pp,
                  const double *g_coord, double *g_coord_pp);
 
+/* Output section (p121.f90:124-138): calc_nodes_pp (gather_scatter.f90:2139-2234);
+ * nodal values of the owned equations for nodes node_start..node_start+nodes_pp-1
+ * (what scatter_nodes, gather_scatter.f90:1786-1929, yields for a conforming field:
+ * restrained freedoms 0), out(nodof,nodes_pp); and the EnSight Gold ASCII writer of
+ * dismsh_ensi_p (output.f90:2983-3111): 4 header lines, then component-major values,
+ * one per line, Fortran e12.<decimals> (5 in the current source, 4 in the shipped
+ * p121_demo.ensi.DISPL-000001).                                               */
+void pf_calc_nodes_pp(int64_t nn, int npes, int numpe, int64_t *nodes_pp, int64_t *node_start);
+int pf_nodal_values(int nodof, int64_t nn, const int32_t *nf, int64_t ieq_start, int64_t neq_pp,
+                    const double *x_pp, int64_t node_start, int64_t nodes_pp, double *out);
+int pf_write_ensi(const char *path, int numvar, int64_t nn, const double *values, int decimals);
+
 /* Halo tables (make_ggl, gather_scatter.f90:1387-1780, rebuilt from g_g_pp).
  * Local numbering of this rank's gather buffer: slot 0 = restrained dump
  * slot, 1..neq_pp = owned equations, then the remote equations the local

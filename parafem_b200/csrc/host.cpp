@@ -451,6 +451,52 @@ int pf_coords_pp(int nod, int64_t nels_pp, const int32_t *g_num_pp, const double
   return 0;
 }
 
+// Fortran Ew.d edit descriptor (0.ddddE+xx), as dismsh_ensi_p's '(e12.5)' (output.f90:3050,3100)
+static void fortran_e(char *out, size_t cap, double x, int w, int d) {
+  char buf[64], body[64];
+  if (x == 0.0) snprintf(body, sizeof body, "0.%0*dE+00", d, 0);
+  else {
+    snprintf(buf, sizeof buf, "%.*E", d - 1, x);
+    std::string m(buf);
+    const size_t epos = m.find('E');
+    const int ex = atoi(m.c_str() + epos + 1) + 1;
+    std::string digits;
+    for (char c : m.substr(0, epos)) if (c >= '0' && c <= '9') digits.push_back(c);
+    snprintf(body, sizeof body, "%s0.%sE%c%02d", x < 0 ? "-" : "", digits.c_str(), ex < 0 ? '-' : '+', ex < 0 ? -ex : ex);
+  }
+  snprintf(out, cap, "%*s", w, body);
+}
+
+void pf_calc_nodes_pp(int64_t nn, int npes, int numpe, int64_t *nodes_pp, int64_t *node_start) {
+  even_split(nn, npes, numpe, nodes_pp, node_start);
+}
+
+int pf_nodal_values(int nodof, int64_t nn, const int32_t *nf, int64_t ieq_start, int64_t neq_pp,
+                    const double *x_pp, int64_t node_start, int64_t nodes_pp, double *out) {
+  if (node_start < 1 || node_start + nodes_pp - 1 > nn) return 1;
+  for (int64_t j = 0; j < nodes_pp; ++j)
+    for (int k = 0; k < nodof; ++k) {
+      const int64_t eq = nf[(node_start - 1 + j) * nodof + k];
+      out[j * nodof + k] = (eq >= ieq_start && eq < ieq_start + neq_pp) ? x_pp[eq - ieq_start] : 0.0;
+    }
+  return 0;
+}
+
+int pf_write_ensi(const char *path, int numvar, int64_t nn, const double *values, int decimals) {
+  FILE *f = fopen(path, "w");
+  if (!f) return 1;
+  fprintf(f, "Alya Ensight Gold --- %s per-node variable file\n", numvar == 1 ? "Scalar" : "Vector");
+  fprintf(f, "part\n%s\ncoordinates\n", numvar == 1 ? "    1" : "     1");
+  char buf[64];
+  for (int c = 0; c < numvar; ++c)
+    for (int64_t j = 0; j < nn; ++j) {
+      fortran_e(buf, sizeof buf, values[j * numvar + c], 12, decimals);
+      fprintf(f, "%s\n", buf);
+    }
+  fclose(f);
+  return 0;
+}
+
 int pf_make_ggl(int ntot, int64_t nels_pp, const int32_t *g_g_pp, int64_t neq, int npes, int numpe,
                 int32_t *ggl_pp, int64_t cap, int32_t *halo_eq, int64_t *halo_cnt, int64_t *nhalo) {
   int64_t neq_pp, ieq_start;

@@ -138,6 +138,15 @@ int main(int argc, char **argv) {
     fprintf(o, "\nThis analysis took  :%10.4f\n", now() - t_start);
   }
   if (f) fclose(f);
+  // displacements for ParaView (p121.f90:124-138)
+  {
+    int64_t nodes_pp, node_start;
+    pf_calc_nodes_pp(nn, 1, 1, &nodes_pp, &node_start);
+    std::vector<double> disp((size_t)nodes_pp * nodof);
+    pf_nodal_values(nodof, nn, nf.data(), ieq_start, neq_pp, x.data(), node_start, nodes_pp, disp.data());
+    const std::string ensi = res_path.substr(0, res_path.size() - 4) + ".ensi.DISPL-000001";
+    pf_write_ensi(ensi.c_str(), nodof, nn, disp.data(), 5);
+  }
   pf_finalize(h);
   return converged ? 0 : 3;
 }

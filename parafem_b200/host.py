@@ -208,3 +208,20 @@ def make_ggl(prob):
     check(L.pf_make_ggl(prob.ntot, prob.nels_pp, ptr(prob.g_g_pp), prob.neq, prob.npes, prob.numpe,
                         ptr(ggl), halo.size, ptr(halo), ptr(cnt), C.byref(nh)), what="pf_make_ggl")
     return ggl, halo[:nh.value], cnt
+
+
+def nodal_values(prob, x_pp):
+    """Nodal field of this rank's node range (calc_nodes_pp + what scatter_nodes yields)."""
+    L = lib()
+    a, b = c_i64(), c_i64()
+    L.pf_calc_nodes_pp(prob.nn, prob.npes, prob.numpe, C.byref(a), C.byref(b))
+    out = np.zeros((a.value, prob.nodof))
+    check(L.pf_nodal_values(prob.nodof, prob.nn, ptr(prob.nf), prob.ieq_start, prob.neq_pp, ptr(f64(x_pp)),
+                            b.value, a.value, ptr(out)), what="pf_nodal_values")
+    return out
+
+
+def write_ensi(path, values, decimals=5):
+    """dismsh_ensi_p's EnSight Gold ASCII file: values (nn, numvar), component-major on disk."""
+    v = f64(values)
+    check(lib().pf_write_ensi(str(path).encode(), v.shape[1], v.shape[0], ptr(v), decimals), what="pf_write_ensi")

@@ -46,6 +46,8 @@ def main():
     json.dump(digests, open(f"{HERE}/p121_demo_digests.json", "w"), indent=1)
     disp = np.loadtxt(f"{REF}/5th_ed/p121/demo/p121_demo.ensi.DISPL-000001", skiprows=4)
     np.savez_compressed(f"{HERE}/p121_demo_displ.npz", displ=disp.reshape(3, p.nn).T.astype(np.float32))
+    with open(f"{REF}/5th_ed/p121/demo/p121_demo.ensi.DISPL-000001") as f, open(f"{HERE}/p121_demo_ensi_head.txt", "w") as g:
+        g.writelines([next(f) for _ in range(204)])   # header + the first 200 x-displacements, verbatim
     print("golden fixtures written to", HERE)
 
 

@@ -108,3 +108,31 @@ def test_deck_reader_roundtrip(tmp_path, tiny, golden):
     c = tiny.g_coord_pp[0]
     corners = c[:, [0, 2, 4, 6, 12, 14, 16, 18]]
     assert np.allclose(corners.min(axis=1), c.min(axis=1)) and np.allclose(corners.max(axis=1), c.max(axis=1))
+
+
+def test_ensight_writer_matches_the_shipped_file_format(tmp_path, golden, demo):
+    """dismsh_ensi_p (output.f90:2983-3111) restated in host.cpp: header lines byte-identical to
+    p121_demo.ensi.DISPL-000001, one value per line in the golden file's 12-column 0.ddddE+xx
+    format, component-major; values (here: the oracle's solution) agree with the golden's to
+    the printed digits."""
+    import oracle
+    km = oracle.form_km_elastic(demo.g_coord_pp, 20, 8, demo.e, demo.v)
+    r = oracle.pcg(km, demo.g_g_pp, demo.neq, demo.r_pp, demo.tol, demo.limit, npes=4, red_mode=1)
+    disp = host.nodal_values(demo, r["x"])
+    assert disp.shape == (demo.nn, 3)
+    path = tmp_path / "demo.ensi.DISPL-000001"
+    host.write_ensi(path, disp, decimals=4)
+    mine = open(path).read().splitlines()
+    gold = open(os.path.join(golden, "p121_demo_ensi_head.txt")).read().splitlines()
+    assert mine[:4] == gold[:4]
+    assert len(mine) == 4 + 3 * demo.nn
+    assert all(len(l) == 12 for l in mine[4:])
+    import re
+    assert all(re.fullmatch(r" {1,2}-?0\.\d{4}E[+-]\d\d", l) for l in mine[4:2000])
+    a = np.array([float(l) for l in mine[4:204]])
+    b = np.array([float(l) for l in gold[4:204]])
+    assert np.abs(a - b).max() <= 1.0001e-4                                # one unit of the 4th printed digit
+    assert sum(x == y for x, y in zip(mine[4:204], gold[4:204])) > 100      # most lines are identical text (119 of 200;
+    # the rest differ by one unit of the last digit: golden stopped at iteration 295, this solve at 297)
+    # y-displacements start after nn x-values (component-major)
+    assert float(mine[4 + demo.nn]) == 0.0
