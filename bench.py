@@ -48,6 +48,8 @@ def parse():
                          "2 = same with stored geometric factors (FP64-pipe roofline)")
     ap.add_argument("--weak", action="store_true",
                     help="weak scaling: n x (n*N) x n elements, i.e. one n^3 slab of y-planes per GPU")
+    ap.add_argument("--no-variants", dest="variants", action="store_false",
+                    help="skip the two matrix-free variants of the same workload (key `variants`)")
     ap.add_argument("--no-solve", action="store_true", help="skip the solve to convergence (time-to-solution)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     return ap.parse_args()
@@ -202,74 +204,88 @@ def main():
     storkm_bytes_pp = prob.nels_pp * ntot * ntot * 8
 
     K, W = args.steps, max(args.warmup, 3)
-    # ---- device-resident arm: `value` --------------------------------------------------------
-    s.pcg_load_rhs(prob.r_pp)
-    s.pcg_run(-1.0, W)                       # W untimed warm-up steps (tol < 0: never converges)
-    s.set_profile(True)
-    s.reset_profile()
-    sampler = ClockSampler(local)
-    barrier()
-    launches0 = s.kernel_launches()
-    if rank == 0:
-        sampler.start()
-    iters, _, ms = s.pcg_run(-1.0, K)        # exactly K steps, CUDA events on the solver stream
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    launches = s.kernel_launches() - launches0
-    assert iters == K
-    ms = maxf(ms)
-    mv_ms, mv_n = s.kernel_ms(0)
-    sc_ms, sc_n = s.kernel_ms(1)
-    vec_ms, vec_n = s.kernel_ms(2)
-    halo_ms, halo_n = s.kernel_ms(3)
-    s.set_profile(False)
-    value = prob.neq * K / (ms / 1e3) / 1e6
-
-    # ---- end-to-end arm: host buffers through pf_pcg_solve ----------------------------------
+    import ctypes as C
+    from parafem_b200._lib import lib, ptr
     r_pin = torch.empty(prob.neq_pp, dtype=torch.float64).pin_memory()
     x_pin = torch.empty(prob.neq_pp, dtype=torch.float64).pin_memory()
     r_np, x_np = r_pin.numpy(), x_pin.numpy()
     r_np[:] = prob.r_pp
-    import ctypes as C
-    from parafem_b200._lib import lib, ptr
     it_c, cv_c = C.c_int(), C.c_int()
 
-    def e2e_once(k):
+    def measure():
+        """W warm-up + K timed iterations device-resident (`value`), then the same through
+        pf_pcg_solve with pinned host buffers (`e2e`)."""
+        s.pcg_load_rhs(prob.r_pp)
+        s.pcg_run(-1.0, W)                       # W untimed warm-up steps (tol < 0: never converges)
+        s.set_profile(True)
+        s.reset_profile()
+        sampler = ClockSampler(local)
         barrier()
-        t = time.perf_counter()
-        rc = lib().pf_pcg_solve(s._h, ptr(r_np), -1.0, k, ptr(x_np), C.byref(it_c), C.byref(cv_c))
-        assert rc == 0 and it_c.value == k
-        chk = float(x_np[0])                 # the step's result is read on the host
-        dt = time.perf_counter() - t
-        return maxf(dt), chk
+        launches0 = s.kernel_launches()
+        if rank == 0:
+            sampler.start()
+        iters, _, ms = s.pcg_run(-1.0, K)        # exactly K steps, CUDA events on the solver stream
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        launches = s.kernel_launches() - launches0
+        assert iters == K
+        ms = maxf(ms)
+        km = {name: s.kernel_ms(i) for i, name in enumerate(("matvec", "scatter", "vector", "halo"))}
+        s.set_profile(False)
 
-    e2e_once(W)
-    e2e_s, _ = e2e_once(K)
-    e2e_value = prob.neq * K / e2e_s / 1e6
+        def e2e_once(k):
+            barrier()
+            t = time.perf_counter()
+            rc = lib().pf_pcg_solve(s._h, ptr(r_np), -1.0, k, ptr(x_np), C.byref(it_c), C.byref(cv_c))
+            assert rc == 0 and it_c.value == k
+            chk = float(x_np[0])                 # the step's result is read on the host
+            return maxf(time.perf_counter() - t), chk
 
-    # ---- solve to convergence: time-to-solution, iteration count ---------------------------
-    tts = None
-    if not args.no_solve:
+        e2e_once(W)
+        e2e_s, _ = e2e_once(K)
+        return {"ms": ms, "value": prob.neq * K / (ms / 1e3) / 1e6, "launches": launches, "clocks": clocks,
+                "kernel_ms": km, "e2e_s": e2e_s, "e2e_value": prob.neq * K / e2e_s / 1e6}
+
+    def solve_to_convergence():
         s.pcg_load_rhs(prob.r_pp)
         barrier()
         it_full, conv, ms_full = s.pcg_run(prob.tol, prob.limit)
         ms_full = maxf(ms_full)
         x = s.pcg_get_x()
-        tts = {"iters": it_full, "converged": bool(conv), "solve_s": ms_full / 1e3,
-               "mdof_iters_per_s": prob.neq * it_full / (ms_full / 1e3) / 1e6,
-               "x1": float(x[0]) if rank == 0 else None, "tol": prob.tol}
+        return {"iters": it_full, "converged": bool(conv), "solve_s": ms_full / 1e3,
+                "mdof_iters_per_s": prob.neq * it_full / (ms_full / 1e3) / 1e6,
+                "x1": float(x[0]) if rank == 0 else None, "tol": prob.tol}
+
+    def mf_flops(mode, nodn):
+        # flops of the operator form per element (k_apply_mf), fma = 2 flop: per Gauss point and node
+        # jac 9 fma (mode 1 only), deriv 9 fma twice, eps 9 fma, B^T sigma 9 fma; per point the
+        # determinant/adjugate (~45 flop, mode 1 only) and sigma (36 fma + 7 mul); 7 adds per dof
+        if mode == 2:
+            return 8 * (2 * 36 * nodn + 2 * 36 + 7) + 7 * 3 * nodn
+        return 8 * (2 * 45 * nodn + 45 + 2 * 36 + 7) + 7 * 3 * nodn
+
+    def mf_roofline(mode, m, peak):
+        mv_ms_, mv_n_ = m["kernel_ms"]["matvec"]
+        avg = mv_ms_ / max(mv_n_, 1)
+        fl = prob.nels_pp * mf_flops(mode, args.nod)
+        return {"bound": "fp64", "achieved": fl / (avg / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                "frac": fl / (avg / 1e3) / 1e12 / peak, "traffic": None,
+                "kernel": "k_apply_mf (matrix-free operator form, gather fused)",
+                "peak_kind": "DFMA micro-benchmark on this device (pf_measure_fp64), fma = 2 flop",
+                "algorithmic_flops_per_launch": fl, "flops_per_element": mf_flops(mode, args.nod),
+                "avg_launch_ms": avg, "launches_timed": int(mv_n_)}
+
+    m = measure()
+    ms, value, launches, clocks = m["ms"], m["value"], m["launches"], m["clocks"]
+    (mv_ms, mv_n), (sc_ms, sc_n), (vec_ms, vec_n), (halo_ms, halo_n) = (m["kernel_ms"][k] for k in ("matvec", "scatter", "vector", "halo"))
+    e2e_s, e2e_value = m["e2e_s"], m["e2e_value"]
+
+    # ---- solve to convergence: time-to-solution, iteration count ---------------------------
+    tts = None if args.no_solve else solve_to_convergence()
 
     pk, pk_kind = peaks()
     mv_avg_ms = mv_ms / max(mv_n, 1)
     achieved = storkm_bytes_pp / (mv_avg_ms / 1e3) / 1e9 if mv_n else None
-    # matrix-free: flops of the operator form per element (k_apply_mf), fma = 2 flop:
-    # per Gauss point 9*nod (jac) + 2*(9+12)*nod... counted from the kernel source:
-    #   jac 9 fma/node, deriv 9 fma/node twice, eps 9 fma/node, B^T sigma 9 fma/node  -> 45*nod fma
-    #   + determinant/adjugate (~45 flop) + sigma (36 fma + 7 mul); 8 points; + 7 adds per dof
-    nodn = args.nod
-    mf_flops_per_el = 8 * (2 * 45 * nodn + 45 + 2 * 36 + 7) + 7 * 3 * nodn
-    if args.matrix_free == 2:   # no Jacobian pass (9 fma/node) and no determinant / adjugate
-        mf_flops_per_el = 8 * (2 * 36 * nodn + 2 * 36 + 7) + 7 * 3 * nodn
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -277,6 +293,23 @@ def main():
         traffic = tj.get(key, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
+
+    # ---- the matrix-free variants of the same workload (BASELINE config E), same process ----------
+    variants = None
+    if args.variants and args.program == "p121" and not args.matrix_free:
+        variants = {}
+        peak = None
+        for mode, name in ((2, "matrix_free_geometric_factors"), (1, "matrix_free_rebuilt_from_coordinates")):
+            solver.setup_problem(s, prob, matrix_free=mode)
+            peak = peak or s.measure_fp64()
+            mm = measure()
+            v = {"value": mm["value"], "unit": UNIT, "ms_per_step": mm["ms"] / K,
+                 "e2e": {"value": mm["e2e_value"], "unit": UNIT},
+                 "kernel_ms_per_step": {k: mm["kernel_ms"][k][0] / K for k in mm["kernel_ms"]},
+                 "roofline": mf_roofline(mode, mm, peak), "gpu_launches": int(mm["launches"])}
+            if mode == 2 and not args.no_solve:
+                v["time_to_solution"] = solve_to_convergence()
+            variants[name] = v
 
     cpu = None
     if rank == 0 and nranks == 1 and not args.no_cpu and args.program == "p121":
@@ -304,20 +337,14 @@ def main():
                           "kernel": "k_matvec (storkm stream; gather fused)", "peak_kind": pk_kind,
                           "algorithmic_bytes_per_launch": storkm_bytes_pp, "avg_launch_ms": mv_avg_ms,
                           "launches_timed": int(mv_n)} if not args.matrix_free else
-                         {"bound": "fp64", "achieved": prob.nels_pp * mf_flops_per_el / (mv_avg_ms / 1e3) / 1e12,
-                          "peak": fp64_tflops, "unit": "TFLOP/s",
-                          "frac": prob.nels_pp * mf_flops_per_el / (mv_avg_ms / 1e3) / 1e12 / fp64_tflops,
-                          "traffic": None, "kernel": "k_apply_mf (matrix-free operator form, gather fused)",
-                          "peak_kind": "DFMA micro-benchmark on this device (pf_measure_fp64), fma = 2 flop",
-                          "algorithmic_flops_per_launch": prob.nels_pp * mf_flops_per_el,
-                          "flops_per_element": mf_flops_per_el, "avg_launch_ms": mv_avg_ms,
-                          "launches_timed": int(mv_n)}),
+                         mf_roofline(args.matrix_free, m, fp64_tflops)),
             "variant": {0: "stored storkm", 1: "matrix-free, rebuilt from coordinates (config E)",
                         2: "matrix-free, stored geometric factors"}[args.matrix_free],
             "kernel_ms_per_step": {"matvec": mv_ms / K, "scatter": sc_ms / K, "vector_and_reductions": vec_ms / K,
                                    "halo": halo_ms / K},
             "clocks": clocks,
             "time_to_solution": tts,
+            "variants": variants,
             "setup_s": {"mesh_host": t_mesh, "device_setup_incl_storkm": t_dev_setup},
             "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
         }
