@@ -220,6 +220,14 @@ int pf_read_lds(const char *job, int64_t loaded, int nodof, int32_t *node, doubl
 int pf_coords_pp(int nod, int64_t nels_pp, const int32_t *g_num_pp,
                  const double *g_coord, double *g_coord_pp);
 
+/* p12meshgen's output side for p121 (p12meshgen.f90:244-323): <job>.d/.bnd/.lds/.dat in the
+ * reference's formats ((I12,3E14.6) nodes, Abaqus-ordered 20-node bricks with meshgen = 2,
+ * (I15,3I6) restraints, E16.8 loads).  g_coord(3,nn), g_num(nod,nels) in S&G order,
+ * rest(nr,4) column-major, node(loaded), val(3,loaded).                      */
+int pf_write_deck_p121(const char *job, int nod, int64_t nels, int64_t nn, int64_t nr, int nip,
+                       int64_t loaded, double e, double v, double tol, int limit, const double *g_coord,
+                       const int32_t *g_num, const int32_t *rest, const int32_t *node, const double *val);
+
 /* Output section (p121.f90:124-138): calc_nodes_pp (gather_scatter.f90:2139-2234);
  * nodal values of the owned equations for nodes node_start..node_start+nodes_pp-1
  * (what scatter_nodes, gather_scatter.f90:1786-1929, yields for a conforming field:

@@ -84,6 +84,8 @@ SIGNATURES = {
     "pf_read_bnd": (c_int, [C.c_char_p, c_i64, c_int, vp]),
     "pf_read_lds": (c_int, [C.c_char_p, c_i64, c_int, vp, vp]),
     "pf_coords_pp": (c_int, [c_int, c_i64, vp, vp, vp]),
+    "pf_write_deck_p121": (c_int, [C.c_char_p, c_int, c_i64, c_i64, c_i64, c_int, c_i64, c_dbl, c_dbl, c_dbl, c_int,
+                                   vp, vp, vp, vp, vp]),
     "pf_calc_nodes_pp": (None, [c_i64, c_int, c_int, P(c_i64), P(c_i64)]),
     "pf_nodal_values": (c_int, [c_int, c_i64, vp, c_i64, c_i64, vp, c_i64, c_i64, vp]),
     "pf_write_ensi": (c_int, [C.c_char_p, c_int, c_i64, vp, c_int]),

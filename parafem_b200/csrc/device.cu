@@ -90,7 +90,7 @@ struct pf_ctx {
   DevBuf<unsigned int> acc_ptr, acc_pos;
 
   // peer-memory collectives (CUDA IPC mappings of the peers' p_ext / receive buffer / sync block)
-  bool peer_ok = false, use_peer = true, ptab_valid = false, fuse = true;
+  bool peer_ok = false, use_peer = true, ptab_valid = false;
   DevBuf<PeerSync> sync;
   DevBuf<PeerTable> ptab;
   PeerTable host_tab;
@@ -298,16 +298,13 @@ int launch_matvec(pf_handle h, const double *pvec, const State *st) {
   switch (h->ntot) {
     case 60: return launch_matvec_t<60, 1, 7, GATHER>(h, pvec, st);
     // measured on B200 (profiles/r01_tile_tuning.md): small tiles on many ring slots win --
-    // hex8 8x5 -> 0.90 of HBM peak, 2x16 -> 0.99; p123 64x6 -> 0.67, 16x16 -> 0.85
+    // hex8 8x5 -> 0.90 of HBM peak, 2x16 -> 0.99, 1x32 -> 1.00; p123 64x6 -> 0.67, 16x16 -> 0.85
     case 24:
       if (tune == 1) return launch_matvec_t<24, 8, 5, GATHER>(h, pvec, st);
-      if (tune == 2) return launch_matvec_t<24, 1, 32, GATHER>(h, pvec, st);
-      if (tune == 3) return launch_matvec_t<24, 2, 24, GATHER>(h, pvec, st);
-      return launch_matvec_t<24, 2, 16, GATHER>(h, pvec, st);
+      if (tune == 2) return launch_matvec_t<24, 2, 16, GATHER>(h, pvec, st);
+      return launch_matvec_t<24, 1, 32, GATHER>(h, pvec, st);
     case 8:
       if (tune == 1) return launch_matvec_t<8, 64, 6, GATHER>(h, pvec, st);
-      if (tune == 2) return launch_matvec_t<8, 8, 32, GATHER>(h, pvec, st);
-      if (tune == 3) return launch_matvec_t<8, 16, 24, GATHER>(h, pvec, st);
       return launch_matvec_t<8, 16, 16, GATHER>(h, pvec, st);
   }
   return fail(h, 3, "unsupported ntot %d (supported: 60, 24, 8)", h->ntot);
@@ -475,21 +472,10 @@ int vec_grid(pf_handle h) {
 }
 
 // u_ext = A p_ext over this rank's elements + halo exchanges (gather, mat-vec, scatter)
-int apply_operator(pf_handle h, const State *st, bool peer = false, bool fuse_dot = false) {
+int apply_operator(pf_handle h, const State *st, bool peer = false) {
   int rc;
   if ((rc = halo_forward(h, h->p_ext.p, st, peer))) return rc;
   if ((rc = launch_matvec<true>(h, h->p_ext.p, st))) return rc;
-  if (fuse_dot) {
-    // single rank, no fixed freedoms: scatter and p.u in one pass
-    Scope sc(h, K_SCATTER);
-    const int64_t nchunks_all = (h->nslots - 1 + kChunk - 1) / kChunk;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nchunks_all, (int64_t)h->sm_count * 8));
-    k_scatter_dot<<<grid, kRedThreads, 0, h->stream>>>(h->csr_ptr.p, h->csr_pos.p, h->utemp.p, h->p_ext.p, h->u_ext.p,
-                                                        (long long)h->nslots, (long long)h->neq_pp, h->part.p, h->state.p);
-    h->launches++;
-    CU(cudaGetLastError());
-    return 0;
-  }
   if ((rc = launch_scatter(h, st, false, h->u_ext.p))) return rc;
   if ((rc = halo_reverse(h, h->u_ext.p, st, peer))) return rc;
   if (h->nfixed > 0) {
@@ -506,15 +492,12 @@ int one_iteration(pf_handle h) {
   const bool peer = h->peer_ok && h->use_peer;
   PeerTable *T = peer ? h->ptab.p : nullptr;
   int rc;
-  const bool fuse_dot = single && h->nfixed == 0 && h->fuse;
-  if ((rc = apply_operator(h, st, peer, fuse_dot))) return rc;
+  if ((rc = apply_operator(h, st, peer))) return rc;
   {
     Scope sc(h, K_VECTOR);
-    if (!fuse_dot) {
-      k_dot<<<vec_grid(h), kRedThreads, 0, h->stream>>>(h->p_ext.p + 1, h->u_ext.p + 1, n, h->part.p, st, single, 1, T);
-      h->launches++;
-      if (!peer && (rc = combine_scalars(h, 1))) return rc;
-    }
+    k_dot<<<vec_grid(h), kRedThreads, 0, h->stream>>>(h->p_ext.p + 1, h->u_ext.p + 1, n, h->part.p, st, single, 1, T);
+    h->launches++;
+    if (!peer && (rc = combine_scalars(h, 1))) return rc;
     k_pcg_update<<<vec_grid(h), kRedThreads, 0, h->stream>>>(h->diag_ext.p + 1, h->p_ext.p + 1, h->u_ext.p + 1, h->x.p, h->r.p,
                                                               h->d.p, n, h->part.p, st, single, h->ratio_hist.p, T);
     h->launches++;
@@ -568,7 +551,6 @@ int pf_init(int rank, int nranks, int device, const void *id128, pf_handle *out)
   CU(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(h, 13, "pf_init: device is sm_%d%d; this build targets sm_100a (B200) only", prop.major, prop.minor);
   h = new pf_ctx();
-  { const char *f = getenv("PF_FUSE"); h->fuse = !(f && !strcmp(f, "0")); }   // PF_FUSE=0: separate scatter / dot kernels
   h->rank = rank; h->nranks = nranks; h->device = device; h->sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(h->state.alloc(1));

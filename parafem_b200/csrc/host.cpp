@@ -497,6 +497,55 @@ int pf_write_ensi(const char *path, int numvar, int64_t nn, const double *values
   return 0;
 }
 
+// p12meshgen's output side for p121 (p12meshgen.f90:244-323): writes <job>.d/.bnd/.lds/.dat in the
+// formats the reference's readers expect.  g_num is in S&G order; 20-node bricks are written in
+// Abaqus order with meshgen = 2, 8-node bricks as they are with meshgen = 1.
+int pf_write_deck_p121(const char *job, int nod, int64_t nels, int64_t nn, int64_t nr, int nip,
+                       int64_t loaded, double e, double v, double tol, int limit, const double *g_coord,
+                       const int32_t *g_num, const int32_t *rest, const int32_t *node, const double *val) {
+  if (nod != 8 && nod != 20) return 1;
+  static const int to_abaqus20[20] = {3, 5, 7, 1, 15, 17, 19, 13, 4, 6, 8, 2, 16, 18, 20, 14, 10, 11, 12, 9};
+  char a[64], b[64], c[64];
+  FILE *f = fopen((std::string(job) + ".d").c_str(), "w");
+  if (!f) return 2;
+  fprintf(f, "*THREE_DIMENSIONAL\n*NODES\n");
+  for (int64_t i = 0; i < nn; ++i) {
+    fortran_e(a, sizeof a, g_coord[i * 3], 14, 6); fortran_e(b, sizeof b, g_coord[i * 3 + 1], 14, 6);
+    fortran_e(c, sizeof c, g_coord[i * 3 + 2], 14, 6);
+    fprintf(f, "%12lld%s%s%s\n", (long long)(i + 1), a, b, c);
+  }
+  fprintf(f, "*ELEMENTS\n");
+  for (int64_t el = 0; el < nels; ++el) {
+    fprintf(f, "%12lld %s", (long long)(el + 1), nod == 20 ? "3 20 1 " : "3 8 1 ");
+    for (int q = 0; q < nod; ++q) {
+      const int m = nod == 20 ? to_abaqus20[q] - 1 : q;
+      fprintf(f, "%12d", g_num[el * nod + m]);
+    }
+    fprintf(f, " 1\n");
+  }
+  fclose(f);
+  f = fopen((std::string(job) + ".bnd").c_str(), "w");
+  if (!f) return 2;
+  for (int64_t i = 0; i < nr; ++i)
+    fprintf(f, "%15d%6d%6d%6d\n", rest[i], rest[nr + i], rest[2 * nr + i], rest[3 * nr + i]);
+  fclose(f);
+  f = fopen((std::string(job) + ".lds").c_str(), "w");
+  if (!f) return 2;
+  for (int64_t i = 0; i < loaded; ++i) {
+    fortran_e(a, sizeof a, val[i * 3], 16, 8); fortran_e(b, sizeof b, val[i * 3 + 1], 16, 8);
+    fortran_e(c, sizeof c, val[i * 3 + 2], 16, 8);
+    fprintf(f, "%12d%s%s%s\n", node[i], a, b, c);
+  }
+  fclose(f);
+  f = fopen((std::string(job) + ".dat").c_str(), "w");
+  if (!f) return 2;
+  fortran_e(a, sizeof a, e, 12, 4); fortran_e(b, sizeof b, v, 12, 4); fortran_e(c, sizeof c, tol, 12, 4);
+  fprintf(f, "'hexahedron'\n%s\n1\n%12lld%12lld%12lld%5d%5d%9lld\n%s%s%s%8d\n", nod == 8 ? "1" : "2",
+          (long long)nels, (long long)nn, (long long)nr, nip, nod, (long long)loaded, a, b, c, limit);
+  fclose(f);
+  return 0;
+}
+
 int pf_make_ggl(int ntot, int64_t nels_pp, const int32_t *g_g_pp, int64_t neq, int npes, int numpe,
                 int32_t *ggl_pp, int64_t cap, int32_t *halo_eq, int64_t *halo_cnt, int64_t *nhalo) {
   int64_t neq_pp, ieq_start;

@@ -550,50 +550,6 @@ k_dot(const double *__restrict__ a, const double *__restrict__ b, long long n, d
   }
 }
 
-// single-rank fusion of k_scatter and k_dot: u = scatter(utemp) and the blocked partial sums
-// of p.u in one pass.  Thread t of the block that owns chunk c handles slots
-// 1 + 2048c + 512k + 2t (+1), k = 0..3 -- the index order of the reduction tree, so the
-// result is bit-identical to k_scatter followed by k_dot.
-__global__ void __launch_bounds__(kRedThreads)
-k_scatter_dot(const unsigned int *__restrict__ csr_ptr, const unsigned int *__restrict__ csr_pos,
-              const double *__restrict__ utemp, const double *__restrict__ p_ext, double *__restrict__ u_ext,
-              long long nslots, long long neq_pp, double *part, State *st) {
-  if (*(volatile const int *)&st->done) return;
-  __shared__ double sh[8];
-  __shared__ int flag;
-  const long long nchunks_all = (nslots - 1 + kChunk - 1) / kChunk;
-  const long long nchunks = (neq_pp + kChunk - 1) / kChunk;     // chunks that hold owned equations
-  for (long long c = blockIdx.x; c < nchunks_all; c += gridDim.x) {
-    double dacc = 0.0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long long i = c * kChunk + 512 * k + 2 * threadIdx.x;   // 0-based equation index
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const long long sidx = i + h + 1;
-        if (sidx < nslots) {
-          const unsigned int a = csr_ptr[sidx], b = csr_ptr[sidx + 1];
-          double acc = 0.0;
-          for (unsigned int q = a; q < b; ++q) acc = acc + utemp[csr_pos[q]];
-          u_ext[sidx] = acc;
-          if (i + h < neq_pp) dacc = dacc + p_ext[sidx] * acc;
-        }
-      }
-    }
-    if (c < nchunks) {
-      const double s = block_tree(dacc, sh);
-      if (threadIdx.x == 0) part[c] = s;
-    }
-  }
-  if (last_block(&st->ticket[1], &flag)) {
-    const double s = final_sum(part, nchunks, sh);
-    if (threadIdx.x == 0) {
-      st->loc[0] = s; st->loc[1] = 0.0; st->loc[2] = 0.0; st->loc[3] = 0.0;
-      finish_pu(st, s);
-    }
-  }
-}
-
 // xnew = x + p*alpha; r = r - u*alpha; d = diag*r; partial r.d, max|xnew|, max|xnew-x|; x = xnew
 // (p121.f90:100-102 and checon_par maths.f90:1048-1061)
 __global__ void __launch_bounds__(kRedThreads)

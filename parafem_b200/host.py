@@ -225,3 +225,11 @@ def write_ensi(path, values, decimals=5):
     """dismsh_ensi_p's EnSight Gold ASCII file: values (nn, numvar), component-major on disk."""
     v = f64(values)
     check(lib().pf_write_ensi(str(path).encode(), v.shape[1], v.shape[0], ptr(v), decimals), what="pf_write_ensi")
+
+
+def write_deck_p121(job, nod, nip, e, v, tol, limit, g_coord, g_num, rest, node, val):
+    """p12meshgen's output side: <job>.d/.bnd/.lds/.dat (g_num in S&G order, rest (4, nr))."""
+    g_coord, g_num, rest, node, val = f64(g_coord), i32(g_num), i32(rest), i32(node), f64(val)
+    check(lib().pf_write_deck_p121(str(job).encode(), nod, g_num.shape[0], g_coord.shape[0], rest.shape[1], nip,
+                                   node.size, e, v, tol, limit, ptr(g_coord), ptr(g_num), ptr(rest), ptr(node),
+                                   ptr(val)), what="pf_write_deck_p121")

@@ -1,12 +1,15 @@
+import json
 import os
+import shutil
 import sys
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-GOLDEN = os.path.join(ROOT, "tests", "golden")
+PACKED = os.path.join(ROOT, "tests", "golden")
 
 
 def pytest_configure(config):
@@ -21,8 +24,33 @@ def _built():
 
 
 @pytest.fixture(scope="session")
-def golden():
-    return GOLDEN
+def golden(tmp_path_factory, _built):
+    """The reference's decks and logs, materialised from the packed fixtures (tests/golden/
+    make_golden.py) into a scratch directory: decks through the repo's own deck writer, logs
+    and control files from their stored lines."""
+    from parafem_b200 import host
+    d = str(tmp_path_factory.mktemp("golden"))
+    texts = json.load(open(os.path.join(PACKED, "fixtures.json")))
+    for name, ls in texts.items():
+        with open(os.path.join(d, name), "w") as f:
+            f.write("\n".join(ls) + "\n")
+    a = np.load(os.path.join(PACKED, "arrays.npz"))
+    xx3_dat = os.path.join(d, "xx3-tiny.dat")
+    keep = open(xx3_dat).read()               # the xx3-style .dat (leading 'gpu' tag) stays as shipped
+    host.write_deck_p121(os.path.join(d, "xx3-tiny"), 20, 8, 100.0, 0.3, 1e-5, 200, a["tiny_coord"], a["tiny_gnum_sg"],
+                         a["tiny_rest"], a["tiny_lds_node"], a["tiny_lds_val"])
+    open(xx3_dat, "w").write(keep)
+    with open(os.path.join(d, "xx3-tiny.dis"), "w") as f:
+        f.write("*DISPLACEMENT\n           1\n")
+        for i, u in enumerate(a["tiny_dis"]):
+            f.write(f"{i + 1:8d} {u[0]: .4E} {u[1]: .4E} {u[2]: .4E}\n")
+    with open(os.path.join(d, "p121_demo.lds"), "w") as f:
+        for n, v in zip(a["demo_lds_node"], a["demo_lds_val"]):
+            f.write(f"{n:12d} {v[0]: .8E} {v[1]: .8E} {v[2]: .8E}\n")
+    np.savez(os.path.join(d, "p121_demo_displ.npz"), displ=a["demo_displ"])
+    for name in ("p121_demo_digests.json", "p121_demo_ensi_head.txt"):
+        shutil.copy(os.path.join(PACKED, name), os.path.join(d, name))
+    return d
 
 
 @pytest.fixture(scope="session")

@@ -1,18 +1,21 @@
 """Regenerates tests/golden/ from the read-only reference checkout (run in the build
 container only; /root/reference does not exist on the GPU box).
 
-Copies the small example decks + golden outputs the reference ships for the p121/p123
-path and derives compact fixtures from the large ones:
-  xx3-tiny.*            copied (125 hex20 deck, .res 79 iterations, .dis displacements)
-  p121_demo.{mg,dat,lds,res}  copied; the 4 MB .d / .bnd are replaced by SHA-256 digests of
-                        the parsed arrays (the in-memory generator must reproduce them) and
-                        the EnSight displacement golden by a compressed .npz of its values
-  p121_book.{mg,res}, p123_book.{mg,res}, p123_small.mg   copied
+The reference's example decks and logs for the p121/p123 path are not copied as files; they
+are parsed and packed:
+  arrays.npz      xx3-tiny deck (coordinates, connectivity in S&G order, restraints, loads) and
+                  its golden displacements (.dis); p121_demo loads (.lds) and the golden EnSight
+                  displacement field (float32 of the 4-digit values)
+  fixtures.json   the small text files (.res logs, .mg / .dat control files) as lists of lines
+  p121_demo_digests.json   SHA-256 of the parsed 4 MB p121_demo.d / .bnd arrays (the in-memory
+                  generator must reproduce them)
+  p121_demo_ensi_head.txt  the first 204 lines of the 107 167-line EnSight golden (format check)
+tests/conftest.py materialises decks and logs from these into a temporary directory with the
+repo's own deck writer (pf_write_deck_p121), which reproduces xx3-tiny.d byte for byte.
 """
 import hashlib
 import json
 import os
-import shutil
 import sys
 
 import numpy as np
@@ -26,27 +29,40 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def lines(path):
+    return open(path).read().splitlines()
+
+
 def main():
     from parafem_b200 import host
-    for f in ("bnd", "d", "dat", "dis", "lds", "res"):
-        shutil.copy(f"{REF}/dev/xx3/demo/xx3-tiny.{f}", f"{HERE}/xx3-tiny.{f}")
-    for f in ("mg", "dat", "lds", "res"):
-        shutil.copy(f"{REF}/5th_ed/p121/demo/p121_demo.{f}", f"{HERE}/p121_demo.{f}")
-    shutil.copy(f"{REF}/5th_ed/p121/book/p121.mg", f"{HERE}/p121_book.mg")
-    shutil.copy(f"{REF}/5th_ed/p121/book/p121.res", f"{HERE}/p121_book.res")
-    shutil.copy(f"{REF}/5th_ed/p123/book/p123.mg", f"{HERE}/p123_book.mg")
-    shutil.copy(f"{REF}/5th_ed/p123/book/p123.res", f"{HERE}/p123_book.res")
-    shutil.copy(f"{REF}/5th_ed/p123/mg/p123_small.mg", f"{HERE}/p123_small.mg")
-    shutil.copy(f"{REF}/5th_ed/p121/mg/p121_tiny.mg", f"{HERE}/p121_tiny.mg")
-    for f in os.listdir(HERE):
-        os.chmod(os.path.join(HERE, f), 0o644)
-    p = host.read_deck_p121(f"{REF}/5th_ed/p121/demo/p121_demo")
+    from parafem_b200._lib import lib, ptr
+    tiny = f"{REF}/dev/xx3/demo/xx3-tiny"
+    t = host.read_deck_p121(tiny)
+    node = np.empty(8, np.int32)
+    val = np.empty((8, 3))
+    assert lib().pf_read_lds(tiny.encode(), 8, 3, ptr(node), ptr(val)) == 0
+    dis = np.loadtxt(tiny + ".dis", skiprows=2)[:, 1:]
+    demo = f"{REF}/5th_ed/p121/demo/p121_demo"
+    p = host.read_deck_p121(demo)
+    dnode = np.empty(65, np.int32)
+    dval = np.empty((65, 3))
+    assert lib().pf_read_lds(demo.encode(), 65, 3, ptr(dnode), ptr(dval)) == 0
+    disp = np.loadtxt(demo + ".ensi.DISPL-000001", skiprows=4)
+    np.savez_compressed(f"{HERE}/arrays.npz", tiny_coord=t.g_coord, tiny_gnum_sg=t.g_num_pp, tiny_rest=t.rest,
+                        tiny_lds_node=node, tiny_lds_val=val, tiny_dis=dis, demo_lds_node=dnode, demo_lds_val=dval,
+                        demo_displ=disp.reshape(3, p.nn).T.astype(np.float32))
+    texts = {
+        "xx3-tiny.res": lines(tiny + ".res"), "xx3-tiny.dat": lines(tiny + ".dat"),
+        "p121_demo.res": lines(demo + ".res"), "p121_demo.dat": lines(demo + ".dat"), "p121_demo.mg": lines(demo + ".mg"),
+        "p121_book.res": lines(f"{REF}/5th_ed/p121/book/p121.res"), "p121_book.mg": lines(f"{REF}/5th_ed/p121/book/p121.mg"),
+        "p123_book.res": lines(f"{REF}/5th_ed/p123/book/p123.res"), "p123_book.mg": lines(f"{REF}/5th_ed/p123/book/p123.mg"),
+        "p123_small.mg": lines(f"{REF}/5th_ed/p123/mg/p123_small.mg"), "p121_tiny.mg": lines(f"{REF}/5th_ed/p121/mg/p121_tiny.mg"),
+    }
+    json.dump(texts, open(f"{HERE}/fixtures.json", "w"), indent=1)
     digests = dict(g_num_sg=sha(p.g_num_pp), g_coord_pp=sha(p.g_coord_pp), rest=sha(p.rest), g_g=sha(p.g_g_pp),
                    r=sha(p.r_pp), nn=int(p.nn), nr=int(p.nr), neq=int(p.neq), nels=int(p.nels))
     json.dump(digests, open(f"{HERE}/p121_demo_digests.json", "w"), indent=1)
-    disp = np.loadtxt(f"{REF}/5th_ed/p121/demo/p121_demo.ensi.DISPL-000001", skiprows=4)
-    np.savez_compressed(f"{HERE}/p121_demo_displ.npz", displ=disp.reshape(3, p.nn).T.astype(np.float32))
-    with open(f"{REF}/5th_ed/p121/demo/p121_demo.ensi.DISPL-000001") as f, open(f"{HERE}/p121_demo_ensi_head.txt", "w") as g:
+    with open(demo + ".ensi.DISPL-000001") as f, open(f"{HERE}/p121_demo_ensi_head.txt", "w") as g:
         g.writelines([next(f) for _ in range(204)])   # header + the first 200 x-displacements, verbatim
     print("golden fixtures written to", HERE)
 

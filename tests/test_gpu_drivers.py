@@ -42,7 +42,7 @@ def test_cpp_driver_reads_the_tiny_deck(golden, tmp_path):
     it = int(re.search(r"iterations to convergence was\s+(\d+)", res.stdout).group(1))
     assert abs(it - 79) <= 1
     assert "The total load is: -0.1000E+03" in res.stdout
-    os.remove(os.path.join(golden, "xx3-tiny.b200.res"))
+    assert os.path.exists(os.path.join(golden, "xx3-tiny.b200.ensi.DISPL-000001"))
 
 
 def test_python_driver_res_file(golden, tmp_path, demo):
