@@ -71,3 +71,49 @@ def write_res(path, prob, res, t_read=0.0, t_total=0.0):
                 if lo <= q < lo + prob.neq_pp:
                     f.write(f"{q:8d}     {_fe(res['x'][q - lo])}\n")
             f.write(f"Time spent in the solver was {res['solve_s']:10.4f}\n")
+
+
+def main(argv=None):
+    """python -m parafem_b200.driver (--deck JOB | --cube N [--hex 8|20] | --p123 N) [--matrix-free M] [--out DIR]
+
+    Runs program p121 (or p123) on cuda:0 and writes <job>.res and the EnSight nodal file as the
+    reference does (p121.f90:70-77,105-110,124-140 / p123.f90:153-181)."""
+    import argparse
+    import os
+
+    from . import host
+    ap = argparse.ArgumentParser(prog="parafem_b200.driver")
+    g = ap.add_mutually_exclusive_group(required=True)
+    g.add_argument("--deck", help="ParaFEM p121 deck base name (<job>.dat/.d/.bnd/.lds)")
+    g.add_argument("--cube", type=int, help="p12meshgen p121 cube with N^3 elements, generated in memory")
+    g.add_argument("--p123", type=int, help="p12meshgen p123 box with N^3 8-node bricks")
+    ap.add_argument("--hex", type=int, default=20, choices=[8, 20])
+    ap.add_argument("--matrix-free", type=int, default=0, choices=[0, 1, 2])
+    ap.add_argument("--out", default=".")
+    a = ap.parse_args(argv)
+    t0 = time.time()
+    if a.deck:
+        prob, job = host.read_deck_p121(a.deck), os.path.basename(a.deck)
+    elif a.cube:
+        prob, job = host.cube_p121(a.cube, a.cube, a.cube, a.hex, limit=20000), f"p121_cube{a.cube}_hex{a.hex}"
+    else:
+        prob, job = host.cube_p123(a.p123, a.p123, a.p123, limit=20000), f"p123_box{a.p123}"
+    t_read = time.time() - t0
+    with _solver.Solver(0, 1, 0) as s:
+        if a.matrix_free and prob.program == 121:
+            _solver.setup_problem(s, prob, matrix_free=a.matrix_free)
+            x, iters, conv = s.pcg_solve(prob.r_pp, prob.tol, prob.limit)
+            res = dict(iters=iters, converged=conv, x=x, solve_s=0.0, setup_s=0.0, total_load=prob.total_load,
+                       sigma=s.centroid_stress(0, prob.e, prob.v))
+        else:
+            res = run(prob, s)
+    base = os.path.join(a.out, job)
+    write_res(base + ".res", prob, res, t_read=t_read, t_total=time.time() - t0)
+    kind = "DISPL" if prob.program == 121 else "NDPTL"
+    host.write_ensi(f"{base}.ensi.{kind}-000001", host.nodal_values(prob, res["x"]), decimals=5)
+    print(open(base + ".res").read(), end="")
+    return 0 if res["converged"] else 3
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -66,3 +66,48 @@ def test_python_driver_p123(tmp_path):
     txt = open(path).read()
     assert "The total load is   0.1000E+02" in txt             # p123.res line format
     assert res["converged"]
+
+
+def test_driver_cli_writes_res_and_ensight(tmp_path):
+    rc = driver.main(["--cube", "10", "--out", str(tmp_path)])
+    assert rc == 0
+    res = open(tmp_path / "p121_cube10_hex20.res").read()
+    assert "The total load is: -0.1000E+03" in res and "iterations to convergence" in res
+    ens = open(tmp_path / "p121_cube10_hex20.ensi.DISPL-000001").read().splitlines()
+    p = host.cube_p121(10, 10, 10, 20)
+    assert ens[0].startswith("Alya Ensight Gold --- Vector") and len(ens) == 4 + 3 * p.nn
+    rc = driver.main(["--p123", "8", "--out", str(tmp_path)])
+    assert rc == 0
+    ens = open(tmp_path / "p123_box8.ensi.NDPTL-000001").read().splitlines()
+    assert ens[0].startswith("Alya Ensight Gold --- Scalar") and len(ens) == 4 + 9 ** 3
+
+
+def test_bad_arguments_return_status_codes():
+    """Errors are status codes + pf_last_error text (xx3 convention), never exit()/abort()."""
+    import ctypes as C
+    import numpy as np
+    from parafem_b200 import PfError, solver as S
+    from parafem_b200._lib import lib, ptr
+    p = host.cube_p121(3, 3, 3, 20)
+    with S.Solver(0, 1, 0) as s:
+        with pytest.raises(PfError, match="neq_pp/ieq_start"):
+            s._ck(lib().pf_setup_mesh(s._h, 20, 3, 8, p.nels_pp, ptr(p.g_coord_pp), ptr(p.g_g_pp), p.neq, 1, p.neq - 1), "x")
+        with pytest.raises(PfError, match="nod must be"):
+            s._ck(lib().pf_setup_mesh(s._h, 10, 3, 8, p.nels_pp, ptr(p.g_coord_pp), ptr(p.g_g_pp), p.neq, 1, p.neq), "x")
+        bad = p.g_g_pp.copy(); bad[0, 0] = p.neq + 5
+        with pytest.raises(PfError, match="outside"):
+            s._ck(lib().pf_setup_mesh(s._h, 20, 3, 8, p.nels_pp, ptr(p.g_coord_pp), ptr(bad), p.neq, 1, p.neq), "x")
+        s.setup_mesh(p)
+        with pytest.raises(PfError, match="element matrices"):
+            s.build_precon()
+        s.form_km_elastic(p.e, p.v)
+        with pytest.raises(PfError, match="pf_build_precon"):
+            s.pcg_run(1e-5, 10)
+        s.build_precon()
+        with pytest.raises(PfError, match="limit"):
+            s.pcg_run(1e-5, 0)
+        with pytest.raises(PfError):
+            s.get_storkm(p.nels_pp - 1, 5)
+    h = C.c_void_p()
+    assert lib().pf_init(0, 1, 99, None, C.byref(h)) > 0          # no such device
+    assert lib().pf_init(3, 2, 0, None, C.byref(h)) > 0           # rank outside [0, nranks)

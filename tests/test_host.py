@@ -136,3 +136,50 @@ def test_ensight_writer_matches_the_shipped_file_format(tmp_path, golden, demo):
     # the rest differ by one unit of the last digit: golden stopped at iteration 295, this solve at 297)
     # y-displacements start after nn x-values (component-major)
     assert float(mine[4 + demo.nn]) == 0.0
+
+
+def test_deck_writer_reader_round_trip(tmp_path):
+    """p12meshgen restated end to end: generate a cube, write <job>.d/.bnd/.lds/.dat in the
+    reference's formats, read it back with the read_p121-family readers: same steering and loads;
+    coordinates and loads as they survive the E14.6 / E16.8 text fields (round_mode 1)."""
+    import ctypes as C
+    from parafem_b200._lib import lib, ptr
+    for nod, dims in ((20, (5, 4, 3)), (8, (5, 5, 5))):
+        nxe, nye, nze = dims
+        exact = host.cube_p121(nxe, nye, nze, nod, aa=1. / 3, bb=.7, cc=1.1)
+        text = host.cube_p121(nxe, nye, nze, nod, aa=1. / 3, bb=.7, cc=1.1, round_mode=1)
+        rest = np.zeros((4, exact.nr), np.int32)
+        assert lib().pf_cube_rest(0, nxe, nye, nze, nod, exact.nr, ptr(rest)) == 0
+        nn, nr, loaded = C.c_int64(), C.c_int64(), C.c_int64()
+        lib().pf_p121_sizes(nxe, nye, nze, nod, C.byref(nn), C.byref(nr), C.byref(loaded))
+        node = np.empty(loaded.value, np.int32)
+        val = np.empty((loaded.value, 3))
+        assert lib().pf_p121_loads(nxe, nze, nod, 1. / 3, .7, 0, ptr(node), ptr(val)) == 0
+        g_coord = np.zeros((exact.nn, 3))
+        g_coord[exact.g_num_pp - 1] = np.transpose(exact.g_coord_pp, (0, 2, 1))
+        job = str(tmp_path / f"cube{nod}")
+        host.write_deck_p121(job, nod, 8, 100.0, 0.3, 1e-5, 321, g_coord, exact.g_num_pp, rest, node, val)
+        back = host.read_deck_p121(job)
+        assert (back.nod, back.nip, back.limit, back.nn, back.nr, back.neq) == (nod, 8, 321, exact.nn, exact.nr, exact.neq)
+        assert np.array_equal(back.g_num_pp, exact.g_num_pp)          # Abaqus order on disk, S&G after abaqus2sg
+        assert np.array_equal(back.g_g_pp, exact.g_g_pp)
+        assert np.array_equal(back.g_coord_pp, text.g_coord_pp)
+        assert np.array_equal(back.r_pp, text.r_pp)
+        assert np.abs(back.g_coord_pp - exact.g_coord_pp).max() < 1e-5 and np.abs(back.r_pp - exact.r_pp).max() < 1e-6
+
+
+def test_nodal_values_and_node_partition():
+    p = host.cube_p121(4, 4, 4, 20)
+    x = np.arange(1, p.neq + 1, dtype=np.float64)
+    d = host.nodal_values(p, x)
+    m = p.nf > 0
+    assert np.array_equal(d[m], p.nf[m].astype(np.float64)) and np.all(d[~m] == 0.0)
+    import ctypes as C
+    from parafem_b200._lib import lib
+    nxt = 1
+    for numpe in range(1, 6):
+        a, b = C.c_int64(), C.c_int64()
+        lib().pf_calc_nodes_pp(p.nn, 5, numpe, C.byref(a), C.byref(b))
+        assert b.value == nxt
+        nxt += a.value
+    assert nxt == p.nn + 1
