@@ -824,16 +824,6 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
   double cr[NS], pr[NS];
   int ir[NS];
   double2 gr[5];
-  // where value s = lane + 32 i of a group lands in shared memory: independent of the group
-  short co_off[NS], p_off[NS], row_off[NS];
-#pragma unroll
-  for (int i = 0; i < NS; ++i) {
-    const int s = lane + 32 * i, le = s / NTOT, k = s - le * NTOT;
-    const int d = k / NOD, m = k - d * NOD;
-    co_off[i] = (short)(le * Cfg::kRow + m * 4 + d);              // g_coord_pp(nod,3,nels) -> [m][d]
-    p_off[i] = (short)(le * Cfg::kRow + (k / 3) * 4 + (k % 3));   // dof k = 3m+c -> [m][c]
-    row_off[i] = (short)((le * 8) * Cfg::kPart + k);
-  }
   const long long gstride = (long long)gridDim.x * nwarps;
   auto load_idx = [&](long long g) {
     const long long e0 = g * 4;
@@ -872,8 +862,13 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
     for (int i = 0; i < NS; ++i) {
       const int s = lane + 32 * i;
       if (s < ne * NTOT) {
-        if (GEOM != 2) s_co[co_off[i]] = cr[i];
-        if (GEOM != 1) s_p[p_off[i]] = pr[i];
+        const int le = s / NTOT, k = s - le * NTOT;
+        // coordinates: g_coord_pp(nod,3,nels) -> [m][d]; p: dof k = 3m+c -> [m][c]
+        if (GEOM != 2) {
+          const int d = k / NOD, m = k - d * NOD;
+          s_co[le * Cfg::kRow + m * 4 + d] = cr[i];
+        }
+        if (GEOM != 1) s_p[le * Cfg::kRow + (k / 3) * 4 + (k % 3)] = pr[i];
       }
     }
     double inv[9], f = 0.0;
@@ -930,7 +925,6 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
         e3_ = fma(gy, pxy.x, e3_); e3_ = fma(gx, pxy.y, e3_);
         e4_ = fma(gz, pxy.y, e4_); e4_ = fma(gy, pz, e4_);
         e5_ = fma(gz, pxy.x, e5_); e5_ = fma(gx, pz, e5_);
-        part[3 * m] = gx; part[3 * m + 1] = gy; part[3 * m + 2] = gz;   // reused below: same bits, 9 fma/node saved
       }
       const double eps[6] = {e0_, e1_, e2_, e3_, e4_, e5_};
       double sig[6];
@@ -943,7 +937,11 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
       }
 #pragma unroll
       for (int m = 0; m < NOD; ++m) {
-        const double gx = part[3 * m], gy = part[3 * m + 1], gz = part[3 * m + 2];
+        const double2 dxy = *reinterpret_cast<const double2 *>(der + m * 4);
+        const double dz = der[m * 4 + 2];
+        const double gx = fma(inv[6], dz, fma(inv[3], dxy.y, fma(inv[0], dxy.x, 0.0)));
+        const double gy = fma(inv[7], dz, fma(inv[4], dxy.y, fma(inv[1], dxy.x, 0.0)));
+        const double gz = fma(inv[8], dz, fma(inv[5], dxy.y, fma(inv[2], dxy.x, 0.0)));
         part[3 * m] = fma(gz, sig[5], fma(gy, sig[3], fma(gx, sig[0], 0.0)));
         part[3 * m + 1] = fma(gz, sig[4], fma(gx, sig[3], fma(gy, sig[1], 0.0)));
         part[3 * m + 2] = fma(gx, sig[5], fma(gy, sig[4], fma(gz, sig[2], 0.0)));
@@ -952,16 +950,13 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
     }
     __syncwarp();
     if (GEOM != 1) {
+      for (int s = lane; s < ne * NTOT; s += 32) {
+        const int le = s / NTOT, k = s - le * NTOT;
+        const double *row = s_part + (le * 8) * Cfg::kPart + k;
+        double acc = row[0];
 #pragma unroll
-      for (int i = 0; i < NS; ++i) {
-        const int s = lane + 32 * i;
-        if (s < ne * NTOT) {
-          const double *row = s_part + row_off[i];
-          double acc = row[0];
-#pragma unroll
-          for (int g = 1; g < 8; ++g) acc = acc + row[g * Cfg::kPart];
-          utemp[e0 * NTOT + s] = acc;    // (e0+le)*NTOT + k == e0*NTOT + s: contiguous
-        }
+        for (int g = 1; g < 8; ++g) acc = acc + row[g * Cfg::kPart];
+        utemp[(e0 + le) * NTOT + k] = acc;
       }
     }
   }
