@@ -257,12 +257,14 @@ def main():
                 "x1": float(x[0]) if rank == 0 else None, "tol": prob.tol}
 
     def mf_flops(mode, nodn):
-        # flops of the operator form per element (k_apply_mf), fma = 2 flop: per Gauss point and node
-        # jac 9 fma (mode 1 only), deriv 9 fma twice, eps 9 fma, B^T sigma 9 fma; per point the
-        # determinant/adjugate (~45 flop, mode 1 only) and sigma (36 fma + 7 mul); 7 adds per dof
-        if mode == 2:
-            return 8 * (2 * 36 * nodn + 2 * 36 + 7) + 7 * 3 * nodn
-        return 8 * (2 * 45 * nodn + 45 + 2 * 36 + 7) + 7 * 3 * nodn
+        # flops per element of k_apply_mf as executed (fma = 2 flop, mul/add = 1), 8 Gauss points:
+        # phase 1  H = der x p: 9 fma per node and point; per point G (9 mul + 18 fma), eps (3 add),
+        # sigma (12 mul + 30 fma), T (9 mul + 18 fma) = 165 flop; phase 2: per dof 1 mul + 23 fma.
+        # Mode 1 adds the Jacobian pass: 9 fma per node and point + det/inverse/det*w (51 flop) per point.
+        fl = 8 * 18 * nodn + 8 * 165 + 3 * nodn * 47
+        if mode == 1:
+            fl += 8 * 18 * nodn + 8 * 51
+        return fl
 
     def mf_roofline(mode, m, peak):
         mv_ms_, mv_n_ = m["kernel_ms"]["matvec"]

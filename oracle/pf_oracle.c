@@ -403,63 +403,73 @@ void orc_matvec(int ntot, int64_t nels, const double *storkm, const double *pmul
 /* matrix-free variant (BASELINE config E): utemp(:,e) = sum_gp B^T (D (B p)) det w   */
 /* ------------------------------------------------------------------------- */
 /*
- * Operator form of elements_3 without storkm: per element and Gauss point (ascending) the
- * Jacobian, its inverse and the Cartesian derivatives are recomputed as in gauss_point()
- * but with fused multiply-adds (fma chains from 0.0), then
- *   eps   = B p      node-ascending fma chains, rows in beemat's order
- *   sigma = D eps    c-ascending fma chain per row, then sigma *= det*w
- *   ug    = B^T sigma   per dof three fmas from 0.0 in row order
- * and the eight per-point vectors are added in Gauss-point order.  This is the operation
- * order of k_apply_mf in parafem_b200/csrc/kernels.cuh.  It is a different rounding of
- * the same operator as MATMUL(storkm,pmul) (p121.f90:94), hence its own oracle.
+ * Operator form of elements_3 without storkm.  With deriv = jac^-1 * der the element product
+ * factors through two 3x3 matrices per Gauss point (ascending):
+ *   jac, det, jac^-1 as in gauss_point() but with fused multiply-adds (fma chains from 0.0)
+ *   H(b,c) = sum_m der(b,m) p_c(m)          node-ascending fma chains from 0.0
+ *   G(a,c) = sum_b inv(a,b) H(b,c)          product, then two fmas, b ascending
+ *   eps    = (G00, G11, G22, G10+G01, G21+G12, G20+G02)      beemat's row order
+ *   sigma  = D eps                          product + c-ascending fmas per row, then * det*w
+ *   T(b,c) = sum_a inv(a,b) S(a,c)          S = symmetric stress tensor; product, two fmas
+ * and then per dof ONE chain over (Gauss point ascending, b ascending):
+ *   u_c(m) = sum_gp sum_b der_gp(b,m) T_gp(b,c)      first term a product, then 23 fmas.
+ * This is the operation order of k_apply_mf in parafem_b200/csrc/kernels.cuh.  It is a
+ * different rounding of the same operator as MATMUL(storkm,pmul) (p121.f90:94), hence its
+ * own oracle.
  */
-static void mf_point(int nod, const double *der /*(3,20) at [a*20+m]*/, const double *coord, const double *dee,
-                     double wt, const double *pm, double *ug) {
-  double jac[9], inv[9];
-  for (int b = 0; b < 3; ++b)
-    for (int a = 0; a < 3; ++a) {
-      double s = 0.0;
-      for (int m = 0; m < nod; ++m) s = fma(der[a * 20 + m], coord[b * nod + m], s);
-      jac[b * 3 + a] = s;
+static void mf_element(int nod, double der[8][60] /*[ig][a*20+m]*/, const double *coord, const double *dee,
+                       const double *weights, const double *pm, double *ut) {
+  double T[8][9];
+  for (int ig = 0; ig < 8; ++ig) {
+    double jac[9], inv[9], H[9], G[9], sig[6];
+    for (int b = 0; b < 3; ++b)
+      for (int a = 0; a < 3; ++a) {
+        double s = 0.0;
+        for (int m = 0; m < nod; ++m) s = fma(der[ig][a * 20 + m], coord[b * nod + m], s);
+        jac[b * 3 + a] = s;
+      }
+    const double det = orc_determinant3(jac);
+    memcpy(inv, jac, sizeof inv);
+    orc_invert3(inv);
+    const double f = det * weights[ig];
+    for (int b = 0; b < 3; ++b)
+      for (int c = 0; c < 3; ++c) {
+        double s = 0.0;
+        for (int m = 0; m < nod; ++m) s = fma(der[ig][b * 20 + m], pm[3 * m + c], s);
+        H[b * 3 + c] = s;
+      }
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 3; ++c) {
+        double s = inv[a] * H[c];
+        s = fma(inv[3 + a], H[3 + c], s);
+        s = fma(inv[6 + a], H[6 + c], s);
+        G[a * 3 + c] = s;
+      }
+    const double eps[6] = {G[0], G[4], G[8], G[3] + G[1], G[7] + G[5], G[6] + G[2]};
+    for (int r = 0; r < 6; ++r) {
+      double s = dee[r] * eps[0];
+      for (int c = 1; c < 6; ++c) s = fma(dee[c * 6 + r], eps[c], s);
+      sig[r] = s * f;
     }
-  const double det = orc_determinant3(jac);
-  memcpy(inv, jac, sizeof inv);
-  orc_invert3(inv);
-  double eps[6] = {0, 0, 0, 0, 0, 0}, sig[6];
-  for (int m = 0; m < nod; ++m) {
-    double d[3];
-    for (int a = 0; a < 3; ++a) {
-      double s = 0.0;
-      for (int b = 0; b < 3; ++b) s = fma(inv[b * 3 + a], der[b * 20 + m], s);
-      d[a] = s;
+    const double S[9] = {sig[0], sig[3], sig[5], sig[3], sig[1], sig[4], sig[5], sig[4], sig[2]};
+    for (int b = 0; b < 3; ++b)
+      for (int c = 0; c < 3; ++c) {
+        double s = inv[b * 3] * S[c];
+        s = fma(inv[b * 3 + 1], S[3 + c], s);
+        s = fma(inv[b * 3 + 2], S[6 + c], s);
+        T[ig][b * 3 + c] = s;
+      }
+  }
+  for (int m = 0; m < nod; ++m)
+    for (int c = 0; c < 3; ++c) {
+      double s = der[0][m] * T[0][c];
+      for (int ig = 0; ig < 8; ++ig)
+        for (int b = 0; b < 3; ++b) {
+          if (ig == 0 && b == 0) continue;
+          s = fma(der[ig][b * 20 + m], T[ig][b * 3 + c], s);
+        }
+      ut[3 * m + c] = s;
     }
-    const double px = pm[3 * m], py = pm[3 * m + 1], pz = pm[3 * m + 2];
-    eps[0] = fma(d[0], px, eps[0]);
-    eps[1] = fma(d[1], py, eps[1]);
-    eps[2] = fma(d[2], pz, eps[2]);
-    eps[3] = fma(d[1], px, eps[3]); eps[3] = fma(d[0], py, eps[3]);
-    eps[4] = fma(d[2], py, eps[4]); eps[4] = fma(d[1], pz, eps[4]);
-    eps[5] = fma(d[2], px, eps[5]); eps[5] = fma(d[0], pz, eps[5]);
-  }
-  const double f = det * wt;
-  for (int r = 0; r < 6; ++r) {
-    double s = 0.0;
-    for (int c = 0; c < 6; ++c) s = fma(dee[c * 6 + r], eps[c], s);
-    sig[r] = s * f;
-  }
-  for (int m = 0; m < nod; ++m) {
-    double d[3];
-    for (int a = 0; a < 3; ++a) {
-      double s = 0.0;
-      for (int b = 0; b < 3; ++b) s = fma(inv[b * 3 + a], der[b * 20 + m], s);
-      d[a] = s;
-    }
-    double ux = 0.0, uy = 0.0, uz = 0.0;
-    ux = fma(d[0], sig[0], ux); ux = fma(d[1], sig[3], ux); ux = fma(d[2], sig[5], ux);
-    uy = fma(d[1], sig[1], uy); uy = fma(d[0], sig[3], uy); uy = fma(d[2], sig[4], uy);
-    uz = fma(d[2], sig[2], uz); uz = fma(d[1], sig[4], uz); uz = fma(d[0], sig[5], uz);
-    ug[3 * m] = ux; ug[3 * m + 1] = uy; ug[3 * m + 2] = uz;
-  }
 }
 
 int orc_apply_mf(int64_t nels, int nod, int nip, const double *g_coord_pp, double e, double v,
@@ -476,16 +486,8 @@ int orc_apply_mf(int64_t nels, int nod, int nip, const double *g_coord_pp, doubl
       for (int a = 0; a < 3; ++a) der[ig][a * 20 + m] = d3[m * 3 + a];
   }
 #pragma omp parallel for schedule(static)
-  for (int64_t iel = 0; iel < nels; ++iel) {
-    double ug[8][60];
-    for (int ig = 0; ig < nip; ++ig)
-      mf_point(nod, der[ig], g_coord_pp + iel * nod * 3, dee, weights[ig], pmul + iel * ntot, ug[ig]);
-    for (int k = 0; k < ntot; ++k) {
-      double s = ug[0][k];
-      for (int ig = 1; ig < nip; ++ig) s = s + ug[ig][k];
-      utemp[iel * ntot + k] = s;
-    }
-  }
+  for (int64_t iel = 0; iel < nels; ++iel)
+    mf_element(nod, der, g_coord_pp + iel * nod * 3, dee, weights, pmul + iel * ntot, utemp + iel * ntot);
   return 0;
 }
 

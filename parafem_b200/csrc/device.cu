@@ -255,31 +255,27 @@ int launch_matvec_t(pf_handle h, const double *pvec, const State *st) {
   return 0;
 }
 
-template <int NOD, bool GATHER, int GEOM, int kWarps>
-int launch_mf_w(pf_handle h, const double *pvec, const State *st) {
-  using Cfg = MfCfg<NOD>;
-  auto kern = k_apply_mf<NOD, GATHER, GEOM, kWarps>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem(kWarps)));
-    attr_set = true;
-  }
-  const int64_t ngroups = (h->nels + 3) / 4;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (ngroups + kWarps - 1) / kWarps));
-  kern<<<grid, kWarps * 32, Cfg::smem(kWarps), h->stream>>>(h->coord.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st,
-                                                            h->geom.p);
-  h->launches++;
-  CU(cudaGetLastError());
-  return 0;
+constexpr int kMfWarps = 8;   // 256 threads = 256 elements in flight per SM; ~190 registers per thread
+
+int mf_grid(pf_handle h) {
+  const int64_t ngroups = (h->nels + 31) / 32;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (ngroups + kMfWarps - 1) / kMfWarps));
 }
 
 template <int NOD, bool GATHER, int GEOM>
 int launch_mf_t(pf_handle h, const double *pvec, const State *st) {
-  // hex20 keeps ~200 live registers with the prefetch pipeline: 8 warps (255 regs) avoid spills,
-  // 10 warps (168 regs) spill ~0.5 KB per thread; PF_TUNE=1 selects the 10-warp build
-  static const int tune = getenv("PF_TUNE") ? atoi(getenv("PF_TUNE")) : 0;
-  if (NOD == 20 && tune != 1) return launch_mf_w<NOD, GATHER, GEOM, 8>(h, pvec, st);
-  return launch_mf_w<NOD, GATHER, GEOM, 10>(h, pvec, st);
+  using Cfg = MfCfg<NOD>;
+  auto kern = k_apply_mf<NOD, GATHER, GEOM, kMfWarps>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem(kMfWarps)));
+    attr_set = true;
+  }
+  kern<<<mf_grid(h), kMfWarps * 32, Cfg::smem(kMfWarps), h->stream>>>(h->coord.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st,
+                                                                      h->geom.p);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
 }
 
 template <bool GATHER>
@@ -805,11 +801,14 @@ int pf_form_km_elastic(pf_handle h, double e, double v) {
     diag_only = h->diag_tmp.p;
     if (h->mf_mode == 2) {
       // geometric factors: inverse Jacobian (9) + det*w (1) per element and Gauss point
-      CU(h->geom.alloc((size_t)h->nels * 80));
+      CU(h->geom.alloc((size_t)((h->nels + 31) / 32) * 32 * 80));   // [group][point][word][lane], padded to whole groups
       if (h->nod == 20) rc = launch_mf_t<20, false, 1>(h, nullptr, nullptr);
       else rc = launch_mf_t<8, false, 1>(h, nullptr, nullptr);
       if (rc) return rc;
-    } else h->geom.release();
+    } else {
+      // mode 1: the factors are rebuilt every call; one 640 B scratch line per resident thread
+      CU(h->geom.alloc((size_t)mf_grid(h) * kMfWarps * 32 * 80));
+    }
   } else if ((rc = alloc_km(h))) return rc;
   const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 16);
   if (h->nod == 20) k_form_km_elastic<20, 128><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, diag_only);

@@ -772,192 +772,319 @@ k_form_km_elastic(const double *__restrict__ g_coord, double *__restrict__ km, l
 // ----------------------------------------------------------------------------
 // BASELINE config E: matrix-free element products, utemp(:,e) = sum_gp B^T (D (B p)) det w
 // ----------------------------------------------------------------------------
-// One thread per (element, Gauss point); a warp owns 4 elements x 8 points and works out of
-// its own slice of shared memory, so there is no block-wide barrier.  Per point the thread
-// rebuilds jac, its inverse and the Cartesian derivatives (fused multiply-adds), forms
-// eps = B p, sigma = D eps * det * w and the 3 nodal products B^T sigma, writes them to a
-// per-point row and the warp then adds the 8 rows in point order.  Same operation order as
-// orc_apply_mf in the oracle.  FP64-pipe bound (~14 kflop per hex20 element), not HBM bound.
+// One THREAD per element, a warp owns 32 consecutive elements.  With the Cartesian derivatives
+// written as deriv = jac^-1 * der, the operator factors through two 3x3 matrices per Gauss point:
+//   H(b,c)  = sum_m der(b,m) p_c(m)                    (phase 1, 9 fma per node and point)
+//   G = jac^-1 H  ->  eps  ->  sigma = D eps det w  ->  T = jac^-T S(sigma)      (~100 flop per point)
+//   u_c(m)  = sum_gp sum_b der(b,m) T_gp(b,c)          (phase 2, 9 fma per node and point)
+// i.e. 18 fma per node and point instead of the 36 of the B-matrix form, and the sum over the Gauss
+// points happens inside the phase-2 chains.  der is the same for every element, so with the loops
+// fully unrolled every der value is an immediate constant-bank operand of its DFMA: the FP64 pipe
+// sees almost nothing but DFMAs, shared memory only carries the thread's own row of right-hand
+// sides / results (staged by the warp with coalesced global accesses), and the 72 T values live in
+// registers.  The Gauss points are processed two at a time so that at most 2x9 H accumulators and
+// the two points' geometric factors are live next to T.  Same operation order as orc_apply_mf.
+// FP64-pipe bound (7 020 flop per hex20 element with stored factors), not HBM bound.
 template <int NOD>
 struct MfCfg {
   static constexpr int NTOT = 3 * NOD;
-  static constexpr int kNodeStride = 4;                   // doubles per node: x,y,z,pad
-  static constexpr int kRow = NOD * kNodeStride + 2;      // +16 B: rows land in distinct 16 B bank groups
-  static constexpr int kPart = NTOT + 1;                  // odd stride: conflict-free per-point rows
-  static constexpr int kWarpDoubles = 4 * kRow * 2 + 32 * kPart;   // coords, p, 32 partial rows
-  static constexpr int kDerDoubles = 8 * kRow;
-  static constexpr size_t smem(int warps) { return (size_t)(kDerDoubles + warps * kWarpDoubles) * 8; }
+  // per-lane rows are read/written with 128-bit accesses: a stride of NTOT+2 doubles (496 / 208 B)
+  // keeps them 16-byte aligned and puts the 8 lanes of a quarter-warp on distinct 16-byte bank groups
+  static constexpr int kRow = NTOT + 2;
+  static constexpr int kGeom = 80;                        // doubles per element: 8 x (jac^-1 (9), det*w)
+  static constexpr int kIdxBytes = 32 * NTOT * 4;         // one group's gather indices (bulk-copied)
+  static constexpr int kDerBytes = NOD * 24 * 8;          // der(b,m) of the 8 points as [m][g][b]
+  static constexpr size_t smem(int warps) { return (size_t)kDerBytes + (size_t)warps * (32 * kRow * 8 + kIdxBytes + 16); }
+  // geometric factors of a group of 32 elements: [g][j][lane] double2, j = 0..4 -- lanes read
+  // consecutive 16-byte words (coalesced); 2560 doubles per group
+  static constexpr long long kGroupGeom = 32LL * kGeom;
 };
 
-// GEOM 0: rebuild jac / inverse / det at every point from the coordinates (config E as named);
-// GEOM 1: only write the 10 geometric factors per (element, point) -- inverse Jacobian and det*w;
-// GEOM 2: read those factors (640 B per hex element instead of 28 800 B of storkm) and skip the
-//         Jacobian pass and its 9 FP64 divisions.  Modes 0 and 2 produce identical bits.
+__device__ __forceinline__ void lds128(uint32_t addr, double &x, double &y) {
+  asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+
+// H(b,c) at [b*3+c], inv = jac^-1 with (a,b) at [b*3+a], f = det*w  ->  T(b,c) at [b*3+c]
+__device__ __forceinline__ void mf_point_mid(const double *H, const double *inv, double f, double *T) {
+  double G[9];  // G(a,c) at [a*3+c]: displacement gradient d u_c / d x_a
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double s = inv[a] * H[c];
+      s = fma(inv[3 + a], H[3 + c], s);
+      s = fma(inv[6 + a], H[6 + c], s);
+      G[a * 3 + c] = s;
+    }
+  // strains in beemat's row order (new_library.f90:976-993)
+  const double eps[6] = {G[0], G[4], G[8], G[3] + G[1], G[7] + G[5], G[6] + G[2]};
+  double sig[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    double s = c_tab.dee[r] * eps[0];
+#pragma unroll
+    for (int c = 1; c < 6; ++c) s = fma(c_tab.dee[c * 6 + r], eps[c], s);
+    sig[r] = s * f;
+  }
+  const double S[9] = {sig[0], sig[3], sig[5], sig[3], sig[1], sig[4], sig[5], sig[4], sig[2]};  // S(a,c) at [a*3+c]
+#pragma unroll
+  for (int b = 0; b < 3; ++b)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double s = inv[b * 3] * S[c];
+      s = fma(inv[b * 3 + 1], S[3 + c], s);
+      s = fma(inv[b * 3 + 2], S[6 + c], s);
+      T[b * 3 + c] = s;
+    }
+}
+
+// GEOM 0: rebuild jac / inverse / det at every point from the coordinates every call (config E as
+//         named); the 80 factors of an element pass through a per-thread scratch line in `geom`
+//         (L2-resident, never re-read by another thread);
+// GEOM 1: only write the factors of every element to `geom` (setup of mode 2);
+// GEOM 2: read them (640 B per hex element instead of 28 800 B of storkm): no Jacobian pass, no
+//         FP64 divisions.  Modes 0 and 2 produce identical bits.
+// Data movement per group of 32 elements: the NEXT group's gather indices arrive by one 1-D bulk
+// async copy (mbarrier) and its geometric factors are prefetched into L2 while the current group is
+// computed; the gather itself keeps one load per dof of the whole group in flight per lane; der comes
+// from a 3.8 KB shared-memory table as warp-uniform (broadcast) 128-bit loads; the factors of the
+// next Gauss point are loaded while the current one is finished.  The Gauss points are accumulated
+// four at a time, so a row of right-hand sides is read from shared memory only twice.
 template <int NOD, bool GATHER, int GEOM, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, const double *__restrict__ pvec,
-           double *__restrict__ utemp, long long nels, const State *st, double *__restrict__ geom) {
+           double *__restrict__ utemp, long long nels, const State *st, double *geom) {
   using Cfg = MfCfg<NOD>;
-  constexpr int NTOT = Cfg::NTOT;
+  constexpr int NTOT = Cfg::NTOT, ROW = Cfg::kRow, KP = (NTOT + 31) / 32;
+  static_assert(NOD % 2 == 0, "nodes are processed in pairs");
   if (st && *(volatile const int *)&st->done) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *s_der = reinterpret_cast<double *>(smem_raw);            // [ig][m][4]
-  const int nwarps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double *s_co = s_der + Cfg::kDerDoubles + (size_t)w * Cfg::kWarpDoubles;   // [el][m][4]
-  double *s_p = s_co + 4 * Cfg::kRow;                                         // [el][m][4]
-  double *s_part = s_p + 4 * Cfg::kRow;                                       // [el*8+ig][kPart]
-  for (int q = threadIdx.x; q < 8 * NOD * 3; q += blockDim.x) {
-    const int ig = q / (NOD * 3), r = q - ig * NOD * 3, a = r / NOD, m = r - a * NOD;
-    s_der[ig * Cfg::kRow + m * 4 + a] = c_tab.der[ig * 60 + a * 20 + m];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *s_der = reinterpret_cast<double *>(smem_raw);                                   // [m][g][b]
+  double *rows = reinterpret_cast<double *>(smem_raw + Cfg::kDerBytes) + (size_t)w * 32 * ROW;
+  int *idxbuf = reinterpret_cast<int *>(smem_raw + Cfg::kDerBytes + (size_t)WARPS * 32 * ROW * 8) + (size_t)w * 32 * NTOT;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + Cfg::kDerBytes + (size_t)WARPS * (32 * ROW * 8 + Cfg::kIdxBytes));
+  const uint32_t bar = smem_u32(&bars[w]);
+  const uint32_t row_s = smem_u32(rows + lane * ROW);       // this lane's element row
+  for (int q = threadIdx.x; q < NOD * 24; q += blockDim.x) {
+    const int m = q / 24, r = q - m * 24, g = r / 3, b = r - g * 3;
+    s_der[q] = c_tab.der[g * 60 + b * 20 + m];
   }
   __syncthreads();
-  const int el = lane >> 3, ig = lane & 7;
-  const double *der = s_der + ig * Cfg::kRow;
-  const double *co = s_co + el * Cfg::kRow;
-  const double *pp = s_p + el * Cfg::kRow;
-  double *part = s_part + lane * Cfg::kPart;
-  const double wt = c_tab.weights[ig];
-  const long long ngroups = (nels + 3) / 4;
-  // software pipeline: while group n is being computed, the coordinates / right-hand sides /
-  // geometric factors of group n+1 and the gather indices of group n+2 are in flight in registers
-  constexpr int NS = (4 * NTOT + 31) / 32;
-  double cr[NS], pr[NS];
-  int ir[NS];
-  double2 gr[5];
-  const long long gstride = (long long)gridDim.x * nwarps;
-  auto load_idx = [&](long long g) {
-    const long long e0 = g * 4;
-    const int ne = (int)((nels - e0) < 4 ? (nels - e0) : 4);
-#pragma unroll
-    for (int i = 0; i < NS; ++i) {
-      const int s = lane + 32 * i;
-      ir[i] = (GATHER && GEOM != 1 && s < ne * NTOT) ? ggl[e0 * NTOT + s] : 0;
-    }
+  const long long ngroups = (nels + 31) / 32;
+  const long long gstride = (long long)gridDim.x * WARPS;
+  uint64_t policy = 0;
+  uint32_t phase = 0;
+  auto issue_idx = [&](long long g) {                      // lane 0 only
+    const long long e0 = g * 32;
+    const int ne = (int)((nels - e0) < 32 ? (nels - e0) : 32);
+    const uint32_t bytes = (uint32_t)ne * NTOT * 4;
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(smem_u32(idxbuf), ggl + e0 * NTOT, bytes, bar, policy);
   };
-  auto load_vals = [&](long long g) {
-    const long long e0 = g * 4;
-    const int ne = (int)((nels - e0) < 4 ? (nels - e0) : 4);
-#pragma unroll
-    for (int i = 0; i < NS; ++i) {
-      const int s = lane + 32 * i;
-      if (s < ne * NTOT) {
-        if (GEOM != 2) cr[i] = g_coord[e0 * NTOT + s];
-        if (GEOM != 1) pr[i] = GATHER ? pvec[ir[i]] : pvec[e0 * NTOT + s];
-      }
+  long long grp = (long long)blockIdx.x * WARPS + w;
+  if (GATHER && GEOM != 1) {
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+      policy = policy_evict_first();
+      if (grp < ngroups) issue_idx(grp);
     }
-    if (GEOM == 2 && el < ne) {
-      const double2 *gf = reinterpret_cast<const double2 *>(geom + ((e0 + el) * 8 + ig) * 10);
-#pragma unroll
-      for (int q = 0; q < 5; ++q) gr[q] = gf[q];
-    }
-  };
-  long long grp = (long long)blockIdx.x * nwarps + w;
-  if (grp < ngroups) { load_idx(grp); load_vals(grp); }
-  if (grp + gstride < ngroups) load_idx(grp + gstride);
+    __syncwarp();
+  }
   for (; grp < ngroups; grp += gstride) {
-    const long long e0 = grp * 4;
-    const int ne = (int)((nels - e0) < 4 ? (nels - e0) : 4);
-    __syncwarp();
+    const long long e0 = grp * 32;
+    const int ne = (int)((nels - e0) < 32 ? (nels - e0) : 32);
+    // this lane's 16-byte words of the group's factors: word (g*5+j) at gfl[(g*5+j)*32]
+    double2 *gfl = reinterpret_cast<double2 *>(geom + (GEOM == 0 ? (long long)blockIdx.x * WARPS + w : grp) * Cfg::kGroupGeom) + lane;
+    if (GEOM == 2 && lane == 0 && grp + gstride < ngroups) {
+      // next group's factors (20 KB) towards L2 while this group is computed
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(geom + (grp + gstride) * Cfg::kGroupGeom),
+                   "r"((uint32_t)(Cfg::kGroupGeom * 8)) : "memory");
+    }
+    if (GEOM != 2) {
+      // coordinates g_coord_pp(nod,3,nels) -> the element's row, [b*NOD+m]
+      if (ne == 32) {
+        double val[32][KP];
 #pragma unroll
-    for (int i = 0; i < NS; ++i) {
-      const int s = lane + 32 * i;
-      if (s < ne * NTOT) {
-        const int le = s / NTOT, k = s - le * NTOT;
-        // coordinates: g_coord_pp(nod,3,nels) -> [m][d]; p: dof k = 3m+c -> [m][c]
-        if (GEOM != 2) {
-          const int d = k / NOD, m = k - d * NOD;
-          s_co[le * Cfg::kRow + m * 4 + d] = cr[i];
+        for (int el = 0; el < 32; ++el)
+#pragma unroll
+          for (int kp = 0; kp < KP; ++kp) {
+            const int k = lane + 32 * kp;
+            val[el][kp] = (k < NTOT) ? g_coord[(e0 + el) * NTOT + k] : 0.0;
+          }
+#pragma unroll
+        for (int el = 0; el < 32; ++el)
+#pragma unroll
+          for (int kp = 0; kp < KP; ++kp) {
+            const int k = lane + 32 * kp;
+            if (k < NTOT) rows[el * ROW + k] = val[el][kp];
+          }
+      } else {
+        for (int el = 0; el < ne; ++el)
+          for (int k = lane; k < NTOT; k += 32) rows[el * ROW + k] = g_coord[(e0 + el) * NTOT + k];
+      }
+      __syncwarp();
+      if (lane < ne) {
+#pragma unroll
+        for (int Q = 0; Q < 2; ++Q) {
+          double J[4][9];
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int z = 0; z < 9; ++z) J[g][z] = 0.0;
+#pragma unroll 2
+          for (int t = 0; t < NOD / 2; ++t) {
+            // [b*NOD+m]: x of nodes 2t,2t+1 / y / z
+            double cx[2], cy[2], cz[2];
+            lds128(row_s + (2 * t) * 8, cx[0], cx[1]);
+            lds128(row_s + (NOD + 2 * t) * 8, cy[0], cy[1]);
+            lds128(row_s + (2 * NOD + 2 * t) * 8, cz[0], cz[1]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const double *der = s_der + (2 * t + h) * 24 + Q * 12;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const double d0 = der[3 * g], d1 = der[3 * g + 1], d2 = der[3 * g + 2];
+                // jac(a,b) at [b*3+a], node-ascending fma chains
+                J[g][0] = fma(d0, cx[h], J[g][0]); J[g][1] = fma(d1, cx[h], J[g][1]); J[g][2] = fma(d2, cx[h], J[g][2]);
+                J[g][3] = fma(d0, cy[h], J[g][3]); J[g][4] = fma(d1, cy[h], J[g][4]); J[g][5] = fma(d2, cy[h], J[g][5]);
+                J[g][6] = fma(d0, cz[h], J[g][6]); J[g][7] = fma(d1, cz[h], J[g][7]); J[g][8] = fma(d2, cz[h], J[g][8]);
+              }
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            double inv[9];
+            const double det = det3(J[g]);
+            inv3(J[g], det, inv);
+            const double f = det * c_tab.weights[4 * Q + g];
+            double2 *o = gfl + (4 * Q + g) * 5 * 32;
+            o[0] = make_double2(inv[0], inv[1]); o[32] = make_double2(inv[2], inv[3]);
+            o[64] = make_double2(inv[4], inv[5]); o[96] = make_double2(inv[6], inv[7]);
+            o[128] = make_double2(inv[8], f);
+          }
         }
-        if (GEOM != 1) s_p[le * Cfg::kRow + (k / 3) * 4 + (k % 3)] = pr[i];
       }
+      __syncwarp();
+      asm volatile("" ::: "memory");  // GEOM 0 re-reads its scratch line below
     }
-    double inv[9], f = 0.0;
-    if (GEOM == 2) {
-      inv[0] = gr[0].x; inv[1] = gr[0].y; inv[2] = gr[1].x; inv[3] = gr[1].y; inv[4] = gr[2].x; inv[5] = gr[2].y;
-      inv[6] = gr[3].x; inv[7] = gr[3].y; inv[8] = gr[4].x; f = gr[4].y;
-    }
-    __syncwarp();
-    if (grp + gstride < ngroups) {
-      load_vals(grp + gstride);
-      if (grp + 2 * gstride < ngroups) load_idx(grp + 2 * gstride);
-    }
-    if (el < ne) {
-      if (GEOM != 2) {
-        double jac[9];
-#pragma unroll
-        for (int q = 0; q < 9; ++q) jac[q] = 0.0;
-#pragma unroll
-        for (int m = 0; m < NOD; ++m) {
-          const double2 dxy = *reinterpret_cast<const double2 *>(der + m * 4);
-          const double dz = der[m * 4 + 2];
-          const double2 cxy = *reinterpret_cast<const double2 *>(co + m * 4);
-          const double cz = co[m * 4 + 2];
-          // jac(a,b) at [b*3+a], node-ascending fma chains
-          jac[0] = fma(dxy.x, cxy.x, jac[0]); jac[1] = fma(dxy.y, cxy.x, jac[1]); jac[2] = fma(dz, cxy.x, jac[2]);
-          jac[3] = fma(dxy.x, cxy.y, jac[3]); jac[4] = fma(dxy.y, cxy.y, jac[4]); jac[5] = fma(dz, cxy.y, jac[5]);
-          jac[6] = fma(dxy.x, cz, jac[6]);    jac[7] = fma(dxy.y, cz, jac[7]);    jac[8] = fma(dz, cz, jac[8]);
-        }
-        const double det = det3(jac);
-        inv3(jac, det, inv);
-        f = det * wt;
-        if (GEOM == 1) {
-          double *gf = geom + ((e0 + el) * 8 + ig) * 10;
-#pragma unroll
-          for (int q = 0; q < 9; ++q) gf[q] = inv[q];
-          gf[9] = f;
-        }
-      }
-      if (GEOM != 1) {
-      double e0_ = 0.0, e1_ = 0.0, e2_ = 0.0, e3_ = 0.0, e4_ = 0.0, e5_ = 0.0;
-#pragma unroll
-      for (int m = 0; m < NOD; ++m) {
-        const double2 dxy = *reinterpret_cast<const double2 *>(der + m * 4);
-        const double dz = der[m * 4 + 2];
-        // deriv(a,m) = sum_b inv(a,b) der(b,m), b ascending from 0
-        const double gx = fma(inv[6], dz, fma(inv[3], dxy.y, fma(inv[0], dxy.x, 0.0)));
-        const double gy = fma(inv[7], dz, fma(inv[4], dxy.y, fma(inv[1], dxy.x, 0.0)));
-        const double gz = fma(inv[8], dz, fma(inv[5], dxy.y, fma(inv[2], dxy.x, 0.0)));
-        const double2 pxy = *reinterpret_cast<const double2 *>(pp + m * 4);
-        const double pz = pp[m * 4 + 2];
-        e0_ = fma(gx, pxy.x, e0_);
-        e1_ = fma(gy, pxy.y, e1_);
-        e2_ = fma(gz, pz, e2_);
-        e3_ = fma(gy, pxy.x, e3_); e3_ = fma(gx, pxy.y, e3_);
-        e4_ = fma(gz, pxy.y, e4_); e4_ = fma(gy, pz, e4_);
-        e5_ = fma(gz, pxy.x, e5_); e5_ = fma(gx, pz, e5_);
-      }
-      const double eps[6] = {e0_, e1_, e2_, e3_, e4_, e5_};
-      double sig[6];
-#pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        double s = 0.0;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) s = fma(c_tab.dee[c * 6 + r], eps[c], s);
-        sig[r] = s * f;
-      }
-#pragma unroll
-      for (int m = 0; m < NOD; ++m) {
-        const double2 dxy = *reinterpret_cast<const double2 *>(der + m * 4);
-        const double dz = der[m * 4 + 2];
-        const double gx = fma(inv[6], dz, fma(inv[3], dxy.y, fma(inv[0], dxy.x, 0.0)));
-        const double gy = fma(inv[7], dz, fma(inv[4], dxy.y, fma(inv[1], dxy.x, 0.0)));
-        const double gz = fma(inv[8], dz, fma(inv[5], dxy.y, fma(inv[2], dxy.x, 0.0)));
-        part[3 * m] = fma(gz, sig[5], fma(gy, sig[3], fma(gx, sig[0], 0.0)));
-        part[3 * m + 1] = fma(gz, sig[4], fma(gx, sig[3], fma(gy, sig[1], 0.0)));
-        part[3 * m + 2] = fma(gx, sig[5], fma(gy, sig[4], fma(gz, sig[2], 0.0)));
-      }
-      }
-    }
-    __syncwarp();
     if (GEOM != 1) {
-      for (int s = lane; s < ne * NTOT; s += 32) {
-        const int le = s / NTOT, k = s - le * NTOT;
-        const double *row = s_part + (le * 8) * Cfg::kPart + k;
-        double acc = row[0];
-#pragma unroll
-        for (int g = 1; g < 8; ++g) acc = acc + row[g * Cfg::kPart];
-        utemp[(e0 + le) * NTOT + k] = acc;
+      // right-hand sides into the elements' rows: one load per dof of the group in flight per lane
+      if (GATHER) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
       }
+      if (ne == 32) {
+        double val[32][KP];
+#pragma unroll
+        for (int el = 0; el < 32; ++el)
+#pragma unroll
+          for (int kp = 0; kp < KP; ++kp) {
+            const int k = lane + 32 * kp;
+            if (GATHER) val[el][kp] = pvec[(k < NTOT) ? idxbuf[el * NTOT + k] : 0];
+            else val[el][kp] = (k < NTOT) ? pvec[(e0 + el) * NTOT + k] : 0.0;
+          }
+#pragma unroll
+        for (int el = 0; el < 32; ++el)
+#pragma unroll
+          for (int kp = 0; kp < KP; ++kp) {
+            const int k = lane + 32 * kp;
+            if (k < NTOT) rows[el * ROW + k] = val[el][kp];
+          }
+      } else {
+        for (int el = 0; el < ne; ++el)
+          for (int k = lane; k < NTOT; k += 32)
+            rows[el * ROW + k] = GATHER ? pvec[idxbuf[el * NTOT + k]] : pvec[(e0 + el) * NTOT + k];
+      }
+      __syncwarp();
+      if (GATHER && lane == 0 && grp + gstride < ngroups) {
+        fence_proxy_async();  // the warp's generic reads of idxbuf are ordered before the async overwrite
+        issue_idx(grp + gstride);
+      }
+      if (lane < ne) {
+        double T[8][9];
+        double gq[4][10];                                   // factors of up to three Gauss points in flight
+        auto load_gq = [&](int g, double *dst) {
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const double2 *src = gfl + (g * 5 + j) * 32;
+            const double2 v = (GEOM == 2) ? __ldg(src) : *src;
+            dst[2 * j] = v.x; dst[2 * j + 1] = v.y;
+          }
+        };
+#pragma unroll
+        for (int Q = 0; Q < 2; ++Q) {
+          // the first two points of this half: in flight during the 4 x 9 x NOD fma below
+          load_gq(4 * Q, gq[0]);
+          load_gq(4 * Q + 1, gq[1]);
+          double H[4][9];
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int z = 0; z < 9; ++z) H[g][z] = 0.0;
+#pragma unroll 2
+          for (int t = 0; t < NOD / 2; ++t) {
+            // dofs 6t..6t+5 = (x,y,z) of nodes 2t and 2t+1
+            double v[6];
+            lds128(row_s + (6 * t) * 8, v[0], v[1]);
+            lds128(row_s + (6 * t + 2) * 8, v[2], v[3]);
+            lds128(row_s + (6 * t + 4) * 8, v[4], v[5]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const double px = v[3 * h], py = v[3 * h + 1], pz = v[3 * h + 2];
+              const double *der = s_der + (2 * t + h) * 24 + Q * 12;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const double d0 = der[3 * g], d1 = der[3 * g + 1], d2 = der[3 * g + 2];
+                H[g][0] = fma(d0, px, H[g][0]); H[g][1] = fma(d0, py, H[g][1]); H[g][2] = fma(d0, pz, H[g][2]);
+                H[g][3] = fma(d1, px, H[g][3]); H[g][4] = fma(d1, py, H[g][4]); H[g][5] = fma(d1, pz, H[g][5]);
+                H[g][6] = fma(d2, px, H[g][6]); H[g][7] = fma(d2, py, H[g][7]); H[g][8] = fma(d2, pz, H[g][8]);
+              }
+            }
+          }
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            if (g4 + 2 < 4) load_gq(4 * Q + g4 + 2, gq[g4 + 2]);     // two points ahead
+            mf_point_mid(H[g4], gq[g4], gq[g4][9], T[4 * Q + g4]);
+          }
+        }
+        // phase 2: one 24-term chain per dof, Gauss points ascending, b ascending inside
+        // (the node loops are NOT fully unrolled: the whole kernel stays within the instruction cache)
+#pragma unroll 2
+        for (int t = 0; t < NOD / 2; ++t) {
+          double o[6];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const double *der = s_der + (2 * t + h) * 24;
+            double ox = der[0] * T[0][0], oy = der[0] * T[0][1], oz = der[0] * T[0][2];
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+#pragma unroll
+              for (int b = 0; b < 3; ++b) {
+                if (g == 0 && b == 0) continue;
+                const double d = der[g * 3 + b];
+                ox = fma(d, T[g][b * 3], ox); oy = fma(d, T[g][b * 3 + 1], oy); oz = fma(d, T[g][b * 3 + 2], oz);
+              }
+            o[3 * h] = ox; o[3 * h + 1] = oy; o[3 * h + 2] = oz;
+          }
+          sts128(row_s + (6 * t) * 8, o[0], o[1]);
+          sts128(row_s + (6 * t + 2) * 8, o[2], o[3]);
+          sts128(row_s + (6 * t + 4) * 8, o[4], o[5]);
+        }
+      }
+      __syncwarp();
+#pragma unroll 8
+      for (int el = 0; el < ne; ++el)
+#pragma unroll
+        for (int kp = 0; kp < KP; ++kp) {
+          const int k = lane + 32 * kp;
+          if (k < NTOT) utemp[(e0 + el) * NTOT + k] = rows[el * ROW + k];
+        }
+      __syncwarp();
     }
   }
 }
