@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--matrix-free", type=int, default=0, choices=[0, 1, 2],
                     help="BASELINE config E: 1 = rebuild the element operator from coordinates every iteration, "
                          "2 = same with stored geometric factors (FP64-pipe roofline)")
+    ap.add_argument("--layout", type=int, default=0, choices=[0, 1],
+                    help="storkm layout of the main measurement: 0 = the reference's storkm_pp (headline), "
+                         "1 = packed lower triangles (half the stream)")
     ap.add_argument("--weak", action="store_true",
                     help="weak scaling: n x (n*N) x n elements, i.e. one n^3 slab of y-planes per GPU")
     ap.add_argument("--no-variants", dest="variants", action="store_false",
@@ -196,12 +199,12 @@ def main():
     t_mesh = time.time() - t_setup0
     s = solver.Solver(rank, nranks, local, nccl_id)
     t0 = time.time()
-    solver.setup_problem(s, prob, matrix_free=args.matrix_free)
+    solver.setup_problem(s, prob, matrix_free=args.matrix_free, layout=args.layout)
     barrier()
     t_dev_setup = time.time() - t0
     fp64_tflops = s.measure_fp64() if args.matrix_free else None
     ntot = prob.ntot
-    storkm_bytes_pp = prob.nels_pp * ntot * ntot * 8
+    storkm_bytes_pp = prob.nels_pp * (ntot * (ntot + 1) // 2 if args.layout == 1 else ntot * ntot) * 8
 
     K, W = args.steps, max(args.warmup, 3)
     import ctypes as C
@@ -298,9 +301,27 @@ def main():
 
     # ---- the matrix-free variants of the same workload (BASELINE config E), same process ----------
     variants = None
-    if args.variants and args.program == "p121" and not args.matrix_free:
+    if args.variants and args.program == "p121" and not args.matrix_free and args.layout == 0:
         variants = {}
         peak = None
+        # packed lower triangles (pf_set_storkm_layout 1): same algorithm and summation order, half the stream
+        solver.setup_problem(s, prob, layout=1)
+        mm = measure()
+        sym_bytes = prob.nels_pp * (ntot * (ntot + 1) // 2) * 8
+        sv_ms, sv_n = mm["kernel_ms"]["matvec"]
+        sv_avg = sv_ms / max(sv_n, 1)
+        variants["stored_symmetric_packed"] = {
+            "value": mm["value"], "unit": UNIT, "ms_per_step": mm["ms"] / K, "e2e": {"value": mm["e2e_value"], "unit": UNIT},
+            "kernel_ms_per_step": {k: mm["kernel_ms"][k][0] / K for k in mm["kernel_ms"]},
+            "roofline": {"bound": "hbm", "achieved": sym_bytes / (sv_avg / 1e3) / 1e9, "peak": peaks()[0]["hbm_gbs"],
+                         "unit": "GB/s", "frac": sym_bytes / (sv_avg / 1e3) / 1e9 / peaks()[0]["hbm_gbs"], "traffic": None,
+                         "kernel": "k_matvec_sym (packed lower triangles, gather fused)",
+                         "algorithmic_bytes_per_launch": sym_bytes, "avg_launch_ms": sv_avg, "launches_timed": int(sv_n)},
+            "gpu_launches": int(mm["launches"]),
+            "note": "K(i,j) = L(max,min): bit-identical to MATMUL on the symmetrised matrices; not the headline "
+                    "because the reference's storkm_pp is only symmetric to rounding"}
+        if not args.no_solve:
+            variants["stored_symmetric_packed"]["time_to_solution"] = solve_to_convergence()
         for mode, name in ((2, "matrix_free_geometric_factors"), (1, "matrix_free_rebuilt_from_coordinates")):
             solver.setup_problem(s, prob, matrix_free=mode)
             peak = peak or s.measure_fp64()
@@ -336,10 +357,11 @@ def main():
             "gpu_launches": int(launches),
             "roofline": ({"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                           "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": traffic,
-                          "kernel": "k_matvec (storkm stream; gather fused)", "peak_kind": pk_kind,
+                          "kernel": ("k_matvec_sym" if args.layout == 1 else "k_matvec") + " (storkm stream; gather fused)", "peak_kind": pk_kind,
                           "algorithmic_bytes_per_launch": storkm_bytes_pp, "avg_launch_ms": mv_avg_ms,
                           "launches_timed": int(mv_n)} if not args.matrix_free else
                          mf_roofline(args.matrix_free, m, fp64_tflops)),
+            "storkm_layout": "packed lower triangles" if args.layout == 1 else "storkm_pp(ntot,ntot,nels_pp) as the reference",
             "variant": {0: "stored storkm", 1: "matrix-free, rebuilt from coordinates (config E)",
                         2: "matrix-free, stored geometric factors"}[args.matrix_free],
             "kernel_ms_per_step": {"matvec": mv_ms / K, "scatter": sc_ms / K, "vector_and_reductions": vec_ms / K,

@@ -60,6 +60,15 @@ MODULE parafem_gpu
       IMPORT; TYPE(c_ptr),VALUE :: h; REAL(c_double) :: storkm_pp(*)
     END FUNCTION
 
+    ! optional variants, call before forming the matrices: matrix-free operator (1 rebuild, 2 stored
+    ! geometric factors) and the packed-lower-triangle storkm layout (1; 0 = storkm_pp as in p121.f90:33)
+    INTEGER(c_int) FUNCTION pf_set_matrix_free(h,mode) BIND(C,name='pf_set_matrix_free')
+      IMPORT; TYPE(c_ptr),VALUE :: h; INTEGER(c_int),VALUE :: mode
+    END FUNCTION
+    INTEGER(c_int) FUNCTION pf_set_storkm_layout(h,layout) BIND(C,name='pf_set_storkm_layout')
+      IMPORT; TYPE(c_ptr),VALUE :: h; INTEGER(c_int),VALUE :: layout
+    END FUNCTION
+
     ! p121.f90:65-69,86 / p123.f90:86-92,120-125 ; no_f_pp = GLOBAL equation numbers
     INTEGER(c_int) FUNCTION pf_build_precon(h,nfixed_pp,no_f_pp,penalty) BIND(C,name='pf_build_precon')
       IMPORT; TYPE(c_ptr),VALUE :: h; INTEGER(c_int64_t),VALUE :: nfixed_pp

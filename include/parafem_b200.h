@@ -88,7 +88,17 @@ int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp,
  * pf_set_matrix_free(2): as 1, but the inverse Jacobian and det*w of every
  * Gauss point (10 doubles, 640 B per element) are stored at setup and read
  * back instead of being rebuilt -- same bits as mode 1, no FP64 divisions
- * in the loop ("partial assembly").                                        */
+ * in the loop ("partial assembly").
+ * pf_set_storkm_layout(h, 1) (call before forming / uploading the matrices):
+ * keep only the lower triangle of every element matrix, packed by columns
+ * (ntot(ntot+1)/2 doubles: 14 640 B instead of 28 800 B per 20-node brick),
+ * which halves the storkm stream of every iteration.  The product keeps the
+ * reference's summation order with K(i,j) = L(max(i,j),min(i,j)); it is
+ * bit-identical to MATMUL on the symmetrised matrix, and differs from the
+ * reference's unsymmetrised storkm_pp only where BtDB rounding breaks the
+ * symmetry (relative 1e-16).  pf_get_storkm returns the symmetrised matrices.
+ * Layout 0 (default) is the reference's storkm_pp, bit for bit.             */
+int pf_set_storkm_layout(pf_handle h, int layout);
 int pf_form_km_elastic(pf_handle h, double e, double v);
 int pf_form_kc_laplace(pf_handle h, double kx, double ky, double kz);
 int pf_set_storkm(pf_handle h, const double *storkm_pp);

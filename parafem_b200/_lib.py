@@ -46,6 +46,7 @@ SIGNATURES = {
     "pf_set_storkm": (c_int, [vp, vp]),
     "pf_get_storkm": (c_int, [vp, c_i64, c_i64, vp]),
     "pf_set_matrix_free": (c_int, [vp, c_int]),
+    "pf_set_storkm_layout": (c_int, [vp, c_int]),
     "pf_build_precon": (c_int, [vp, c_i64, vp, c_dbl]),
     "pf_get_diag_precon": (c_int, [vp, vp]),
     "pf_get_store": (c_int, [vp, vp]),

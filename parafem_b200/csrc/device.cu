@@ -77,6 +77,7 @@ struct pf_ctx {
   bool have_mesh = false, have_km = false, have_precon = false, matrix_free = false;
   DevBuf<double> coord, km, utemp, diag_tmp, geom;
   int mf_mode = 0;
+  int km_layout = 0;   // 0: storkm_pp(ntot,ntot,nels_pp) as the reference; 1: packed lower triangles (SymCfg)
   DevBuf<int> ggl;
   DevBuf<unsigned int> csr_ptr, csr_pos;
 
@@ -262,6 +263,23 @@ int mf_grid(pf_handle h) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (ngroups + kMfWarps - 1) / kMfWarps));
 }
 
+template <int NTOT, int EPT, int STAGES, bool GATHER>
+int launch_matvec_sym_t(pf_handle h, const double *pvec, const State *st) {
+  using Cfg = MatvecSymCfg<NTOT, EPT, STAGES>;
+  auto kern = k_matvec_sym<NTOT, EPT, STAGES, GATHER>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+    attr_set = true;
+  }
+  const int64_t ntiles = (h->nels + EPT - 1) / EPT;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, ntiles));
+  kern<<<grid, Cfg::kThreads, Cfg::kSmem, h->stream>>>(h->km.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
 template <int NOD, bool GATHER, int GEOM>
 int launch_mf_t(pf_handle h, const double *pvec, const State *st) {
   using Cfg = MfCfg<NOD>;
@@ -291,6 +309,19 @@ int launch_matvec(pf_handle h, const double *pvec, const State *st) {
   }
   // PF_TUNE selects an alternative tile shape (elements per tile x ring slots) for experiments
   static const int tune = getenv("PF_TUNE") ? atoi(getenv("PF_TUNE")) : 0;
+  if (h->km_layout == 1) {
+    switch (h->ntot) {
+      case 60:
+        if (tune == 1) return launch_matvec_sym_t<60, 1, 8, GATHER>(h, pvec, st);
+        if (tune == 2) return launch_matvec_sym_t<60, 2, 6, GATHER>(h, pvec, st);
+        return launch_matvec_sym_t<60, 1, 13, GATHER>(h, pvec, st);
+      case 24:
+        if (tune == 1) return launch_matvec_sym_t<24, 4, 16, GATHER>(h, pvec, st);
+        return launch_matvec_sym_t<24, 2, 32, GATHER>(h, pvec, st);
+      case 8: return launch_matvec_sym_t<8, 16, 32, GATHER>(h, pvec, st);
+    }
+    return fail(h, 3, "unsupported ntot %d (supported: 60, 24, 8)", h->ntot);
+  }
   switch (h->ntot) {
     case 60: return launch_matvec_t<60, 1, 7, GATHER>(h, pvec, st);
     // measured on B200 (profiles/r01_tile_tuning.md): small tiles on many ring slots win --
@@ -309,7 +340,7 @@ int launch_matvec(pf_handle h, const double *pvec, const State *st) {
 int launch_scatter(pf_handle h, const State *st, bool diag, double *dst) {
   Scope sc(h, K_SCATTER);
   const int grid = grid_for(h, h->nslots, 256, 16);
-  if (diag) k_scatter<true><<<grid, 256, 0, h->stream>>>(h->csr_ptr.p, h->csr_pos.p, h->km.p, dst, (long long)h->nslots, h->ntot, st);
+  if (diag) k_scatter<true><<<grid, 256, 0, h->stream>>>(h->csr_ptr.p, h->csr_pos.p, h->km.p, dst, (long long)h->nslots, h->ntot, st, h->km_layout);
   else k_scatter<false><<<grid, 256, 0, h->stream>>>(h->csr_ptr.p, h->csr_pos.p, h->utemp.p, dst, (long long)h->nslots, h->ntot, st);
   h->launches++;
   CU(cudaGetLastError());
@@ -781,8 +812,12 @@ int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp, con
   return 0;
 }
 
+static size_t km_per_element(pf_handle h) {
+  return h->km_layout == 1 ? (size_t)h->ntot * (h->ntot + 1) / 2 : (size_t)h->ntot * h->ntot;
+}
 static int alloc_km(pf_handle h) {
-  if (h->km.n != (size_t)h->nels * h->ntot * h->ntot) CU(h->km.alloc((size_t)h->nels * h->ntot * h->ntot));
+  const size_t n = (size_t)h->nels * km_per_element(h);
+  if (h->km.n != n) CU(h->km.alloc(n));
   return 0;
 }
 
@@ -811,8 +846,8 @@ int pf_form_km_elastic(pf_handle h, double e, double v) {
     }
   } else if ((rc = alloc_km(h))) return rc;
   const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 16);
-  if (h->nod == 20) k_form_km_elastic<20, 128><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, diag_only);
-  else k_form_km_elastic<8, 64><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, diag_only);
+  if (h->nod == 20) k_form_km_elastic<20, 128><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, diag_only, h->km_layout);
+  else k_form_km_elastic<8, 64><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, diag_only, h->km_layout);
   h->launches++;
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));
@@ -828,7 +863,7 @@ int pf_form_kc_laplace(pf_handle h, double kx, double ky, double kz) {
   CU(cudaMemcpyToSymbol(c_tab, &T, sizeof T));
   if ((rc = alloc_km(h))) return rc;
   const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 32);
-  k_form_kc_laplace<<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels);
+  k_form_kc_laplace<<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout);
   h->launches++;
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));
@@ -841,7 +876,24 @@ int pf_set_storkm(pf_handle h, const double *storkm_pp) {
   NEED(h->have_mesh && storkm_pp, "needs pf_setup_mesh");
   NEED(!h->matrix_free, "matrix-free variant: storkm is not stored");
   if ((rc = alloc_km(h))) return rc;
-  CU(cudaMemcpy(h->km.p, storkm_pp, h->km.bytes(), cudaMemcpyHostToDevice));
+  if (h->km_layout == 0) {
+    CU(cudaMemcpy(h->km.p, storkm_pp, h->km.bytes(), cudaMemcpyHostToDevice));
+  } else {
+    // symmetric layout: the lower triangle of every matrix is kept (chunks through a staging buffer)
+    const size_t per = (size_t)h->ntot * h->ntot, P = km_per_element(h);
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)((256u << 20) / (per * 8)));
+    DevBuf<double> stage;
+    CU(stage.alloc((size_t)std::min<int64_t>(chunk, h->nels) * per));
+    for (int64_t e = 0; e < h->nels; e += chunk) {
+      const int64_t n = std::min<int64_t>(chunk, h->nels - e);
+      CU(cudaMemcpyAsync(stage.p, storkm_pp + (size_t)e * per, (size_t)n * per * 8, cudaMemcpyHostToDevice, h->stream));
+      k_pack_lower<<<grid_for(h, n * (int64_t)per, 256), 256, 0, h->stream>>>(stage.p, h->km.p + (size_t)e * P, (long long)n, h->ntot);
+      h->launches++;
+      CU(cudaStreamSynchronize(h->stream));
+    }
+    CU(cudaGetLastError());
+    stage.release();
+  }
   h->have_km = true; h->have_precon = false;
   return 0;
 }
@@ -851,7 +903,32 @@ int pf_get_storkm(pf_handle h, int64_t iel0, int64_t n, double *out) {
   NEED(!h->matrix_free, "matrix-free variant: storkm is not stored");
   NEED(h->have_km && iel0 >= 0 && n >= 0 && iel0 + n <= h->nels, "range outside the local elements");
   const size_t per = (size_t)h->ntot * h->ntot;
-  CU(cudaMemcpy(out, h->km.p + (size_t)iel0 * per, (size_t)n * per * 8, cudaMemcpyDeviceToHost));
+  if (h->km_layout == 0) {
+    CU(cudaMemcpy(out, h->km.p + (size_t)iel0 * per, (size_t)n * per * 8, cudaMemcpyDeviceToHost));
+    return 0;
+  }
+  // symmetric layout: K(i,j) = L(max,min) -- the matrix the product uses
+  const size_t P = km_per_element(h);
+  const int64_t chunk = std::max<int64_t>(1, (int64_t)((256u << 20) / (per * 8)));
+  DevBuf<double> stage;
+  CU(stage.alloc((size_t)std::max<int64_t>(1, std::min<int64_t>(chunk, n)) * per));
+  for (int64_t e = 0; e < n; e += chunk) {
+    const int64_t m = std::min<int64_t>(chunk, n - e);
+    k_unpack_lower<<<grid_for(h, m * (int64_t)per, 256), 256, 0, h->stream>>>(h->km.p + (size_t)(iel0 + e) * P, stage.p, (long long)m, h->ntot);
+    h->launches++;
+    CU(cudaMemcpyAsync(out + (size_t)e * per, stage.p, (size_t)m * per * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  CU(cudaGetLastError());
+  stage.release();
+  return 0;
+}
+
+int pf_set_storkm_layout(pf_handle h, int layout) {
+  if (!h) return 1;
+  NEED(layout == 0 || layout == 1, "layout must be 0 (reference storkm_pp) or 1 (packed lower triangles)");
+  if (layout != h->km_layout) { h->km.release(); h->have_km = false; h->have_precon = false; }
+  h->km_layout = layout;
   return 0;
 }
 

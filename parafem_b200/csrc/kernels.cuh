@@ -164,6 +164,115 @@ k_matvec(const double *__restrict__ km, const int *__restrict__ ggl, const doubl
   }
 }
 
+// ----------------------------------------------------------------------------
+// a8 on the symmetric-packed layout (pf_set_storkm_layout(h, 1)): half the storkm stream.
+// ----------------------------------------------------------------------------
+// Only the lower triangle of every element matrix is stored, packed by columns: column j holds
+// rows j..NTOT-1 at offset coloff(j) = j*NTOT - j(j-1)/2 (1 830 doubles = 14 640 B per 20-node
+// brick instead of 28 800 B).  The product keeps the reference's order, u_r = sum_j K(r,j) p_j with
+// j ascending from 0.0 and separate multiply / add, with K(r,j) = L(max(r,j), min(r,j)): it equals
+// MATMUL(storkm,pmul) of the symmetrised matrix bit for bit (and of storkm itself wherever storkm
+// is bitwise symmetric).  Lane t of an element owns rows t and NTOT-1-t, so every lane does the
+// same work: for j <= r the entry sits in column j (lanes read consecutive words), for j > r in
+// the lane's own column r.  Same persistent ring of bulk-copied tiles as k_matvec.
+template <int NTOT>
+struct SymCfg {
+  static constexpr int kPacked = NTOT * (NTOT + 1) / 2;
+  __host__ __device__ static constexpr int coloff(int j) { return j * NTOT - j * (j - 1) / 2; }
+};
+template <int NTOT, int EPT, int STAGES>
+struct MatvecSymCfg {
+  static constexpr int kTileDoubles = EPT * SymCfg<NTOT>::kPacked;
+  static constexpr int kTileBytes = kTileDoubles * 8;
+  static constexpr int kPmDoubles = EPT * NTOT;
+  static constexpr int kThreads = STAGES * 32;
+  static constexpr size_t kSmem = (size_t)STAGES * kTileBytes + (size_t)STAGES * kPmDoubles * 8 + STAGES * 8;
+};
+
+template <int NTOT, int EPT, int STAGES, bool GATHER>
+__global__ void __launch_bounds__(STAGES * 32, 1)
+k_matvec_sym(const double *__restrict__ kp, const int *__restrict__ ggl, const double *__restrict__ pvec,
+             double *__restrict__ utemp, long long nels, const State *st) {
+  using Cfg = MatvecSymCfg<NTOT, EPT, STAGES>;
+  constexpr int P = SymCfg<NTOT>::kPacked, LPE = NTOT / 2, EPW = 32 / LPE;   // lanes per element, elements per warp pass
+  static_assert(NTOT % 2 == 0 && LPE <= 32 && (EPT % EPW == 0 || EPW == 1), "tile shape");
+  if (st && *(volatile const int *)&st->done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *tiles = reinterpret_cast<double *>(smem_raw);
+  double *pm_all = tiles + (size_t)STAGES * Cfg::kTileDoubles;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(pm_all + STAGES * Cfg::kPmDoubles);
+
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ntiles = (nels + EPT - 1) / EPT;
+  const long long t0 = ntiles * blockIdx.x / gridDim.x;
+  const long long t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
+  double *tile = tiles + (size_t)w * Cfg::kTileDoubles;
+  double *pm = pm_all + w * Cfg::kPmDoubles;
+  const uint32_t bar = smem_u32(&bars[w]);
+  const uint32_t tile_s = smem_u32(tile);
+  uint64_t policy = 0;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    policy = policy_evict_first();
+  }
+  __syncwarp();
+
+  auto issue = [&](long long t) {
+    const long long e0 = t * EPT;
+    const int ne = (int)((nels - e0) < EPT ? (nels - e0) : EPT);
+    const uint32_t bytes = (uint32_t)ne * P * 8;
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(tile_s, kp + e0 * (long long)P, bytes, bar, policy);
+  };
+
+  // this lane's two rows and where their own columns start (minus the row number)
+  const int sub = lane / LPE, tl = lane - sub * LPE;
+  const int r0 = tl, r1 = NTOT - 1 - tl;
+  const int c0 = SymCfg<NTOT>::coloff(r0) - r0, c1 = SymCfg<NTOT>::coloff(r1) - r1;
+  const bool lane_on = sub < EPW;
+
+  long long t = t0 + w;
+  if (t < t1 && lane == 0) issue(t);
+  uint32_t phase = 0;
+  for (; t < t1; t += STAGES) {
+    const long long e0 = t * EPT;
+    const int ne = (int)((nels - e0) < EPT ? (nels - e0) : EPT);
+    for (int s = lane; s < ne * NTOT; s += 32) {
+      if (GATHER) pm[s] = pvec[ggl[e0 * NTOT + s]];
+      else pm[s] = pvec[e0 * NTOT + s];
+    }
+    __syncwarp();
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    for (int eb = 0; eb < ne; eb += EPW) {
+      const int el = eb + sub;
+      const bool on = lane_on && el < ne;
+      const double *L = tile + (on ? el : 0) * P;
+      const double *pv = pm + (on ? el : 0) * NTOT;
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < NTOT; ++j) {
+        const double pj = pv[j];
+        const int o0 = (r0 >= j) ? (SymCfg<NTOT>::coloff(j) - j) + r0 : c0 + j;
+        const int o1 = (r1 >= j) ? (SymCfg<NTOT>::coloff(j) - j) + r1 : c1 + j;
+        a0 = a0 + L[o0] * pj;
+        a1 = a1 + L[o1] * pj;
+      }
+      if (on) {
+        utemp[(e0 + el) * NTOT + r0] = a0;
+        utemp[(e0 + el) * NTOT + r1] = a1;
+      }
+    }
+    __syncwarp();
+    const long long tn = t + STAGES;
+    if (tn < t1 && lane == 0) {
+      fence_proxy_async();
+      issue(tn);
+    }
+  }
+}
+
 // pmul materialised (pf_gather only; the solver never does this)
 __global__ void k_gather(const int *__restrict__ ggl, const double *__restrict__ p_ext,
                          double *__restrict__ pmul, long long n) {
@@ -180,7 +289,7 @@ __global__ void k_gather(const int *__restrict__ ggl, const double *__restrict__
 template <bool DIAG>
 __global__ void k_scatter(const unsigned int *__restrict__ csr_ptr, const unsigned int *__restrict__ csr_pos,
                           const double *__restrict__ src, double *__restrict__ u_ext, long long nslots,
-                          int ntot, const State *st) {
+                          int ntot, const State *st, int packed = 0) {
   if (st && *(volatile const int *)&st->done) return;
   long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x + 1;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -191,7 +300,8 @@ __global__ void k_scatter(const unsigned int *__restrict__ csr_ptr, const unsign
       const unsigned int pos = csr_pos[k];
       if (DIAG) {
         const unsigned int e = pos / ntot, d = pos - e * ntot;
-        acc = acc + src[(size_t)e * ntot * ntot + (size_t)d * ntot + d];
+        if (packed) acc = acc + src[(size_t)e * (ntot * (ntot + 1) / 2) + (size_t)d * ntot - d * (d - 1) / 2];
+        else acc = acc + src[(size_t)e * ntot * ntot + (size_t)d * ntot + d];
       } else {
         acc = acc + src[pos];
       }
@@ -704,7 +814,8 @@ __device__ __forceinline__ double gauss_point(int ig, const double *s_coord, dou
 template <int NOD, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_form_km_elastic(const double *__restrict__ g_coord, double *__restrict__ km, long long nels,
-                  double *__restrict__ diag_only /* matrix-free: (ntot,nels) diagonal instead of km */) {
+                  double *__restrict__ diag_only /* matrix-free: (ntot,nels) diagonal instead of km */,
+                  int packed /* 1: lower triangle only, packed by columns (SymCfg) */) {
   constexpr int NTOT = 3 * NOD, NENT = NTOT * NTOT, PER = (NENT + THREADS - 1) / THREADS;
   __shared__ double s_coord[NOD * 3], s_jac[9], s_deriv[NOD * 3];
   __shared__ double s_bee[6 * NTOT];  // bee(l,c) at [c*6+l]
@@ -760,6 +871,9 @@ k_form_km_elastic(const double *__restrict__ g_coord, double *__restrict__ km, l
         if (diag_only) {
           const int j = idx / NTOT, i = idx - j * NTOT;
           if (i == j) diag_only[e * (long long)NTOT + i] = acc[n];
+        } else if (packed) {
+          const int j = idx / NTOT, i = idx - j * NTOT;
+          if (i >= j) km[e * (long long)SymCfg<NTOT>::kPacked + SymCfg<NTOT>::coloff(j) + (i - j)] = acc[n];
         } else {
           km[e * (long long)NENT + idx] = acc[n];
         }
@@ -1091,7 +1205,7 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
 
 // elements_1 of p123.f90:71-84; 8-node bricks, 64 threads = one per entry
 __global__ void __launch_bounds__(64)
-k_form_kc_laplace(const double *__restrict__ g_coord, double *__restrict__ kc, long long nels) {
+k_form_kc_laplace(const double *__restrict__ g_coord, double *__restrict__ kc, long long nels, int packed) {
   constexpr int NOD = 8;
   __shared__ double s_coord[NOD * 3], s_jac[9], s_deriv[NOD * 3];
   const int j = threadIdx.x / 8, i = threadIdx.x % 8;
@@ -1108,10 +1222,34 @@ k_form_kc_laplace(const double *__restrict__ g_coord, double *__restrict__ kc, l
       kz = kz + s_deriv[i * 3 + 2] * s_deriv[j * 3 + 2] * det * wt;
       __syncthreads();
     }
-    kc[e * 64 + threadIdx.x] = kx * c_tab.kxyz[0] + ky * c_tab.kxyz[1] + kz * c_tab.kxyz[2];
+    const double val = kx * c_tab.kxyz[0] + ky * c_tab.kxyz[1] + kz * c_tab.kxyz[2];
+    if (!packed) kc[e * 64 + threadIdx.x] = val;
+    else if (i >= j) kc[e * SymCfg<8>::kPacked + SymCfg<8>::coloff(j) + (i - j)] = val;
   }
 }
 
+
+// full (ntot,ntot) column-major element matrices <-> packed lower triangles (pf_set_storkm / pf_get_storkm
+// on the symmetric layout); unpacking mirrors the lower triangle
+__global__ void k_pack_lower(const double *__restrict__ full, double *__restrict__ packed, long long nel, int ntot) {
+  const int P = ntot * (ntot + 1) / 2;
+  const long long total = nel * (long long)ntot * ntot;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const long long e = q / (ntot * ntot);
+    const int r = (int)(q - e * ntot * ntot), j = r / ntot, i = r - j * ntot;
+    if (i >= j) packed[e * P + j * ntot - j * (j - 1) / 2 + (i - j)] = full[q];
+  }
+}
+__global__ void k_unpack_lower(const double *__restrict__ packed, double *__restrict__ full, long long nel, int ntot) {
+  const int P = ntot * (ntot + 1) / 2;
+  const long long total = nel * (long long)ntot * ntot;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const long long e = q / (ntot * ntot);
+    const int r = (int)(q - e * ntot * ntot), j = r / ntot, i = r - j * ntot;
+    const int hi = i >= j ? i : j, lo = i >= j ? j : i;
+    full[q] = packed[e * P + lo * ntot - lo * (lo - 1) / 2 + (hi - lo)];
+  }
+}
 
 // DFMA micro-benchmark: the FP64 denominator for the matrix-free variant ("of measured").
 // 8 independent fma chains per thread, `iters` rounds; 2 flop per fma.

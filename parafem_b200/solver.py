@@ -70,6 +70,10 @@ class Solver:
         """BASELINE config E: call before form_km_elastic."""
         self._ck(lib().pf_set_matrix_free(self._h, int(on)), "pf_set_matrix_free")
 
+    def set_storkm_layout(self, layout):
+        """0: the reference's storkm_pp; 1: packed lower triangles (half the stream). Before forming."""
+        self._ck(lib().pf_set_storkm_layout(self._h, int(layout)), "pf_set_storkm_layout")
+
     def measure_fp64(self):
         t = C.c_double()
         self._ck(lib().pf_measure_fp64(self._h, C.byref(t)), "pf_measure_fp64")
@@ -184,10 +188,11 @@ class Solver:
         return sm.value, fr.value, tot.value
 
 
-def setup_problem(solver, prob, matrix_free=False):
+def setup_problem(solver, prob, matrix_free=False, layout=0):
     """The device part of p121.f90:49-69,86 / p123.f90:57-92,120-125 for one rank."""
     solver.setup_mesh(prob)
     solver.set_matrix_free(matrix_free)
+    solver.set_storkm_layout(layout)
     if prob.program == 121:
         solver.form_km_elastic(prob.e, prob.v)
         solver.build_precon()
