@@ -312,12 +312,14 @@ int launch_matvec(pf_handle h, const double *pvec, const State *st) {
   if (h->km_layout == 1) {
     switch (h->ntot) {
       case 60:
-        if (tune == 1) return launch_matvec_sym_t<60, 1, 8, GATHER>(h, pvec, st);
-        if (tune == 2) return launch_matvec_sym_t<60, 2, 6, GATHER>(h, pvec, st);
-        return launch_matvec_sym_t<60, 1, 13, GATHER>(h, pvec, st);
-      case 24:
-        if (tune == 1) return launch_matvec_sym_t<24, 4, 16, GATHER>(h, pvec, st);
-        return launch_matvec_sym_t<24, 2, 32, GATHER>(h, pvec, st);
+        // measured: 10 ring slots 0.95 of HBM peak, 13 slots 0.93, 8 slots 0.94, 2 elements x 6 slots 0.72
+        if (tune == 1) return launch_matvec_sym_t<60, 1, 13, GATHER>(h, pvec, st);
+        if (tune == 2) return launch_matvec_sym_t<60, 1, 8, GATHER>(h, pvec, st);
+        return launch_matvec_sym_t<60, 1, 10, GATHER>(h, pvec, st);
+      case 24:   // measured (profiles/r01_symmetric_layout.md): 4 x 16 beats 2 x 32 (64-register cap, spills)
+        if (tune == 1) return launch_matvec_sym_t<24, 2, 32, GATHER>(h, pvec, st);
+        if (tune == 2) return launch_matvec_sym_t<24, 6, 12, GATHER>(h, pvec, st);
+        return launch_matvec_sym_t<24, 4, 16, GATHER>(h, pvec, st);
       case 8: return launch_matvec_sym_t<8, 16, 32, GATHER>(h, pvec, st);
     }
     return fail(h, 3, "unsupported ntot %d (supported: 60, 24, 8)", h->ntot);
