@@ -37,11 +37,14 @@ def main():
     dist.broadcast(idt, src=0)
     s = solver.Solver(rank, world, local, idt.numpy())
     failures = []
-    for name in sys.argv[1:]:
+    for spec in sys.argv[1:]:
+        # "name" or "name:sym" (packed lower triangles) or "name:mf1" / "name:mf2" (matrix-free variants)
+        name, _, variant = spec.partition(":")
         p = problem(name, world, rank + 1)
         full = problem(name, 1, 1)
         r0 = p.r_pp.copy()
-        solver.setup_problem(s, p)
+        mf_mode = int(variant[2:]) if variant.startswith("mf") else 0
+        solver.setup_problem(s, p, matrix_free=mf_mode, layout=1 if variant == "sym" else 0)
         lo = p.ieq_start - 1
         # operator pieces
         rng = np.random.RandomState(11)
@@ -49,10 +52,14 @@ def main():
         qv = rng.randn(p.neq)
         km = (oracle.form_km_elastic(full.g_coord_pp, full.nod, full.nip, full.e, full.v) if p.program == 121
               else oracle.form_kc_laplace(full.g_coord_pp, full.nip, full.kx, full.ky, full.kz))
+        if variant == "sym":      # K(i,j) = L(max,min): the oracle on the symmetrised matrices
+            km = np.triu(km) + np.triu(km, 1).transpose(0, 2, 1)
+        mf = dict(g_coord_pp=full.g_coord_pp, nod=full.nod, nip=full.nip, e=full.e, v=full.v) if mf_mode else None
         pm_ref = oracle.gather(full.g_g_pp, pv)
         e0 = p.iel_start - 1
         ok_g = np.array_equal(s.gather(pv[lo:lo + p.neq_pp]), pm_ref[e0:e0 + p.nels_pp])
-        u_ref = oracle.scatter(full.g_g_pp, oracle.matvec(km, pm_ref), p.neq, npes=world)
+        ut_ref = oracle.apply_mf(full.g_coord_pp, full.nod, full.nip, full.e, full.v, pm_ref) if mf_mode else oracle.matvec(km, pm_ref)
+        u_ref = oracle.scatter(full.g_g_pp, ut_ref, p.neq, npes=world)
         s.nfixed_saved = None
         u = s.apply(pv[lo:lo + p.neq_pp])
         if p.no_f.size:   # fixed freedom rows are overridden by u = p*store in the solver path
@@ -65,11 +72,11 @@ def main():
         x, iters, conv = s.pcg_solve(p.r_pp, p.tol, p.limit)
         no_f = full.no_f if full.no_f.size else None
         ref = oracle.pcg(km, full.g_g_pp, p.neq, full.r_pp if no_f is None else np.zeros(p.neq), p.tol, p.limit,
-                         npes=world, red_mode=1, no_f=no_f, val_f=full.val_f if no_f is not None else None)
+                         npes=world, red_mode=1, no_f=no_f, val_f=full.val_f if no_f is not None else None, mf=mf)
         ok_x = np.array_equal(x, ref["x"][lo:lo + p.neq_pp])
         ok_i = iters == ref["iters"] and conv == ref["converged"]
         rel = np.linalg.norm(x - ref["x"][lo:lo + p.neq_pp]) / max(np.linalg.norm(ref["x"][lo:lo + p.neq_pp]), 1e-300)
-        line = f"[rank {rank}] {name}: gather={ok_g} apply={ok_u} dot={ok_d} iters={iters}/{ref['iters']} x_equal={ok_x} rel={rel:.2e}"
+        line = f"[rank {rank}] {spec}: gather={ok_g} apply={ok_u} dot={ok_d} iters={iters}/{ref['iters']} x_equal={ok_x} rel={rel:.2e}"
         print(line, flush=True)
         if not (ok_g and ok_u and ok_d and ok_x and ok_i):
             failures.append(line)
