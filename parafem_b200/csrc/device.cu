@@ -280,10 +280,10 @@ int launch_matvec_sym_t(pf_handle h, const double *pvec, const State *st) {
   return 0;
 }
 
-template <int NOD, bool GATHER, int GEOM>
+template <int NOD, bool GATHER, int GEOM, int UNR = 2>
 int launch_mf_t(pf_handle h, const double *pvec, const State *st) {
   using Cfg = MfCfg<NOD>;
-  auto kern = k_apply_mf<NOD, GATHER, GEOM, kMfWarps>;
+  auto kern = k_apply_mf<NOD, GATHER, GEOM, kMfWarps, UNR>;
   static bool attr_set = false;
   if (!attr_set) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem(kMfWarps)));
@@ -301,6 +301,10 @@ int launch_matvec(pf_handle h, const double *pvec, const State *st) {
   Scope sc(h, K_MATVEC);
   if (h->matrix_free) {
     if (h->mf_mode == 2) {
+      // PF_TUNE: unroll factor of the node-pair loops (default 2; measured in profiles/r01_mf_kernel_history.md)
+      static const int mtune = getenv("PF_TUNE") ? atoi(getenv("PF_TUNE")) : 0;
+      if (h->nod == 20 && GATHER && mtune == 1) return launch_mf_t<20, GATHER, 2, 1>(h, pvec, st);
+      if (h->nod == 20 && GATHER && mtune == 2) return launch_mf_t<20, GATHER, 2, 5>(h, pvec, st);
       if (h->nod == 20) return launch_mf_t<20, GATHER, 2>(h, pvec, st);
       return launch_mf_t<8, GATHER, 2>(h, pvec, st);
     }
@@ -532,8 +536,7 @@ int one_iteration(pf_handle h) {
     h->launches++;
     if (!peer && (rc = combine_scalars(h, 2))) return rc;
     k_pupdate<<<grid_for(h, (n + 1) / 2, 256, 8), 256, 0, h->stream>>>(h->d.p, h->p_ext.p + 1, n, st);
-    k_exit_test<<<1, 1, 0, h->stream>>>(st);
-    h->launches += 2;
+    h->launches++;
   }
   CU(cudaGetLastError());
   return 0;

@@ -668,8 +668,10 @@ k_pcg_update(const double *__restrict__ diag, const double *__restrict__ p, cons
              double *part /*3*nchunks*/, State *st, int single_rank, double *ratio_hist, PeerTable *T) {
   if (*(volatile const int *)&st->done) return;
   __shared__ double sh[8];
+  __shared__ double sh3[2][24];
   __shared__ double sh_loc[4], sh_out[3];
   __shared__ int flag;
+  int nloc = 0;
   const double alpha = st->alpha;
   const long long nchunks = (n + kChunk - 1) / kChunk;
   for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
@@ -690,10 +692,22 @@ k_pcg_update(const double *__restrict__ diag, const double *__restrict__ p, cons
           md = fmax(md, fabs(xn - xo));
         }
     }
-    const double s = block_tree(acc, sh);
-    const double m1 = block_max(ml, sh);
-    const double m2 = block_max(md, sh);
-    if (threadIdx.x == 0) { part[c] = s; part[nchunks + c] = m1; part[2 * nchunks + c] = m2; }
+    // the three block reductions of a chunk share one barrier (double-buffered by chunk parity);
+    // same trees as block_tree / block_max: warp xor-tree, then warps 0..7 in order
+    const double ws = warp_tree_sum(acc), wm1 = warp_tree_max(ml), wm2 = warp_tree_max(md);
+    double *buf = sh3[nloc & 1];
+    if ((threadIdx.x & 31) == 0) {
+      const int w = threadIdx.x >> 5;
+      buf[w] = ws; buf[8 + w] = wm1; buf[16 + w] = wm2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = buf[0], m1 = buf[8], m2 = buf[16];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) { s = s + buf[w]; m1 = fmax(m1, buf[8 + w]); m2 = fmax(m2, buf[16 + w]); }
+      part[c] = s; part[nchunks + c] = m1; part[2 * nchunks + c] = m2;
+    }
+    ++nloc;
   }
   if (last_block(&st->ticket[2], &flag)) {
     const double s = final_sum(part, nchunks, sh);
@@ -712,9 +726,11 @@ k_pcg_update(const double *__restrict__ diag, const double *__restrict__ p, cons
   }
 }
 
-// p = d + p*beta (p121.f90:102), then the exit test of p121.f90:103
+// p = d + p*beta (p121.f90:102), then the exit test of p121.f90:103.  `done` is raised by the last
+// block to finish, so no block of this kernel can observe it early and every later kernel sees it.
 __global__ void k_pupdate(const double *__restrict__ d, double *__restrict__ p, long long n, State *st) {
   if (*(volatile const int *)&st->done) return;
+  __shared__ int flag;
   const double beta = st->beta;
   long long i = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
   const long long stride = 2 * (long long)gridDim.x * blockDim.x;
@@ -722,11 +738,9 @@ __global__ void k_pupdate(const double *__restrict__ d, double *__restrict__ p, 
     p[i] = d[i] + p[i] * beta;
     if (i + 1 < n) p[i + 1] = d[i + 1] + p[i + 1] * beta;
   }
-}
-// separate 1-thread launch after k_pupdate so no block can observe `done` early
-__global__ void k_exit_test(State *st) {
-  if (st->done) return;
-  if (st->converged || st->iters == st->limit) st->done = 1;
+  if (last_block(&st->ticket[3], &flag) && threadIdx.x == 0) {
+    if (st->converged || st->iters == st->limit) st->done = 1;
+  }
 }
 
 // diag = 1/diag (+ penalty on fixed equations first; p123.f90:120-125, p121.f90:86)
@@ -967,7 +981,7 @@ __device__ __forceinline__ void mf_point_mid(const double *H, const double *inv,
 // from a 3.8 KB shared-memory table as warp-uniform (broadcast) 128-bit loads; the factors of the
 // next Gauss point are loaded while the current one is finished.  The Gauss points are accumulated
 // four at a time, so a row of right-hand sides is read from shared memory only twice.
-template <int NOD, bool GATHER, int GEOM, int WARPS>
+template <int NOD, bool GATHER, int GEOM, int WARPS, int UNR = 2>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, const double *__restrict__ pvec,
            double *__restrict__ utemp, long long nels, const State *st, double *geom) {
@@ -1050,7 +1064,7 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
           for (int g = 0; g < 4; ++g)
 #pragma unroll
             for (int z = 0; z < 9; ++z) J[g][z] = 0.0;
-#pragma unroll 2
+#pragma unroll UNR
           for (int t = 0; t < NOD / 2; ++t) {
             // [b*NOD+m]: x of nodes 2t,2t+1 / y / z
             double cx[2], cy[2], cz[2];
@@ -1140,7 +1154,7 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
           for (int g = 0; g < 4; ++g)
 #pragma unroll
             for (int z = 0; z < 9; ++z) H[g][z] = 0.0;
-#pragma unroll 2
+#pragma unroll UNR
           for (int t = 0; t < NOD / 2; ++t) {
             // dofs 6t..6t+5 = (x,y,z) of nodes 2t and 2t+1
             double v[6];
@@ -1168,7 +1182,7 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
         }
         // phase 2: one 24-term chain per dof, Gauss points ascending, b ascending inside
         // (the node loops are NOT fully unrolled: the whole kernel stays within the instruction cache)
-#pragma unroll 2
+#pragma unroll UNR
         for (int t = 0; t < NOD / 2; ++t) {
           double o[6];
 #pragma unroll
