@@ -203,6 +203,7 @@ def main():
     barrier()
     t_dev_setup = time.time() - t0
     fp64_tflops = s.measure_fp64() if args.matrix_free else None
+    hbm_read_gbs = s.measure_hbm_read() if not args.matrix_free else None   # read-only stream ceiling (informational)
     ntot = prob.ntot
     storkm_bytes_pp = prob.nels_pp * (ntot * (ntot + 1) // 2 if args.layout == 1 else ntot * ntot) * 8
 
@@ -358,6 +359,8 @@ def main():
             "roofline": ({"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                           "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": traffic,
                           "kernel": ("k_matvec_sym" if args.layout == 1 else "k_matvec") + " (storkm stream; gather fused)", "peak_kind": pk_kind,
+                          "read_only_stream_gbs": hbm_read_gbs,
+                          "frac_of_read_only_stream": (achieved / hbm_read_gbs) if (achieved and hbm_read_gbs) else None,
                           "algorithmic_bytes_per_launch": storkm_bytes_pp, "avg_launch_ms": mv_avg_ms,
                           "launches_timed": int(mv_n)} if not args.matrix_free else
                          mf_roofline(args.matrix_free, m, fp64_tflops)),

@@ -167,6 +167,9 @@ int64_t pf_kernel_launches(pf_handle h); /* all kernel launches since pf_init */
 /* DFMA micro-benchmark on this device: the FP64 roofline denominator of the
  * matrix-free variant ("FP64 peak is not in MEASURED_PEAKS.json").  */
 int pf_measure_fp64(pf_handle h, double *tflops);
+/* Read-only HBM stream through the same bulk-copy ring as the mat-vec, no arithmetic (GB/s):
+ * MEASURED_PEAKS.json's hbm_gbs is a copy (read + write); this is the read-stream ceiling.     */
+int pf_measure_hbm_read(pf_handle h, double *gbs);
 int pf_device_info(pf_handle h, int *sm_count, int64_t *free_bytes, int64_t *total_bytes);
 
 /* ===================================================================== */
@@ -177,6 +180,10 @@ int pf_device_info(pf_handle h, int *sm_count, int64_t *free_bytes, int64_t *tot
  * (gather_scatter.f90:319-339).  numpe is 1-based; *_start 1-based.       */
 void pf_calc_nels_pp(int64_t nels, int npes, int numpe, int64_t *nels_pp, int64_t *iel_start);
 void pf_calc_neq_pp(int64_t neq, int npes, int numpe, int64_t *neq_pp, int64_t *ieq_start);
+/* calc_nels_pp partitioner 2 = read_nels_pp (input.f90:3108-3196): <job>.psize holds
+ * "npes n_1 ... n_npes" (elements pre-sorted by partition, e.g. by METIS).  Any contiguous
+ * element ranges are accepted by pf_setup_mesh; the equation partition stays calc_neq_pp. */
+int pf_read_psize(const char *job, int npes, int numpe, int64_t *nels_pp, int64_t *iel_start);
 
 /* p12meshgen cubes (tools/preprocessing/p12meshgen/p12meshgen.f90:118-236,
  * 658-701; geometry.f90 geometry_20bxz :175-286, geometry_8bxz :70-169,

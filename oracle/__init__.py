@@ -47,6 +47,8 @@ def lib():
         L.orc_pcg.argtypes = [cint, i64, vp, vp, i64, vp, i64, vp, vp, dbl, cint, cint, dbl, cint, vp,
                               C.POINTER(cint), C.POINTER(cint), vp, vp, C.POINTER(dbl), vp, cint, cint, dbl, dbl]
         L.orc_apply_mf.argtypes = [i64, cint, cint, vp, dbl, dbl, vp, vp]
+        L.orc_set_element_partition.argtypes = [vp, cint]
+        L.orc_set_element_partition.restype = None
         L.orc_sample_hex.argtypes = [cint, vp, vp]
         L.orc_shape_der.argtypes = [cint, vp, cint, cint, vp]
         L.orc_set_threads.argtypes = [cint]
@@ -68,6 +70,16 @@ def _i32(a):
 
 def set_threads(n):
     lib().orc_set_threads(int(n))
+
+
+def set_element_partition(counts=None):
+    """Partitioner 2 (read_nels_pp, input.f90:3108-3196): elements per emulated rank from a .psize
+    list instead of calc_nels_pp; None restores partitioner 1.  Applies when npes == len(counts)."""
+    if counts is None:
+        lib().orc_set_element_partition(None, 0)
+    else:
+        c = np.ascontiguousarray(counts, np.int64)
+        lib().orc_set_element_partition(_p(c), len(c))
 
 
 def max_threads():

@@ -499,6 +499,29 @@ typedef struct {
   double **ul;          /* per-rank partial-sum buffers over [lo,hi) */
 } orc_ranks;
 
+/* partitioner 2 (read_nels_pp, input.f90:3108-3196): elements per rank from <job>.psize instead of
+ * calc_nels_pp.  orc_set_element_partition(counts, npes) makes every emulated-rank routine below use
+ * those counts (npes must match; counts == NULL restores partitioner 1). */
+static int64_t g_psize[64];
+static int g_psize_n = 0;
+void orc_set_element_partition(const int64_t *counts, int npes) {
+  g_psize_n = 0;
+  if (!counts || npes < 1 || npes > 64) return;
+  for (int r = 0; r < npes; ++r) g_psize[r] = counts[r];
+  g_psize_n = npes;
+}
+static void element_range(int64_t nels, int npes, int r, int64_t *e0, int64_t *e1) {
+  if (g_psize_n == npes) {
+    int64_t s = 0;
+    for (int q = 0; q < r; ++q) s += g_psize[q];
+    *e0 = s; *e1 = s + g_psize[r];
+    return;
+  }
+  int64_t c, s;
+  orc_partition(nels, npes, r + 1, &c, &s);
+  *e0 = s - 1; *e1 = s - 1 + c;
+}
+
 static orc_ranks *ranks_new(int npes, int ntot, int64_t nels, const int32_t *g_g, int64_t neq) {
   orc_ranks *R = calloc(1, sizeof *R);
   R->npes = npes;
@@ -508,7 +531,7 @@ static orc_ranks *ranks_new(int npes, int ntot, int64_t nels, const int32_t *g_g
   R->ul = calloc(npes, sizeof(double *));
   for (int r = 0; r < npes; ++r) {
     int64_t c, s;
-    orc_partition(nels, npes, r + 1, &c, &s); R->el0[r] = s - 1; R->el1[r] = s - 1 + c;
+    element_range(nels, npes, r, &R->el0[r], &R->el1[r]);
     orc_partition(neq, npes, r + 1, &c, &s);  R->eq0[r] = s - 1; R->eq1[r] = s - 1 + c;
     int64_t lo = neq, hi = 0;
     for (int64_t i = R->el0[r] * ntot; i < R->el1[r] * ntot; ++i)

@@ -67,10 +67,12 @@ SIGNATURES = {
     "pf_get_kernel_ms": (c_int, [vp, c_int, P(c_dbl), P(c_i64)]),
     "pf_kernel_launches": (c_i64, [vp]),
     "pf_measure_fp64": (c_int, [vp, P(c_dbl)]),
+    "pf_measure_hbm_read": (c_int, [vp, P(c_dbl)]),
     "pf_device_info": (c_int, [vp, P(c_int), P(c_i64), P(c_i64)]),
     # B. host helpers
     "pf_calc_nels_pp": (None, [c_i64, c_int, c_int, P(c_i64), P(c_i64)]),
     "pf_calc_neq_pp": (None, [c_i64, c_int, c_int, P(c_i64), P(c_i64)]),
+    "pf_read_psize": (c_int, [C.c_char_p, c_int, c_int, P(c_i64), P(c_i64)]),
     "pf_p121_sizes": (c_int, [c_int, c_int, c_int, c_int, P(c_i64), P(c_i64), P(c_i64)]),
     "pf_p123_sizes": (c_int, [c_int, c_int, c_int, P(c_i64), P(c_i64), P(c_i64)]),
     "pf_cube_elements": (c_int, [c_int, c_int, c_int, c_dbl, c_dbl, c_dbl, c_i64, c_i64, c_int, vp, vp]),

@@ -663,6 +663,44 @@ int pf_measure_fp64(pf_handle h, double *tflops) {
   return 0;
 }
 
+int pf_measure_hbm_read(pf_handle h, double *gbs) {
+  int rc = need_device(h); if (rc) return rc;
+  constexpr int kTile = 28800, kStages = 7;                 // the hex20 tile shape of k_matvec
+  const size_t smem = (size_t)kStages * kTile + kStages * 8;
+  auto kern = k_stream_read<kTile, kStages>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // stream over the element matrices when they are resident (no extra memory), else over a scratch buffer
+  DevBuf<double> scratch;
+  const double *src = h->km.p;
+  size_t bytes = h->km.bytes();
+  if (!src || bytes < ((size_t)1 << 30)) {
+    size_t f = 0, t = 0;
+    CU(cudaMemGetInfo(&f, &t));
+    bytes = std::min<size_t>((size_t)8 << 30, f / 2);
+    CU(scratch.alloc(bytes / 8));
+    CU(cudaMemsetAsync(scratch.p, 0, bytes, h->stream));
+    src = scratch.p;
+  }
+  const long long ntiles = (long long)(bytes / kTile);
+  DevBuf<double> out; CU(out.alloc(1));
+  cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CU(cudaEventRecord(e0, h->stream));
+    kern<<<h->sm_count, kStages * 32, smem, h->stream>>>(src, ntiles, out.p);
+    CU(cudaEventRecord(e1, h->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f; CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double g = (double)ntiles * kTile / (ms * 1e-3) / 1e9;
+    if (rep > 0 && g > best) best = g;
+  }
+  h->launches += 4;
+  CU(cudaGetLastError());
+  cudaEventDestroy(e0); cudaEventDestroy(e1); out.release(); scratch.release();
+  *gbs = best;
+  return 0;
+}
+
 int pf_set_profile(pf_handle h, int on) { if (!h) return 1; h->profile = on != 0; return 0; }
 int pf_reset_profile(pf_handle h) {
   if (!h) return 1;

@@ -162,6 +162,25 @@ void pf_calc_neq_pp(int64_t neq, int npes, int numpe, int64_t *neq_pp, int64_t *
   even_split(neq, npes, numpe, neq_pp, ieq_start);
 }
 
+// calc_nels_pp partitioner 2 = read_nels_pp (input.f90:3108-3196): "<npes> n_1 ... n_npes"
+int pf_read_psize(const char *job, int npes, int numpe, int64_t *nels_pp, int64_t *iel_start) {
+  if (!job || npes < 1 || numpe < 1 || numpe > npes) return 2;
+  FILE *f = fopen((std::string(job) + ".psize").c_str(), "r");
+  if (!f) return 5;
+  long long p = 0;
+  if (fscanf(f, "%lld", &p) != 1 || p != npes) { fclose(f); return 6; }   // "Number of partitions is different ..."
+  int64_t start = 1, mine = -1;
+  for (int r = 1; r <= npes; ++r) {
+    long long c = 0;
+    if (fscanf(f, "%lld", &c) != 1 || c < 0) { fclose(f); return 7; }
+    if (r < numpe) start += c;
+    if (r == numpe) mine = c;
+  }
+  fclose(f);
+  *nels_pp = mine; *iel_start = start;
+  return 0;
+}
+
 int pf_p121_sizes(int nxe, int nye, int nze, int nod, int64_t *nn, int64_t *nr, int64_t *loaded) {
   int64_t X = nxe, Y = nye, Z = nze, nle = nxe / 5;
   if (nod == 20) {

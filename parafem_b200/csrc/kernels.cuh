@@ -1265,6 +1265,40 @@ __global__ void k_unpack_lower(const double *__restrict__ packed, double *__rest
   }
 }
 
+// Read-only HBM stream probe: the k_matvec data path (persistent CTAs, ring of 1-D bulk copies, evict-first)
+// without the arithmetic.  MEASURED_PEAKS.json's figure is a COPY (read + write); a pure read stream
+// can run faster, so this is the ceiling the storkm stream should be compared with as well.
+template <int TILE_BYTES, int STAGES>
+__global__ void __launch_bounds__(STAGES * 32, 1)
+k_stream_read(const double *__restrict__ src, long long ntiles, double *out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *tiles = reinterpret_cast<double *>(smem_raw);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * TILE_BYTES);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t0 = ntiles * blockIdx.x / gridDim.x, t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
+  double *tile = tiles + (size_t)w * (TILE_BYTES / 8);
+  const uint32_t bar = smem_u32(&bars[w]), tile_s = smem_u32(tile);
+  uint64_t policy = 0;
+  if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); policy = policy_evict_first(); }
+  __syncwarp();
+  long long t = t0 + w;
+  if (t < t1 && lane == 0) { mbar_expect_tx(bar, TILE_BYTES); bulk_g2s(tile_s, src + t * (TILE_BYTES / 8), TILE_BYTES, bar, policy); }
+  uint32_t phase = 0;
+  double acc = 0.0;
+  for (; t < t1; t += STAGES) {
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    acc += tile[lane];
+    __syncwarp();
+    if (t + STAGES < t1 && lane == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(bar, TILE_BYTES);
+      bulk_g2s(tile_s, src + (t + STAGES) * (TILE_BYTES / 8), TILE_BYTES, bar, policy);
+    }
+  }
+  if (acc == 12345.678) out[0] = acc;
+}
+
 // DFMA micro-benchmark: the FP64 denominator for the matrix-free variant ("of measured").
 // 8 independent fma chains per thread, `iters` rounds; 2 flop per fma.
 __global__ void k_fp64_peak(double *out, int iters, double a, double b) {

@@ -12,10 +12,24 @@ import numpy as np
 from ._lib import DeckInfo, PfError, c_i64, check, f64, i32, lib, ptr
 
 
-def calc_nels_pp(nels, npes, numpe):
-    """calc_nels_pp, partitioner 1 (gather_scatter.f90:217-238) -> (nels_pp, iel_start)."""
+def calc_nels_pp(nels, npes, numpe, psize=None):
+    """calc_nels_pp (gather_scatter.f90:146-257) -> (nels_pp, iel_start).  Partitioner 1 (internal,
+    :217-238) unless ``psize`` -- the element counts per rank of a .psize file (partitioner 2,
+    read_nels_pp input.f90:3108-3196) -- is given."""
+    if psize is not None:
+        psize = [int(c) for c in psize]
+        if len(psize) != npes or sum(psize) != nels or min(psize) < 1:
+            raise PfError(f"psize {psize} does not partition {nels} elements over {npes} ranks")
+        return psize[numpe - 1], 1 + sum(psize[:numpe - 1])
     a, b = c_i64(), c_i64()
     lib().pf_calc_nels_pp(nels, npes, numpe, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def read_psize(job, npes, numpe):
+    """read_nels_pp (input.f90:3108-3196): this rank's (nels_pp, iel_start) from <job>.psize."""
+    a, b = c_i64(), c_i64()
+    check(lib().pf_read_psize(job.encode(), npes, numpe, C.byref(a), C.byref(b)), what="pf_read_psize")
     return a.value, b.value
 
 
@@ -77,7 +91,7 @@ def _steer(nn, nodof, rest, g_num_pp, nod):
 
 
 def cube_p121(nxe, nye, nze, nod=20, aa=None, bb=None, cc=None, e=100.0, v=0.3, tol=1e-5,
-              limit=2000, nip=8, npes=1, numpe=1, round_mode=0, distort=0.0, seed=12345):
+              limit=2000, nip=8, npes=1, numpe=1, round_mode=0, distort=0.0, seed=12345, psize=None):
     """In-memory p12meshgen cube for p121 (p12meshgen.f90:118-236): this rank's share.
 
     ``distort`` > 0 perturbs interior node coordinates by up to distort*h (uniform,
@@ -91,7 +105,7 @@ def cube_p121(nxe, nye, nze, nod=20, aa=None, bb=None, cc=None, e=100.0, v=0.3, 
     check(L.pf_p121_sizes(nxe, nye, nze, nod, C.byref(nn), C.byref(nr), C.byref(loaded)), what="pf_p121_sizes")
     nn, nr, loaded = nn.value, nr.value, loaded.value
     nels = nxe * nye * nze
-    nels_pp, iel_start = calc_nels_pp(nels, npes, numpe)
+    nels_pp, iel_start = calc_nels_pp(nels, npes, numpe, psize)
     g_num = np.empty((nels_pp, nod), np.int32)
     g_coord = np.empty((nels_pp, 3, nod), np.float64)
     check(L.pf_cube_elements(nxe, nze, nod, aa, bb, cc, iel_start, nels_pp, round_mode, ptr(g_num), ptr(g_coord)),
@@ -123,7 +137,7 @@ def _distort(g_coord, g_num, rest, nn, amp, seed):
 
 
 def cube_p123(nxe, nye, nze, aa=None, bb=None, cc=None, kx=2.0, ky=2.0, kz=2.0, tol=1e-5, limit=500,
-              nip=8, npes=1, numpe=1, round_mode=0, source=10.0, fixed=False, fixed_value=100.0):
+              nip=8, npes=1, numpe=1, round_mode=0, source=10.0, fixed=False, fixed_value=100.0, psize=None):
     """In-memory p12meshgen box for p123 (p12meshgen.f90:658-701)."""
     aa = 1.0 / nxe if aa is None else aa
     bb = 1.0 / nye if bb is None else bb
@@ -133,7 +147,7 @@ def cube_p123(nxe, nye, nze, aa=None, bb=None, cc=None, kx=2.0, ky=2.0, kz=2.0, 
     check(L.pf_p123_sizes(nxe, nye, nze, C.byref(nn), C.byref(nr), C.byref(nres)), what="pf_p123_sizes")
     nn, nr, nres = nn.value, nr.value, nres.value
     nels = nxe * nye * nze
-    nels_pp, iel_start = calc_nels_pp(nels, npes, numpe)
+    nels_pp, iel_start = calc_nels_pp(nels, npes, numpe, psize)
     g_num = np.empty((nels_pp, 8), np.int32)
     g_coord = np.empty((nels_pp, 3, 8), np.float64)
     check(L.pf_cube_elements(nxe, nze, 8, aa, bb, cc, iel_start, nels_pp, round_mode, ptr(g_num), ptr(g_coord)),
@@ -173,9 +187,12 @@ def read_deck_p121(job, npes=1, numpe=1):
     check(L.pf_read_d(job.encode(), nn, nels, nod, ptr(g_coord), ptr(g_num)), what="pf_read_d")
     if info.meshgen == 2:
         check(L.pf_abaqus2sg(nod, nels, ptr(g_num)), what="pf_abaqus2sg")
-    if info.partitioner != 1:
-        raise PfError("only partitioner 1 (internal) decks are supported")
-    nels_pp, iel_start = calc_nels_pp(nels, npes, numpe)
+    if info.partitioner == 2:      # external partition: <job>.psize, elements pre-sorted by rank
+        nels_pp, iel_start = read_psize(job, npes, numpe)
+    elif info.partitioner == 1:
+        nels_pp, iel_start = calc_nels_pp(nels, npes, numpe)
+    else:
+        raise PfError("partitioner must be 1 (internal) or 2 (.psize)")
     g_num_pp = np.ascontiguousarray(g_num[iel_start - 1:iel_start - 1 + nels_pp])
     g_coord_pp = np.empty((nels_pp, 3, nod), np.float64)
     check(L.pf_coords_pp(nod, nels_pp, ptr(g_num_pp), ptr(g_coord), ptr(g_coord_pp)), what="pf_coords_pp")

@@ -79,6 +79,12 @@ class Solver:
         self._ck(lib().pf_measure_fp64(self._h, C.byref(t)), "pf_measure_fp64")
         return t.value
 
+    def measure_hbm_read(self):
+        """GB/s of a read-only stream through the mat-vec's bulk-copy ring (no arithmetic)."""
+        t = C.c_double()
+        self._ck(lib().pf_measure_hbm_read(self._h, C.byref(t)), "pf_measure_hbm_read")
+        return t.value
+
     def get_storkm(self, iel0=0, n=None):
         n = self.prob.nels_pp - iel0 if n is None else n
         nt = self.prob.ntot

@@ -16,7 +16,18 @@ import oracle  # noqa: E402
 from parafem_b200 import host, solver  # noqa: E402
 
 
+def uneven(nels, npes):
+    """A deliberately lopsided external partition (what a .psize file would hold)."""
+    w = np.array([3 + (5 * r) % 7 for r in range(npes)], float)
+    c = np.maximum(1, np.floor(nels * w / w.sum()).astype(int))
+    c[-1] += nels - c.sum()
+    return [int(v) for v in c]
+
+
 def problem(name, npes, numpe):
+    if name == "hex20_psize":   # partitioner 2 (read_nels_pp, input.f90:3108-3196)
+        ps = uneven(6 * 7 * 5, npes) if npes > 1 else None
+        return host.cube_p121(6, 7, 5, 20, aa=1., bb=1., cc=1., limit=500, npes=npes, numpe=numpe, psize=ps)
     if name == "hex20":
         return host.cube_p121(6, 7, 5, 20, aa=1., bb=1., cc=1., limit=500, npes=npes, numpe=numpe)
     if name == "hex20_thin":   # element and equation cuts badly misaligned -> +-2 neighbours
@@ -43,6 +54,7 @@ def main():
         p = problem(name, world, rank + 1)
         full = problem(name, 1, 1)
         r0 = p.r_pp.copy()
+        oracle.set_element_partition(uneven(full.nels, world) if name == "hex20_psize" else None)
         mf_mode = int(variant[2:]) if variant.startswith("mf") else 0
         solver.setup_problem(s, p, matrix_free=mf_mode, layout=1 if variant == "sym" else 0)
         lo = p.ieq_start - 1

@@ -183,3 +183,24 @@ def test_nodal_values_and_node_partition():
         assert b.value == nxt
         nxt += a.value
     assert nxt == p.nn + 1
+
+
+def test_psize_partitioner_2(tmp_path):
+    """calc_nels_pp partitioner 2 = read_nels_pp (input.f90:3108-3196): '<npes> n_1 ... n_npes'."""
+    from parafem_b200 import PfError
+    job = str(tmp_path / "ext")
+    open(job + ".psize", "w").write("3   70 20\n 30\n")             # list-directed: tokens may span lines
+    assert [host.read_psize(job, 3, r) for r in (1, 2, 3)] == [(70, 1), (20, 71), (30, 91)]
+    with pytest.raises(PfError):
+        host.read_psize(job, 2, 1)                                     # "Number of partitions is different ..."
+    with pytest.raises(PfError):
+        host.read_psize(str(tmp_path / "missing"), 3, 1)
+    # the slices of an unevenly partitioned cube tile the serial cube, and the equation partition
+    # stays calc_neq_pp whatever the element partition is
+    full = host.cube_p121(5, 6, 4, 20, aa=1., bb=1., cc=1.)
+    parts = [host.cube_p121(5, 6, 4, 20, aa=1., bb=1., cc=1., npes=3, numpe=r, psize=[70, 20, 30]) for r in (1, 2, 3)]
+    assert np.array_equal(np.concatenate([q.g_g_pp for q in parts]), full.g_g_pp)
+    assert np.array_equal(np.concatenate([q.g_coord_pp for q in parts]), full.g_coord_pp)
+    assert [(q.neq_pp, q.ieq_start) for q in parts] == [host.calc_neq_pp(full.neq, 3, r) for r in (1, 2, 3)]
+    with pytest.raises(PfError):
+        host.calc_nels_pp(120, 3, 1, psize=[70, 20, 31])

@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, psize=None):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -30,7 +30,8 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         full = host.cube_p121(5, 6, 4, 20, aa=1., bb=1., cc=1.)
-        p = host.cube_p121(5, 6, 4, 20, aa=1., bb=1., cc=1., npes=world, numpe=rank + 1)
+        p = host.cube_p121(5, 6, 4, 20, aa=1., bb=1., cc=1., npes=world, numpe=rank + 1, psize=psize)
+        oracle.set_element_partition(psize)        # partitioner 2: the oracle emulates the same uneven ranks
         ggl, halo, get_cnt = host.make_ggl(p)
         # counts matrix, then the wanted equation lists (pf_setup_mesh does this over NCCL)
         cnts = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
@@ -110,13 +111,15 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_halo_protocol_over_gloo(world):
+@pytest.mark.parametrize("world,psize", [(2, None), (3, None), (2, [85, 35]), (3, [70, 14, 36])])
+def test_halo_protocol_over_gloo(world, psize):
+    """psize: external element partition (.psize, partitioner 2) -- element and equation cuts far apart,
+    so ranks exchange with non-adjacent ranks too."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, psize)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in range(world)]
@@ -125,4 +128,6 @@ def test_halo_protocol_over_gloo(world):
         assert p.exitcode == 0
     for rank, okg, oks, okd, nh, npu in sorted(res):
         assert okg and oks and okd, (rank, okg, oks, okd)
-        assert nh > 0 and npu > 0
+        assert psize is not None or (nh > 0 and npu > 0)
+    # (with a lopsided external partition a rank may own every equation its elements touch)
+    assert sum(r[4] for r in res) > 0 and sum(r[4] for r in res) == sum(r[5] for r in res)
