@@ -865,27 +865,46 @@ k_form_km_elastic(const double *__restrict__ g_coord, double *__restrict__ km, l
         s_btd[k * NTOT + i] = s;
       }
       __syncthreads();
+      if (diag_only) {
+        // matrix-free setup: only km(i,i) is needed -- same expression, 1/NTOT of the work
 #pragma unroll
-      for (int n = 0; n < PER; ++n) {
-        const int idx = threadIdx.x + n * THREADS;
-        if (idx < NENT) {
-          const int j = idx / NTOT, i = idx - j * NTOT;
-          double s = 0.0;
+        for (int m = 0; m < (NTOT + THREADS - 1) / THREADS; ++m) {
+          const int i = threadIdx.x + m * THREADS;
+          if (i < NTOT) {
+            double s = 0.0;
 #pragma unroll
-          for (int k = 0; k < 6; ++k) s = s + s_btd[k * NTOT + i] * s_bee[j * 6 + k];
-          acc[n] = acc[n] + s * det * wt;
+            for (int k = 0; k < 6; ++k) s = s + s_btd[k * NTOT + i] * s_bee[i * 6 + k];
+            acc[m] = acc[m] + s * det * wt;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int n = 0; n < PER; ++n) {
+          const int idx = threadIdx.x + n * THREADS;
+          if (idx < NENT) {
+            const int j = idx / NTOT, i = idx - j * NTOT;
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) s = s + s_btd[k * NTOT + i] * s_bee[j * 6 + k];
+            acc[n] = acc[n] + s * det * wt;
+          }
         }
       }
       __syncthreads();
+    }
+    if (diag_only) {
+#pragma unroll
+      for (int m = 0; m < (NTOT + THREADS - 1) / THREADS; ++m) {
+        const int i = threadIdx.x + m * THREADS;
+        if (i < NTOT) diag_only[e * (long long)NTOT + i] = acc[m];
+      }
+      continue;
     }
 #pragma unroll
     for (int n = 0; n < PER; ++n) {
       const int idx = threadIdx.x + n * THREADS;
       if (idx < NENT) {
-        if (diag_only) {
-          const int j = idx / NTOT, i = idx - j * NTOT;
-          if (i == j) diag_only[e * (long long)NTOT + i] = acc[n];
-        } else if (packed) {
+        if (packed) {
           const int j = idx / NTOT, i = idx - j * NTOT;
           if (i >= j) km[e * (long long)SymCfg<NTOT>::kPacked + SymCfg<NTOT>::coloff(j) + (i - j)] = acc[n];
         } else {
