@@ -296,14 +296,26 @@ __global__ void k_scatter(const unsigned int *__restrict__ csr_ptr, const unsign
   for (; s < nslots; s += stride) {
     const unsigned int a = csr_ptr[s], b = csr_ptr[s + 1];
     double acc = 0.0;
-    for (unsigned int k = a; k < b; ++k) {
-      const unsigned int pos = csr_pos[k];
-      if (DIAG) {
+    if (DIAG) {
+      for (unsigned int k = a; k < b; ++k) {
+        const unsigned int pos = csr_pos[k];
         const unsigned int e = pos / ntot, d = pos - e * ntot;
         if (packed) acc = acc + src[(size_t)e * (ntot * (ntot + 1) / 2) + (size_t)d * ntot - d * (d - 1) / 2];
         else acc = acc + src[(size_t)e * ntot * ntot + (size_t)d * ntot + d];
-      } else {
-        acc = acc + src[pos];
+      }
+    } else {
+      // kBatch contributions in flight at a time (index loads, then value loads), added in list order
+      constexpr int kBatch = 4;   // measured: 4 -> hex8 200^3 0.77 -> 0.58 ms, hex20 0.34 -> 0.32; 8 -> no gain on hex8
+      for (unsigned int k = a; k < b; k += kBatch) {
+        unsigned int pos[kBatch];
+        double v[kBatch];
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) pos[i] = (k + i < b) ? __ldg(csr_pos + k + i) : 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) v[i] = (pos[i] != 0xffffffffu) ? src[pos[i]] : 0.0;
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i)
+          if (pos[i] != 0xffffffffu) acc = acc + v[i];
       }
     }
     u_ext[s] = acc;
