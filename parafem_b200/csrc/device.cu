@@ -345,7 +345,11 @@ int launch_matvec(pf_handle h, const double *pvec, const State *st) {
 
 int launch_scatter(pf_handle h, const State *st, bool diag, double *dst) {
   Scope sc(h, K_SCATTER);
-  const int grid = grid_for(h, h->nslots, 256, 16);
+  // grid-stride kernel: exactly one resident wave (k_scatter needs 30 registers: 8 blocks of 256 per SM)
+  static int per_sm = 0;
+  if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scatter<false>, 256, 0) != cudaSuccess || per_sm < 1))
+    per_sm = 8;
+  const int grid = grid_for(h, h->nslots, 256, per_sm);
   if (diag) k_scatter<true><<<grid, 256, 0, h->stream>>>(h->csr_ptr.p, h->csr_pos.p, h->km.p, dst, (long long)h->nslots, h->ntot, st, h->km_layout);
   else k_scatter<false><<<grid, 256, 0, h->stream>>>(h->csr_ptr.p, h->csr_pos.p, h->utemp.p, dst, (long long)h->nslots, h->ntot, st);
   h->launches++;
@@ -499,9 +503,16 @@ int combine_scalars(pf_handle h, int mode) {
   return 0;
 }
 
-int vec_grid(pf_handle h) {
+// grid of a chunk-looping reduction kernel: exactly the blocks that are resident at once (a second
+// partial wave would leave a tail); the reduction tree does not depend on the grid size
+template <class K>
+int vec_grid(pf_handle h, K kernel) {
+  static int per_sm = 0;   // one value per kernel (template instantiation); all devices of a box are the same part
+  if (per_sm == 0 &&
+      (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRedThreads, 0) != cudaSuccess || per_sm < 1))
+    per_sm = 4;
   const int64_t nchunks = (h->neq_pp + kChunk - 1) / kChunk;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(nchunks, (int64_t)h->sm_count * 8));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(nchunks, (int64_t)h->sm_count * per_sm));
 }
 
 // u_ext = A p_ext over this rank's elements + halo exchanges (gather, mat-vec, scatter)
@@ -528,10 +539,10 @@ int one_iteration(pf_handle h) {
   if ((rc = apply_operator(h, st, peer))) return rc;
   {
     Scope sc(h, K_VECTOR);
-    k_dot<<<vec_grid(h), kRedThreads, 0, h->stream>>>(h->p_ext.p + 1, h->u_ext.p + 1, n, h->part.p, st, single, 1, T);
+    k_dot<<<vec_grid(h, k_dot), kRedThreads, 0, h->stream>>>(h->p_ext.p + 1, h->u_ext.p + 1, n, h->part.p, st, single, 1, T);
     h->launches++;
     if (!peer && (rc = combine_scalars(h, 1))) return rc;
-    k_pcg_update<<<vec_grid(h), kRedThreads, 0, h->stream>>>(h->diag_ext.p + 1, h->p_ext.p + 1, h->u_ext.p + 1, h->x.p, h->r.p,
+    k_pcg_update<<<vec_grid(h, k_pcg_update), kRedThreads, 0, h->stream>>>(h->diag_ext.p + 1, h->p_ext.p + 1, h->u_ext.p + 1, h->x.p, h->r.p,
                                                               h->d.p, n, h->part.p, st, single, h->ratio_hist.p, T);
     h->launches++;
     if (!peer && (rc = combine_scalars(h, 2))) return rc;
@@ -1053,7 +1064,7 @@ int pf_pcg_run(pf_handle h, double tol, int limit, int *iters, int *converged, d
   init.tol = tol; init.limit = limit;
   CU(cudaMemcpyAsync(h->state.p, &init, sizeof init, cudaMemcpyHostToDevice, h->stream));
   // d = M^-1 r, p = d, x = 0 (p121.f90:87; p123.f90:132)
-  k_pcg_init<<<vec_grid(h), kRedThreads, 0, h->stream>>>(h->diag_ext.p + 1, h->r.p, h->d.p, h->p_ext.p + 1, h->x.p,
+  k_pcg_init<<<vec_grid(h, k_pcg_init), kRedThreads, 0, h->stream>>>(h->diag_ext.p + 1, h->r.p, h->d.p, h->p_ext.p + 1, h->x.p,
                                                           (long long)h->neq_pp, h->part.p, h->state.p, h->nranks == 1,
                                                           (h->peer_ok && h->use_peer) ? h->ptab.p : nullptr);
   h->launches++;
@@ -1179,7 +1190,7 @@ int pf_dot(pf_handle h, const double *a_pp, const double *b_pp, double *result) 
   // p_ext / u_ext double as staging for the two operands
   if ((rc = upload_owned(h, h->p_ext.p, a_pp))) return rc;
   if ((rc = upload_owned(h, h->u_ext.p, b_pp))) return rc;
-  k_dot<<<vec_grid(h), kRedThreads, 0, h->stream>>>(h->p_ext.p + 1, h->u_ext.p + 1, (long long)h->neq_pp, h->part.p, h->state.p,
+  k_dot<<<vec_grid(h, k_dot), kRedThreads, 0, h->stream>>>(h->p_ext.p + 1, h->u_ext.p + 1, (long long)h->neq_pp, h->part.p, h->state.p,
                                                      h->nranks == 1, -1, nullptr);
   h->launches++;
   CU(cudaGetLastError());
