@@ -55,6 +55,20 @@ MODULE parafem_gpu
       IMPORT; TYPE(c_ptr),VALUE :: h; REAL(c_double),VALUE :: kx,ky,kz
     END FUNCTION
 
+    ! p124 (transient conduction, theta method): storka_pp/storkb_pp of p124.f90:81-95 on the device,
+    ! then per time step one call replacing p124.f90:143-218
+    INTEGER(c_int) FUNCTION pf_form_k_transient(h,kx,ky,kz,rho,cp,theta,dtim) BIND(C,name='pf_form_k_transient')
+      IMPORT; TYPE(c_ptr),VALUE :: h; REAL(c_double),VALUE :: kx,ky,kz,rho,cp,theta,dtim
+    END FUNCTION
+    INTEGER(c_int) FUNCTION pf_transient_start(h,val0,val_f_pp) BIND(C,name='pf_transient_start')
+      IMPORT; TYPE(c_ptr),VALUE :: h; REAL(c_double),VALUE :: val0; REAL(c_double) :: val_f_pp(*)
+    END FUNCTION
+    INTEGER(c_int) FUNCTION pf_transient_step(h,loads_pp,tol,limit,iters,converged,elapsed_ms) &
+        BIND(C,name='pf_transient_step')
+      IMPORT; TYPE(c_ptr),VALUE :: h; REAL(c_double) :: loads_pp(*); REAL(c_double),VALUE :: tol
+      INTEGER(c_int),VALUE :: limit; INTEGER(c_int) :: iters,converged; REAL(c_double) :: elapsed_ms
+    END FUNCTION
+
     ! alternative: upload a host storkm_pp (xx3.f90:440-452)
     INTEGER(c_int) FUNCTION pf_set_storkm(h,storkm_pp) BIND(C,name='pf_set_storkm')
       IMPORT; TYPE(c_ptr),VALUE :: h; REAL(c_double) :: storkm_pp(*)

@@ -132,6 +132,29 @@ int pf_pcg_get_x(pf_handle h, double *xnew_pp);
 /* checon_par ratio max|xnew-x|/max|xnew| of every iteration of the last run */
 int pf_get_ratio_history(pf_handle h, double *out, int maxn, int *n);
 
+/* --- transient conduction: program p124 ---------------
+ * Same three kernels as p123, two element-matrix sets and one PCG solve per
+ * time step (implicit theta method), everything resident on the device.
+ * pf_form_k_transient: elements_3/gauss_pts of p124.f90:81-95 for 8-node bricks,
+ *   kc += MATMUL(MATMUL(TRANSPOSE(deriv),kay),deriv)*det*w, pm += fun fun^T det*w*rho*cp,
+ *   storka_pp = pm + kc*theta*dtim (the PCG matrix: pf_get_storkm, pf_build_precon,
+ *   pf_apply see it), storkb_pp = pm - kc*(1-theta)*dtim (pf_get_storkb).
+ *   One material (p12meshgen forces np_types = 1, p12meshgen.f90:837).
+ * pf_build_precon as for p123 (no_f_pp = fixed freedoms, penalty 1e20; p124.f90:97-124).
+ * pf_transient_start: x_pp = val0, x_pp(l) = val_f(k) on the fixed freedoms
+ *   (p124.f90:168-173); val_f_pp (nfixed_pp, order of no_f_pp) may be NULL when none.
+ * pf_transient_step: one pass of the timesteps loop (p124.f90:139-218): right-hand side
+ *   loads_pp + storkb*xnew (storka*x on the first step after pf_transient_start), fixed-freedom
+ *   rows as the reference writes them, then PCG from x = 0.  loads_pp (host, neq_pp) =
+ *   val*dtim at the loaded freedoms, NULL = none.  xnew_pp stays on the device
+ *   (pf_pcg_get_x reads it); elapsed_ms = the whole step on the solver stream.       */
+int pf_form_k_transient(pf_handle h, double kx, double ky, double kz, double rho, double cp,
+                        double theta, double dtim);
+int pf_get_storkb(pf_handle h, int64_t iel0, int64_t n, double *out);
+int pf_transient_start(pf_handle h, double val0, const double *val_f_pp);
+int pf_transient_step(pf_handle h, const double *loads_pp, double tol, int limit, int *iters,
+                      int *converged, double *elapsed_ms);
+
 /* --- fine-grained entry points (kernel-level parity tests) --------------
  * Same argument meaning as the reference routines they replace:
  *   pf_gather  = gather(p_pp,pmul_pp)            gather_scatter.f90:547-688

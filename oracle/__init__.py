@@ -52,6 +52,9 @@ def lib():
         L.orc_sample_hex.argtypes = [cint, vp, vp]
         L.orc_shape_der.argtypes = [cint, vp, cint, cint, vp]
         L.orc_set_threads.argtypes = [cint]
+        L.orc_shape_fun.argtypes = [cint, vp, cint, cint, vp]
+        L.orc_form_k_transient.argtypes = [i64, cint, cint, vp, dbl, dbl, dbl, dbl, dbl, dbl, dbl, vp, vp, vp, vp]
+        L.orc_apply.argtypes = [cint, i64, vp, vp, i64, cint, vp, vp]
         _lib = L
     return _lib
 
@@ -184,7 +187,7 @@ def pcg(storkm, g_g, neq, r, tol, limit, npes=1, red_mode=0, no_f=None, val_f=No
     nels, ntot = g.shape
     nfixed = 0 if no_f is None else len(no_f)
     no_f = _i32(no_f) if nfixed else None
-    val_f = _f64(val_f) if nfixed else None
+    val_f = _f64(val_f) if (nfixed and val_f is not None) else None
     x = np.empty(neq)
     diag = np.empty(neq)
     ratio = np.zeros(limit)
@@ -197,3 +200,59 @@ def pcg(storkm, g_g, neq, r, tol, limit, npes=1, red_mode=0, no_f=None, val_f=No
     assert rc == 0
     return dict(x=x, iters=it.value, converged=bool(conv.value), ratio=ratio[:it.value], diag=diag,
                 seconds=secs.value)
+
+
+def form_k_transient(g_coord_pp, nip, kx, ky, kz, rho, cp, theta, dtim, raw=False):
+    """p124.f90:81-95: (storka, storkb) for 8-node bricks; raw=True also returns (kc, pm)."""
+    g = _f64(g_coord_pp)
+    nels = g.shape[0]
+    a, b = np.empty((nels, 8, 8)), np.empty((nels, 8, 8))
+    kc = np.empty((nels, 8, 8)) if raw else None
+    pm = np.empty((nels, 8, 8)) if raw else None
+    rc = lib().orc_form_k_transient(nels, 8, nip, _p(g), kx, ky, kz, rho, cp, theta, dtim, _p(a), _p(b), _p(kc), _p(pm))
+    assert rc == 0
+    return (a, b, kc, pm) if raw else (a, b)
+
+
+def apply(storkm, g_g, neq, x, npes=1):
+    """u = scatter(MATMUL(storkm, gather(x))) over npes emulated ranks."""
+    k, g = _f64(storkm), _i32(g_g)
+    u = np.zeros(neq)
+    lib().orc_apply(g.shape[1], g.shape[0], _p(g), _p(k), neq, npes, _p(_f64(x)), _p(u))
+    return u
+
+
+def p124(storka, storkb, g_g, neq, val0, nstep, tol, limit, npes=1, red_mode=0, loads=None, keep=(),
+         no_f=None, val_f=None, penalty=1e20):
+    """The time-stepping loop of p124.f90:139-232: per step the right-hand side loads + B*x (A*x0 on the
+    first step), then PCG from x = 0 on storka.  `loads` = val*dtim at the loaded freedoms (neq) or None;
+    no_f / val_f = fixed freedoms (global equation numbers, values), handled line by line as the reference
+    writes them (:155-160, :170-173, :193-199, :209-212).  Returns dict(iters[nstep], x (last), fields
+    {step: x} for the steps listed in `keep` (0 = the initial field))."""
+    nfix = 0 if no_f is None else len(no_f)
+    if nfix:
+        no_f, val_f = _i32(no_f), _f64(val_f)
+        ntot = storka.shape[1]
+        diag_tmp = np.ascontiguousarray(storka[:, np.arange(ntot), np.arange(ntot)])
+        store = scatter(g_g, diag_tmp, neq, npes)[no_f - 1] + penalty
+    x = np.full(neq, float(val0))
+    if nfix:
+        x[no_f - 1] = val_f
+    fields = {0: x.copy()} if 0 in keep else {}
+    iters, conv = [], []
+    for j in range(1, nstep + 1):
+        rhs = np.zeros(neq) if loads is None else _f64(loads).copy()
+        u = apply(storka if j == 1 else storkb, g_g, neq, x, npes)
+        if nfix and j != 1:
+            u[no_f - 1] = store * val_f
+        rhs = rhs + u
+        if nfix:
+            rhs[no_f - 1] = rhs[no_f - 1] - store * val_f
+        res = pcg(storka, g_g, neq, rhs, tol, limit, npes=npes, red_mode=red_mode, no_f=no_f if nfix else None,
+                  val_f=None, penalty=penalty)
+        x = res["x"]
+        iters.append(res["iters"])
+        conv.append(res["converged"])
+        if j in keep:
+            fields[j] = x.copy()
+    return dict(iters=iters, converged=conv, x=x, fields=fields)

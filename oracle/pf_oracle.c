@@ -266,6 +266,66 @@ int orc_form_kc_laplace(int64_t nels, int nod, int nip, const double *g_coord_pp
   return 0;
 }
 
+/* shape_fun, 3-D nod = 8 (new_library.f90:397-422) at Gauss point i (0-based) */
+int orc_shape_fun(int nod, const double *points, int nip, int i, double *fun) {
+  if (nod != 8) return 1;
+  const double xi = points[0 * nip + i], eta = points[1 * nip + i], zeta = points[2 * nip + i];
+  const double etam = 1.0 - eta, xim = 1.0 - xi, zetam = 1.0 - zeta;
+  const double etap = eta + 1.0, xip = xi + 1.0, zetap = zeta + 1.0;
+  fun[0] = 0.125 * xim * etam * zetam; fun[1] = 0.125 * xim * etam * zetap;
+  fun[2] = 0.125 * xip * etam * zetap; fun[3] = 0.125 * xip * etam * zetam;
+  fun[4] = 0.125 * xim * etap * zetam; fun[5] = 0.125 * xim * etap * zetap;
+  fun[6] = 0.125 * xip * etap * zetap; fun[7] = 0.125 * xip * etap * zetam;
+  return 0;
+}
+
+/* elements_3 / gauss_pts of p124.f90:81-95 (also p125.f90's kc / pm):
+ *   kc += MATMUL(MATMUL(TRANSPOSE(deriv),kay),deriv)*det*weights(i)
+ *   pm += MATMUL(TRANSPOSE(funny),funny)*det*weights(i)*rho*cp
+ *   storka = pm + kc*theta*dtim ; storkb = pm - kc*(1-theta)*dtim
+ * kay = diag(kx,ky,kz).  storka/storkb (8,8,nels); either may be NULL.  kc_out / pm_out (may be
+ * NULL) receive the raw kc and pm (p125 uses them directly). */
+int orc_form_k_transient(int64_t nels, int nod, int nip, const double *g_coord_pp, double kx,
+                         double ky, double kz, double rho, double cp, double theta, double dtim,
+                         double *storka_pp, double *storkb_pp, double *kc_out, double *pm_out) {
+  if (nod != 8 || (nip != 1 && nip != 8)) return 1;
+  double points[24], weights[8], kay[9] = {0};
+  orc_sample_hex(nip, points, weights);
+  kay[0] = kx; kay[4] = ky; kay[8] = kz;                       /* kay(a,b) at [b*3+a] */
+  const double omt = 1.0 - theta;
+#pragma omp parallel for schedule(static)
+  for (int64_t iel = 0; iel < nels; ++iel) {
+    double der[24], deriv[24], fun[8], kc[64], pm[64], t1[24];
+    memset(kc, 0, sizeof kc); memset(pm, 0, sizeof pm);
+    for (int ig = 0; ig < nip; ++ig) {
+      const double det = gauss_point(nod, points, nip, ig, g_coord_pp + iel * nod * 3, der, deriv);
+      orc_shape_fun(nod, points, nip, ig, fun);
+      for (int b = 0; b < 3; ++b)                               /* t1 = MATMUL(TRANSPOSE(deriv),kay): (nod,3) */
+        for (int m = 0; m < 8; ++m) {
+          double s = 0.0;
+          for (int a = 0; a < 3; ++a) s += deriv[m * 3 + a] * kay[b * 3 + a];
+          t1[b * 8 + m] = s;
+        }
+      for (int j = 0; j < 8; ++j)
+        for (int i = 0; i < 8; ++i) {
+          double s = 0.0;
+          for (int b = 0; b < 3; ++b) s += t1[b * 8 + i] * deriv[j * 3 + b];
+          kc[j * 8 + i] = kc[j * 8 + i] + s * det * weights[ig];
+          double f = 0.0;
+          f += fun[i] * fun[j];
+          pm[j * 8 + i] = pm[j * 8 + i] + f * det * weights[ig] * rho * cp;
+        }
+    }
+    for (int q = 0; q < 64; ++q) {
+      if (storka_pp) storka_pp[iel * 64 + q] = pm[q] + kc[q] * theta * dtim;
+      if (storkb_pp) storkb_pp[iel * 64 + q] = pm[q] - kc[q] * omt * dtim;
+      if (kc_out) kc_out[iel * 64 + q] = kc[q];
+      if (pm_out) pm_out[iel * 64 + q] = pm[q];
+    }
+  }
+  return 0;
+}
+
 /* centroid stresses, p121.f90:113-123: one point at (0,0,0); sigma = dee*(bee*eld) */
 int orc_centroid_stress(int nod, const double *coord, const double *eld, double e, double v,
                         double *sigma) {
@@ -580,6 +640,19 @@ int orc_scatter(int ntot, int64_t nels, const int32_t *g_g, int64_t neq, int npe
   return 0;
 }
 
+/* u = scatter(MATMUL(storkm, gather(x))) over npes emulated ranks: the operator product the
+ * drivers form outside the PCG loop (p124.f90:150-154 with storkb, :175-178 with storka) */
+int orc_apply(int ntot, int64_t nels, const int32_t *g_g, const double *storkm, int64_t neq, int npes,
+              const double *x, double *u) {
+  double *pmul = malloc(sizeof(double) * (size_t)(nels * ntot));
+  double *utemp = malloc(sizeof(double) * (size_t)(nels * ntot));
+  orc_gather(ntot, nels, g_g, x, pmul);
+  orc_matvec(ntot, nels, storkm, pmul, utemp);
+  orc_scatter(ntot, nels, g_g, neq, npes, utemp, u);
+  free(pmul); free(utemp);
+  return 0;
+}
+
 /*
  * The fixed blocked reduction tree (red_mode 1).  For a local vector of n
  * entries:
@@ -689,7 +762,8 @@ int orc_pcg(int ntot, int64_t nels, const int32_t *g_g, const double *storkm, in
     diag[j] = diag[j] + penalty; store[i] = diag[j];
   }
   for (int64_t i = 0; i < neq; ++i) diag[i] = 1.0 / diag[i];
-  for (int64_t i = 0; i < nfixed; ++i) r[no_f[i] - 1] = store[i] * val_f[i];   /* p123.f90:127-131 */
+  if (val_f)   /* p123.f90:127-131; p124 passes its own fixed-freedom residual (val_f == NULL) */
+    for (int64_t i = 0; i < nfixed; ++i) r[no_f[i] - 1] = store[i] * val_f[i];
   for (int64_t i = 0; i < neq; ++i) { d[i] = diag[i] * r[i]; p[i] = d[i]; }
   if (diag_out) memcpy(diag_out, diag, sizeof(double) * (size_t)neq);
 

@@ -55,6 +55,10 @@ SIGNATURES = {
     "pf_pcg_run": (c_int, [vp, c_dbl, c_int, P(c_int), P(c_int), P(c_dbl)]),
     "pf_pcg_get_x": (c_int, [vp, vp]),
     "pf_get_ratio_history": (c_int, [vp, vp, c_int, P(c_int)]),
+    "pf_form_k_transient": (c_int, [vp, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl]),
+    "pf_get_storkb": (c_int, [vp, c_i64, c_i64, vp]),
+    "pf_transient_start": (c_int, [vp, c_dbl, vp]),
+    "pf_transient_step": (c_int, [vp, vp, c_dbl, c_int, P(c_int), P(c_int), P(c_dbl)]),
     "pf_gather": (c_int, [vp, vp, vp]),
     "pf_matvec": (c_int, [vp, vp, vp]),
     "pf_scatter": (c_int, [vp, vp, vp]),

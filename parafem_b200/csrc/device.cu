@@ -76,6 +76,11 @@ struct pf_ctx {
   int64_t nels = 0, neq = 0, ieq_start = 0, neq_pp = 0, nhalo = 0, nslots = 0;
   bool have_mesh = false, have_km = false, have_precon = false, matrix_free = false;
   DevBuf<double> coord, km, utemp, diag_tmp, geom;
+  // p124 (transient conduction): km holds storka_pp (the PCG matrix), kb holds storkb_pp; mat_override
+  // selects the matrix set of the next operator product (nullptr = km)
+  DevBuf<double> kb, val_f;
+  const double *mat_override = nullptr;
+  bool transient = false, transient_first = false;
   int mf_mode = 0;
   int km_layout = 0;   // 0: storkm_pp(ntot,ntot,nels_pp) as the reference; 1: packed lower triangles (SymCfg)
   DevBuf<int> ggl;
@@ -198,6 +203,10 @@ int fill_tables(int nod, int nip, double e, double v, double kx, double ky, doub
       const double dz[8] = {-0.125 * xm * em, 0.125 * xm * em, 0.125 * xp * em, -0.125 * xp * em,
                             -0.125 * xm * ep, 0.125 * xm * ep, 0.125 * xp * ep, -0.125 * xp * ep};
       for (int m = 0; m < 8; ++m) { D[m] = dx[m]; D[20 + m] = dy[m]; D[40 + m] = dz[m]; }
+      // shape_fun, 3-D nod = 8 (new_library.f90:397-422)
+      const double fn[8] = {0.125 * xm * em * zm, 0.125 * xm * em * zp, 0.125 * xp * em * zp, 0.125 * xp * em * zm,
+                            0.125 * xm * ep * zm, 0.125 * xm * ep * zp, 0.125 * xp * ep * zp, 0.125 * xp * ep * zm};
+      for (int m = 0; m < 8; ++m) T.fun[ig * 8 + m] = fn[m];
     } else if (nod == 20) {
       // corner / mid-edge classes of the 20-node brick in S&G order
       const int sx[20] = {-1, -1, -1, 0, 1, 1, 1, 0, -1, -1, 1, 1, -1, -1, -1, 0, 1, 1, 1, 0};
@@ -250,7 +259,8 @@ int launch_matvec_t(pf_handle h, const double *pvec, const State *st) {
   }
   const int64_t ntiles = (h->nels + EPT - 1) / EPT;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, ntiles));
-  kern<<<grid, Cfg::kThreads, Cfg::kSmem, h->stream>>>(h->km.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmem, h->stream>>>(h->mat_override ? h->mat_override : h->km.p, h->ggl.p, pvec, h->utemp.p,
+                                                       (long long)h->nels, st);
   h->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -632,7 +642,7 @@ int pf_finalize(pf_handle h) {
     g_nccl.CommDestroy(h->comm);
   }
   h->sync.release(); h->ptab.release();
-  h->coord.release(); h->km.release(); h->diag_tmp.release(); h->geom.release(); h->utemp.release(); h->ggl.release(); h->csr_ptr.release(); h->csr_pos.release();
+  h->coord.release(); h->km.release(); h->kb.release(); h->val_f.release(); h->diag_tmp.release(); h->geom.release(); h->utemp.release(); h->ggl.release(); h->csr_ptr.release(); h->csr_pos.release();
   h->put_slot.release(); h->sendbuf.release(); h->recvbuf.release(); h->acc_slot.release(); h->acc_ptr.release(); h->acc_pos.release();
   h->p_ext.release(); h->u_ext.release(); h->diag_ext.release(); h->r.release(); h->x.release(); h->d.release();
   h->part.release(); h->gath.release(); h->state.release(); h->ratio_hist.release(); h->fix_slot.release(); h->store.release();
@@ -756,6 +766,7 @@ int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp, con
   h->nod = nod; h->nodof = nodof; h->nip = nip; h->ntot = ntot;
   h->nels = nels_pp; h->neq = neq; h->ieq_start = ieq_start; h->neq_pp = neq_pp;
   h->have_km = h->have_precon = false;
+  h->transient = h->transient_first = false; h->mat_override = nullptr; h->kb.release();
 
   // gather table (make_ggl rebuilt from g_g_pp)
   const int64_t total = nels_pp * ntot;
@@ -877,6 +888,7 @@ static int alloc_km(pf_handle h) {
 
 int pf_form_km_elastic(pf_handle h, double e, double v) {
   int rc = need_device(h); if (rc) return rc;
+  h->transient = false; h->kb.release();
   NEED(h->have_mesh && h->nodof == 3, "needs pf_setup_mesh with nodof = 3");
   ElemTables T;
   if (fill_tables(h->nod, h->nip, e, v, 0, 0, 0, T)) return fail(h, 3, "unsupported nod/nip");
@@ -911,6 +923,7 @@ int pf_form_km_elastic(pf_handle h, double e, double v) {
 
 int pf_form_kc_laplace(pf_handle h, double kx, double ky, double kz) {
   int rc = need_device(h); if (rc) return rc;
+  h->transient = false; h->kb.release();
   NEED(h->have_mesh && h->nodof == 1 && h->nod == 8, "needs pf_setup_mesh with nod = 8, nodof = 1");
   ElemTables T;
   if (fill_tables(h->nod, h->nip, 0, 0, kx, ky, kz, T)) return fail(h, 3, "unsupported nod/nip");
@@ -925,10 +938,107 @@ int pf_form_kc_laplace(pf_handle h, double kx, double ky, double kz) {
   return 0;
 }
 
+// ---- p124: transient heat conduction, implicit theta method ----
+int pf_form_k_transient(pf_handle h, double kx, double ky, double kz, double rho, double cp, double theta, double dtim) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_mesh && h->nodof == 1 && h->nod == 8, "needs pf_setup_mesh with nod = 8, nodof = 1");
+  NEED(h->km_layout == 0 && !h->matrix_free, "the transient matrices use the reference storkm layout");
+  ElemTables T;
+  if (fill_tables(h->nod, h->nip, 0, 0, kx, ky, kz, T)) return fail(h, 3, "unsupported nod/nip");
+  T.trans[0] = rho; T.trans[1] = cp; T.trans[2] = theta; T.trans[3] = dtim;
+  CU(cudaMemcpyToSymbol(c_tab, &T, sizeof T));
+  if ((rc = alloc_km(h))) return rc;
+  if (h->kb.n != h->km.n) CU(h->kb.alloc(h->km.n));
+  const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 32);
+  k_form_k_transient<<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, h->kb.p, (long long)h->nels);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  h->have_km = true; h->have_precon = false; h->transient = true; h->transient_first = false;
+  return 0;
+}
+
+int pf_get_storkb(pf_handle h, int64_t iel0, int64_t n, double *out) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->transient && h->have_km && iel0 >= 0 && n >= 0 && iel0 + n <= h->nels, "needs pf_form_k_transient and a local element range");
+  const size_t per = (size_t)h->ntot * h->ntot;
+  CU(cudaMemcpy(out, h->kb.p + (size_t)iel0 * per, (size_t)n * per * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int pf_transient_start(pf_handle h, double val0, const double *val_f_pp) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->transient && h->have_precon, "needs pf_form_k_transient and pf_build_precon");
+  NEED(h->nfixed == 0 || val_f_pp, "fixed freedoms were declared in pf_build_precon: val_f_pp is required");
+  // x_pp = val0; x_pp(l) = val_f(k) on the fixed freedoms   (p124.f90:168-173)
+  if (h->neq_pp > 0) {
+    k_fill<<<grid_for(h, h->neq_pp, 256), 256, 0, h->stream>>>(h->x.p, val0, (long long)h->neq_pp);
+    h->launches++;
+  }
+  if (h->nfixed > 0) {
+    CU(h->val_f.alloc((size_t)h->nfixed));
+    CU(cudaMemcpyAsync(h->val_f.p, val_f_pp, (size_t)h->nfixed * 8, cudaMemcpyHostToDevice, h->stream));
+    k_fixed_transient<<<(h->nfixed + 255) / 256, 256, 0, h->stream>>>(h->fix_slot.p, h->store.p, h->val_f.p, h->x.p - 1, h->nfixed, 0);
+    h->launches++;
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  h->transient_first = true;
+  return 0;
+}
+
+int pf_transient_step(pf_handle h, const double *loads_pp, double tol, int limit, int *iters, int *converged,
+                      double *elapsed_ms) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->transient && h->have_precon, "needs pf_form_k_transient, pf_build_precon and pf_transient_start");
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, h->stream));
+  // u = storka*x on the first step (p124.f90:174-178), storkb*xnew afterwards (:149-154); x lives in h->x
+  CU(cudaMemcpyAsync(h->p_ext.p + 1, h->x.p, (size_t)h->neq_pp * 8, cudaMemcpyDeviceToDevice, h->stream));
+  const int nfixed = h->nfixed;
+  h->nfixed = 0;                                   // no u = p*store fix-up on this product
+  h->mat_override = h->transient_first ? nullptr : h->kb.p;
+  rc = apply_operator(h, nullptr);
+  h->mat_override = nullptr;
+  h->nfixed = nfixed;
+  if (rc) return rc;
+  if (!h->transient_first && nfixed > 0) {         // u_pp(l) = store_pp(i)*val_f(k)   (:155-160)
+    k_fixed_transient<<<(nfixed + 255) / 256, 256, 0, h->stream>>>(h->fix_slot.p, h->store.p, h->val_f.p, h->u_ext.p, nfixed, 1);
+    h->launches++;
+  }
+  // loads_pp = loads_pp + u_pp ; r_pp = loads_pp - r_pp, r_pp = +0.0 off the fixed freedoms (:161,:187-199)
+  const double *l = nullptr;
+  if (loads_pp) {
+    CU(cudaMemcpyAsync(h->d.p, loads_pp, (size_t)h->neq_pp * 8, cudaMemcpyHostToDevice, h->stream));
+    l = h->d.p;
+  }
+  if (h->neq_pp > 0) {
+    k_transient_rhs<<<grid_for(h, h->neq_pp, 256), 256, 0, h->stream>>>(h->r.p, l, h->u_ext.p + 1, (long long)h->neq_pp);
+    h->launches++;
+  }
+  if (nfixed > 0) {
+    k_fixed_transient<<<(nfixed + 255) / 256, 256, 0, h->stream>>>(h->fix_slot.p, h->store.p, h->val_f.p, h->r.p - 1, nfixed, 2);
+    h->launches++;
+  }
+  CU(cudaGetLastError());
+  h->transient_first = false;
+  // d = M^-1 r, p = d, x = 0 and the PCG loop (:199-218)
+  if ((rc = pf_pcg_run(h, tol, limit, iters, converged, nullptr))) return rc;
+  CU(cudaEventRecord(e1, h->stream));
+  CU(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (elapsed_ms) *elapsed_ms = ms;
+  return 0;
+}
+
 int pf_set_storkm(pf_handle h, const double *storkm_pp) {
   int rc = need_device(h); if (rc) return rc;
   NEED(h->have_mesh && storkm_pp, "needs pf_setup_mesh");
   NEED(!h->matrix_free, "matrix-free variant: storkm is not stored");
+  h->transient = false; h->kb.release();
   if ((rc = alloc_km(h))) return rc;
   if (h->km_layout == 0) {
     CU(cudaMemcpy(h->km.p, storkm_pp, h->km.bytes(), cudaMemcpyHostToDevice));

@@ -780,7 +780,9 @@ struct ElemTables {
   double der[8 * 3 * 20];  // [ig][a][m]  = der(a,m) at Gauss point ig   (shape_der)
   double weights[8];       // sample
   double dee[36];          // dee(l,k) at [k*6+l]                        (deemat)
-  double kxyz[3];          // p123 conductivities
+  double kxyz[3];          // p123 / p124 conductivities (diagonal of kay)
+  double fun[8 * 8];       // [ig][m] = fun(m) at Gauss point ig, 8-node brick   (shape_fun)
+  double trans[4];         // p124: rho, cp, theta, dtim
   int nip;
 };
 __constant__ ElemTables c_tab;  // single translation unit (device.cu)
@@ -1273,6 +1275,68 @@ k_form_kc_laplace(const double *__restrict__ g_coord, double *__restrict__ kc, l
   }
 }
 
+
+// elements_3 / gauss_pts of p124.f90:81-95; 8-node bricks, 64 threads = one per entry:
+//   kc += MATMUL(MATMUL(TRANSPOSE(deriv),kay),deriv)*det*w ;  pm += fun fun^T *det*w*rho*cp
+//   storka = pm + kc*theta*dtim ; storkb = pm - kc*(1-theta)*dtim
+__global__ void __launch_bounds__(64)
+k_form_k_transient(const double *__restrict__ g_coord, double *__restrict__ ka, double *__restrict__ kb, long long nels) {
+  constexpr int NOD = 8;
+  __shared__ double s_coord[NOD * 3], s_jac[9], s_deriv[NOD * 3];
+  const int j = threadIdx.x / 8, i = threadIdx.x % 8;
+  const double rho = c_tab.trans[0], cp = c_tab.trans[1], theta = c_tab.trans[2], dtim = c_tab.trans[3];
+  const double omt = 1.0 - theta;
+  for (long long e = blockIdx.x; e < nels; e += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x < NOD * 3) s_coord[threadIdx.x] = g_coord[e * NOD * 3 + threadIdx.x];
+    __syncthreads();
+    double kc = 0.0, pm = 0.0;
+    for (int ig = 0; ig < c_tab.nip; ++ig) {
+      const double det = gauss_point<NOD>(ig, s_coord, s_jac, s_deriv);
+      const double wt = c_tab.weights[ig];
+      double s = 0.0;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        // t1(i,b) = sum_a deriv(a,i)*kay(a,b), kay diagonal: the full a-ascending sum from 0.0
+        double t1 = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) t1 = t1 + s_deriv[i * 3 + a] * (a == b ? c_tab.kxyz[b] : 0.0);
+        s = s + t1 * s_deriv[j * 3 + b];
+      }
+      kc = kc + s * det * wt;
+      double f = 0.0;
+      f = f + c_tab.fun[ig * 8 + i] * c_tab.fun[ig * 8 + j];
+      pm = pm + f * det * wt * rho * cp;
+      __syncthreads();
+    }
+    ka[e * 64 + threadIdx.x] = pm + kc * theta * dtim;
+    kb[e * 64 + threadIdx.x] = pm - kc * omt * dtim;
+  }
+}
+
+// p124 time stepping, right-hand side of one step (p124.f90:143-200):
+//   loads = (loaded freedoms, or 0) + u ;  r = loads - r0 with r0 = +0.0 off the fixed freedoms
+__global__ void k_transient_rhs(double *__restrict__ r, const double *__restrict__ loads, const double *__restrict__ u, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) r[i] = ((loads ? loads[i] : 0.0) + u[i]) - 0.0;
+}
+__global__ void k_fill(double *__restrict__ v, double val, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) v[i] = val;
+}
+// fixed freedoms of p124: mode 0  x(l) = val_f (p124.f90:170-173); mode 1  u(l) = store*val_f (:156-159);
+// mode 2  r(l) = loads(l) - store*val_f (:193-198, dst holds loads).  dst is slot-indexed (slot 0 = dump).
+__global__ void k_fixed_transient(const int *__restrict__ fix_slot, const double *__restrict__ store,
+                                  const double *__restrict__ val_f, double *__restrict__ dst, int n, int mode) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = fix_slot[i];
+  if (mode == 0) dst[s] = val_f[i];
+  else if (mode == 1) dst[s] = store[i] * val_f[i];
+  else dst[s] = dst[s] - store[i] * val_f[i];
+}
 
 // full (ntot,ntot) column-major element matrices <-> packed lower triangles (pf_set_storkm / pf_get_storkm
 // on the symmetric layout); unpacking mirrors the lower triangle

@@ -41,6 +41,62 @@ def run(prob, s):
     return out
 
 
+def run_p124(prob, s, out_base=None, source=None, decimals=5):
+    """Program p124 (p124.f90) for one rank: setup, then the time-stepping loop with one device-resident
+    PCG solve per step.  `source` = value of the loaded freedom nres (loads_pp = source*dtim every step,
+    p124.f90:143-148; None = no loads, as every shipped deck).  With `out_base` the nodal temperature
+    files <out_base>.ensi.NDTTR-NNNNNN are written at step 0 and every npri steps (p124.f90:180-191,
+    219-231; single rank).  -> dict(times, temps (x at freedom nres), iters, rows (the printed steps),
+    x (last field), solve_s, setup_s)."""
+    from . import host
+    t0 = time.time()
+    _solver.setup_problem(s, prob)
+    s.transient_start(prob.val0, prob.val_f if prob.no_f.size else None)
+    t_setup = time.time() - t0
+    lo = prob.ieq_start
+    owns = lo <= prob.nres < lo + prob.neq_pp
+    loads = None
+    if source is not None:
+        loads = np.zeros(prob.neq_pp)
+        if owns:
+            loads[prob.nres - lo] = source * prob.dtim
+    rows = [(0.0, prob.val0, None)] if owns else []
+    if out_base and prob.npes == 1:
+        x0 = np.full(prob.neq_pp, prob.val0)
+        if prob.no_f.size:
+            x0[prob.no_f - lo] = prob.val_f
+        host.write_ensi(f"{out_base}.ensi.NDTTR-{0:06d}", host.nodal_values(prob, x0), decimals=decimals)
+    iters, solve_ms, x = [], 0.0, None
+    for j in range(1, prob.nstep + 1):
+        it, _, ms = s.transient_step(prob.tol, prob.limit, loads)
+        iters.append(it)
+        solve_ms += ms
+        if j // prob.npri * prob.npri == j:
+            x = s.pcg_get_x()
+            if out_base and prob.npes == 1:
+                host.write_ensi(f"{out_base}.ensi.NDTTR-{j:06d}", host.nodal_values(prob, x), decimals=decimals)
+            if owns:
+                rows.append((j * prob.dtim, float(x[prob.nres - lo]), it))
+    if x is None or prob.nstep % prob.npri:
+        x = s.pcg_get_x()
+    return dict(iters=iters, rows=rows, x=x, solve_s=solve_ms / 1e3, setup_s=t_setup,
+                times=[r[0] for r in rows], temps=[r[1] for r in rows])
+
+
+def write_res_p124(path, prob, res, t_total=0.0, t_output=0.0):
+    """<job>.res of p124 as the rank owning freedom nres writes it (p124.f90:56-62,136,169,228,233-238)."""
+    with open(path, "w") as f:
+        f.write(f"This job ran on {prob.npes:5d}  processes\n")
+        f.write(f"There are {prob.nn:12d} nodes{prob.nr:12d} restrained and   {prob.neq:12d} equations\n")
+        f.write(f"Time after setup is {res['setup_s']:10.4f}\n")
+        f.write("  Time       Temperature  Iterations \n")
+        for t, v, it in res["rows"]:
+            f.write(_fe(t) + _fe(v) + ("" if it is None else f"{it:10d}") + "\n")
+        f.write(f"The solution phase took {res['solve_s']:10.4f}\n")
+        f.write(f"Writing the output took {t_output:10.4f}\n")
+        f.write(f"This analysis took      {t_total:10.4f}\n")
+
+
 def write_res(path, prob, res, t_read=0.0, t_total=0.0):
     """<job>.res as rank 1 writes it."""
     with open(path, "w") as f:
@@ -87,6 +143,8 @@ def main(argv=None):
     g.add_argument("--deck", help="ParaFEM p121 deck base name (<job>.dat/.d/.bnd/.lds)")
     g.add_argument("--cube", type=int, help="p12meshgen p121 cube with N^3 elements, generated in memory")
     g.add_argument("--p123", type=int, help="p12meshgen p123 box with N^3 8-node bricks")
+    g.add_argument("--p124", type=int, help="p12meshgen p124 box with N^3 8-node bricks (transient conduction, "
+                                            "150 steps of 0.01 as the shipped p124_*.mg)")
     ap.add_argument("--hex", type=int, default=20, choices=[8, 20])
     ap.add_argument("--matrix-free", type=int, default=0, choices=[0, 1, 2])
     ap.add_argument("--out", default=".")
@@ -94,6 +152,14 @@ def main(argv=None):
     t0 = time.time()
     if a.deck:
         prob, job = host.read_deck_p121(a.deck), os.path.basename(a.deck)
+    elif a.p124:
+        prob, job = host.cube_p124(a.p124, a.p124, a.p124), f"p124_box{a.p124}"
+        base = os.path.join(a.out, job)
+        with _solver.Solver(0, 1, 0) as s:
+            res = run_p124(prob, s, out_base=base)
+        write_res_p124(base + ".res", prob, res, t_total=time.time() - t0)
+        print(open(base + ".res").read(), end="")
+        return 0
     elif a.cube:
         prob, job = host.cube_p121(a.cube, a.cube, a.cube, a.hex, limit=20000), f"p121_cube{a.cube}_hex{a.hex}"
     else:

@@ -73,6 +73,14 @@ class Problem:
     no_f: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))   # fixed eq (global)
     val_f: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float64))
     total_load: float = 0.0
+    # p124 (transient conduction): rho, cp, theta method, time stepping, initial value, print interval
+    rho: float = 1.0
+    cp: float = 1.0
+    theta: float = 0.5
+    dtim: float = 0.01
+    nstep: int = 0
+    npri: int = 1
+    val0: float = 0.0
 
     @property
     def ntot(self):
@@ -175,6 +183,19 @@ def cube_p123(nxe, nye, nze, aa=None, bb=None, cc=None, kx=2.0, ky=2.0, kz=2.0, 
                    no_f=no_f, val_f=val_f, total_load=total)
 
 
+def cube_p124(nxe, nye, nze, aa=None, bb=None, cc=None, kx=1.0, ky=1.0, kz=1.0, rho=1.0, cp=1.0, dtim=0.01,
+              nstep=150, theta=0.5, npri=10, tol=1e-4, limit=100, val0=100.0, nip=8, npes=1, numpe=1,
+              round_mode=0, fixed=False, fixed_value=100.0, psize=None):
+    """In-memory p12meshgen box for p124 (p12meshgen.f90:827-905): the p123 box (geometry_8bxz, box_bc8,
+    nres) with the transient data of the .mg file (defaults = the shipped p124_*.mg)."""
+    p = cube_p123(nxe, nye, nze, aa, bb, cc, kx, ky, kz, tol, limit, nip, npes, numpe, round_mode, 0.0, fixed,
+                  fixed_value, psize)
+    p.program = 124
+    p.r_pp[:] = 0.0
+    p.rho, p.cp, p.theta, p.dtim, p.nstep, p.npri, p.val0 = rho, cp, theta, dtim, nstep, npri, val0
+    return p
+
+
 def read_deck_p121(job, npes=1, numpe=1):
     """read_p121 + read_g_num_pp + abaqus2sg + read_g_coord_pp + read_rest + steering +
     read_loads + load (p121.f90:28-49, 79-85) for one rank."""
@@ -239,7 +260,8 @@ def nodal_values(prob, x_pp):
 
 
 def write_ensi(path, values, decimals=5):
-    """dismsh_ensi_p's EnSight Gold ASCII file: values (nn, numvar), component-major on disk."""
+    """dismsh_ensi_p's EnSight Gold ASCII file: values (nn, numvar), component-major on disk
+    (numvar = 1 gets the "Scalar per-node" header p123/p124 write, p124.f90:183-186)."""
     v = f64(values)
     check(lib().pf_write_ensi(str(path).encode(), v.shape[1], v.shape[0], ptr(v), decimals), what="pf_write_ensi")
 

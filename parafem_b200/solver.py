@@ -137,6 +137,30 @@ class Solver:
         self._ck(lib().pf_get_ratio_history(self._h, ptr(out), maxn, C.byref(n)), "pf_get_ratio_history")
         return out[:n.value].copy()
 
+    # -- p124: transient conduction ---------------------------------------------------
+    def form_k_transient(self, kx, ky, kz, rho, cp, theta, dtim):
+        """p124.f90:81-95: storka_pp (the PCG matrix) and storkb_pp on the device."""
+        self._ck(lib().pf_form_k_transient(self._h, kx, ky, kz, rho, cp, theta, dtim), "pf_form_k_transient")
+
+    def get_storkb(self, iel0=0, n=None):
+        n = self.prob.nels_pp - iel0 if n is None else n
+        nt = self.prob.ntot
+        out = np.empty((n, nt, nt))
+        self._ck(lib().pf_get_storkb(self._h, iel0, n, ptr(out)), "pf_get_storkb")
+        return out
+
+    def transient_start(self, val0, val_f=None):
+        v = f64(val_f) if val_f is not None and len(val_f) else None
+        self._ck(lib().pf_transient_start(self._h, val0, ptr(v)), "pf_transient_start")
+
+    def transient_step(self, tol, limit, loads_pp=None):
+        """One pass of p124's timesteps loop. -> (iters, converged, elapsed_ms)"""
+        it, cv, ms = C.c_int(), C.c_int(), C.c_double()
+        l = f64(loads_pp) if loads_pp is not None else None
+        self._ck(lib().pf_transient_step(self._h, ptr(l), tol, limit, C.byref(it), C.byref(cv), C.byref(ms)),
+                 "pf_transient_step")
+        return it.value, bool(cv.value), ms.value
+
     # -- fine-grained -----------------------------------------------------------------
     def gather(self, p_pp):
         out = np.empty((self.prob.nels_pp, self.prob.ntot))
@@ -202,6 +226,9 @@ def setup_problem(solver, prob, matrix_free=False, layout=0):
     if prob.program == 121:
         solver.form_km_elastic(prob.e, prob.v)
         solver.build_precon()
+    elif prob.program == 124:
+        solver.form_k_transient(prob.kx, prob.ky, prob.kz, prob.rho, prob.cp, prob.theta, prob.dtim)
+        solver.build_precon(prob.no_f, 1e20)
     else:
         solver.form_kc_laplace(prob.kx, prob.ky, prob.kz)
         solver.build_precon(prob.no_f, 1e20)

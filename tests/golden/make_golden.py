@@ -10,6 +10,9 @@ are parsed and packed:
   p121_demo_digests.json   SHA-256 of the parsed 4 MB p121_demo.d / .bnd arrays (the in-memory
                   generator must reproduce them)
   p121_demo_ensi_head.txt  the first 204 lines of the 107 167-line EnSight golden (format check)
+  p124_demo_digests.json   SHA-256 of the parsed p124_demo.d / .bnd arrays (25^3 8-node bricks); arrays.npz
+                  also holds three of the sixteen golden nodal temperature files (steps 10, 80, 150;
+                  float32 of the 5-digit values) and fixtures.json the p124 logs / control files
 tests/conftest.py materialises decks and logs from these into a temporary directory with the
 repo's own deck writer (pf_write_deck_p121), which reproduces xx3-tiny.d byte for byte.
 """
@@ -48,7 +51,24 @@ def main():
     dval = np.empty((65, 3))
     assert lib().pf_read_lds(demo.encode(), 65, 3, ptr(dnode), ptr(dval)) == 0
     disp = np.loadtxt(demo + ".ensi.DISPL-000001", skiprows=4)
-    np.savez_compressed(f"{HERE}/arrays.npz", tiny_coord=t.g_coord, tiny_gnum_sg=t.g_num_pp, tiny_rest=t.rest,
+    # p124 demo deck (transient conduction, 25^3 8-node bricks, Abaqus node order on disk)
+    d124 = f"{REF}/5th_ed/p124/demo/p124_demo"
+    dat = open(d124 + ".dat").read().split()
+    nels4, nn4, nr4, nip4, nod4 = (int(v) for v in dat[4:9])
+    gc4 = np.empty((nn4, 3), np.float64)
+    gn4 = np.empty((nels4, nod4), np.int32)
+    assert lib().pf_read_d(d124.encode(), nn4, nels4, nod4, ptr(gc4), ptr(gn4)) == 0
+    assert lib().pf_abaqus2sg(nod4, nels4, ptr(gn4)) == 0
+    rest4 = np.zeros((2, nr4), np.int32)
+    assert lib().pf_read_bnd(d124.encode(), nr4, 1, ptr(rest4)) == 0
+    gcpp4 = np.empty((nels4, 3, nod4), np.float64)
+    assert lib().pf_coords_pp(nod4, nels4, ptr(gn4), ptr(gc4), ptr(gcpp4)) == 0
+    # (+ 0.0: p124_demo.d prints the top face's -(is-1)*cc = -0.0 unsigned, p121_demo.d prints it signed)
+    json.dump(dict(g_num_sg=sha(gn4), g_coord_pp=sha(gcpp4 + 0.0), rest=sha(rest4), nn=nn4, nr=nr4, nels=nels4, nip=nip4,
+                   nod=nod4), open(f"{HERE}/p124_demo_digests.json", "w"), indent=1)
+    ndttr = {f"p124_ndttr_{j:03d}": np.loadtxt(f"{d124}.ensi.NDTTR-{j:06d}", skiprows=4).astype(np.float32)
+             for j in (10, 80, 150)}
+    np.savez_compressed(f"{HERE}/arrays.npz", **ndttr, tiny_coord=t.g_coord, tiny_gnum_sg=t.g_num_pp, tiny_rest=t.rest,
                         tiny_lds_node=node, tiny_lds_val=val, tiny_dis=dis, demo_lds_node=dnode, demo_lds_val=dval,
                         demo_displ=disp.reshape(3, p.nn).T.astype(np.float32))
     texts = {
@@ -56,6 +76,9 @@ def main():
         "p121_demo.res": lines(demo + ".res"), "p121_demo.dat": lines(demo + ".dat"), "p121_demo.mg": lines(demo + ".mg"),
         "p121_book.res": lines(f"{REF}/5th_ed/p121/book/p121.res"), "p121_book.mg": lines(f"{REF}/5th_ed/p121/book/p121.mg"),
         "p123_book.res": lines(f"{REF}/5th_ed/p123/book/p123.res"), "p123_book.mg": lines(f"{REF}/5th_ed/p123/book/p123.mg"),
+        "p124_demo.res": lines(d124 + ".res"), "p124_demo.dat": lines(d124 + ".dat"), "p124_demo.mat": lines(d124 + ".mat"),
+        "p124_book.res": lines(f"{REF}/5th_ed/p124/book/p124.res"), "p124_book.mg": lines(f"{REF}/5th_ed/p124/book/p124.mg"),
+        "p124_tiny.mg": lines(f"{REF}/5th_ed/p124/mg/p124_tiny.mg"),
         "p123_small.mg": lines(f"{REF}/5th_ed/p123/mg/p123_small.mg"), "p121_tiny.mg": lines(f"{REF}/5th_ed/p121/mg/p121_tiny.mg"),
     }
     json.dump(texts, open(f"{HERE}/fixtures.json", "w"), indent=1)

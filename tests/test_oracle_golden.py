@@ -142,3 +142,78 @@ def test_blocked_dot_is_a_valid_sum():
         a, b = rng.randn(n), rng.randn(n)
         exact = float(np.dot(a.astype(np.longdouble), b.astype(np.longdouble)))
         assert abs(oracle.dot_blocked(a, b) - exact) <= 1e-12 * np.abs(a * b).sum()
+
+
+# ---- p124: transient heat conduction --------------------------------------------
+
+def _p124_rows(path):
+    """(time, temperature, iterations) rows of a p124 .res file."""
+    rows = []
+    for line in open(path):
+        m = re.match(r"^\s+(0\.\d+E[+-]\d+)\s+(-?0\.\d+E[+-]\d+)\s+(\d+)\s*$", line)
+        if m:
+            rows.append((float(m.group(1)), float(m.group(2)), int(m.group(3))))
+    return rows
+
+
+@pytest.fixture(scope="module")
+def p124_demo():
+    """p124_demo.mg = p124_tiny.mg: 25^3 8-node bricks of 0.04, coordinates as they survive the deck."""
+    return host.cube_p124(25, 25, 25, aa=.04, bb=.04, cc=.04, round_mode=1)
+
+
+def test_p124_generator_reproduces_shipped_deck(p124_demo):
+    """The in-memory box equals examples/5th_ed/p124/demo/p124_demo.d/.bnd (digests of the parsed files)."""
+    import hashlib
+    dg = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "p124_demo_digests.json")))
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    p = p124_demo
+    assert (p.nn, p.nr, p.nels, p.nip, p.nod) == (dg["nn"], dg["nr"], dg["nels"], dg["nip"], dg["nod"])
+    assert sha(p.g_num_pp) == dg["g_num_sg"]
+    assert sha(p.g_coord_pp + 0.0) == dg["g_coord_pp"]       # + 0.0: this deck prints -0.0 unsigned
+    rest = np.zeros((2, p.nr), np.int32)
+    from parafem_b200._lib import lib, ptr
+    assert lib().pf_cube_rest(1, 25, 25, 25, 8, p.nr, ptr(rest)) == 0
+    assert sha(rest) == dg["rest"]
+
+
+@pytest.mark.parametrize("red_mode,npes", [(0, 2), (1, 1)])
+def test_p124_demo_log_and_fields(p124_demo, golden, red_mode, npes):
+    """examples/5th_ed/p124/demo/p124_demo.res (2 ranks): 15 625 equations, and at every tenth of the 150 steps
+    the temperature at freedom nres = 601 (4 digits) and the PCG iteration count -- all fifteen rows
+    reproduced exactly; nodal temperature files of steps 10, 80, 150 to the 5 digits they print."""
+    p = p124_demo
+    dat = open(os.path.join(golden, "p124_demo.dat")).read().split()
+    assert (int(dat[4]), int(dat[5]), int(dat[6])) == (p.nels, p.nn, p.nr) and int(dat[-1]) == p.nres == 601
+    val0, dtim, nstep, npri, theta = float(dat[11]), float(dat[12]), int(dat[13]), int(dat[14]), float(dat[15])
+    tol, limit = float(dat[16]), int(dat[17])
+    assert (val0, dtim, nstep, npri, theta, tol, limit) == (100.0, 0.01, 150, 10, 0.5, 1e-4, 100)
+    mat = [float(v) for v in open(os.path.join(golden, "p124_demo.mat")).read().splitlines()[2].split()[1:]]
+    rows = _p124_rows(os.path.join(golden, "p124_demo.res"))
+    assert len(rows) == 15 and "15625 equations" in open(os.path.join(golden, "p124_demo.res")).read()
+    a, b = oracle.form_k_transient(p.g_coord_pp, p.nip, *mat, theta, dtim)
+    r = oracle.p124(a, b, p.g_g_pp, p.neq, val0, nstep, tol, limit, npes=npes, red_mode=red_mode, keep=(10, 80, 150))
+    assert all(r["converged"])
+    arr = np.load(os.path.join(os.path.dirname(__file__), "golden", "arrays.npz"))
+    for k, (t, temp, its) in enumerate(rows):
+        j = (k + 1) * npri
+        assert abs(t - j * dtim) < 1e-12
+        assert r["iters"][j - 1] == its, (j, r["iters"][j - 1], its)
+    for j in (10, 80, 150):
+        gold = arr[f"p124_ndttr_{j:03d}"].astype(np.float64)
+        field = host.nodal_values(p, r["fields"][j])[:, 0]
+        assert np.abs(field - gold).max() <= 6e-5 * np.abs(gold).max()          # e12.5: 5 significant digits
+        k = j // npri - 1
+        assert abs(r["fields"][j][p.nres - 1] - rows[k][1]) <= 6e-4 * abs(rows[k][1])   # E12.4 in the .res
+
+
+def test_p124_transient_matrices_properties():
+    """storka - storkb = kc*dtim and storka + storkb ~ 2 pm: rows of kc sum to 0 (constant field),
+    pm sums to rho*cp*volume."""
+    p = host.cube_p124(3, 2, 2, aa=.5, bb=.25, cc=.2)
+    a, b, kc, pm = oracle.form_k_transient(p.g_coord_pp, 8, 1.5, 2.0, 0.5, 3.0, 2.0, 0.5, 0.01, raw=True)
+    assert np.abs(kc.sum(axis=2)).max() < 1e-13
+    assert np.allclose(pm.sum(axis=(1, 2)), 3.0 * 2.0 * .5 * .25 * .2, rtol=1e-13)
+    assert np.allclose(a - b, kc * 0.01, rtol=0, atol=1e-16)
+    lap = oracle.form_kc_laplace(p.g_coord_pp, 8, 1.5, 2.0, 0.5)
+    assert np.allclose(kc, lap, rtol=1e-12, atol=1e-15)       # same operator as p123's kcx*kx+kcy*ky+kcz*kz
