@@ -50,6 +50,12 @@ MODULE parafem_gpu
       IMPORT; TYPE(c_ptr),VALUE :: h; REAL(c_double),VALUE :: e,v
     END FUNCTION
 
+    ! per-element materials (xx2.f90:169-193): prop(2,np_types) = (e,v), etype_pp(nels_pp)
+    INTEGER(c_int) FUNCTION pf_form_km_elastic_mat(h,np_types,prop,etype_pp) BIND(C,name='pf_form_km_elastic_mat')
+      IMPORT; TYPE(c_ptr),VALUE :: h; INTEGER(c_int),VALUE :: np_types
+      REAL(c_double) :: prop(2,*); INTEGER(c_int) :: etype_pp(*)
+    END FUNCTION
+
     ! elements_1 of p123.f90:70-84 on the device
     INTEGER(c_int) FUNCTION pf_form_kc_laplace(h,kx,ky,kz) BIND(C,name='pf_form_kc_laplace')
       IMPORT; TYPE(c_ptr),VALUE :: h; REAL(c_double),VALUE :: kx,ky,kz

@@ -101,6 +101,11 @@ int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp,
 int pf_set_storkm_layout(pf_handle h, int layout);
 int pf_form_km_elastic(pf_handle h, double e, double v);
 int pf_form_kc_laplace(pf_handle h, double kx, double ky, double kz);
+/* Per-element materials (xx2 / rfemsolve): elements_3 of
+ * programs/dev/xx2/xx2.f90:169-193, e = prop(1,etype_pp(iel)), v = prop(2,etype_pp(iel)).
+ * prop(2,np_types) column-major, etype_pp(nels_pp) 1-based material numbers (the last
+ * column of the .d element lines, read_elements input.f90:1434-1583).               */
+int pf_form_km_elastic_mat(pf_handle h, int np_types, const double *prop, const int32_t *etype_pp);
 int pf_set_storkm(pf_handle h, const double *storkm_pp);
 int pf_get_storkm(pf_handle h, int64_t iel0, int64_t n, double *out);
 int pf_set_matrix_free(pf_handle h, int on);
@@ -250,8 +255,17 @@ typedef struct {
   int meshgen, partitioner, nip, nod, limit;
   int64_t nels, nn, nr, loaded, fixed, nres;
   double e, v, kx, ky, kz, tol;
+  /* p124 (read_p124, input.f90:3997-4169) and xx2 (read_xx2, :5391-5562) */
+  int np_types, nstep, npri, pad_;
+  double val0, dtim, theta;
 } pf_deck_info;
+/* program: 121, 123, 124, or 2 for the dev program xx2 (per-element materials) */
 int pf_read_dat(const char *job, int program, pf_deck_info *info);
+/* pf_read_d + the material number of every element (read_elements, input.f90:1434-1583); etype may be NULL */
+int pf_read_d_mat(const char *job, int64_t nn, int64_t nels, int nod,
+                  double *g_coord /*(3,nn)*/, int32_t *g_num /*(nod,nels)*/, int32_t *etype /*(nels)*/);
+/* <job>.mat (read_material input.f90:3067-3102): prop(nprops,np_types) */
+int pf_read_mat(const char *job, int nprops, int np_types, double *prop);
 int pf_read_d(const char *job, int64_t nn, int64_t nels, int nod,
               double *g_coord /*(3,nn)*/, int32_t *g_num /*(nod,nels)*/);
 int pf_read_bnd(const char *job, int64_t nr, int nodof, int32_t *rest);

@@ -99,6 +99,16 @@ def form_km_elastic(g_coord_pp, nod, nip, e, v):
     return out
 
 
+def form_km_elastic_mat(g_coord_pp, nod, nip, prop, etype):
+    """xx2.f90:169-193: e, v = prop(:, etype(iel)) per element (prop (np_types, 2), etype 1-based)."""
+    g, et = _f64(g_coord_pp), _i32(etype)
+    out = np.empty((g.shape[0], 3 * nod, 3 * nod))
+    for m in np.unique(et):
+        sel = np.flatnonzero(et == m)
+        out[sel] = form_km_elastic(g[sel], nod, nip, float(prop[m - 1][0]), float(prop[m - 1][1]))
+    return out
+
+
 def form_kc_laplace(g_coord_pp, nip, kx, ky, kz):
     g = _f64(g_coord_pp)
     nels = g.shape[0]

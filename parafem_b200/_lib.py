@@ -28,7 +28,9 @@ class DeckInfo(C.Structure):
     _fields_ = [("program", c_int), ("meshgen", c_int), ("partitioner", c_int), ("nip", c_int),
                 ("nod", c_int), ("limit", c_int), ("nels", c_i64), ("nn", c_i64), ("nr", c_i64),
                 ("loaded", c_i64), ("fixed", c_i64), ("nres", c_i64), ("e", c_dbl), ("v", c_dbl),
-                ("kx", c_dbl), ("ky", c_dbl), ("kz", c_dbl), ("tol", c_dbl)]
+                ("kx", c_dbl), ("ky", c_dbl), ("kz", c_dbl), ("tol", c_dbl),
+                ("np_types", c_int), ("nstep", c_int), ("npri", c_int), ("pad_", c_int),
+                ("val0", c_dbl), ("dtim", c_dbl), ("theta", c_dbl)]
 
 
 P = C.POINTER
@@ -43,6 +45,7 @@ SIGNATURES = {
     "pf_setup_mesh": (c_int, [vp, c_int, c_int, c_int, c_i64, vp, vp, c_i64, c_i64, c_i64]),
     "pf_form_km_elastic": (c_int, [vp, c_dbl, c_dbl]),
     "pf_form_kc_laplace": (c_int, [vp, c_dbl, c_dbl, c_dbl]),
+    "pf_form_km_elastic_mat": (c_int, [vp, c_int, vp, vp]),
     "pf_set_storkm": (c_int, [vp, vp]),
     "pf_get_storkm": (c_int, [vp, c_i64, c_i64, vp]),
     "pf_set_matrix_free": (c_int, [vp, c_int]),
@@ -88,6 +91,8 @@ SIGNATURES = {
     "pf_abaqus2sg": (c_int, [c_int, c_i64, vp]),
     "pf_read_dat": (c_int, [C.c_char_p, c_int, P(DeckInfo)]),
     "pf_read_d": (c_int, [C.c_char_p, c_i64, c_i64, c_int, vp, vp]),
+    "pf_read_d_mat": (c_int, [C.c_char_p, c_i64, c_i64, c_int, vp, vp, vp]),
+    "pf_read_mat": (c_int, [C.c_char_p, c_int, c_int, vp]),
     "pf_read_bnd": (c_int, [C.c_char_p, c_i64, c_int, vp]),
     "pf_read_lds": (c_int, [C.c_char_p, c_i64, c_int, vp, vp]),
     "pf_coords_pp": (c_int, [c_int, c_i64, vp, vp, vp]),

@@ -921,6 +921,39 @@ int pf_form_km_elastic(pf_handle h, double e, double v) {
   return 0;
 }
 
+// xx2.f90:169-193: as pf_form_km_elastic with e, v = prop(:,etype_pp(iel)) per element
+int pf_form_km_elastic_mat(pf_handle h, int np_types, const double *prop, const int32_t *etype_pp) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_mesh && h->nodof == 3, "needs pf_setup_mesh with nodof = 3");
+  NEED(!h->matrix_free, "the matrix-free variant takes one material (pf_form_km_elastic)");
+  NEED(np_types >= 1 && prop && etype_pp, "np_types >= 1, prop(2,np_types) and etype_pp(nels_pp) are required");
+  for (int64_t e = 0; e < h->nels; ++e)
+    if (etype_pp[e] < 1 || etype_pp[e] > np_types) return fail(h, 4, "pf_form_km_elastic_mat: etype_pp(%lld) = %d outside 1..%d",
+                                                               (long long)e + 1, etype_pp[e], np_types);
+  h->transient = false; h->kb.release();
+  ElemTables T;
+  std::vector<double> dees((size_t)np_types * 36);
+  for (int m = 0; m < np_types; ++m) {           // deemat(e,v,dee) per material (xx2.f90:176-180)
+    if (fill_tables(h->nod, h->nip, prop[2 * m], prop[2 * m + 1], 0, 0, 0, T)) return fail(h, 3, "unsupported nod/nip");
+    memcpy(&dees[(size_t)m * 36], T.dee, sizeof T.dee);
+  }
+  CU(cudaMemcpyToSymbol(c_tab, &T, sizeof T));
+  DevBuf<double> d_dee; DevBuf<int> d_etype;
+  CU(d_dee.alloc(dees.size())); CU(d_etype.alloc((size_t)h->nels));
+  CU(cudaMemcpy(d_dee.p, dees.data(), dees.size() * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d_etype.p, etype_pp, (size_t)h->nels * 4, cudaMemcpyHostToDevice));
+  if ((rc = alloc_km(h))) return rc;
+  const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 16);
+  if (h->nod == 20) k_form_km_elastic<20, 128, true><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, nullptr, h->km_layout, d_dee.p, d_etype.p);
+  else k_form_km_elastic<8, 64, true><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, nullptr, h->km_layout, d_dee.p, d_etype.p);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  d_dee.release(); d_etype.release();
+  h->have_km = true; h->have_precon = false;
+  return 0;
+}
+
 int pf_form_kc_laplace(pf_handle h, double kx, double ky, double kz) {
   int rc = need_device(h); if (rc) return rc;
   h->transient = false; h->kb.release();

@@ -401,11 +401,81 @@ int pf_read_dat(const char *job, int program, pf_deck_info *info) {
     info->fixed = (int64_t)v[8];
     info->kx = v[9]; info->ky = v[10]; info->kz = v[11]; info->tol = v[12];
     info->limit = (int)v[13]; info->nres = (int64_t)v[14];
+  } else if (program == 124) {
+    // read_p124 (input.f90:3997-4169): element, mesh, partition, np_types / nels nn nr nip nod loaded fixed /
+    // val0 / dtim nstep npri theta / tol limit nres   (p12meshgen.f90:975-987)
+    if (v.size() < 18) return 2;
+    info->meshgen = (int)v[0]; info->partitioner = (int)v[1]; info->np_types = (int)v[2];
+    info->nels = (int64_t)v[3]; info->nn = (int64_t)v[4]; info->nr = (int64_t)v[5];
+    info->nip = (int)v[6]; info->nod = (int)v[7]; info->loaded = (int64_t)v[8]; info->fixed = (int64_t)v[9];
+    info->val0 = v[10]; info->dtim = v[11]; info->nstep = (int)v[12]; info->npri = (int)v[13]; info->theta = v[14];
+    info->tol = v[15]; info->limit = (int)v[16]; info->nres = (int64_t)v[17];
+  } else if (program == 2) {
+    // read_xx2 (input.f90:5391-5562): element, mesh, partition, np_types, nels nn nr nip nod loaded_nodes
+    // fixed_freedoms, tol limit
+    if (v.size() < 12) return 2;
+    info->meshgen = (int)v[0]; info->partitioner = (int)v[1]; info->np_types = (int)v[2];
+    info->nels = (int64_t)v[3]; info->nn = (int64_t)v[4]; info->nr = (int64_t)v[5];
+    info->nip = (int)v[6]; info->nod = (int)v[7]; info->loaded = (int64_t)v[8]; info->fixed = (int64_t)v[9];
+    info->tol = v[10]; info->limit = (int)v[11];
   } else return 3;
   return 0;
 }
 
 int pf_read_d(const char *job, int64_t nn, int64_t nels, int nod, double *g_coord, int32_t *g_num) {
+  return pf_read_d_mat(job, nn, nels, nod, g_coord, g_num, nullptr);
+}
+
+// <job>.mat: read_material / read_materialValue (input.f90:3067-3102, 2789-2824) expect
+// "*MATERIAL nmats nvals" / a name line / nmats lines "id v_1 .. v_nvals"; the shipped xx2-tiny.mat
+// predates the header: a line with the material count, then the nmats lines.  Both are accepted.
+// prop(nprops,np_types).
+int pf_read_mat(const char *job, int nprops, int np_types, double *prop) {
+  FILE *f = fopen((std::string(job) + ".mat").c_str(), "r");
+  if (!f) return 1;
+  char line[1024];
+  int got = 0, rc = 0;
+  bool header = false, first = true;
+  while (got < np_types && fgets(line, sizeof line, f)) {
+    char *q = line;
+    while (*q == ' ' || *q == '\t') ++q;
+    if (*q == '\n' || *q == 0) continue;
+    if (first) {
+      first = false;
+      if (*q == '*') {                       // keyword nmats nvals, then one line to skip
+        char kw[64]; int nm = 0, nv = 0;
+        if (sscanf(q, "%63s %d %d", kw, &nm, &nv) != 3 || nm < np_types || nv != nprops) { rc = 2; break; }
+        header = true;
+        if (!fgets(line, sizeof line, f)) { rc = 3; break; }
+        continue;
+      }
+    }
+    char *end = nullptr;
+    strtol(q, &end, 10);                     // material number
+    if (end == q) { rc = 4; break; }
+    {                                        // a lone integer on the line = the material count of the old format
+      char *r = end;
+      while (*r == ' ' || *r == '\t' || *r == '\r') ++r;
+      if (*r == '\n' || *r == 0) continue;
+    }
+    for (int k = 0; k < nprops; ++k) {
+      char *e2 = nullptr;
+      const double val = strtod(end, &e2);
+      if (e2 == end) { rc = 5; break; }
+      prop[(size_t)got * nprops + k] = val; end = e2;
+    }
+    if (rc) break;
+    ++got;
+  }
+  (void)header;
+  fclose(f);
+  if (!rc && got != np_types) rc = 6;
+  return rc;
+}
+
+// read_elements (input.f90:1434-1583): as pf_read_d, and the material number of every element
+// (last column of the element lines) into etype (may be NULL)
+int pf_read_d_mat(const char *job, int64_t nn, int64_t nels, int nod, double *g_coord, int32_t *g_num, int32_t *etype) {
   FILE *f = fopen((std::string(job) + ".d").c_str(), "r");
   if (!f) return 1;
   char word[256];
@@ -425,6 +495,7 @@ int pf_read_d(const char *job, int64_t nn, int64_t nels, int nod, double *g_coor
       g_num[e * nod + m] = (int32_t)v;
     }
     if (!rc && fscanf(f, "%lld", &v) != 1) rc = 7;  // material id
+    if (!rc && etype) etype[e] = (int32_t)v;
   }
   fclose(f);
   return rc;

@@ -839,18 +839,25 @@ __device__ __forceinline__ double gauss_point(int ig, const double *s_coord, dou
 }
 
 // elements_1 of p121.f90:56-64.  km(i,j) += (sum_k btd(i,k)*bee(k,j)) * det * w
-template <int NOD, int THREADS>
+// MAT: one dee per material (xx2.f90:176-180: e, v = prop(:,etype_pp(iel))), dee_tab (36, np_types) in global
+// memory and etype 1-based; otherwise the single dee of p121 in constant memory.
+template <int NOD, int THREADS, bool MAT = false>
 __global__ void __launch_bounds__(THREADS)
 k_form_km_elastic(const double *__restrict__ g_coord, double *__restrict__ km, long long nels,
                   double *__restrict__ diag_only /* matrix-free: (ntot,nels) diagonal instead of km */,
-                  int packed /* 1: lower triangle only, packed by columns (SymCfg) */) {
+                  int packed /* 1: lower triangle only, packed by columns (SymCfg) */,
+                  const double *__restrict__ dee_tab = nullptr, const int *__restrict__ etype = nullptr) {
   constexpr int NTOT = 3 * NOD, NENT = NTOT * NTOT, PER = (NENT + THREADS - 1) / THREADS;
   __shared__ double s_coord[NOD * 3], s_jac[9], s_deriv[NOD * 3];
   __shared__ double s_bee[6 * NTOT];  // bee(l,c) at [c*6+l]
   __shared__ double s_btd[6 * NTOT];  // btd(i,k) at [k*NTOT+i]
+  __shared__ double s_dee[MAT ? 36 : 1];
   for (long long e = blockIdx.x; e < nels; e += gridDim.x) {
     __syncthreads();
     for (int q = threadIdx.x; q < NOD * 3; q += THREADS) s_coord[q] = g_coord[e * NOD * 3 + q];
+    if constexpr (MAT) {
+      if (threadIdx.x < 36) s_dee[threadIdx.x] = dee_tab[(long long)(etype[e] - 1) * 36 + threadIdx.x];
+    }
     double acc[PER];
 #pragma unroll
     for (int n = 0; n < PER; ++n) acc[n] = 0.0;
@@ -875,7 +882,10 @@ k_form_km_elastic(const double *__restrict__ g_coord, double *__restrict__ km, l
         const int k = q / NTOT, i = q - k * NTOT;
         double s = 0.0;
 #pragma unroll
-        for (int l = 0; l < 6; ++l) s = s + s_bee[i * 6 + l] * c_tab.dee[k * 6 + l];
+        for (int l = 0; l < 6; ++l) {
+          if constexpr (MAT) s = s + s_bee[i * 6 + l] * s_dee[k * 6 + l];
+          else s = s + s_bee[i * 6 + l] * c_tab.dee[k * 6 + l];
+        }
         s_btd[k * NTOT + i] = s;
       }
       __syncthreads();

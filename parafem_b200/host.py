@@ -73,6 +73,9 @@ class Problem:
     no_f: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))   # fixed eq (global)
     val_f: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float64))
     total_load: float = 0.0
+    # xx2: per-element materials -- prop (np_types, 2) = (e, v), etype_pp (nels_pp) 1-based; None = one material
+    prop: np.ndarray = None
+    etype_pp: np.ndarray = None
     # p124 (transient conduction): rho, cp, theta method, time stepping, initial value, print interval
     rho: float = 1.0
     cp: float = 1.0
@@ -231,6 +234,45 @@ def read_deck_p121(job, npes=1, numpe=1):
                 total_load=float(val.sum()))
     p.rest = rest
     p.g_coord = g_coord
+    return p
+
+
+def read_deck_xx2(job, npes=1, numpe=1):
+    """Input section of programs/dev/xx2/xx2.f90:60-160 for one rank: read_xx2, read_elements (connectivity +
+    material number of every element), abaqus2sg, read_g_coord_pp, read_rest, read_materialValue, steering,
+    read_loads + load.  -> Problem(program 121) with prop / etype_pp set."""
+    L = lib()
+    info = DeckInfo()
+    check(L.pf_read_dat(job.encode(), 2, C.byref(info)), what="pf_read_dat")
+    nod, nn, nels, nr, loaded = info.nod, info.nn, info.nels, info.nr, info.loaded
+    if info.fixed:
+        raise PfError("xx2 decks with fixed_freedoms > 0: pass no_f / val_f to Solver.build_precon yourself")
+    g_coord = np.empty((nn, 3), np.float64)
+    g_num = np.empty((nels, nod), np.int32)
+    etype = np.empty(nels, np.int32)
+    check(L.pf_read_d_mat(job.encode(), nn, nels, nod, ptr(g_coord), ptr(g_num), ptr(etype)), what="pf_read_d_mat")
+    if info.meshgen == 2:
+        check(L.pf_abaqus2sg(nod, nels, ptr(g_num)), what="pf_abaqus2sg")
+    nels_pp, iel_start = read_psize(job, npes, numpe) if info.partitioner == 2 else calc_nels_pp(nels, npes, numpe)
+    g_num_pp = np.ascontiguousarray(g_num[iel_start - 1:iel_start - 1 + nels_pp])
+    g_coord_pp = np.empty((nels_pp, 3, nod), np.float64)
+    check(L.pf_coords_pp(nod, nels_pp, ptr(g_num_pp), ptr(g_coord), ptr(g_coord_pp)), what="pf_coords_pp")
+    rest = np.zeros((4, nr), np.int32)
+    check(L.pf_read_bnd(job.encode(), nr, 3, ptr(rest)), what="pf_read_bnd")
+    prop = np.empty((info.np_types, 2), np.float64)
+    check(L.pf_read_mat(job.encode(), 2, info.np_types, ptr(prop)), what="pf_read_mat")
+    nf, g_g, neq = _steer(nn, 3, rest, g_num_pp, nod)
+    neq_pp, ieq_start = calc_neq_pp(neq, npes, numpe)
+    node = np.empty(loaded, np.int32)
+    val = np.empty((loaded, 3), np.float64)
+    check(L.pf_read_lds(job.encode(), loaded, 3, ptr(node), ptr(val)), what="pf_read_lds")
+    r = np.empty(neq_pp, np.float64)
+    check(L.pf_load(3, loaded, ptr(node), ptr(val), ptr(nf), ieq_start, neq_pp, ptr(r)), what="pf_load")
+    p = Problem(121, nod, 3, info.nip, nels, nn, nr, neq, npes, numpe, nels_pp, iel_start, neq_pp, ieq_start,
+                g_num_pp, g_coord_pp, g_g, nf, r, tol=info.tol, limit=info.limit, total_load=float(val.sum()))
+    p.prop = prop
+    p.etype_pp = np.ascontiguousarray(etype[iel_start - 1:iel_start - 1 + nels_pp])
+    p.rest, p.g_coord = rest, g_coord
     return p
 
 

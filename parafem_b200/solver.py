@@ -58,6 +58,12 @@ class Solver:
     def form_km_elastic(self, e, v):
         self._ck(lib().pf_form_km_elastic(self._h, e, v), "pf_form_km_elastic")
 
+    def form_km_elastic_mat(self, prop, etype_pp):
+        """xx2.f90:169-193: prop (np_types, 2) = (e, v) per material, etype_pp 1-based material of each element."""
+        pr, et = f64(prop), i32(etype_pp)
+        assert pr.ndim == 2 and pr.shape[1] == 2 and et.size == self.prob.nels_pp
+        self._ck(lib().pf_form_km_elastic_mat(self._h, pr.shape[0], ptr(pr), ptr(et)), "pf_form_km_elastic_mat")
+
     def form_kc_laplace(self, kx, ky, kz):
         self._ck(lib().pf_form_kc_laplace(self._h, kx, ky, kz), "pf_form_kc_laplace")
 
@@ -224,8 +230,14 @@ def setup_problem(solver, prob, matrix_free=False, layout=0):
     solver.set_matrix_free(matrix_free)
     solver.set_storkm_layout(layout)
     if prob.program == 121:
-        solver.form_km_elastic(prob.e, prob.v)
-        solver.build_precon()
+        if prob.prop is not None:           # per-element materials (xx2)
+            solver.form_km_elastic_mat(prob.prop, prob.etype_pp)
+        else:
+            solver.form_km_elastic(prob.e, prob.v)
+        solver.build_precon(prob.no_f if prob.no_f.size else None, 1e20)
+        if prob.no_f.size:
+            # r_pp(j) = store_pp(i)*valf(k)   (xx2.f90:294-300)
+            prob.r_pp[prob.no_f - prob.ieq_start] = solver.store() * prob.val_f
     elif prob.program == 124:
         solver.form_k_transient(prob.kx, prob.ky, prob.kz, prob.rho, prob.cp, prob.theta, prob.dtim)
         solver.build_precon(prob.no_f, 1e20)

@@ -40,6 +40,23 @@ def golden(tmp_path_factory, _built):
     host.write_deck_p121(os.path.join(d, "xx3-tiny"), 20, 8, 100.0, 0.3, 1e-5, 200, a["tiny_coord"], a["tiny_gnum_sg"],
                          a["tiny_rest"], a["tiny_lds_node"], a["tiny_lds_val"])
     open(xx3_dat, "w").write(keep)
+    # xx2-tiny = the same mesh, restraints and loads with five materials: the element lines of the .d carry
+    # the material number in their last column; .dat / .mat as shipped
+    x2 = os.path.join(d, "xx2-tiny")
+    keep2 = open(x2 + ".dat").read()
+    host.write_deck_p121(x2, 20, 8, 100.0, 0.3, 1e-5, 200, a["tiny_coord"], a["tiny_gnum_sg"], a["tiny_rest"],
+                         a["tiny_lds_node"], a["tiny_lds_val"])
+    open(x2 + ".dat", "w").write(keep2)
+    body = open(x2 + ".d").read().splitlines()
+    k0 = body.index("*ELEMENTS") + 1
+    for e, m in enumerate(a["xx2_etype"]):
+        assert body[k0 + e].endswith(" 1")
+        body[k0 + e] = body[k0 + e][:-1] + str(int(m))
+    open(x2 + ".d", "w").write("\n".join(body) + "\n")
+    with open(x2 + ".dis", "w") as f:
+        f.write("*DISPLACEMENT\n           1\n")
+        for i, u in enumerate(a["xx2_dis"]):
+            f.write(f"{i + 1:8d} {u[0]: .4E} {u[1]: .4E} {u[2]: .4E}\n")
     with open(os.path.join(d, "xx3-tiny.dis"), "w") as f:
         f.write("*DISPLACEMENT\n           1\n")
         for i, u in enumerate(a["tiny_dis"]):
@@ -57,6 +74,12 @@ def golden(tmp_path_factory, _built):
 def tiny(golden):
     from parafem_b200 import host
     return host.read_deck_p121(os.path.join(golden, "xx3-tiny"))
+
+
+@pytest.fixture(scope="session")
+def tiny_xx2(golden):
+    from parafem_b200 import host
+    return host.read_deck_xx2(os.path.join(golden, "xx2-tiny"))
 
 
 @pytest.fixture(scope="session")

@@ -10,6 +10,8 @@ are parsed and packed:
   p121_demo_digests.json   SHA-256 of the parsed 4 MB p121_demo.d / .bnd arrays (the in-memory
                   generator must reproduce them)
   p121_demo_ensi_head.txt  the first 204 lines of the 107 167-line EnSight golden (format check)
+  (arrays.npz also holds xx2-tiny's material numbers, material table and golden displacements; its mesh,
+  restraints and loads are xx3-tiny's, asserted here)
   p124_demo_digests.json   SHA-256 of the parsed p124_demo.d / .bnd arrays (25^3 8-node bricks); arrays.npz
                   also holds three of the sixteen golden nodal temperature files (steps 10, 80, 150;
                   float32 of the 5-digit values) and fixtures.json the p124 logs / control files
@@ -51,6 +53,12 @@ def main():
     dval = np.empty((65, 3))
     assert lib().pf_read_lds(demo.encode(), 65, 3, ptr(dnode), ptr(dval)) == 0
     disp = np.loadtxt(demo + ".ensi.DISPL-000001", skiprows=4)
+    # xx2-tiny: the xx3-tiny mesh with five materials (per-element e, v) -- 59 iterations
+    x2 = f"{REF}/dev/xx2/xx2-tiny"
+    t2 = host.read_deck_xx2(x2)
+    assert np.array_equal(t2.g_num_pp, t.g_num_pp) and np.array_equal(t2.g_coord, t.g_coord) and np.array_equal(t2.rest, t.rest)
+    assert np.array_equal(t2.r_pp, t.r_pp)
+    xx2 = dict(xx2_etype=t2.etype_pp, xx2_prop=t2.prop, xx2_dis=np.loadtxt(x2 + ".dis", skiprows=2)[:, 1:])
     # p124 demo deck (transient conduction, 25^3 8-node bricks, Abaqus node order on disk)
     d124 = f"{REF}/5th_ed/p124/demo/p124_demo"
     dat = open(d124 + ".dat").read().split()
@@ -68,7 +76,7 @@ def main():
                    nod=nod4), open(f"{HERE}/p124_demo_digests.json", "w"), indent=1)
     ndttr = {f"p124_ndttr_{j:03d}": np.loadtxt(f"{d124}.ensi.NDTTR-{j:06d}", skiprows=4).astype(np.float32)
              for j in (10, 80, 150)}
-    np.savez_compressed(f"{HERE}/arrays.npz", **ndttr, tiny_coord=t.g_coord, tiny_gnum_sg=t.g_num_pp, tiny_rest=t.rest,
+    np.savez_compressed(f"{HERE}/arrays.npz", **ndttr, **xx2, tiny_coord=t.g_coord, tiny_gnum_sg=t.g_num_pp, tiny_rest=t.rest,
                         tiny_lds_node=node, tiny_lds_val=val, tiny_dis=dis, demo_lds_node=dnode, demo_lds_val=dval,
                         demo_displ=disp.reshape(3, p.nn).T.astype(np.float32))
     texts = {
@@ -76,6 +84,7 @@ def main():
         "p121_demo.res": lines(demo + ".res"), "p121_demo.dat": lines(demo + ".dat"), "p121_demo.mg": lines(demo + ".mg"),
         "p121_book.res": lines(f"{REF}/5th_ed/p121/book/p121.res"), "p121_book.mg": lines(f"{REF}/5th_ed/p121/book/p121.mg"),
         "p123_book.res": lines(f"{REF}/5th_ed/p123/book/p123.res"), "p123_book.mg": lines(f"{REF}/5th_ed/p123/book/p123.mg"),
+        "xx2-tiny.res": lines(x2 + ".res"), "xx2-tiny.dat": lines(x2 + ".dat"), "xx2-tiny.mat": lines(x2 + ".mat"),
         "p124_demo.res": lines(d124 + ".res"), "p124_demo.dat": lines(d124 + ".dat"), "p124_demo.mat": lines(d124 + ".mat"),
         "p124_book.res": lines(f"{REF}/5th_ed/p124/book/p124.res"), "p124_book.mg": lines(f"{REF}/5th_ed/p124/book/p124.mg"),
         "p124_tiny.mg": lines(f"{REF}/5th_ed/p124/mg/p124_tiny.mg"),

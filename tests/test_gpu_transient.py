@@ -70,19 +70,20 @@ def test_time_stepping_equals_oracle(gpu, name, fixed, source):
         assert ms > 0.0
 
 
-def test_cooling_is_monotone_and_bounded(gpu):
-    """Size-independent property: with the boundary held at 0 and no source the field stays inside [0, val0]
-    (up to the solver tolerance) and its maximum decays step by step."""
+def test_cooling_is_bounded_and_decays(gpu):
+    """Size-independent property: boundary held at 0, no source.  theta = 0.5 (Crank-Nicolson) rings after the
+    discontinuous start -- negative temperatures next to the boundary are the reference's own behaviour (the
+    oracle shows -67 at step 2 on this box) -- but the field stays inside [-val0, val0] and its maximum decays."""
     p = host.cube_p124(20, 20, 20, nstep=30)
     solver.setup_problem(gpu, p)
     gpu.transient_start(p.val0)
-    last = p.val0
+    last = p.val0 * (1 + 1e-4)
     for _ in range(p.nstep):
         it, conv, _ = gpu.transient_step(p.tol, p.limit)
         x = gpu.pcg_get_x()
-        assert conv and x.min() > -1e-2 * p.val0 and x.max() <= last * (1 + 1e-3)
+        assert conv and np.abs(x).max() <= p.val0 * (1 + 1e-3) and x.max() <= last * (1 + 1e-3)
         last = x.max()
-    assert last < p.val0
+    assert last < 0.3 * p.val0          # oracle: 23.96 after 30 steps
 
 
 def _golden_rows(path):
@@ -135,9 +136,13 @@ def test_p124_book_size(gpu):
     it10 = [r[2] for r in res["rows"][1:]]
     temps = [r[1] for r in res["rows"][1:]]
     ORACLE_ITERS = [43, 36, 25, 23, 21, 20, 21, 20, 20, 20]
-    ORACLE_TEMPS = [89.408, 49.325, 23.961, 11.474, 5.4767, 2.6121, 1.2451, 0.59271, 0.28103, 0.13134]
+    ORACLE_TEMPS = [89.40804605854989, 49.32539246531203, 23.96065667504979, 11.473649552351398, 5.476709837171172,
+                    2.612114502404774, 1.2450951898330878, 0.5927098036075268, 0.28103067311629465, 0.13134409525010568]
     assert all(abs(a - b) <= 1 for a, b in zip(it10, ORACLE_ITERS)), it10
-    assert np.allclose(temps, ORACLE_TEMPS, rtol=2e-4), temps
+    assert np.allclose(temps, ORACLE_TEMPS, rtol=1e-9), temps     # same summation order: equal in practice
+    assert np.allclose(res["x"][:8], [-11.1812433649001, -11.181242208333845, -11.181238908699843, -11.181233931362732,
+                                      -11.181228038030893, -11.181221976029208, -11.181216863363865,
+                                      -11.181213537466169], rtol=1e-9)
 
 
 def test_transient_api_errors(gpu):

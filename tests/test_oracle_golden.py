@@ -217,3 +217,42 @@ def test_p124_transient_matrices_properties():
     assert np.allclose(a - b, kc * 0.01, rtol=0, atol=1e-16)
     lap = oracle.form_kc_laplace(p.g_coord_pp, 8, 1.5, 2.0, 0.5)
     assert np.allclose(kc, lap, rtol=1e-12, atol=1e-15)       # same operator as p123's kcx*kx+kcy*ky+kcz*kz
+
+
+# ---- xx2: per-element materials ---------------------------------------------------
+
+def test_xx2_tiny_deck_and_readers(tiny_xx2, tiny, golden):
+    """read_xx2 / read_elements / read_materialValue restated in host.cpp: five materials of 25 elements
+    each on the xx3-tiny mesh; the old-format .mat (count line + rows) and the header format both parse."""
+    p = tiny_xx2
+    assert (p.nels, p.nn, p.nr, p.neq, p.nod, p.nip) == (125, 756, 396, 1640, 20, 8)
+    assert np.array_equal(np.bincount(p.etype_pp), [0, 25, 25, 25, 25, 25])
+    assert np.array_equal(p.prop, [[500., .15], [1000., .2], [1500., .25], [2000., .3], [3000., .35]])
+    assert np.array_equal(p.g_g_pp, tiny.g_g_pp) and np.array_equal(p.r_pp, tiny.r_pp)
+    from parafem_b200._lib import lib, ptr
+    job = os.path.join(golden, "xx2-header")
+    with open(job + ".mat", "w") as f:       # what read_material (input.f90:3067-3102) expects today
+        f.write("*MATERIAL    2    2\n<edit material_name>\n 1  0.5000E+03  0.1500E+00\n 2  0.1000E+04  0.2000E+00\n")
+    prop = np.empty((2, 2))
+    assert lib().pf_read_mat(job.encode(), 2, 2, ptr(prop)) == 0
+    assert np.array_equal(prop, [[500., .15], [1000., .2]])
+    assert lib().pf_read_mat(job.encode(), 3, 2, ptr(prop)) != 0          # nvals mismatch is an error
+
+
+@pytest.mark.parametrize("red_mode,npes,slack", [(0, 1, 0), (0, 2, 0), (1, 1, 2), (1, 2, 2)])
+def test_xx2_tiny_iterations_and_displacements(tiny_xx2, golden, red_mode, npes, slack):
+    """examples/dev/xx2/xx2-tiny.res (2 ranks): 1640 equations, 59 PCG iterations, total load -100; .dis to the
+    5 digits it prints.  Sequential reductions reproduce 59 exactly; the blocked tree (the GPU's order) 57-58."""
+    p = tiny_xx2
+    res = os.path.join(golden, "xx2-tiny.res")
+    assert res_int(res, r"Number of equations solved\s+(\d+)") == p.neq
+    gold_iters = res_int(res, r"Number of PCG iterations\s+(\d+)")
+    assert gold_iters == 59 and abs(p.total_load + 100.0) < 1e-5
+    km = oracle.form_km_elastic_mat(p.g_coord_pp, p.nod, p.nip, p.prop, p.etype_pp)
+    r = oracle.pcg(km, p.g_g_pp, p.neq, p.r_pp, p.tol, p.limit, npes=npes, red_mode=red_mode)
+    assert r["converged"] and abs(r["iters"] - gold_iters) <= slack
+    dis = np.loadtxt(os.path.join(golden, "xx2-tiny.dis"), skiprows=2)[:, 1:]
+    u = np.zeros((p.nn, 3))
+    m = p.nf > 0
+    u[m] = r["x"][p.nf[m] - 1]
+    assert np.abs(u - dis).max() < 1e-5                  # 5 significant digits, max|u| 0.13
