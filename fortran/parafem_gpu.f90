@@ -75,6 +75,17 @@ MODULE parafem_gpu
       INTEGER(c_int),VALUE :: limit; INTEGER(c_int) :: iters,converged; REAL(c_double) :: elapsed_ms
     END FUNCTION
 
+    ! p125 (explicit transient conduction): store_pm_pp / globma_pp of p125.f90:66-82, then nsteps passes of :94-99
+    INTEGER(c_int) FUNCTION pf_form_k_explicit(h,kx,ky,kz,dtim) BIND(C,name='pf_form_k_explicit')
+      IMPORT; TYPE(c_ptr),VALUE :: h; REAL(c_double),VALUE :: kx,ky,kz,dtim
+    END FUNCTION
+    INTEGER(c_int) FUNCTION pf_explicit_start(h,val0) BIND(C,name='pf_explicit_start')
+      IMPORT; TYPE(c_ptr),VALUE :: h; REAL(c_double),VALUE :: val0
+    END FUNCTION
+    INTEGER(c_int) FUNCTION pf_explicit_steps(h,nsteps,elapsed_ms) BIND(C,name='pf_explicit_steps')
+      IMPORT; TYPE(c_ptr),VALUE :: h; INTEGER(c_int),VALUE :: nsteps; REAL(c_double) :: elapsed_ms
+    END FUNCTION
+
     ! alternative: upload a host storkm_pp (xx3.f90:440-452)
     INTEGER(c_int) FUNCTION pf_set_storkm(h,storkm_pp) BIND(C,name='pf_set_storkm')
       IMPORT; TYPE(c_ptr),VALUE :: h; REAL(c_double) :: storkm_pp(*)

@@ -160,6 +160,18 @@ int pf_transient_start(pf_handle h, double val0, const double *val_f_pp);
 int pf_transient_step(pf_handle h, const double *loads_pp, double tol, int limit, int *iters,
                       int *converged, double *elapsed_ms);
 
+/* --- explicit transient conduction: program p125 ------
+ * The gather / mat-vec / scatter kernels without a solver: forward Euler with a lumped mass.
+ * pf_form_k_explicit: elements_1 of p125.f90:66-82 for 8-node bricks: store_pm_pp = diag(mass) - kc*dtim
+ *   with mass(i) = SUM(pm(i,:)) (pf_get_storkm returns it) and globma_pp = 1/scatter(mass)
+ *   (pf_get_diag_precon returns it).
+ * pf_explicit_start: loads_pp = val0 (p125.f90:83).
+ * pf_explicit_steps: nsteps passes of p125.f90:94-99, loads_pp = scatter(store_pm*gather(loads_pp))*globma_pp,
+ *   resident on the device; pf_pcg_get_x reads the field; elapsed_ms on the solver stream.              */
+int pf_form_k_explicit(pf_handle h, double kx, double ky, double kz, double dtim);
+int pf_explicit_start(pf_handle h, double val0);
+int pf_explicit_steps(pf_handle h, int nsteps, double *elapsed_ms);
+
 /* --- fine-grained entry points (kernel-level parity tests) --------------
  * Same argument meaning as the reference routines they replace:
  *   pf_gather  = gather(p_pp,pmul_pp)            gather_scatter.f90:547-688

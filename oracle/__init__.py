@@ -266,3 +266,27 @@ def p124(storka, storkb, g_g, neq, val0, nstep, tol, limit, npes=1, red_mode=0, 
         if j in keep:
             fields[j] = x.copy()
     return dict(iters=iters, converged=conv, x=x, fields=fields)
+
+
+def form_k_explicit(g_coord_pp, nip, kx, ky, kz, dtim):
+    """p125.f90:66-79: (store_pm (nels,8,8), mass (nels,8)); mass(i) = SUM(pm(i,:)), j ascending."""
+    _, _, kc, pm = form_k_transient(g_coord_pp, nip, kx, ky, kz, 1.0, 1.0, 0.5, dtim, raw=True)
+    mass = 0.0 + pm[:, 0, :]
+    for j in range(1, 8):
+        mass = mass + pm[:, j, :]
+    store = 0.0 - kc * dtim
+    idx = np.arange(8)
+    store[:, idx, idx] = mass - kc[:, idx, idx] * dtim
+    return store, mass
+
+
+def p125(store_pm, mass, g_g, neq, val0, nstep, npes=1, keep=()):
+    """The recursion of p125.f90:82-99: globma = 1/scatter(mass); loads = scatter(store_pm*gather(loads))*globma."""
+    globma = 1.0 / scatter(g_g, mass, neq, npes)
+    x = np.full(neq, float(val0))
+    fields = {}
+    for j in range(1, nstep + 1):
+        x = apply(store_pm, g_g, neq, x, npes) * globma
+        if j in keep:
+            fields[j] = x.copy()
+    return dict(x=x, fields=fields, globma=globma)

@@ -62,6 +62,9 @@ SIGNATURES = {
     "pf_get_storkb": (c_int, [vp, c_i64, c_i64, vp]),
     "pf_transient_start": (c_int, [vp, c_dbl, vp]),
     "pf_transient_step": (c_int, [vp, vp, c_dbl, c_int, P(c_int), P(c_int), P(c_dbl)]),
+    "pf_form_k_explicit": (c_int, [vp, c_dbl, c_dbl, c_dbl, c_dbl]),
+    "pf_explicit_start": (c_int, [vp, c_dbl]),
+    "pf_explicit_steps": (c_int, [vp, c_int, P(c_dbl)]),
     "pf_gather": (c_int, [vp, vp, vp]),
     "pf_matvec": (c_int, [vp, vp, vp]),
     "pf_scatter": (c_int, [vp, vp, vp]),

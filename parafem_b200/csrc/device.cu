@@ -81,6 +81,7 @@ struct pf_ctx {
   DevBuf<double> kb, val_f;
   const double *mat_override = nullptr;
   bool transient = false, transient_first = false;
+  bool explicit_ = false;   // p125: km holds store_pm_pp, diag_ext the inverted lumped mass globma_pp
   int mf_mode = 0;
   int km_layout = 0;   // 0: storkm_pp(ntot,ntot,nels_pp) as the reference; 1: packed lower triangles (SymCfg)
   DevBuf<int> ggl;
@@ -767,6 +768,7 @@ int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp, con
   h->nels = nels_pp; h->neq = neq; h->ieq_start = ieq_start; h->neq_pp = neq_pp;
   h->have_km = h->have_precon = false;
   h->transient = h->transient_first = false; h->mat_override = nullptr; h->kb.release();
+  h->explicit_ = false;
 
   // gather table (make_ggl rebuilt from g_g_pp)
   const int64_t total = nels_pp * ntot;
@@ -888,7 +890,7 @@ static int alloc_km(pf_handle h) {
 
 int pf_form_km_elastic(pf_handle h, double e, double v) {
   int rc = need_device(h); if (rc) return rc;
-  h->transient = false; h->kb.release();
+  h->transient = false; h->explicit_ = false; h->kb.release();
   NEED(h->have_mesh && h->nodof == 3, "needs pf_setup_mesh with nodof = 3");
   ElemTables T;
   if (fill_tables(h->nod, h->nip, e, v, 0, 0, 0, T)) return fail(h, 3, "unsupported nod/nip");
@@ -930,7 +932,7 @@ int pf_form_km_elastic_mat(pf_handle h, int np_types, const double *prop, const 
   for (int64_t e = 0; e < h->nels; ++e)
     if (etype_pp[e] < 1 || etype_pp[e] > np_types) return fail(h, 4, "pf_form_km_elastic_mat: etype_pp(%lld) = %d outside 1..%d",
                                                                (long long)e + 1, etype_pp[e], np_types);
-  h->transient = false; h->kb.release();
+  h->transient = false; h->explicit_ = false; h->kb.release();
   ElemTables T;
   std::vector<double> dees((size_t)np_types * 36);
   for (int m = 0; m < np_types; ++m) {           // deemat(e,v,dee) per material (xx2.f90:176-180)
@@ -956,7 +958,7 @@ int pf_form_km_elastic_mat(pf_handle h, int np_types, const double *prop, const 
 
 int pf_form_kc_laplace(pf_handle h, double kx, double ky, double kz) {
   int rc = need_device(h); if (rc) return rc;
-  h->transient = false; h->kb.release();
+  h->transient = false; h->explicit_ = false; h->kb.release();
   NEED(h->have_mesh && h->nodof == 1 && h->nod == 8, "needs pf_setup_mesh with nod = 8, nodof = 1");
   ElemTables T;
   if (fill_tables(h->nod, h->nip, 0, 0, kx, ky, kz, T)) return fail(h, 3, "unsupported nod/nip");
@@ -1067,11 +1069,86 @@ int pf_transient_step(pf_handle h, const double *loads_pp, double tol, int limit
   return 0;
 }
 
+// ---- p125: explicit transient conduction (forward Euler with a lumped mass) ----
+int pf_form_k_explicit(pf_handle h, double kx, double ky, double kz, double dtim) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_mesh && h->nodof == 1 && h->nod == 8, "needs pf_setup_mesh with nod = 8, nodof = 1");
+  NEED(h->km_layout == 0 && !h->matrix_free, "store_pm_pp uses the reference storkm layout");
+  h->transient = false; h->kb.release();
+  ElemTables T;
+  if (fill_tables(h->nod, h->nip, 0, 0, kx, ky, kz, T)) return fail(h, 3, "unsupported nod/nip");
+  T.trans[3] = dtim;
+  CU(cudaMemcpyToSymbol(c_tab, &T, sizeof T));
+  if ((rc = alloc_km(h))) return rc;
+  CU(h->diag_tmp.alloc((size_t)h->nels * h->ntot));
+  const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 32);
+  k_form_k_explicit<<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, h->diag_tmp.p, (long long)h->nels);
+  h->launches++;
+  // globma_pp = 1/scatter(globma_tmp)   (p125.f90:78,82)
+  h->nfixed = 0;
+  {
+    Scope sc(h, K_SCATTER);
+    k_scatter<false><<<grid_for(h, h->nslots, 256, 16), 256, 0, h->stream>>>(h->csr_ptr.p, h->csr_pos.p, h->diag_tmp.p, h->diag_ext.p,
+                                                                              (long long)h->nslots, h->ntot, nullptr);
+    h->launches++;
+  }
+  if ((rc = halo_reverse(h, h->diag_ext.p, nullptr))) return rc;
+  if (h->neq_pp > 0) {
+    k_invert<<<grid_for(h, h->neq_pp, 256), 256, 0, h->stream>>>(h->diag_ext.p + 1, (long long)h->neq_pp);
+    h->launches++;
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  h->diag_tmp.release();
+  h->have_km = true; h->have_precon = true; h->explicit_ = true;
+  return 0;
+}
+
+int pf_explicit_start(pf_handle h, double val0) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->explicit_, "needs pf_form_k_explicit");
+  if (h->neq_pp > 0) {     // loads_pp = val0 (p125.f90:83); the field lives in the owned part of p_ext
+    k_fill<<<grid_for(h, h->neq_pp, 256), 256, 0, h->stream>>>(h->p_ext.p + 1, val0, (long long)h->neq_pp);
+    k_fill<<<grid_for(h, h->neq_pp, 256), 256, 0, h->stream>>>(h->x.p, val0, (long long)h->neq_pp);
+    h->launches += 2;
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int pf_explicit_steps(pf_handle h, int nsteps, double *elapsed_ms) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->explicit_ && nsteps >= 0, "needs pf_form_k_explicit and nsteps >= 0");
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, h->stream));
+  for (int j = 0; j < nsteps; ++j) {
+    // newlo_pp = scatter(MATMUL(store_pm_pp, gather(loads_pp))); loads_pp = newlo_pp*globma_pp  (p125.f90:94-99)
+    if ((rc = apply_operator(h, nullptr))) return rc;
+    if (h->neq_pp > 0) {
+      Scope sc(h, K_VECTOR);
+      k_scale<<<grid_for(h, h->neq_pp, 256), 256, 0, h->stream>>>(h->p_ext.p + 1, h->u_ext.p + 1, h->diag_ext.p + 1, (long long)h->neq_pp);
+      h->launches++;
+    }
+  }
+  CU(cudaMemcpyAsync(h->x.p, h->p_ext.p + 1, (size_t)h->neq_pp * 8, cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaEventRecord(e1, h->stream));
+  CU(cudaEventSynchronize(e1));
+  CU(cudaGetLastError());
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  collect_spans(h);
+  if (elapsed_ms) *elapsed_ms = ms;
+  return 0;
+}
+
 int pf_set_storkm(pf_handle h, const double *storkm_pp) {
   int rc = need_device(h); if (rc) return rc;
   NEED(h->have_mesh && storkm_pp, "needs pf_setup_mesh");
   NEED(!h->matrix_free, "matrix-free variant: storkm is not stored");
-  h->transient = false; h->kb.release();
+  h->transient = false; h->explicit_ = false; h->kb.release();
   if ((rc = alloc_km(h))) return rc;
   if (h->km_layout == 0) {
     CU(cudaMemcpy(h->km.p, storkm_pp, h->km.bytes(), cudaMemcpyHostToDevice));

@@ -1324,6 +1324,58 @@ k_form_k_transient(const double *__restrict__ g_coord, double *__restrict__ ka, 
   }
 }
 
+// elements_1 of p125.f90:66-79 (explicit transient conduction); 8-node bricks, 64 threads = one per entry:
+//   kc, pm as in p124 (no rho*cp); mass(i) = SUM(pm(i,:)), j ascending; store_pm = diag(mass) - kc*dtim;
+//   mass_out(i,iel) = mass(i) feeds globma_pp (p125.f90:78,82)
+__global__ void __launch_bounds__(64)
+k_form_k_explicit(const double *__restrict__ g_coord, double *__restrict__ store_pm, double *__restrict__ mass_out, long long nels) {
+  constexpr int NOD = 8;
+  __shared__ double s_coord[NOD * 3], s_jac[9], s_deriv[NOD * 3], s_pm[64], s_mass[8];
+  const int j = threadIdx.x / 8, i = threadIdx.x % 8;
+  const double dtim = c_tab.trans[3];
+  for (long long e = blockIdx.x; e < nels; e += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x < NOD * 3) s_coord[threadIdx.x] = g_coord[e * NOD * 3 + threadIdx.x];
+    __syncthreads();
+    double kc = 0.0, pm = 0.0;
+    for (int ig = 0; ig < c_tab.nip; ++ig) {
+      const double det = gauss_point<NOD>(ig, s_coord, s_jac, s_deriv);
+      const double wt = c_tab.weights[ig];
+      double s = 0.0;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        double t1 = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) t1 = t1 + s_deriv[i * 3 + a] * (a == b ? c_tab.kxyz[b] : 0.0);
+        s = s + t1 * s_deriv[j * 3 + b];
+      }
+      kc = kc + s * det * wt;
+      double f = 0.0;
+      f = f + c_tab.fun[ig * 8 + i] * c_tab.fun[ig * 8 + j];
+      pm = pm + f * det * wt;
+      __syncthreads();
+    }
+    s_pm[threadIdx.x] = pm;                       // pm(i,j) at [j*8+i]
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      double m = 0.0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) m = m + s_pm[c * 8 + threadIdx.x];
+      s_mass[threadIdx.x] = m;
+      mass_out[e * 8 + threadIdx.x] = m;
+    }
+    __syncthreads();
+    store_pm[e * 64 + threadIdx.x] = (i == j ? s_mass[i] : 0.0) - kc * dtim;
+  }
+}
+
+// loads_pp = newlo_pp*globma_pp (p125.f90:99)
+__global__ void k_scale(double *__restrict__ dst, const double *__restrict__ a, const double *__restrict__ b, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = a[i] * b[i];
+}
+
 // p124 time stepping, right-hand side of one step (p124.f90:143-200):
 //   loads = (loaded freedoms, or 0) + u ;  r = loads - r0 with r0 = +0.0 off the fixed freedoms
 __global__ void k_transient_rhs(double *__restrict__ r, const double *__restrict__ loads, const double *__restrict__ u, long long n) {

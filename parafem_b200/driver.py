@@ -97,6 +97,49 @@ def write_res_p124(path, prob, res, t_total=0.0, t_output=0.0):
         f.write(f"This analysis took      {t_total:10.4f}\n")
 
 
+def run_p125(prob, s, out_base=None, decimals=5):
+    """Program p125 (p125.f90) for one rank: element integration, then nstep passes of the explicit recursion
+    on the device, npri at a time; with `out_base` the nodal files <out_base>.ensi.NDPRE-NNNNNN every npri steps
+    (single rank).  -> dict(rows [(time, value at freedom nres)], x, step_s, setup_s)."""
+    from . import host
+    t0 = time.time()
+    _solver.setup_problem(s, prob)
+    s.explicit_start(prob.val0)
+    t_setup = time.time() - t0
+    lo = prob.ieq_start
+    owns = lo <= prob.nres < lo + prob.neq_pp
+    rows = [(0.0, prob.val0)] if owns else []
+    ms, done, x = 0.0, 0, None
+    while done < prob.nstep:
+        n = min(prob.npri, prob.nstep - done)
+        ms += s.explicit_steps(n)
+        done += n
+        if done // prob.npri * prob.npri == done:
+            x = s.pcg_get_x()
+            if owns:
+                rows.append((done * prob.dtim, float(x[prob.nres - lo])))
+            if out_base and prob.npes == 1:
+                host.write_ensi(f"{out_base}.ensi.NDPRE-{done:06d}", host.nodal_values(prob, x), decimals=decimals)
+    if x is None or prob.nstep % prob.npri:
+        x = s.pcg_get_x()
+    return dict(rows=rows, x=x, step_s=ms / 1e3, setup_s=t_setup)
+
+
+def write_res_p125(path, prob, res, t_read=0.0, t_total=0.0):
+    """<job>.res of p125 (p125.f90:49-56,80-81,86-87,101,116-118)."""
+    with open(path, "w") as f:
+        f.write(f"This job ran on {prob.npes:5d}  processes\n")
+        f.write(f"There are {prob.nn:12d} nodes{prob.nr:12d} restrained and{prob.neq:12d} equations\n")
+        f.write(f"Time to read input is:{t_read:10.4f}\n")
+        f.write(f"Time after setup is:{t_read + res['setup_s']:10.4f}\n")
+        f.write(f"Time for element integration is :{res['setup_s']:10.4f}\n")
+        f.write("  Time        Pressure\n")
+        for t, v in res["rows"]:
+            f.write(_fe(t) + _fe(v) + "\n")
+        f.write(f"Time stepping recursion took  :{res['step_s']:10.4f}\n")
+        f.write(f"This analysis took  :{t_total:10.4f}\n")
+
+
 def write_res(path, prob, res, t_read=0.0, t_total=0.0):
     """<job>.res as rank 1 writes it."""
     with open(path, "w") as f:
@@ -145,6 +188,8 @@ def main(argv=None):
     g.add_argument("--p123", type=int, help="p12meshgen p123 box with N^3 8-node bricks")
     g.add_argument("--p124", type=int, help="p12meshgen p124 box with N^3 8-node bricks (transient conduction, "
                                             "150 steps of 0.01 as the shipped p124_*.mg)")
+    g.add_argument("--p125", type=int, help="p12meshgen p125 box with N^3 8-node bricks (explicit transient conduction, "
+                                            "5000 steps of 0.0002 as the shipped p125_*.mg)")
     ap.add_argument("--hex", type=int, default=20, choices=[8, 20])
     ap.add_argument("--matrix-free", type=int, default=0, choices=[0, 1, 2])
     ap.add_argument("--out", default=".")
@@ -158,6 +203,14 @@ def main(argv=None):
         with _solver.Solver(0, 1, 0) as s:
             res = run_p124(prob, s, out_base=base)
         write_res_p124(base + ".res", prob, res, t_total=time.time() - t0)
+        print(open(base + ".res").read(), end="")
+        return 0
+    elif a.p125:
+        prob, job = host.cube_p125(a.p125, a.p125, a.p125), f"p125_box{a.p125}"
+        base = os.path.join(a.out, job)
+        with _solver.Solver(0, 1, 0) as s:
+            res = run_p125(prob, s, out_base=base)
+        write_res_p125(base + ".res", prob, res, t_total=time.time() - t0)
         print(open(base + ".res").read(), end="")
         return 0
     elif a.cube:

@@ -199,6 +199,17 @@ def cube_p124(nxe, nye, nze, aa=None, bb=None, cc=None, kx=1.0, ky=1.0, kz=1.0, 
     return p
 
 
+def cube_p125(nxe, nye, nze, aa=None, bb=None, cc=None, kx=1.0, ky=1.0, kz=1.0, dtim=2e-4, nstep=5000, npri=500,
+              val0=100.0, nip=8, npes=1, numpe=1, round_mode=0, psize=None):
+    """In-memory p12meshgen box for p125 (p12meshgen.f90:1017-1170): the p123 box with the explicit time
+    stepping data of the .mg file (defaults = the shipped p125_*.mg)."""
+    p = cube_p123(nxe, nye, nze, aa, bb, cc, kx, ky, kz, 0.0, 0, nip, npes, numpe, round_mode, 0.0, False, 0.0, psize)
+    p.program = 125
+    p.r_pp[:] = 0.0
+    p.dtim, p.nstep, p.npri, p.val0 = dtim, nstep, npri, val0
+    return p
+
+
 def read_deck_p121(job, npes=1, numpe=1):
     """read_p121 + read_g_num_pp + abaqus2sg + read_g_coord_pp + read_rest + steering +
     read_loads + load (p121.f90:28-49, 79-85) for one rank."""

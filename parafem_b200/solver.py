@@ -167,6 +167,20 @@ class Solver:
                  "pf_transient_step")
         return it.value, bool(cv.value), ms.value
 
+    # -- p125: explicit transient conduction -----------------------------------------------
+    def form_k_explicit(self, kx, ky, kz, dtim):
+        """p125.f90:66-82: store_pm_pp and the inverted lumped mass globma_pp on the device."""
+        self._ck(lib().pf_form_k_explicit(self._h, kx, ky, kz, dtim), "pf_form_k_explicit")
+
+    def explicit_start(self, val0):
+        self._ck(lib().pf_explicit_start(self._h, val0), "pf_explicit_start")
+
+    def explicit_steps(self, nsteps):
+        """nsteps passes of p125's recursion on the device. -> elapsed_ms"""
+        ms = C.c_double()
+        self._ck(lib().pf_explicit_steps(self._h, nsteps, C.byref(ms)), "pf_explicit_steps")
+        return ms.value
+
     # -- fine-grained -----------------------------------------------------------------
     def gather(self, p_pp):
         out = np.empty((self.prob.nels_pp, self.prob.ntot))
@@ -238,6 +252,8 @@ def setup_problem(solver, prob, matrix_free=False, layout=0):
         if prob.no_f.size:
             # r_pp(j) = store_pp(i)*valf(k)   (xx2.f90:294-300)
             prob.r_pp[prob.no_f - prob.ieq_start] = solver.store() * prob.val_f
+    elif prob.program == 125:
+        solver.form_k_explicit(prob.kx, prob.ky, prob.kz, prob.dtim)
     elif prob.program == 124:
         solver.form_k_transient(prob.kx, prob.ky, prob.kz, prob.rho, prob.cp, prob.theta, prob.dtim)
         solver.build_precon(prob.no_f, 1e20)

@@ -76,7 +76,17 @@ def main():
                    nod=nod4), open(f"{HERE}/p124_demo_digests.json", "w"), indent=1)
     ndttr = {f"p124_ndttr_{j:03d}": np.loadtxt(f"{d124}.ensi.NDTTR-{j:06d}", skiprows=4).astype(np.float32)
              for j in (10, 80, 150)}
-    np.savez_compressed(f"{HERE}/arrays.npz", **ndttr, **xx2, tiny_coord=t.g_coord, tiny_gnum_sg=t.g_num_pp, tiny_rest=t.rest,
+    # p125 demo (explicit transient conduction): same 25^3 deck; two of the ten golden nodal files
+    d125 = f"{REF}/5th_ed/p125/demo/p125_demo"
+    gn5 = np.empty((nels4, nod4), np.int32)
+    gc5 = np.empty((nn4, 3), np.float64)
+    assert lib().pf_read_d(d125.encode(), nn4, nels4, nod4, ptr(gc5), ptr(gn5)) == 0
+    assert lib().pf_abaqus2sg(nod4, nels4, ptr(gn5)) == 0
+    assert np.array_equal(gn5, gn4) and np.array_equal(gc5, gc4)            # p125_demo.d == p124_demo.d
+    assert open(d125 + ".bnd").read() == open(d124 + ".bnd").read()
+    ndpre = {f"p125_ndpre_{j:04d}": np.loadtxt(f"{d125}.ensi.NDPRE-{j:06d}", skiprows=4).astype(np.float32)
+             for j in (500, 5000)}
+    np.savez_compressed(f"{HERE}/arrays.npz", **ndttr, **ndpre, **xx2, tiny_coord=t.g_coord, tiny_gnum_sg=t.g_num_pp, tiny_rest=t.rest,
                         tiny_lds_node=node, tiny_lds_val=val, tiny_dis=dis, demo_lds_node=dnode, demo_lds_val=dval,
                         demo_displ=disp.reshape(3, p.nn).T.astype(np.float32))
     texts = {
@@ -85,6 +95,7 @@ def main():
         "p121_book.res": lines(f"{REF}/5th_ed/p121/book/p121.res"), "p121_book.mg": lines(f"{REF}/5th_ed/p121/book/p121.mg"),
         "p123_book.res": lines(f"{REF}/5th_ed/p123/book/p123.res"), "p123_book.mg": lines(f"{REF}/5th_ed/p123/book/p123.mg"),
         "xx2-tiny.res": lines(x2 + ".res"), "xx2-tiny.dat": lines(x2 + ".dat"), "xx2-tiny.mat": lines(x2 + ".mat"),
+        "p125_demo.res": lines(d125 + ".res"), "p125_demo.dat": lines(d125 + ".dat"),
         "p124_demo.res": lines(d124 + ".res"), "p124_demo.dat": lines(d124 + ".dat"), "p124_demo.mat": lines(d124 + ".mat"),
         "p124_book.res": lines(f"{REF}/5th_ed/p124/book/p124.res"), "p124_book.mg": lines(f"{REF}/5th_ed/p124/book/p124.mg"),
         "p124_tiny.mg": lines(f"{REF}/5th_ed/p124/mg/p124_tiny.mg"),

@@ -256,3 +256,47 @@ def test_xx2_tiny_iterations_and_displacements(tiny_xx2, golden, red_mode, npes,
     m = p.nf > 0
     u[m] = r["x"][p.nf[m] - 1]
     assert np.abs(u - dis).max() < 1e-5                  # 5 significant digits, max|u| 0.13
+
+
+# ---- p125: explicit transient conduction -------------------------------------------
+
+def _p125_rows(path):
+    rows = []
+    for line in open(path):
+        m = re.match(r"^\s+(0\.\d+E[+-]\d+)\s+(-?0\.\d+E[+-]\d+)\s*$", line)
+        if m:
+            rows.append((float(m.group(1)), float(m.group(2))))
+    return rows
+
+
+def test_p125_demo_log_and_fields(p124_demo, golden):
+    """examples/5th_ed/p125/demo/p125_demo.res (4 ranks; the p124 demo mesh): pressure at freedom 601 after every
+    500 of the 5000 explicit steps, all ten rows to the 4 digits printed, and the nodal files of steps 500 / 5000."""
+    p = p124_demo
+    dat = open(os.path.join(golden, "p125_demo.dat")).read().split()
+    assert [int(v) for v in dat[3:8]] == [p.nels, p.nn, p.nr, 8, 8]
+    kx, ky, kz, dtim, nstep, npri, nres, val0 = (float(dat[10]), float(dat[11]), float(dat[12]), float(dat[13]),
+                                                 int(dat[14]), int(dat[15]), int(dat[16]), float(dat[17]))
+    assert (kx, ky, kz, dtim, nstep, npri, nres, val0) == (1., 1., 1., 2e-4, 5000, 500, p.nres, 100.)
+    rows = _p125_rows(os.path.join(golden, "p125_demo.res"))
+    assert len(rows) == 11 and rows[0] == (0.0, 100.0)
+    store, mass = oracle.form_k_explicit(p.g_coord_pp, p.nip, kx, ky, kz, dtim)
+    r = oracle.p125(store, mass, p.g_g_pp, p.neq, val0, nstep, npes=4, keep=tuple(range(npri, nstep + 1, npri)))
+    for k, (t, val) in enumerate(rows[1:]):
+        j = (k + 1) * npri
+        assert abs(t - j * dtim) < 1e-12
+        assert abs(r["fields"][j][p.nres - 1] - val) <= 5.1e-5 * abs(val) * 10     # E12.4: half a unit of the 4th digit
+    arr = np.load(os.path.join(os.path.dirname(__file__), "golden", "arrays.npz"))
+    for j in (500, 5000):
+        gold = arr[f"p125_ndpre_{j:04d}"].astype(np.float64)
+        field = host.nodal_values(p, r["fields"][j])[:, 0]
+        assert np.abs(field - gold).max() <= 6e-5 * np.abs(gold).max()
+
+
+def test_p125_matrices_properties():
+    """Lumped mass sums to the element volume; every row of store_pm sums to the lumped mass (constant fields are
+    in the null space of kc)."""
+    p = host.cube_p125(3, 2, 2, aa=.5, bb=.25, cc=.2)
+    store, mass = oracle.form_k_explicit(p.g_coord_pp, 8, 1.5, 2.0, 0.5, 1e-3)
+    assert np.allclose(mass.sum(axis=1), .5 * .25 * .2, rtol=1e-13)
+    assert np.allclose(store.sum(axis=1), mass, rtol=0, atol=1e-15)
