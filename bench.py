@@ -39,8 +39,10 @@ def parse():
     #  rejects e.g. --n / --nod even after the script name)
     ap.add_argument("--cube", dest="n", type=int, default=125, help="cube edge in elements (125 = BASELINE config C)")
     ap.add_argument("--hex", dest="nod", type=int, default=20, choices=[8, 20], help="nodes per brick")
-    ap.add_argument("--program", default="p121", choices=["p121", "p123"],
-                    help="p123 = steady heat conduction, 8-node bricks (BASELINE config B at --n 100)")
+    ap.add_argument("--program", default="p121", choices=["p121", "p123", "p124", "p125"],
+                    help="p123 = steady heat conduction, 8-node bricks (BASELINE config B at --cube 100); p124 = transient "
+                         "conduction, one PCG solve per time step (a step = one time step); p125 = explicit transient "
+                         "conduction (a step = one pass of gather / mat-vec / scatter)")
     ap.add_argument("--cpu-n", type=int, default=40, help="cube edge of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=60)
     ap.add_argument("--matrix-free", type=int, default=0, choices=[0, 1, 2],
@@ -148,6 +150,87 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def transient_bench(args, rank, nranks, local, nccl_id, barrier, maxf):
+    """the drivers that reuse the three kernels.  p124: K time steps, each one resident PCG solve
+    (value = neq * PCG iterations / s); p125: K explicit steps (value = neq * steps / s).  Same JSON keys as the
+    headline line; not a BASELINE config, so `vs_baseline` is null and there is no cpu_baseline leg."""
+    from parafem_b200 import host, solver
+    n, K, W = args.n, args.steps, max(args.warmup, 3)
+    nye = n * nranks if args.weak else n
+    make = host.cube_p124 if args.program == "p124" else host.cube_p125
+    prob = make(n, nye, n, npes=nranks, numpe=rank + 1)
+    s = solver.Solver(rank, nranks, local, nccl_id)
+    solver.setup_problem(s, prob)
+    pk, pk_kind = peaks()
+    sampler = ClockSampler(local)
+    if args.program == "p124":
+        s.transient_start(prob.val0)
+        for _ in range(W):
+            s.transient_step(prob.tol, prob.limit)
+        s.set_profile(True); s.reset_profile()
+        barrier()
+        l0 = s.kernel_launches()
+        if rank == 0:
+            sampler.start()
+        ms, its = 0.0, 0
+        for _ in range(K):
+            it, _, m = s.transient_step(prob.tol, prob.limit)
+            ms += m
+            its += it
+        units = its
+    else:
+        s.explicit_start(prob.val0)
+        s.explicit_steps(W)
+        s.set_profile(True); s.reset_profile()
+        barrier()
+        l0 = s.kernel_launches()
+        if rank == 0:
+            sampler.start()
+        ms = s.explicit_steps(K)
+        units = K
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = s.kernel_launches() - l0
+    ms = maxf(ms)
+    km = {name: s.kernel_ms(i) for i, name in enumerate(("matvec", "scatter", "vector", "halo"))}
+    x = s.pcg_get_x()                       # the step's result read on the host (e2e adds this copy)
+    t = time.perf_counter()
+    e_units = K
+    if args.program == "p124":
+        e_units = sum(s.transient_step(prob.tol, prob.limit)[0] for _ in range(K))
+    else:
+        s.explicit_steps(K)
+    x = s.pcg_get_x()
+    e2e_s = maxf(time.perf_counter() - t)
+    mv_ms, mv_n = km["matvec"]
+    bytes_pp = prob.nels_pp * 64 * 8
+    achieved = bytes_pp / (mv_ms / max(mv_n, 1) / 1e3) / 1e9 if mv_n else None
+    if rank == 0:
+        line = {"metric": f"{args.program} EBE MDOF-" + ("iters/s" if args.program == "p124" else "steps/s"),
+                "value": prob.neq * units / (ms / 1e3) / 1e6, "unit": UNIT if args.program == "p124" else "MDOF*steps/s",
+                "n_gpus": nranks, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+                "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"{args.program} {n}x{nye}x{n} hex8 box, p12meshgen geometry: {prob.nels} elements, "
+                                       f"{prob.neq} equations, dtim {prob.dtim}",
+                           "step": "one time step = right-hand side product + one PCG solve to tol 1e-4" if args.program == "p124"
+                                   else "one explicit step (gather, store_pm mat-vec, scatter, scale by the lumped mass)",
+                           "l2": "element matrices per rank " + f"{bytes_pp / 1e6:.0f} MB" + (" (larger than L2)" if bytes_pp > 126e6 else " (fits L2)"),
+                           "nels": prob.nels, "neq": prob.neq},
+                "pcg_iterations_timed": units if args.program == "p124" else None,
+                "e2e": {"value": prob.neq * e_units / e2e_s / 1e6, "seconds": e2e_s,
+                        "unit": UNIT if args.program == "p124" else "MDOF*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": prob.neq_pp * 8 / K,
+                        "note": "K steps through the C-ABI + the field read back to the host"},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                             "frac": achieved / pk["hbm_gbs"] if achieved else None, "traffic": None,
+                             "kernel": "k_matvec<8> (storka / store_pm stream; gather fused)", "peak_kind": pk_kind,
+                             "algorithmic_bytes_per_launch": bytes_pp, "launches_timed": int(mv_n)},
+                "kernel_ms_per_step": {k: v[0] / K for k, v in km.items()},
+                "clocks": clocks, "x_checksum": float(x.sum())}
+        print(json.dumps(line), flush=True)
+    s.close()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -190,6 +273,11 @@ def main():
     t_setup0 = time.time()
     n = args.n
     nye = n * nranks if args.weak else n
+    if args.program in ("p124", "p125"):
+        transient_bench(args, rank, nranks, local, nccl_id, barrier, maxf)
+        if nranks > 1:
+            dist.destroy_process_group()
+        return
     if args.program == "p123":
         args.nod = 8
         prob = host.cube_p123(n, nye, n, aa=1.0 / n, bb=1.0 / n, cc=1.0 / n, limit=20000, npes=nranks, numpe=rank + 1)
