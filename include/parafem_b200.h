@@ -180,6 +180,7 @@ int pf_explicit_steps(pf_handle h, int nsteps, double *elapsed_ms);
  *   pf_apply   = the three fused as the solver runs them (u = A p)
  *   pf_dot     = dot_product_p                   maths.f90:168-216
  *   pf_norm    = norm_p                          maths.f90:222-265
+ *   pf_sum     = sum_p                           maths.f90:271-315
  * All pointers are host arrays.                                           */
 int pf_gather(pf_handle h, const double *p_pp, double *pmul_pp);
 int pf_matvec(pf_handle h, const double *pmul_pp, double *utemp_pp);
@@ -187,6 +188,7 @@ int pf_scatter(pf_handle h, const double *utemp_pp, double *u_pp);
 int pf_apply(pf_handle h, const double *p_pp, double *u_pp);
 int pf_dot(pf_handle h, const double *a_pp, const double *b_pp, double *result);
 int pf_norm(pf_handle h, const double *a_pp, double *result);
+int pf_sum(pf_handle h, const double *a_pp, double *result);
 
 /* --- post-solve ---------------------------------------
  * pf_centroid_stress: p121.f90:113-123 for local 0-based element iel
@@ -282,6 +284,8 @@ int pf_read_d(const char *job, int64_t nn, int64_t nels, int nod,
               double *g_coord /*(3,nn)*/, int32_t *g_num /*(nod,nels)*/);
 int pf_read_bnd(const char *job, int64_t nr, int nodof, int32_t *rest);
 int pf_read_lds(const char *job, int64_t loaded, int nodof, int32_t *node, double *val);
+/* read_fixed (input.f90:2483-2564): node(fixed), sense(fixed) (1-based freedom of the node), valf(fixed) */
+int pf_read_fix(const char *job, int64_t fixed, int32_t *node, int32_t *sense, double *valf);
 /* g_coord_pp(nod,3,nels_pp) from g_coord(3,nn) and g_num_pp                */
 int pf_coords_pp(int nod, int64_t nels_pp, const int32_t *g_num_pp,
                  const double *g_coord, double *g_coord_pp);

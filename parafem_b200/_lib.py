@@ -71,6 +71,7 @@ SIGNATURES = {
     "pf_apply": (c_int, [vp, vp, vp]),
     "pf_dot": (c_int, [vp, vp, vp, P(c_dbl)]),
     "pf_norm": (c_int, [vp, vp, P(c_dbl)]),
+    "pf_sum": (c_int, [vp, vp, P(c_dbl)]),
     "pf_centroid_stress": (c_int, [vp, c_i64, c_dbl, c_dbl, vp]),
     "pf_set_profile": (c_int, [vp, c_int]),
     "pf_reset_profile": (c_int, [vp]),
@@ -98,6 +99,7 @@ SIGNATURES = {
     "pf_read_mat": (c_int, [C.c_char_p, c_int, c_int, vp]),
     "pf_read_bnd": (c_int, [C.c_char_p, c_i64, c_int, vp]),
     "pf_read_lds": (c_int, [C.c_char_p, c_i64, c_int, vp, vp]),
+    "pf_read_fix": (c_int, [C.c_char_p, c_i64, vp, vp, vp]),
     "pf_coords_pp": (c_int, [c_int, c_i64, vp, vp, vp]),
     "pf_write_deck_p121": (c_int, [C.c_char_p, c_int, c_i64, c_i64, c_i64, c_int, c_i64, c_dbl, c_dbl, c_dbl, c_int,
                                    vp, vp, vp, vp, vp]),

@@ -1428,6 +1428,14 @@ int pf_dot(pf_handle h, const double *a_pp, const double *b_pp, double *result) 
   return 0;
 }
 
+int pf_sum(pf_handle h, const double *a_pp, double *result) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_mesh, "needs pf_setup_mesh");
+  // sum_p (maths.f90:271-315) through the dot-product tree: a(i)*1.0 == a(i)
+  std::vector<double> ones((size_t)std::max<int64_t>(h->neq_pp, 1), 1.0);
+  return pf_dot(h, a_pp, ones.data(), result);
+}
+
 int pf_norm(pf_handle h, const double *a_pp, double *result) {
   double s = 0.0;
   int rc = pf_dot(h, a_pp, a_pp, &s);

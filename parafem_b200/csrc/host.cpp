@@ -515,6 +515,20 @@ int pf_read_bnd(const char *job, int64_t nr, int nodof, int32_t *rest) {
   return rc;
 }
 
+// read_fixed (input.f90:2483-2564): <job>.fix holds `fixed` lines "node sense value"
+int pf_read_fix(const char *job, int64_t fixed, int32_t *node, int32_t *sense, double *valf) {
+  FILE *f = fopen((std::string(job) + ".fix").c_str(), "r");
+  if (!f) return 1;
+  int rc = 0;
+  for (int64_t i = 0; i < fixed; ++i) {
+    long long n, s; double v;
+    if (fscanf(f, "%lld %lld %lf", &n, &s, &v) != 3) { rc = 2; break; }
+    node[i] = (int32_t)n; sense[i] = (int32_t)s; valf[i] = v;
+  }
+  fclose(f);
+  return rc;
+}
+
 int pf_read_lds(const char *job, int64_t loaded, int nodof, int32_t *node, double *val) {
   FILE *f = fopen((std::string(job) + ".lds").c_str(), "r");
   if (!f) return 1;

@@ -248,6 +248,59 @@ def read_deck_p121(job, npes=1, numpe=1):
     return p
 
 
+def read_deck_p123(job, npes=1, numpe=1):
+    """Input section of p123.f90:27-55,94-131 (and of programs/dev/xx11/xx11.f90, which shares its deck format)
+    for one rank: read_p123, read_g_num_pp, abaqus2sg, read_g_coord_pp, read_rest + rearrange_2/find_g4 -- or
+    g_g_pp = g_num_pp when nr = 0 (p123.f90:54) --, read_loads (first column = global equation number,
+    p123.f90:111-116) and read_fixed + find_no2 + reindex (node, sense -> this rank's fixed equations)."""
+    L = lib()
+    info = DeckInfo()
+    check(L.pf_read_dat(job.encode(), 123, C.byref(info)), what="pf_read_dat")
+    nod, nn, nels, nr = info.nod, info.nn, info.nels, info.nr
+    if nod != 8:
+        raise PfError("p123 decks hold 8-node bricks")
+    g_coord = np.empty((nn, 3), np.float64)
+    g_num = np.empty((nels, nod), np.int32)
+    check(L.pf_read_d(job.encode(), nn, nels, nod, ptr(g_coord), ptr(g_num)), what="pf_read_d")
+    if info.meshgen == 2:
+        check(L.pf_abaqus2sg(nod, nels, ptr(g_num)), what="pf_abaqus2sg")
+    nels_pp, iel_start = read_psize(job, npes, numpe) if info.partitioner == 2 else calc_nels_pp(nels, npes, numpe)
+    g_num_pp = np.ascontiguousarray(g_num[iel_start - 1:iel_start - 1 + nels_pp])
+    g_coord_pp = np.empty((nels_pp, 3, nod), np.float64)
+    check(L.pf_coords_pp(nod, nels_pp, ptr(g_num_pp), ptr(g_coord), ptr(g_coord_pp)), what="pf_coords_pp")
+    if nr > 0:
+        rest = np.zeros((2, nr), np.int32)
+        check(L.pf_read_bnd(job.encode(), nr, 1, ptr(rest)), what="pf_read_bnd")
+        nf, g_g, neq = _steer(nn, 1, rest, g_num_pp, nod)
+    else:                                   # "When nr = 0, g_num_pp and g_g_pp are identical"
+        nf = np.arange(1, nn + 1, dtype=np.int32).reshape(nn, 1)
+        g_g, neq = g_num_pp.copy(), int(nn)
+    neq_pp, ieq_start = calc_neq_pp(neq, npes, numpe)
+    r = np.zeros(neq_pp, np.float64)
+    total = 0.0
+    if info.loaded:
+        eqn = np.empty(info.loaded, np.int32)
+        val = np.empty((info.loaded, 1), np.float64)
+        check(L.pf_read_lds(job.encode(), info.loaded, 1, ptr(eqn), ptr(val)), what="pf_read_lds")
+        mine = (eqn >= ieq_start) & (eqn < ieq_start + neq_pp)
+        r[eqn[mine] - ieq_start] = val[mine, 0]
+        total = float(val.sum())
+    no_f, val_f = np.zeros(0, np.int32), np.zeros(0, np.float64)
+    if info.fixed:
+        node = np.empty(info.fixed, np.int32)
+        sense = np.empty(info.fixed, np.int32)
+        valf = np.empty(info.fixed, np.float64)
+        check(L.pf_read_fix(job.encode(), info.fixed, ptr(node), ptr(sense), ptr(valf)), what="pf_read_fix")
+        eq = nf[node - 1, sense - 1]        # find_no2 (loading.f90:742-828): the equation of (node, sense)
+        mine = (eq >= ieq_start) & (eq < ieq_start + neq_pp)
+        no_f, val_f = np.ascontiguousarray(eq[mine]), np.ascontiguousarray(valf[mine])
+    p = Problem(123, nod, 1, info.nip, nels, nn, nr, neq, npes, numpe, nels_pp, iel_start, neq_pp, ieq_start,
+                g_num_pp, g_coord_pp, g_g, nf, r, kx=info.kx, ky=info.ky, kz=info.kz, tol=info.tol,
+                limit=info.limit, nres=info.nres, no_f=no_f, val_f=val_f, total_load=total)
+    p.g_coord = g_coord
+    return p
+
+
 def read_deck_xx2(job, npes=1, numpe=1):
     """Input section of programs/dev/xx2/xx2.f90:60-160 for one rank: read_xx2, read_elements (connectivity +
     material number of every element), abaqus2sg, read_g_coord_pp, read_rest, read_materialValue, steering,

@@ -212,6 +212,11 @@ class Solver:
         self._ck(lib().pf_norm(self._h, ptr(f64(a_pp)), C.byref(res)), "pf_norm")
         return res.value
 
+    def sum(self, a_pp):
+        res = C.c_double()
+        self._ck(lib().pf_sum(self._h, ptr(f64(a_pp)), C.byref(res)), "pf_sum")
+        return res.value
+
     def centroid_stress(self, iel, e, v):
         out = np.empty(6)
         self._ck(lib().pf_centroid_stress(self._h, iel, e, v, ptr(out)), "pf_centroid_stress")

@@ -57,6 +57,28 @@ def golden(tmp_path_factory, _built):
         f.write("*DISPLACEMENT\n           1\n")
         for i, u in enumerate(a["xx2_dis"]):
             f.write(f"{i + 1:8d} {u[0]: .4E} {u[1]: .4E} {u[2]: .4E}\n")
+    # xx11 (p123 deck format, nr = 0, loads + fixed freedoms): rewritten in S&G node order, so meshgen = 1
+    x11 = os.path.join(d, "xx11")
+    dat = open(x11 + ".dat").read().split()
+    dat[1] = "1"
+    open(x11 + ".dat", "w").write("\n".join(dat[:3]) + "\n" + " ".join(dat[3:10]) + "\n" + " ".join(dat[10:]) + "\n")
+    with open(x11 + ".d", "w") as f:
+        f.write("*THREE_DIMENSIONAL\n*NODES\n")
+        for i, c in enumerate(a["xx11_coord"]):
+            f.write(f"{i + 1}  {float(c[0])!r}  {float(c[1])!r}  {float(c[2])!r}\n")
+        f.write("*ELEMENTS\n")
+        for e, g in enumerate(a["xx11_gnum_sg"]):
+            f.write(f"{e + 1}  3  8  1  " + "  ".join(str(int(v)) for v in g) + "  1\n")
+    with open(x11 + ".lds", "w") as f:
+        for q, v in zip(a["xx11_lds_eq"], a["xx11_lds_val"]):
+            f.write(f"{int(q):7d} {v:.8E}\n")
+    with open(x11 + ".fix", "w") as f:
+        for q, v in zip(a["xx11_fix_node"], a["xx11_fix_val"]):
+            f.write(f"{int(q)} 1 {float(v)!r}\n")
+    with open(x11 + ".ttr", "w") as f:
+        f.write("*TEMPERATURE\n 1\n")
+        for i, v in enumerate(a["xx11_ttr"]):
+            f.write(f"{i + 1:8d} {v: .4E}\n")
     with open(os.path.join(d, "xx3-tiny.dis"), "w") as f:
         f.write("*DISPLACEMENT\n           1\n")
         for i, u in enumerate(a["tiny_dis"]):

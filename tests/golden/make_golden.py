@@ -59,6 +59,16 @@ def main():
     assert np.array_equal(t2.g_num_pp, t.g_num_pp) and np.array_equal(t2.g_coord, t.g_coord) and np.array_equal(t2.rest, t.rest)
     assert np.array_equal(t2.r_pp, t.r_pp)
     xx2 = dict(xx2_etype=t2.etype_pp, xx2_prop=t2.prop, xx2_dis=np.loadtxt(x2 + ".dis", skiprows=2)[:, 1:])
+    # xx11 (dev program sharing p123's deck format): 64 8-node bricks, nr = 0, 25 loaded + 25 fixed freedoms.
+    # Its golden xx11.ttr was written with the loads of xx11.old.lds (100 per freedom); the shipped xx11.lds
+    # holds 10 per freedom and gives exactly one tenth of it.
+    x11 = f"{REF}/dev/xx11/xx11"
+    t11 = host.read_deck_p123(x11)
+    old = np.loadtxt(x11 + ".old.lds")
+    assert np.array_equal(old[:, 0].astype(int), np.flatnonzero(t11.r_pp) + 1) and np.all(old[:, 1] == 100.0)
+    xx11 = dict(xx11_coord=t11.g_coord, xx11_gnum_sg=t11.g_num_pp, xx11_lds_eq=(np.flatnonzero(t11.r_pp) + 1).astype(np.int32),
+                xx11_lds_val=t11.r_pp[np.flatnonzero(t11.r_pp)], xx11_fix_node=t11.no_f, xx11_fix_val=t11.val_f,
+                xx11_ttr=np.loadtxt(x11 + ".ttr", skiprows=2)[:, 1])
     # p124 demo deck (transient conduction, 25^3 8-node bricks, Abaqus node order on disk)
     d124 = f"{REF}/5th_ed/p124/demo/p124_demo"
     dat = open(d124 + ".dat").read().split()
@@ -86,7 +96,7 @@ def main():
     assert open(d125 + ".bnd").read() == open(d124 + ".bnd").read()
     ndpre = {f"p125_ndpre_{j:04d}": np.loadtxt(f"{d125}.ensi.NDPRE-{j:06d}", skiprows=4).astype(np.float32)
              for j in (500, 5000)}
-    np.savez_compressed(f"{HERE}/arrays.npz", **ndttr, **ndpre, **xx2, tiny_coord=t.g_coord, tiny_gnum_sg=t.g_num_pp, tiny_rest=t.rest,
+    np.savez_compressed(f"{HERE}/arrays.npz", **ndttr, **ndpre, **xx2, **xx11, tiny_coord=t.g_coord, tiny_gnum_sg=t.g_num_pp, tiny_rest=t.rest,
                         tiny_lds_node=node, tiny_lds_val=val, tiny_dis=dis, demo_lds_node=dnode, demo_lds_val=dval,
                         demo_displ=disp.reshape(3, p.nn).T.astype(np.float32))
     texts = {
@@ -95,6 +105,7 @@ def main():
         "p121_book.res": lines(f"{REF}/5th_ed/p121/book/p121.res"), "p121_book.mg": lines(f"{REF}/5th_ed/p121/book/p121.mg"),
         "p123_book.res": lines(f"{REF}/5th_ed/p123/book/p123.res"), "p123_book.mg": lines(f"{REF}/5th_ed/p123/book/p123.mg"),
         "xx2-tiny.res": lines(x2 + ".res"), "xx2-tiny.dat": lines(x2 + ".dat"), "xx2-tiny.mat": lines(x2 + ".mat"),
+        "xx11.dat": lines(x11 + ".dat"),
         "p125_demo.res": lines(d125 + ".res"), "p125_demo.dat": lines(d125 + ".dat"),
         "p124_demo.res": lines(d124 + ".res"), "p124_demo.dat": lines(d124 + ".dat"), "p124_demo.mat": lines(d124 + ".mat"),
         "p124_book.res": lines(f"{REF}/5th_ed/p124/book/p124.res"), "p124_book.mg": lines(f"{REF}/5th_ed/p124/book/p124.mg"),

@@ -79,6 +79,7 @@ def test_gather_matvec_scatter_dot_equal_oracle(gpu, name):
     q = rng.randn(p.neq)
     assert gpu.dot(pv, q) == oracle.dot_blocked(pv, q)                  # maths.f90:210-214, blocked order
     assert gpu.norm(pv) == np.sqrt(oracle.dot_blocked(pv, pv))
+    assert gpu.sum(pv) == oracle.dot_blocked(pv, np.ones(p.neq))       # sum_p, maths.f90:271-315, blocked order
 
 
 def test_operator_properties(gpu):
@@ -130,6 +131,21 @@ def test_p123_fixed_freedom(gpu):
     assert iters == ref["iters"] and conv
     assert np.array_equal(x, ref["x"])
     assert abs(x[p.nres - 1] - 100.0) < 1e-6                              # the fixed freedom holds its value
+
+
+def test_xx11_fixed_freedom_golden(gpu, golden):
+    """examples/dev/xx11 (p123's deck format, nr = 0, 25 loaded + 25 fixed freedoms): the reference's only golden
+    on the penalty path -- xx11.ttr (written with 100 per loaded freedom, the shipped .lds holds 10)."""
+    p = host.read_deck_p123(os.path.join(golden, "xx11"))
+    p.r_pp *= 10.0
+    r0 = p.r_pp.copy()
+    solver.setup_problem(gpu, p)
+    x, iters, conv = gpu.pcg_solve(p.r_pp, p.tol, p.limit)
+    gold = np.loadtxt(os.path.join(golden, "xx11.ttr"), skiprows=2)[:, 1]
+    assert conv and iters == 11
+    assert np.abs(x - gold).max() <= 2e-4 * np.abs(gold).max()
+    ref = oracle.pcg(km_oracle(p), p.g_g_pp, p.neq, r0, p.tol, p.limit, npes=1, red_mode=1, no_f=p.no_f, val_f=p.val_f)
+    assert iters == ref["iters"] and np.array_equal(x, ref["x"])
 
 
 def test_xx3_tiny_deck_golden(gpu, tiny, golden):

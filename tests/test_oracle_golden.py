@@ -300,3 +300,23 @@ def test_p125_matrices_properties():
     store, mass = oracle.form_k_explicit(p.g_coord_pp, 8, 1.5, 2.0, 0.5, 1e-3)
     assert np.allclose(mass.sum(axis=1), .5 * .25 * .2, rtol=1e-13)
     assert np.allclose(store.sum(axis=1), mass, rtol=0, atol=1e-15)
+
+
+# ---- xx11: p123's deck format with nr = 0, loaded and fixed freedoms ------------------------------------
+
+def test_xx11_fixed_freedom_golden(golden):
+    """examples/dev/xx11/xx11.{dat,d,lds,fix,ttr}: 64 bricks, 125 nodes, no restrained nodes (g_g_pp = g_num_pp,
+    p123.f90:54), 25 loaded and 25 fixed freedoms (penalty rows, p123.f90:120-131,141-145) -- the only golden of
+    the reference that exercises the fixed-freedom path.  xx11.ttr was written with 100 per loaded freedom
+    (xx11.old.lds); the shipped xx11.lds holds 10, so the field is one tenth of it."""
+    p = host.read_deck_p123(os.path.join(golden, "xx11"))
+    assert (p.nels, p.nn, p.nr, p.neq, p.no_f.size, int(np.count_nonzero(p.r_pp))) == (64, 125, 0, 125, 25, 25)
+    assert np.array_equal(p.g_g_pp, p.g_num_pp) and (p.kx, p.ky, p.kz, p.tol, p.limit) == (100., 100., 100., 1e-5, 500)
+    kc = oracle.form_kc_laplace(p.g_coord_pp, p.nip, p.kx, p.ky, p.kz)
+    gold = np.loadtxt(os.path.join(golden, "xx11.ttr"), skiprows=2)[:, 1]
+    for red_mode, npes in ((0, 1), (0, 2), (1, 1)):
+        r = oracle.pcg(kc, p.g_g_pp, p.neq, 10.0 * p.r_pp, p.tol, p.limit, npes=npes, red_mode=red_mode, no_f=p.no_f,
+                       val_f=p.val_f)
+        assert r["converged"] and r["iters"] == 11
+        assert np.abs(r["x"] - gold).max() <= 2e-4 * np.abs(gold).max()      # 5 digits printed; tol 1e-5 solve
+        assert np.all(r["x"][p.no_f - 1] == 0.0)
