@@ -38,7 +38,46 @@ def problem(name, npes, numpe):
         return host.cube_p123(9, 11, 8, limit=500, npes=npes, numpe=numpe)
     if name == "p123_fixed":
         return host.cube_p123(9, 11, 8, limit=500, npes=npes, numpe=numpe, fixed=True)
+    if name in ("p124", "p124_fixed"):   # transient conduction: one PCG solve per time step
+        return host.cube_p124(9, 11, 8, aa=.1, bb=.1, cc=.1, nstep=6, npes=npes, numpe=numpe, fixed=name.endswith("fixed"))
+    if name == "p125":                   # explicit transient conduction
+        return host.cube_p125(9, 11, 8, aa=.1, bb=.1, cc=.1, dtim=1e-4, nstep=30, npes=npes, numpe=numpe)
+    if name == "hex20_mat":              # per-element materials (xx2)
+        p = host.cube_p121(6, 7, 5, 20, aa=1., bb=1., cc=1., limit=800, npes=npes, numpe=numpe)
+        rng = np.random.RandomState(3)
+        p.prop = np.column_stack([rng.uniform(50., 5000., 5), rng.uniform(0.05, 0.45, 5)])
+        p.etype_pp = rng.randint(1, 6, p.nels).astype(np.int32)[p.iel_start - 1:p.iel_start - 1 + p.nels_pp]
+        return p
     raise KeyError(name)
+
+
+def transient_specs(s, name, p, full, world):
+    """p124 / p125 on N ranks == the oracle emulating the same N ranks, step by step."""
+    lo = p.ieq_start - 1
+    solver.setup_problem(s, p)
+    ok = True
+    if name == "p125":
+        store, mass = oracle.form_k_explicit(full.g_coord_pp, full.nip, full.kx, full.ky, full.kz, full.dtim)
+        ref = oracle.p125(store, mass, full.g_g_pp, full.neq, full.val0, full.nstep, npes=world, keep=(1, 7, full.nstep))
+        s.explicit_start(p.val0)
+        done = 0
+        for j in (1, 7, full.nstep):
+            s.explicit_steps(j - done)
+            done = j
+            ok = ok and np.array_equal(s.pcg_get_x(), ref["fields"][j][lo:lo + p.neq_pp])
+        return ok, f"steps={full.nstep}"
+    a, b = oracle.form_k_transient(full.g_coord_pp, full.nip, full.kx, full.ky, full.kz, full.rho, full.cp, full.theta, full.dtim)
+    fixed = full.no_f.size > 0
+    ref = oracle.p124(a, b, full.g_g_pp, full.neq, full.val0, full.nstep, full.tol, full.limit, npes=world, red_mode=1,
+                      keep=tuple(range(1, full.nstep + 1)), no_f=full.no_f if fixed else None,
+                      val_f=full.val_f if fixed else None)
+    s.transient_start(p.val0, p.val_f if p.no_f.size else None)
+    its = []
+    for j in range(1, full.nstep + 1):
+        it, conv, _ = s.transient_step(p.tol, p.limit)
+        its.append(it)
+        ok = ok and it == ref["iters"][j - 1] and np.array_equal(s.pcg_get_x(), ref["fields"][j][lo:lo + p.neq_pp])
+    return ok, f"iters={its}/{ref['iters']}"
 
 
 def main():
@@ -53,6 +92,14 @@ def main():
         name, _, variant = spec.partition(":")
         p = problem(name, world, rank + 1)
         full = problem(name, 1, 1)
+        if name in ("p124", "p124_fixed", "p125"):
+            oracle.set_element_partition(None)
+            ok, info = transient_specs(s, name, p, full, world)
+            line = f"[rank {rank}] {spec}: equal={ok} {info}"
+            print(line, flush=True)
+            if not ok:
+                failures.append(line)
+            continue
         r0 = p.r_pp.copy()
         oracle.set_element_partition(uneven(full.nels, world) if name == "hex20_psize" else None)
         mf_mode = int(variant[2:]) if variant.startswith("mf") else 0
@@ -62,8 +109,11 @@ def main():
         rng = np.random.RandomState(11)
         pv = rng.randn(p.neq)
         qv = rng.randn(p.neq)
-        km = (oracle.form_km_elastic(full.g_coord_pp, full.nod, full.nip, full.e, full.v) if p.program == 121
-              else oracle.form_kc_laplace(full.g_coord_pp, full.nip, full.kx, full.ky, full.kz))
+        if full.prop is not None:
+            km = oracle.form_km_elastic_mat(full.g_coord_pp, full.nod, full.nip, full.prop, full.etype_pp)
+        else:
+            km = (oracle.form_km_elastic(full.g_coord_pp, full.nod, full.nip, full.e, full.v) if p.program == 121
+                  else oracle.form_kc_laplace(full.g_coord_pp, full.nip, full.kx, full.ky, full.kz))
         if variant == "sym":      # K(i,j) = L(max,min): the oracle on the symmetrised matrices
             km = np.triu(km) + np.triu(km, 1).transpose(0, 2, 1)
         mf = dict(g_coord_pp=full.g_coord_pp, nod=full.nod, nip=full.nip, e=full.e, v=full.v) if mf_mode else None
