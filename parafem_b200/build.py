@@ -44,11 +44,12 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed building libparafem_b200.so")
         with open(os.path.join(_HERE, "ptxas_info.txt"), "w") as f:
             f.write(res.stdout)
-    drv_src = os.path.join(CSRC, "p121_b200.cpp")
-    if os.path.exists(drv_src) and (force or _stale(DRIVER, [drv_src, LIB])):
-        cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), drv_src,
-               "-o", DRIVER, "-L", _HERE, "-lparafem_b200", "-Wl,-rpath,$ORIGIN"]
-        subprocess.run(cmd, check=True)
+    for name in ("p121_b200", "p12x_b200"):          # host drivers above the C-ABI (no Fortran compiler here)
+        drv_src, exe = os.path.join(CSRC, name + ".cpp"), os.path.join(_HERE, name)
+        if os.path.exists(drv_src) and (force or _stale(exe, [drv_src, LIB])):
+            cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), drv_src,
+                   "-o", exe, "-L", _HERE, "-lparafem_b200", "-Wl,-rpath,$ORIGIN"]
+            subprocess.run(cmd, check=True)
     return LIB
 
 

@@ -68,6 +68,35 @@ def test_python_driver_p123(tmp_path):
     assert res["converged"]
 
 
+def test_cpp_scalar_driver_reproduces_p124_and_p125_golden_logs(golden):
+    """p12x_b200 (C++ host code above the C-ABI) on the 25^3 demo box, deck-rounded coordinates: every
+    '  Time  Temperature  Iterations' line of p124_demo.res and every '  Time  Pressure' line of p125_demo.res,
+    as text."""
+    exe = os.path.join(ROOT, "parafem_b200", "p12x_b200")
+    for prog, pat in (("p124", r"^\s+0\.\d+E[+-]\d+\s+0\.\d+E[+-]\d+\s+\d+\s*$"), ("p125", r"^\s+0\.\d+E[+-]\d+\s+0\.\d+E[+-]\d+\s*$")):
+        res = subprocess.run([exe, prog, "25", "1"], capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stderr
+        out = res.stdout.splitlines()
+        rows = [l for l in open(os.path.join(golden, f"{prog}_demo.res")).read().splitlines() if re.match(pat, l)]
+        assert len(rows) == (15 if prog == "p124" else 11)
+        for line in rows:
+            assert line in out, (prog, line, out)
+        assert [int(v) for v in re.findall(r"\d+", [l for l in out if l.startswith("There are")][0])] == [17576, 1951, 15625]
+
+
+def test_cpp_scalar_driver_p123_matches_python_driver():
+    exe = os.path.join(ROOT, "parafem_b200", "p12x_b200")
+    res = subprocess.run([exe, "p123", "20"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr
+    p = host.cube_p123(20, 20, 20, limit=10000)
+    with solver.Solver(0, 1, 0) as s:
+        ref = driver.run(p, s)
+    it = int(re.search(r"iterations to convergence was\s+(\d+)", res.stdout).group(1))
+    assert it == ref["iters"]
+    assert f"{p.nres:8d}     {driver._fe(ref['x'][p.nres - 1])}" in res.stdout.splitlines()
+    assert "The total load is   0.1000E+02" in res.stdout
+
+
 def test_driver_cli_writes_res_and_ensight(tmp_path):
     rc = driver.main(["--cube", "10", "--out", str(tmp_path)])
     assert rc == 0
@@ -80,6 +109,12 @@ def test_driver_cli_writes_res_and_ensight(tmp_path):
     assert rc == 0
     ens = open(tmp_path / "p123_box8.ensi.NDPTL-000001").read().splitlines()
     assert ens[0].startswith("Alya Ensight Gold --- Scalar") and len(ens) == 4 + 9 ** 3
+    assert driver.main(["--p124", "6", "--out", str(tmp_path)]) == 0
+    assert len(open(tmp_path / "p124_box6.res").read().splitlines()) == 4 + 1 + 15 + 3
+    assert os.path.exists(tmp_path / "p124_box6.ensi.NDTTR-000150")
+    assert driver.main(["--p125", "6", "--out", str(tmp_path)]) == 0
+    assert len(open(tmp_path / "p125_box6.res").read().splitlines()) == 6 + 11 + 2
+    assert os.path.exists(tmp_path / "p125_box6.ensi.NDPRE-005000")
 
 
 def test_bad_arguments_return_status_codes():
