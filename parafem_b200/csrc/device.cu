@@ -914,7 +914,12 @@ int pf_form_km_elastic(pf_handle h, double e, double v) {
     }
   } else if ((rc = alloc_km(h))) return rc;
   const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 16);
-  if (h->nod == 20) k_form_km_elastic<20, 128><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, diag_only, h->km_layout);
+  // PF_FORM=old: the first (untiled) build of the full matrix, kept for comparison
+  static const bool old_form = getenv("PF_FORM") && !strcmp(getenv("PF_FORM"), "old");
+  if (!diag_only && !old_form) {
+    if (h->nod == 20) k_form_km_tiled<20, 2, 2, 128, false><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout, nullptr, nullptr);
+    else k_form_km_tiled<8, 1, 1, 64, false><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout, nullptr, nullptr);
+  } else if (h->nod == 20) k_form_km_elastic<20, 128><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, diag_only, h->km_layout);
   else k_form_km_elastic<8, 64><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, diag_only, h->km_layout);
   h->launches++;
   CU(cudaGetLastError());
@@ -946,8 +951,8 @@ int pf_form_km_elastic_mat(pf_handle h, int np_types, const double *prop, const 
   CU(cudaMemcpy(d_etype.p, etype_pp, (size_t)h->nels * 4, cudaMemcpyHostToDevice));
   if ((rc = alloc_km(h))) return rc;
   const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 16);
-  if (h->nod == 20) k_form_km_elastic<20, 128, true><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, nullptr, h->km_layout, d_dee.p, d_etype.p);
-  else k_form_km_elastic<8, 64, true><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, nullptr, h->km_layout, d_dee.p, d_etype.p);
+  if (h->nod == 20) k_form_km_tiled<20, 2, 2, 128, true><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout, d_dee.p, d_etype.p);
+  else k_form_km_tiled<8, 1, 1, 64, true><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout, d_dee.p, d_etype.p);
   h->launches++;
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));

@@ -940,6 +940,134 @@ k_form_km_elastic(const double *__restrict__ g_coord, double *__restrict__ km, l
 }
 
 
+// elements_1 of p121.f90:56-64 again, register-tiled: the version that forms the whole storkm_pp.
+// One CTA per element.  (1) jac / det / inverse / deriv of ALL Gauss points at once (no barrier per point);
+// (2) thread (ta,tb) owns the TA x TB node block of km = 3TA x 3TB entries in registers and walks the
+// Gauss points in order: btd = MATMUL(TRANSPOSE(bee),dee) and km += (btd*bee)*det*w are evaluated from the
+// node derivatives directly, with exactly the reference's products in the reference's order (l, k ascending)
+// MINUS the products that have a structural zero of bee or dee as a factor -- those contribute +-0.0 and
+// can only change the sign of a zero; (3) the element matrix is staged in shared memory and written out in
+// 128-bit coalesced stores (or packed).  21 products per 3x3 node block and point instead of 54, and 0.1
+// shared loads per product instead of 2: the first build (k_form_km_elastic above, kept for the matrix-free
+// diagonal) was bound by its shared-memory loads at ~19 % of the FP64 pipe.
+template <int NOD, int TA, int TB, int THREADS, bool MAT>
+__global__ void __launch_bounds__(THREADS)
+k_form_km_tiled(const double *__restrict__ g_coord, double *__restrict__ km, long long nels, int packed,
+                const double *__restrict__ dee_tab, const int *__restrict__ etype) {
+  constexpr int NTOT = 3 * NOD, NENT = NTOT * NTOT, NA = NOD / TA, NB = NOD / TB, MAXIP = 8;
+  static_assert(NOD % TA == 0 && NOD % TB == 0 && NA * NB <= THREADS && NENT % 2 == 0, "tile shape");
+  __shared__ double s_coord[NOD * 3], s_jac[MAXIP * 9], s_det[MAXIP], s_dee[36];
+  __shared__ double s_deriv[MAXIP * NOD * 3];            // [ig][m*3+a] = deriv(a,m) at Gauss point ig
+  __shared__ __align__(16) double s_km[NENT];
+  const int nip = c_tab.nip, t = threadIdx.x;
+  const int ta = t % NA, tb = t / NA;
+  for (long long e = blockIdx.x; e < nels; e += gridDim.x) {
+    __syncthreads();                                      // the previous element's s_km has been written out
+    for (int q = t; q < NOD * 3; q += THREADS) s_coord[q] = g_coord[e * NOD * 3 + q];
+    if (t < 36) s_dee[t] = MAT ? dee_tab[(long long)(etype[e] - 1) * 36 + t] : c_tab.dee[t];
+    __syncthreads();
+    for (int q = t; q < nip * 9; q += THREADS) {          // jac = MATMUL(der,coord), every point
+      const int ig = q / 9, r = q - 9 * ig, a = r % 3, b = r / 3;
+      const double *der = c_tab.der + ig * 60;
+      double sum = 0.0;
+#pragma unroll
+      for (int m = 0; m < NOD; ++m) sum = sum + der[a * 20 + m] * s_coord[b * NOD + m];
+      s_jac[ig * 9 + b * 3 + a] = sum;
+    }
+    __syncthreads();
+    if (t < nip) {                                        // determinant, invert
+      double jac[9], inv[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) jac[q] = s_jac[t * 9 + q];
+      const double det = det3(jac);
+      inv3(jac, det, inv);
+#pragma unroll
+      for (int q = 0; q < 9; ++q) s_jac[t * 9 + q] = inv[q];
+      s_det[t] = det;
+    }
+    __syncthreads();
+    for (int q = t; q < nip * NOD * 3; q += THREADS) {    // deriv = MATMUL(jac^-1,der)
+      const int ig = q / (NOD * 3), r = q - ig * (NOD * 3), m = r / 3, a = r - 3 * m;
+      const double *der = c_tab.der + ig * 60, *inv = s_jac + ig * 9;
+      double sum = 0.0;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) sum = sum + inv[b * 3 + a] * der[b * 20 + m];
+      s_deriv[q] = sum;
+    }
+    __syncthreads();
+    if (tb < NB) {
+      // D(l,k) = dee(l,k); only the entries an isotropic dee holds
+      const double d00 = s_dee[0], d10 = s_dee[1], d20 = s_dee[2];        // dee(:,0) at [0*6+l]
+      const double d01 = s_dee[6], d11 = s_dee[7], d21 = s_dee[8];
+      const double d02 = s_dee[12], d12 = s_dee[13], d22 = s_dee[14];
+      const double d33 = s_dee[21], d44 = s_dee[28], d55 = s_dee[35];
+      double acc[TA][TB][9];
+#pragma unroll
+      for (int ia = 0; ia < TA; ++ia)
+#pragma unroll
+        for (int ib = 0; ib < TB; ++ib)
+#pragma unroll
+          for (int q = 0; q < 9; ++q) acc[ia][ib][q] = 0.0;
+      for (int ig = 0; ig < nip; ++ig) {
+        const double det = s_det[ig], wt = c_tab.weights[ig];
+        const double *dv = s_deriv + ig * (NOD * 3);
+        double xb[TB], yb[TB], zb[TB];
+#pragma unroll
+        for (int ib = 0; ib < TB; ++ib) {
+          const int b = tb * TB + ib;
+          xb[ib] = dv[b * 3]; yb[ib] = dv[b * 3 + 1]; zb[ib] = dv[b * 3 + 2];
+        }
+#pragma unroll
+        for (int ia = 0; ia < TA; ++ia) {
+          const int a = ta * TA + ia;
+          const double x = dv[a * 3], y = dv[a * 3 + 1], z = dv[a * 3 + 2];
+          // btd(3a+p,k) = sum_l bee(l,3a+p)*dee(l,k): one surviving product each
+          const double b00 = x * d00, b01 = x * d01, b02 = x * d02, b03 = y * d33, b05 = z * d55;
+          const double b10 = y * d10, b11 = y * d11, b12 = y * d12, b13 = x * d33, b14 = z * d44;
+          const double b20 = z * d20, b21 = z * d21, b22 = z * d22, b24 = y * d44, b25 = x * d55;
+#pragma unroll
+          for (int ib = 0; ib < TB; ++ib) {
+            const double X = xb[ib], Y = yb[ib], Z = zb[ib];
+            double *A = acc[ia][ib];                     // A[q*3+p] = km(3a+p, 3b+q)
+            double s;
+            s = b00 * X; s = s + b03 * Y; s = s + b05 * Z; A[0] = A[0] + s * det * wt;   // (0,0): k = 0,3,5
+            s = b10 * X; s = s + b13 * Y;                  A[1] = A[1] + s * det * wt;   // (1,0): k = 0,3
+            s = b20 * X; s = s + b25 * Z;                  A[2] = A[2] + s * det * wt;   // (2,0): k = 0,5
+            s = b01 * Y; s = s + b03 * X;                  A[3] = A[3] + s * det * wt;   // (0,1): k = 1,3
+            s = b11 * Y; s = s + b13 * X; s = s + b14 * Z; A[4] = A[4] + s * det * wt;   // (1,1): k = 1,3,4
+            s = b21 * Y; s = s + b24 * Z;                  A[5] = A[5] + s * det * wt;   // (2,1): k = 1,4
+            s = b02 * Z; s = s + b05 * X;                  A[6] = A[6] + s * det * wt;   // (0,2): k = 2,5
+            s = b12 * Z; s = s + b14 * Y;                  A[7] = A[7] + s * det * wt;   // (1,2): k = 2,4
+            s = b22 * Z; s = s + b24 * Y; s = s + b25 * X; A[8] = A[8] + s * det * wt;   // (2,2): k = 2,4,5
+          }
+        }
+      }
+#pragma unroll
+      for (int ia = 0; ia < TA; ++ia)
+#pragma unroll
+        for (int ib = 0; ib < TB; ++ib)
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int pp = 0; pp < 3; ++pp)
+              s_km[(3 * (tb * TB + ib) + q) * NTOT + 3 * (ta * TA + ia) + pp] = acc[ia][ib][q * 3 + pp];
+    }
+    __syncthreads();
+    if (!packed) {
+      double2 *dst = reinterpret_cast<double2 *>(km + e * (long long)NENT);
+      const double2 *src = reinterpret_cast<const double2 *>(s_km);
+      for (int q = t; q < NENT / 2; q += THREADS) dst[q] = src[q];
+    } else {
+      double *dst = km + e * (long long)SymCfg<NTOT>::kPacked;
+      for (int q = t; q < NENT; q += THREADS) {
+        const int j = q / NTOT, i = q - j * NTOT;
+        if (i >= j) dst[SymCfg<NTOT>::coloff(j) + (i - j)] = s_km[q];
+      }
+    }
+  }
+}
+
+
 // ----------------------------------------------------------------------------
 // BASELINE config E: matrix-free element products, utemp(:,e) = sum_gp B^T (D (B p)) det w
 // ----------------------------------------------------------------------------
