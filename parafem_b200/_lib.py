@@ -109,6 +109,17 @@ SIGNATURES = {
     "pf_make_ggl": (c_int, [c_int, c_i64, vp, c_i64, c_int, c_int, vp, c_i64, vp, vp, P(c_i64)]),
 }
 
+# the reference's existing CUDA boundary (include/parafem_xx3_compat.h = xx3.f90:56-148): scalars by reference
+PI = P(c_int)
+XX3_SIGNATURES = {
+    "set_gpu": (c_int, [PI]),
+    "allocate_memory_on_gpu": (c_int, [PI, PI, P(vp)]),
+    "free_memory_on_gpu": (c_int, [P(vp)]),
+    "copy_data_to_gpu": (c_int, [PI, PI, vp, P(vp)]),
+    "copy_data_from_gpu": (c_int, [PI, PI, vp, P(vp)]),
+    "matrix_vector_multiplies": (c_int, [PI, PI, PI, P(vp), P(vp), P(vp)]),
+}
+
 _lib = None
 
 
@@ -120,7 +131,7 @@ def lib():
             raise PfError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the device path.")
         L = C.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
+        for name, (res, args) in list(SIGNATURES.items()) + list(XX3_SIGNATURES.items()):
             fn = getattr(L, name)  # AttributeError here = header/library mismatch
             fn.restype = res
             fn.argtypes = args

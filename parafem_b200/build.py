@@ -33,7 +33,8 @@ def _stale(target, sources):
 
 def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, f) for f in ("device.cu", "host.cpp")]
-    deps = srcs + [os.path.join(CSRC, "kernels.cuh"), os.path.join(ROOT, "include", "parafem_b200.h")]
+    deps = srcs + [os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "xx3_compat.cuh"),
+                   os.path.join(ROOT, "include", "parafem_b200.h"), os.path.join(ROOT, "include", "parafem_xx3_compat.h")]
     if force or _stale(LIB, deps):
         cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-I", os.path.join(ROOT, "include"), "-I", "/usr/include",
                                         "-o", LIB] + srcs + ["-lgomp", "-ldl"]

@@ -1524,3 +1524,5 @@ int pf_centroid_stress(pf_handle h, int64_t iel, double e, double v, double *sig
 }
 
 }  // extern "C"
+
+#include "xx3_compat.cuh"

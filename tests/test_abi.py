@@ -28,6 +28,17 @@ def test_every_declared_symbol_is_exported_and_bound():
     _lib.lib()
 
 
+def test_xx3_compat_symbols_are_exported():
+    """include/parafem_xx3_compat.h: the six names xx3.f90:56-148 binds today, so xx3 links unchanged."""
+    txt = open(os.path.join(ROOT, "include", "parafem_xx3_compat.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    syms = sorted(set(re.findall(r"\bint\s+([a-z_0-9]+)\s*\(", txt)))
+    assert syms == sorted(_lib.XX3_SIGNATURES) and len(syms) == 6
+    L = C.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(L, s), s
+
+
 def test_signatures_are_plain_c():
     """No C++/torch types in the boundary: only C scalars, pointers and one POD struct."""
     txt = open(os.path.join(ROOT, "include", "parafem_b200.h")).read()
