@@ -114,6 +114,10 @@ struct pf_ctx {
   DevBuf<int> fix_slot;
   DevBuf<double> store;
 
+  // one PCG iteration captured as a CUDA graph (single rank; re-captured when the problem changes)
+  cudaGraphExec_t graph_exec = nullptr;
+  int64_t epoch = 0, graph_epoch = -1, graph_launches = 0;
+
   // profiling
   bool profile = false;
   struct Span { cudaEvent_t a, b; int kind; };
@@ -631,6 +635,7 @@ int pf_finalize(pf_handle h) {
   cudaStreamSynchronize(h->stream);
   collect_spans(h);
   for (auto e : h->pool) cudaEventDestroy(e);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   close_imports(h);
   if (h->comm) {
     // peers must have closed their mappings of my buffers before I free them
@@ -1105,7 +1110,7 @@ int pf_form_k_explicit(pf_handle h, double kx, double ky, double kz, double dtim
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));
   h->diag_tmp.release();
-  h->have_km = true; h->have_precon = true; h->explicit_ = true;
+  h->have_km = true; h->have_precon = true; h->explicit_ = true; h->epoch++;
   return 0;
 }
 
@@ -1255,6 +1260,7 @@ int pf_build_precon(pf_handle h, int64_t nfixed_pp, const int32_t *no_f_pp, doub
   CU(cudaStreamSynchronize(h->stream));
   h->diag_tmp.release();
   h->have_precon = true;
+  h->epoch++;
   return 0;
 }
 
@@ -1284,7 +1290,7 @@ int pf_pcg_run(pf_handle h, double tol, int limit, int *iters, int *converged, d
   int rc = need_device(h); if (rc) return rc;
   NEED(h->have_precon, "needs pf_build_precon");
   NEED(limit >= 1, "limit must be >= 1");
-  if (h->ratio_cap < limit) { CU(h->ratio_hist.alloc((size_t)limit)); h->ratio_cap = limit; }
+  if (h->ratio_cap < limit) { CU(h->ratio_hist.alloc((size_t)limit)); h->ratio_cap = limit; h->epoch++; }
   State init; memset(&init, 0, sizeof init);
   init.tol = tol; init.limit = limit;
   CU(cudaMemcpyAsync(h->state.p, &init, sizeof init, cudaMemcpyHostToDevice, h->stream));
@@ -1297,12 +1303,38 @@ int pf_pcg_run(pf_handle h, double tol, int limit, int *iters, int *converged, d
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
   CU(cudaEventRecord(e0, h->stream));  // timest(3), p121.f90:89
+  // Single rank: the iteration (5 launches with constant arguments) is captured once per problem as a CUDA graph
+  // and replayed -- at config B / p124 sizes the launch gaps were ~15 % of an iteration.  PF_GRAPH=0 disables it.
+  static const bool graph_allowed = !(getenv("PF_GRAPH") && !strcmp(getenv("PF_GRAPH"), "0"));
+  bool use_graph = graph_allowed && h->nranks == 1 && !h->profile;
+  if (use_graph && (!h->graph_exec || h->graph_epoch != h->epoch)) {
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    cudaGraph_t g = nullptr;
+    const int64_t l0 = h->launches;
+    CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+    rc = one_iteration(h);
+    const cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+    h->graph_launches = h->launches - l0;
+    h->launches = l0;
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (ce != cudaSuccess || !g || cudaGraphInstantiate(&h->graph_exec, g, 0) != cudaSuccess) {
+      cudaGetLastError();
+      h->graph_exec = nullptr;
+      use_graph = false;                             // plain stream launches
+    }
+    if (g) cudaGraphDestroy(g);
+    h->graph_epoch = h->epoch;
+  }
+  use_graph = use_graph && h->graph_exec;
   State snap;
   const int batch = 8;
   int queued = 0;
   for (;;) {
     const int nb = std::min(batch, limit - queued);
-    for (int k = 0; k < nb; ++k) if ((rc = one_iteration(h))) return rc;
+    for (int k = 0; k < nb; ++k) {
+      if (use_graph) { CU(cudaGraphLaunch(h->graph_exec, h->stream)); h->launches += h->graph_launches; }
+      else if ((rc = one_iteration(h))) return rc;
+    }
     queued += nb;
     CU(cudaMemcpyAsync(&snap, h->state.p, sizeof snap, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
