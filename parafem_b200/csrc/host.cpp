@@ -659,11 +659,26 @@ int pf_make_ggl(int ntot, int64_t nels_pp, const int32_t *g_g_pp, int64_t neq, i
   // remote equations referenced by local elements, sorted unique; ascending
   // global number == ascending owner rank because ownership is contiguous
   std::vector<int32_t> remote;
-  for (int64_t i = 0; i < total; ++i) {
-    int64_t g = g_g_pp[i];
-    if (g < 0 || g > neq) return 2;
-    if (g != 0 && (g < lo || g >= hi)) remote.push_back((int32_t)g);
+  int bad = 0;
+#pragma omp parallel
+  {
+    std::vector<int32_t> mine;
+    int bad_t = 0;
+#pragma omp for schedule(static) nowait
+    for (int64_t i = 0; i < total; ++i) {
+      int64_t g = g_g_pp[i];
+      if (g < 0 || g > neq) bad_t = 1;
+      else if (g != 0 && (g < lo || g >= hi)) mine.push_back((int32_t)g);
+    }
+    std::sort(mine.begin(), mine.end());
+    mine.erase(std::unique(mine.begin(), mine.end()), mine.end());
+#pragma omp critical
+    {
+      remote.insert(remote.end(), mine.begin(), mine.end());
+      bad |= bad_t;
+    }
   }
+  if (bad) return 2;
   std::sort(remote.begin(), remote.end());
   remote.erase(std::unique(remote.begin(), remote.end()), remote.end());
   *nhalo = (int64_t)remote.size();

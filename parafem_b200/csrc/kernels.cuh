@@ -1504,6 +1504,30 @@ __global__ void k_scale(double *__restrict__ dst, const double *__restrict__ a, 
   for (; i < n; i += stride) dst[i] = a[i] * b[i];
 }
 
+// scatter tables on the device (pf_setup_mesh): positions 0..n-1, and csr_ptr from the sorted slot numbers:
+// csr_ptr[s] = (number of sorted keys < s) - (number of keys == 0) for s >= 1, csr_ptr[0] = 0 -- slot 0, the
+// restrained dump slot, keeps no contributions
+__global__ void k_iota(unsigned int *__restrict__ v, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) v[i] = (unsigned int)i;
+}
+__device__ __forceinline__ long long lower_bound_i32(const int *__restrict__ keys, long long n, int s) {
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (keys[mid] < s) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__global__ void k_csr_ptr(const int *__restrict__ sorted_keys, long long n, unsigned int *__restrict__ ptr, long long nslots) {
+  const long long n0 = lower_bound_i32(sorted_keys, n, 1);
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; s <= nslots; s += stride)
+    ptr[s] = s == 0 ? 0u : (unsigned int)((s == nslots ? n : lower_bound_i32(sorted_keys, n, (int)s)) - n0);
+}
+
 // p124 time stepping, right-hand side of one step (p124.f90:143-200):
 //   loads = (loaded freedoms, or 0) + u ;  r = loads - r0 with r0 = +0.0 off the fixed freedoms
 __global__ void k_transient_rhs(double *__restrict__ r, const double *__restrict__ loads, const double *__restrict__ u, long long n) {
