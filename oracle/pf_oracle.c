@@ -12,10 +12,17 @@
  * (tests/golden/, tests/test_oracle_golden.py): xx3-tiny 79 iterations +
  * 756x3 displacements, p121_demo 98 360 equations / 295 iterations / x(1) /
  * centroid stresses / EnSight displacement field, p121 book 777 520 equations,
- * p123 potentials.
+ * p123 potentials; and for the drivers that reuse the same kernels: p124_demo
+ * (all fifteen temperature / iteration rows + nodal temperature files), p125_demo
+ * (all ten pressure rows + nodal files), xx2-tiny (five materials: 59 iterations +
+ * displacements), xx11 (fixed-freedom path: 125 temperatures).
  *
  * Reference files followed (under /root/reference/parafem/src):
  *   programs/5th_ed/p121/p121.f90 (whole), programs/5th_ed/p123/p123.f90 (whole)
+ *   programs/5th_ed/p124/p124.f90:81-95,139-232, programs/5th_ed/p125/p125.f90:66-99,
+ *   programs/dev/xx2/xx2.f90:169-193 (the time loops / material loop are composed from
+ *   these C functions in oracle/__init__.py: p124(), p125(), form_km_elastic_mat())
+ *   modules/shared/new_library.f90: shape_fun :204-484 (3-D nod = 8 branch :397-422)
  *   modules/shared/new_library.f90: shape_der :745-896, beemat :918-1000,
  *       sample :1397-1520, deemat :1604-1691, rearrange :3059-3112,
  *       rearrange_2 :3118-3124, find_g3 :3130-3212, find_g4 :3249-3271
