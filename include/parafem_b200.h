@@ -63,8 +63,10 @@ int pf_version(void);
  * gather_scatter.f90:50-70, PRIVATE there) are rebuilt inside the library
  * from g_g_pp and the closed-form owner map of calc_neq_pp
  * (gather_scatter.f90:319-339), so the Fortran module needs no accessor.
- *   nod          nodes per element (8 or 20), nodof dof per node (3 or 1)
- *   nip          Gauss points (1, 8)
+ *   nod          nodes per element: 8 or 20 (hexahedra) or 4 (tetrahedra; shape_der nod = 4,
+ *                new_library.f90:757-767, with sample('tetrahedron') nip = 1, :1329-1341);
+ *                nodof dof per node (3 or 1)
+ *   nip          integrating points (1 or 8; 1 for tetrahedra)
  *   nels_pp      elements of this rank
  *   g_coord_pp   (nod, ndim=3, nels_pp) coordinates        [p121.f90:33]
  *   g_g_pp       (ntot, nels_pp) global equation numbers, 0 = restrained

@@ -110,10 +110,11 @@ def form_km_elastic_mat(g_coord_pp, nod, nip, prop, etype):
 
 
 def form_kc_laplace(g_coord_pp, nip, kx, ky, kz):
+    """p123.f90:70-84; 8-node bricks or (nip = 1) 4-node tetrahedra, from the last axis of g_coord_pp."""
     g = _f64(g_coord_pp)
-    nels = g.shape[0]
-    out = np.empty((nels, 8, 8))
-    rc = lib().orc_form_kc_laplace(nels, 8, nip, _p(g), kx, ky, kz, _p(out))
+    nels, nod = g.shape[0], g.shape[2]
+    out = np.empty((nels, nod, nod))
+    rc = lib().orc_form_kc_laplace(nels, nod, nip, _p(g), kx, ky, kz, _p(out))
     assert rc == 0
     return out
 

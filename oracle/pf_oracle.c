@@ -78,11 +78,29 @@ int orc_sample_hex(int nip, double *points, double *weights) {
   return 1;
 }
 
+/* sample('tetrahedron'), nip = 1 (new_library.f90:1329-1341): the centroid, weight 1/6.  The 4- and 5-point
+ * rules are written with single-precision literals there and are not restated. */
+int orc_sample_tet(int nip, double *points, double *weights) {
+  if (nip != 1) return 1;
+  points[0] = points[1] = points[2] = 0.25; weights[0] = 1.0 / 6.0;
+  return 0;
+}
+/* the rule of an element with nod nodes: tetrahedron for nod = 4, hexahedron otherwise */
+static int sample_for(int nod, int nip, double *points, double *weights) {
+  return nod == 4 ? orc_sample_tet(nip, points, weights) : orc_sample_hex(nip, points, weights);
+}
+
 /* shape_der for 3-D nod = 8 / 20 at Gauss point i (0-based); der(3,nod) col-major,
  * new_library.f90:745-755, 769-794, 865-896 */
 int orc_shape_der(int nod, const double *points, int nip, int i, double *der) {
   const double xi = points[0 * nip + i], eta = points[1 * nip + i], zeta = points[2 * nip + i];
 #define DER(a, l) der[((l)-1) * 3 + ((a)-1)]
+  if (nod == 4) {   /* 4-node tetrahedron, new_library.f90:757-767: constant derivatives */
+    for (int q = 0; q < 12; ++q) der[q] = 0.0;
+    DER(1, 1) = 1.0; DER(2, 2) = 1.0; DER(3, 3) = 1.0;
+    DER(1, 4) = -1.0; DER(2, 4) = -1.0; DER(3, 4) = -1.0;
+    return 0;
+  }
   if (nod == 8) {
     const double etam = 1.0 - eta, xim = 1.0 - xi, zetam = 1.0 - zeta;
     const double etap = eta + 1.0, xip = xi + 1.0, zetap = zeta + 1.0;
@@ -212,10 +230,10 @@ static double gauss_point(int nod, const double *points, int nip, int ig, const 
  * g_coord_pp(nod,3,nels), storkm_pp(ntot,ntot,nels), ntot = 3*nod. */
 int orc_form_km_elastic(int64_t nels, int nod, int nip, const double *g_coord_pp, double e,
                         double v, double *storkm_pp) {
-  if ((nod != 8 && nod != 20) || (nip != 1 && nip != 8)) return 1;
+  if ((nod != 4 && nod != 8 && nod != 20) || (nip != 1 && nip != 8) || (nod == 4 && nip != 1)) return 1;
   const int ntot = 3 * nod;
   double points[24], weights[8], dee[36];
-  orc_sample_hex(nip, points, weights);
+  sample_for(nod, nip, points, weights);
   orc_deemat6(dee, e, v);
 #pragma omp parallel
   {
@@ -253,9 +271,10 @@ int orc_form_km_elastic(int64_t nels, int nod, int nip, const double *g_coord_pp
 /* elements_1 of p123.f90:70-84: kcx,kcy,kcz outer products; storkc_pp(8,8,nels) */
 int orc_form_kc_laplace(int64_t nels, int nod, int nip, const double *g_coord_pp, double kx,
                         double ky, double kz, double *storkc_pp) {
-  if (nod != 8 || (nip != 1 && nip != 8)) return 1;
+  if ((nod != 8 && nod != 4) || (nip != 1 && nip != 8) || (nod == 4 && nip != 1)) return 1;
   double points[24], weights[8];
-  orc_sample_hex(nip, points, weights);
+  sample_for(nod, nip, points, weights);
+  const int nn2 = nod * nod;
 #pragma omp parallel for schedule(static)
   for (int64_t iel = 0; iel < nels; ++iel) {
     double der[24], deriv[24], kc[3][64];
@@ -263,12 +282,12 @@ int orc_form_kc_laplace(int64_t nels, int nod, int nip, const double *g_coord_pp
     for (int ig = 0; ig < nip; ++ig) {
       const double det = gauss_point(nod, points, nip, ig, g_coord_pp + iel * nod * 3, der, deriv);
       for (int a = 0; a < 3; ++a)
-        for (int j = 0; j < 8; ++j)
-          for (int i = 0; i < 8; ++i)
-            kc[a][j * 8 + i] = kc[a][j * 8 + i] + deriv[i * 3 + a] * deriv[j * 3 + a] * det * weights[ig];
+        for (int j = 0; j < nod; ++j)
+          for (int i = 0; i < nod; ++i)
+            kc[a][j * nod + i] = kc[a][j * nod + i] + deriv[i * 3 + a] * deriv[j * 3 + a] * det * weights[ig];
     }
-    double *out = storkc_pp + iel * 64;
-    for (int q = 0; q < 64; ++q) out[q] = kc[0][q] * kx + kc[1][q] * ky + kc[2][q] * kz;
+    double *out = storkc_pp + iel * nn2;
+    for (int q = 0; q < nn2; ++q) out[q] = kc[0][q] * kx + kc[1][q] * ky + kc[2][q] * kz;
   }
   return 0;
 }
@@ -336,7 +355,7 @@ int orc_form_k_transient(int64_t nels, int nod, int nip, const double *g_coord_p
 /* centroid stresses, p121.f90:113-123: one point at (0,0,0); sigma = dee*(bee*eld) */
 int orc_centroid_stress(int nod, const double *coord, const double *eld, double e, double v,
                         double *sigma) {
-  if (nod != 8 && nod != 20) return 1;
+  if (nod != 4 && nod != 8 && nod != 20) return 1;
   const int ntot = 3 * nod;
   double points[3] = {0, 0, 0}, der[60], deriv[60], dee[36], eps[6];
   double *bee = malloc(sizeof(double) * 6 * ntot);

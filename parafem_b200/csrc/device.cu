@@ -186,7 +186,10 @@ int grid_for(pf_handle h, int64_t n, int threads, int per_sm = 8) {
 int fill_tables(int nod, int nip, double e, double v, double kx, double ky, double kz, ElemTables &T) {
   memset(&T, 0, sizeof T);
   double pts[8][3];
-  if (nip == 1) { pts[0][0] = pts[0][1] = pts[0][2] = 0.0; T.weights[0] = 8.0; }
+  if (nod == 4) {          // sample('tetrahedron'), nip = 1 (new_library.f90:1329-1341): centroid, weight 1/6
+    if (nip != 1) return 1;
+    pts[0][0] = pts[0][1] = pts[0][2] = 0.25; T.weights[0] = 1.0 / 6.0;
+  } else if (nip == 1) { pts[0][0] = pts[0][1] = pts[0][2] = 0.0; T.weights[0] = 8.0; }
   else if (nip == 8) {
     const double r3 = 1.0 / std::sqrt(3.0);
     for (int i = 0; i < 8; ++i) {
@@ -200,7 +203,10 @@ int fill_tables(int nod, int nip, double e, double v, double kx, double ky, doub
   for (int ig = 0; ig < nip; ++ig) {
     const double xi = pts[ig][0], eta = pts[ig][1], zeta = pts[ig][2];
     double *D = T.der + ig * 60;  // D[a*20+m]
-    if (nod == 8) {
+    if (nod == 4) {        // shape_der, 3-D nod = 4 (new_library.f90:757-767): constant
+      D[0] = 1.0; D[20 + 1] = 1.0; D[40 + 2] = 1.0;
+      D[3] = -1.0; D[20 + 3] = -1.0; D[40 + 3] = -1.0;
+    } else if (nod == 8) {
       const double em = 1.0 - eta, xm = 1.0 - xi, zm = 1.0 - zeta, ep = eta + 1.0, xp = xi + 1.0, zp = zeta + 1.0;
       const double dx[8] = {-0.125 * em * zm, -0.125 * em * zp, 0.125 * em * zp, 0.125 * em * zm,
                             -0.125 * ep * zm, -0.125 * ep * zp, 0.125 * ep * zp, 0.125 * ep * zm};
@@ -355,8 +361,10 @@ int launch_matvec(pf_handle h, const double *pvec, const State *st) {
     case 8:
       if (tune == 1) return launch_matvec_t<8, 64, 6, GATHER>(h, pvec, st);
       return launch_matvec_t<8, 16, 16, GATHER>(h, pvec, st);
+    case 12: return launch_matvec_t<12, 8, 16, GATHER>(h, pvec, st);    // 4-node tetrahedra, elastic: 9 KB tiles
+    case 4: return launch_matvec_t<4, 64, 16, GATHER>(h, pvec, st);     // 4-node tetrahedra, scalar: 8 KB tiles
   }
-  return fail(h, 3, "unsupported ntot %d (supported: 60, 24, 8)", h->ntot);
+  return fail(h, 3, "unsupported ntot %d (supported: 60, 24, 12, 8, 4)", h->ntot);
 }
 
 int launch_scatter(pf_handle h, const State *st, bool diag, double *dst) {
@@ -749,11 +757,13 @@ int pf_get_kernel_ms(pf_handle h, int which, double *total_ms, int64_t *launches
 int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp, const double *g_coord_pp,
                   const int32_t *g_g_pp, int64_t neq, int64_t ieq_start, int64_t neq_pp) {
   int rc = need_device(h); if (rc) return rc;
-  NEED((nod == 8 || nod == 20) && (nodof == 1 || nodof == 3), "nod must be 8 or 20, nodof 1 or 3");
+  NEED((nod == 4 || nod == 8 || nod == 20) && (nodof == 1 || nodof == 3), "nod must be 4 (tetrahedra), 8 or 20 (hexahedra), nodof 1 or 3");
   NEED(nip == 1 || nip == 8, "nip must be 1 or 8");
+  NEED(nod != 4 || nip == 1, "4-node tetrahedra take nip = 1");
   NEED(nels_pp >= 1 && neq >= 1 && neq_pp >= 0 && ieq_start >= 1, "bad sizes");
   const int ntot = nod * nodof;
-  NEED(ntot == 60 || ntot == 24 || ntot == 8, "supported element types: hex20/hex8 elastic, hex8 scalar");
+  NEED(ntot == 60 || ntot == 24 || ntot == 8 || ntot == 12 || ntot == 4,
+       "supported element types: hex20 / hex8 / tet4 elastic, hex8 / tet4 scalar");
   NEED(nels_pp * ntot < (int64_t)0xffffffffu, "nels_pp*ntot exceeds 32-bit table range; use more ranks");
   {
     int64_t c, s;
@@ -913,6 +923,7 @@ int pf_form_km_elastic(pf_handle h, double e, double v) {
   int rc = need_device(h); if (rc) return rc;
   h->transient = false; h->explicit_ = false; h->kb.release();
   NEED(h->have_mesh && h->nodof == 3, "needs pf_setup_mesh with nodof = 3");
+  NEED(h->nod != 4 || (h->km_layout == 0 && !h->matrix_free), "tetrahedra: reference storkm layout, stored matrices only");
   ElemTables T;
   if (fill_tables(h->nod, h->nip, e, v, 0, 0, 0, T)) return fail(h, 3, "unsupported nod/nip");
   CU(cudaMemcpyToSymbol(c_tab, &T, sizeof T));
@@ -937,7 +948,10 @@ int pf_form_km_elastic(pf_handle h, double e, double v) {
   const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 16);
   // PF_FORM=old: the first (untiled) build of the full matrix, kept for comparison
   static const bool old_form = getenv("PF_FORM") && !strcmp(getenv("PF_FORM"), "old");
-  if (!diag_only && !old_form) {
+  if (h->nod == 4) {
+    NEED(!diag_only, "the matrix-free variant exists for the hexahedra only");
+    k_form_km_elastic<4, 64><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, nullptr, h->km_layout);
+  } else if (!diag_only && !old_form) {
     if (h->nod == 20) k_form_km_tiled<20, 2, 2, 128, false><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout, nullptr, nullptr);
     else k_form_km_tiled<8, 1, 1, 64, false><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout, nullptr, nullptr);
   } else if (h->nod == 20) k_form_km_elastic<20, 128><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, diag_only, h->km_layout);
@@ -955,6 +969,7 @@ int pf_form_km_elastic_mat(pf_handle h, int np_types, const double *prop, const 
   NEED(h->have_mesh && h->nodof == 3, "needs pf_setup_mesh with nodof = 3");
   NEED(!h->matrix_free, "the matrix-free variant takes one material (pf_form_km_elastic)");
   NEED(np_types >= 1 && prop && etype_pp, "np_types >= 1, prop(2,np_types) and etype_pp(nels_pp) are required");
+  NEED(h->nod != 4 || h->km_layout == 0, "tetrahedra: reference storkm layout only");
   for (int64_t e = 0; e < h->nels; ++e)
     if (etype_pp[e] < 1 || etype_pp[e] > np_types) return fail(h, 4, "pf_form_km_elastic_mat: etype_pp(%lld) = %d outside 1..%d",
                                                                (long long)e + 1, etype_pp[e], np_types);
@@ -972,7 +987,8 @@ int pf_form_km_elastic_mat(pf_handle h, int np_types, const double *prop, const 
   CU(cudaMemcpy(d_etype.p, etype_pp, (size_t)h->nels * 4, cudaMemcpyHostToDevice));
   if ((rc = alloc_km(h))) return rc;
   const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 16);
-  if (h->nod == 20) k_form_km_tiled<20, 2, 2, 128, true><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout, d_dee.p, d_etype.p);
+  if (h->nod == 4) k_form_km_elastic<4, 64, true><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, nullptr, h->km_layout, d_dee.p, d_etype.p);
+  else if (h->nod == 20) k_form_km_tiled<20, 2, 2, 128, true><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout, d_dee.p, d_etype.p);
   else k_form_km_tiled<8, 1, 1, 64, true><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout, d_dee.p, d_etype.p);
   h->launches++;
   CU(cudaGetLastError());
@@ -985,13 +1001,15 @@ int pf_form_km_elastic_mat(pf_handle h, int np_types, const double *prop, const 
 int pf_form_kc_laplace(pf_handle h, double kx, double ky, double kz) {
   int rc = need_device(h); if (rc) return rc;
   h->transient = false; h->explicit_ = false; h->kb.release();
-  NEED(h->have_mesh && h->nodof == 1 && h->nod == 8, "needs pf_setup_mesh with nod = 8, nodof = 1");
+  NEED(h->have_mesh && h->nodof == 1 && (h->nod == 8 || h->nod == 4), "needs pf_setup_mesh with nod = 8 or 4, nodof = 1");
+  NEED(h->nod != 4 || h->km_layout == 0, "tetrahedra: reference storkm layout only");
   ElemTables T;
   if (fill_tables(h->nod, h->nip, 0, 0, kx, ky, kz, T)) return fail(h, 3, "unsupported nod/nip");
   CU(cudaMemcpyToSymbol(c_tab, &T, sizeof T));
   if ((rc = alloc_km(h))) return rc;
   const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 32);
-  k_form_kc_laplace<<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout);
+  if (h->nod == 8) k_form_kc_laplace<8><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout);
+  else k_form_kc_laplace<4><<<grid, 32, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout);
   h->launches++;
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));

@@ -367,7 +367,8 @@ int pf_abaqus2sg(int nod, int64_t nels, int32_t *g_num) {
   // new position m (0-based) takes old position perm[m] (0-based)
   static const int p20[20] = {3, 11, 0, 8, 1, 9, 2, 10, 19, 16, 17, 18, 7, 15, 4, 12, 5, 13, 6, 14};
   static const int p8[8] = {0, 4, 5, 1, 3, 7, 6, 2};
-  const int *p = nod == 20 ? p20 : nod == 8 ? p8 : nullptr;
+  static const int p4[4] = {0, 2, 1, 3};      // tetrahedron, new_library.f90:3647-3650
+  const int *p = nod == 20 ? p20 : nod == 8 ? p8 : nod == 4 ? p4 : nullptr;
   if (!p) return 1;
   for (int64_t e = 0; e < nels; ++e) {
     int32_t t[20];
@@ -530,15 +531,33 @@ int pf_read_fix(const char *job, int64_t fixed, int32_t *node, int32_t *sense, d
 }
 
 int pf_read_lds(const char *job, int64_t loaded, int nodof, int32_t *node, double *val) {
+  // read_loads (input.f90:2350-2411): READ(10,*) node(i),val(:,i) -- one list-directed READ per record, so
+  // values beyond the first nodof of a line are ignored (the xx11 decks carry three per line for nodof = 1)
   FILE *f = fopen((std::string(job) + ".lds").c_str(), "r");
   if (!f) return 1;
   int rc = 0;
+  char line[4096];
   for (int64_t i = 0; i < loaded && !rc; ++i) {
-    long long n;
-    if (fscanf(f, "%lld", &n) != 1) { rc = 2; break; }
+    char *q = nullptr;
+    for (;;) {                                       // next non-blank record
+      if (!fgets(line, sizeof line, f)) { rc = 2; break; }
+      q = line;
+      while (*q == ' ' || *q == '\t' || *q == '\r' || *q == '\n') ++q;
+      if (*q) break;
+    }
+    if (rc) break;
+    char *end = nullptr;
+    const long long n = strtoll(q, &end, 10);
+    if (end == q) { rc = 2; break; }
     node[i] = (int32_t)n;
-    for (int k = 0; k < nodof; ++k)
-      if (fscanf(f, "%lf", &val[i * nodof + k]) != 1) { rc = 3; break; }
+    for (int k = 0; k < nodof; ++k) {
+      q = end;
+      val[i * nodof + k] = strtod(q, &end);
+      if (end == q) {                                // the record ended early: list-directed input continues on the next one
+        if (!fgets(line, sizeof line, f)) { rc = 3; break; }
+        end = line; --k;
+      }
+    }
   }
   fclose(f);
   return rc;

@@ -1388,12 +1388,13 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
   }
 }
 
-// elements_1 of p123.f90:71-84; 8-node bricks, 64 threads = one per entry
-__global__ void __launch_bounds__(64)
+// elements_1 of p123.f90:71-84; 8-node bricks (or 4-node tetrahedra), NOD*NOD threads = one per entry
+template <int NOD>
+__global__ void __launch_bounds__(NOD * NOD < 32 ? 32 : NOD * NOD)
 k_form_kc_laplace(const double *__restrict__ g_coord, double *__restrict__ kc, long long nels, int packed) {
-  constexpr int NOD = 8;
+  constexpr int NENT = NOD * NOD;
   __shared__ double s_coord[NOD * 3], s_jac[9], s_deriv[NOD * 3];
-  const int j = threadIdx.x / 8, i = threadIdx.x % 8;
+  const int j = threadIdx.x / NOD, i = threadIdx.x % NOD;
   for (long long e = blockIdx.x; e < nels; e += gridDim.x) {
     __syncthreads();
     if (threadIdx.x < NOD * 3) s_coord[threadIdx.x] = g_coord[e * NOD * 3 + threadIdx.x];
@@ -1402,17 +1403,20 @@ k_form_kc_laplace(const double *__restrict__ g_coord, double *__restrict__ kc, l
     for (int ig = 0; ig < c_tab.nip; ++ig) {
       const double det = gauss_point<NOD>(ig, s_coord, s_jac, s_deriv);
       const double wt = c_tab.weights[ig];
-      kx = kx + s_deriv[i * 3 + 0] * s_deriv[j * 3 + 0] * det * wt;
-      ky = ky + s_deriv[i * 3 + 1] * s_deriv[j * 3 + 1] * det * wt;
-      kz = kz + s_deriv[i * 3 + 2] * s_deriv[j * 3 + 2] * det * wt;
+      if (threadIdx.x < NENT) {
+        kx = kx + s_deriv[i * 3 + 0] * s_deriv[j * 3 + 0] * det * wt;
+        ky = ky + s_deriv[i * 3 + 1] * s_deriv[j * 3 + 1] * det * wt;
+        kz = kz + s_deriv[i * 3 + 2] * s_deriv[j * 3 + 2] * det * wt;
+      }
       __syncthreads();
     }
-    const double val = kx * c_tab.kxyz[0] + ky * c_tab.kxyz[1] + kz * c_tab.kxyz[2];
-    if (!packed) kc[e * 64 + threadIdx.x] = val;
-    else if (i >= j) kc[e * SymCfg<8>::kPacked + SymCfg<8>::coloff(j) + (i - j)] = val;
+    if (threadIdx.x < NENT) {
+      const double val = kx * c_tab.kxyz[0] + ky * c_tab.kxyz[1] + kz * c_tab.kxyz[2];
+      if (!packed) kc[e * NENT + threadIdx.x] = val;
+      else if (i >= j) kc[e * SymCfg<NOD>::kPacked + SymCfg<NOD>::coloff(j) + (i - j)] = val;
+    }
   }
 }
-
 
 // elements_3 / gauss_pts of p124.f90:81-95; 8-node bricks, 64 threads = one per entry:
 //   kc += MATMUL(MATMUL(TRANSPOSE(deriv),kay),deriv)*det*w ;  pm += fun fun^T *det*w*rho*cp

@@ -257,8 +257,8 @@ def read_deck_p123(job, npes=1, numpe=1):
     info = DeckInfo()
     check(L.pf_read_dat(job.encode(), 123, C.byref(info)), what="pf_read_dat")
     nod, nn, nels, nr = info.nod, info.nn, info.nels, info.nr
-    if nod != 8:
-        raise PfError("p123 decks hold 8-node bricks")
+    if nod not in (8, 4):
+        raise PfError("p123 decks hold 8-node bricks (or, for xx11, 4-node tetrahedra)")
     g_coord = np.empty((nn, 3), np.float64)
     g_num = np.empty((nels, nod), np.int32)
     check(L.pf_read_d(job.encode(), nn, nels, nod, ptr(g_coord), ptr(g_num)), what="pf_read_d")

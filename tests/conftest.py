@@ -57,25 +57,27 @@ def golden(tmp_path_factory, _built):
         f.write("*DISPLACEMENT\n           1\n")
         for i, u in enumerate(a["xx2_dis"]):
             f.write(f"{i + 1:8d} {u[0]: .4E} {u[1]: .4E} {u[2]: .4E}\n")
-    # xx11 (p123 deck format, nr = 0, loads + fixed freedoms): rewritten in S&G node order, so meshgen = 1
-    x11 = os.path.join(d, "xx11")
-    dat = open(x11 + ".dat").read().split()
-    dat[1] = "1"
-    open(x11 + ".dat", "w").write("\n".join(dat[:3]) + "\n" + " ".join(dat[3:10]) + "\n" + " ".join(dat[10:]) + "\n")
-    with open(x11 + ".d", "w") as f:
-        f.write("*THREE_DIMENSIONAL\n*NODES\n")
-        for i, c in enumerate(a["xx11_coord"]):
-            f.write(f"{i + 1}  {float(c[0])!r}  {float(c[1])!r}  {float(c[2])!r}\n")
-        f.write("*ELEMENTS\n")
-        for e, g in enumerate(a["xx11_gnum_sg"]):
-            f.write(f"{e + 1}  3  8  1  " + "  ".join(str(int(v)) for v in g) + "  1\n")
-    with open(x11 + ".lds", "w") as f:
-        for q, v in zip(a["xx11_lds_eq"], a["xx11_lds_val"]):
-            f.write(f"{int(q):7d} {v:.8E}\n")
-    with open(x11 + ".fix", "w") as f:
-        for q, v in zip(a["xx11_fix_node"], a["xx11_fix_val"]):
-            f.write(f"{int(q)} 1 {float(v)!r}\n")
-    with open(x11 + ".ttr", "w") as f:
+    # xx11 (p123 deck format, nr = 0, loads + fixed freedoms) on bricks and on tetrahedra: rewritten in S&G node
+    # order, so meshgen = 1; loads in the three-value-column form of xx11_hexcube.lds (read_loads takes the first)
+    for job, key, nod in (("xx11", "xx11", 8), ("xx11_tetcube", "xx11tet", 4)):
+        base = os.path.join(d, job)
+        dat = open(base + ".dat").read().split()
+        dat[1] = "1"
+        open(base + ".dat", "w").write("\n".join(dat[:3]) + "\n" + " ".join(dat[3:10]) + "\n" + " ".join(dat[10:]) + "\n")
+        with open(base + ".d", "w") as f:
+            f.write("*THREE_DIMENSIONAL\n*NODES\n")
+            for i, c in enumerate(a[key + "_coord"]):
+                f.write(f"{i + 1}  {float(c[0])!r}  {float(c[1])!r}  {float(c[2])!r}\n")
+            f.write("*ELEMENTS\n")
+            for e, g in enumerate(a[key + "_gnum_sg"]):
+                f.write(f"{e + 1}  3  {nod}  1  " + "  ".join(str(int(v)) for v in g) + "  1\n")
+        with open(base + ".lds", "w") as f:
+            for q, v in zip(a[key + "_lds_eq"], a[key + "_lds_val"]):
+                f.write(f"{int(q)}   {float(v)!r} 0.0 0.0\n")
+        with open(base + ".fix", "w") as f:
+            for q, v in zip(a[key + "_fix_node"], a[key + "_fix_val"]):
+                f.write(f"{int(q)} 1 {float(v)!r}\n")
+    with open(os.path.join(d, "xx11.ttr"), "w") as f:
         f.write("*TEMPERATURE\n 1\n")
         for i, v in enumerate(a["xx11_ttr"]):
             f.write(f"{i + 1:8d} {v: .4E}\n")

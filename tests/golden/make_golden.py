@@ -60,15 +60,20 @@ def main():
     assert np.array_equal(t2.r_pp, t.r_pp)
     xx2 = dict(xx2_etype=t2.etype_pp, xx2_prop=t2.prop, xx2_dis=np.loadtxt(x2 + ".dis", skiprows=2)[:, 1:])
     # xx11 (dev program sharing p123's deck format): 64 8-node bricks, nr = 0, 25 loaded + 25 fixed freedoms.
-    # Its golden xx11.ttr was written with the loads of xx11.old.lds (100 per freedom); the shipped xx11.lds
-    # holds 10 per freedom and gives exactly one tenth of it.
+    # Its golden xx11.ttr belongs to the loads of hexahedron_cube/xx11_hexcube.lds (= xx11.old.lds: 100 per
+    # freedom, three value columns of which read_loads takes the first); xx11.lds itself holds 10 per freedom.
     x11 = f"{REF}/dev/xx11/xx11"
-    t11 = host.read_deck_p123(x11)
-    old = np.loadtxt(x11 + ".old.lds")
-    assert np.array_equal(old[:, 0].astype(int), np.flatnonzero(t11.r_pp) + 1) and np.all(old[:, 1] == 100.0)
+    t11 = host.read_deck_p123(f"{REF}/dev/xx11/hexahedron_cube/xx11_hexcube")
+    t11b = host.read_deck_p123(x11)
+    assert np.array_equal(t11.g_num_pp, t11b.g_num_pp) and np.array_equal(t11.g_coord, t11b.g_coord)
+    assert np.array_equal(t11.no_f, t11b.no_f) and np.array_equal(t11.r_pp, 10.0 * t11b.r_pp)
     xx11 = dict(xx11_coord=t11.g_coord, xx11_gnum_sg=t11.g_num_pp, xx11_lds_eq=(np.flatnonzero(t11.r_pp) + 1).astype(np.int32),
                 xx11_lds_val=t11.r_pp[np.flatnonzero(t11.r_pp)], xx11_fix_node=t11.no_f, xx11_fix_val=t11.val_f,
                 xx11_ttr=np.loadtxt(x11 + ".ttr", skiprows=2)[:, 1])
+    # the same cube meshed with 569 4-node tetrahedra (no output shipped): mesh in S&G order, loads, fixed nodes
+    tt = host.read_deck_p123(f"{REF}/dev/xx11/tetrahedron_cube/xx11_tetcube")
+    xx11.update(xx11tet_coord=tt.g_coord, xx11tet_gnum_sg=tt.g_num_pp, xx11tet_lds_eq=(np.flatnonzero(tt.r_pp) + 1).astype(np.int32),
+                xx11tet_lds_val=tt.r_pp[np.flatnonzero(tt.r_pp)], xx11tet_fix_node=tt.no_f, xx11tet_fix_val=tt.val_f)
     # p124 demo deck (transient conduction, 25^3 8-node bricks, Abaqus node order on disk)
     d124 = f"{REF}/5th_ed/p124/demo/p124_demo"
     dat = open(d124 + ".dat").read().split()
@@ -105,7 +110,7 @@ def main():
         "p121_book.res": lines(f"{REF}/5th_ed/p121/book/p121.res"), "p121_book.mg": lines(f"{REF}/5th_ed/p121/book/p121.mg"),
         "p123_book.res": lines(f"{REF}/5th_ed/p123/book/p123.res"), "p123_book.mg": lines(f"{REF}/5th_ed/p123/book/p123.mg"),
         "xx2-tiny.res": lines(x2 + ".res"), "xx2-tiny.dat": lines(x2 + ".dat"), "xx2-tiny.mat": lines(x2 + ".mat"),
-        "xx11.dat": lines(x11 + ".dat"),
+        "xx11.dat": lines(x11 + ".dat"), "xx11_tetcube.dat": lines(f"{REF}/dev/xx11/tetrahedron_cube/xx11_tetcube.dat"),
         "p125_demo.res": lines(d125 + ".res"), "p125_demo.dat": lines(d125 + ".dat"),
         "p124_demo.res": lines(d124 + ".res"), "p124_demo.dat": lines(d124 + ".dat"), "p124_demo.mat": lines(d124 + ".mat"),
         "p124_book.res": lines(f"{REF}/5th_ed/p124/book/p124.res"), "p124_book.mg": lines(f"{REF}/5th_ed/p124/book/p124.mg"),

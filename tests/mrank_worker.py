@@ -8,12 +8,14 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import oracle  # noqa: E402
 from parafem_b200 import host, solver  # noqa: E402
+from shuffle_util import shuffled  # noqa: E402
 
 
 def uneven(nels, npes):
@@ -25,6 +27,8 @@ def uneven(nels, npes):
 
 
 def problem(name, npes, numpe):
+    if name.endswith("_shuffled"):
+        return shuffled(problem(name[:-len("_shuffled")], 1, 1), npes, numpe)
     if name == "hex20_psize":   # partitioner 2 (read_nels_pp, input.f90:3108-3196)
         ps = uneven(6 * 7 * 5, npes) if npes > 1 else None
         return host.cube_p121(6, 7, 5, 20, aa=1., bb=1., cc=1., limit=500, npes=npes, numpe=numpe, psize=ps)
@@ -42,6 +46,12 @@ def problem(name, npes, numpe):
         return host.cube_p124(9, 11, 8, aa=.1, bb=.1, cc=.1, nstep=6, npes=npes, numpe=numpe, fixed=name.endswith("fixed"))
     if name == "p125":                   # explicit transient conduction
         return host.cube_p125(9, 11, 8, aa=.1, bb=.1, cc=.1, dtim=1e-4, nstep=30, npes=npes, numpe=numpe)
+    if name == "tet4":                   # 4-node tetrahedra, elastic (12x12 element matrices)
+        from tet_util import tet_problem
+        return tet_problem(host.cube_p121(5, 6, 3, 8, aa=1., bb=1., cc=1., limit=3000), npes, numpe)
+    if name == "tet4_scalar":            # 4-node tetrahedra, p123 (4x4)
+        from tet_util import tet_problem
+        return tet_problem(host.cube_p123(6, 7, 5, limit=800), npes, numpe)
     if name == "hex20_mat":              # per-element materials (xx2)
         p = host.cube_p121(6, 7, 5, 20, aa=1., bb=1., cc=1., limit=800, npes=npes, numpe=numpe)
         rng = np.random.RandomState(3)

@@ -13,6 +13,7 @@ import pytest
 
 import oracle
 from parafem_b200 import host, solver
+from shuffle_util import shuffled
 
 pytestmark = pytest.mark.gpu
 TOL_L2 = 1e-9        # north_star: converged field within 1e-9 relative L2
@@ -43,6 +44,9 @@ PROBLEMS = {
     "hex8_nip1": lambda: host.cube_p121(5, 5, 5, 8, aa=1., bb=1., cc=1., nip=1, limit=50),
     "p123_box": lambda: host.cube_p123(12, 9, 10, limit=500),
     "p123_one_element_tile_tail": lambda: host.cube_p123(5, 5, 5, limit=200),
+    # random equation numbers and element order: nothing in the device path may rely on the cube's numbering
+    "shuffled_hex20": lambda: shuffled(host.cube_p121(5, 4, 6, 20, aa=1., bb=1., cc=1., limit=600), 1, 1),
+    "shuffled_p123": lambda: shuffled(host.cube_p123(9, 7, 8, limit=500), 1, 1),
 }
 
 
@@ -97,7 +101,8 @@ def test_operator_properties(gpu):
     assert np.array_equal(gpu.apply(np.zeros(p.neq)), np.zeros(p.neq))
 
 
-@pytest.mark.parametrize("name", ["tiny_hex20", "ragged_hex20", "distorted_hex20", "hex8_elastic", "p123_box"])
+@pytest.mark.parametrize("name", ["tiny_hex20", "ragged_hex20", "distorted_hex20", "hex8_elastic", "p123_box",
+                                  "shuffled_hex20", "shuffled_p123"])
 def test_pcg_equals_oracle(gpu, name):
     p = PROBLEMS[name]()
     solver.setup_problem(gpu, p)
@@ -135,9 +140,8 @@ def test_p123_fixed_freedom(gpu):
 
 def test_xx11_fixed_freedom_golden(gpu, golden):
     """examples/dev/xx11 (p123's deck format, nr = 0, 25 loaded + 25 fixed freedoms): the reference's only golden
-    on the penalty path -- xx11.ttr (written with 100 per loaded freedom, the shipped .lds holds 10)."""
+    on the penalty path -- xx11.ttr, with the loads of hexahedron_cube/xx11_hexcube.lds (100 per freedom)."""
     p = host.read_deck_p123(os.path.join(golden, "xx11"))
-    p.r_pp *= 10.0
     r0 = p.r_pp.copy()
     solver.setup_problem(gpu, p)
     x, iters, conv = gpu.pcg_solve(p.r_pp, p.tol, p.limit)

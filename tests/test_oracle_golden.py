@@ -305,18 +305,60 @@ def test_p125_matrices_properties():
 # ---- xx11: p123's deck format with nr = 0, loaded and fixed freedoms ------------------------------------
 
 def test_xx11_fixed_freedom_golden(golden):
-    """examples/dev/xx11/xx11.{dat,d,lds,fix,ttr}: 64 bricks, 125 nodes, no restrained nodes (g_g_pp = g_num_pp,
-    p123.f90:54), 25 loaded and 25 fixed freedoms (penalty rows, p123.f90:120-131,141-145) -- the only golden of
-    the reference that exercises the fixed-freedom path.  xx11.ttr was written with 100 per loaded freedom
-    (xx11.old.lds); the shipped xx11.lds holds 10, so the field is one tenth of it."""
+    """examples/dev/xx11/xx11.{dat,d,fix,ttr} with the loads of hexahedron_cube/xx11_hexcube.lds: 64 bricks, 125 nodes,
+    no restrained nodes (g_g_pp = g_num_pp, p123.f90:54), 25 loaded and 25 fixed freedoms (penalty rows,
+    p123.f90:120-131,141-145) -- the only golden of the reference that exercises the fixed-freedom path.  (xx11.ttr was
+    written with 100 per loaded freedom; xx11.lds itself holds 10 and gives exactly one tenth.)"""
     p = host.read_deck_p123(os.path.join(golden, "xx11"))
     assert (p.nels, p.nn, p.nr, p.neq, p.no_f.size, int(np.count_nonzero(p.r_pp))) == (64, 125, 0, 125, 25, 25)
     assert np.array_equal(p.g_g_pp, p.g_num_pp) and (p.kx, p.ky, p.kz, p.tol, p.limit) == (100., 100., 100., 1e-5, 500)
+    assert p.total_load == 2500.0                      # the first of the three value columns of every record
     kc = oracle.form_kc_laplace(p.g_coord_pp, p.nip, p.kx, p.ky, p.kz)
     gold = np.loadtxt(os.path.join(golden, "xx11.ttr"), skiprows=2)[:, 1]
     for red_mode, npes in ((0, 1), (0, 2), (1, 1)):
-        r = oracle.pcg(kc, p.g_g_pp, p.neq, 10.0 * p.r_pp, p.tol, p.limit, npes=npes, red_mode=red_mode, no_f=p.no_f,
+        r = oracle.pcg(kc, p.g_g_pp, p.neq, p.r_pp, p.tol, p.limit, npes=npes, red_mode=red_mode, no_f=p.no_f,
                        val_f=p.val_f)
         assert r["converged"] and r["iters"] == 11
         assert np.abs(r["x"] - gold).max() <= 2e-4 * np.abs(gold).max()      # 5 digits printed; tol 1e-5 solve
         assert np.all(r["x"][p.no_f - 1] == 0.0)
+
+
+# ---- 4-node tetrahedra (SURVEY 8f rank 4) -------------------------------------------------------------
+
+def test_tetrahedra_patch_test():
+    """shape_der nod = 4 (new_library.f90:757-767) + sample('tetrahedron') nip = 1 (:1329-1341) in the p123
+    element loop: with every boundary node held at a linear field the interior reproduces it (the defining
+    property of a conforming linear element, independent of the mesh)."""
+    from tet_util import patch_problem
+    p, field = patch_problem()
+    assert (p.nod, p.nip, p.nels) == (4, 1, 6 * 5 * 6 * 4)
+    kc = oracle.form_kc_laplace(p.g_coord_pp, 1, 1., 1., 1.)
+    assert np.abs(kc.sum(axis=2)).max() < 1e-12                     # constants in the null space
+    r = oracle.pcg(kc, p.g_g_pp, p.neq, np.zeros(p.neq), p.tol, p.limit, npes=1, red_mode=1, no_f=p.no_f, val_f=p.val_f)
+    assert r["converged"] and np.abs(r["x"] - field).max() <= 1e-10 * np.abs(field).max()
+
+
+def test_xx11_tetrahedron_deck(golden):
+    """examples/dev/xx11/tetrahedron_cube/xx11_tetcube.*: the xx11 cube meshed with 569 tetrahedra (155 nodes).  The
+    reference ships no output for it; it is checked against the brick deck's golden: total volume 64, every element
+    positively oriented after abaqus2sg, and the mean temperature of the loaded face within 2 % of the brick mesh's
+    (6.48 against 6.54)."""
+    p = host.read_deck_p123(os.path.join(golden, "xx11_tetcube"))
+    assert (p.nod, p.nip, p.nels, p.nn, p.neq, p.no_f.size) == (4, 1, 569, 155, 155, 25) and p.total_load == 2500.0
+    x = p.g_coord[p.g_num_pp - 1]
+    det = np.linalg.det(x[:, :3, :] - x[:, 3:4, :])
+    assert det.min() > 0 and abs(det.sum() / 6 - 64.0) < 1e-9
+    kc = oracle.form_kc_laplace(p.g_coord_pp, p.nip, p.kx, p.ky, p.kz)
+    r = oracle.pcg(kc, p.g_g_pp, p.neq, p.r_pp, p.tol, p.limit, npes=1, red_mode=0, no_f=p.no_f, val_f=p.val_f)
+    gold = np.loadtxt(os.path.join(golden, "xx11.ttr"), skiprows=2)[:, 1]
+    brick = host.read_deck_p123(os.path.join(golden, "xx11"))
+    t_tet, t_brick = r["x"][np.flatnonzero(p.r_pp)].mean(), gold[np.flatnonzero(brick.r_pp)].mean()
+    assert r["converged"] and abs(t_tet - t_brick) < 0.02 * t_brick
+
+
+def test_abaqus2sg_tetrahedron():
+    """abaqus2sg, tetrahedron branch (new_library.f90:3634-3652): nodes 2 and 3 swap."""
+    from parafem_b200._lib import lib, ptr
+    g = np.array([[10, 20, 30, 40], [1, 2, 3, 4]], np.int32)
+    assert lib().pf_abaqus2sg(4, 2, ptr(g)) == 0
+    assert np.array_equal(g, [[10, 30, 20, 40], [1, 3, 2, 4]])
