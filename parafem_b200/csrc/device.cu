@@ -175,6 +175,13 @@ void collect_spans(pf_handle h) {
   h->spans.clear();
 }
 
+// a pair of timing events released on every return path
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaError_t create() { cudaError_t e = cudaEventCreate(&a); return e != cudaSuccess ? e : cudaEventCreate(&b); }
+  ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
+
 int grid_for(pf_handle h, int64_t n, int threads, int per_sm = 8) {
   int64_t blocks = (n + threads - 1) / threads;
   int64_t cap = (int64_t)h->sm_count * per_sm;
@@ -951,6 +958,9 @@ int pf_form_km_elastic(pf_handle h, double e, double v) {
   if (h->nod == 4) {
     NEED(!diag_only, "the matrix-free variant exists for the hexahedra only");
     k_form_km_elastic<4, 64><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, nullptr, h->km_layout);
+  } else if (diag_only && !old_form) {
+    if (h->nod == 20) k_form_km_tiled<20, 2, 2, 128, false, true><<<grid, 128, 0, h->stream>>>(h->coord.p, diag_only, (long long)h->nels, 0, nullptr, nullptr);
+    else k_form_km_tiled<8, 1, 1, 64, false, true><<<grid, 64, 0, h->stream>>>(h->coord.p, diag_only, (long long)h->nels, 0, nullptr, nullptr);
   } else if (!diag_only && !old_form) {
     if (h->nod == 20) k_form_km_tiled<20, 2, 2, 128, false><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout, nullptr, nullptr);
     else k_form_km_tiled<8, 1, 1, 64, false><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout, nullptr, nullptr);
@@ -1070,8 +1080,9 @@ int pf_transient_step(pf_handle h, const double *loads_pp, double tol, int limit
                       double *elapsed_ms) {
   int rc = need_device(h); if (rc) return rc;
   NEED(h->transient && h->have_precon, "needs pf_form_k_transient, pf_build_precon and pf_transient_start");
-  cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  EventPair ev;
+  CU(ev.create());
+  const cudaEvent_t e0 = ev.a, e1 = ev.b;
   CU(cudaEventRecord(e0, h->stream));
   // u = storka*x on the first step (p124.f90:174-178), storkb*xnew afterwards (:149-154); x lives in h->x
   CU(cudaMemcpyAsync(h->p_ext.p + 1, h->x.p, (size_t)h->neq_pp * 8, cudaMemcpyDeviceToDevice, h->stream));
@@ -1108,7 +1119,6 @@ int pf_transient_step(pf_handle h, const double *loads_pp, double tol, int limit
   CU(cudaEventSynchronize(e1));
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (elapsed_ms) *elapsed_ms = ms;
   return 0;
 }
@@ -1164,8 +1174,9 @@ int pf_explicit_start(pf_handle h, double val0) {
 int pf_explicit_steps(pf_handle h, int nsteps, double *elapsed_ms) {
   int rc = need_device(h); if (rc) return rc;
   NEED(h->explicit_ && nsteps >= 0, "needs pf_form_k_explicit and nsteps >= 0");
-  cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  EventPair ev;
+  CU(ev.create());
+  const cudaEvent_t e0 = ev.a, e1 = ev.b;
   CU(cudaEventRecord(e0, h->stream));
   for (int j = 0; j < nsteps; ++j) {
     // newlo_pp = scatter(MATMUL(store_pm_pp, gather(loads_pp))); loads_pp = newlo_pp*globma_pp  (p125.f90:94-99)
@@ -1182,7 +1193,6 @@ int pf_explicit_steps(pf_handle h, int nsteps, double *elapsed_ms) {
   CU(cudaGetLastError());
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   collect_spans(h);
   if (elapsed_ms) *elapsed_ms = ms;
   return 0;
@@ -1334,8 +1344,9 @@ int pf_pcg_run(pf_handle h, double tol, int limit, int *iters, int *converged, d
                                                           (h->peer_ok && h->use_peer) ? h->ptab.p : nullptr);
   h->launches++;
   if (!(h->peer_ok && h->use_peer) && (rc = combine_scalars(h, 0))) return rc;
-  cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  EventPair ev;
+  CU(ev.create());
+  const cudaEvent_t e0 = ev.a, e1 = ev.b;
   CU(cudaEventRecord(e0, h->stream));  // timest(3), p121.f90:89
   // Single rank: the iteration (5 launches with constant arguments) is captured once per problem as a CUDA graph
   // and replayed -- at config B / p124 sizes the launch gaps were ~15 % of an iteration.  PF_GRAPH=0 disables it.
@@ -1378,7 +1389,6 @@ int pf_pcg_run(pf_handle h, double tol, int limit, int *iters, int *converged, d
   CU(cudaEventSynchronize(e1));
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   collect_spans(h);
   h->last_iters = snap.iters;
   if (iters) *iters = snap.iters;

@@ -950,7 +950,9 @@ k_form_km_elastic(const double *__restrict__ g_coord, double *__restrict__ km, l
 // 128-bit coalesced stores (or packed).  21 products per 3x3 node block and point instead of 54, and 0.1
 // shared loads per product instead of 2: the first build (k_form_km_elastic above, kept for the matrix-free
 // diagonal) was bound by its shared-memory loads at ~19 % of the FP64 pipe.
-template <int NOD, int TA, int TB, int THREADS, bool MAT>
+// DIAG (matrix-free setup): only the diagonal of km is wanted, km receives (ntot,nels); thread a < NOD evaluates
+// the diagonal entries of node block (a,a) with the same products in the same order.
+template <int NOD, int TA, int TB, int THREADS, bool MAT, bool DIAG = false>
 __global__ void __launch_bounds__(THREADS)
 k_form_km_tiled(const double *__restrict__ g_coord, double *__restrict__ km, long long nels, int packed,
                 const double *__restrict__ dee_tab, const int *__restrict__ etype) {
@@ -995,6 +997,25 @@ k_form_km_tiled(const double *__restrict__ g_coord, double *__restrict__ km, lon
       s_deriv[q] = sum;
     }
     __syncthreads();
+    if constexpr (DIAG) {
+      if (t < NOD) {
+        const double d00 = s_dee[0], d11 = s_dee[7], d22 = s_dee[14], d33 = s_dee[21], d44 = s_dee[28], d55 = s_dee[35];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int ig = 0; ig < nip; ++ig) {
+          const double det = s_det[ig], wt = c_tab.weights[ig];
+          const double *dv = s_deriv + ig * (NOD * 3);
+          const double x = dv[t * 3], y = dv[t * 3 + 1], z = dv[t * 3 + 2];
+          double s;
+          s = (x * d00) * x; s = s + (y * d33) * y; s = s + (z * d55) * z; a0 = a0 + s * det * wt;   // (0,0): k = 0,3,5
+          s = (y * d11) * y; s = s + (x * d33) * x; s = s + (z * d44) * z; a1 = a1 + s * det * wt;   // (1,1): k = 1,3,4
+          s = (z * d22) * z; s = s + (y * d44) * y; s = s + (x * d55) * x; a2 = a2 + s * det * wt;   // (2,2): k = 2,4,5
+        }
+        km[e * (long long)NTOT + 3 * t] = a0;
+        km[e * (long long)NTOT + 3 * t + 1] = a1;
+        km[e * (long long)NTOT + 3 * t + 2] = a2;
+      }
+      continue;
+    }
     if (tb < NB) {
       // D(l,k) = dee(l,k); only the entries an isotropic dee holds
       const double d00 = s_dee[0], d10 = s_dee[1], d20 = s_dee[2];        // dee(:,0) at [0*6+l]
