@@ -378,7 +378,7 @@ def main():
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = f"hex{args.nod}_n{n}_gpus{nranks}"
+        key = f"hex{args.nod}_n{n}_gpus{nranks}" if args.program == "p121" else f"{args.program}_n{n}_gpus{nranks}"
         traffic = tj.get(key, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
