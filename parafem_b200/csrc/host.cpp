@@ -624,8 +624,8 @@ int pf_read_d_mat(const char *job, int64_t nn, int64_t nels, int nod, double *g_
   if (fscanf(f, "%255s", word) != 1 || fscanf(f, "%255s", word) != 1) rc = 2;  // *THREE_DIMENSIONAL *NODES
   for (int64_t i = 0; i < nn && !rc; ++i) {
     long long id; double x, y, z;
-    if (fscanf(f, "%lld %lf %lf %lf", &id, &x, &y, &z) != 4 || id < 1 || id > nn) { rc = 3; break; }
-    g_coord[(id - 1) * 3 + 0] = x; g_coord[(id - 1) * 3 + 1] = y; g_coord[(id - 1) * 3 + 2] = z;
+    if (fscanf(f, "%lld %lf %lf %lf", &id, &x, &y, &z) != 4) { rc = 3; break; }
+    g_coord[i * 3 + 0] = x; g_coord[i * 3 + 1] = y; g_coord[i * 3 + 2] = z;      // line order (bitBucket, input.f90:389)
   }
   if (!rc && fscanf(f, "%255s", word) != 1) rc = 4;  // *ELEMENTS
   for (int64_t e = 0; e < nels && !rc; ++e) {

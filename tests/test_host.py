@@ -204,3 +204,43 @@ def test_psize_partitioner_2(tmp_path):
     assert [(q.neq_pp, q.ieq_start) for q in parts] == [host.calc_neq_pp(full.neq, 3, r) for r in (1, 2, 3)]
     with pytest.raises(PfError):
         host.calc_nels_pp(120, 3, 1, psize=[70, 20, 31])
+
+
+def test_d_reader_fast_path_and_fallback_agree(tmp_path, tiny, golden):
+    """<job>.d is parsed from memory in parallel chunks; unusual but legal list-directed input (blank lines, CRLF,
+    comma separators, a leading '+') is still read, in line order as the reference does (input.f90:388-390,
+    1053); a file with a missing record is an error in both readers."""
+    import ctypes as C
+    from parafem_b200._lib import lib, ptr
+    src = open(os.path.join(golden, "xx3-tiny.d")).read().splitlines()
+    k_el = src.index("*ELEMENTS")
+    ref_c, ref_n = np.empty((tiny.nn, 3)), np.empty((tiny.nels, 20), np.int32)
+    assert lib().pf_read_d(os.path.join(golden, "xx3-tiny").encode(), tiny.nn, tiny.nels, 20, ptr(ref_c), ptr(ref_n)) == 0
+
+    def read(lines, nn=tiny.nn, nels=tiny.nels, eol="\n"):
+        job = str(tmp_path / "variant")
+        with open(job + ".d", "w", newline="") as f:
+            f.write(eol.join(lines) + eol)
+        c, n, et = np.full((nn, 3), np.nan), np.zeros((nels, 20), np.int32), np.zeros(nels, np.int32)
+        return lib().pf_read_d_mat(job.encode(), nn, nels, 20, ptr(c), ptr(n), ptr(et)), c, n, et
+
+    odd = list(src)
+    odd.insert(5, "")                                             # blank record inside the node section
+    odd.insert(k_el + 3, "   ")
+    odd[3] = "  " + ", ".join(odd[3].split())                     # comma separators
+    odd[4] = odd[4].replace(" 0.", " +0.", 1)                     # explicit sign
+    for eol in ("\n", "\r\n"):
+        rc, c, n, et = read(odd, eol=eol)
+        assert rc == 0 and np.array_equal(c, ref_c) and np.array_equal(n, ref_n) and np.all(et == 1)
+    # line order, not the leading number, places a record (READ(10,*) bitBucket, g_coord(:,j))
+    swapped = list(src)
+    swapped[2], swapped[3] = swapped[3], swapped[2]
+    rc, c, n, et = read(swapped)
+    assert rc == 0 and np.array_equal(c[0], ref_c[1]) and np.array_equal(c[1], ref_c[0]) and np.array_equal(c[2:], ref_c[2:])
+    # a record short: both the fast path and the record reader refuse
+    rc, *_ = read(src[:-1])
+    assert rc != 0
+    # Fortran D exponents are outside from_chars: the record-by-record reader takes over and fails cleanly too
+    dexp = [l.replace("E+", "D+").replace("E-", "D-") if 2 <= i < k_el else l for i, l in enumerate(src)]
+    rc, *_ = read(dexp)
+    assert rc != 0
