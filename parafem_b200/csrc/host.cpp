@@ -498,6 +498,19 @@ inline bool take_double(const char *&p, const char *e, double &v) {
   if (p < e && *p == '+') ++p;
   auto r = std::from_chars(p, e, v);
   if (r.ec != std::errc()) return false;
+  if (r.ptr < e && (*r.ptr == 'D' || *r.ptr == 'd')) {     // Fortran double-precision exponent letter
+    char tmp[64];
+    const char *q = r.ptr + 1;
+    while (q < e && (*q == '+' || *q == '-' || (*q >= '0' && *q <= '9'))) ++q;
+    const size_t n = (size_t)(q - p);
+    if (n >= sizeof tmp) return false;
+    memcpy(tmp, p, n);
+    tmp[r.ptr - p] = 'E';
+    auto r2 = std::from_chars(tmp, tmp + n, v);
+    if (r2.ec != std::errc() || r2.ptr != tmp + n) return false;
+    p = q;
+    return true;
+  }
   p = r.ptr;
   return true;
 }
