@@ -962,7 +962,11 @@ int pf_form_km_elastic(pf_handle h, double e, double v) {
     if (h->nod == 20) k_form_km_tiled<20, 2, 2, 128, false, true><<<grid, 128, 0, h->stream>>>(h->coord.p, diag_only, (long long)h->nels, 0, nullptr, nullptr);
     else k_form_km_tiled<8, 1, 1, 64, false, true><<<grid, 64, 0, h->stream>>>(h->coord.p, diag_only, (long long)h->nels, 0, nullptr, nullptr);
   } else if (!diag_only && !old_form) {
-    if (h->nod == 20) k_form_km_tiled<20, 2, 2, 128, false><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout, nullptr, nullptr);
+    // hex20: 128-register cap = four resident CTAs per SM (84 B of spills) -- measured 45.5 ms against 59.0 ms with
+    // three CTAs at 164 registers on the same box (scripts/gpu_round27.sh); PF_FORM=b3 selects the latter
+    static const bool b3 = getenv("PF_FORM") && !strcmp(getenv("PF_FORM"), "b3");
+    if (h->nod == 20 && !b3) k_form_km_tiled<20, 2, 2, 128, false, false, 4><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout, nullptr, nullptr);
+    else if (h->nod == 20) k_form_km_tiled<20, 2, 2, 128, false><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout, nullptr, nullptr);
     else k_form_km_tiled<8, 1, 1, 64, false><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout, nullptr, nullptr);
   } else if (h->nod == 20) k_form_km_elastic<20, 128><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, diag_only, h->km_layout);
   else k_form_km_elastic<8, 64><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, diag_only, h->km_layout);
@@ -998,7 +1002,7 @@ int pf_form_km_elastic_mat(pf_handle h, int np_types, const double *prop, const 
   if ((rc = alloc_km(h))) return rc;
   const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 16);
   if (h->nod == 4) k_form_km_elastic<4, 64, true><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, nullptr, h->km_layout, d_dee.p, d_etype.p);
-  else if (h->nod == 20) k_form_km_tiled<20, 2, 2, 128, true><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout, d_dee.p, d_etype.p);
+  else if (h->nod == 20) k_form_km_tiled<20, 2, 2, 128, true, false, 4><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout, d_dee.p, d_etype.p);
   else k_form_km_tiled<8, 1, 1, 64, true><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout, d_dee.p, d_etype.p);
   h->launches++;
   CU(cudaGetLastError());

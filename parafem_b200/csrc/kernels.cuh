@@ -952,8 +952,8 @@ k_form_km_elastic(const double *__restrict__ g_coord, double *__restrict__ km, l
 // diagonal) was bound by its shared-memory loads at ~19 % of the FP64 pipe.
 // DIAG (matrix-free setup): only the diagonal of km is wanted, km receives (ntot,nels); thread a < NOD evaluates
 // the diagonal entries of node block (a,a) with the same products in the same order.
-template <int NOD, int TA, int TB, int THREADS, bool MAT, bool DIAG = false>
-__global__ void __launch_bounds__(THREADS)
+template <int NOD, int TA, int TB, int THREADS, bool MAT, bool DIAG = false, int MINB = 1>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_form_km_tiled(const double *__restrict__ g_coord, double *__restrict__ km, long long nels, int packed,
                 const double *__restrict__ dee_tab, const int *__restrict__ etype) {
   constexpr int NTOT = 3 * NOD, NENT = NTOT * NTOT, NA = NOD / TA, NB = NOD / TB, MAXIP = 8;
