@@ -274,6 +274,7 @@ typedef struct {
   /* p124 (read_p124, input.f90:3997-4169) and xx2 (read_xx2, :5391-5562) */
   int np_types, nstep, npri, pad_;
   double val0, dtim, theta;
+  double rho, cp;   /* p124 material (the .mat file, read_material input.f90:3067-3102) */
 } pf_deck_info;
 /* program: 121, 123, 124, or 2 for the dev program xx2 (per-element materials) */
 int pf_read_dat(const char *job, int program, pf_deck_info *info);
@@ -299,6 +300,15 @@ int pf_coords_pp(int nod, int64_t nels_pp, const int32_t *g_num_pp,
 int pf_write_deck_p121(const char *job, int nod, int64_t nels, int64_t nn, int64_t nr, int nip,
                        int64_t loaded, double e, double v, double tol, int limit, const double *g_coord,
                        const int32_t *g_num, const int32_t *rest, const int32_t *node, const double *val);
+
+/* p12meshgen's output side for the scalar programs on 8-node bricks: p123 (p12meshgen.f90:703-797), p124
+ * (:879-987, plus <job>.mat) and p125 (:1075-1160), selected by info->program; formats as written there
+ * (elements in Abaqus order with meshgen = 2; I10 / I12 node fields and I8 / I12 restraint fields differ between
+ * the programs).  Reproduces the shipped p124_demo / p125_demo decks byte for byte.  g_coord(3,nn), g_num(8,nels)
+ * in S&G order, rest(nr,2) column-major; .lds / .fix as p12meshgen writes them (freedom nres, 10.0 / 100.0) when
+ * info->loaded / info->fixed > 0.                                                                    */
+int pf_write_deck_scalar(const char *job, const pf_deck_info *info, const double *g_coord,
+                         const int32_t *g_num, const int32_t *rest);
 
 /* Output section (p121.f90:124-138): calc_nodes_pp (gather_scatter.f90:2139-2234);
  * nodal values of the owned equations for nodes node_start..node_start+nodes_pp-1

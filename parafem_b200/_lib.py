@@ -30,7 +30,7 @@ class DeckInfo(C.Structure):
                 ("loaded", c_i64), ("fixed", c_i64), ("nres", c_i64), ("e", c_dbl), ("v", c_dbl),
                 ("kx", c_dbl), ("ky", c_dbl), ("kz", c_dbl), ("tol", c_dbl),
                 ("np_types", c_int), ("nstep", c_int), ("npri", c_int), ("pad_", c_int),
-                ("val0", c_dbl), ("dtim", c_dbl), ("theta", c_dbl)]
+                ("val0", c_dbl), ("dtim", c_dbl), ("theta", c_dbl), ("rho", c_dbl), ("cp", c_dbl)]
 
 
 P = C.POINTER
@@ -103,6 +103,7 @@ SIGNATURES = {
     "pf_coords_pp": (c_int, [c_int, c_i64, vp, vp, vp]),
     "pf_write_deck_p121": (c_int, [C.c_char_p, c_int, c_i64, c_i64, c_i64, c_int, c_i64, c_dbl, c_dbl, c_dbl, c_int,
                                    vp, vp, vp, vp, vp]),
+    "pf_write_deck_scalar": (c_int, [C.c_char_p, P(DeckInfo), vp, vp, vp]),
     "pf_calc_nodes_pp": (None, [c_i64, c_int, c_int, P(c_i64), P(c_i64)]),
     "pf_nodal_values": (c_int, [c_int, c_i64, vp, c_i64, c_i64, vp, c_i64, c_i64, vp]),
     "pf_write_ensi": (c_int, [C.c_char_p, c_int, c_i64, vp, c_int]),

@@ -415,6 +415,14 @@ int pf_read_dat(const char *job, int program, pf_deck_info *info) {
     info->nip = (int)v[6]; info->nod = (int)v[7]; info->loaded = (int64_t)v[8]; info->fixed = (int64_t)v[9];
     info->val0 = v[10]; info->dtim = v[11]; info->nstep = (int)v[12]; info->npri = (int)v[13]; info->theta = v[14];
     info->tol = v[15]; info->limit = (int)v[16]; info->nres = (int64_t)v[17];
+  } else if (program == 125) {
+    // read_p125: element, mesh, partition / nels nn nr nip nod loaded fixed / kx ky kz / dtim nstep npri / nres val0
+    if (v.size() < 17) return 2;
+    info->meshgen = (int)v[0]; info->partitioner = (int)v[1];
+    info->nels = (int64_t)v[2]; info->nn = (int64_t)v[3]; info->nr = (int64_t)v[4];
+    info->nip = (int)v[5]; info->nod = (int)v[6]; info->loaded = (int64_t)v[7]; info->fixed = (int64_t)v[8];
+    info->kx = v[9]; info->ky = v[10]; info->kz = v[11]; info->dtim = v[12]; info->nstep = (int)v[13];
+    info->npri = (int)v[14]; info->nres = (int64_t)v[15]; info->val0 = v[16];
   } else if (program == 2) {
     // read_xx2 (input.f90:5391-5562): element, mesh, partition, np_types, nels nn nr nip nod loaded_nodes
     // fixed_freedoms, tol limit
@@ -850,6 +858,87 @@ int pf_write_deck_p121(const char *job, int nod, int64_t nels, int64_t nn, int64
   fortran_e(a, sizeof a, e, 12, 4); fortran_e(b, sizeof b, v, 12, 4); fortran_e(c, sizeof c, tol, 12, 4);
   fprintf(f, "'hexahedron'\n%s\n1\n%12lld%12lld%12lld%5d%5d%9lld\n%s%s%s%8d\n", nod == 8 ? "1" : "2",
           (long long)nels, (long long)nn, (long long)nr, nip, nod, (long long)loaded, a, b, c, limit);
+  fclose(f);
+  return 0;
+}
+
+// p12meshgen's output side for p123 / p124 / p125 (8-node bricks, one freedom per node)
+int pf_write_deck_scalar(const char *job, const pf_deck_info *info, const double *g_coord, const int32_t *g_num,
+                         const int32_t *rest) {
+  if (!info || info->nod != 8 || (info->program != 123 && info->program != 124 && info->program != 125)) return 1;
+  const int prog = info->program;
+  const int64_t nn = info->nn, nels = info->nels, nr = info->nr;
+  static const int to_abaqus8[8] = {1, 4, 8, 5, 2, 3, 7, 6};            // p12meshgen.f90:720-725, 887-891
+  FILE *f = fopen((std::string(job) + ".d").c_str(), "w");
+  if (!f) return 2;
+  fprintf(f, "*THREE_DIMENSIONAL\n*NODES\n");
+  write_records(f, nn, [&](int64_t i, std::string &o) {
+    char x[64], y[64], z[64], ln[160];
+    fortran_e(x, sizeof x, g_coord[i * 3], 14, 6); fortran_e(y, sizeof y, g_coord[i * 3 + 1], 14, 6);
+    fortran_e(z, sizeof z, g_coord[i * 3 + 2], 14, 6);
+    snprintf(ln, sizeof ln, "%12lld%s%s%s\n", (long long)(i + 1), x, y, z);
+    o += ln;
+  });
+  fprintf(f, "*ELEMENTS\n");
+  const int wnode = prog == 123 ? 10 : 12;                               // (I12,A,8I10,A) / (I12,A,8I12,A)
+  write_records(f, nels, [&](int64_t el, std::string &o) {
+    char ln[32];
+    snprintf(ln, sizeof ln, "%12lld 3 8 1 ", (long long)(el + 1));
+    o += ln;
+    for (int q = 0; q < 8; ++q) {
+      snprintf(ln, sizeof ln, "%*d", wnode, g_num[el * 8 + to_abaqus8[q] - 1]);
+      o += ln;
+    }
+    o += " 1\n";
+  });
+  fclose(f);
+  f = fopen((std::string(job) + ".bnd").c_str(), "w");
+  if (!f) return 2;
+  for (int64_t i = 0; i < nr; ++i) fprintf(f, "%*d%6d\n", prog == 123 ? 8 : 12, rest[i], rest[nr + i]);   // (I8,3I6) / (I12,3I6)
+  fclose(f);
+  char a[64], b[64], c[64], d[64], e[64];
+  if (info->loaded > 0) {
+    f = fopen((std::string(job) + ".lds").c_str(), "w");
+    if (!f) return 2;
+    fortran_e(a, sizeof a, 10.0, 16, 8);
+    for (int64_t i = 0; i < info->loaded; ++i) fprintf(f, "%*lld%s\n", prog == 123 ? 10 : prog == 124 ? 12 : 11, (long long)info->nres, a);
+    fclose(f);
+  }
+  if (info->fixed > 0) {
+    f = fopen((std::string(job) + ".fix").c_str(), "w");
+    if (!f) return 2;
+    fortran_e(a, sizeof a, 100.0, 16, 8);
+    for (int64_t i = 0; i < info->fixed; ++i) fprintf(f, "%*lld%s\n", prog == 123 ? 10 : 12, (long long)info->nres, a);
+    fclose(f);
+  }
+  if (prog == 124) {
+    f = fopen((std::string(job) + ".mat").c_str(), "w");
+    if (!f) return 2;
+    fortran_e(a, sizeof a, info->kx, 12, 4); fortran_e(b, sizeof b, info->ky, 12, 4); fortran_e(c, sizeof c, info->kz, 12, 4);
+    fortran_e(d, sizeof d, info->rho, 12, 4); fortran_e(e, sizeof e, info->cp, 12, 4);
+    fprintf(f, "*MATERIAL%5d%5d\n<edit material_name>\n 1%s%s%s%s%s\n", 1, 5, a, b, c, d, e);
+    fclose(f);
+  }
+  f = fopen((std::string(job) + ".dat").c_str(), "w");
+  if (!f) return 2;
+  fprintf(f, "'hexahedron'\n2\n1\n");
+  if (prog == 123) {
+    fortran_e(a, sizeof a, info->kx, 12, 4); fortran_e(b, sizeof b, info->ky, 12, 4); fortran_e(c, sizeof c, info->kz, 12, 4);
+    fortran_e(d, sizeof d, info->tol, 12, 4);
+    fprintf(f, "%12lld%12lld%12lld%6d%6d%6lld%6lld\n%s%s%s%s%8d%8lld\n", (long long)nels, (long long)nn, (long long)nr, info->nip,
+            info->nod, (long long)info->loaded, (long long)info->fixed, a, b, c, d, info->limit, (long long)info->nres);
+  } else if (prog == 124) {
+    fortran_e(a, sizeof a, info->val0, 12, 4); fortran_e(b, sizeof b, info->dtim, 12, 4); fortran_e(c, sizeof c, info->theta, 12, 4);
+    fortran_e(d, sizeof d, info->tol, 12, 4);
+    fprintf(f, "1\n%12lld%12lld%9lld%9d%9d%9lld%9lld\n%s\n%s%8d%8d%s\n%s%8d%8lld\n", (long long)nels, (long long)nn, (long long)nr,
+            info->nip, info->nod, (long long)info->loaded, (long long)info->fixed, a, b, info->nstep, info->npri, c, d, info->limit,
+            (long long)info->nres);
+  } else {
+    fortran_e(a, sizeof a, info->kx, 12, 4); fortran_e(b, sizeof b, info->ky, 12, 4); fortran_e(c, sizeof c, info->kz, 12, 4);
+    fortran_e(d, sizeof d, info->dtim, 12, 4); fortran_e(e, sizeof e, info->val0, 12, 4);
+    fprintf(f, "%9lld%9lld%9lld%9d%9d%9lld%9lld\n%s%s%s\n%s%8d%8d\n%8lld%s\n", (long long)nels, (long long)nn, (long long)nr, info->nip,
+            info->nod, (long long)info->loaded, (long long)info->fixed, a, b, c, d, info->nstep, info->npri, (long long)info->nres, e);
+  }
   fclose(f);
   return 0;
 }

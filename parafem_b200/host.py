@@ -248,14 +248,26 @@ def read_deck_p121(job, npes=1, numpe=1):
     return p
 
 
-def read_deck_p123(job, npes=1, numpe=1):
+def read_deck_p124(job, npes=1, numpe=1):
+    """Input section of p124.f90:27-49 (read_p124, read_elements, read_material): the p123 reader with the transient
+    data of the .dat and the one material of the .mat."""
+    p = read_deck_p123(job, npes, numpe, program=124)
+    return p
+
+
+def read_deck_p125(job, npes=1, numpe=1):
+    """Input section of p125.f90:19-33 (read_p125)."""
+    return read_deck_p123(job, npes, numpe, program=125)
+
+
+def read_deck_p123(job, npes=1, numpe=1, program=123):
     """Input section of p123.f90:27-55,94-131 (and of programs/dev/xx11/xx11.f90, which shares its deck format)
     for one rank: read_p123, read_g_num_pp, abaqus2sg, read_g_coord_pp, read_rest + rearrange_2/find_g4 -- or
     g_g_pp = g_num_pp when nr = 0 (p123.f90:54) --, read_loads (first column = global equation number,
     p123.f90:111-116) and read_fixed + find_no2 + reindex (node, sense -> this rank's fixed equations)."""
     L = lib()
     info = DeckInfo()
-    check(L.pf_read_dat(job.encode(), 123, C.byref(info)), what="pf_read_dat")
+    check(L.pf_read_dat(job.encode(), program, C.byref(info)), what="pf_read_dat")
     nod, nn, nels, nr = info.nod, info.nn, info.nels, info.nr
     if nod not in (8, 4):
         raise PfError("p123 decks hold 8-node bricks (or, for xx11, 4-node tetrahedra)")
@@ -294,9 +306,16 @@ def read_deck_p123(job, npes=1, numpe=1):
         eq = nf[node - 1, sense - 1]        # find_no2 (loading.f90:742-828): the equation of (node, sense)
         mine = (eq >= ieq_start) & (eq < ieq_start + neq_pp)
         no_f, val_f = np.ascontiguousarray(eq[mine]), np.ascontiguousarray(valf[mine])
-    p = Problem(123, nod, 1, info.nip, nels, nn, nr, neq, npes, numpe, nels_pp, iel_start, neq_pp, ieq_start,
+    p = Problem(program, nod, 1, info.nip, nels, nn, nr, neq, npes, numpe, nels_pp, iel_start, neq_pp, ieq_start,
                 g_num_pp, g_coord_pp, g_g, nf, r, kx=info.kx, ky=info.ky, kz=info.kz, tol=info.tol,
                 limit=info.limit, nres=info.nres, no_f=no_f, val_f=val_f, total_load=total)
+    if program in (124, 125):
+        p.dtim, p.nstep, p.npri, p.val0 = info.dtim, info.nstep, info.npri, info.val0
+    if program == 124:
+        p.theta = info.theta
+        prop = np.empty((info.np_types, 5), np.float64)
+        check(L.pf_read_mat(job.encode(), 5, info.np_types, ptr(prop)), what="pf_read_mat")
+        p.kx, p.ky, p.kz, p.rho, p.cp = (float(v) for v in prop[0])      # one material (p12meshgen.f90:837)
     p.g_coord = g_coord
     return p
 
@@ -338,6 +357,19 @@ def read_deck_xx2(job, npes=1, numpe=1):
     p.etype_pp = np.ascontiguousarray(etype[iel_start - 1:iel_start - 1 + nels_pp])
     p.rest, p.g_coord = rest, g_coord
     return p
+
+
+def write_deck_scalar(job, prob, g_coord, g_num, rest, loaded=0, fixed=0):
+    """p12meshgen's output side for p123 / p124 / p125 (prob.program): <job>.d/.bnd/.dat (+ .mat for p124)."""
+    info = DeckInfo()
+    info.program, info.meshgen, info.partitioner, info.nip, info.nod, info.limit = prob.program, 2, 1, prob.nip, 8, prob.limit
+    info.nels, info.nn, info.nr, info.loaded, info.fixed, info.nres = prob.nels, prob.nn, prob.nr, loaded, fixed, prob.nres
+    info.kx, info.ky, info.kz, info.tol = prob.kx, prob.ky, prob.kz, prob.tol
+    info.np_types, info.nstep, info.npri = 1, prob.nstep, prob.npri
+    info.val0, info.dtim, info.theta, info.rho, info.cp = prob.val0, prob.dtim, prob.theta, prob.rho, prob.cp
+    g_coord, g_num, rest = f64(g_coord), i32(g_num), i32(rest)
+    check(lib().pf_write_deck_scalar(str(job).encode(), C.byref(info), ptr(g_coord), ptr(g_num), ptr(rest)),
+          what="pf_write_deck_scalar")
 
 
 def make_ggl(prob):

@@ -87,7 +87,10 @@ def main():
     gcpp4 = np.empty((nels4, 3, nod4), np.float64)
     assert lib().pf_coords_pp(nod4, nels4, ptr(gn4), ptr(gc4), ptr(gcpp4)) == 0
     # (+ 0.0: p124_demo.d prints the top face's -(is-1)*cc = -0.0 unsigned, p121_demo.d prints it signed)
-    json.dump(dict(g_num_sg=sha(gn4), g_coord_pp=sha(gcpp4 + 0.0), rest=sha(rest4), nn=nn4, nr=nr4, nels=nels4, nip=nip4,
+    fsha = lambda path: hashlib.sha256(open(path, "rb").read()).hexdigest()
+    files = {f"p124_demo{ext}": fsha(d124 + ext) for ext in (".d", ".bnd", ".dat", ".mat")}
+    files.update({f"p125_demo{ext}": fsha(f"{REF}/5th_ed/p125/demo/p125_demo{ext}") for ext in (".d", ".bnd", ".dat")})
+    json.dump(dict(files=files, g_num_sg=sha(gn4), g_coord_pp=sha(gcpp4 + 0.0), rest=sha(rest4), nn=nn4, nr=nr4, nels=nels4, nip=nip4,
                    nod=nod4), open(f"{HERE}/p124_demo_digests.json", "w"), indent=1)
     ndttr = {f"p124_ndttr_{j:03d}": np.loadtxt(f"{d124}.ensi.NDTTR-{j:06d}", skiprows=4).astype(np.float32)
              for j in (10, 80, 150)}

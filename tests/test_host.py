@@ -244,3 +244,30 @@ def test_d_reader_fast_path_and_fallback_agree(tmp_path, tiny, golden):
     dexp = [l.replace("E+", "D+").replace("E-", "D-") if 2 <= i < k_el else l for i, l in enumerate(src)]
     rc, c, n, et = read(dexp)
     assert rc == 0 and np.array_equal(c, ref_c) and np.array_equal(n, ref_n)
+
+
+def test_scalar_deck_writer_reproduces_the_shipped_p124_and_p125_decks(tmp_path):
+    """p12meshgen's output side for p124 / p125 (p12meshgen.f90:879-987, 1075-1160): <job>.d (2.8 MB), .bnd, .dat
+    (and p124's .mat) of examples/5th_ed/p124/demo and p125/demo, byte for byte (SHA-256 of the shipped files), and
+    the readers bring the problem back."""
+    import hashlib
+    import json
+    from parafem_b200._lib import lib, ptr
+    dg = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "p124_demo_digests.json")))["files"]
+    for prog, make, read in ((124, host.cube_p124, host.read_deck_p124), (125, host.cube_p125, host.read_deck_p125)):
+        p = make(25, 25, 25, aa=.04, bb=.04, cc=.04)
+        g_coord = np.zeros((p.nn, 3))
+        g_coord[p.g_num_pp - 1] = np.transpose(p.g_coord_pp, (0, 2, 1))
+        rest = np.zeros((2, p.nr), np.int32)
+        assert lib().pf_cube_rest(1, 25, 25, 25, 8, p.nr, ptr(rest)) == 0
+        job = str(tmp_path / f"p{prog}_demo")
+        host.write_deck_scalar(job, p, g_coord, p.g_num_pp, rest)
+        for ext in (".d", ".bnd", ".dat") + ((".mat",) if prog == 124 else ()):
+            assert hashlib.sha256(open(job + ext, "rb").read()).hexdigest() == dg[f"p{prog}_demo{ext}"], (prog, ext)
+        q = read(job)
+        ref = make(25, 25, 25, aa=.04, bb=.04, cc=.04, round_mode=1)
+        assert np.array_equal(q.g_num_pp, ref.g_num_pp) and np.array_equal(q.g_g_pp, ref.g_g_pp)
+        assert np.array_equal(q.g_coord_pp, ref.g_coord_pp + 0.0)        # the deck prints -0.0 unsigned
+        assert (q.neq, q.nres, q.dtim, q.nstep, q.npri, q.val0) == (ref.neq, ref.nres, ref.dtim, ref.nstep, ref.npri, ref.val0)
+        if prog == 124:
+            assert (q.kx, q.ky, q.kz, q.rho, q.cp, q.theta, q.tol, q.limit) == (1., 1., 1., 1., 1., .5, 1e-4, 100)
