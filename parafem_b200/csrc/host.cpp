@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <charconv>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -69,7 +70,9 @@ void hex8_element(int64_t iel, int nxe, int nze, double aa, double bb, double cc
   for (int m = 0; m < 8; ++m) num[m] = (int32_t)n[m];
   double x0 = (ip - 1) * aa, x1 = ip * aa;
   double y0 = (iq - 1) * bb, y1 = iq * bb;
-  double zb = -(double)is * cc, zt = -(double)(is - 1) * cc;
+  // geometry_8bxz writes -is*cc and -(is-1)*cc with INTEGER is: the shipped 8-node decks (p124_demo.d) show the top
+  // face at +0.0, i.e. the integer is negated before the product
+  double zb = (double)(-is) * cc, zt = (double)(-(is - 1)) * cc;
   const int xhi[8] = {0, 0, 1, 1, 0, 0, 1, 1};
   const int yhi[8] = {0, 0, 0, 0, 1, 1, 1, 1};
   const int ztop[8] = {0, 1, 1, 0, 0, 1, 1, 0};
@@ -738,7 +741,7 @@ int pf_coords_pp(int nod, int64_t nels_pp, const int32_t *g_num_pp, const double
 // Fortran Ew.d edit descriptor (0.ddddE+xx), as dismsh_ensi_p's '(e12.5)' (output.f90:3050,3100)
 static void fortran_e(char *out, size_t cap, double x, int w, int d) {
   char buf[64], body[64];
-  if (x == 0.0) snprintf(body, sizeof body, "0.%0*dE+00", d, 0);
+  if (x == 0.0) snprintf(body, sizeof body, "%s0.%0*dE+00", std::signbit(x) ? "-" : "", d, 0);   // gfortran prints -0.0 signed
   else {
     snprintf(buf, sizeof buf, "%.*E", d - 1, x);
     std::string m(buf);

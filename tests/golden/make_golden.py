@@ -121,7 +121,9 @@ def main():
         "p123_small.mg": lines(f"{REF}/5th_ed/p123/mg/p123_small.mg"), "p121_tiny.mg": lines(f"{REF}/5th_ed/p121/mg/p121_tiny.mg"),
     }
     json.dump(texts, open(f"{HERE}/fixtures.json", "w"), indent=1)
-    digests = dict(g_num_sg=sha(p.g_num_pp), g_coord_pp=sha(p.g_coord_pp), rest=sha(p.rest), g_g=sha(p.g_g_pp),
+    fsha_ = lambda path: hashlib.sha256(open(path, "rb").read()).hexdigest()
+    digests = dict(files={f"p121_demo{ext}": fsha_(demo + ext) for ext in (".d", ".bnd", ".lds", ".dat")},
+                   g_num_sg=sha(p.g_num_pp), g_coord_pp=sha(p.g_coord_pp), rest=sha(p.rest), g_g=sha(p.g_g_pp),
                    r=sha(p.r_pp), nn=int(p.nn), nr=int(p.nr), neq=int(p.neq), nels=int(p.nels))
     json.dump(digests, open(f"{HERE}/p121_demo_digests.json", "w"), indent=1)
     with open(demo + ".ensi.DISPL-000001") as f, open(f"{HERE}/p121_demo_ensi_head.txt", "w") as g:

@@ -271,3 +271,27 @@ def test_scalar_deck_writer_reproduces_the_shipped_p124_and_p125_decks(tmp_path)
         assert (q.neq, q.nres, q.dtim, q.nstep, q.npri, q.val0) == (ref.neq, ref.nres, ref.dtim, ref.nstep, ref.npri, ref.val0)
         if prog == 124:
             assert (q.kx, q.ky, q.kz, q.rho, q.cp, q.theta, q.tol, q.limit) == (1., 1., 1., 1., 1., .5, 1e-4, 100)
+
+
+def test_meshgen_tool_reproduces_the_shipped_decks_from_their_mg_files(tmp_path, golden):
+    """p12meshgen restated as a tool (parafem_b200/meshgen.py): the reference's own <job>.mg inputs give the
+    reference's own decks byte for byte -- p121_demo.mg -> p121_demo.{d,bnd,lds,dat} (4 MB .d, signed zeros
+    included) and p124_tiny.mg -> p124_demo.{d,bnd,dat,mat} (SHA-256 of the shipped files)."""
+    import hashlib
+    import json
+    import shutil
+    from parafem_b200 import meshgen
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    want = dict(json.load(open(os.path.join(gdir, "p121_demo_digests.json")))["files"])
+    want.update(json.load(open(os.path.join(gdir, "p124_demo_digests.json")))["files"])
+    for mg, job, exts in (("p121_demo.mg", "p121_demo", (".d", ".bnd", ".lds", ".dat")),
+                          ("p124_tiny.mg", "p124_demo", (".d", ".bnd", ".dat", ".mat"))):
+        base = str(tmp_path / job)
+        shutil.copy(os.path.join(golden, mg), base + ".mg")
+        assert meshgen.main([base]) == 0
+        for ext in exts:
+            assert hashlib.sha256(open(base + ext, "rb").read()).hexdigest() == want[job + ext], (job, ext)
+    with open(tmp_path / "bad.mg", "w") as f:
+        f.write("'p126' 'parafem' 8 2 2 8\n")
+    with pytest.raises(Exception, match="not one of"):
+        meshgen.generate(str(tmp_path / "bad"))
