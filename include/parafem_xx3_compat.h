@@ -14,7 +14,10 @@
  *     596 523 20-node elements);
  *   - matrix_vector_multiplies runs the bulk-copy-ring mat-vec of this library (k_matvec, the kernel of
  *     pf_pcg_solve) for the element sizes of p121 / p123 (n_row = n_col = 60, 24, 8) and a plain row-per-
- *     thread kernel otherwise; either way lhs(:,e) = MATMUL(matrix(:,:,e), rhs(:,e)) with the column
+ *     thread kernel otherwise; either way, in the reference's naming, d_rhs_vector(:,e) =
+ *     MATMUL(d_matrix(:,:,e), d_lhs_vector(:,e)) -- pmul_pp is uploaded to d_lhs_vector (xx3.f90:496-500), utemp_pp
+ *     is read back from d_rhs_vector (:525-529), the kernel reads lhs_vector and writes rhs_vector
+ *     (cuda_helpers.cu:168-176) -- with the column
  *     sweep j ascending and separate multiply / add, i.e. the bits of the Fortran loop at xx3.f90:476-480
  *     (the reference's kernel MultiMatVecMultiply1, cuda_helpers.cu:144-177, sums in the same order);
  *   - the call is synchronous as in the reference (cudaDeviceSynchronize, cuda_helpers.cu:360).

@@ -23,6 +23,29 @@ def build(force=False):
                        stdout=subprocess.DEVNULL)
 
 
+REF_SRC = "/root/reference/parafem/src/programs/dev/xx3/cuda_helpers.cu"
+REF_DIR = os.path.join(_HERE, "_ref")
+
+
+def build_ref():
+    """oracle/_ref: the reference's own CUDA mat-vec (xx3/cuda_helpers.cu) compiled from where it lies -- only
+    where /root/reference exists (this container); the GPU box uses the shipped binaries."""
+    if os.path.exists(REF_SRC):
+        subprocess.run(["make", "-C", _HERE, "ref"], check=True, stdout=subprocess.DEVNULL)
+    return ref_available()
+
+
+def ref_available():
+    return all(os.path.exists(os.path.join(REF_DIR, n)) for n in ("libxx3_cuda_helpers.so", "libxx3_cuda_helpers_nofma.so"))
+
+
+def ref_lib(nofma=False):
+    """ctypes handle of the reference's compiled cuda_helpers (RTLD_LOCAL: its symbols have the same names as the
+    product's xx3-compatible entry points)."""
+    name = "libxx3_cuda_helpers_nofma.so" if nofma else "libxx3_cuda_helpers.so"
+    return C.CDLL(os.path.join(REF_DIR, name), mode=os.RTLD_LOCAL | os.RTLD_NOW)
+
+
 def lib():
     global _lib
     if _lib is None:

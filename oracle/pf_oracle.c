@@ -7,8 +7,10 @@
  *
  * It is a plain-C restatement (not a copy) of the reference's algorithm; the
  * reference itself is Fortran 90 + MPI and cannot be compiled in this image
- * (no gfortran, no MPI -- see DESIGN.md), so there is no oracle/_ref binary.
- * Parity is pinned against the reference's own golden outputs instead
+ * (no gfortran, no MPI -- see DESIGN.md); the one compilable source of the
+ * reference on this path, xx3/cuda_helpers.cu, is built into oracle/_ref by
+ * `make ref` and compared on the GPU in tests/test_gpu_xx3_compat.py.
+ * Parity is otherwise pinned against the reference's own golden outputs
  * (tests/golden/, tests/test_oracle_golden.py): xx3-tiny 79 iterations +
  * 756x3 displacements, p121_demo 98 360 equations / 295 iterations / x(1) /
  * centroid stresses / EnSight displacement field, p121 book 777 520 equations,

@@ -73,8 +73,10 @@ int matrix_vector_multiplies(int *n_mat, int *n_row, int *n_col, void **d_lhs_ve
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return xx3_fail("Failed to launch multiply kernel!", e);
-  const double *mat = static_cast<const double *>(*d_matrix), *rhs = static_cast<const double *>(*d_rhs_vector);
-  double *lhs = static_cast<double *>(*d_lhs_vector);
+  // The reference's naming: d_lhs_vector is the LEFT-HAND OPERAND (pmul_pp goes in, xx3.f90:496-500) and
+  // d_rhs_vector receives the products (utemp_pp comes out, xx3.f90:525-529; cuda_helpers.cu:172-176).
+  const double *mat = static_cast<const double *>(*d_matrix), *rhs = static_cast<const double *>(*d_lhs_vector);
+  double *lhs = static_cast<double *>(*d_rhs_vector);
   const long long n = *n_mat;
   if (*n_row == *n_col && *n_row == 60) e = xx3_ring<60, 1, 7>(mat, rhs, lhs, n, sms);
   else if (*n_row == *n_col && *n_row == 24) e = xx3_ring<24, 1, 32>(mat, rhs, lhs, n, sms);

@@ -40,12 +40,12 @@ for n_mat, nr, nc in ((37, 60, 60), (41, 24, 24), (67, 8, 8), (19, 12, 7)):
     dk, dr, dl = C.c_void_p(), C.c_void_p(), C.c_void_p()
     km, pm, out = np.random.rand(n_mat, nc, nr), np.random.rand(n_mat, nc), np.empty((n_mat, nr))
     assert L.allocate_memory_on_gpu(ci(km.size), ci(8), C.byref(dk)) == 0
-    assert L.allocate_memory_on_gpu(ci(pm.size), ci(8), C.byref(dr)) == 0
-    assert L.allocate_memory_on_gpu(ci(out.size), ci(8), C.byref(dl)) == 0
+    assert L.allocate_memory_on_gpu(ci(pm.size), ci(8), C.byref(dl)) == 0
+    assert L.allocate_memory_on_gpu(ci(out.size), ci(8), C.byref(dr)) == 0
     assert L.copy_data_to_gpu(ci(km.size), ci(8), ptr(km), C.byref(dk)) == 0
-    assert L.copy_data_to_gpu(ci(pm.size), ci(8), ptr(pm), C.byref(dr)) == 0
+    assert L.copy_data_to_gpu(ci(pm.size), ci(8), ptr(pm), C.byref(dl)) == 0
     assert L.matrix_vector_multiplies(ci(n_mat), ci(nr), ci(nc), C.byref(dl), C.byref(dk), C.byref(dr)) == 0
-    assert L.copy_data_from_gpu(ci(out.size), ci(8), ptr(out), C.byref(dl)) == 0
+    assert L.copy_data_from_gpu(ci(out.size), ci(8), ptr(out), C.byref(dr)) == 0
     for d in (dk, dr, dl):
         assert L.free_memory_on_gpu(C.byref(d)) == 0
     print("xx3", n_mat, nr, nc, float(out.sum()))

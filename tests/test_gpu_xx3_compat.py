@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle
-from parafem_b200._lib import lib, ptr
+from parafem_b200._lib import XX3_SIGNATURES, lib, ptr
 
 pytestmark = pytest.mark.gpu
 
@@ -17,16 +17,17 @@ def ci(v):
 
 
 class Xx3Gpu:
-    """What xx3.f90 does with its three device pointers."""
+    """What xx3.f90 does with its three device pointers: pmul_pp -> device_lhs_vector, the products come back from
+    device_rhs_vector (xx3.f90:496-529).  L = the library that provides the six symbols."""
 
-    def __init__(self, n_mat, n_row, n_col):
-        self.L, self.shape = lib(), (n_mat, n_row, n_col)
+    def __init__(self, n_mat, n_row, n_col, L=None):
+        self.L, self.shape = (L if L is not None else lib()), (n_mat, n_row, n_col)
         self.d_km, self.d_rhs, self.d_lhs = C.c_void_p(), C.c_void_p(), C.c_void_p()
         dev = C.c_int(0)
         assert self.L.set_gpu(C.byref(dev)) == 0
         assert self.L.allocate_memory_on_gpu(ci(n_mat * n_row * n_col), ci(8), C.byref(self.d_km)) == 0      # xx3.f90:423
-        assert self.L.allocate_memory_on_gpu(ci(n_mat * n_col), ci(8), C.byref(self.d_rhs)) == 0              # :433
-        assert self.L.allocate_memory_on_gpu(ci(n_mat * n_row), ci(8), C.byref(self.d_lhs)) == 0              # :443
+        assert self.L.allocate_memory_on_gpu(ci(n_mat * n_col), ci(8), C.byref(self.d_lhs)) == 0              # :433
+        assert self.L.allocate_memory_on_gpu(ci(n_mat * n_row), ci(8), C.byref(self.d_rhs)) == 0              # :443
 
     def upload(self, km):
         n_mat, n_row, n_col = self.shape
@@ -35,10 +36,10 @@ class Xx3Gpu:
     def multiply(self, pmul):
         n_mat, n_row, n_col = self.shape
         out = np.empty((n_mat, n_row))
-        assert self.L.copy_data_to_gpu(ci(n_mat * n_col), ci(8), ptr(pmul), C.byref(self.d_rhs)) == 0         # :496
+        assert self.L.copy_data_to_gpu(ci(n_mat * n_col), ci(8), ptr(pmul), C.byref(self.d_lhs)) == 0         # :496
         assert self.L.matrix_vector_multiplies(ci(n_mat), ci(n_row), ci(n_col), C.byref(self.d_lhs), C.byref(self.d_km),
                                                C.byref(self.d_rhs)) == 0                                      # :509
-        assert self.L.copy_data_from_gpu(ci(n_mat * n_row), ci(8), ptr(out), C.byref(self.d_lhs)) == 0        # :525
+        assert self.L.copy_data_from_gpu(ci(n_mat * n_row), ci(8), ptr(out), C.byref(self.d_rhs)) == 0        # :525
         return out
 
     def close(self):
@@ -70,6 +71,41 @@ def test_any_shape_equals_the_column_sweep(n_mat, n_row, n_col):
         ref = ref + km[:, j, :] * pmul[:, j:j + 1]
     assert np.array_equal(g.multiply(pmul), ref)
     g.close()
+
+
+def _ref_handle(nofma):
+    L = oracle.ref_lib(nofma=nofma)
+    for name, (res, args) in XX3_SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    return L
+
+
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref was not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("n_mat,ntot", [(2000, 60), (3001, 24), (10007, 8), (77, 12)])
+def test_against_the_reference_binary(n_mat, ntot):
+    """oracle/_ref: the reference's OWN cuda_helpers.cu (xx3's MultiMatVecMultiply1, cuda_helpers.cu:144-177),
+    compiled by oracle/Makefile from where it lies, run on this GPU through the same six symbols.  Built with
+    --fmad=false (the rounding of the Fortran MATMUL loop the GPU path of xx3 replaces) it must give the SAME BITS as
+    this library; built as the reference builds it (nvcc default: the multiply-add is contracted to an FMA) the two
+    agree to rounding."""
+    rng = np.random.RandomState(ntot)
+    km = rng.randn(n_mat, ntot, ntot)
+    pmul = rng.randn(n_mat, ntot)
+    ours = Xx3Gpu(n_mat, ntot, ntot)
+    ours.upload(km)
+    u = ours.multiply(pmul)
+    ours.close()
+    assert np.array_equal(u, oracle.matvec(km, pmul))
+    for nofma in (True, False):
+        ref = Xx3Gpu(n_mat, ntot, ntot, L=_ref_handle(nofma))
+        ref.upload(km)
+        u_ref = ref.multiply(pmul)
+        ref.close()
+        if nofma:
+            assert np.array_equal(u, u_ref)
+        else:
+            assert np.abs(u - u_ref).max() <= 1e-13 * np.abs(u_ref).max()       # FMA contraction: last-bit differences
 
 
 def test_failures_return_exit_failure():
