@@ -35,6 +35,12 @@ def build_ref():
     return ref_available()
 
 
+def ref_tool(name="metout2pf"):
+    """Path of a reference tool built into oracle/_ref (None when it was not built)."""
+    path = os.path.join(REF_DIR, name)
+    return path if os.path.exists(path) else None
+
+
 def ref_available():
     return all(os.path.exists(os.path.join(REF_DIR, n)) for n in ("libxx3_cuda_helpers.so", "libxx3_cuda_helpers_nofma.so"))
 

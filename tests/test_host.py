@@ -295,3 +295,60 @@ def test_meshgen_tool_reproduces_the_shipped_decks_from_their_mg_files(tmp_path,
         f.write("'p126' 'parafem' 8 2 2 8\n")
     with pytest.raises(Exception, match="not one of"):
         meshgen.generate(str(tmp_path / "bad"))
+
+
+@pytest.mark.skipif(oracle.ref_tool("metout2pf") is None, reason="oracle/_ref/metout2pf was not built (needs /root/reference)")
+def test_partitioner_2_on_a_deck_produced_by_the_reference_partition_tool(tmp_path):
+    """The reference's own metout2pf (tools/preprocessing/partitioner/metout2pf.c, compiled into oracle/_ref) turns a
+    deck + a METIS element partition into a deck sorted by partition with renumbered nodes + <job>.psize -- exactly what
+    partitioner 2 (read_nels_pp, input.f90:3108-3196) consumes.  Its output goes through this repo's readers and
+    partition arithmetic at 3 ranks, and the solve on it equals the solve on the original deck node by node."""
+    import subprocess
+    from parafem_b200 import meshgen
+    d = str(tmp_path)
+    with open(f"{d}/cube.mg", "w") as f:
+        f.write("'p121'\n'parafem' 60 5 3 20 8\n1.0 1.0 1.0 100.0 0.3\n1.0e-11 3000\n")
+    meshgen.generate(f"{d}/cube")
+    for ext in (".d", ".bnd", ".lds"):                     # the tool reads records into a 256-byte buffer: compact them
+        rows = [" ".join(l.split()) for l in open(f"{d}/cube{ext}")]
+        open(f"{d}/cube{ext}", "w").write("\n".join(rows) + "\n")
+    part = np.random.RandomState(4).randint(0, 3, 60)
+    open(f"{d}/cube.epart.3", "w").write("\n".join(str(v) for v in part) + "\n")
+    res = subprocess.run([oracle.ref_tool("metout2pf"), f"{d}/cube.epart.3", f"{d}/cube", f"{d}/cube_part"],
+                         capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0 and os.path.exists(f"{d}/cube_part.psize")
+    dat = open(f"{d}/cube.dat").read().splitlines()
+    dat[2] = "2"                                            # partitioner 2: element counts from <job>.psize
+    open(f"{d}/cube_part.dat", "w").write("\n".join(dat) + "\n")
+    sizes = [int(v) for v in open(f"{d}/cube_part.psize").read().split()][1:]
+    assert sizes == list(np.bincount(part, minlength=3))
+    ranks = [host.read_deck_p121(f"{d}/cube_part", npes=3, numpe=k) for k in (1, 2, 3)]
+    assert [r.nels_pp for r in ranks] == sizes and [r.iel_start for r in ranks] == [1, 1 + sizes[0], 1 + sizes[0] + sizes[1]]
+    assert sum(r.neq_pp for r in ranks) == ranks[0].neq
+    # the solve on the partitioned deck (3 emulated ranks on the tool's partition) ...
+    g_g = np.concatenate([r.g_g_pp for r in ranks])
+    coord = np.concatenate([r.g_coord_pp for r in ranks])
+    rhs = np.concatenate([r.r_pp for r in ranks])
+    oracle.set_element_partition(sizes)
+    try:
+        a = oracle.pcg(oracle.form_km_elastic(coord, 20, 8, 100.0, 0.3), g_g, ranks[0].neq, rhs, 1e-11, 3000, npes=3, red_mode=0)
+    finally:
+        oracle.set_element_partition(None)
+    # ... against the original deck with the loads as the tool rewrote them (single precision, 5 digits)
+    o = host.read_deck_p121(f"{d}/cube")
+    node, val = np.loadtxt(f"{d}/cube.lds")[:, 0].astype(int), np.loadtxt(f"{d}/cube.lds")[:, 1:]
+    val5 = np.array([[float(f"{np.float32(v): 1.4E}") for v in row] for row in val])
+    r_o = np.zeros(o.neq)
+    for n, v in zip(node, val5):
+        for k in range(3):
+            if o.nf[n - 1, k]:
+                r_o[o.nf[n - 1, k] - 1] = v[k]
+    b = oracle.pcg(oracle.form_km_elastic(o.g_coord_pp, 20, 8, 100.0, 0.3), o.g_g_pp, o.neq, r_o, 1e-11, 3000, npes=1, red_mode=0)
+    assert a["converged"] and b["converged"] and ranks[0].neq == o.neq
+    field = lambda p, x: np.where(p.nf > 0, x[np.maximum(p.nf, 1) - 1], 0.0)
+    ua, ub = field(ranks[0], a["x"]), field(o, b["x"])
+    key = lambda c: tuple(np.round(c * 4).astype(int))      # coordinates are multiples of 0.5: exact in the tool's % 1.4E
+    where = {key(c): i for i, c in enumerate(o.g_coord)}
+    perm = np.array([where[key(c)] for c in ranks[0].g_coord])
+    assert sorted(perm) == list(range(o.nn))
+    assert np.abs(ua - ub[perm]).max() <= 1e-8 * np.abs(ub).max()
