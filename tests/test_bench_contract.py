@@ -57,3 +57,25 @@ def test_variant_lines_carry_their_own_roofline():
     for name in ("matrix_free_geometric_factors", "matrix_free_rebuilt_from_coordinates"):
         r = v[name]["roofline"]
         assert r["bound"] == "fp64" and r["unit"] == "TFLOP/s" and 0 < r["frac"] < 1
+
+
+def test_reference_arm_runs_on_cpu_and_under_torchrun():
+    """`bench.py --impl reference` is CPU work: alone it prints ONE JSON line; launched like the GPU arm for N = 2
+    (torch.distributed.run, rendezvous on 127.0.0.1) rank 0 alone prints it and the other rank exits 0 without work."""
+    import subprocess
+    import sys
+    bench = os.path.join(ROOT, "bench.py")
+    common = ["--impl", "reference", "--steps", "3", "--warmup", "1", "--cpu-n", "8"]
+    one = subprocess.run([sys.executable, bench] + common, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert one.returncode == 0, one.stderr[-2000:]
+    lines = [l for l in one.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["steps"] == 3 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "8^3" in d["cpu_baseline"]["sample"]
+    two = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29377", bench, "--gpus", "2"] + common,
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert two.returncode == 0, two.stderr[-2000:]
+    lines = [l for l in two.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and json.loads(lines[0])["n_gpus"] == 2 and json.loads(lines[0])["impl"] == "reference"
