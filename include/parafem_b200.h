@@ -3,8 +3,12 @@
  *
  * B200-native (sm_100a) replacement for the EBE-PCG hot path of ParaFEM programs
  * p121 (3-D elasticity, 20-/8-node hexahedra) and p123 (steady heat conduction,
- * 8-node hexahedra).  It is, in the reference's own terms, the missing
- * "modules/gpu" platform library (parafem/src/modules/readme.txt:9-40).
+ * 8-node hexahedra), and of the drivers that reuse the same gather / mat-vec /
+ * scatter kernels: p124 (implicit transient conduction), p125 (explicit transient
+ * conduction), xx2 (per-element materials); 4-node tetrahedra are served too.
+ * It is, in the reference's own terms, the missing "modules/gpu" platform library
+ * (parafem/src/modules/readme.txt:9-40).  The six symbols the reference's existing
+ * GPU driver xx3 binds are declared in parafem_xx3_compat.h.
  *
  * Conventions (same as the reference's existing CUDA boundary,
  * parafem/src/programs/dev/xx3/cuda_helpers.cu:183-368 and the
