@@ -740,18 +740,31 @@ int pf_coords_pp(int nod, int64_t nels_pp, const int32_t *g_num_pp, const double
 
 // Fortran Ew.d edit descriptor (0.ddddE+xx), as dismsh_ensi_p's '(e12.5)' (output.f90:3050,3100)
 static void fortran_e(char *out, size_t cap, double x, int w, int d) {
-  char buf[64], body[64];
-  if (x == 0.0) snprintf(body, sizeof body, "%s0.%0*dE+00", std::signbit(x) ? "-" : "", d, 0);   // gfortran prints -0.0 signed
-  else {
-    snprintf(buf, sizeof buf, "%.*E", d - 1, x);
-    std::string m(buf);
-    const size_t epos = m.find('E');
-    const int ex = atoi(m.c_str() + epos + 1) + 1;
-    std::string digits;
-    for (char c : m.substr(0, epos)) if (c >= '0' && c <= '9') digits.push_back(c);
-    snprintf(body, sizeof body, "%s0.%sE%c%02d", x < 0 ? "-" : "", digits.c_str(), ex < 0 ? '-' : '+', ex < 0 ? -ex : ex);
+  // d significant digits, correctly rounded (to_chars, same digits as printf's %.{d-1}E), written as 0.DDDDE+XX
+  char body[80];
+  int n = 0;
+  if (std::signbit(x)) body[n++] = '-';                   // gfortran prints -0.0 signed
+  body[n++] = '0'; body[n++] = '.';
+  if (x == 0.0) {
+    for (int k = 0; k < d; ++k) body[n++] = '0';
+    memcpy(body + n, "E+00", 4); n += 4;
+  } else {
+    char t[64];
+    auto r = std::to_chars(t, t + sizeof t, std::fabs(x), std::chars_format::scientific, d - 1);
+    *r.ptr = 0;
+    const char *e = strchr(t, 'e');
+    for (const char *q = t; q < e; ++q) if (*q != '.') body[n++] = *q;
+    int ex = atoi(e + 1) + 1;
+    body[n++] = 'E'; body[n++] = ex < 0 ? '-' : '+';
+    if (ex < 0) ex = -ex;
+    if (ex >= 100) { body[n - 2] = body[n - 1]; --n; body[n++] = (char)('0' + ex / 100); ex %= 100; }   // E+100 -> +100
+    body[n++] = (char)('0' + ex / 10); body[n++] = (char)('0' + ex % 10);
   }
-  snprintf(out, cap, "%*s", w, body);
+  int pad = w - n;
+  size_t o = 0;
+  for (; pad > 0 && o + 1 < cap; --pad) out[o++] = ' ';
+  for (int k = 0; k < n && o + 1 < cap; ++k) out[o++] = body[k];
+  out[o] = 0;
 }
 
 }  // extern "C"
