@@ -27,15 +27,23 @@ def _fe(x, w=12, d=4):
     return s.rjust(w)
 
 
-def run(prob, s):
-    """-> dict(iters, converged, x, solve_s, setup_s, sigma, total_load)."""
+def run(prob, s, profile=False):
+    """-> dict(iters, converged, x, solve_s, setup_s, sigma, total_load); profile=True brackets every kernel of the
+    solve with CUDA events and adds kernels = {name: (total_ms, launches)}."""
     t0 = time.time()
     _solver.setup_problem(s, prob)
     t_setup = time.time() - t0
+    if profile:
+        s.set_profile(True)
+        s.reset_profile()
     t1 = time.time()
     x, iters, conv = s.pcg_solve(prob.r_pp, prob.tol, prob.limit)
     t_solve = time.time() - t1
     out = dict(iters=iters, converged=conv, x=x, solve_s=t_solve, setup_s=t_setup, total_load=prob.total_load)
+    if profile:
+        names = ("mat-vec kernel (storkm stream)", "scatter kernel", "vector kernels + reductions", "halo exchange")
+        out["kernels"] = {n: s.kernel_ms(i) for i, n in enumerate(names)}
+        s.set_profile(False)
     if prob.program == 121:
         out["sigma"] = s.centroid_stress(0, prob.e, prob.v) if prob.numpe == 1 else None
     return out
@@ -140,6 +148,36 @@ def write_res_p125(path, prob, res, t_read=0.0, t_total=0.0):
         f.write(f"This analysis took  :{t_total:10.4f}\n")
 
 
+XX3_SECTIONS = ("Setup", "Read element steering array", "Convert Abaqus to S&G node ordering", "Read nodal coordinates",
+                "Read restrained nodes", "Compute steering array and neq", "Compute interprocessor communication tables",
+                "Allocate neq_pp arrays", "Compute element stiffness matrices", "Build the preconditioner",
+                "Get starting r", "Solve equations", "Output results")
+
+
+def write_res_xx3(path, prob, res, loaded_nodes, seconds, kernels=None):
+    """<job>.res in the layout of the reference's GPU driver xx3 (programs/dev/xx3/xx3.f90, golden
+    examples/dev/xx3/demo/xx3-tiny.res): BASIC JOB DATA, then the 'section / seconds / %total' table -- SURVEY 5.1's
+    hook for the device timings.  `seconds`: {section name: seconds} for the names in XX3_SECTIONS (missing = 0);
+    `kernels`: optional {name: (total_ms, launches)} from Solver.kernel_ms, appended as indented rows under
+    'Solve equations' (CUDA events on the solver stream)."""
+    total = sum(seconds.get(k, 0.0) for k in XX3_SECTIONS)
+    with open(path, "w") as f:
+        f.write("\n" + "BASIC JOB DATA".ljust(48) + "\n")
+        for label, val in (("Number of processors used", prob.npes), ("Number of nodes in the mesh", prob.nn),
+                           ("Number of nodes that were restrained", prob.nr), ("Number of equations solved", prob.neq),
+                           ("Number of PCG iterations", res["iters"]), ("Number of loaded nodes", loaded_nodes)):
+            f.write(f"{label:<44}{val:12d}\n")
+        f.write(f"{'Total load applied':<44}{_fe(res['total_load'])}\n\n")
+        f.write("PROGRAM SECTION EXECUTION TIMES                  SECONDS  %TOTAL    \n")
+        for name in XX3_SECTIONS:
+            t = seconds.get(name, 0.0)
+            f.write(f"{name:<44}{t:12.6f}{100.0 * t / total if total > 0 else 0.0:8.2f}\n")
+            if name == "Solve equations" and kernels:
+                for kname, (ms, n) in kernels.items():
+                    f.write(f"{'  ' + kname + f' ({n} launches)':<44}{ms / 1e3:12.6f}{100.0 * ms / 1e3 / total if total > 0 else 0.0:8.2f}\n")
+        f.write(f"{'Total execution time':<44}{total:12.6f}{100.0 if total > 0 else 0.0:8.2f}\n")
+
+
 def write_res(path, prob, res, t_read=0.0, t_total=0.0):
     """<job>.res as rank 1 writes it."""
     with open(path, "w") as f:
@@ -193,6 +231,9 @@ def main(argv=None):
     ap.add_argument("--hex", type=int, default=20, choices=[8, 20])
     ap.add_argument("--matrix-free", type=int, default=0, choices=[0, 1, 2])
     ap.add_argument("--out", default=".")
+    ap.add_argument("--xx3-res", action="store_true",
+                    help="p121: also write <job>.xx3.res, the section / seconds / %%total table of the reference's GPU "
+                         "driver xx3 with the device kernels (CUDA events) listed under 'Solve equations'")
     a = ap.parse_args(argv)
     t0 = time.time()
     if a.deck:
@@ -225,8 +266,11 @@ def main(argv=None):
             res = dict(iters=iters, converged=conv, x=x, solve_s=0.0, setup_s=0.0, total_load=prob.total_load,
                        sigma=s.centroid_stress(0, prob.e, prob.v))
         else:
-            res = run(prob, s)
+            res = run(prob, s, profile=a.xx3_res)
     base = os.path.join(a.out, job)
+    if a.xx3_res and prob.program == 121 and "kernels" in res:
+        secs = {"Setup": t_read, "Compute element stiffness matrices": res["setup_s"], "Solve equations": res["solve_s"]}
+        write_res_xx3(base + ".xx3.res", prob, res, 0, secs, kernels=res["kernels"])
     write_res(base + ".res", prob, res, t_read=t_read, t_total=time.time() - t0)
     kind = "DISPL" if prob.program == 121 else "NDPTL"
     host.write_ensi(f"{base}.ensi.{kind}-000001", host.nodal_values(prob, res["x"]), decimals=5)

@@ -352,3 +352,24 @@ def test_partitioner_2_on_a_deck_produced_by_the_reference_partition_tool(tmp_pa
     perm = np.array([where[key(c)] for c in ranks[0].g_coord])
     assert sorted(perm) == list(range(o.nn))
     assert np.abs(ua - ub[perm]).max() <= 1e-8 * np.abs(ub).max()
+
+
+def test_xx3_style_res_table(tmp_path, tiny, golden):
+    """driver.write_res_xx3 writes the reference GPU driver's log layout: fed the numbers of the shipped xx3-tiny.res
+    it reproduces the WHOLE file as text (BASIC JOB DATA block, section table, %total column); device kernel rows are
+    appended under 'Solve equations' when given."""
+    from parafem_b200 import driver
+    gold = open(os.path.join(golden, "xx3-tiny.res")).read().splitlines()
+    tiny_4 = host.read_deck_p121(os.path.join(golden, "xx3-tiny"), npes=4, numpe=1)
+    assert gold[1].startswith("BASIC JOB DATA") and gold[11].startswith("Setup")
+    secs = {name: float(line[44:56]) for name, line in zip(driver.XX3_SECTIONS, gold[11:24])}
+    path = tmp_path / "xx3-tiny.res"
+    driver.write_res_xx3(path, tiny_4, dict(iters=79, total_load=tiny.total_load), 8, secs)
+    assert open(path).read().splitlines() == gold[:len(open(path).read().splitlines())]
+    assert len(open(path).read().splitlines()) == 25
+    driver.write_res_xx3(path, tiny_4, dict(iters=79, total_load=tiny.total_load), 8, secs,
+                         kernels={"mat-vec": (12.5, 79), "scatter": (1.25, 79)})
+    out = open(path).read().splitlines()
+    kern = [l for l in out if l.startswith("  ")]
+    assert len(out) == 27 and out.index(kern[0]) == out.index(gold[22]) + 1          # right under 'Solve equations'
+    assert kern[0].startswith("  mat-vec (79 launches)") and kern[0][44:56] == "    0.012500"
