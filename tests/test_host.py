@@ -312,6 +312,20 @@ def test_partitioner_2_on_a_deck_produced_by_the_reference_partition_tool(tmp_pa
     for ext in (".d", ".bnd", ".lds"):                     # the tool reads records into a 256-byte buffer: compact them
         rows = [" ".join(l.split()) for l in open(f"{d}/cube{ext}")]
         open(f"{d}/cube{ext}", "w").write("\n".join(rows) + "\n")
+    # the other half of the reference's METIS glue, pf2metin (deck -> METIS mesh file; 8-node bricks and 4-node
+    # tetrahedra only), reads a deck this repo wrote: element count, METIS element type 3, the eight nodes per element
+    if oracle.ref_tool("pf2metin"):
+        with open(f"{d}/cube8.mg", "w") as f:
+            f.write("'p121'\n'parafem' 60 5 3 8 8\n1.0 1.0 1.0 100.0 0.3\n1.0e-5 200\n")
+        meshgen.generate(f"{d}/cube8")
+        rows = [" ".join(l.split()) for l in open(f"{d}/cube8.d")]
+        open(f"{d}/cube8.d", "w").write("\n".join(rows) + "\n")
+        res = subprocess.run([oracle.ref_tool("pf2metin"), f"{d}/cube8.d", f"{d}/cube8.met"], capture_output=True, text=True, timeout=120)
+        met = open(f"{d}/cube8.met").read().split()
+        deck = [r.split() for r in rows[rows.index("*ELEMENTS") + 1:]]
+        assert res.returncode == 0 and met[:2] == ["60", "3"] and len(met) == 2 + 60 * 8
+        order = (4, 0, 3, 7, 5, 1, 2, 6)                    # the tool's METIS hexahedron order (pf2metin.c:184-188)
+        assert [met[2 + 8 * e:10 + 8 * e] for e in range(60)] == [[row[4 + k] for k in order] for row in deck]
     part = np.random.RandomState(4).randint(0, 3, 60)
     open(f"{d}/cube.epart.3", "w").write("\n".join(str(v) for v in part) + "\n")
     res = subprocess.run([oracle.ref_tool("metout2pf"), f"{d}/cube.epart.3", f"{d}/cube", f"{d}/cube_part"],
