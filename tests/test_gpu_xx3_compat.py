@@ -81,7 +81,6 @@ def _ref_handle(nofma):
     return L
 
 
-@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref was not built (needs /root/reference at build time)")
 @pytest.mark.parametrize("n_mat,ntot", [(2000, 60), (3001, 24), (10007, 8), (77, 12)])
 def test_against_the_reference_binary(n_mat, ntot):
     """oracle/_ref: the reference's OWN cuda_helpers.cu (xx3's MultiMatVecMultiply1, cuda_helpers.cu:144-177),
@@ -89,6 +88,8 @@ def test_against_the_reference_binary(n_mat, ntot):
     --fmad=false (the rounding of the Fortran MATMUL loop the GPU path of xx3 replaces) it must give the SAME BITS as
     this library; built as the reference builds it (nvcc default: the multiply-add is contracted to an FMA) the two
     agree to rounding."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref was not built (needs /root/reference at build time)")
     rng = np.random.RandomState(ntot)
     km = rng.randn(n_mat, ntot, ntot)
     pmul = rng.randn(n_mat, ntot)
