@@ -74,6 +74,18 @@ def main():
     tt = host.read_deck_p123(f"{REF}/dev/xx11/tetrahedron_cube/xx11_tetcube")
     xx11.update(xx11tet_coord=tt.g_coord, xx11tet_gnum_sg=tt.g_num_pp, xx11tet_lds_eq=(np.flatnonzero(tt.r_pp) + 1).astype(np.int32),
                 xx11tet_lds_val=tt.r_pp[np.flatnonzero(tt.r_pp)], xx11tet_fix_node=tt.no_f, xx11tet_fix_val=tt.val_f)
+    # p122 demo deck (elasto-plasticity; oracle only this round): unstructured 8-node mesh, 19 fixed freedoms
+    d122 = f"{REF}/5th_ed/p122/demo/p122_demo"
+    tk = open(d122 + ".dat").read().split()
+    nels2, nn2, nr2, nod2, fix2 = int(tk[3]), int(tk[4]), int(tk[5]), int(tk[7]), int(tk[8])
+    gc2, gn2 = np.empty((nn2, 3)), np.empty((nels2, nod2), np.int32)
+    assert lib().pf_read_d(d122.encode(), nn2, nels2, nod2, ptr(gc2), ptr(gn2)) == 0 and int(tk[1]) == 1
+    rest2 = np.zeros((4, nr2), np.int32)
+    assert lib().pf_read_bnd(d122.encode(), nr2, 3, ptr(rest2)) == 0
+    fn2, fs2, fv2 = np.empty(fix2, np.int32), np.empty(fix2, np.int32), np.empty(fix2)
+    assert lib().pf_read_fix(d122.encode(), fix2, ptr(fn2), ptr(fs2), ptr(fv2)) == 0
+    p122 = dict(p122_coord=gc2, p122_gnum_sg=gn2, p122_rest=rest2, p122_fix_node=fn2, p122_fix_sense=fs2, p122_fix_val=fv2,
+                p122_displ_010=np.loadtxt(d122 + ".ensi.DISPL-000010", skiprows=4).astype(np.float32))
     # p124 demo deck (transient conduction, 25^3 8-node bricks, Abaqus node order on disk)
     d124 = f"{REF}/5th_ed/p124/demo/p124_demo"
     dat = open(d124 + ".dat").read().split()
@@ -104,7 +116,7 @@ def main():
     assert open(d125 + ".bnd").read() == open(d124 + ".bnd").read()
     ndpre = {f"p125_ndpre_{j:04d}": np.loadtxt(f"{d125}.ensi.NDPRE-{j:06d}", skiprows=4).astype(np.float32)
              for j in (500, 5000)}
-    np.savez_compressed(f"{HERE}/arrays.npz", **ndttr, **ndpre, **xx2, **xx11, tiny_coord=t.g_coord, tiny_gnum_sg=t.g_num_pp, tiny_rest=t.rest,
+    np.savez_compressed(f"{HERE}/arrays.npz", **ndttr, **ndpre, **xx2, **xx11, **p122, tiny_coord=t.g_coord, tiny_gnum_sg=t.g_num_pp, tiny_rest=t.rest,
                         tiny_lds_node=node, tiny_lds_val=val, tiny_dis=dis, demo_lds_node=dnode, demo_lds_val=dval,
                         demo_displ=disp.reshape(3, p.nn).T.astype(np.float32))
     texts = {
@@ -113,6 +125,7 @@ def main():
         "p121_book.res": lines(f"{REF}/5th_ed/p121/book/p121.res"), "p121_book.mg": lines(f"{REF}/5th_ed/p121/book/p121.mg"),
         "p123_book.res": lines(f"{REF}/5th_ed/p123/book/p123.res"), "p123_book.mg": lines(f"{REF}/5th_ed/p123/book/p123.mg"),
         "xx2-tiny.res": lines(x2 + ".res"), "xx2-tiny.dat": lines(x2 + ".dat"), "xx2-tiny.mat": lines(x2 + ".mat"),
+        "p122_demo.dat": lines(d122 + ".dat"), "p122_demo.res": lines(d122 + ".res"),
         "xx11.dat": lines(x11 + ".dat"), "xx11_tetcube.dat": lines(f"{REF}/dev/xx11/tetrahedron_cube/xx11_tetcube.dat"),
         "p125_demo.res": lines(d125 + ".res"), "p125_demo.dat": lines(d125 + ".dat"),
         "p124_demo.res": lines(d124 + ".res"), "p124_demo.dat": lines(d124 + ".dat"), "p124_demo.mat": lines(d124 + ".mat"),

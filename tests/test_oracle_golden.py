@@ -362,3 +362,41 @@ def test_abaqus2sg_tetrahedron():
     g = np.array([[10, 20, 30, 40], [1, 2, 3, 4]], np.int32)
     assert lib().pf_abaqus2sg(4, 2, ptr(g)) == 0
     assert np.array_equal(g, [[10, 30, 20, 40], [1, 3, 2, 4]])
+
+
+# ---- p122: elasto-plasticity (oracle only; the device side is the next round's) -------------
+
+def test_p122_demo_log_and_displacements(golden):
+    """examples/5th_ed/p122/demo/p122_demo.res (4 ranks): 3636 equations, ten displacement-controlled load increments
+    of a Mohr-Coulomb solid (viscoplastic strain method, PCG restarted from the current x) -- displacement, the three
+    stresses of the first Gauss point, the total cj iterations and the plastic iterations of EVERY increment reproduced
+    exactly, and the final displacement field to the 4 digits of p122_demo.ensi.DISPL-000010."""
+    from oracle import p122_oracle
+    a = np.load(os.path.join(os.path.dirname(__file__), "golden", "arrays.npz"))
+    tk = open(os.path.join(golden, "p122_demo.dat")).read().split()
+    nels, nn, nr, nip, nod, fixed, loaded = (int(v) for v in tk[3:10])
+    phi, c, psi, e, v = (float(t) for t in tk[10:15])
+    incs, plasits, cjits = (int(t) for t in tk[15:18])
+    plastol, cjtol, qinc = float(tk[18]), float(tk[19]), [float(t) for t in tk[20:20 + int(tk[15])]]
+    assert (nels, nn, nr, nip, nod, fixed, loaded, incs) == (1152, 1469, 497, 8, 8, 19, 0, 10)
+    gn = np.ascontiguousarray(a["p122_gnum_sg"])
+    nf, g_g, neq = host._steer(nn, 3, np.ascontiguousarray(a["p122_rest"]), gn, nod)
+    coord = np.ascontiguousarray(np.transpose(a["p122_coord"][gn - 1], (0, 2, 1)))
+    no_f = nf[a["p122_fix_node"] - 1, a["p122_fix_sense"] - 1]
+    res = open(os.path.join(golden, "p122_demo.res")).read()
+    assert f"{neq} equations" in res and neq == 3636
+    out, totd = p122_oracle.p122(coord, g_g, neq, phi, c, psi, e, v, qinc, plasits, cjits, plastol, cjtol, no_f=no_f,
+                                 valf=a["p122_fix_val"])
+    gold_d = [float(x) for x in re.findall(r"The displacement is\s+(\S+)", res)]
+    gold_s = [[float(x) for x in m] for m in re.findall(r"sigma y\s*\n\s*(\S+)\s+(\S+)\s+(\S+)", res)]
+    gold_cj = [int(x) for x in re.findall(r"total number of cj iterations was\s+(\d+)", res)]
+    gold_pl = [int(x) for x in re.findall(r"number of plastic iterations was\s+(\d+)", res)]
+    assert len(out) == len(gold_d) == len(gold_s) == len(gold_cj) == len(gold_pl) == 10
+    for o, d, sg, cj, pl in zip(out, gold_d, gold_s, gold_cj, gold_pl):
+        assert (o["cjtot"], o["plasiters"]) == (cj, pl)
+        assert abs(o["disp1"] - d) <= 6e-4 * abs(d)
+        mine = (o["sigma"][2], o["sigma"][0], o["sigma"][1])          # printed as sigma z, sigma x, sigma y
+        assert all(abs(m - g) <= 6e-4 * abs(g) for m, g in zip(mine, sg))
+    field = np.where(nf > 0, totd[np.maximum(nf, 1) - 1], 0.0)
+    gold_f = a["p122_displ_010"].astype(np.float64).reshape(3, nn).T
+    assert np.abs(field - gold_f).max() <= 6e-4 * np.abs(gold_f).max()
