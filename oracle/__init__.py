@@ -84,6 +84,7 @@ def lib():
         L.orc_shape_fun.argtypes = [cint, vp, cint, cint, vp]
         L.orc_form_k_transient.argtypes = [i64, cint, cint, vp, dbl, dbl, dbl, dbl, dbl, dbl, dbl, vp, vp, vp, vp]
         L.orc_apply.argtypes = [cint, i64, vp, vp, i64, cint, vp, vp]
+        L.orc_p122_elements.argtypes = [i64, cint, cint, vp, dbl, dbl, dbl, dbl, dbl, dbl, cint, vp, vp, vp, vp]
         _lib = L
     return _lib
 

@@ -114,8 +114,10 @@ def _checon(new, old, tol):
 
 
 def p122(g_coord_pp, g_g_pp, neq, phi, c, psi, e, v, qinc, plasits, cjits, plastol, cjtol, no_f=None, valf=None, ld0=None,
-         npes=1, penalty=1e20):
-    """-> list of dict(disp1 = totd(1), sigma = tensor(:,1,1), cjtot, plasiters) per load increment, and totd."""
+         npes=1, penalty=1e20, c_elements=True):
+    """-> list of dict(disp1 = totd(1), sigma = tensor(:,1,1), cjtot, plasiters) per load increment, and totd.
+    c_elements: the Gauss-point update through orc_p122_elements (pf_oracle.c: the reference's loop with defined
+    summation orders -- what a device kernel will be held to); False: the vectorised numpy form of the same."""
     g_g = _i32(g_g_pp)
     nels, ntot = g_g.shape
     km = form_km_elastic(g_coord_pp, ntot // 3, 8, e, v)
@@ -178,6 +180,17 @@ def p122(g_coord_pp, g_g_pp, neq, phi, c, psi, e, v, qinc, plasits, cjits, plast
             if last:
                 bdylds = np.zeros(neq)
             eld = np.where(g_g > 0, loads[safe], 0.0)                                 # gather(loads_pp,pmul_pp)
+            if c_elements:
+                bload = np.empty((nels, ntot))
+                coord = _f64(g_coord_pp)
+                eldc = _f64(eld)
+                rc = lib().orc_p122_elements(nels, ntot // 3, nip, _p(coord), e, v, phi, c, psi, dt, int(last), _p(eldc),
+                                             _p(evpt), _p(tensor), _p(bload))
+                assert rc == 0
+                bdylds = bdylds + scatter(g_g, bload, neq, npes)
+                if last:
+                    break
+                continue
             eps = np.einsum("egsc,ec->egs", bee, eld) - evpt
             sigma = eps @ dee.T
             stress = sigma + tensor

@@ -21,6 +21,8 @@
  *
  * Reference files followed (under /root/reference/parafem/src):
  *   programs/5th_ed/p121/p121.f90 (whole), programs/5th_ed/p123/p123.f90 (whole)
+ *   programs/5th_ed/p122/p122.f90:197-231 (orc_p122_elements; the load-increment loop around it is in
+ *   oracle/p122_oracle.py), new_library.f90: formm :85-198, invar :1813-1916, mocouf :2364-2417, mocouq :2423-2490
  *   programs/5th_ed/p124/p124.f90:81-95,139-232, programs/5th_ed/p125/p125.f90:66-99,
  *   programs/dev/xx2/xx2.f90:169-193 (the time loops / material loop are composed from
  *   these C functions in oracle/__init__.py: p124(), p125(), form_km_elastic_mat())
@@ -381,6 +383,138 @@ int orc_centroid_stress(int nod, const double *coord, const double *eld, double 
 /* ------------------------------------------------------------------------- */
 /* steering: rearrange + find_g3, rearrange_2 + find_g4                       */
 /* ------------------------------------------------------------------------- */
+
+
+/* ------------------------------------------------------------------------- */
+/* p122 (elasto-plasticity): the Gauss-point update of elements_4, p122.f90:199-229 */
+/* ------------------------------------------------------------------------- */
+/* invar, nst = 6 (new_library.f90:1893-1912) */
+static void invar6(const double *s, double *sigm, double *dsbar, double *theta) {
+  const double sq3 = sqrt(3.0);
+  *sigm = (s[0] + s[1] + s[2]) / 3.0;
+  const double d2 = ((s[0] - s[1]) * (s[0] - s[1]) + (s[1] - s[2]) * (s[1] - s[2]) + (s[2] - s[0]) * (s[2] - s[0])) / 6.0 +
+                    s[3] * s[3] + s[4] * s[4] + s[5] * s[5];
+  const double ds1 = s[0] - *sigm, ds2 = s[1] - *sigm, ds3 = s[2] - *sigm;
+  const double d3 = ds1 * ds2 * ds3 - ds1 * s[4] * s[4] - ds2 * s[5] * s[5] - ds3 * s[3] * s[3] + 2.0 * s[3] * s[4] * s[5];
+  *dsbar = sq3 * sqrt(d2);
+  if (*dsbar < 1e-10) *theta = 0.0;
+  else {
+    const double r = sqrt(d2);
+    double sine = -3.0 * sq3 * d3 / (2.0 * r * r * r);
+    if (sine > 1.0) sine = 1.0;
+    if (sine < -1.0) sine = -1.0;
+    *theta = asin(sine) / 3.0;
+  }
+}
+/* mocouf (new_library.f90:2364-2417) */
+static double mocouf(double phi, double c, double sigm, double dsbar, double theta) {
+  const double phir = phi * 4.0 * atan(1.0) / 180.0;
+  const double snph = sin(phir), csph = cos(phir), csth = cos(theta), snth = sin(theta);
+  return snph * sigm + dsbar * (csth / sqrt(3.0) - snth * snph / 3.0) - c * csph;
+}
+/* mocouq (new_library.f90:2423-2490) */
+static void mocouq(double psi, double dsbar, double theta, double *dq1, double *dq2, double *dq3) {
+  const double psir = psi * 4.0 * atan(1.0) / 180.0;
+  const double snth = sin(theta), snps = sin(psir), sq3 = sqrt(3.0);
+  *dq1 = snps;
+  if (fabs(snth) > 0.49) {
+    const double c1 = snth < 0.0 ? -1.0 : 1.0;
+    *dq2 = (sq3 * 0.5 - c1 * snps * 0.5 / sq3) * sq3 * 0.5 / dsbar;
+    *dq3 = 0.0;
+  } else {
+    const double csth = cos(theta), cs3th = cos(3.0 * theta), tn3th = tan(3.0 * theta), tnth = snth / csth;
+    *dq2 = sq3 * csth / dsbar * ((1.0 + tnth * tn3th) + snps * (tn3th - tnth) / sq3) * 0.5;
+    *dq3 = 0.5 * 3.0 * (sq3 * snth + snps * csth) / (cs3th * dsbar * dsbar);
+  }
+}
+/* formm, nst = 6 (new_library.f90:145-194); m(i,j) at [j*6+i] */
+static void formm6(const double *st, double *m1, double *m2, double *m3) {
+  const double sx = st[0], sy = st[1], sz = st[2], txy = st[3], tyz = st[4], tzx = st[5];
+  const double sigm = (sx + sy + sz) / 3.0, dx = sx - sigm, dy = sy - sigm, dz = sz - sigm;
+  memset(m1, 0, 36 * sizeof(double)); memset(m2, 0, 36 * sizeof(double)); memset(m3, 0, 36 * sizeof(double));
+#define M(m, i, j) (m)[((j)-1) * 6 + ((i)-1)]
+  for (int i = 1; i <= 3; ++i) for (int j = 1; j <= 3; ++j) M(m1, i, j) = 1.0 / (3.0 * sigm);
+  for (int i = 1; i <= 3; ++i) { M(m2, i, i) = 2.0; M(m2, i + 3, i + 3) = 6.0; }
+  M(m2, 1, 2) = -1.0; M(m2, 1, 3) = -1.0; M(m2, 2, 3) = -1.0;
+  M(m3, 1, 1) = dx; M(m3, 1, 2) = dz; M(m3, 1, 3) = dy; M(m3, 1, 4) = txy; M(m3, 1, 5) = -2.0 * tyz; M(m3, 1, 6) = tzx;
+  M(m3, 2, 2) = dy; M(m3, 2, 3) = dx; M(m3, 2, 4) = txy; M(m3, 2, 5) = tyz; M(m3, 2, 6) = -2.0 * tzx;
+  M(m3, 3, 3) = dz; M(m3, 3, 4) = -2.0 * txy; M(m3, 3, 5) = tyz; M(m3, 3, 6) = tzx;
+  M(m3, 4, 4) = -3.0 * dz; M(m3, 4, 5) = 3.0 * tzx; M(m3, 4, 6) = 3.0 * tyz;
+  M(m3, 5, 5) = -3.0 * dx; M(m3, 5, 6) = 3.0 * txy; M(m3, 6, 6) = -3.0 * dy;
+  for (int i = 1; i <= 6; ++i)
+    for (int j = i + 1; j <= 6; ++j) { M(m1, j, i) = M(m1, i, j); M(m2, j, i) = M(m2, i, j); M(m3, j, i) = M(m3, i, j); }
+  for (int q = 0; q < 36; ++q) { m1[q] = m1[q] / 3.0; m2[q] = m2[q] / 3.0; m3[q] = m3[q] / 3.0; }
+#undef M
+}
+
+/* elements_4 of p122.f90:197-231 over all elements: pmul (ntot,nels) = gathered displacement increment;
+ * evpt, tensor (6,nip,nels) updated in place; utemp (ntot,nels) receives bload.  last = plastic_converged .OR.
+ * plasiters == plasits.  Every MATMUL is the k-ascending sum from 0.0 of the arithmetic contract above. */
+int orc_p122_elements(int64_t nels, int nod, int nip, const double *g_coord_pp, double e, double v, double phi,
+                      double c, double psi, double dt, int last, const double *pmul, double *evpt, double *tensor,
+                      double *utemp) {
+  if ((nod != 8 && nod != 20) || nip != 8) return 1;
+  const int ntot = 3 * nod;
+  double points[24], weights[8], dee[36];
+  orc_sample_hex(nip, points, weights);
+  orc_deemat6(dee, e, v);
+#pragma omp parallel for schedule(static)
+  for (int64_t iel = 0; iel < nels; ++iel) {
+    double der[60], deriv[60], bee[6 * 60], bload[60], eps[6], sigma[6], stress[6], devp[6] = {0}, evp[6], erate[6];
+    double m1[36], m2[36], m3[36], flow[36];
+    const double *eld = pmul + iel * ntot;
+    for (int q = 0; q < ntot; ++q) bload[q] = 0.0;
+    for (int ig = 0; ig < nip; ++ig) {
+      double *ev = evpt + (iel * nip + ig) * 6, *te = tensor + (iel * nip + ig) * 6;
+      const double det = gauss_point(nod, points, nip, ig, g_coord_pp + iel * nod * 3, der, deriv);
+      orc_beemat6(bee, deriv, nod);
+      for (int r = 0; r < 6; ++r) {
+        double s = 0.0;
+        for (int q = 0; q < ntot; ++q) s += bee[q * 6 + r] * eld[q];
+        eps[r] = s - ev[r];
+      }
+      for (int r = 0; r < 6; ++r) {
+        double s = 0.0;
+        for (int q = 0; q < 6; ++q) s += dee[q * 6 + r] * eps[q];
+        sigma[r] = s;
+        stress[r] = s + te[r];
+      }
+      double sigm, dsbar, theta;
+      invar6(stress, &sigm, &dsbar, &theta);
+      const double f = mocouf(phi, c, sigm, dsbar, theta);
+      if (last) {
+        for (int r = 0; r < 6; ++r) devp[r] = stress[r];
+      } else if (f >= 0.0) {
+        double dq1, dq2, dq3;
+        mocouq(psi, dsbar, theta, &dq1, &dq2, &dq3);
+        formm6(stress, m1, m2, m3);
+        for (int q = 0; q < 36; ++q) flow[q] = f * (m1[q] * dq1 + m2[q] * dq2 + m3[q] * dq3);
+        for (int r = 0; r < 6; ++r) {
+          double s = 0.0;
+          for (int q = 0; q < 6; ++q) s += flow[q * 6 + r] * stress[q];
+          erate[r] = s;
+          evp[r] = s * dt;
+          ev[r] = ev[r] + evp[r];
+        }
+        for (int r = 0; r < 6; ++r) {
+          double s = 0.0;
+          for (int q = 0; q < 6; ++q) s += dee[q * 6 + r] * evp[q];
+          devp[r] = s;
+        }
+      }
+      if (f >= 0.0)
+        for (int q = 0; q < ntot; ++q) {
+          double s = 0.0;
+          for (int r = 0; r < 6; ++r) s += bee[q * 6 + r] * devp[r];
+          bload[q] = bload[q] + s * det * weights[ig];
+        }
+      if (last) for (int r = 0; r < 6; ++r) te[r] = stress[r];
+      (void)sigma; (void)erate;
+    }
+    for (int q = 0; q < ntot; ++q) utemp[iel * ntot + q] = bload[q];
+  }
+  return 0;
+}
 
 /* rest(nr,nodof+1) col-major, modified in place (new_library.f90:3059-3112) */
 void orc_rearrange(int64_t nr, int nodof, int32_t *rest) {

@@ -366,7 +366,8 @@ def test_abaqus2sg_tetrahedron():
 
 # ---- p122: elasto-plasticity (oracle only; the device side is the next round's) -------------
 
-def test_p122_demo_log_and_displacements(golden):
+@pytest.mark.parametrize("c_elements", [True, False])
+def test_p122_demo_log_and_displacements(golden, c_elements):
     """examples/5th_ed/p122/demo/p122_demo.res (4 ranks): 3636 equations, ten displacement-controlled load increments
     of a Mohr-Coulomb solid (viscoplastic strain method, PCG restarted from the current x) -- displacement, the three
     stresses of the first Gauss point, the total cj iterations and the plastic iterations of EVERY increment reproduced
@@ -385,8 +386,9 @@ def test_p122_demo_log_and_displacements(golden):
     no_f = nf[a["p122_fix_node"] - 1, a["p122_fix_sense"] - 1]
     res = open(os.path.join(golden, "p122_demo.res")).read()
     assert f"{neq} equations" in res and neq == 3636
+    # c_elements: the Gauss-point update in C with defined summation orders (orc_p122_elements) / vectorised numpy
     out, totd = p122_oracle.p122(coord, g_g, neq, phi, c, psi, e, v, qinc, plasits, cjits, plastol, cjtol, no_f=no_f,
-                                 valf=a["p122_fix_val"])
+                                 valf=a["p122_fix_val"], c_elements=c_elements)
     gold_d = [float(x) for x in re.findall(r"The displacement is\s+(\S+)", res)]
     gold_s = [[float(x) for x in m] for m in re.findall(r"sigma y\s*\n\s*(\S+)\s+(\S+)\s+(\S+)", res)]
     gold_cj = [int(x) for x in re.findall(r"total number of cj iterations was\s+(\d+)", res)]
