@@ -201,6 +201,10 @@ int pf_sum(pf_handle h, const double *a_pp, double *result);
  * (gather of xnew into eld, one shape_der/beemat at the centroid,
  * sigma = dee*bee*eld).  Uses the x of the last solve.                    */
 int pf_centroid_stress(pf_handle h, int64_t iel, double e, double v, double *sigma6);
+/* The same at the local point (xi, eta, zeta) of the element.  The 2013 build of p121 that produced
+ * examples/5th_ed/p121/book/p121.res printed the stress at the LAST Gauss point of the rule,
+ * (-1/sqrt(3), -1/sqrt(3), -1/sqrt(3)), not at the centroid (p121.res:9-10). */
+int pf_point_stress(pf_handle h, int64_t iel, double xi, double eta, double zeta, double e, double v, double *sigma6);
 
 /* --- measurement ---------------------------------------------------------
  * pf_set_profile(1) brackets every launch of the named kernels with CUDA
@@ -219,6 +223,12 @@ int pf_measure_fp64(pf_handle h, double *tflops);
  * MEASURED_PEAKS.json's hbm_gbs is a copy (read + write); this is the read-stream ceiling.     */
 int pf_measure_hbm_read(pf_handle h, double *gbs);
 int pf_device_info(pf_handle h, int *sm_count, int64_t *free_bytes, int64_t *total_bytes);
+/* How the halo exchange of this handle travels: 0 one rank (none), 1 NCCL send/recv + all-gather,
+ * 2 peer memory over NVLink (CUDA IPC mappings; gather_scatter.f90:547-850 replaced either way). */
+int pf_halo_transport(pf_handle h);
+/* Device time (CUDA events on the solver stream) of the iteration loop of the last pf_pcg_run /
+ * pf_pcg_solve: the window of timest(3) in p121.f90:89,107-108. */
+int pf_get_last_solve_ms(pf_handle h, double *ms);
 
 /* ===================================================================== */
 /* B. Host helpers (CPU; restate ParaFEM library routines)                */
@@ -336,6 +346,17 @@ int pf_write_ensi(const char *path, int numvar, int64_t nn, const double *values
 int pf_make_ggl(int ntot, int64_t nels_pp, const int32_t *g_g_pp, int64_t neq,
                 int npes, int numpe, int32_t *ggl_pp, int64_t cap,
                 int32_t *halo_eq, int64_t *halo_cnt, int64_t *nhalo);
+
+/* Tables of the halo exchanges fused into the PCG kernels (peer transport, device.cu).  Forward: which owned
+ * equations peers gather (one bit each in `bits`, the equations ascending in `slot0`, per equation its
+ * destinations rank[ptr[i]..ptr[i+1]) / dst = index in that rank's p_ext) from the put list of pf_setup_mesh
+ * (put_slot grouped by destination rank, put_off[nranks+1]) -- replaces the send side of gather's exchange
+ * (gather_scatter.f90:600-640).  Reverse: the accumulate entries of every reduction chunk -- the receive side of
+ * scatter's exchange (gather_scatter.f90:790-840). */
+int pf_make_put_tables(int nranks, int64_t neq_pp, const int64_t *put_off, const int32_t *put_slot,
+                       const int64_t *fwd_dst_off, uint32_t *bits, int32_t *slot0, uint32_t *ptr, int32_t *rank,
+                       int64_t *dst, int64_t *n_unique);
+int pf_make_acc_chunks(int64_t neq_pp, int chunk, int64_t nacc, const int32_t *acc_slot, uint32_t *chunk_ptr);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,7 @@ def lib():
         L.orc_form_km_elastic.argtypes = [i64, cint, cint, vp, dbl, dbl, vp]
         L.orc_form_kc_laplace.argtypes = [i64, cint, cint, vp, dbl, dbl, dbl, vp]
         L.orc_centroid_stress.argtypes = [cint, vp, vp, dbl, dbl, vp]
+        L.orc_point_stress.argtypes = [cint, vp, vp, dbl, dbl, dbl, dbl, dbl, vp]
         L.orc_gather.argtypes = [cint, i64, vp, vp, vp]
         L.orc_matvec.argtypes = [cint, i64, vp, vp, vp]
         L.orc_scatter.argtypes = [cint, i64, vp, i64, cint, vp, vp]
@@ -85,6 +86,13 @@ def lib():
         L.orc_form_k_transient.argtypes = [i64, cint, cint, vp, dbl, dbl, dbl, dbl, dbl, dbl, dbl, vp, vp, vp, vp]
         L.orc_apply.argtypes = [cint, i64, vp, vp, i64, cint, vp, vp]
         L.orc_p122_elements.argtypes = [i64, cint, cint, vp, dbl, dbl, dbl, dbl, dbl, dbl, cint, vp, vp, vp, vp]
+        L.orc_cube_elements.argtypes = [cint, cint, cint, dbl, dbl, dbl, i64, i64, vp, vp]
+        L.orc_cube_rest.argtypes = [cint, cint, cint, cint, i64, vp]
+        L.orc_cube_rest.restype = i64
+        L.orc_load_p121.argtypes = [cint, cint, cint, dbl, dbl, vp, vp]
+        L.orc_load_p121.restype = i64
+        L.orc_find_g_all.argtypes = [cint, cint, i64, vp, vp, i64, vp]
+        L.orc_find_g_all.restype = None
         _lib = L
     return _lib
 
@@ -117,6 +125,116 @@ def set_element_partition(counts=None):
 
 def max_threads():
     return lib().orc_max_threads()
+
+
+def host_cores():
+    """The cores this process may run on -- NOT the launcher's OMP_NUM_THREADS (torchrun sets it to 1)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def use_all_cores():
+    n = host_cores()
+    set_threads(n)
+    return n
+
+
+def _round_sig(a, digits):
+    """What a value becomes after a trip through a Fortran Ew.d field (d significant digits)."""
+    u, inv = np.unique(a, return_inverse=True)
+    r = np.array([float(f"{x:.{digits - 1}e}") for x in u])
+    return r[inv].reshape(a.shape)
+
+
+class Mesh:
+    """What p121 / p123 hold after read_* + rearrange + find_g (global arrays, one rank)."""
+
+
+def cube_p121(nxe, nye, nze, nod=20, aa=None, bb=None, cc=None, e=100.0, v=0.3, tol=1e-5, limit=2000, nip=8,
+              deck_rounding=False):
+    """p12meshgen's p121 cube (p12meshgen.f90:118-236) followed by p121.f90:30-45,79-84: connectivity,
+    element coordinates, restraints -> steering array, loads -> starting residual.  Built from the oracle's
+    own restatement of geometry_*bxz / cube_bc* / load_p121 / rearrange / find_g3 -- independent of the
+    product's host library.  ``deck_rounding``: coordinates through E14.6 and loads through E16.8, as
+    when the mesh travels through the deck files."""
+    aa = 10.0 / nxe if aa is None else aa
+    bb = 10.0 / nye if bb is None else bb
+    cc = 10.0 / nze if cc is None else cc
+    L = lib()
+    nels = nxe * nye * nze
+    if nod == 20:
+        nr = (((2 * nxe + 1) * (nze + 1) + (nxe + 1) * nze) * 2 + ((2 * nye - 1) * nze + (nye - 1) * nze) * 2
+              + (2 * nye - 1) * (nxe + 1) + (nye - 1) * nxe)
+        nn = ((2 * nxe + 1) * (nze + 1) + (nxe + 1) * nze) * (nye + 1) + (nxe + 1) * (nze + 1) * nye
+    else:
+        nr = (nxe + 1) * (nze + 1) * 2 + (nye - 1) * (nze + 1) * 2 + (nxe - 1) * (nze - 1)
+        nn = (nxe + 1) * (nye + 1) * (nze + 1)
+    m = Mesh()
+    m.program, m.nod, m.nodof, m.nip, m.nels, m.nn, m.nr = 121, nod, 3, nip, nels, nn, nr
+    m.e, m.v, m.tol, m.limit = e, v, tol, limit
+    m.g_num_pp = np.empty((nels, nod), np.int32)
+    m.g_coord_pp = np.empty((nels, 3, nod))
+    assert L.orc_cube_elements(nod, nxe, nze, aa, bb, cc, 0, nels, _p(m.g_num_pp), _p(m.g_coord_pp)) == 0
+    if deck_rounding:
+        m.g_coord_pp = _round_sig(m.g_coord_pp, 6)
+    # nod = 8: p12meshgen.f90:178's nr equals the rows cube_bc8 emits only on nxe == nye == nze boxes; the
+    # rows cube_bc8 emits are what a deck can hold, so they are counted (first call writes nothing)
+    emitted = L.orc_cube_rest(nod, nxe, nye, nze, 0, None)
+    assert emitted == nr or (nod == 8 and not nxe == nye == nze), (emitted, nr)
+    m.nr = nr = emitted
+    rest = np.zeros((4, nr), np.int32)
+    assert L.orc_cube_rest(nod, nxe, nye, nze, nr, _p(rest)) == nr
+    m.rest = rest.copy()
+    L.orc_rearrange(nr, 3, _p(rest))
+    m.g_g_pp = np.zeros((nels, 3 * nod), np.int32)
+    L.orc_find_g_all(nod, 3, nels, _p(m.g_num_pp), _p(m.g_g_pp), nr, _p(rest))
+    m.neq = int(m.g_g_pp.max())
+    loaded = L.orc_load_p121(nod, nxe, nze, aa, bb, None, None)
+    node = np.empty(loaded, np.int32)
+    val = np.empty(loaded)
+    assert L.orc_load_p121(nod, nxe, nze, aa, bb, _p(node), _p(val)) == loaded
+    if deck_rounding:
+        val = _round_sig(val, 8)
+    # load() + scatter_noadd (loading.f90:60-140): the z-load of every loaded node lands on its equation
+    nf_z = np.zeros(nn + 1, np.int32)
+    nf_z[m.g_num_pp.ravel()] = m.g_g_pp.reshape(nels, nod, 3)[:, :, 2].ravel()
+    m.r_pp = np.zeros(m.neq)
+    eq = nf_z[node]
+    m.r_pp[eq[eq > 0] - 1] = val[eq > 0]
+    m.loaded_nodes, m.load_node, m.load_val = loaded, node, val
+    m.total_load = float(val.sum())
+    return m
+
+
+def cube_p123(nxe, nye, nze, aa=None, bb=None, cc=None, kx=2.0, ky=2.0, kz=2.0, tol=1e-5, limit=500, nip=8,
+              source=10.0):
+    """p12meshgen's p123 box (p12meshgen.f90:658-701) followed by p123.f90's rearrange_2 / find_g4 and the
+    loaded freedom nres (used directly as an equation number, p123.f90:111-116)."""
+    aa = 1.0 / nxe if aa is None else aa
+    bb = 1.0 / nye if bb is None else bb
+    cc = 1.0 / nze if cc is None else cc
+    L = lib()
+    nels = nxe * nye * nze
+    nr = (nxe + 1) * (nye + 1) + (nxe + 1) * nze + nye * nze
+    nn = (nxe + 1) * (nye + 1) * (nze + 1)
+    m = Mesh()
+    m.program, m.nod, m.nodof, m.nip, m.nels, m.nn, m.nr = 123, 8, 1, nip, nels, nn, nr
+    m.kx, m.ky, m.kz, m.tol, m.limit, m.nres = kx, ky, kz, tol, limit, nxe * (nze - 1) + 1
+    m.g_num_pp = np.empty((nels, 8), np.int32)
+    m.g_coord_pp = np.empty((nels, 3, 8))
+    assert L.orc_cube_elements(8, nxe, nze, aa, bb, cc, 0, nels, _p(m.g_num_pp), _p(m.g_coord_pp)) == 0
+    rest = np.zeros((2, nr), np.int32)
+    assert L.orc_cube_rest(1, nxe, nye, nze, nr, _p(rest)) == nr
+    L.orc_rearrange_2(nr, _p(rest))
+    m.g_g_pp = np.zeros((nels, 8), np.int32)
+    L.orc_find_g_all(8, 1, nels, _p(m.g_num_pp), _p(m.g_g_pp), nr, _p(rest))
+    m.neq = int(m.g_g_pp.max())
+    m.r_pp = np.zeros(m.neq)
+    m.r_pp[m.nres - 1] = source
+    m.total_load = source
+    return m
 
 
 def form_km_elastic(g_coord_pp, nod, nip, e, v):
@@ -152,6 +270,13 @@ def form_kc_laplace(g_coord_pp, nip, kx, ky, kz):
 def centroid_stress(nod, coord, eld, e, v):
     sig = np.empty(6)
     rc = lib().orc_centroid_stress(nod, _p(_f64(coord)), _p(_f64(eld)), e, v, _p(sig))
+    assert rc == 0
+    return sig
+
+
+def point_stress(nod, coord, eld, e, v, xi, eta, zeta):
+    sig = np.empty(6)
+    rc = lib().orc_point_stress(nod, _p(_f64(coord)), _p(_f64(eld)), e, v, xi, eta, zeta, _p(sig))
     assert rc == 0
     return sig
 

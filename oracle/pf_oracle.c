@@ -357,11 +357,19 @@ int orc_form_k_transient(int64_t nels, int nod, int nip, const double *g_coord_p
 }
 
 /* centroid stresses, p121.f90:113-123: one point at (0,0,0); sigma = dee*(bee*eld) */
+int orc_point_stress(int nod, const double *coord, const double *eld, double e, double v, double xi, double eta,
+                     double zeta, double *sigma);
 int orc_centroid_stress(int nod, const double *coord, const double *eld, double e, double v,
                         double *sigma) {
+  return orc_point_stress(nod, coord, eld, e, v, 0.0, 0.0, 0.0, sigma);
+}
+/* the same at any local point: the 2013 build of p121 behind examples/5th_ed/p121/book/p121.res printed the
+ * stress at the last point of the 8-point rule, not at the centroid */
+int orc_point_stress(int nod, const double *coord, const double *eld, double e, double v, double xi, double eta,
+                     double zeta, double *sigma) {
   if (nod != 4 && nod != 8 && nod != 20) return 1;
   const int ntot = 3 * nod;
-  double points[3] = {0, 0, 0}, der[60], deriv[60], dee[36], eps[6];
+  double points[3] = {xi, eta, zeta}, der[60], deriv[60], dee[36], eps[6];
   double *bee = malloc(sizeof(double) * 6 * ntot);
   gauss_point(nod, points, 1, 0, coord, der, deriv);
   orc_beemat6(bee, deriv, nod);
@@ -563,6 +571,16 @@ void orc_find_g3(int nod, int nodof, const int32_t *num, int32_t *g, int64_t nr,
   }
 }
 
+/* elements_0 of p121.f90:43-45 / p123.f90: find_g3 (nodof 3) or find_g4 (nodof 1) over n elements */
+void orc_find_g4(int nod, const int32_t *num, int32_t *g, int64_t nr, const int32_t *rest);
+void orc_find_g_all(int nod, int nodof, int64_t n, const int32_t *g_num, int32_t *g_g, int64_t nr, const int32_t *rest) {
+#pragma omp parallel for schedule(static)
+  for (int64_t e = 0; e < n; ++e) {
+    if (nodof == 1) orc_find_g4(nod, g_num + e * nod, g_g + e * nod, nr, rest);
+    else orc_find_g3(nod, nodof, g_num + e * nod, g_g + e * nod * nodof, nr, rest);
+  }
+}
+
 /* rearrange_2 (new_library.f90:3118-3124); rest(nr,2) */
 void orc_rearrange_2(int64_t nr, int32_t *rest) {
   int64_t m = 0;
@@ -584,6 +602,166 @@ void orc_find_g4(int nod, const int32_t *num, int32_t *g, int64_t nr, const int3
   }
 }
 #undef REST
+
+/* ------------------------------------------------------------------------- */
+/* p12meshgen cubes (tools/preprocessing/p12meshgen/p12meshgen.f90) -- the mesh  */
+/* of the reference arm of bench.py and of the full-size parity tests, built     */
+/* without the product's library.  In-memory (full precision), S&G node order:   */
+/* what p121 / p123 hold after read_g_num_pp + abaqus2sg + read_g_coord_pp when  */
+/* the deck's E14.6 rounding is left out.                                        */
+/* ------------------------------------------------------------------------- */
+
+/* geometry_8bxz (geometry.f90:118-166) / geometry_20bxz (:230-289) for elements iel0+1 .. iel0+n:
+ * g_num(nod,n) and g_coord_pp(nod,3,n) -- coord(m,b) of element e at [e*3*nod + b*nod + m] */
+int orc_cube_elements(int nod, int nxe, int nze, double aa, double bb, double cc, int64_t iel0, int64_t n,
+                      int32_t *g_num, double *g_coord_pp) {
+  if (nod != 8 && nod != 20) return 1;
+#pragma omp parallel for schedule(static)
+  for (int64_t q = 0; q < n; ++q) {
+    const int64_t iel = iel0 + q + 1;
+    const int64_t iq = (iel - 1) / ((int64_t)nxe * nze) + 1;
+    const int64_t iplane = iel - (iq - 1) * (int64_t)nxe * nze;
+    const int64_t is = (iplane - 1) / nxe + 1;
+    const int64_t ip = iplane - (is - 1) * nxe;
+    int64_t num[21];
+    double x[21], y[21], z[21];
+    if (nod == 8) {
+      num[1] = (iq - 1) * (int64_t)(nxe + 1) * (nze + 1) + is * (nxe + 1) + ip;
+      num[2] = num[1] - nxe - 1; num[3] = num[2] + 1; num[4] = num[1] + 1;
+      num[5] = num[1] + (int64_t)(nxe + 1) * (nze + 1);
+      num[6] = num[5] - nxe - 1; num[7] = num[6] + 1; num[8] = num[5] + 1;
+      const double x0 = (double)(ip - 1) * aa, x1 = (double)ip * aa;
+      const double y0 = (double)(iq - 1) * bb, y1 = (double)iq * bb;
+      const double z0 = (double)(-is) * cc, z1 = (double)(-(is - 1)) * cc;
+      x[1] = x[2] = x[5] = x[6] = x0; x[3] = x[4] = x[7] = x[8] = x1;
+      y[1] = y[2] = y[3] = y[4] = y0; y[5] = y[6] = y[7] = y[8] = y1;
+      z[1] = z[4] = z[5] = z[8] = z0; z[2] = z[3] = z[6] = z[7] = z1;
+    } else {
+      const int64_t plane = (int64_t)(2 * nxe + 1) * (nze + 1) + (int64_t)(2 * nze + 1) * (nxe + 1);
+      const int64_t fac1 = plane * (iq - 1), fac2 = plane * iq;
+      num[1] = fac1 + (3 * nxe + 2) * is + 2 * ip - 1;
+      num[2] = fac1 + (3 * nxe + 2) * is - nxe + ip - 1;
+      num[3] = num[1] - 3 * nxe - 2; num[4] = num[3] + 1; num[5] = num[4] + 1; num[6] = num[2] + 1;
+      num[7] = num[1] + 2; num[8] = num[1] + 1;
+      num[9] = fac2 - (int64_t)(nxe + 1) * (nze + 1) + (nxe + 1) * is + ip;
+      num[10] = num[9] - nxe - 1; num[11] = num[10] + 1; num[12] = num[9] + 1;
+      num[13] = fac2 + (3 * nxe + 2) * is + 2 * ip - 1;
+      num[14] = fac2 + (3 * nxe + 2) * is - nxe + ip - 1;
+      num[15] = num[13] - 3 * nxe - 2; num[16] = num[15] + 1; num[17] = num[16] + 1; num[18] = num[14] + 1;
+      num[19] = num[13] + 2; num[20] = num[13] + 1;
+      const double x0 = (double)(ip - 1) * aa, x1 = (double)ip * aa;
+      x[1] = x[2] = x[3] = x[9] = x[10] = x[13] = x[14] = x[15] = x0;
+      x[5] = x[6] = x[7] = x[11] = x[12] = x[17] = x[18] = x[19] = x1;
+      x[4] = .5 * (x[3] + x[5]); x[8] = .5 * (x[1] + x[7]); x[16] = .5 * (x[15] + x[17]); x[20] = .5 * (x[13] + x[19]);
+      const double y0 = (double)(iq - 1) * bb, y1 = (double)iq * bb;
+      for (int m = 1; m <= 8; ++m) y[m] = y0;
+      for (int m = 13; m <= 20; ++m) y[m] = y1;
+      y[9] = .5 * (y[1] + y[13]); y[10] = .5 * (y[3] + y[15]); y[11] = .5 * (y[5] + y[17]); y[12] = .5 * (y[7] + y[19]);
+      const double z0 = (double)(-is) * cc, z1 = (double)(-(is - 1)) * cc;
+      z[1] = z[7] = z[8] = z[9] = z[12] = z[13] = z[19] = z[20] = z0;
+      z[3] = z[4] = z[5] = z[10] = z[11] = z[15] = z[16] = z[17] = z1;
+      z[2] = .5 * (z[1] + z[3]); z[6] = .5 * (z[5] + z[7]); z[14] = .5 * (z[13] + z[15]); z[18] = .5 * (z[17] + z[19]);
+    }
+    for (int m = 1; m <= nod; ++m) {
+      g_num[q * nod + m - 1] = (int32_t)num[m];
+      g_coord_pp[q * 3 * nod + m - 1] = x[m];
+      g_coord_pp[q * 3 * nod + nod + m - 1] = y[m];
+      g_coord_pp[q * 3 * nod + 2 * nod + m - 1] = z[m];
+    }
+  }
+  return 0;
+}
+
+/* cube_bc20 (geometry.f90:445-498), cube_bc8 (:609-647), box_bc8 (:664-694): rest(nr,nodof+1) col-major,
+ * kind 20 / 8 (nodof 3) or 1 (box_bc8, nodof 1).  Returns the number of rows written (= nr of p12meshgen). */
+int64_t orc_cube_rest(int kind, int nxe, int nye, int nze, int64_t nr, int32_t *rest) {
+  const int nodof = kind == 1 ? 1 : 3;
+  int64_t count = 0;
+#define PUT(node, a, b, c) do { if (count < nr) { rest[count] = (int32_t)(node); rest[nr + count] = (a); \
+      if (nodof == 3) { rest[2 * nr + count] = (b); rest[3 * nr + count] = (c); } } ++count; } while (0)
+  if (kind == 1) {
+    const int64_t face = (int64_t)(nxe + 1) * (nze + 1);
+    for (int64_t i = 0; i <= nye - 1; ++i)
+      for (int64_t j = i * face + 1; j <= (i + 1) * face; ++j)
+        if (j / (nxe + 1) * (nxe + 1) == j || j < i * face + nxe + 1) PUT(j, 0, 0, 0);
+    for (int64_t j = nye * face + 1; j <= (nye + 1) * face; ++j) PUT(j, 0, 0, 0);
+    return count;
+  }
+  int64_t face1, face2, l, m, n;
+  if (kind == 20) {
+    face1 = 3LL * nxe * nze + 2 * (nxe + nze) + 1; face2 = (int64_t)(nxe + 1) * (nze + 1);
+    l = (int64_t)nze * (nxe + 1); m = 3 * nxe + 2; n = 3LL * nxe * nze + 2 * nze;
+  } else {
+    face1 = (int64_t)(nxe + 1) * (nze + 1); face2 = 0;
+    l = 0; m = 2 * nxe + 2; n = (int64_t)(nxe + 1) * nze;
+  }
+  const int64_t face = face1 + face2;
+  for (int64_t i = 0; i <= nye; ++i) {
+    for (int64_t j = i * face + 1; j <= i * face + face1; ++j) {
+      const int64_t k = j - i * face;
+      const int edge = k <= n && ((k + m - 1) / m * m == (k + m - 1) || (k + nxe + 1) / m * m == (k + nxe + 1) ||
+                                  (k + nxe) / m * m == (k + nxe) || k / m * m == k);
+      if (i == 0 || i == nye) {
+        if (edge) PUT(j, 0, 0, 1);
+        else if (k <= n) PUT(j, 1, 0, 1);
+        else PUT(j, 0, 0, 0);
+      } else {
+        if (edge) PUT(j, 0, 1, 1);
+        else if (k > n) PUT(j, 0, 0, 0);
+      }
+    }
+    if (kind == 20 && i < nye)
+      for (int64_t j = i * face + face1 + 1; j <= (i + 1) * face; ++j) {
+        const int64_t k = j - (face1 + i * face);
+        if (k <= l && ((k + nxe) / (nxe + 1) * (nxe + 1) == (k + nxe) || k / (nxe + 1) * (nxe + 1) == k)) PUT(j, 0, 1, 1);
+        else if (k > l) PUT(j, 0, 0, 0);
+      }
+  }
+#undef PUT
+  return count;
+}
+
+/* load_p121 (loading.f90:386-546) followed by p12meshgen's scaling (p12meshgen.f90:167-168, 210-211):
+ * node[loaded], val[loaded] = the z-load of every loaded node; returns loaded (call with node == NULL for the count) */
+int64_t orc_load_p121(int nod, int nxe, int nze, double aa, double bb, int32_t *node, double *val) {
+  const int nle = nxe / 5;
+  const int64_t loaded = nod == 20 ? 3LL * nle * nle + 4 * nle + 1 : (int64_t)(nle + 1) * (nle + 1);
+  if (!node) return loaded;
+  int64_t c = 0;
+  if (nod == 20) {
+    const int64_t f1 = (int64_t)(2 * nxe + 1) * (nze + 1) + (int64_t)(nxe + 1) * nze, f2 = (int64_t)(nxe + 1) * (nze + 1);
+    for (int i = 1; i <= 2 * nle + 1; ++i, ++c) {
+      node[c] = i;
+      val[c] = (i == 1 || i == 2 * nle + 1) ? -1.0 : (i % 2 == 0 ? 4.0 : -2.0);
+    }
+    for (int j = 0; j <= nle - 1; ++j) {
+      for (int i = 1; i <= nle + 1; ++i, ++c) {
+        node[c] = (int32_t)(i + f1 + j * (f1 + f2));
+        val[c] = (i == 1 || i == nle + 1) ? 4.0 : 8.0;
+      }
+      for (int i = 1; i <= 2 * nle + 1; ++i, ++c) {
+        node[c] = (int32_t)(i + f1 + (j + 1) * f2 + j * f1);
+        if (j != nle - 1) val[c] = (i == 1 || i == 2 * nle + 1) ? -2.0 : (i % 2 == 0 ? 8.0 : -4.0);
+        else val[c] = (i == 1 || i == 2 * nle + 1) ? -1.0 : (i % 2 == 0 ? 4.0 : -2.0);
+      }
+    }
+    for (int64_t i = 0; i < c; ++i) val[i] = -val[i] * aa * bb * (25.0 / 12.0);
+  } else {
+    const int64_t f1 = (int64_t)(nxe + 1) * (nze + 1);
+    for (int i = 1; i <= nle + 1; ++i, ++c) {
+      node[c] = i;
+      val[c] = (i == 1 || i == nle + 1) ? -6.25 : -12.5;
+    }
+    for (int j = 0; j <= nle - 1; ++j)
+      for (int i = 1; i <= nle + 1; ++i, ++c) {
+        node[c] = (int32_t)(i + (j + 1) * f1);
+        if (j != nle - 1) val[c] = (i == 1 || i == nle + 1) ? -12.5 : -25.0;
+        else val[c] = (i == 1 || i == nle + 1) ? -6.25 : -12.5;
+      }
+    for (int64_t i = 0; i < c; ++i) val[i] = val[i] * aa * bb;
+  }
+  return c == loaded ? loaded : -1;
+}
 
 /* ------------------------------------------------------------------------- */
 /* partition (calc_nels_pp / calc_neq_pp, gather_scatter.f90:217-238,319-339) */
@@ -876,6 +1054,20 @@ static double dot_seq(const double *a, const double *b, int64_t n) {
 /* dot_product_p over emulated ranks: local dot, then ranks ascending */
 double orc_dot_ranks(const double *a, const double *b, int64_t neq, int npes, int red_mode) {
   double s = 0.0;
+  if (!red_mode && npes > 1) {
+    /* every emulated rank forms its local DOT_PRODUCT at the same time (as the MPI ranks do); the partials
+     * are then added in rank order: the same bits as the serial loop below */
+    double *part = malloc(sizeof(double) * (size_t)npes);
+#pragma omp parallel for schedule(static, 1)
+    for (int r = 0; r < npes; ++r) {
+      int64_t c, st;
+      orc_partition(neq, npes, r + 1, &c, &st);
+      part[r] = dot_seq(a + st - 1, b + st - 1, c);
+    }
+    for (int r = 0; r < npes; ++r) s = (r == 0) ? part[r] : s + part[r];
+    free(part);
+    return s;
+  }
   for (int r = 0; r < npes; ++r) {
     int64_t c, st;
     orc_partition(neq, npes, r + 1, &c, &st);

@@ -73,6 +73,9 @@ SIGNATURES = {
     "pf_norm": (c_int, [vp, vp, P(c_dbl)]),
     "pf_sum": (c_int, [vp, vp, P(c_dbl)]),
     "pf_centroid_stress": (c_int, [vp, c_i64, c_dbl, c_dbl, vp]),
+    "pf_point_stress": (c_int, [vp, c_i64, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, vp]),
+    "pf_halo_transport": (c_int, [vp]),
+    "pf_get_last_solve_ms": (c_int, [vp, P(c_dbl)]),
     "pf_set_profile": (c_int, [vp, c_int]),
     "pf_reset_profile": (c_int, [vp]),
     "pf_get_kernel_ms": (c_int, [vp, c_int, P(c_dbl), P(c_i64)]),
@@ -108,6 +111,8 @@ SIGNATURES = {
     "pf_nodal_values": (c_int, [c_int, c_i64, vp, c_i64, c_i64, vp, c_i64, c_i64, vp]),
     "pf_write_ensi": (c_int, [C.c_char_p, c_int, c_i64, vp, c_int]),
     "pf_make_ggl": (c_int, [c_int, c_i64, vp, c_i64, c_int, c_int, vp, c_i64, vp, vp, P(c_i64)]),
+    "pf_make_put_tables": (c_int, [c_int, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, P(c_i64)]),
+    "pf_make_acc_chunks": (c_int, [c_i64, c_int, c_i64, vp, vp]),
 }
 
 # the reference's existing CUDA boundary (include/parafem_xx3_compat.h = xx3.f90:56-148): scalars by reference

@@ -53,6 +53,10 @@ struct Nccl {
 template <class T>
 struct DevBuf {
   T *p = nullptr; size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }          // temporaries are freed on every return path (CU / NC / NEED return early)
   cudaError_t alloc(size_t count) {
     release(); n = count;
     return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
@@ -97,6 +101,15 @@ struct pf_ctx {
   DevBuf<int> acc_slot;
   DevBuf<unsigned int> acc_ptr, acc_pos;
 
+  // fused exchanges of the peer transport: forward puts from k_pupdate (owned equations wanted by peers),
+  // reverse accumulation inside k_dot (accumulate entries per reduction chunk)
+  DevBuf<unsigned int> put_bits, pk_ptr, acc_chunk_ptr;
+  DevBuf<int> pk_slot0, pk_rank;
+  DevBuf<long long> pk_dst;
+  int npk = 0;
+  State *snap_pinned = nullptr;         // two pinned snapshots of the device state (double-buffered polling)
+  cudaEvent_t snap_ev[2] = {nullptr, nullptr};
+
   // peer-memory collectives (CUDA IPC mappings of the peers' p_ext / receive buffer / sync block)
   bool peer_ok = false, use_peer = true, ptab_valid = false;
   DevBuf<PeerSync> sync;
@@ -109,6 +122,7 @@ struct pf_ctx {
   DevBuf<State> state;
   DevBuf<double> ratio_hist;
   int ratio_cap = 0, last_iters = 0;
+  double last_ms = 0.0;   // device time of the last pf_pcg_run loop (CUDA events on the solver stream)
 
   // p123 fixed freedoms
   int nfixed = 0;
@@ -188,6 +202,59 @@ int grid_for(pf_handle h, int64_t n, int threads, int per_sm = 8) {
   return (int)std::max<int64_t>(1, std::min(blocks, cap));
 }
 
+// shape_der at one local point (new_library.f90:745-794, :865-896); D[a*20+m] = der(a,m); fun (8-node brick only,
+// shape_fun :397-422) may be null
+int shape_der_at(int nod, double xi, double eta, double zeta, double *D, double *fun8) {
+  for (int q = 0; q < 60; ++q) D[q] = 0.0;
+  if (nod == 4) {        // shape_der, 3-D nod = 4 (new_library.f90:757-767): constant
+    D[0] = 1.0; D[20 + 1] = 1.0; D[40 + 2] = 1.0;
+    D[3] = -1.0; D[20 + 3] = -1.0; D[40 + 3] = -1.0;
+  } else if (nod == 8) {
+    const double em = 1.0 - eta, xm = 1.0 - xi, zm = 1.0 - zeta, ep = eta + 1.0, xp = xi + 1.0, zp = zeta + 1.0;
+    const double dx[8] = {-0.125 * em * zm, -0.125 * em * zp, 0.125 * em * zp, 0.125 * em * zm,
+                          -0.125 * ep * zm, -0.125 * ep * zp, 0.125 * ep * zp, 0.125 * ep * zm};
+    const double dy[8] = {-0.125 * xm * zm, -0.125 * xm * zp, -0.125 * xp * zp, -0.125 * xp * zm,
+                          0.125 * xm * zm, 0.125 * xm * zp, 0.125 * xp * zp, 0.125 * xp * zm};
+    const double dz[8] = {-0.125 * xm * em, 0.125 * xm * em, 0.125 * xp * em, -0.125 * xp * em,
+                          -0.125 * xm * ep, 0.125 * xm * ep, 0.125 * xp * ep, -0.125 * xp * ep};
+    for (int m = 0; m < 8; ++m) { D[m] = dx[m]; D[20 + m] = dy[m]; D[40 + m] = dz[m]; }
+    if (fun8) {
+      const double fn[8] = {0.125 * xm * em * zm, 0.125 * xm * em * zp, 0.125 * xp * em * zp, 0.125 * xp * em * zm,
+                            0.125 * xm * ep * zm, 0.125 * xm * ep * zp, 0.125 * xp * ep * zp, 0.125 * xp * ep * zm};
+      for (int m = 0; m < 8; ++m) fun8[m] = fn[m];
+    }
+  } else if (nod == 20) {
+    // corner / mid-edge classes of the 20-node brick in S&G order
+    const int sx[20] = {-1, -1, -1, 0, 1, 1, 1, 0, -1, -1, 1, 1, -1, -1, -1, 0, 1, 1, 1, 0};
+    const int sy[20] = {-1, -1, -1, -1, -1, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1};
+    const int sz[20] = {-1, 0, 1, 1, 1, 0, -1, -1, -1, 1, 1, -1, -1, 0, 1, 1, 1, 0, -1, -1};
+    for (int m = 0; m < 20; ++m) {
+      const double a = sx[m], b = sy[m], c = sz[m];
+      const double x0 = xi * a, e0 = eta * b, z0 = zeta * c;
+      double gx, gy, gz;
+      if (sx[m] == 0) {         // mid-edge along xi
+        gx = -.5 * xi * (1. + e0) * (1. + z0);
+        gy = .25 * b * (1. - xi * xi) * (1. + z0);
+        gz = .25 * c * (1. - xi * xi) * (1. + e0);
+      } else if (sy[m] == 0) {  // mid-edge along eta
+        gx = .25 * a * (1. - eta * eta) * (1. + z0);
+        gy = -.5 * eta * (1. + x0) * (1. + z0);
+        gz = .25 * c * (1. + x0) * (1. - eta * eta);
+      } else if (sz[m] == 0) {  // mid-edge along zeta
+        gx = .25 * a * (1. + e0) * (1. - zeta * zeta);
+        gy = .25 * b * (1. + x0) * (1. - zeta * zeta);
+        gz = -.5 * zeta * (1. + x0) * (1. + e0);
+      } else {                  // corner
+        gx = .125 * a * (1. + e0) * (1. + z0) * (2. * x0 + e0 + z0 - 1.);
+        gy = .125 * b * (1. + x0) * (1. + z0) * (x0 + 2. * e0 + z0 - 1.);
+        gz = .125 * c * (1. + x0) * (1. + e0) * (x0 + e0 + 2. * z0 - 1.);
+      }
+      D[m] = gx; D[20 + m] = gy; D[40 + m] = gz;
+    }
+  } else return 2;
+  return 0;
+}
+
 // ---- host restatement of the element tables (product code; the oracle has its own) ----
 // sample('hexahedron') new_library.f90:1397-1433; shape_der :745-794, :865-896; deemat :1671-1686
 int fill_tables(int nod, int nip, double e, double v, double kx, double ky, double kz, ElemTables &T) {
@@ -207,55 +274,8 @@ int fill_tables(int nod, int nip, double e, double v, double kx, double ky, doub
     }
   } else return 1;
   T.nip = nip;
-  for (int ig = 0; ig < nip; ++ig) {
-    const double xi = pts[ig][0], eta = pts[ig][1], zeta = pts[ig][2];
-    double *D = T.der + ig * 60;  // D[a*20+m]
-    if (nod == 4) {        // shape_der, 3-D nod = 4 (new_library.f90:757-767): constant
-      D[0] = 1.0; D[20 + 1] = 1.0; D[40 + 2] = 1.0;
-      D[3] = -1.0; D[20 + 3] = -1.0; D[40 + 3] = -1.0;
-    } else if (nod == 8) {
-      const double em = 1.0 - eta, xm = 1.0 - xi, zm = 1.0 - zeta, ep = eta + 1.0, xp = xi + 1.0, zp = zeta + 1.0;
-      const double dx[8] = {-0.125 * em * zm, -0.125 * em * zp, 0.125 * em * zp, 0.125 * em * zm,
-                            -0.125 * ep * zm, -0.125 * ep * zp, 0.125 * ep * zp, 0.125 * ep * zm};
-      const double dy[8] = {-0.125 * xm * zm, -0.125 * xm * zp, -0.125 * xp * zp, -0.125 * xp * zm,
-                            0.125 * xm * zm, 0.125 * xm * zp, 0.125 * xp * zp, 0.125 * xp * zm};
-      const double dz[8] = {-0.125 * xm * em, 0.125 * xm * em, 0.125 * xp * em, -0.125 * xp * em,
-                            -0.125 * xm * ep, 0.125 * xm * ep, 0.125 * xp * ep, -0.125 * xp * ep};
-      for (int m = 0; m < 8; ++m) { D[m] = dx[m]; D[20 + m] = dy[m]; D[40 + m] = dz[m]; }
-      // shape_fun, 3-D nod = 8 (new_library.f90:397-422)
-      const double fn[8] = {0.125 * xm * em * zm, 0.125 * xm * em * zp, 0.125 * xp * em * zp, 0.125 * xp * em * zm,
-                            0.125 * xm * ep * zm, 0.125 * xm * ep * zp, 0.125 * xp * ep * zp, 0.125 * xp * ep * zm};
-      for (int m = 0; m < 8; ++m) T.fun[ig * 8 + m] = fn[m];
-    } else if (nod == 20) {
-      // corner / mid-edge classes of the 20-node brick in S&G order
-      const int sx[20] = {-1, -1, -1, 0, 1, 1, 1, 0, -1, -1, 1, 1, -1, -1, -1, 0, 1, 1, 1, 0};
-      const int sy[20] = {-1, -1, -1, -1, -1, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1};
-      const int sz[20] = {-1, 0, 1, 1, 1, 0, -1, -1, -1, 1, 1, -1, -1, 0, 1, 1, 1, 0, -1, -1};
-      for (int m = 0; m < 20; ++m) {
-        const double a = sx[m], b = sy[m], c = sz[m];
-        const double x0 = xi * a, e0 = eta * b, z0 = zeta * c;
-        double gx, gy, gz;
-        if (sx[m] == 0) {         // mid-edge along xi
-          gx = -.5 * xi * (1. + e0) * (1. + z0);
-          gy = .25 * b * (1. - xi * xi) * (1. + z0);
-          gz = .25 * c * (1. - xi * xi) * (1. + e0);
-        } else if (sy[m] == 0) {  // mid-edge along eta
-          gx = .25 * a * (1. - eta * eta) * (1. + z0);
-          gy = -.5 * eta * (1. + x0) * (1. + z0);
-          gz = .25 * c * (1. + x0) * (1. - eta * eta);
-        } else if (sz[m] == 0) {  // mid-edge along zeta
-          gx = .25 * a * (1. + e0) * (1. - zeta * zeta);
-          gy = .25 * b * (1. + x0) * (1. - zeta * zeta);
-          gz = -.5 * zeta * (1. + x0) * (1. + e0);
-        } else {                  // corner
-          gx = .125 * a * (1. + e0) * (1. + z0) * (2. * x0 + e0 + z0 - 1.);
-          gy = .125 * b * (1. + x0) * (1. + z0) * (x0 + 2. * e0 + z0 - 1.);
-          gz = .125 * c * (1. + x0) * (1. + e0) * (x0 + e0 + 2. * z0 - 1.);
-        }
-        D[m] = gx; D[20 + m] = gy; D[40 + m] = gz;
-      }
-    } else return 2;
-  }
+  for (int ig = 0; ig < nip; ++ig)
+    if (shape_der_at(nod, pts[ig][0], pts[ig][1], pts[ig][2], T.der + ig * 60, nod == 8 ? T.fun + ig * 8 : nullptr)) return 2;
   // deemat, 6x6
   const double v2 = v / (1.0 - v), vv = (1.0 - 2.0 * v) / (1.0 - v) * 0.5;
   for (int i = 0; i < 3; ++i) T.dee[i * 6 + i] = 1.0;
@@ -268,7 +288,7 @@ int fill_tables(int nod, int nip, double e, double v, double kx, double ky, doub
 
 // ---- mat-vec dispatch ----
 template <int NTOT, int EPT, int STAGES, bool GATHER>
-int launch_matvec_t(pf_handle h, const double *pvec, const State *st) {
+int launch_matvec_t(pf_handle h, const double *pvec, const State *st, PeerTable *T) {
   using Cfg = MatvecCfg<NTOT, EPT, STAGES>;
   auto kern = k_matvec<NTOT, EPT, STAGES, GATHER>;
   static bool attr_set = false;
@@ -279,7 +299,7 @@ int launch_matvec_t(pf_handle h, const double *pvec, const State *st) {
   const int64_t ntiles = (h->nels + EPT - 1) / EPT;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, ntiles));
   kern<<<grid, Cfg::kThreads, Cfg::kSmem, h->stream>>>(h->mat_override ? h->mat_override : h->km.p, h->ggl.p, pvec, h->utemp.p,
-                                                       (long long)h->nels, st);
+                                                       (long long)h->nels, st, T);
   h->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -293,7 +313,7 @@ int mf_grid(pf_handle h) {
 }
 
 template <int NTOT, int EPT, int STAGES, bool GATHER>
-int launch_matvec_sym_t(pf_handle h, const double *pvec, const State *st) {
+int launch_matvec_sym_t(pf_handle h, const double *pvec, const State *st, PeerTable *T) {
   using Cfg = MatvecSymCfg<NTOT, EPT, STAGES>;
   auto kern = k_matvec_sym<NTOT, EPT, STAGES, GATHER>;
   static bool attr_set = false;
@@ -303,14 +323,14 @@ int launch_matvec_sym_t(pf_handle h, const double *pvec, const State *st) {
   }
   const int64_t ntiles = (h->nels + EPT - 1) / EPT;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, ntiles));
-  kern<<<grid, Cfg::kThreads, Cfg::kSmem, h->stream>>>(h->km.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmem, h->stream>>>(h->km.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st, T);
   h->launches++;
   CU(cudaGetLastError());
   return 0;
 }
 
 template <int NOD, bool GATHER, int GEOM, int UNR = 2>
-int launch_mf_t(pf_handle h, const double *pvec, const State *st) {
+int launch_mf_t(pf_handle h, const double *pvec, const State *st, PeerTable *T = nullptr) {
   using Cfg = MfCfg<NOD>;
   auto kern = k_apply_mf<NOD, GATHER, GEOM, kMfWarps, UNR>;
   static bool attr_set = false;
@@ -319,26 +339,26 @@ int launch_mf_t(pf_handle h, const double *pvec, const State *st) {
     attr_set = true;
   }
   kern<<<mf_grid(h), kMfWarps * 32, Cfg::smem(kMfWarps), h->stream>>>(h->coord.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st,
-                                                                      h->geom.p);
+                                                                      h->geom.p, T);
   h->launches++;
   CU(cudaGetLastError());
   return 0;
 }
 
 template <bool GATHER>
-int launch_matvec(pf_handle h, const double *pvec, const State *st) {
+int launch_matvec(pf_handle h, const double *pvec, const State *st, PeerTable *T = nullptr) {
   Scope sc(h, K_MATVEC);
   if (h->matrix_free) {
     if (h->mf_mode == 2) {
       // PF_TUNE: unroll factor of the node-pair loops (default 2; measured in profiles/r01_mf_kernel_history.md)
       static const int mtune = getenv("PF_TUNE") ? atoi(getenv("PF_TUNE")) : 0;
-      if (h->nod == 20 && GATHER && mtune == 1) return launch_mf_t<20, GATHER, 2, 1>(h, pvec, st);
-      if (h->nod == 20 && GATHER && mtune == 2) return launch_mf_t<20, GATHER, 2, 5>(h, pvec, st);
-      if (h->nod == 20) return launch_mf_t<20, GATHER, 2>(h, pvec, st);
-      return launch_mf_t<8, GATHER, 2>(h, pvec, st);
+      if (h->nod == 20 && GATHER && mtune == 1) return launch_mf_t<20, GATHER, 2, 1>(h, pvec, st, T);
+      if (h->nod == 20 && GATHER && mtune == 2) return launch_mf_t<20, GATHER, 2, 5>(h, pvec, st, T);
+      if (h->nod == 20) return launch_mf_t<20, GATHER, 2>(h, pvec, st, T);
+      return launch_mf_t<8, GATHER, 2>(h, pvec, st, T);
     }
-    if (h->nod == 20) return launch_mf_t<20, GATHER, 0>(h, pvec, st);
-    return launch_mf_t<8, GATHER, 0>(h, pvec, st);
+    if (h->nod == 20) return launch_mf_t<20, GATHER, 0>(h, pvec, st, T);
+    return launch_mf_t<8, GATHER, 0>(h, pvec, st, T);
   }
   // PF_TUNE selects an alternative tile shape (elements per tile x ring slots) for experiments
   static const int tune = getenv("PF_TUNE") ? atoi(getenv("PF_TUNE")) : 0;
@@ -346,35 +366,35 @@ int launch_matvec(pf_handle h, const double *pvec, const State *st) {
     switch (h->ntot) {
       case 60:
         // measured: 10 ring slots 0.95 of HBM peak, 13 slots 0.93, 8 slots 0.94, 2 elements x 6 slots 0.72
-        if (tune == 1) return launch_matvec_sym_t<60, 1, 13, GATHER>(h, pvec, st);
-        if (tune == 2) return launch_matvec_sym_t<60, 1, 8, GATHER>(h, pvec, st);
-        return launch_matvec_sym_t<60, 1, 10, GATHER>(h, pvec, st);
+        if (tune == 1) return launch_matvec_sym_t<60, 1, 13, GATHER>(h, pvec, st, T);
+        if (tune == 2) return launch_matvec_sym_t<60, 1, 8, GATHER>(h, pvec, st, T);
+        return launch_matvec_sym_t<60, 1, 10, GATHER>(h, pvec, st, T);
       case 24:   // measured (profiles/r01_symmetric_layout.md): 4 x 16 beats 2 x 32 (64-register cap, spills)
-        if (tune == 1) return launch_matvec_sym_t<24, 2, 32, GATHER>(h, pvec, st);
-        if (tune == 2) return launch_matvec_sym_t<24, 6, 12, GATHER>(h, pvec, st);
-        return launch_matvec_sym_t<24, 4, 16, GATHER>(h, pvec, st);
-      case 8: return launch_matvec_sym_t<8, 16, 32, GATHER>(h, pvec, st);
+        if (tune == 1) return launch_matvec_sym_t<24, 2, 32, GATHER>(h, pvec, st, T);
+        if (tune == 2) return launch_matvec_sym_t<24, 6, 12, GATHER>(h, pvec, st, T);
+        return launch_matvec_sym_t<24, 4, 16, GATHER>(h, pvec, st, T);
+      case 8: return launch_matvec_sym_t<8, 16, 32, GATHER>(h, pvec, st, T);
     }
     return fail(h, 3, "unsupported ntot %d (supported: 60, 24, 8)", h->ntot);
   }
   switch (h->ntot) {
-    case 60: return launch_matvec_t<60, 1, 7, GATHER>(h, pvec, st);
+    case 60: return launch_matvec_t<60, 1, 7, GATHER>(h, pvec, st, T);
     // measured on B200 (profiles/r01_tile_tuning.md): small tiles on many ring slots win --
     // hex8 8x5 -> 0.90 of HBM peak, 2x16 -> 0.99, 1x32 -> 1.00; p123 64x6 -> 0.67, 16x16 -> 0.85
     case 24:
-      if (tune == 1) return launch_matvec_t<24, 8, 5, GATHER>(h, pvec, st);
-      if (tune == 2) return launch_matvec_t<24, 2, 16, GATHER>(h, pvec, st);
-      return launch_matvec_t<24, 1, 32, GATHER>(h, pvec, st);
+      if (tune == 1) return launch_matvec_t<24, 8, 5, GATHER>(h, pvec, st, T);
+      if (tune == 2) return launch_matvec_t<24, 2, 16, GATHER>(h, pvec, st, T);
+      return launch_matvec_t<24, 1, 32, GATHER>(h, pvec, st, T);
     case 8:
-      if (tune == 1) return launch_matvec_t<8, 64, 6, GATHER>(h, pvec, st);
-      return launch_matvec_t<8, 16, 16, GATHER>(h, pvec, st);
-    case 12: return launch_matvec_t<12, 8, 16, GATHER>(h, pvec, st);    // 4-node tetrahedra, elastic: 9 KB tiles
-    case 4: return launch_matvec_t<4, 64, 16, GATHER>(h, pvec, st);     // 4-node tetrahedra, scalar: 8 KB tiles
+      if (tune == 1) return launch_matvec_t<8, 64, 6, GATHER>(h, pvec, st, T);
+      return launch_matvec_t<8, 16, 16, GATHER>(h, pvec, st, T);
+    case 12: return launch_matvec_t<12, 8, 16, GATHER>(h, pvec, st, T);    // 4-node tetrahedra, elastic: 9 KB tiles
+    case 4: return launch_matvec_t<4, 64, 16, GATHER>(h, pvec, st, T);     // 4-node tetrahedra, scalar: 8 KB tiles
   }
   return fail(h, 3, "unsupported ntot %d (supported: 60, 24, 12, 8, 4)", h->ntot);
 }
 
-int launch_scatter(pf_handle h, const State *st, bool diag, double *dst) {
+int launch_scatter(pf_handle h, const State *st, bool diag, double *dst, PeerTable *T = nullptr) {
   Scope sc(h, K_SCATTER);
   // grid-stride kernel: exactly one resident wave (k_scatter needs 30 registers: 8 blocks of 256 per SM)
   static int per_sm = 0;
@@ -382,7 +402,8 @@ int launch_scatter(pf_handle h, const State *st, bool diag, double *dst) {
     per_sm = 8;
   const int grid = grid_for(h, h->nslots, 256, per_sm);
   if (diag) k_scatter<true><<<grid, 256, 0, h->stream>>>(h->csr_ptr.p, h->csr_pos.p, h->km.p, dst, (long long)h->nslots, h->ntot, st, h->km_layout);
-  else k_scatter<false><<<grid, 256, 0, h->stream>>>(h->csr_ptr.p, h->csr_pos.p, h->utemp.p, dst, (long long)h->nslots, h->ntot, st);
+  else k_scatter<false><<<grid, 256, 0, h->stream>>>(h->csr_ptr.p, h->csr_pos.p, h->utemp.p, dst, (long long)h->nslots, h->ntot, st, 0, T,
+                                                     (long long)h->neq_pp);
   h->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -462,6 +483,60 @@ int setup_peer(pf_handle h, const std::vector<int64_t> &all) {
   h->host_tab = T;
   h->ptab_valid = true;
   h->peer_ok = true;
+  return 0;
+}
+
+// Unanimous verdict before any rank leaves a section that the others continue with collectives: every rank
+// contributes its local status; if any failed, ALL return an error (the failing rank its own, the others status 20)
+// instead of blocking for ever in the next all-gather / send-recv / flag wait.
+int agree(pf_handle h, int local_rc) {
+  if (h->nranks == 1 || !h->comm) return local_rc;
+  const std::string mine = h->err;
+  DevBuf<int> d_one, d_all;
+  if (d_one.alloc(1) != cudaSuccess || d_all.alloc((size_t)h->nranks) != cudaSuccess) return local_rc ? local_rc : 10;
+  std::vector<int> all((size_t)h->nranks, 0);
+  bool ok = cudaMemcpy(d_one.p, &local_rc, sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
+            g_nccl.AllGather(d_one.p, d_all.p, 1, ncclInt32, h->comm, h->stream) == ncclSuccess &&
+            cudaStreamSynchronize(h->stream) == cudaSuccess &&
+            cudaMemcpy(all.data(), d_all.p, all.size() * sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess;
+  d_one.release(); d_all.release();
+  if (!ok) return local_rc ? local_rc : fail(h, 11, "agree: status exchange failed");
+  if (local_rc) { h->err = mine; return local_rc; }
+  for (int r = 0; r < h->nranks; ++r)
+    if (all[(size_t)r]) return fail(h, 20, "rank %d failed (status %d) in a collective section; this rank returns with it", r, all[(size_t)r]);
+  return 0;
+}
+
+// tables of the exchanges fused into k_pupdate (forward) and k_dot (reverse); needs h->host_tab (setup_peer)
+int build_fused_tables(pf_handle h, const std::vector<int> &put_slot_host, const std::vector<int> &acc_slot_host) {
+  const PeerTable &T = h->host_tab;
+  const int R = h->nranks;
+  std::vector<int64_t> off((size_t)R + 1), dst_off((size_t)R);
+  for (int r = 0; r < R; ++r) { off[(size_t)r] = h->put_off[r]; dst_off[(size_t)r] = T.fwd_dst_off[r]; }
+  off[(size_t)R] = h->nput;
+  const size_t np = (size_t)std::max<int64_t>(h->nput, 1);
+  std::vector<unsigned int> bits((size_t)((h->neq_pp + 31) / 32 + 1)), ptr(np + 1);
+  std::vector<int> slot0(np), rank(np);
+  std::vector<int64_t> dst(np);
+  int64_t nu = 0;
+  if (pf_make_put_tables(R, h->neq_pp, off.data(), put_slot_host.data(), dst_off.data(), bits.data(), slot0.data(), ptr.data(),
+                         rank.data(), dst.data(), &nu))
+    return fail(h, 4, "pf_setup_mesh: forward-exchange tables could not be built");
+  h->npk = (int)nu;
+  CU(h->put_bits.alloc(bits.size())); CU(h->pk_ptr.alloc(ptr.size()));
+  CU(h->pk_slot0.alloc(np)); CU(h->pk_rank.alloc(np)); CU(h->pk_dst.alloc(np));
+  CU(cudaMemcpy(h->put_bits.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->pk_ptr.p, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->pk_slot0.p, slot0.data(), np * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->pk_rank.p, rank.data(), np * 4, cudaMemcpyHostToDevice));
+  static_assert(sizeof(long long) == sizeof(int64_t), "pk_dst");
+  CU(cudaMemcpy(h->pk_dst.p, dst.data(), np * 8, cudaMemcpyHostToDevice));
+  const size_t nchunks = (size_t)((h->neq_pp + kChunk - 1) / kChunk);
+  std::vector<unsigned int> cptr(nchunks + 1, 0u);
+  if (pf_make_acc_chunks(h->neq_pp, kChunk, (int64_t)acc_slot_host.size(), acc_slot_host.data(), cptr.data()))
+    return fail(h, 4, "pf_setup_mesh: accumulate table is not ascending");
+  CU(h->acc_chunk_ptr.alloc(cptr.size()));
+  CU(cudaMemcpy(h->acc_chunk_ptr.p, cptr.data(), cptr.size() * 4, cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -560,6 +635,21 @@ int apply_operator(pf_handle h, const State *st, bool peer = false) {
   return 0;
 }
 
+bool fused_peer() {
+  static const bool on = !(getenv("PF_FUSE") && !strcmp(getenv("PF_FUSE"), "0"));
+  return on;
+}
+AccTables acc_tables(pf_handle h) {
+  return AccTables{h->acc_slot.p, h->acc_ptr.p, h->acc_pos.p, h->acc_chunk_ptr.p, h->recvbuf.p, h->u_ext.p};
+}
+PutTables put_tables(pf_handle h) {
+  return PutTables{h->put_bits.p, h->pk_slot0.p, h->pk_ptr.p, h->pk_rank.p, h->pk_dst.p, h->npk};
+}
+
+// One PCG iteration (p121.f90:91-103).  Peer transport: five launches, as on one rank -- the forward exchange of
+// the NEXT iteration rides on k_pupdate, k_matvec waits for it in its prologue, the reverse exchange rides on
+// k_scatter and k_dot adds the received partial sums before reducing.  NCCL transport: the separate pack / send-recv /
+// accumulate / all-gather steps.
 int one_iteration(pf_handle h) {
   State *st = h->state.p;
   const int single = h->nranks == 1;
@@ -567,17 +657,41 @@ int one_iteration(pf_handle h) {
   const bool peer = h->peer_ok && h->use_peer;
   PeerTable *T = peer ? h->ptab.p : nullptr;
   int rc;
-  if ((rc = apply_operator(h, st, peer))) return rc;
+  if (peer && !fused_peer()) {
+    // PF_FUSE=0: the first build of the peer transport (put / wait / accumulate kernels of their own), kept for A/B runs
+    if ((rc = apply_operator(h, st, true))) return rc;
+    Scope sc(h, K_VECTOR);
+    k_dot<false><<<vec_grid(h, k_dot<false>), kRedThreads, 0, h->stream>>>(h->p_ext.p + 1, h->u_ext.p + 1, n, h->part.p, st, single, 1, T, AccTables{});
+    k_pcg_update<<<vec_grid(h, k_pcg_update), kRedThreads, 0, h->stream>>>(h->diag_ext.p + 1, h->p_ext.p + 1, h->u_ext.p + 1, h->x.p, h->r.p,
+                                                              h->d.p, n, h->part.p, st, single, h->ratio_hist.p, T);
+    k_pupdate<<<grid_for(h, (n + 1) / 2, 256, 8), 256, 0, h->stream>>>(h->d.p, h->p_ext.p + 1, n, st, nullptr, PutTables{});
+    h->launches += 3;
+    CU(cudaGetLastError());
+    return 0;
+  }
+  if (peer) {
+    if ((rc = launch_matvec<true>(h, h->p_ext.p, st, T))) return rc;
+    if ((rc = launch_scatter(h, st, false, h->u_ext.p, T))) return rc;
+    if (h->nfixed > 0) {   // owned rows only; the partial sums of others for these rows are overridden as well
+      k_halo_wait<<<1, 32, 0, h->stream>>>(T, 1, st);
+      if (h->nacc > 0) k_halo_accumulate<<<(h->nacc + 255) / 256, 256, 0, h->stream>>>(h->acc_slot.p, h->acc_ptr.p, h->acc_pos.p, h->recvbuf.p, h->u_ext.p, h->nacc, st);
+      k_fixed_u<<<(h->nfixed + 255) / 256, 256, 0, h->stream>>>(h->fix_slot.p, h->store.p, h->p_ext.p, h->u_ext.p, h->nfixed, st);
+      h->launches += 2 + (h->nacc > 0);
+    }
+  } else if ((rc = apply_operator(h, st, false))) return rc;
   {
     Scope sc(h, K_VECTOR);
-    k_dot<<<vec_grid(h, k_dot), kRedThreads, 0, h->stream>>>(h->p_ext.p + 1, h->u_ext.p + 1, n, h->part.p, st, single, 1, T);
+    if (peer && h->nfixed == 0)
+      k_dot<true><<<vec_grid(h, k_dot<true>), kRedThreads, 0, h->stream>>>(h->p_ext.p + 1, h->u_ext.p + 1, n, h->part.p, st, single, 1, T, acc_tables(h));
+    else
+      k_dot<false><<<vec_grid(h, k_dot<false>), kRedThreads, 0, h->stream>>>(h->p_ext.p + 1, h->u_ext.p + 1, n, h->part.p, st, single, 1, T, AccTables{});
     h->launches++;
     if (!peer && (rc = combine_scalars(h, 1))) return rc;
     k_pcg_update<<<vec_grid(h, k_pcg_update), kRedThreads, 0, h->stream>>>(h->diag_ext.p + 1, h->p_ext.p + 1, h->u_ext.p + 1, h->x.p, h->r.p,
                                                               h->d.p, n, h->part.p, st, single, h->ratio_hist.p, T);
     h->launches++;
     if (!peer && (rc = combine_scalars(h, 2))) return rc;
-    k_pupdate<<<grid_for(h, (n + 1) / 2, 256, 8), 256, 0, h->stream>>>(h->d.p, h->p_ext.p + 1, n, st);
+    k_pupdate<<<grid_for(h, (n + 1) / 2, 256, 8), 256, 0, h->stream>>>(h->d.p, h->p_ext.p + 1, n, st, T, peer ? put_tables(h) : PutTables{});
     h->launches++;
   }
   CU(cudaGetLastError());
@@ -630,6 +744,9 @@ int pf_init(int rank, int nranks, int device, const void *id128, pf_handle *out)
   CU(h->state.alloc(1));
   CU(cudaMemset(h->state.p, 0, sizeof(State)));
   CU(h->gath.alloc((size_t)4 * nranks));
+  CU(cudaMallocHost((void **)&h->snap_pinned, 2 * sizeof(State)));
+  CU(cudaEventCreateWithFlags(&h->snap_ev[0], cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&h->snap_ev[1], cudaEventDisableTiming));
   if (nranks > 1) {
     std::string err;
     if (!g_nccl.load(err)) { int rc = fail(h, 12, "%s", err.c_str()); delete h; return rc; }
@@ -652,6 +769,9 @@ int pf_finalize(pf_handle h) {
   collect_spans(h);
   for (auto e : h->pool) cudaEventDestroy(e);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->snap_pinned) cudaFreeHost(h->snap_pinned);
+  for (auto e : h->snap_ev) if (e) cudaEventDestroy(e);
+  h->put_bits.release(); h->pk_ptr.release(); h->acc_chunk_ptr.release(); h->pk_slot0.release(); h->pk_rank.release(); h->pk_dst.release();
   close_imports(h);
   if (h->comm) {
     // peers must have closed their mappings of my buffers before I free them
@@ -764,19 +884,30 @@ int pf_get_kernel_ms(pf_handle h, int which, double *total_ms, int64_t *launches
 int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp, const double *g_coord_pp,
                   const int32_t *g_g_pp, int64_t neq, int64_t ieq_start, int64_t neq_pp) {
   int rc = need_device(h); if (rc) return rc;
-  NEED((nod == 4 || nod == 8 || nod == 20) && (nodof == 1 || nodof == 3), "nod must be 4 (tetrahedra), 8 or 20 (hexahedra), nodof 1 or 3");
-  NEED(nip == 1 || nip == 8, "nip must be 1 or 8");
-  NEED(nod != 4 || nip == 1, "4-node tetrahedra take nip = 1");
-  NEED(nels_pp >= 1 && neq >= 1 && neq_pp >= 0 && ieq_start >= 1, "bad sizes");
   const int ntot = nod * nodof;
-  NEED(ntot == 60 || ntot == 24 || ntot == 8 || ntot == 12 || ntot == 4,
-       "supported element types: hex20 / hex8 / tet4 elastic, hex8 / tet4 scalar");
-  NEED(nels_pp * ntot < (int64_t)0xffffffffu, "nels_pp*ntot exceeds 32-bit table range; use more ranks");
-  {
-    int64_t c, s;
-    pf_calc_neq_pp(neq, h->nranks, h->rank + 1, &c, &s);
-    NEED(c == neq_pp && s == ieq_start, "neq_pp/ieq_start do not match calc_neq_pp for this rank");
-  }
+  const int64_t total = nels_pp * ntot;
+  std::vector<int32_t> halo;
+  std::vector<int64_t> halo_cnt((size_t)h->nranks, 0);
+  int64_t nhalo = 0;
+
+  // ---- section A, local: argument checks, gather table, scatter tables on the device, vectors.  Several ranks:
+  // nobody enters the collectives below unless every rank got through (agree) ----
+  auto local_a = [&]() -> int {
+    NEED((nod == 4 || nod == 8 || nod == 20) && (nodof == 1 || nodof == 3), "nod must be 4 (tetrahedra), 8 or 20 (hexahedra), nodof 1 or 3");
+    NEED(nip == 1 || nip == 8, "nip must be 1 or 8");
+    NEED(nod != 4 || nip == 1, "4-node tetrahedra take nip = 1");
+    NEED(nels_pp >= 1 && neq >= 1 && neq_pp >= 0 && ieq_start >= 1, "bad sizes");
+    NEED(ntot == 60 || ntot == 24 || ntot == 8 || ntot == 12 || ntot == 4,
+         "supported element types: hex20 / hex8 / tet4 elastic, hex8 / tet4 scalar");
+    NEED(nels_pp * ntot < (int64_t)0xffffffffu, "nels_pp*ntot exceeds 32-bit table range; use more ranks");
+    {
+      int64_t c, s;
+      pf_calc_neq_pp(neq, h->nranks, h->rank + 1, &c, &s);
+      NEED(c == neq_pp && s == ieq_start, "neq_pp/ieq_start do not match calc_neq_pp for this rank");
+    }
+    return 0;
+  };
+  if ((rc = agree(h, local_a()))) return rc;
   if (h->nranks > 1) {
     // re-setup: drop the mappings of the peers' old buffers, and make sure every peer has
     // dropped its mappings of mine, before anything is freed
@@ -787,79 +918,80 @@ int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp, con
     CU(cudaStreamSynchronize(h->stream));
     a.release(); b.release();
   }
-  h->nod = nod; h->nodof = nodof; h->nip = nip; h->ntot = ntot;
-  h->nels = nels_pp; h->neq = neq; h->ieq_start = ieq_start; h->neq_pp = neq_pp;
-  h->have_km = h->have_precon = false;
-  h->transient = h->transient_first = false; h->mat_override = nullptr; h->kb.release();
-  h->explicit_ = false;
+  auto local_b = [&]() -> int {
+    h->nod = nod; h->nodof = nodof; h->nip = nip; h->ntot = ntot;
+    h->nels = nels_pp; h->neq = neq; h->ieq_start = ieq_start; h->neq_pp = neq_pp;
+    h->have_mesh = false; h->have_km = h->have_precon = false;
+    h->transient = h->transient_first = false; h->mat_override = nullptr; h->kb.release();
+    h->explicit_ = false;
+    h->epoch++;                                   // a captured iteration graph of the previous mesh is stale
 
-  // gather table (make_ggl rebuilt from g_g_pp)
-  const int64_t total = nels_pp * ntot;
-  std::vector<int32_t> ggl((size_t)total), halo;
-  std::vector<int64_t> halo_cnt((size_t)h->nranks, 0);
-  int64_t nhalo = 0;
-  if (pf_make_ggl(ntot, nels_pp, g_g_pp, neq, h->nranks, h->rank + 1, nullptr, 0, nullptr, halo_cnt.data(), &nhalo))
-    return fail(h, 4, "pf_setup_mesh: g_g_pp holds equation numbers outside [0, neq]");
-  halo.resize((size_t)std::max<int64_t>(nhalo, 1));
-  if (pf_make_ggl(ntot, nels_pp, g_g_pp, neq, h->nranks, h->rank + 1, ggl.data(), (int64_t)halo.size(), halo.data(),
-                  halo_cnt.data(), &nhalo))
-    return fail(h, 4, "pf_setup_mesh: gather table construction failed");
-  h->nhalo = nhalo;
-  h->nslots = 1 + neq_pp + nhalo;
-  NEED(h->nslots < (int64_t)0x7fffffff, "slot count exceeds int32");
+    // gather table (make_ggl rebuilt from g_g_pp)
+    std::vector<int32_t> ggl((size_t)total);
+    if (pf_make_ggl(ntot, nels_pp, g_g_pp, neq, h->nranks, h->rank + 1, nullptr, 0, nullptr, halo_cnt.data(), &nhalo))
+      return fail(h, 4, "pf_setup_mesh: g_g_pp holds equation numbers outside [0, neq]");
+    halo.resize((size_t)std::max<int64_t>(nhalo, 1));
+    if (pf_make_ggl(ntot, nels_pp, g_g_pp, neq, h->nranks, h->rank + 1, ggl.data(), (int64_t)halo.size(), halo.data(),
+                    halo_cnt.data(), &nhalo))
+      return fail(h, 4, "pf_setup_mesh: gather table construction failed");
+    h->nhalo = nhalo;
+    h->nslots = 1 + neq_pp + nhalo;
+    NEED(h->nslots < (int64_t)0x7fffffff, "slot count exceeds int32");
 
-  // CSR of contributions per slot in ascending element order: built on the device below (stable radix sort)
-  CU(h->coord.alloc((size_t)nels_pp * nod * 3));
-  CU(cudaMemcpy(h->coord.p, g_coord_pp, h->coord.bytes(), cudaMemcpyHostToDevice));
-  CU(h->ggl.alloc((size_t)total));
-  CU(cudaMemcpy(h->ggl.p, ggl.data(), h->ggl.bytes(), cudaMemcpyHostToDevice));
-  {
-    // csr_pos = positions e*ntot+k sorted by slot, ascending inside a slot (the sort is stable), the slot-0
-    // (restrained) entries dropped; csr_ptr[s] = first position of slot s.  117 M pairs at config C: a few ms
-    // instead of ~0.7 s of random-access host passes.
-    DevBuf<int> keys;
-    DevBuf<unsigned int> iota, vals;
-    DevBuf<unsigned char> tmp;
-    CU(keys.alloc((size_t)total)); CU(iota.alloc((size_t)total)); CU(vals.alloc((size_t)total));
-    k_iota<<<grid_for(h, total, 256), 256, 0, h->stream>>>(iota.p, (long long)total);
-    int end_bit = 1;
-    while (end_bit < 31 && ((int64_t)1 << end_bit) < h->nslots) ++end_bit;
-    size_t tmp_bytes = 0;
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->ggl.p, keys.p, iota.p, vals.p, (int64_t)total, 0, end_bit, h->stream));
-    CU(tmp.alloc(tmp_bytes));
-    CU(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, h->ggl.p, keys.p, iota.p, vals.p, (int64_t)total, 0, end_bit, h->stream));
-    CU(h->csr_ptr.alloc((size_t)h->nslots + 1));
-    k_csr_ptr<<<grid_for(h, h->nslots + 1, 256), 256, 0, h->stream>>>(keys.p, (long long)total, h->csr_ptr.p, (long long)h->nslots);
-    h->launches += 2;
-    CU(cudaGetLastError());
-    unsigned int n0 = 0, nnz = 0;       // entries of slot 0, entries of slots >= 1
-    CU(cudaMemcpyAsync(&nnz, h->csr_ptr.p + h->nslots, 4, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    n0 = (unsigned int)total - nnz;
-    CU(h->csr_pos.alloc(std::max<size_t>(nnz, 1)));
-    CU(cudaMemcpyAsync(h->csr_pos.p, vals.p + n0, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    keys.release(); iota.release(); vals.release(); tmp.release();
-  }
-  CU(h->utemp.alloc((size_t)total));
+    // CSR of contributions per slot in ascending element order: built on the device below (stable radix sort)
+    CU(h->coord.alloc((size_t)nels_pp * nod * 3));
+    CU(cudaMemcpy(h->coord.p, g_coord_pp, h->coord.bytes(), cudaMemcpyHostToDevice));
+    CU(h->ggl.alloc((size_t)total));
+    CU(cudaMemcpy(h->ggl.p, ggl.data(), h->ggl.bytes(), cudaMemcpyHostToDevice));
+    {
+      // csr_pos = positions e*ntot+k sorted by slot, ascending inside a slot (the sort is stable), the slot-0
+      // (restrained) entries dropped; csr_ptr[s] = first position of slot s.  117 M pairs at config C: a few ms
+      // instead of ~0.7 s of random-access host passes.  (DevBuf releases on every return path.)
+      DevBuf<int> keys;
+      DevBuf<unsigned int> iota, vals;
+      DevBuf<unsigned char> tmp;
+      CU(keys.alloc((size_t)total)); CU(iota.alloc((size_t)total)); CU(vals.alloc((size_t)total));
+      k_iota<<<grid_for(h, total, 256), 256, 0, h->stream>>>(iota.p, (long long)total);
+      int end_bit = 1;
+      while (end_bit < 31 && ((int64_t)1 << end_bit) < h->nslots) ++end_bit;
+      size_t tmp_bytes = 0;
+      CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->ggl.p, keys.p, iota.p, vals.p, (int64_t)total, 0, end_bit, h->stream));
+      CU(tmp.alloc(tmp_bytes));
+      CU(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, h->ggl.p, keys.p, iota.p, vals.p, (int64_t)total, 0, end_bit, h->stream));
+      CU(h->csr_ptr.alloc((size_t)h->nslots + 1));
+      k_csr_ptr<<<grid_for(h, h->nslots + 1, 256), 256, 0, h->stream>>>(keys.p, (long long)total, h->csr_ptr.p, (long long)h->nslots);
+      h->launches += 2;
+      CU(cudaGetLastError());
+      unsigned int n0 = 0, nnz = 0;       // entries of slot 0, entries of slots >= 1
+      CU(cudaMemcpyAsync(&nnz, h->csr_ptr.p + h->nslots, 4, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      n0 = (unsigned int)total - nnz;
+      CU(h->csr_pos.alloc(std::max<size_t>(nnz, 1)));
+      CU(cudaMemcpyAsync(h->csr_pos.p, vals.p + n0, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+    }
+    CU(h->utemp.alloc((size_t)total));
 
-  const size_t ns = (size_t)h->nslots, nq = (size_t)std::max<int64_t>(neq_pp, 1);
-  CU(h->p_ext.alloc(ns)); CU(h->u_ext.alloc(ns)); CU(h->diag_ext.alloc(ns));
-  CU(h->r.alloc(nq)); CU(h->x.alloc(nq)); CU(h->d.alloc(nq));
-  CU(cudaMemset(h->p_ext.p, 0, ns * 8)); CU(cudaMemset(h->u_ext.p, 0, ns * 8)); CU(cudaMemset(h->diag_ext.p, 0, ns * 8));
-  CU(cudaMemset(h->x.p, 0, nq * 8));
-  const size_t nchunks = (size_t)((neq_pp + kChunk - 1) / kChunk);
-  CU(h->part.alloc(3 * std::max<size_t>(nchunks, 1)));
+    const size_t ns = (size_t)h->nslots, nq = (size_t)std::max<int64_t>(neq_pp, 1);
+    CU(h->p_ext.alloc(ns)); CU(h->u_ext.alloc(ns)); CU(h->diag_ext.alloc(ns));
+    CU(h->r.alloc(nq)); CU(h->x.alloc(nq)); CU(h->d.alloc(nq));
+    CU(cudaMemset(h->p_ext.p, 0, ns * 8)); CU(cudaMemset(h->u_ext.p, 0, ns * 8)); CU(cudaMemset(h->diag_ext.p, 0, ns * 8));
+    CU(cudaMemset(h->x.p, 0, nq * 8));
+    const size_t nchunks = (size_t)((neq_pp + kChunk - 1) / kChunk);
+    CU(h->part.alloc(3 * std::max<size_t>(nchunks, 1)));
+    return 0;
+  };
+  if ((rc = agree(h, local_b()))) return rc;
 
   // halo tables: what I get from each owner is known; tell each owner what to put
   h->get_cnt.assign((size_t)h->nranks, 0); h->get_off.assign((size_t)h->nranks, 0);
   h->put_cnt.assign((size_t)h->nranks, 0); h->put_off.assign((size_t)h->nranks, 0);
-  h->nput = 0; h->nacc = 0;
+  h->nput = 0; h->nacc = 0; h->npk = 0;
   if (h->nranks > 1) {
     const int R = h->nranks;
     int64_t off = 0;
     for (int r = 0; r < R; ++r) { h->get_cnt[r] = halo_cnt[r]; h->get_off[r] = off; off += halo_cnt[r]; }
-    // counts matrix via all-gather (int64 as 8-byte doubles would mangle; use ncclInt64)
+    // ---- section B, collective: counts matrix by all-gather, wanted equation numbers by grouped send/recv ----
     DevBuf<int64_t> d_cnt, d_all;
     CU(d_cnt.alloc((size_t)R)); CU(d_all.alloc((size_t)R * R));
     CU(cudaMemcpy(d_cnt.p, h->get_cnt.data(), (size_t)R * 8, cudaMemcpyHostToDevice));
@@ -871,8 +1003,6 @@ int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp, con
     off = 0;
     for (int r = 0; r < R; ++r) { h->put_cnt[r] = all[(size_t)r * R + h->rank]; h->put_off[r] = off; off += h->put_cnt[r]; }
     h->nput = off;
-    NEED(h->put_cnt[h->rank] == 0, "a rank lists its own equations as remote");
-    // exchange the wanted global equation numbers
     DevBuf<int> d_want, d_asked;
     CU(d_want.alloc((size_t)std::max<int64_t>(nhalo, 1))); CU(d_asked.alloc((size_t)std::max<int64_t>(h->nput, 1)));
     CU(cudaMemcpy(d_want.p, halo.data(), (size_t)nhalo * 4, cudaMemcpyHostToDevice));
@@ -887,31 +1017,41 @@ int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp, con
     std::vector<int> asked((size_t)std::max<int64_t>(h->nput, 1));
     CU(cudaMemcpy(asked.data(), d_asked.p, (size_t)h->nput * 4, cudaMemcpyDeviceToHost));
     d_want.release(); d_asked.release();
-    for (int64_t k = 0; k < h->nput; ++k) {
-      const int64_t g = asked[(size_t)k];
-      NEED(g >= ieq_start && g < ieq_start + neq_pp, "peer asked for an equation this rank does not own");
-      asked[(size_t)k] = (int)(g - ieq_start + 1);  // -> slot
-    }
-    CU(h->put_slot.alloc(asked.size()));
-    CU(cudaMemcpy(h->put_slot.p, asked.data(), asked.size() * 4, cudaMemcpyHostToDevice));
-    CU(h->sendbuf.alloc(asked.size())); CU(h->recvbuf.alloc(asked.size()));
-    // accumulate table: per owned slot, receive-buffer positions in ascending source rank
-    // (recvbuf is grouped by source rank ascending, so ascending position == ascending rank)
-    std::vector<std::pair<int, unsigned int>> pairs((size_t)h->nput);
-    for (int64_t k = 0; k < h->nput; ++k) pairs[(size_t)k] = {asked[(size_t)k], (unsigned int)k};
-    std::sort(pairs.begin(), pairs.end());
-    std::vector<int> aslot; std::vector<unsigned int> aptr, apos;
-    for (size_t k = 0; k < pairs.size(); ++k) {
-      if (k == 0 || pairs[k].first != pairs[k - 1].first) { aslot.push_back(pairs[k].first); aptr.push_back((unsigned int)k); }
-      apos.push_back(pairs[k].second);
-    }
-    aptr.push_back((unsigned int)pairs.size());
-    h->nacc = (int)aslot.size();
-    CU(h->acc_slot.alloc(std::max<size_t>(aslot.size(), 1))); CU(h->acc_ptr.alloc(aptr.size())); CU(h->acc_pos.alloc(std::max<size_t>(apos.size(), 1)));
-    CU(cudaMemcpy(h->acc_slot.p, aslot.data(), aslot.size() * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->acc_ptr.p, aptr.data(), aptr.size() * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->acc_pos.p, apos.data(), apos.size() * 4, cudaMemcpyHostToDevice));
+    // ---- section C, local: validate what the peers asked for, build the put / accumulate tables ----
+    std::vector<int> aslot;
+    auto local_c = [&]() -> int {
+      NEED(h->put_cnt[h->rank] == 0, "a rank lists its own equations as remote");
+      for (int64_t k = 0; k < h->nput; ++k) {
+        const int64_t g = asked[(size_t)k];
+        NEED(g >= ieq_start && g < ieq_start + neq_pp, "peer asked for an equation this rank does not own");
+        asked[(size_t)k] = (int)(g - ieq_start + 1);  // -> slot
+      }
+      CU(h->put_slot.alloc(asked.size()));
+      CU(cudaMemcpy(h->put_slot.p, asked.data(), asked.size() * 4, cudaMemcpyHostToDevice));
+      CU(h->sendbuf.alloc(asked.size())); CU(h->recvbuf.alloc(asked.size()));
+      // accumulate table: per owned slot, receive-buffer positions in ascending source rank
+      // (recvbuf is grouped by source rank ascending, so ascending position == ascending rank)
+      std::vector<std::pair<int, unsigned int>> pairs((size_t)h->nput);
+      for (int64_t k = 0; k < h->nput; ++k) pairs[(size_t)k] = {asked[(size_t)k], (unsigned int)k};
+      std::sort(pairs.begin(), pairs.end());
+      std::vector<unsigned int> aptr, apos;
+      for (size_t k = 0; k < pairs.size(); ++k) {
+        if (k == 0 || pairs[k].first != pairs[k - 1].first) { aslot.push_back(pairs[k].first); aptr.push_back((unsigned int)k); }
+        apos.push_back(pairs[k].second);
+      }
+      aptr.push_back((unsigned int)pairs.size());
+      h->nacc = (int)aslot.size();
+      CU(h->acc_slot.alloc(std::max<size_t>(aslot.size(), 1))); CU(h->acc_ptr.alloc(aptr.size())); CU(h->acc_pos.alloc(std::max<size_t>(apos.size(), 1)));
+      CU(cudaMemcpy(h->acc_slot.p, aslot.data(), aslot.size() * 4, cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(h->acc_ptr.p, aptr.data(), aptr.size() * 4, cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(h->acc_pos.p, apos.data(), apos.size() * 4, cudaMemcpyHostToDevice));
+      return 0;
+    };
+    if ((rc = agree(h, local_c()))) return rc;
+    // ---- section D: peer mappings (collective, ends with its own unanimous verdict), then the tables of the fused
+    // exchanges (local) ----
     if ((rc = setup_peer(h, all))) return rc;
+    if ((rc = agree(h, h->peer_ok ? build_fused_tables(h, asked, aslot) : 0))) return rc;
   }
   h->have_mesh = true;
   return 0;
@@ -1348,14 +1488,23 @@ int pf_pcg_run(pf_handle h, double tol, int limit, int *iters, int *converged, d
                                                           (h->peer_ok && h->use_peer) ? h->ptab.p : nullptr);
   h->launches++;
   if (!(h->peer_ok && h->use_peer) && (rc = combine_scalars(h, 0))) return rc;
+  const bool peer = h->peer_ok && h->use_peer;
+  if (peer && fused_peer()) {
+    // the forward exchange of the first iteration; every later one rides on k_pupdate
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((h->nput + 255) / 256, 2 * h->sm_count));
+    k_halo_put_peer<<<grid, 256, 0, h->stream>>>(h->ptab.p, h->put_slot.p, h->p_ext.p, (long long)h->nput, h->state.p);
+    h->launches++;
+    CU(cudaGetLastError());
+  }
   EventPair ev;
   CU(ev.create());
   const cudaEvent_t e0 = ev.a, e1 = ev.b;
   CU(cudaEventRecord(e0, h->stream));  // timest(3), p121.f90:89
-  // Single rank: the iteration (5 launches with constant arguments) is captured once per problem as a CUDA graph
-  // and replayed -- at config B / p124 sizes the launch gaps were ~15 % of an iteration.  PF_GRAPH=0 disables it.
+  // The iteration (5 launches with constant arguments; sequence numbers and scalars live in device memory) is
+  // captured once per problem as a CUDA graph and replayed -- on one rank and, in the peer transport, on N ranks
+  // (no NCCL call inside).  PF_GRAPH=0 disables it; so does per-launch profiling.
   static const bool graph_allowed = !(getenv("PF_GRAPH") && !strcmp(getenv("PF_GRAPH"), "0"));
-  bool use_graph = graph_allowed && h->nranks == 1 && !h->profile;
+  bool use_graph = graph_allowed && (h->nranks == 1 || (peer && fused_peer())) && !h->profile;
   if (use_graph && (!h->graph_exec || h->graph_epoch != h->epoch)) {
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     cudaGraph_t g = nullptr;
@@ -1375,19 +1524,38 @@ int pf_pcg_run(pf_handle h, double tol, int limit, int *iters, int *converged, d
     h->graph_epoch = h->epoch;
   }
   use_graph = use_graph && h->graph_exec;
-  State snap;
+  // The host runs ahead of the device: batches of 8 iterations, and the state snapshot of batch b is only awaited
+  // after batch b+1 has been queued (two pinned snapshots) -- the device never idles while the host looks at the
+  // stopping flag.  Every kernel returns at once when `done` is set, so a batch queued past convergence costs
+  // microseconds.  Never more than `limit` iterations are queued.
   const int batch = 8;
-  int queued = 0;
-  for (;;) {
+  int queued = 0, slot = 0;
+  auto enqueue = [&](int which) -> int {
     const int nb = std::min(batch, limit - queued);
     for (int k = 0; k < nb; ++k) {
       if (use_graph) { CU(cudaGraphLaunch(h->graph_exec, h->stream)); h->launches += h->graph_launches; }
-      else if ((rc = one_iteration(h))) return rc;
+      else if (int r2 = one_iteration(h)) return r2;
     }
     queued += nb;
-    CU(cudaMemcpyAsync(&snap, h->state.p, sizeof snap, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    if (snap.done || queued >= limit) break;
+    CU(cudaMemcpyAsync(&h->snap_pinned[which], h->state.p, sizeof(State), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->snap_ev[which], h->stream));
+    return 0;
+  };
+  if ((rc = enqueue(slot))) return rc;
+  State snap;
+  for (;;) {
+    const bool more = queued < limit;
+    if (more && (rc = enqueue(slot ^ 1))) return rc;
+    CU(cudaEventSynchronize(h->snap_ev[slot]));
+    snap = h->snap_pinned[slot];
+    if (snap.done || !more) {
+      if (more) {                                    // the batch queued ahead drains as no-ops
+        CU(cudaEventSynchronize(h->snap_ev[slot ^ 1]));
+        snap = h->snap_pinned[slot ^ 1];
+      }
+      break;
+    }
+    slot ^= 1;
   }
   CU(cudaEventRecord(e1, h->stream));
   CU(cudaEventSynchronize(e1));
@@ -1395,9 +1563,13 @@ int pf_pcg_run(pf_handle h, double tol, int limit, int *iters, int *converged, d
   CU(cudaEventElapsedTime(&ms, e0, e1));
   collect_spans(h);
   h->last_iters = snap.iters;
+  h->last_ms = ms;
   if (iters) *iters = snap.iters;
   if (converged) *converged = snap.converged;
   if (elapsed_ms) *elapsed_ms = ms;
+  if (snap.fault)
+    return fail(h, 14, "pf_pcg_run: a peer rank did not arrive at a halo / reduction flag within %d s; the solve was abandoned",
+                (int)(kSpinTimeoutNs / 1000000000ull));
   return 0;
 }
 
@@ -1495,8 +1667,8 @@ int pf_dot(pf_handle h, const double *a_pp, const double *b_pp, double *result) 
   // p_ext / u_ext double as staging for the two operands
   if ((rc = upload_owned(h, h->p_ext.p, a_pp))) return rc;
   if ((rc = upload_owned(h, h->u_ext.p, b_pp))) return rc;
-  k_dot<<<vec_grid(h, k_dot), kRedThreads, 0, h->stream>>>(h->p_ext.p + 1, h->u_ext.p + 1, (long long)h->neq_pp, h->part.p, h->state.p,
-                                                     h->nranks == 1, -1, nullptr);
+  k_dot<false><<<vec_grid(h, k_dot<false>), kRedThreads, 0, h->stream>>>(h->p_ext.p + 1, h->u_ext.p + 1, (long long)h->neq_pp, h->part.p, h->state.p,
+                                                                   h->nranks == 1, -1, nullptr, AccTables{});
   h->launches++;
   CU(cudaGetLastError());
   std::vector<double> all((size_t)4 * h->nranks, 0.0);
@@ -1529,7 +1701,7 @@ int pf_norm(pf_handle h, const double *a_pp, double *result) {
   return 0;
 }
 
-int pf_centroid_stress(pf_handle h, int64_t iel, double e, double v, double *sigma6) {
+static int stress_at(pf_handle h, int64_t iel, const double *pt, double e, double v, double *sigma6) {
   int rc = need_device(h); if (rc) return rc;
   NEED(h->have_mesh && h->nodof == 3 && iel >= 0 && iel < h->nels, "needs an elastic mesh and a local element index");
   // gather xnew into eld (p121.f90:114) for this one element, then one point at the centroid
@@ -1552,6 +1724,7 @@ int pf_centroid_stress(pf_handle h, int64_t iel, double e, double v, double *sig
   }
   ElemTables T;
   if (fill_tables(nod, 1, e, v, 0, 0, 0, T)) return fail(h, 3, "unsupported nod");
+  if (pt && shape_der_at(nod, pt[0], pt[1], pt[2], T.der, nullptr)) return fail(h, 3, "unsupported nod");
   // jac, inverse, deriv with the same operation order as the kernels
   double jac[9], inv[9], deriv[60];
   for (int b = 0; b < 3; ++b)
@@ -1600,6 +1773,26 @@ int pf_centroid_stress(pf_handle h, int64_t iel, double e, double v, double *sig
     for (int c = 0; c < 6; ++c) s = s + T.dee[c * 6 + row] * eps[c];
     sigma6[row] = s;
   }
+  return 0;
+}
+
+int pf_centroid_stress(pf_handle h, int64_t iel, double e, double v, double *sigma6) {
+  return stress_at(h, iel, nullptr, e, v, sigma6);
+}
+
+int pf_point_stress(pf_handle h, int64_t iel, double xi, double eta, double zeta, double e, double v, double *sigma6) {
+  const double pt[3] = {xi, eta, zeta};
+  return stress_at(h, iel, pt, e, v, sigma6);
+}
+
+int pf_halo_transport(pf_handle h) {
+  if (!h || h->nranks == 1) return 0;
+  return (h->peer_ok && h->use_peer) ? 2 : 1;
+}
+
+int pf_get_last_solve_ms(pf_handle h, double *ms) {
+  if (!h || !ms) return 1;
+  *ms = h->last_ms;
   return 0;
 }
 

@@ -1014,4 +1014,52 @@ int pf_make_ggl(int ntot, int64_t nels_pp, const int32_t *g_g_pp, int64_t neq, i
   return 0;
 }
 
+
+/* Tables of the exchanges fused into the PCG kernels of the peer transport (device.cu: k_pupdate stores every new p
+ * value a peer's elements gather straight into that peer's halo segment; k_dot adds the received partial sums
+ * chunk by chunk).  Pure index work on the halo tables of pf_setup_mesh, kept here so that it is testable on CPU. */
+int pf_make_put_tables(int nranks, int64_t neq_pp, const int64_t *put_off /*nranks+1*/, const int32_t *put_slot,
+                       const int64_t *fwd_dst_off /*nranks*/, uint32_t *bits /*(neq_pp+31)/32 + 1, zeroed here*/,
+                       int32_t *slot0, uint32_t *ptr /*nput+1*/, int32_t *rank, int64_t *dst, int64_t *n_unique) {
+  if (nranks < 1 || neq_pp < 0 || !put_off || !bits || !ptr || !n_unique) return 1;
+  const int64_t nput = put_off[nranks];
+  struct Ent { int32_t eq0, rank; int64_t dst; };
+  std::vector<Ent> ents((size_t)nput);
+  for (int r = 0; r < nranks; ++r)
+    for (int64_t k = put_off[r]; k < put_off[r + 1]; ++k) {
+      const int64_t slot = put_slot[k];
+      if (slot < 1 || slot > neq_pp) return 2;
+      ents[(size_t)k] = {(int32_t)(slot - 1), r, fwd_dst_off[r] + (k - put_off[r])};
+    }
+  std::stable_sort(ents.begin(), ents.end(), [](const Ent &a, const Ent &b) { return a.eq0 < b.eq0; });
+  const int64_t nwords = (neq_pp + 31) / 32 + 1;
+  for (int64_t w = 0; w < nwords; ++w) bits[w] = 0u;
+  int64_t nu = 0;
+  for (int64_t k = 0; k < nput; ++k) {
+    if (k == 0 || ents[(size_t)k].eq0 != ents[(size_t)k - 1].eq0) { slot0[nu] = ents[(size_t)k].eq0; ptr[nu] = (uint32_t)k; ++nu; }
+    bits[ents[(size_t)k].eq0 >> 5] |= 1u << (ents[(size_t)k].eq0 & 31);
+    rank[k] = ents[(size_t)k].rank; dst[k] = ents[(size_t)k].dst;
+  }
+  ptr[nu] = (uint32_t)nput;
+  *n_unique = nu;
+  return 0;
+}
+
+/* accumulate entries per reduction chunk: entry k (owned slot acc_slot[k], ascending) belongs to chunk
+ * (acc_slot[k]-1)/chunk; chunk_ptr[c] = first entry of chunk c, chunk_ptr[nchunks] = nacc */
+int pf_make_acc_chunks(int64_t neq_pp, int chunk, int64_t nacc, const int32_t *acc_slot, uint32_t *chunk_ptr) {
+  if (chunk < 1 || neq_pp < 0 || nacc < 0 || !chunk_ptr) return 1;
+  const int64_t nchunks = (neq_pp + chunk - 1) / chunk;
+  int64_t k = 0;
+  for (int64_t c = 0; c < nchunks; ++c) {
+    chunk_ptr[c] = (uint32_t)k;
+    while (k < nacc && (int64_t)(acc_slot[k] - 1) / chunk == c) {
+      if (k > 0 && acc_slot[k] <= acc_slot[k - 1]) return 2;
+      ++k;
+    }
+  }
+  chunk_ptr[nchunks] = (uint32_t)k;
+  return k == nacc ? 0 : 2;
+}
+
 }  // extern "C"

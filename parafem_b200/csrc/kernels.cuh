@@ -28,6 +28,7 @@ struct State {
   int iters, limit;
   int done, converged;
   unsigned int ticket[4];  // "last block" counters, one per reducing kernel
+  int fault, pad_;         // 1: a peer rank did not arrive within kSpinTimeoutNs (the solve is abandoned, `done` raised)
 };
 
 // ----------------------------------------------------------------------------
@@ -81,6 +82,9 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
 // p values while the copy is in flight, waits on the slot's mbarrier, multiplies,
 // stores utemp and re-arms the slot.  Every byte of storkm is read once; lanes
 // hold two rows each so shared-memory reads are conflict-free 128-bit loads.
+struct PeerTable;
+__device__ __forceinline__ void warp_wait_fwd(PeerTable *T, const State *st);
+
 template <int NTOT, int EPT, int STAGES>
 struct MatvecCfg {
   static constexpr int kTileDoubles = EPT * NTOT * NTOT;
@@ -93,7 +97,7 @@ struct MatvecCfg {
 template <int NTOT, int EPT, int STAGES, bool GATHER>
 __global__ void __launch_bounds__(STAGES * 32, 1)
 k_matvec(const double *__restrict__ km, const int *__restrict__ ggl, const double *__restrict__ pvec,
-         double *__restrict__ utemp, long long nels, const State *st) {
+         double *__restrict__ utemp, long long nels, const State *st, PeerTable *T) {
   using Cfg = MatvecCfg<NTOT, EPT, STAGES>;
   if (st && *(volatile const int *)&st->done) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -127,14 +131,17 @@ k_matvec(const double *__restrict__ km, const int *__restrict__ ggl, const doubl
 
   long long t = t0 + w;
   if (t < t1 && lane == 0) issue(t);
+  // N ranks, peer transport: the owners' values of this iteration must have landed in my halo segment of pvec
+  // before the first gather; the first tile of element matrices is already on its way
+  if (GATHER && T) warp_wait_fwd(T, st);
   uint32_t phase = 0;
   constexpr int RP = NTOT / 2;  // row pairs per element
   for (; t < t1; t += STAGES) {
     const long long e0 = t * EPT;
     const int ne = (int)((nels - e0) < EPT ? (nels - e0) : EPT);
-    // gather (or copy) the tile's right-hand sides while the bulk copy flies
+    // gather (or copy) the tile's right-hand sides while the bulk copy flies (peer-written values: L2 loads)
     for (int s = lane; s < ne * NTOT; s += 32) {
-      if (GATHER) pm[s] = pvec[ggl[e0 * NTOT + s]];
+      if (GATHER) pm[s] = T ? __ldcg(pvec + ggl[e0 * NTOT + s]) : pvec[ggl[e0 * NTOT + s]];
       else pm[s] = pvec[e0 * NTOT + s];
     }
     __syncwarp();
@@ -192,7 +199,7 @@ struct MatvecSymCfg {
 template <int NTOT, int EPT, int STAGES, bool GATHER>
 __global__ void __launch_bounds__(STAGES * 32, 1)
 k_matvec_sym(const double *__restrict__ kp, const int *__restrict__ ggl, const double *__restrict__ pvec,
-             double *__restrict__ utemp, long long nels, const State *st) {
+             double *__restrict__ utemp, long long nels, const State *st, PeerTable *T) {
   using Cfg = MatvecSymCfg<NTOT, EPT, STAGES>;
   constexpr int P = SymCfg<NTOT>::kPacked, LPE = NTOT / 2, EPW = 32 / LPE;   // lanes per element, elements per warp pass
   static_assert(NTOT % 2 == 0 && LPE <= 32 && (EPT % EPW == 0 || EPW == 1), "tile shape");
@@ -234,12 +241,13 @@ k_matvec_sym(const double *__restrict__ kp, const int *__restrict__ ggl, const d
 
   long long t = t0 + w;
   if (t < t1 && lane == 0) issue(t);
+  if (GATHER && T) warp_wait_fwd(T, st);
   uint32_t phase = 0;
   for (; t < t1; t += STAGES) {
     const long long e0 = t * EPT;
     const int ne = (int)((nels - e0) < EPT ? (nels - e0) : EPT);
     for (int s = lane; s < ne * NTOT; s += 32) {
-      if (GATHER) pm[s] = pvec[ggl[e0 * NTOT + s]];
+      if (GATHER) pm[s] = T ? __ldcg(pvec + ggl[e0 * NTOT + s]) : pvec[ggl[e0 * NTOT + s]];
       else pm[s] = pvec[e0 * NTOT + s];
     }
     __syncwarp();
@@ -279,47 +287,6 @@ __global__ void k_gather(const int *__restrict__ ggl, const double *__restrict__
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) pmul[i] = p_ext[ggl[i]];
-}
-
-// ----------------------------------------------------------------------------
-// a9: deterministic scatter as a slot-centric gather.  csr_ptr/csr_pos list, for
-// every slot >= 1 of the local gather buffer, the positions e*ntot+k in utemp of
-// its contributions in ascending element order.  DIAG: read K_e(k,k) instead.
-// ----------------------------------------------------------------------------
-template <bool DIAG>
-__global__ void k_scatter(const unsigned int *__restrict__ csr_ptr, const unsigned int *__restrict__ csr_pos,
-                          const double *__restrict__ src, double *__restrict__ u_ext, long long nslots,
-                          int ntot, const State *st, int packed = 0) {
-  if (st && *(volatile const int *)&st->done) return;
-  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x + 1;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (; s < nslots; s += stride) {
-    const unsigned int a = csr_ptr[s], b = csr_ptr[s + 1];
-    double acc = 0.0;
-    if (DIAG) {
-      for (unsigned int k = a; k < b; ++k) {
-        const unsigned int pos = csr_pos[k];
-        const unsigned int e = pos / ntot, d = pos - e * ntot;
-        if (packed) acc = acc + src[(size_t)e * (ntot * (ntot + 1) / 2) + (size_t)d * ntot - d * (d - 1) / 2];
-        else acc = acc + src[(size_t)e * ntot * ntot + (size_t)d * ntot + d];
-      }
-    } else {
-      // kBatch contributions in flight at a time (index loads, then value loads), added in list order
-      constexpr int kBatch = 4;   // measured: 4 -> hex8 200^3 0.77 -> 0.58 ms, hex20 0.34 -> 0.32; 8 -> no gain on hex8
-      for (unsigned int k = a; k < b; k += kBatch) {
-        unsigned int pos[kBatch];
-        double v[kBatch];
-#pragma unroll
-        for (int i = 0; i < kBatch; ++i) pos[i] = (k + i < b) ? __ldg(csr_pos + k + i) : 0xffffffffu;
-#pragma unroll
-        for (int i = 0; i < kBatch; ++i) v[i] = (pos[i] != 0xffffffffu) ? src[pos[i]] : 0.0;
-#pragma unroll
-        for (int i = 0; i < kBatch; ++i)
-          if (pos[i] != 0xffffffffu) acc = acc + v[i];
-      }
-    }
-    u_ext[s] = acc;
-  }
 }
 
 // owner side of the reverse halo exchange: add received partial sums, sources in
@@ -380,9 +347,71 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+// Every wait on a peer is bounded: after kSpinTimeoutNs without the flag the rank raises State::fault and `done`
+// (every kernel of the solve then returns at once) and pf_pcg_run reports the failure -- a rank that died or left a
+// collective section early can no longer hang its peers for ever.
+constexpr unsigned long long kSpinTimeoutNs = 30ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsigned long long seq, const State *st) {
+  if (ld_acquire_sys(flag) >= seq) return true;
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned int n = 0;
+  while (ld_acquire_sys(flag) < seq) {
+    if ((++n & 255u) == 0 && globaltimer_ns() - t0 > kSpinTimeoutNs) {
+      if (st) { State *w = const_cast<State *>(st); w->fault = 1; w->done = 1; __threadfence(); }
+      return false;
+    }
+  }
+  return true;
+}
+// called by a whole warp: wait until every owner I gather from has stored this iteration's values into my halo
+// segment (its k_pupdate / k_halo_put_peer released fwd_flag[owner] = seq_fwd)
+__device__ __forceinline__ void warp_wait_fwd(PeerTable *T, const State *st) {
+  const int lane = threadIdx.x & 31, me = T->rank;
+  if (lane < T->nranks && lane != me && T->get_off[lane + 1] > T->get_off[lane])
+    spin_until(&T->sync[me]->fwd_flag[lane], T->seq_fwd, st);
+  __syncwarp();
+}
+// called by a whole block (>= nranks threads): the same for the ranks that send me partial sums
+__device__ __forceinline__ void block_wait_rev(PeerTable *T, const State *st) {
+  const int t = threadIdx.x, me = T->rank;
+  if (t < T->nranks && t != me && T->put_off[t + 1] > T->put_off[t])
+    spin_until(&T->sync[me]->rev_flag[t], T->seq_rev, st);
+  __syncthreads();
+}
+// every block of a kernel that stored into peer memory calls this once, after its stores: the last block to arrive
+// releases the flags (dir 0: forward, my owned values are in the peers' halo segments; dir 1: reverse, my partial
+// sums are in the owners' receive buffers) and advances the sequence number
+__device__ __forceinline__ void peer_release_flags(PeerTable *T, int dir) {
+  __shared__ int flag;
+  const unsigned long long seq = (dir == 0 ? T->seq_fwd : T->seq_rev) + 1;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(&T->ticket[dir], 1u);
+    flag = (prev == gridDim.x - 1);
+    if (flag) T->ticket[dir] = 0;
+  }
+  __syncthreads();
+  if (flag) {
+    __threadfence_system();
+    const int t = threadIdx.x, me = T->rank;
+    if (t < T->nranks && t != me) {
+      if (dir == 0 && T->put_off[t + 1] > T->put_off[t]) st_release_sys(&T->sync[t]->fwd_flag[me], seq);
+      if (dir == 1 && T->get_off[t + 1] > T->get_off[t]) st_release_sys(&T->sync[t]->rev_flag[me], seq);
+    }
+    __syncthreads();
+    if (t == 0) { if (dir == 0) T->seq_fwd = seq; else T->seq_rev = seq; }
+  }
+}
 // all threads of ONE block call; loc[4] in shared memory; result (rank-ordered sum, maxima)
 // valid in thread 0.  Writes my partials into every peer, waits for theirs.
-__device__ __forceinline__ void peer_allreduce(PeerTable *T, int which, const double *loc, double *out) {
+__device__ __forceinline__ void peer_allreduce(PeerTable *T, int which, const double *loc, double *out,
+                                               const State *st) {
   const unsigned long long seq = T->seq_red[which] + 1;
   const int t = threadIdx.x, me = T->rank, n = T->nranks;
   const int par = (int)(seq & 1);
@@ -391,7 +420,7 @@ __device__ __forceinline__ void peer_allreduce(PeerTable *T, int which, const do
     dst[0] = loc[0]; dst[1] = loc[1]; dst[2] = loc[2]; dst[3] = loc[3];
     __threadfence_system();
     st_release_sys(&T->sync[t]->red_flag[which][me], seq);
-    while (ld_acquire_sys(&T->sync[me]->red_flag[which][t]) < seq) { }
+    spin_until(&T->sync[me]->red_flag[which][t], seq, st);
   }
   __syncthreads();
   if (t == 0) {
@@ -413,57 +442,23 @@ __device__ __forceinline__ void peer_allreduce(PeerTable *T, int which, const do
 __global__ void k_halo_put_peer(PeerTable *T, const int *__restrict__ put_slot, const double *__restrict__ p_ext,
                                 long long nput, const State *st) {
   if (st && *(volatile const int *)&st->done) return;
-  __shared__ int flag;
-  const unsigned long long seq = T->seq_fwd + 1;
-  const int me = T->rank, n = T->nranks;
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nput; k += (long long)gridDim.x * blockDim.x) {
     int r = 0;
     while (k >= T->put_off[r + 1]) ++r;
     T->p_ext[r][T->fwd_dst_off[r] + (k - T->put_off[r])] = p_ext[put_slot[k]];
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int prev = atomicAdd(&T->ticket[0], 1u);
-    flag = (prev == gridDim.x - 1);
-    if (flag) T->ticket[0] = 0;
-  }
-  __syncthreads();
-  if (flag) {
-    __threadfence_system();
-    const int t = threadIdx.x;
-    if (t < n && t != me && T->put_off[t + 1] > T->put_off[t]) st_release_sys(&T->sync[t]->fwd_flag[me], seq);
-    __syncthreads();
-    if (t == 0) T->seq_fwd = seq;
-  }
+  peer_release_flags(T, 0);
 }
 // reverse: partial sums of remote equations straight into their owners' receive buffers
 __global__ void k_halo_rev_peer(PeerTable *T, const double *__restrict__ vec_ext, long long neq_pp, long long nhalo,
                                 const State *st) {
   if (st && *(volatile const int *)&st->done) return;
-  __shared__ int flag;
-  const unsigned long long seq = T->seq_rev + 1;
-  const int me = T->rank, n = T->nranks;
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nhalo; k += (long long)gridDim.x * blockDim.x) {
     int r = 0;
     while (k >= T->get_off[r + 1]) ++r;
     T->recv[r][T->rev_dst_off[r] + (k - T->get_off[r])] = vec_ext[1 + neq_pp + k];
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int prev = atomicAdd(&T->ticket[1], 1u);
-    flag = (prev == gridDim.x - 1);
-    if (flag) T->ticket[1] = 0;
-  }
-  __syncthreads();
-  if (flag) {
-    __threadfence_system();
-    const int t = threadIdx.x;
-    if (t < n && t != me && T->get_off[t + 1] > T->get_off[t]) st_release_sys(&T->sync[t]->rev_flag[me], seq);
-    __syncthreads();
-    if (t == 0) T->seq_rev = seq;
-  }
+  peer_release_flags(T, 1);
 }
 // dir 0: wait for the owners I gather from; dir 1: wait for the ranks that send me partial sums
 __global__ void k_halo_wait(PeerTable *T, int dir, const State *st) {
@@ -473,8 +468,59 @@ __global__ void k_halo_wait(PeerTable *T, int dir, const State *st) {
     const bool need = dir == 0 ? (T->get_off[t + 1] > T->get_off[t]) : (T->put_off[t + 1] > T->put_off[t]);
     const unsigned long long seq = dir == 0 ? T->seq_fwd : T->seq_rev;
     const unsigned long long *f = dir == 0 ? &T->sync[me]->fwd_flag[t] : &T->sync[me]->rev_flag[t];
-    if (need) while (ld_acquire_sys(f) < seq) { }
+    if (need) spin_until(f, seq, st);
   }
+}
+
+// ----------------------------------------------------------------------------
+// a9: deterministic scatter as a slot-centric gather.  csr_ptr/csr_pos list, for
+// every slot >= 1 of the local gather buffer, the positions e*ntot+k in utemp of
+// its contributions in ascending element order.  DIAG: read K_e(k,k) instead.
+// N ranks, peer transport (T != nullptr): the partial sum of a halo slot (an equation another rank owns) is also
+// stored straight into its owner's receive buffer, and the last block to finish releases the reverse-halo flags --
+// the reverse exchange of gather_scatter.f90:694-850 without a kernel of its own.
+// ----------------------------------------------------------------------------
+template <bool DIAG>
+__global__ void k_scatter(const unsigned int *__restrict__ csr_ptr, const unsigned int *__restrict__ csr_pos,
+                          const double *__restrict__ src, double *__restrict__ u_ext, long long nslots,
+                          int ntot, const State *st, int packed = 0, PeerTable *T = nullptr, long long neq_pp = 0) {
+  if (st && *(volatile const int *)&st->done) return;
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; s < nslots; s += stride) {
+    const unsigned int a = csr_ptr[s], b = csr_ptr[s + 1];
+    double acc = 0.0;
+    if (DIAG) {
+      for (unsigned int k = a; k < b; ++k) {
+        const unsigned int pos = csr_pos[k];
+        const unsigned int e = pos / ntot, d = pos - e * ntot;
+        if (packed) acc = acc + src[(size_t)e * (ntot * (ntot + 1) / 2) + (size_t)d * ntot - d * (d - 1) / 2];
+        else acc = acc + src[(size_t)e * ntot * ntot + (size_t)d * ntot + d];
+      }
+    } else {
+      // kBatch contributions in flight at a time (index loads, then value loads), added in list order
+      constexpr int kBatch = 4;   // measured: 4 -> hex8 200^3 0.77 -> 0.58 ms, hex20 0.34 -> 0.32; 8 -> no gain on hex8
+      for (unsigned int k = a; k < b; k += kBatch) {
+        unsigned int pos[kBatch];
+        double v[kBatch];
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) pos[i] = (k + i < b) ? __ldg(csr_pos + k + i) : 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) v[i] = (pos[i] != 0xffffffffu) ? src[pos[i]] : 0.0;
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i)
+          if (pos[i] != 0xffffffffu) acc = acc + v[i];
+      }
+    }
+    u_ext[s] = acc;
+    if (!DIAG && T && s > neq_pp) {
+      const long long k = s - 1 - neq_pp;      // halo slots are grouped by owner rank, ascending
+      int r = 0;
+      while (k >= T->get_off[r + 1]) ++r;
+      T->recv[r][T->rev_dst_off[r] + (k - T->get_off[r])] = acc;
+    }
+  }
+  if (!DIAG && T) peer_release_flags(T, 1);
 }
 
 // ----------------------------------------------------------------------------
@@ -622,7 +668,7 @@ k_pcg_init(const double *__restrict__ diag, const double *__restrict__ r, double
     }
     if (T) {
       __syncthreads();
-      peer_allreduce(T, 0, sh_loc, sh_out);
+      peer_allreduce(T, 0, sh_loc, sh_out, st);
       if (threadIdx.x == 0) finish_init(st, sh_out[0]);
     }
   }
@@ -636,23 +682,56 @@ __global__ void k_fixed_u(const int *__restrict__ fix_slot, const double *__rest
   if (i < n) u_ext[fix_slot[i]] = p_ext[fix_slot[i]] * store[i];
 }
 
-// pu = p.u over the owned equations
+// owner side of the reverse halo exchange folded into the p.u reduction (N ranks, peer transport): the accumulate
+// entries whose equation lies in chunk c are acc_chunk_ptr[c] .. acc_chunk_ptr[c+1] (acc_slot is ascending)
+struct AccTables {
+  const int *slot;                 // owned slots that receive partial sums, ascending
+  const unsigned int *ptr, *pos;   // per entry: positions in the receive buffer, source ranks ascending
+  const unsigned int *chunk_ptr;   // per reduction chunk: first entry
+  const double *recv;
+  double *u_ext;                   // slot-indexed
+};
+
+// pu = p.u over the owned equations.  ACC: the block first waits for the partial sums of the other ranks and adds
+// them to its chunk's equations (own partial sum first, then the sources in ascending rank order -- what
+// k_halo_accumulate does in the NCCL transport), then reduces.
+template <bool ACC>
 __global__ void __launch_bounds__(kRedThreads)
-k_dot(const double *__restrict__ a, const double *__restrict__ b, long long n, double *part, State *st,
-      int single_rank, int mode /*1: p.u epilogue, -1: plain dot into loc[0]*/, PeerTable *T) {
+k_dot(const double *__restrict__ a, const double *b_, long long n, double *part, State *st,
+      int single_rank, int mode /*1: p.u epilogue, -1: plain dot into loc[0]*/, PeerTable *T, AccTables A) {
   if (mode == 1 && *(volatile const int *)&st->done) return;
   __shared__ double sh[8];
   __shared__ double sh_loc[4], sh_out[3];
   __shared__ int flag;
   const long long nchunks = (n + kChunk - 1) / kChunk;
+  if (ACC) block_wait_rev(T, st);
   for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
     double acc = 0.0;
+    if (ACC) {
+      for (unsigned int k = A.chunk_ptr[c] + threadIdx.x; k < A.chunk_ptr[c + 1]; k += kRedThreads) {
+        const int slot = A.slot[k];
+        double v = A.u_ext[slot];
+        for (unsigned int q = A.ptr[k]; q < A.ptr[k + 1]; ++q) v = v + __ldcg(A.recv + A.pos[q]);   // peer-written: L2
+        A.u_ext[slot] = v;
+      }
+      __syncthreads();
+      const double *b = b_;          // same memory as A.u_ext + 1: plain (coherent) loads
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long long i = c * kChunk + 512 * k + 2 * threadIdx.x;
+      for (int k = 0; k < 4; ++k) {
+        const long long i = c * kChunk + 512 * k + 2 * threadIdx.x;
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
-        if (i + h < n) acc = acc + a[i + h] * b[i + h];
+        for (int h = 0; h < 2; ++h)
+          if (i + h < n) acc = acc + a[i + h] * b[i + h];
+      }
+    } else {
+      const double *__restrict__ b = b_;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long i = c * kChunk + 512 * k + 2 * threadIdx.x;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          if (i + h < n) acc = acc + a[i + h] * b[i + h];
+      }
     }
     const double s = block_tree(acc, sh);
     if (threadIdx.x == 0) part[c] = s;
@@ -666,7 +745,7 @@ k_dot(const double *__restrict__ a, const double *__restrict__ b, long long n, d
     }
     if (T && mode == 1) {
       __syncthreads();
-      peer_allreduce(T, 1, sh_loc, sh_out);
+      peer_allreduce(T, 1, sh_loc, sh_out, st);
       if (threadIdx.x == 0) finish_pu(st, sh_out[0]);
     }
   }
@@ -732,24 +811,55 @@ k_pcg_update(const double *__restrict__ diag, const double *__restrict__ p, cons
     }
     if (T) {
       __syncthreads();
-      peer_allreduce(T, 2, sh_loc, sh_out);
+      peer_allreduce(T, 2, sh_loc, sh_out, st);
       if (threadIdx.x == 0) finish_update(st, sh_out[0], sh_out[1], sh_out[2], ratio_hist);
     }
   }
 }
 
+// forward halo exchange folded into the p update (N ranks, peer transport): which owned equations are wanted by
+// peers (one bit each), and where each goes
+struct PutTables {
+  const unsigned int *bits;        // bit i of word i/32: owned equation i (0-based) is wanted by at least one peer
+  const int *slot0;                // those equations, ascending (0-based)
+  const unsigned int *ptr;         // per such equation: its destinations
+  const int *rank;                 // destination rank
+  const long long *dst;            // index in that rank's p_ext
+  int n;                           // number of such equations
+};
+__device__ __forceinline__ void put_one(PeerTable *T, const PutTables &P, long long i, double v) {
+  int lo = 0, hi = P.n - 1;
+  while (lo < hi) {                // slot0 holds i (its bit is set)
+    const int mid = (lo + hi) >> 1;
+    if (P.slot0[mid] < i) lo = mid + 1; else hi = mid;
+  }
+  for (unsigned int q = P.ptr[lo]; q < P.ptr[lo + 1]; ++q) T->p_ext[P.rank[q]][P.dst[q]] = v;
+}
+
 // p = d + p*beta (p121.f90:102), then the exit test of p121.f90:103.  `done` is raised by the last
 // block to finish, so no block of this kernel can observe it early and every later kernel sees it.
-__global__ void k_pupdate(const double *__restrict__ d, double *__restrict__ p, long long n, State *st) {
+// T != nullptr: every new p value a peer's elements need is stored into that peer's halo segment as it is formed,
+// and the last block releases the forward-halo flags: the gather's exchange of the NEXT iteration
+// (gather_scatter.f90:547-688) costs no kernel of its own.
+__global__ void k_pupdate(const double *__restrict__ d, double *__restrict__ p, long long n, State *st,
+                          PeerTable *T, PutTables P) {
   if (*(volatile const int *)&st->done) return;
   __shared__ int flag;
   const double beta = st->beta;
   long long i = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
   const long long stride = 2 * (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
-    p[i] = d[i] + p[i] * beta;
-    if (i + 1 < n) p[i + 1] = d[i + 1] + p[i + 1] * beta;
+    const double v0 = d[i] + p[i] * beta;
+    p[i] = v0;
+    double v1 = 0.0;
+    if (i + 1 < n) { v1 = d[i + 1] + p[i + 1] * beta; p[i + 1] = v1; }
+    if (T) {
+      const unsigned int w = P.bits[i >> 5] >> (i & 31);      // i is even: both bits sit in the same word
+      if (w & 1u) put_one(T, P, i, v0);
+      if ((w & 2u) && i + 1 < n) put_one(T, P, i + 1, v1);
+    }
   }
+  if (T) peer_release_flags(T, 0);
   if (last_block(&st->ticket[3], &flag) && threadIdx.x == 0) {
     if (st->converged || st->iters == st->limit) st->done = 1;
   }
@@ -1176,7 +1286,7 @@ __device__ __forceinline__ void mf_point_mid(const double *H, const double *inv,
 template <int NOD, bool GATHER, int GEOM, int WARPS, int UNR = 2>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, const double *__restrict__ pvec,
-           double *__restrict__ utemp, long long nels, const State *st, double *geom) {
+           double *__restrict__ utemp, long long nels, const State *st, double *geom, PeerTable *T) {
   using Cfg = MfCfg<NOD>;
   constexpr int NTOT = Cfg::NTOT, ROW = Cfg::kRow, KP = (NTOT + 31) / 32;
   static_assert(NOD % 2 == 0, "nodes are processed in pairs");
@@ -1214,6 +1324,7 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
       if (grp < ngroups) issue_idx(grp);
     }
     __syncwarp();
+    if (T) warp_wait_fwd(T, st);     // N ranks, peer transport: the owners' values are in my halo segment of pvec
   }
   for (; grp < ngroups; grp += gstride) {
     const long long e0 = grp * 32;
@@ -1305,7 +1416,7 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
 #pragma unroll
           for (int kp = 0; kp < KP; ++kp) {
             const int k = lane + 32 * kp;
-            if (GATHER) val[el][kp] = pvec[(k < NTOT) ? idxbuf[el * NTOT + k] : 0];
+            if (GATHER) val[el][kp] = T ? __ldcg(pvec + ((k < NTOT) ? idxbuf[el * NTOT + k] : 0)) : pvec[(k < NTOT) ? idxbuf[el * NTOT + k] : 0];
             else val[el][kp] = (k < NTOT) ? pvec[(e0 + el) * NTOT + k] : 0.0;
           }
 #pragma unroll
@@ -1318,7 +1429,7 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
       } else {
         for (int el = 0; el < ne; ++el)
           for (int k = lane; k < NTOT; k += 32)
-            rows[el * ROW + k] = GATHER ? pvec[idxbuf[el * NTOT + k]] : pvec[(e0 + el) * NTOT + k];
+            rows[el * ROW + k] = GATHER ? (T ? __ldcg(pvec + idxbuf[el * NTOT + k]) : pvec[idxbuf[el * NTOT + k]]) : pvec[(e0 + el) * NTOT + k];
       }
       __syncwarp();
       if (GATHER && lane == 0 && grp + gstride < ngroups) {

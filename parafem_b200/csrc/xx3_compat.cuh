@@ -29,7 +29,7 @@ cudaError_t xx3_ring(const double *mat, const double *rhs, double *lhs, long lon
   if (e != cudaSuccess) return e;
   const long long ntiles = (n_mat + EPT - 1) / EPT;
   const int grid = (int)std::max<long long>(1, std::min<long long>(sms, ntiles));
-  kern<<<grid, Cfg::kThreads, Cfg::kSmem>>>(mat, nullptr, rhs, lhs, n_mat, nullptr);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmem>>>(mat, nullptr, rhs, lhs, n_mat, nullptr, nullptr);
   return cudaGetLastError();
 }
 

@@ -222,6 +222,20 @@ class Solver:
         self._ck(lib().pf_centroid_stress(self._h, iel, e, v, ptr(out)), "pf_centroid_stress")
         return out
 
+    def point_stress(self, iel, xi, eta, zeta, e, v):
+        """sigma at a local point of element iel (0-based, local); see pf_point_stress."""
+        out = np.empty(6)
+        self._ck(lib().pf_point_stress(self._h, iel, xi, eta, zeta, e, v, ptr(out)), "pf_point_stress")
+        return out
+
+    def halo_transport(self):
+        return {0: "none", 1: "nccl", 2: "peer"}[lib().pf_halo_transport(self._h)]
+
+    def last_solve_ms(self):
+        ms = C.c_double()
+        self._ck(lib().pf_get_last_solve_ms(self._h, C.byref(ms)), "pf_get_last_solve_ms")
+        return ms.value
+
     # -- measurement -----------------------------------------------------------------
     def set_profile(self, on):
         self._ck(lib().pf_set_profile(self._h, int(on)), "pf_set_profile")

@@ -192,6 +192,33 @@ def test_p121_demo_golden(gpu, demo, golden):
     assert np.allclose(sig, oracle.centroid_stress(20, demo.g_coord_pp[0], eld, demo.e, demo.v), rtol=0, atol=1e-12)
 
 
+def test_p121_demo_golden_iteration_count_exactly(gpu, golden):
+    """p121_demo.res says 295.  On this deck the stopping ratio sits within 2 % of tol from iteration 295 to 297
+    (1.004e-5 ... 1.009e-5 at 295), so the count depends on rounding-level differences between legal executions:
+    with storkm_pp integrated element by element (what p121.f90 does) every summation order tried gives 297, with
+    full-precision and with file-rounded loads alike; with ONE element matrix shared by the congruent bricks (they
+    differ by 2e-14 relative) the blocked order gives exactly the golden's 295.  Both through the device path
+    (pf_set_storkm uploads a caller's storkm_pp) and both bit-equal to the oracle."""
+    p = host.cube_p121(20, 20, 20, 20, aa=.5, bb=.5, cc=.5, round_mode=0)        # full-precision generated deck
+    km = oracle.form_km_elastic(p.g_coord_pp, 20, 8, p.e, p.v)
+    assert np.abs(km - km[0]).max() <= 1e-13 * np.abs(km[0]).max()
+    shared = np.ascontiguousarray(np.broadcast_to(km[0], km.shape))
+    gpu.setup_mesh(p)
+    gpu.set_matrix_free(0); gpu.set_storkm_layout(0)
+    gpu.set_storkm(shared)
+    gpu.build_precon()
+    x, iters, conv = gpu.pcg_solve(p.r_pp, p.tol, p.limit)
+    gold = int(re.search(r"iterations to convergence was\s+(\d+)", open(os.path.join(golden, "p121_demo.res")).read()).group(1))
+    assert conv and iters == gold == 295
+    assert f"{x[0]:.3E}" == "-8.571E-01"                                          # golden prints -0.8571E+00
+    ref = oracle.pcg(shared, p.g_g_pp, p.neq, p.r_pp, p.tol, p.limit, npes=1, red_mode=1)
+    assert ref["iters"] == 295 and np.array_equal(x, ref["x"])
+    solver.setup_problem(gpu, p)                                                  # element-by-element storkm_pp
+    x2, iters2, conv2 = gpu.pcg_solve(p.r_pp, p.tol, p.limit)
+    hist = gpu.ratio_history()
+    assert conv2 and iters2 == 297 and 1.0e-5 < hist[294] < 1.02e-5
+
+
 def test_tight_tolerance_vs_sequential_reference_order(gpu):
     """Against the oracle in its *sequential* reduction order (a different legal summation
     order): with the solve driven to tol 1e-13 both land on the same solution within 1e-9."""

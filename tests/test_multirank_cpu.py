@@ -94,10 +94,68 @@ def _worker(rank, world, port, q, psize=None):
                 reqs.append(dist.irecv(bufs[r], r))
         for w in reqs:
             w.wait()
+        u_own = u_ext.copy()                              # own partial sums, before the peers' are added
         for r in sorted(bufs):
             np.add.at(u_ext, put_slot[r], bufs[r].numpy())
+        # ---- the same two exchanges as the FUSED kernels of the peer transport do them (device.cu: k_pupdate stores
+        # into the peers' halo segments through pf_make_put_tables; k_dot accumulates chunk by chunk through
+        # pf_make_acc_chunks): identical p_ext halo segments and identical owned sums
+        from parafem_b200._lib import lib, ptr
+        import ctypes as C
+        allc = np.array([[int(cnts[r][o]) for o in range(world)] for r in range(world)])   # allc[r][o]: r gathers from o
+        neq_pp_of = [host.calc_neq_pp(full.neq, world, r + 1)[0] for r in range(world)]
+        fwd_dst = np.array([1 + neq_pp_of[r] + allc[r][:rank].sum() for r in range(world)], np.int64)
+        put_flat = np.concatenate([np.zeros(0, np.int64)] + [ps for ps in put_slot if ps is not None]).astype(np.int32)
+        nput = int(put_off[-1])
+        bits = np.zeros((p.neq_pp + 31) // 32 + 1, np.uint32)
+        slot0, rnk = np.zeros(max(nput, 1), np.int32), np.zeros(max(nput, 1), np.int32)
+        pptr, dst = np.zeros(max(nput, 1) + 1, np.uint32), np.zeros(max(nput, 1), np.int64)
+        nu = C.c_int64()
+        assert lib().pf_make_put_tables(world, p.neq_pp, ptr(put_off.astype(np.int64)), ptr(put_flat), ptr(fwd_dst), ptr(bits),
+                                        ptr(slot0), ptr(pptr), ptr(rnk), ptr(dst), C.byref(nu)) == 0
+        msgs = []                                          # what k_pupdate's threads store into peer memory
+        for i in range(p.neq_pp):
+            if (bits[i >> 5] >> (i & 31)) & 1:
+                j = int(np.searchsorted(slot0[:nu.value], i))
+                assert slot0[j] == i
+                for jj in range(pptr[j], pptr[j + 1]):
+                    msgs.append((int(rnk[jj]), int(dst[jj]), float(p_ext[1 + i])))
+        assert len(msgs) == nput
+        everyone = [None] * world
+        dist.all_gather_object(everyone, msgs)
+        p_ext2 = np.zeros_like(p_ext)
+        p_ext2[1:1 + p.neq_pp] = p_ext[1:1 + p.neq_pp]
+        for src in everyone:
+            for r, d, v in src:
+                if r == rank:
+                    p_ext2[d] = v
+        ok_gather = ok_gather and np.array_equal(p_ext2, p_ext)
+        recv = np.zeros(max(nput, 1))                      # receive buffer: grouped by source rank ascending
+        for r, b in bufs.items():
+            recv[put_off[r]:put_off[r + 1]] = b.numpy()
+        pairs = sorted((int(sl), k) for k, sl in enumerate(put_flat))
+        aslot, aptr, apos = [], [], []
+        for k, (sl, pos) in enumerate(pairs):
+            if k == 0 or sl != pairs[k - 1][0]:
+                aslot.append(sl); aptr.append(k)
+            apos.append(pos)
+        aptr.append(len(pairs))
+        chunk = 64
+        nchunks = (p.neq_pp + chunk - 1) // chunk
+        cptr = np.zeros(nchunks + 1, np.uint32)
+        assert lib().pf_make_acc_chunks(p.neq_pp, chunk, len(aslot), ptr(np.array(aslot + [0], np.int32)), ptr(cptr)) == 0
+        u2 = u_own.copy()
+        for c in range(nchunks):                           # k_dot<ACC>: each block adds the entries of its chunk
+            for k in range(cptr[c], cptr[c + 1]):
+                assert (aslot[k] - 1) // chunk == c
+                v = u2[aslot[k]]
+                for qq in range(aptr[k], aptr[k + 1]):
+                    v = v + recv[apos[qq]]
+                u2[aslot[k]] = v
+        assert cptr[nchunks] == len(aslot)
+        ok_fused_rev = np.array_equal(u2[1:1 + p.neq_pp], u_ext[1:1 + p.neq_pp])
         u_ref = oracle.scatter(full.g_g_pp, oracle.matvec(km, oracle.gather(full.g_g_pp, pv)), full.neq, npes=world)
-        ok_scatter = np.array_equal(u_ext[1:1 + p.neq_pp], u_ref[lo:lo + p.neq_pp])
+        ok_scatter = np.array_equal(u_ext[1:1 + p.neq_pp], u_ref[lo:lo + p.neq_pp]) and ok_fused_rev
         # dot: blocked local partial, all-gather, ranks ascending
         part = torch.tensor([oracle.dot_blocked(pv[lo:lo + p.neq_pp], u_ref[lo:lo + p.neq_pp])], dtype=torch.float64)
         parts = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
