@@ -269,10 +269,13 @@ int pf_p121_loads(int nxe, int nze, int nod, double aa, double bb, int round_mod
  * freedoms in ascending node order": nf(nodof,nn), 0 = restrained.         */
 int pf_form_nf(int64_t nn, int nodof, int64_t nr, const int32_t *rest,
                int32_t *nf, int64_t *neq);
-int pf_find_g(int nod, int nodof, int64_t nels_pp, const int32_t *g_num_pp,
+/* Node numbers come from deck files: every routine that indexes with one takes nn and returns status 5 for a
+ * number outside 1..nn instead of reading out of bounds (the readers return 8 for the connectivity, pf_form_nf 2
+ * for the restraint list, pf_read_dat 4 for sizes no deck can have).                                      */
+int pf_find_g(int nod, int nodof, int64_t nels_pp, int64_t nn, const int32_t *g_num_pp,
               const int32_t *nf, int32_t *g_g_pp);
 /* load + scatter_noadd (loading.f90:36-142): r_pp(neq_pp) from nodal loads */
-int pf_load(int nodof, int64_t loaded_nodes, const int32_t *node, const double *val,
+int pf_load(int nodof, int64_t loaded_nodes, int64_t nn, const int32_t *node, const double *val,
             const int32_t *nf, int64_t ieq_start, int64_t neq_pp, double *r_pp);
 /* abaqus2sg (new_library.f90:3515-3682) for hexahedra, in place            */
 int pf_abaqus2sg(int nod, int64_t nels, int32_t *g_num);
@@ -304,7 +307,7 @@ int pf_read_lds(const char *job, int64_t loaded, int nodof, int32_t *node, doubl
 /* read_fixed (input.f90:2483-2564): node(fixed), sense(fixed) (1-based freedom of the node), valf(fixed) */
 int pf_read_fix(const char *job, int64_t fixed, int32_t *node, int32_t *sense, double *valf);
 /* g_coord_pp(nod,3,nels_pp) from g_coord(3,nn) and g_num_pp                */
-int pf_coords_pp(int nod, int64_t nels_pp, const int32_t *g_num_pp,
+int pf_coords_pp(int nod, int64_t nels_pp, int64_t nn, const int32_t *g_num_pp,
                  const double *g_coord, double *g_coord_pp);
 
 /* p12meshgen's output side for p121 (p12meshgen.f90:244-323): <job>.d/.bnd/.lds/.dat in the

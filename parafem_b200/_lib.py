@@ -93,8 +93,8 @@ SIGNATURES = {
     "pf_cube_rest": (c_int, [c_int, c_int, c_int, c_int, c_int, c_i64, vp]),
     "pf_p121_loads": (c_int, [c_int, c_int, c_int, c_dbl, c_dbl, c_int, vp, vp]),
     "pf_form_nf": (c_int, [c_i64, c_int, c_i64, vp, vp, P(c_i64)]),
-    "pf_find_g": (c_int, [c_int, c_int, c_i64, vp, vp, vp]),
-    "pf_load": (c_int, [c_int, c_i64, vp, vp, vp, c_i64, c_i64, vp]),
+    "pf_find_g": (c_int, [c_int, c_int, c_i64, c_i64, vp, vp, vp]),
+    "pf_load": (c_int, [c_int, c_i64, c_i64, vp, vp, vp, c_i64, c_i64, vp]),
     "pf_abaqus2sg": (c_int, [c_int, c_i64, vp]),
     "pf_read_dat": (c_int, [C.c_char_p, c_int, P(DeckInfo)]),
     "pf_read_d": (c_int, [C.c_char_p, c_i64, c_i64, c_int, vp, vp]),
@@ -103,7 +103,7 @@ SIGNATURES = {
     "pf_read_bnd": (c_int, [C.c_char_p, c_i64, c_int, vp]),
     "pf_read_lds": (c_int, [C.c_char_p, c_i64, c_int, vp, vp]),
     "pf_read_fix": (c_int, [C.c_char_p, c_i64, vp, vp, vp]),
-    "pf_coords_pp": (c_int, [c_int, c_i64, vp, vp, vp]),
+    "pf_coords_pp": (c_int, [c_int, c_i64, c_i64, vp, vp, vp]),
     "pf_write_deck_p121": (c_int, [C.c_char_p, c_int, c_i64, c_i64, c_i64, c_int, c_i64, c_dbl, c_dbl, c_dbl, c_int,
                                    vp, vp, vp, vp, vp]),
     "pf_write_deck_scalar": (c_int, [C.c_char_p, P(DeckInfo), vp, vp, vp]),

@@ -15,6 +15,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -133,6 +135,13 @@ struct pf_ctx {
   cudaGraphExec_t graph_exec = nullptr;
   int64_t epoch = 0, graph_epoch = -1, graph_launches = 0;
 
+  // per-handle (= per-device) launch state: kernels whose dynamic shared-memory opt-in was set on this device,
+  // resident blocks per SM of the reduction kernels, and the element tables this handle last uploaded to c_tab
+  std::set<const void *> smem_ok;
+  std::map<const void *, int> occ;
+  ElemTables tab;
+  bool have_tab = false;
+
   // profiling
   bool profile = false;
   struct Span { cudaEvent_t a, b; int kind; };
@@ -163,6 +172,42 @@ int fail(pf_handle h, int code, const char *fmt, ...) {
     if (r_ != ncclSuccess) return fail(h, 11, "%s: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
   } while (0)
 #define NEED(cond, msg) do { if (!(cond)) return fail(h, 2, "%s: %s", __func__, msg); } while (0)
+
+// c_tab is per DEVICE (one __constant__ copy each) while tables are per HANDLE: the handle that uploaded last is
+// remembered per device, and a handle whose kernels read c_tab at apply time (k_apply_mf: dee, weights) re-uploads
+// its own tables when another handle on the same device has formed matrices in between.
+pf_ctx *g_ctab_owner[64] = {nullptr};
+int upload_tables(pf_handle h, const ElemTables &T) {
+  CU(cudaMemcpyToSymbol(c_tab, &T, sizeof T));
+  h->tab = T; h->have_tab = true;
+  if (h->device >= 0 && h->device < 64) g_ctab_owner[h->device] = h;
+  return 0;
+}
+int ensure_tables(pf_handle h) {
+  if (!h->have_tab || (h->device >= 0 && h->device < 64 && g_ctab_owner[h->device] == h)) return 0;
+  CU(cudaStreamSynchronize(h->stream));
+  return upload_tables(h, h->tab);
+}
+// dynamic shared memory above 48 KB needs an opt-in per kernel and per device
+template <class K>
+int ensure_smem(pf_handle h, K kern, size_t bytes) {
+  const void *key = reinterpret_cast<const void *>(kern);
+  if (h->smem_ok.count(key)) return 0;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  h->smem_ok.insert(key);
+  return 0;
+}
+// resident blocks per SM of a kernel at `threads` threads (cached per handle)
+template <class K>
+int resident_blocks(pf_handle h, K kern, int threads, int fallback) {
+  const void *key = reinterpret_cast<const void *>(kern);
+  auto it = h->occ.find(key);
+  if (it != h->occ.end()) return it->second;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0) != cudaSuccess || per_sm < 1) per_sm = fallback;
+  h->occ[key] = per_sm;
+  return per_sm;
+}
 
 // ---- profiling spans: CUDA events on the solver stream around a group of launches ----
 struct Scope {
@@ -291,11 +336,7 @@ template <int NTOT, int EPT, int STAGES, bool GATHER>
 int launch_matvec_t(pf_handle h, const double *pvec, const State *st, PeerTable *T) {
   using Cfg = MatvecCfg<NTOT, EPT, STAGES>;
   auto kern = k_matvec<NTOT, EPT, STAGES, GATHER>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
-    attr_set = true;
-  }
+  if (int rc_ = ensure_smem(h, kern, Cfg::kSmem)) return rc_;
   const int64_t ntiles = (h->nels + EPT - 1) / EPT;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, ntiles));
   kern<<<grid, Cfg::kThreads, Cfg::kSmem, h->stream>>>(h->mat_override ? h->mat_override : h->km.p, h->ggl.p, pvec, h->utemp.p,
@@ -316,11 +357,7 @@ template <int NTOT, int EPT, int STAGES, bool GATHER>
 int launch_matvec_sym_t(pf_handle h, const double *pvec, const State *st, PeerTable *T) {
   using Cfg = MatvecSymCfg<NTOT, EPT, STAGES>;
   auto kern = k_matvec_sym<NTOT, EPT, STAGES, GATHER>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
-    attr_set = true;
-  }
+  if (int rc_ = ensure_smem(h, kern, Cfg::kSmem)) return rc_;
   const int64_t ntiles = (h->nels + EPT - 1) / EPT;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, ntiles));
   kern<<<grid, Cfg::kThreads, Cfg::kSmem, h->stream>>>(h->km.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st, T);
@@ -333,11 +370,7 @@ template <int NOD, bool GATHER, int GEOM, int UNR = 2>
 int launch_mf_t(pf_handle h, const double *pvec, const State *st, PeerTable *T = nullptr) {
   using Cfg = MfCfg<NOD>;
   auto kern = k_apply_mf<NOD, GATHER, GEOM, kMfWarps, UNR>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem(kMfWarps)));
-    attr_set = true;
-  }
+  if (int rc_ = ensure_smem(h, kern, Cfg::smem(kMfWarps))) return rc_;
   kern<<<mf_grid(h), kMfWarps * 32, Cfg::smem(kMfWarps), h->stream>>>(h->coord.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st,
                                                                       h->geom.p, T);
   h->launches++;
@@ -397,10 +430,7 @@ int launch_matvec(pf_handle h, const double *pvec, const State *st, PeerTable *T
 int launch_scatter(pf_handle h, const State *st, bool diag, double *dst, PeerTable *T = nullptr) {
   Scope sc(h, K_SCATTER);
   // grid-stride kernel: exactly one resident wave (k_scatter needs 30 registers: 8 blocks of 256 per SM)
-  static int per_sm = 0;
-  if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scatter<false>, 256, 0) != cudaSuccess || per_sm < 1))
-    per_sm = 8;
-  const int grid = grid_for(h, h->nslots, 256, per_sm);
+  const int grid = grid_for(h, h->nslots, 256, resident_blocks(h, k_scatter<false>, 256, 8));
   if (diag) k_scatter<true><<<grid, 256, 0, h->stream>>>(h->csr_ptr.p, h->csr_pos.p, h->km.p, dst, (long long)h->nslots, h->ntot, st, h->km_layout);
   else k_scatter<false><<<grid, 256, 0, h->stream>>>(h->csr_ptr.p, h->csr_pos.p, h->utemp.p, dst, (long long)h->nslots, h->ntot, st, 0, T,
                                                      (long long)h->neq_pp);
@@ -613,10 +643,7 @@ int combine_scalars(pf_handle h, int mode) {
 // partial wave would leave a tail); the reduction tree does not depend on the grid size
 template <class K>
 int vec_grid(pf_handle h, K kernel) {
-  static int per_sm = 0;   // one value per kernel (template instantiation); all devices of a box are the same part
-  if (per_sm == 0 &&
-      (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRedThreads, 0) != cudaSuccess || per_sm < 1))
-    per_sm = 4;
+  const int per_sm = resident_blocks(h, kernel, kRedThreads, 4);
   const int64_t nchunks = (h->neq_pp + kChunk - 1) / kChunk;
   return (int)std::max<int64_t>(1, std::min<int64_t>(nchunks, (int64_t)h->sm_count * per_sm));
 }
@@ -768,6 +795,7 @@ int pf_finalize(pf_handle h) {
   cudaStreamSynchronize(h->stream);
   collect_spans(h);
   for (auto e : h->pool) cudaEventDestroy(e);
+  if (h->device >= 0 && h->device < 64 && g_ctab_owner[h->device] == h) g_ctab_owner[h->device] = nullptr;
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->snap_pinned) cudaFreeHost(h->snap_pinned);
   for (auto e : h->snap_ev) if (e) cudaEventDestroy(e);
@@ -1073,7 +1101,7 @@ int pf_form_km_elastic(pf_handle h, double e, double v) {
   NEED(h->nod != 4 || (h->km_layout == 0 && !h->matrix_free), "tetrahedra: reference storkm layout, stored matrices only");
   ElemTables T;
   if (fill_tables(h->nod, h->nip, e, v, 0, 0, 0, T)) return fail(h, 3, "unsupported nod/nip");
-  CU(cudaMemcpyToSymbol(c_tab, &T, sizeof T));
+  if ((rc = upload_tables(h, T))) return rc;
   double *diag_only = nullptr;
   if (h->matrix_free) {
     // config E: storkm is never stored; only its diagonal is formed (for the preconditioner)
@@ -1134,7 +1162,7 @@ int pf_form_km_elastic_mat(pf_handle h, int np_types, const double *prop, const 
     if (fill_tables(h->nod, h->nip, prop[2 * m], prop[2 * m + 1], 0, 0, 0, T)) return fail(h, 3, "unsupported nod/nip");
     memcpy(&dees[(size_t)m * 36], T.dee, sizeof T.dee);
   }
-  CU(cudaMemcpyToSymbol(c_tab, &T, sizeof T));
+  if ((rc = upload_tables(h, T))) return rc;
   DevBuf<double> d_dee; DevBuf<int> d_etype;
   CU(d_dee.alloc(dees.size())); CU(d_etype.alloc((size_t)h->nels));
   CU(cudaMemcpy(d_dee.p, dees.data(), dees.size() * 8, cudaMemcpyHostToDevice));
@@ -1159,7 +1187,7 @@ int pf_form_kc_laplace(pf_handle h, double kx, double ky, double kz) {
   NEED(h->nod != 4 || h->km_layout == 0, "tetrahedra: reference storkm layout only");
   ElemTables T;
   if (fill_tables(h->nod, h->nip, 0, 0, kx, ky, kz, T)) return fail(h, 3, "unsupported nod/nip");
-  CU(cudaMemcpyToSymbol(c_tab, &T, sizeof T));
+  if ((rc = upload_tables(h, T))) return rc;
   if ((rc = alloc_km(h))) return rc;
   const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 32);
   if (h->nod == 8) k_form_kc_laplace<8><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, h->km_layout);
@@ -1179,7 +1207,7 @@ int pf_form_k_transient(pf_handle h, double kx, double ky, double kz, double rho
   ElemTables T;
   if (fill_tables(h->nod, h->nip, 0, 0, kx, ky, kz, T)) return fail(h, 3, "unsupported nod/nip");
   T.trans[0] = rho; T.trans[1] = cp; T.trans[2] = theta; T.trans[3] = dtim;
-  CU(cudaMemcpyToSymbol(c_tab, &T, sizeof T));
+  if ((rc = upload_tables(h, T))) return rc;
   if ((rc = alloc_km(h))) return rc;
   if (h->kb.n != h->km.n) CU(h->kb.alloc(h->km.n));
   const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 32);
@@ -1276,7 +1304,7 @@ int pf_form_k_explicit(pf_handle h, double kx, double ky, double kz, double dtim
   ElemTables T;
   if (fill_tables(h->nod, h->nip, 0, 0, kx, ky, kz, T)) return fail(h, 3, "unsupported nod/nip");
   T.trans[3] = dtim;
-  CU(cudaMemcpyToSymbol(c_tab, &T, sizeof T));
+  if ((rc = upload_tables(h, T))) return rc;
   if ((rc = alloc_km(h))) return rc;
   CU(h->diag_tmp.alloc((size_t)h->nels * h->ntot));
   const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 32);
@@ -1477,6 +1505,7 @@ int pf_pcg_load_rhs(pf_handle h, const double *r_pp) {
 int pf_pcg_run(pf_handle h, double tol, int limit, int *iters, int *converged, double *elapsed_ms) {
   int rc = need_device(h); if (rc) return rc;
   NEED(h->have_precon, "needs pf_build_precon");
+  if (h->matrix_free && (rc = ensure_tables(h))) return rc;
   NEED(limit >= 1, "limit must be >= 1");
   if (h->ratio_cap < limit) { CU(h->ratio_hist.alloc((size_t)limit)); h->ratio_cap = limit; h->epoch++; }
   State init; memset(&init, 0, sizeof init);
@@ -1619,6 +1648,7 @@ int pf_gather(pf_handle h, const double *p_pp, double *pmul_pp) {
 int pf_matvec(pf_handle h, const double *pmul_pp, double *utemp_pp) {
   int rc = need_device(h); if (rc) return rc;
   NEED(h->have_km, "needs element matrices");
+  if (h->matrix_free && (rc = ensure_tables(h))) return rc;
   const size_t n = (size_t)h->nels * h->ntot;
   DevBuf<double> pm;
   CU(pm.alloc(n));
@@ -1649,6 +1679,7 @@ int pf_scatter(pf_handle h, const double *utemp_pp, double *u_pp) {
 int pf_apply(pf_handle h, const double *p_pp, double *u_pp) {
   int rc = need_device(h); if (rc) return rc;
   NEED(h->have_km, "needs element matrices");
+  if (h->matrix_free && (rc = ensure_tables(h))) return rc;
   if ((rc = upload_owned(h, h->p_ext.p, p_pp))) return rc;
   const int nfixed = h->nfixed;
   if (!h->have_precon) h->nfixed = 0;

@@ -347,21 +347,26 @@ int pf_form_nf(int64_t nn, int nodof, int64_t nr, const int32_t *rest, int32_t *
   return 0;
 }
 
-int pf_find_g(int nod, int nodof, int64_t nels_pp, const int32_t *g_num_pp, const int32_t *nf,
+// status 5: a node number outside 1..nn (what a deck's .d / .lds / .fix files hold is never trusted as an index)
+int pf_find_g(int nod, int nodof, int64_t nels_pp, int64_t nn, const int32_t *g_num_pp, const int32_t *nf,
               int32_t *g_g_pp) {
   int ntot = nod * nodof;
-#pragma omp parallel for schedule(static)
+  int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
   for (int64_t e = 0; e < nels_pp; ++e)
     for (int m = 0; m < nod; ++m) {
       int64_t node = g_num_pp[e * nod + m];
+      if (node < 1 || node > nn) { bad |= 1; continue; }
       for (int k = 0; k < nodof; ++k) g_g_pp[e * ntot + m * nodof + k] = nf[(node - 1) * nodof + k];
     }
-  return 0;
+  return bad ? 5 : 0;
 }
 
-int pf_load(int nodof, int64_t loaded, const int32_t *node, const double *val, const int32_t *nf,
+int pf_load(int nodof, int64_t loaded, int64_t nn, const int32_t *node, const double *val, const int32_t *nf,
             int64_t ieq_start, int64_t neq_pp, double *r_pp) {
   for (int64_t i = 0; i < neq_pp; ++i) r_pp[i] = 0.;
+  for (int64_t i = 0; i < loaded; ++i)
+    if (node[i] < 1 || node[i] > nn) return 5;
   for (int64_t i = 0; i < loaded; ++i)
     for (int k = 0; k < nodof; ++k) {
       int64_t eq = nf[(int64_t)(node[i] - 1) * nodof + k];
@@ -435,6 +440,14 @@ int pf_read_dat(const char *job, int program, pf_deck_info *info) {
     info->nip = (int)v[6]; info->nod = (int)v[7]; info->loaded = (int64_t)v[8]; info->fixed = (int64_t)v[9];
     info->tol = v[10]; info->limit = (int)v[11];
   } else return 3;
+  // sizes a caller allocates from: finite, non-negative and inside the 32-bit node / element numbering
+  for (double x : v) if (!(x == x) || x > 9.0e18 || x < -9.0e18) return 4;
+  const int64_t lim = 2147483647LL;
+  if (info->nels < 1 || info->nels > lim || info->nn < 1 || info->nn > lim || info->nr < 0 || info->nr > info->nn ||
+      info->loaded < 0 || info->loaded > 3 * info->nn || info->fixed < 0 || info->fixed > 3 * info->nn ||
+      info->nod < 1 || info->nod > 20 || info->nip < 1 || info->nip > 27 || info->limit < 0 || info->np_types < 0 ||
+      info->nstep < 0)
+    return 4;
   return 0;
 }
 
@@ -623,7 +636,7 @@ int read_d_fast(const std::string &path, int64_t nn, int64_t nels, int nod, doub
         long long id, a, b, c, v;
         if (!take_int(q, e, id) || !take_int(q, e, a) || !take_int(q, e, b) || !take_int(q, e, c) || b != nod) return false;
         for (int m = 0; m < nod; ++m) {
-          if (!take_int(q, e, v)) return false;
+          if (!take_int(q, e, v) || v < 1 || v > nn) return false;     // the record reader reports which
           g_num[i * nod + m] = (int32_t)v;
         }
         if (!take_int(q, e, v)) return false;
@@ -657,6 +670,7 @@ int pf_read_d_mat(const char *job, int64_t nn, int64_t nels, int nod, double *g_
     if (fscanf(f, "%lld %lld %lld %lld", &id, &a, &b, &c) != 4 || b != nod) { rc = 5; break; }
     for (int m = 0; m < nod; ++m) {
       if (fscanf(f, "%lld", &v) != 1) { rc = 6; break; }
+      if (v < 1 || v > nn) { rc = 8; break; }                         // node number outside 1..nn
       g_num[e * nod + m] = (int32_t)v;
     }
     if (!rc && fscanf(f, "%lld", &v) != 1) rc = 7;  // material id
@@ -727,15 +741,17 @@ int pf_read_lds(const char *job, int64_t loaded, int nodof, int32_t *node, doubl
   return rc;
 }
 
-int pf_coords_pp(int nod, int64_t nels_pp, const int32_t *g_num_pp, const double *g_coord,
+int pf_coords_pp(int nod, int64_t nels_pp, int64_t nn, const int32_t *g_num_pp, const double *g_coord,
                  double *g_coord_pp) {
-#pragma omp parallel for schedule(static)
+  int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
   for (int64_t e = 0; e < nels_pp; ++e)
     for (int m = 0; m < nod; ++m) {
       int64_t node = g_num_pp[e * nod + m] - 1;
+      if (node < 0 || node >= nn) { bad |= 1; continue; }
       for (int d = 0; d < 3; ++d) g_coord_pp[e * nod * 3 + d * nod + m] = g_coord[node * 3 + d];
     }
-  return 0;
+  return bad ? 5 : 0;
 }
 
 // Fortran Ew.d edit descriptor (0.ddddE+xx), as dismsh_ensi_p's '(e12.5)' (output.f90:3050,3100)

@@ -84,7 +84,7 @@ int main(int argc, char **argv) {
     if (pf_read_d(job, nn, nels, nod, g_coord.data(), g_num.data())) { fprintf(stderr, "cannot read %s.d\n", job); return 2; }
     if (info.meshgen == 2) pf_abaqus2sg(nod, nels, g_num.data());
     g_coord_pp.resize(nels * nod * 3);
-    pf_coords_pp(nod, nels, g_num.data(), g_coord.data(), g_coord_pp.data());
+    if (pf_coords_pp(nod, nels, nn, g_num.data(), g_coord.data(), g_coord_pp.data())) { fprintf(stderr, "%s.d names a node outside 1..nn\n", job); return 2; }
     rest.assign(nr * 4, 0);
     if (pf_read_bnd(job, nr, nodof, rest.data())) { fprintf(stderr, "cannot read %s.bnd\n", job); return 2; }
     node.resize(loaded); val.resize(loaded * 3);
@@ -96,7 +96,7 @@ int main(int argc, char **argv) {
   const int ntot = nod * nodof;
   nf.resize(nn * nodof); g_g.resize(nels * ntot);
   if (pf_form_nf(nn, nodof, nr, rest.data(), nf.data(), &neq)) return 2;
-  pf_find_g(nod, nodof, nels, g_num.data(), nf.data(), g_g.data());
+  if (pf_find_g(nod, nodof, nels, nn, g_num.data(), nf.data(), g_g.data())) { fprintf(stderr, "connectivity names a node outside 1..nn\n"); return 2; }
   int64_t neq_pp, ieq_start;
   pf_calc_neq_pp(neq, 1, 1, &neq_pp, &ieq_start);
 
@@ -109,7 +109,7 @@ int main(int argc, char **argv) {
 
   // starting r (p121.f90:79-85)
   std::vector<double> r(neq_pp), x(neq_pp);
-  pf_load(nodof, loaded, node.data(), val.data(), nf.data(), ieq_start, neq_pp, r.data());
+  if (pf_load(nodof, loaded, nn, node.data(), val.data(), nf.data(), ieq_start, neq_pp, r.data())) { fprintf(stderr, "the load list names a node outside 1..nn\n"); return 2; }
   double q = 0.0;
   for (double t : r) q += t;
 

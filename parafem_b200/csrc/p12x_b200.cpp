@@ -59,7 +59,7 @@ int main(int argc, char **argv) {
   pf_cube_elements(n, n, nod, aa, aa, aa, 1, nels, round_mode, g_num.data(), g_coord_pp.data());
   if (pf_cube_rest(1, n, n, n, nod, nr, rest.data())) return 2;
   if (pf_form_nf(nn, nodof, nr, rest.data(), nf.data(), &neq)) return 2;     // rearrange_2 + find_g4
-  pf_find_g(nod, nodof, nels, g_num.data(), nf.data(), g_g.data());
+  if (pf_find_g(nod, nodof, nels, nn, g_num.data(), nf.data(), g_g.data())) { fprintf(stderr, "connectivity names a node outside 1..nn\n"); return 2; }
   int64_t neq_pp, ieq_start;
   pf_calc_neq_pp(neq, 1, 1, &neq_pp, &ieq_start);
   const double t_read = now() - t_start;

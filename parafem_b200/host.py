@@ -97,7 +97,7 @@ def _steer(nn, nodof, rest, g_num_pp, nod):
     check(lib().pf_form_nf(nn, nodof, nr, ptr(rest), ptr(nf), C.byref(neq)), what="pf_form_nf")
     nels_pp = g_num_pp.shape[0]
     g_g = np.empty((nels_pp, nod * nodof), np.int32)
-    check(lib().pf_find_g(nod, nodof, nels_pp, ptr(g_num_pp), ptr(nf), ptr(g_g)), what="pf_find_g")
+    check(lib().pf_find_g(nod, nodof, nels_pp, nn, ptr(g_num_pp), ptr(nf), ptr(g_g)), what="pf_find_g")
     return nf, g_g, neq.value
 
 
@@ -131,7 +131,7 @@ def cube_p121(nxe, nye, nze, nod=20, aa=None, bb=None, cc=None, e=100.0, v=0.3, 
     val = np.empty((loaded, 3), np.float64)
     check(L.pf_p121_loads(nxe, nze, nod, aa, bb, round_mode, ptr(node), ptr(val)), what="pf_p121_loads")
     r = np.empty(neq_pp, np.float64)
-    check(L.pf_load(3, loaded, ptr(node), ptr(val), ptr(nf), ieq_start, neq_pp, ptr(r)), what="pf_load")
+    check(L.pf_load(3, loaded, nn, ptr(node), ptr(val), ptr(nf), ieq_start, neq_pp, ptr(r)), what="pf_load")
     return Problem(121, nod, 3, nip, nels, nn, nr, neq, npes, numpe, nels_pp, iel_start, neq_pp, ieq_start,
                    g_num, g_coord, g_g, nf, r, e=e, v=v, tol=tol, limit=limit,
                    total_load=float(val[:, 2].sum()))
@@ -230,7 +230,7 @@ def read_deck_p121(job, npes=1, numpe=1):
         raise PfError("partitioner must be 1 (internal) or 2 (.psize)")
     g_num_pp = np.ascontiguousarray(g_num[iel_start - 1:iel_start - 1 + nels_pp])
     g_coord_pp = np.empty((nels_pp, 3, nod), np.float64)
-    check(L.pf_coords_pp(nod, nels_pp, ptr(g_num_pp), ptr(g_coord), ptr(g_coord_pp)), what="pf_coords_pp")
+    check(L.pf_coords_pp(nod, nels_pp, nn, ptr(g_num_pp), ptr(g_coord), ptr(g_coord_pp)), what="pf_coords_pp")
     rest = np.zeros((4, nr), np.int32)
     check(L.pf_read_bnd(job.encode(), nr, 3, ptr(rest)), what="pf_read_bnd")
     nf, g_g, neq = _steer(nn, 3, rest, g_num_pp, nod)
@@ -239,7 +239,7 @@ def read_deck_p121(job, npes=1, numpe=1):
     val = np.empty((loaded, 3), np.float64)
     check(L.pf_read_lds(job.encode(), loaded, 3, ptr(node), ptr(val)), what="pf_read_lds")
     r = np.empty(neq_pp, np.float64)
-    check(L.pf_load(3, loaded, ptr(node), ptr(val), ptr(nf), ieq_start, neq_pp, ptr(r)), what="pf_load")
+    check(L.pf_load(3, loaded, nn, ptr(node), ptr(val), ptr(nf), ieq_start, neq_pp, ptr(r)), what="pf_load")
     p = Problem(121, nod, 3, info.nip, nels, nn, nr, neq, npes, numpe, nels_pp, iel_start, neq_pp, ieq_start,
                 g_num_pp, g_coord_pp, g_g, nf, r, e=info.e, v=info.v, tol=info.tol, limit=info.limit,
                 total_load=float(val.sum()))
@@ -279,7 +279,7 @@ def read_deck_p123(job, npes=1, numpe=1, program=123):
     nels_pp, iel_start = read_psize(job, npes, numpe) if info.partitioner == 2 else calc_nels_pp(nels, npes, numpe)
     g_num_pp = np.ascontiguousarray(g_num[iel_start - 1:iel_start - 1 + nels_pp])
     g_coord_pp = np.empty((nels_pp, 3, nod), np.float64)
-    check(L.pf_coords_pp(nod, nels_pp, ptr(g_num_pp), ptr(g_coord), ptr(g_coord_pp)), what="pf_coords_pp")
+    check(L.pf_coords_pp(nod, nels_pp, nn, ptr(g_num_pp), ptr(g_coord), ptr(g_coord_pp)), what="pf_coords_pp")
     if nr > 0:
         rest = np.zeros((2, nr), np.int32)
         check(L.pf_read_bnd(job.encode(), nr, 1, ptr(rest)), what="pf_read_bnd")
@@ -303,6 +303,10 @@ def read_deck_p123(job, npes=1, numpe=1, program=123):
         sense = np.empty(info.fixed, np.int32)
         valf = np.empty(info.fixed, np.float64)
         check(L.pf_read_fix(job.encode(), info.fixed, ptr(node), ptr(sense), ptr(valf)), what="pf_read_fix")
+        if node.min() < 1 or node.max() > nn or sense.min() < 1 or sense.max() > nf.shape[1]:
+            raise PfError(f"{job}.fix names a node outside 1..{nn} or a freedom outside 1..{nf.shape[1]}")
+        if info.loaded and (eqn.min() < 1 or eqn.max() > neq):
+            raise PfError(f"{job}.lds names an equation outside 1..{neq}")
         eq = nf[node - 1, sense - 1]        # find_no2 (loading.f90:742-828): the equation of (node, sense)
         mine = (eq >= ieq_start) & (eq < ieq_start + neq_pp)
         no_f, val_f = np.ascontiguousarray(eq[mine]), np.ascontiguousarray(valf[mine])
@@ -339,7 +343,7 @@ def read_deck_xx2(job, npes=1, numpe=1):
     nels_pp, iel_start = read_psize(job, npes, numpe) if info.partitioner == 2 else calc_nels_pp(nels, npes, numpe)
     g_num_pp = np.ascontiguousarray(g_num[iel_start - 1:iel_start - 1 + nels_pp])
     g_coord_pp = np.empty((nels_pp, 3, nod), np.float64)
-    check(L.pf_coords_pp(nod, nels_pp, ptr(g_num_pp), ptr(g_coord), ptr(g_coord_pp)), what="pf_coords_pp")
+    check(L.pf_coords_pp(nod, nels_pp, nn, ptr(g_num_pp), ptr(g_coord), ptr(g_coord_pp)), what="pf_coords_pp")
     rest = np.zeros((4, nr), np.int32)
     check(L.pf_read_bnd(job.encode(), nr, 3, ptr(rest)), what="pf_read_bnd")
     prop = np.empty((info.np_types, 2), np.float64)
@@ -350,7 +354,7 @@ def read_deck_xx2(job, npes=1, numpe=1):
     val = np.empty((loaded, 3), np.float64)
     check(L.pf_read_lds(job.encode(), loaded, 3, ptr(node), ptr(val)), what="pf_read_lds")
     r = np.empty(neq_pp, np.float64)
-    check(L.pf_load(3, loaded, ptr(node), ptr(val), ptr(nf), ieq_start, neq_pp, ptr(r)), what="pf_load")
+    check(L.pf_load(3, loaded, nn, ptr(node), ptr(val), ptr(nf), ieq_start, neq_pp, ptr(r)), what="pf_load")
     p = Problem(121, nod, 3, info.nip, nels, nn, nr, neq, npes, numpe, nels_pp, iel_start, neq_pp, ieq_start,
                 g_num_pp, g_coord_pp, g_g, nf, r, tol=info.tol, limit=info.limit, total_load=float(val.sum()))
     p.prop = prop

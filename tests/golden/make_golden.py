@@ -97,7 +97,7 @@ def main():
     rest4 = np.zeros((2, nr4), np.int32)
     assert lib().pf_read_bnd(d124.encode(), nr4, 1, ptr(rest4)) == 0
     gcpp4 = np.empty((nels4, 3, nod4), np.float64)
-    assert lib().pf_coords_pp(nod4, nels4, ptr(gn4), ptr(gc4), ptr(gcpp4)) == 0
+    assert lib().pf_coords_pp(nod4, nels4, gc4.shape[0], ptr(gn4), ptr(gc4), ptr(gcpp4)) == 0
     # (+ 0.0: p124_demo.d prints the top face's -(is-1)*cc = -0.0 unsigned, p121_demo.d prints it signed)
     fsha = lambda path: hashlib.sha256(open(path, "rb").read()).hexdigest()
     files = {f"p124_demo{ext}": fsha(d124 + ext) for ext in (".d", ".bnd", ".dat", ".mat")}

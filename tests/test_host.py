@@ -388,3 +388,66 @@ def test_xx3_style_res_table(tmp_path, tiny, golden):
     kern = [l for l in out if l.startswith("  ")]
     assert len(out) == 27 and out.index(kern[0]) == out.index(gold[22]) + 1          # right under 'Solve equations'
     assert kern[0].startswith("  mat-vec (79 launches)") and kern[0][44:56] == "    0.012500"
+
+
+def test_deck_node_numbers_are_range_checked(tmp_path, tiny, golden):
+    """What a deck file holds is never used as an index unchecked: a connectivity, load or restraint
+    record naming a node outside 1..nn, or a .dat with sizes no deck can have, is a status code -- not an
+    out-of-bounds read."""
+    import shutil
+    from parafem_b200 import PfError
+    from parafem_b200._lib import lib, ptr
+    src = os.path.join(golden, "xx3-tiny")
+    good = host.read_deck_p121(src)
+    nn = good.nn
+
+    def variant(name, suffix, edit):
+        base = str(tmp_path / name)
+        for sfx in (".dat", ".d", ".bnd", ".lds"):
+            shutil.copy(src + sfx, base + sfx)
+        lines = open(base + suffix).read().splitlines()
+        edit(lines)
+        open(base + suffix, "w").write("\n".join(lines) + "\n")
+        return base
+
+    def bad_element(lines):
+        k = lines.index("*ELEMENTS") + 3
+        f = lines[k].split()
+        f[6] = str(nn + 7)                      # a node number past the end of the coordinate list
+        lines[k] = " ".join(f)
+    with pytest.raises(PfError):
+        host.read_deck_p121(variant("bad_d", ".d", bad_element))
+
+    def bad_load(lines):
+        f = lines[0].split()
+        f[0] = "0"
+        lines[0] = " ".join(f)
+    with pytest.raises(PfError):
+        host.read_deck_p121(variant("bad_lds", ".lds", bad_load))
+
+    def bad_rest(lines):
+        f = lines[2].split()
+        f[0] = str(nn + 1)
+        lines[2] = " ".join(f)
+    with pytest.raises(PfError):
+        host.read_deck_p121(variant("bad_bnd", ".bnd", bad_rest))
+
+    def bad_dat(lines):
+        for i, l in enumerate(lines):
+            f = l.split()
+            if len(f) >= 6 and f[0].isdigit() and int(f[0]) == good.nels:
+                f[1] = "-5"                     # nn
+                lines[i] = " ".join(f)
+                return
+        raise AssertionError("size line not found")
+    with pytest.raises(PfError):
+        host.read_deck_p121(variant("bad_dat", ".dat", bad_dat))
+    # the steering routines themselves
+    g_num = good.g_num_pp.copy()
+    g_num[3, 5] = nn + 1
+    g_g = np.empty_like(good.g_g_pp)
+    assert lib().pf_find_g(20, 3, good.nels_pp, nn, ptr(g_num), ptr(good.nf), ptr(g_g)) == 5
+    out = np.empty((good.nels_pp, 3, 20))
+    assert lib().pf_coords_pp(20, good.nels_pp, nn, ptr(g_num), ptr(np.zeros((nn, 3))), ptr(out)) == 5
+    r = np.empty(good.neq_pp)
+    assert lib().pf_load(3, 1, nn, ptr(np.array([nn + 1], np.int32)), ptr(np.ones(3)), ptr(good.nf), 1, good.neq_pp, ptr(r)) == 5
