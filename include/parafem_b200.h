@@ -178,6 +178,27 @@ int pf_form_k_explicit(pf_handle h, double kx, double ky, double kz, double dtim
 int pf_explicit_start(pf_handle h, double val0);
 int pf_explicit_steps(pf_handle h, int nsteps, double *elapsed_ms);
 
+/* --- p122: 3-D elasto-plasticity ------------------------
+ * programs/5th_ed/p122/p122.f90: Mohr-Coulomb solid, viscoplastic strain method.  The driver keeps its input
+ * section and output; the device holds storkm_pp, evpt_pp / tensor_pp (nst,nip,nels_pp) and every vector of the
+ * load-increment loop.
+ *   pf_plastic_begin      p122.f90:88-93 after pf_form_km_elastic(e,v) + pf_build_precon(fixed freedoms, 1e20):
+ *                         tensor_pp = totd_pp = oldis_pp = x_pp = 0, dt (returned).
+ *   pf_plastic_increment  one pass of load_increments, p122.f90:115-205: plastic iterations until checon_par on the
+ *                         displacement increment (plastol) or plasits; each one builds loads_pp (ld0_pp*qinc and /
+ *                         or store_pp*valf*qinc on the fixed freedoms of this rank, + bdylds_pp), r = loads - A*x,
+ *                         a PCG solve restarted from the current x (cjits, cjtol; fixed rows u = p*store on the
+ *                         first plastic iteration, 0 afterwards) and the Gauss-point update of elements_4 (invar,
+ *                         mocouf, mocouq, formm -- new_library.f90:1813-1916, 2364-2490, 85-198) whose body
+ *                         loads are scattered into bdylds_pp.  ld0_pp (neq_pp) may be NULL (no loaded nodes);
+ *                         valf_pp holds the values of this rank's fixed freedoms in the order given to
+ *                         pf_build_precon.
+ *   pf_plastic_get        totd_pp and tensor_pp(:,ig,iel) for the log lines of p122.f90:206-214.            */
+int pf_plastic_begin(pf_handle h, double phi, double c, double psi, double e, double v, double *dt);
+int pf_plastic_increment(pf_handle h, double qinc, const double *ld0_pp, const double *valf_pp, int plasits,
+                         double plastol, int cjits, double cjtol, int *plasiters, int *cjtot, double *elapsed_ms);
+int pf_plastic_get(pf_handle h, double *totd_pp, int64_t iel, int ig, double *tensor6);
+
 /* --- fine-grained entry points (kernel-level parity tests) --------------
  * Same argument meaning as the reference routines they replace:
  *   pf_gather  = gather(p_pp,pmul_pp)            gather_scatter.f90:547-688

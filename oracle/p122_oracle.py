@@ -1,5 +1,5 @@
-"""CPU oracle for program p122 (3-D elasto-plasticity, Mohr-Coulomb, viscoplastic strain method, PCG) --
-PREPARATION FOR THE NEXT ROUND: the device side of p122 is not built yet.
+"""CPU oracle for program p122 (3-D elasto-plasticity, Mohr-Coulomb, viscoplastic strain method, PCG); the device
+side is pf_plastic_begin / pf_plastic_increment (tests/test_gpu_plastic.py).
 
 TEST INFRASTRUCTURE ONLY.  Restates programs/5th_ed/p122/p122.f90:66-233 with numpy (the element integrals
 vectorised over elements and Gauss points) on top of the C oracle's storkm / gather-matvec-scatter, and the
@@ -11,7 +11,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import _f64, _i32, _p, apply, form_km_elastic, lib, scatter
+from . import _f64, _i32, _p, apply, dot_blocked, form_km_elastic, lib, scatter
 
 
 def _bee_detw(g_coord_pp, nip=8):
@@ -114,10 +114,13 @@ def _checon(new, old, tol):
 
 
 def p122(g_coord_pp, g_g_pp, neq, phi, c, psi, e, v, qinc, plasits, cjits, plastol, cjtol, no_f=None, valf=None, ld0=None,
-         npes=1, penalty=1e20, c_elements=True):
+         npes=1, penalty=1e20, c_elements=True, red_mode=0):
     """-> list of dict(disp1 = totd(1), sigma = tensor(:,1,1), cjtot, plasiters) per load increment, and totd.
     c_elements: the Gauss-point update through orc_p122_elements (pf_oracle.c: the reference's loop with defined
-    summation orders -- what a device kernel will be held to); False: the vectorised numpy form of the same."""
+    summation orders -- what the device kernel is held to); False: the vectorised numpy form of the same.
+    red_mode 1: DOT_PRODUCT_P through the fixed blocked tree of the CUDA kernels (orc_dot_blocked) instead of numpy's
+    dot -- another legal summation order, and the one a GPU-vs-oracle comparison needs."""
+    dot = (lambda a, b: float(dot_blocked(a, b))) if red_mode else (lambda a, b: float(np.dot(a, b)))
     g_g = _i32(g_g_pp)
     nels, ntot = g_g.shape
     km = form_km_elastic(g_coord_pp, ntot // 3, 8, e, v)
@@ -162,12 +165,12 @@ def p122(g_coord_pp, g_g_pp, neq, phi, c, psi, e, v, qinc, plasits, cjits, plast
                 u = apply(km, g_g, neq, p, npes)
                 if nfix:
                     u[no_f] = p[no_f] * store if plasiters == 1 else 0.0
-                up = float(np.dot(r, d))
-                alpha = up / float(np.dot(p, u))
+                up = dot(r, d)
+                alpha = up / dot(p, u)
                 xnew = x + p * alpha
                 r = r - u * alpha
                 d = diag * r
-                beta = float(np.dot(r, d)) / up
+                beta = dot(r, d) / up
                 p = d + p * beta
                 if _checon(xnew, x, cjtol) or cjiters == cjits:
                     break

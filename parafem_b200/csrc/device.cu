@@ -126,10 +126,16 @@ struct pf_ctx {
   int ratio_cap = 0, last_iters = 0;
   double last_ms = 0.0;   // device time of the last pf_pcg_run loop (CUDA events on the solver stream)
 
-  // p123 fixed freedoms
+  // p123 fixed freedoms; fixed_mode 1 (p122 after the first plastic iteration): u(j) = 0 instead of p(j)*store
+  int fixed_mode = 0;
   int nfixed = 0;
   DevBuf<int> fix_slot;
   DevBuf<double> store;
+
+  // p122 (elasto-plasticity): viscoplastic strains and stresses of every Gauss point, load-increment vectors
+  bool plastic = false;
+  PlasticParams pl_par;
+  DevBuf<double> evpt, tensor, bdylds, oldis, totd, loads, ld0, valf;
 
   // one PCG iteration captured as a CUDA graph (single rank; re-captured when the problem changes)
   cudaGraphExec_t graph_exec = nullptr;
@@ -656,7 +662,7 @@ int apply_operator(pf_handle h, const State *st, bool peer = false) {
   if ((rc = launch_scatter(h, st, false, h->u_ext.p))) return rc;
   if ((rc = halo_reverse(h, h->u_ext.p, st, peer))) return rc;
   if (h->nfixed > 0) {
-    k_fixed_u<<<(h->nfixed + 255) / 256, 256, 0, h->stream>>>(h->fix_slot.p, h->store.p, h->p_ext.p, h->u_ext.p, h->nfixed, st);
+    k_fixed_u<<<(h->nfixed + 255) / 256, 256, 0, h->stream>>>(h->fix_slot.p, h->store.p, h->p_ext.p, h->u_ext.p, h->nfixed, st, h->fixed_mode);
     h->launches++;
   }
   return 0;
@@ -702,7 +708,7 @@ int one_iteration(pf_handle h) {
     if (h->nfixed > 0) {   // owned rows only; the partial sums of others for these rows are overridden as well
       k_halo_wait<<<1, 32, 0, h->stream>>>(T, 1, st);
       if (h->nacc > 0) k_halo_accumulate<<<(h->nacc + 255) / 256, 256, 0, h->stream>>>(h->acc_slot.p, h->acc_ptr.p, h->acc_pos.p, h->recvbuf.p, h->u_ext.p, h->nacc, st);
-      k_fixed_u<<<(h->nfixed + 255) / 256, 256, 0, h->stream>>>(h->fix_slot.p, h->store.p, h->p_ext.p, h->u_ext.p, h->nfixed, st);
+      k_fixed_u<<<(h->nfixed + 255) / 256, 256, 0, h->stream>>>(h->fix_slot.p, h->store.p, h->p_ext.p, h->u_ext.p, h->nfixed, st, h->fixed_mode);
       h->launches += 2 + (h->nacc > 0);
     }
   } else if ((rc = apply_operator(h, st, false))) return rc;
@@ -799,6 +805,7 @@ int pf_finalize(pf_handle h) {
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->snap_pinned) cudaFreeHost(h->snap_pinned);
   for (auto e : h->snap_ev) if (e) cudaEventDestroy(e);
+  h->evpt.release(); h->tensor.release(); h->bdylds.release(); h->oldis.release(); h->totd.release(); h->loads.release(); h->ld0.release(); h->valf.release();
   h->put_bits.release(); h->pk_ptr.release(); h->acc_chunk_ptr.release(); h->pk_slot0.release(); h->pk_rank.release(); h->pk_dst.release();
   close_imports(h);
   if (h->comm) {
@@ -951,7 +958,7 @@ int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp, con
     h->nels = nels_pp; h->neq = neq; h->ieq_start = ieq_start; h->neq_pp = neq_pp;
     h->have_mesh = false; h->have_km = h->have_precon = false;
     h->transient = h->transient_first = false; h->mat_override = nullptr; h->kb.release();
-    h->explicit_ = false;
+    h->explicit_ = false; h->plastic = false; h->fixed_mode = 0;
     h->epoch++;                                   // a captured iteration graph of the previous mesh is stale
 
     // gather table (make_ggl rebuilt from g_g_pp)
@@ -1370,6 +1377,146 @@ int pf_explicit_steps(pf_handle h, int nsteps, double *elapsed_ms) {
   return 0;
 }
 
+static int pcg_run_impl(pf_handle h, double tol, int limit, int *iters, int *converged, double *elapsed_ms, int keep_x);
+
+// ---- p122: 3-D elasto-plasticity, Mohr-Coulomb, viscoplastic strain method ----
+// pf_plastic_begin after pf_form_km_elastic(e, v) + pf_build_precon: zero stresses / totals (p122.f90:88-91), the
+// critical time step (:92-93), angle constants from the host's libm.
+int pf_plastic_begin(pf_handle h, double phi, double c, double psi, double e, double v, double *dt_out) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_precon && h->nodof == 3 && !h->matrix_free && h->km_layout == 0 && h->nip == 8 && (h->nod == 8 || h->nod == 20),
+       "needs pf_form_km_elastic (hexahedra, nip = 8, reference storkm layout) and pf_build_precon");
+  const double pi = std::acos(-1.0);
+  const double snph = std::sin(phi * pi / 180.0);                                   // p122.f90:91
+  const double dt = 4.0 * (1.0 + v) * (1.0 - 2.0 * v) / (e * (1.0 - 2.0 * v + snph * snph));
+  const double phir = phi * 4.0 * std::atan(1.0) / 180.0, psir = psi * 4.0 * std::atan(1.0) / 180.0;   // mocouf / mocouq
+  h->pl_par = PlasticParams{std::sin(phir), std::cos(phir), c, std::sin(psir), dt};
+  const size_t ng = (size_t)h->nels * h->nip * 6, nq = (size_t)std::max<int64_t>(h->neq_pp, 1);
+  CU(h->evpt.alloc(ng)); CU(h->tensor.alloc(ng));
+  CU(h->bdylds.alloc(nq)); CU(h->oldis.alloc(nq)); CU(h->totd.alloc(nq)); CU(h->loads.alloc(nq));
+  CU(cudaMemsetAsync(h->tensor.p, 0, ng * 8, h->stream)); CU(cudaMemsetAsync(h->evpt.p, 0, ng * 8, h->stream));
+  CU(cudaMemsetAsync(h->oldis.p, 0, nq * 8, h->stream)); CU(cudaMemsetAsync(h->totd.p, 0, nq * 8, h->stream));
+  CU(cudaMemsetAsync(h->x.p, 0, nq * 8, h->stream)); CU(cudaMemsetAsync(h->bdylds.p, 0, nq * 8, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->plastic = true;
+  if (dt_out) *dt_out = dt;
+  return 0;
+}
+
+// One pass of load_increments (p122.f90:115-205) on the device: the plastic iteration loop, each iteration a PCG
+// solve restarted from the current x and a Gauss-point stress update; the host sees two scalars per plastic iteration.
+int pf_plastic_increment(pf_handle h, double qinc, const double *ld0_pp, const double *valf_pp, int plasits,
+                         double plastol, int cjits, double cjtol, int *plasiters_out, int *cjtot_out, double *elapsed_ms) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->plastic, "needs pf_plastic_begin");
+  NEED(plasits >= 1 && cjits >= 1, "plasits and cjits must be >= 1");
+  NEED(h->nfixed == 0 || valf_pp, "fixed freedoms were declared in pf_build_precon: valf_pp is required");
+  if ((rc = ensure_tables(h))) return rc;
+  const long long n = h->neq_pp;
+  const int g = grid_for(h, std::max<long long>(n, 1), 256);
+  EventPair ev;
+  CU(ev.create());
+  CU(cudaEventRecord(ev.a, h->stream));
+  const double *ld0 = nullptr;
+  if (ld0_pp) {
+    CU(h->ld0.alloc((size_t)std::max<long long>(n, 1)));
+    CU(cudaMemcpyAsync(h->ld0.p, ld0_pp, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    ld0 = h->ld0.p;
+  }
+  if (h->nfixed > 0) {
+    CU(h->valf.alloc((size_t)h->nfixed));
+    CU(cudaMemcpyAsync(h->valf.p, valf_pp, (size_t)h->nfixed * 8, cudaMemcpyHostToDevice, h->stream));
+  }
+  // plasiters = 0; bdylds_pp = zero; evpt_pp = zero; cjtot = 0   (p122.f90:116)
+  CU(cudaMemsetAsync(h->bdylds.p, 0, (size_t)std::max<long long>(n, 1) * 8, h->stream));
+  CU(cudaMemsetAsync(h->evpt.p, 0, h->evpt.bytes(), h->stream));
+  int plasiters = 0, cjtot = 0;
+  const int nfixed = h->nfixed;
+  for (;;) {
+    ++plasiters;
+    // loads (p122.f90:119-138)
+    if (plasiters == 1) {
+      k_plastic_loads<<<g, 256, 0, h->stream>>>(h->loads.p, nullptr, h->bdylds.p, qinc, 0, n);
+      if (nfixed > 0) k_plastic_fixed<<<(nfixed + 255) / 256, 256, 0, h->stream>>>(h->fix_slot.p, h->store.p, h->valf.p, h->loads.p - 1, qinc, nfixed, 0);
+      if (ld0) k_plastic_loads<<<g, 256, 0, h->stream>>>(h->loads.p, ld0, h->bdylds.p, qinc, 1, n);
+    } else {
+      k_plastic_loads<<<g, 256, 0, h->stream>>>(h->loads.p, ld0, h->bdylds.p, qinc, 1, n);
+      if (nfixed > 0) k_plastic_fixed<<<(nfixed + 255) / 256, 256, 0, h->stream>>>(h->fix_slot.p, h->store.p, h->valf.p, h->loads.p - 1, qinc, nfixed, 1);
+    }
+    h->launches += 1 + (nfixed > 0) + (plasiters == 1 && ld0);
+    // r = loads - A*x   (:139-145); no fixed-freedom fix-up on this product
+    CU(cudaMemcpyAsync(h->p_ext.p + 1, h->x.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    h->nfixed = 0;
+    rc = apply_operator(h, nullptr);
+    h->nfixed = nfixed;
+    if (rc) return rc;
+    k_vsub<<<g, 256, 0, h->stream>>>(h->r.p, h->loads.p, h->u_ext.p + 1, n);
+    h->launches++;
+    // PCG from the current x; fixed rows: u = p*store on the first plastic iteration, 0 afterwards (:154-160)
+    const int mode = plasiters == 1 ? 0 : 1;
+    if (mode != h->fixed_mode) { h->fixed_mode = mode; h->epoch++; }
+    int cjiters = 0, cjconv = 0;
+    rc = pcg_run_impl(h, cjtol, cjits, &cjiters, &cjconv, nullptr, 1);
+    if (rc) { h->fixed_mode = 0; h->epoch++; return rc; }
+    cjtot += cjiters;
+    // loads = xnew; checon_par(loads, plastol, plastic_converged, oldis)   (:171-174)
+    k_checon<<<vec_grid(h, k_checon), kRedThreads, 0, h->stream>>>(h->x.p, h->oldis.p, n, h->part.p, h->state.p);
+    h->launches++;
+    std::vector<double> all((size_t)4 * h->nranks, 0.0);
+    if (h->nranks > 1) {
+      NC(g_nccl.AllGather(h->state.p->loc, h->gath.p, 4, ncclDouble, h->comm, h->stream));
+      CU(cudaMemcpyAsync(all.data(), h->gath.p, all.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+      CU(cudaMemcpyAsync(all.data(), h->state.p->loc, 4 * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    double maxloads = 0.0, maxdiff = 0.0;
+    for (int r = 0; r < h->nranks; ++r) { maxloads = std::max(maxloads, all[(size_t)4 * r + 1]); maxdiff = std::max(maxdiff, all[(size_t)4 * r + 2]); }
+    bool conv = (maxdiff / maxloads) <= plastol;
+    if (plasiters == 1) conv = false;
+    const int last = conv || plasiters == plasits;
+    if (last) CU(cudaMemsetAsync(h->bdylds.p, 0, (size_t)std::max<long long>(n, 1) * 8, h->stream));
+    // gather(loads) -> elements_4 -> scatter adds into bdylds   (:176-203)
+    CU(cudaMemcpyAsync(h->p_ext.p + 1, h->x.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    if ((rc = halo_forward(h, h->p_ext.p, nullptr))) return rc;
+    const int ge = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 16);
+    if (h->nod == 20) k_p122_elements<20><<<ge, 64, 0, h->stream>>>(h->coord.p, h->ggl.p, h->p_ext.p, h->evpt.p, h->tensor.p, h->utemp.p, (long long)h->nels, h->pl_par, last);
+    else k_p122_elements<8><<<ge, 64, 0, h->stream>>>(h->coord.p, h->ggl.p, h->p_ext.p, h->evpt.p, h->tensor.p, h->utemp.p, (long long)h->nels, h->pl_par, last);
+    h->launches++;
+    CU(cudaGetLastError());
+    if ((rc = launch_scatter(h, nullptr, false, h->u_ext.p))) return rc;
+    if ((rc = halo_reverse(h, h->u_ext.p, nullptr))) return rc;
+    k_vadd<<<g, 256, 0, h->stream>>>(h->bdylds.p, h->bdylds.p, h->u_ext.p + 1, n);
+    h->launches++;
+    if (last) break;
+  }
+  // totd = totd + loads   (:205)
+  k_vadd<<<g, 256, 0, h->stream>>>(h->totd.p, h->totd.p, h->x.p, n);
+  h->launches++;
+  h->fixed_mode = 0; h->epoch++;
+  CU(cudaEventRecord(ev.b, h->stream));
+  CU(cudaEventSynchronize(ev.b));
+  CU(cudaGetLastError());
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, ev.a, ev.b));
+  if (plasiters_out) *plasiters_out = plasiters;
+  if (cjtot_out) *cjtot_out = cjtot;
+  if (elapsed_ms) *elapsed_ms = ms;
+  return 0;
+}
+
+// totd_pp (neq_pp, may be NULL) and the stress tensor_pp(:,ig,iel) of one Gauss point (local 0-based; may be NULL)
+int pf_plastic_get(pf_handle h, double *totd_pp, int64_t iel, int ig, double *tensor6) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->plastic, "needs pf_plastic_begin");
+  if (totd_pp) CU(cudaMemcpy(totd_pp, h->totd.p, (size_t)h->neq_pp * 8, cudaMemcpyDeviceToHost));
+  if (tensor6) {
+    NEED(iel >= 0 && iel < h->nels && ig >= 0 && ig < h->nip, "element / Gauss point outside the local range");
+    CU(cudaMemcpy(tensor6, h->tensor.p + ((size_t)iel * h->nip + ig) * 6, 48, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
 int pf_set_storkm(pf_handle h, const double *storkm_pp) {
   int rc = need_device(h); if (rc) return rc;
   NEED(h->have_mesh && storkm_pp, "needs pf_setup_mesh");
@@ -1502,7 +1649,14 @@ int pf_pcg_load_rhs(pf_handle h, const double *r_pp) {
   return 0;
 }
 
+static int pcg_run_impl(pf_handle h, double tol, int limit, int *iters, int *converged, double *elapsed_ms, int keep_x);
+
 int pf_pcg_run(pf_handle h, double tol, int limit, int *iters, int *converged, double *elapsed_ms) {
+  return pcg_run_impl(h, tol, limit, iters, converged, elapsed_ms, 0);
+}
+
+// keep_x: the solve starts from the x of the previous one and h->r already holds loads - A*x (p122.f90:139-146)
+static int pcg_run_impl(pf_handle h, double tol, int limit, int *iters, int *converged, double *elapsed_ms, int keep_x) {
   int rc = need_device(h); if (rc) return rc;
   NEED(h->have_precon, "needs pf_build_precon");
   if (h->matrix_free && (rc = ensure_tables(h))) return rc;
@@ -1514,7 +1668,7 @@ int pf_pcg_run(pf_handle h, double tol, int limit, int *iters, int *converged, d
   // d = M^-1 r, p = d, x = 0 (p121.f90:87; p123.f90:132)
   k_pcg_init<<<vec_grid(h, k_pcg_init), kRedThreads, 0, h->stream>>>(h->diag_ext.p + 1, h->r.p, h->d.p, h->p_ext.p + 1, h->x.p,
                                                           (long long)h->neq_pp, h->part.p, h->state.p, h->nranks == 1,
-                                                          (h->peer_ok && h->use_peer) ? h->ptab.p : nullptr);
+                                                          (h->peer_ok && h->use_peer) ? h->ptab.p : nullptr, keep_x);
   h->launches++;
   if (!(h->peer_ok && h->use_peer) && (rc = combine_scalars(h, 0))) return rc;
   const bool peer = h->peer_ok && h->use_peer;

@@ -638,7 +638,7 @@ __global__ void k_scalars(State *st, const double *all /*nranks x 4*/, int nrank
 __global__ void __launch_bounds__(kRedThreads)
 k_pcg_init(const double *__restrict__ diag, const double *__restrict__ r, double *__restrict__ d,
            double *__restrict__ p, double *__restrict__ x, long long n, double *part, State *st,
-           int single_rank, PeerTable *T) {
+           int single_rank, PeerTable *T, int keep_x /* p122: the solve starts from the current x (p122.f90:139-146) */) {
   __shared__ double sh[8];
   __shared__ double sh_loc[4], sh_out[3];
   __shared__ int flag;
@@ -652,7 +652,8 @@ k_pcg_init(const double *__restrict__ diag, const double *__restrict__ r, double
       for (int h = 0; h < 2; ++h)
         if (i + h < n) {
           const double rr = r[i + h], dd = diag[i + h] * rr;
-          d[i + h] = dd; p[i + h] = dd; x[i + h] = 0.0;
+          d[i + h] = dd; p[i + h] = dd;
+          if (!keep_x) x[i + h] = 0.0;
           acc = acc + rr * dd;
         }
     }
@@ -674,12 +675,13 @@ k_pcg_init(const double *__restrict__ diag, const double *__restrict__ r, double
   }
 }
 
-// p123 fixed freedoms: u(j) = p(j)*store(i)   (p123.f90:141-145)
+// p123 fixed freedoms: u(j) = p(j)*store(i)   (p123.f90:141-145); mode 1: u(j) = 0, what p122 does on every plastic
+// iteration after the first (p122.f90:154-160)
 __global__ void k_fixed_u(const int *__restrict__ fix_slot, const double *__restrict__ store,
-                          const double *__restrict__ p_ext, double *__restrict__ u_ext, int n, const State *st) {
+                          const double *__restrict__ p_ext, double *__restrict__ u_ext, int n, const State *st, int mode) {
   if (st && *(volatile const int *)&st->done) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) u_ext[fix_slot[i]] = p_ext[fix_slot[i]] * store[i];
+  if (i < n) u_ext[fix_slot[i]] = mode == 0 ? p_ext[fix_slot[i]] * store[i] : 0.0;
 }
 
 // owner side of the reverse halo exchange folded into the p.u reduction (N ranks, peer transport): the accumulate
@@ -827,15 +829,6 @@ struct PutTables {
   const long long *dst;            // index in that rank's p_ext
   int n;                           // number of such equations
 };
-__device__ __forceinline__ void put_one(PeerTable *T, const PutTables &P, long long i, double v) {
-  int lo = 0, hi = P.n - 1;
-  while (lo < hi) {                // slot0 holds i (its bit is set)
-    const int mid = (lo + hi) >> 1;
-    if (P.slot0[mid] < i) lo = mid + 1; else hi = mid;
-  }
-  for (unsigned int q = P.ptr[lo]; q < P.ptr[lo + 1]; ++q) T->p_ext[P.rank[q]][P.dst[q]] = v;
-}
-
 // p = d + p*beta (p121.f90:102), then the exit test of p121.f90:103.  `done` is raised by the last
 // block to finish, so no block of this kernel can observe it early and every later kernel sees it.
 // T != nullptr: every new p value a peer's elements need is stored into that peer's halo segment as it is formed,
@@ -846,18 +839,22 @@ __global__ void k_pupdate(const double *__restrict__ d, double *__restrict__ p, 
   if (*(volatile const int *)&st->done) return;
   __shared__ int flag;
   const double beta = st->beta;
+  if (T) {
+    // first the equations peers gather, each exactly once (the sweep below skips them): the stores cross NVLink
+    // while the rest of the vector is updated
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < P.n; j += gridDim.x * blockDim.x) {
+      const int i = P.slot0[j];
+      const double v = d[i] + p[i] * beta;
+      p[i] = v;
+      for (unsigned int q = P.ptr[j]; q < P.ptr[j + 1]; ++q) T->p_ext[P.rank[q]][P.dst[q]] = v;
+    }
+  }
   long long i = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
   const long long stride = 2 * (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
-    const double v0 = d[i] + p[i] * beta;
-    p[i] = v0;
-    double v1 = 0.0;
-    if (i + 1 < n) { v1 = d[i + 1] + p[i + 1] * beta; p[i + 1] = v1; }
-    if (T) {
-      const unsigned int w = P.bits[i >> 5] >> (i & 31);      // i is even: both bits sit in the same word
-      if (w & 1u) put_one(T, P, i, v0);
-      if ((w & 2u) && i + 1 < n) put_one(T, P, i + 1, v1);
-    }
+    const unsigned int w = T ? P.bits[i >> 5] >> (i & 31) : 0u;      // i is even: both bits sit in the same word
+    if (!(w & 1u)) p[i] = d[i] + p[i] * beta;
+    if (i + 1 < n && !(w & 2u)) p[i + 1] = d[i + 1] + p[i + 1] * beta;
   }
   if (T) peer_release_flags(T, 0);
   if (last_block(&st->ticket[3], &flag) && threadIdx.x == 0) {
@@ -1324,7 +1321,9 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
       if (grp < ngroups) issue_idx(grp);
     }
     __syncwarp();
-    if (T) warp_wait_fwd(T, st);     // N ranks, peer transport: the owners' values are in my halo segment of pvec
+    // N ranks, peer transport: the owners' values are in my halo segment of pvec.  The gather below uses ld.global.ca
+    // (not the non-coherent path): nothing of pvec was loaded by this kernel before the flags were seen.
+    if (T) warp_wait_fwd(T, st);
   }
   for (; grp < ngroups; grp += gstride) {
     const long long e0 = grp * 32;
@@ -1416,7 +1415,7 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
 #pragma unroll
           for (int kp = 0; kp < KP; ++kp) {
             const int k = lane + 32 * kp;
-            if (GATHER) val[el][kp] = T ? __ldcg(pvec + ((k < NTOT) ? idxbuf[el * NTOT + k] : 0)) : pvec[(k < NTOT) ? idxbuf[el * NTOT + k] : 0];
+            if (GATHER) val[el][kp] = T ? __ldca(pvec + ((k < NTOT) ? idxbuf[el * NTOT + k] : 0)) : pvec[(k < NTOT) ? idxbuf[el * NTOT + k] : 0];
             else val[el][kp] = (k < NTOT) ? pvec[(e0 + el) * NTOT + k] : 0.0;
           }
 #pragma unroll
@@ -1429,7 +1428,7 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
       } else {
         for (int el = 0; el < ne; ++el)
           for (int k = lane; k < NTOT; k += 32)
-            rows[el * ROW + k] = GATHER ? (T ? __ldcg(pvec + idxbuf[el * NTOT + k]) : pvec[idxbuf[el * NTOT + k]]) : pvec[(e0 + el) * NTOT + k];
+            rows[el * ROW + k] = GATHER ? (T ? __ldca(pvec + idxbuf[el * NTOT + k]) : pvec[idxbuf[el * NTOT + k]]) : pvec[(e0 + el) * NTOT + k];
       }
       __syncwarp();
       if (GATHER && lane == 0 && grp + gstride < ngroups) {
@@ -1517,6 +1516,256 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
         }
       __syncwarp();
     }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// p122 (programs/5th_ed/p122/p122.f90): elasto-plasticity, Mohr-Coulomb, viscoplastic strain method
+// ----------------------------------------------------------------------------
+// The Gauss-point update of elements_4 (p122.f90:197-231): strain increment from the displacement increment,
+// stress = dee*(eps - evpt) + tensor, invar / mocouf; on yield mocouq + formm -> flow -> evp = flow*stress*dt,
+// evpt += evp, devp = dee*evp (on the last plastic iteration devp = stress and tensor = stress); body loads
+// bload = sum_gp bee^T devp det w.  Same summation orders as orc_p122_elements (pf_oracle.c): q / r / k ascending,
+// Gauss points ascending, separate multiply and add; products with a structural zero of bee are left out (they add
+// +-0.0).  The angle constants (sin / cos of phi and psi in radians) come from the host's libm, so that the only
+// transcendental functions evaluated here are asin (invar) and sin / cos / tan of the Lode angle.
+struct PlasticParams {
+  double snph, csph, cohesion, snps, dt;
+};
+// invar, nst = 6 (new_library.f90:1893-1912)
+__device__ __forceinline__ void invar6(const double *s, double &sigm, double &dsbar, double &theta) {
+  const double sq3 = sqrt(3.0);
+  sigm = (s[0] + s[1] + s[2]) / 3.0;
+  const double d2 = ((s[0] - s[1]) * (s[0] - s[1]) + (s[1] - s[2]) * (s[1] - s[2]) + (s[2] - s[0]) * (s[2] - s[0])) / 6.0 +
+                    s[3] * s[3] + s[4] * s[4] + s[5] * s[5];
+  const double ds1 = s[0] - sigm, ds2 = s[1] - sigm, ds3 = s[2] - sigm;
+  const double d3 = ds1 * ds2 * ds3 - ds1 * s[4] * s[4] - ds2 * s[5] * s[5] - ds3 * s[3] * s[3] + 2.0 * s[3] * s[4] * s[5];
+  dsbar = sq3 * sqrt(d2);
+  if (dsbar < 1e-10) theta = 0.0;
+  else {
+    const double r = sqrt(d2);
+    double sine = -3.0 * sq3 * d3 / (2.0 * r * r * r);
+    if (sine > 1.0) sine = 1.0;
+    if (sine < -1.0) sine = -1.0;
+    theta = asin(sine) / 3.0;
+  }
+}
+// mocouf (new_library.f90:2364-2417)
+__device__ __forceinline__ double mocouf(const PlasticParams &P, double sigm, double dsbar, double theta) {
+  const double csth = cos(theta), snth = sin(theta);
+  return P.snph * sigm + dsbar * (csth / sqrt(3.0) - snth * P.snph / 3.0) - P.cohesion * P.csph;
+}
+// mocouq (new_library.f90:2423-2490)
+__device__ __forceinline__ void mocouq(const PlasticParams &P, double dsbar, double theta, double &dq1, double &dq2, double &dq3) {
+  const double snth = sin(theta), snps = P.snps, sq3 = sqrt(3.0);
+  dq1 = snps;
+  if (fabs(snth) > 0.49) {
+    const double c1 = snth < 0.0 ? -1.0 : 1.0;
+    dq2 = (sq3 * 0.5 - c1 * snps * 0.5 / sq3) * sq3 * 0.5 / dsbar;
+    dq3 = 0.0;
+  } else {
+    const double csth = cos(theta), cs3th = cos(3.0 * theta), tn3th = tan(3.0 * theta), tnth = snth / csth;
+    dq2 = sq3 * csth / dsbar * ((1.0 + tnth * tn3th) + snps * (tn3th - tnth) / sq3) * 0.5;
+    dq3 = 0.5 * 3.0 * (sq3 * snth + snps * csth) / (cs3th * dsbar * dsbar);
+  }
+}
+// formm, nst = 6 (new_library.f90:145-194); m(i,j) at [j*6+i]
+__device__ __forceinline__ void formm6(const double *st, double *m1, double *m2, double *m3) {
+  const double sx = st[0], sy = st[1], sz = st[2], txy = st[3], tyz = st[4], tzx = st[5];
+  const double sigm = (sx + sy + sz) / 3.0, dx = sx - sigm, dy = sy - sigm, dz = sz - sigm;
+#pragma unroll
+  for (int q = 0; q < 36; ++q) { m1[q] = 0.0; m2[q] = 0.0; m3[q] = 0.0; }
+#define M(m, i, j) (m)[((j)-1) * 6 + ((i)-1)]
+  for (int i = 1; i <= 3; ++i) for (int j = 1; j <= 3; ++j) M(m1, i, j) = 1.0 / (3.0 * sigm);
+  for (int i = 1; i <= 3; ++i) { M(m2, i, i) = 2.0; M(m2, i + 3, i + 3) = 6.0; }
+  M(m2, 1, 2) = -1.0; M(m2, 1, 3) = -1.0; M(m2, 2, 3) = -1.0;
+  M(m3, 1, 1) = dx; M(m3, 1, 2) = dz; M(m3, 1, 3) = dy; M(m3, 1, 4) = txy; M(m3, 1, 5) = -2.0 * tyz; M(m3, 1, 6) = tzx;
+  M(m3, 2, 2) = dy; M(m3, 2, 3) = dx; M(m3, 2, 4) = txy; M(m3, 2, 5) = tyz; M(m3, 2, 6) = -2.0 * tzx;
+  M(m3, 3, 3) = dz; M(m3, 3, 4) = -2.0 * txy; M(m3, 3, 5) = tyz; M(m3, 3, 6) = tzx;
+  M(m3, 4, 4) = -3.0 * dz; M(m3, 4, 5) = 3.0 * tzx; M(m3, 4, 6) = 3.0 * tyz;
+  M(m3, 5, 5) = -3.0 * dx; M(m3, 5, 6) = 3.0 * txy; M(m3, 6, 6) = -3.0 * dy;
+  for (int i = 1; i <= 6; ++i)
+    for (int j = i + 1; j <= 6; ++j) { M(m1, j, i) = M(m1, i, j); M(m2, j, i) = M(m2, i, j); M(m3, j, i) = M(m3, i, j); }
+#undef M
+  for (int q = 0; q < 36; ++q) { m1[q] = m1[q] / 3.0; m2[q] = m2[q] / 3.0; m3[q] = m3[q] / 3.0; }
+}
+
+// One CTA of 64 threads per element: (1) jac / det / inverse / deriv of all Gauss points (as k_form_km_tiled);
+// (2) thread ig < nip updates Gauss point ig (strain, stress, yield function, flow, evpt / tensor) and leaves devp
+// and the yield flag in shared memory; (3) thread q < ntot adds the points' contributions to bload(q) in point order.
+// loads_ext: the displacement increment, slot-indexed (gather through ggl); evpt / tensor (6,nip,nels).
+template <int NOD>
+__global__ void __launch_bounds__(64)
+k_p122_elements(const double *__restrict__ g_coord, const int *__restrict__ ggl, const double *__restrict__ loads_ext,
+                double *__restrict__ evpt, double *__restrict__ tensor, double *__restrict__ utemp, long long nels,
+                PlasticParams P, int last) {
+  constexpr int NTOT = 3 * NOD, MAXIP = 8, THREADS = 64;
+  static_assert(NTOT <= THREADS, "one thread per element freedom");
+  __shared__ double s_coord[NOD * 3], s_jac[MAXIP * 9], s_det[MAXIP], s_deriv[MAXIP * NOD * 3], s_eld[NTOT];
+  __shared__ double s_devp[MAXIP * 6];
+  __shared__ int s_yield[MAXIP];
+  const int nip = c_tab.nip, t = threadIdx.x;
+  for (long long e = blockIdx.x; e < nels; e += gridDim.x) {
+    __syncthreads();
+    for (int q = t; q < NOD * 3; q += THREADS) s_coord[q] = g_coord[e * NOD * 3 + q];
+    if (t < NTOT) s_eld[t] = loads_ext[ggl[e * NTOT + t]];           // gather(loads_pp,pmul_pp): slot 0 holds 0.0
+    __syncthreads();
+    for (int q = t; q < nip * 9; q += THREADS) {                      // jac = MATMUL(der,coord), every point
+      const int ig = q / 9, r = q - 9 * ig, a = r % 3, b = r / 3;
+      const double *der = c_tab.der + ig * 60;
+      double sum = 0.0;
+#pragma unroll
+      for (int m = 0; m < NOD; ++m) sum = sum + der[a * 20 + m] * s_coord[b * NOD + m];
+      s_jac[ig * 9 + b * 3 + a] = sum;
+    }
+    __syncthreads();
+    if (t < nip) {
+      double jac[9], inv[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) jac[q] = s_jac[t * 9 + q];
+      const double det = det3(jac);
+      inv3(jac, det, inv);
+#pragma unroll
+      for (int q = 0; q < 9; ++q) s_jac[t * 9 + q] = inv[q];
+      s_det[t] = det;
+    }
+    __syncthreads();
+    for (int q = t; q < nip * NOD * 3; q += THREADS) {                // deriv = MATMUL(jac^-1,der)
+      const int ig = q / (NOD * 3), r = q - ig * (NOD * 3), m = r / 3, a = r - 3 * m;
+      const double *der = c_tab.der + ig * 60, *inv = s_jac + ig * 9;
+      double sum = 0.0;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) sum = sum + inv[b * 3 + a] * der[b * 20 + m];
+      s_deriv[q] = sum;
+    }
+    __syncthreads();
+    if (t < nip) {
+      const double *dv = s_deriv + t * (NOD * 3);
+      double *ev = evpt + (e * nip + t) * 6, *te = tensor + (e * nip + t) * 6;
+      double eps[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, stress[6], devp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      for (int m = 0; m < NOD; ++m) {                                 // eps = MATMUL(bee,eld), q ascending
+        const double x = dv[m * 3], y = dv[m * 3 + 1], z = dv[m * 3 + 2];
+        const double e0 = s_eld[3 * m], e1 = s_eld[3 * m + 1], e2 = s_eld[3 * m + 2];
+        eps[0] = eps[0] + x * e0; eps[3] = eps[3] + y * e0; eps[5] = eps[5] + z * e0;     // column 3m
+        eps[1] = eps[1] + y * e1; eps[3] = eps[3] + x * e1; eps[4] = eps[4] + z * e1;     // column 3m+1
+        eps[2] = eps[2] + z * e2; eps[4] = eps[4] + y * e2; eps[5] = eps[5] + x * e2;     // column 3m+2
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) eps[r] = eps[r] - ev[r];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {                                   // sigma = MATMUL(dee,eps); stress = sigma + tensor
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) sum = sum + c_tab.dee[q * 6 + r] * eps[q];
+        stress[r] = sum + te[r];
+      }
+      double sigm, dsbar, theta;
+      invar6(stress, sigm, dsbar, theta);
+      const double f = mocouf(P, sigm, dsbar, theta);
+      if (last) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) devp[r] = stress[r];
+      } else if (f >= 0.0) {
+        double dq1, dq2, dq3, m1[36], m2[36], m3[36], evp[6];
+        mocouq(P, dsbar, theta, dq1, dq2, dq3);
+        formm6(stress, m1, m2, m3);
+        for (int r = 0; r < 6; ++r) {
+          double sum = 0.0;
+          for (int q = 0; q < 6; ++q) {
+            const double flow = f * (m1[q * 6 + r] * dq1 + m2[q * 6 + r] * dq2 + m3[q * 6 + r] * dq3);
+            sum = sum + flow * stress[q];
+          }
+          evp[r] = sum * P.dt;
+          ev[r] = ev[r] + evp[r];
+        }
+        for (int r = 0; r < 6; ++r) {
+          double sum = 0.0;
+          for (int q = 0; q < 6; ++q) sum = sum + c_tab.dee[q * 6 + r] * evp[q];
+          devp[r] = sum;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) s_devp[t * 6 + r] = devp[r];
+      s_yield[t] = f >= 0.0;
+      if (last) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) te[r] = stress[r];
+      }
+    }
+    __syncthreads();
+    if (t < NTOT) {                                                   // bload = bload + MATMUL(TRANSPOSE(bee),devp)*det*w
+      const int m = t / 3, comp = t - 3 * m;
+      double bl = 0.0;
+      for (int ig = 0; ig < nip; ++ig) {
+        if (!s_yield[ig]) continue;
+        const double *dv = s_deriv + ig * (NOD * 3), *dp = s_devp + ig * 6;
+        const double x = dv[m * 3], y = dv[m * 3 + 1], z = dv[m * 3 + 2];
+        double sum = 0.0;
+        if (comp == 0) { sum = sum + x * dp[0]; sum = sum + y * dp[3]; sum = sum + z * dp[5]; }
+        else if (comp == 1) { sum = sum + y * dp[1]; sum = sum + x * dp[3]; sum = sum + z * dp[4]; }
+        else { sum = sum + z * dp[2]; sum = sum + y * dp[4]; sum = sum + x * dp[5]; }
+        bl = bl + sum * s_det[ig] * c_tab.weights[ig];
+      }
+      utemp[e * NTOT + t] = bl;
+    }
+  }
+}
+
+// loads = ld0*q (or 0) [+ bdylds]   (p122.f90:127-137)
+__global__ void k_plastic_loads(double *__restrict__ loads, const double *__restrict__ ld0, const double *__restrict__ bdylds,
+                                double q, int add_bdy, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    double v = ld0 ? ld0[i] * q : 0.0;
+    if (add_bdy) v = v + bdylds[i];
+    loads[i] = v;
+  }
+}
+// fixed freedoms of p122: mode 0  loads(j) = store*valf*qinc (p122.f90:121-126); mode 1  loads(j) = 0 (:133-137).
+// dst is slot-indexed.
+__global__ void k_plastic_fixed(const int *__restrict__ fix_slot, const double *__restrict__ store, const double *__restrict__ valf,
+                                double *__restrict__ dst, double q, int n, int mode) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dst[fix_slot[i]] = mode == 0 ? store[i] * valf[i] * q : 0.0;
+}
+// c = a - b ; c = a + b
+__global__ void k_vsub(double *__restrict__ c, const double *__restrict__ a, const double *__restrict__ b, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) c[i] = a[i] - b[i];
+}
+__global__ void k_vadd(double *__restrict__ c, const double *a, const double *__restrict__ b, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) c[i] = a[i] + b[i];
+}
+// checon_par (maths.f90:1048-1061) outside the solver: max|loads|, max|loads - oldlds| of this rank into st->loc[1],
+// loc[2]; oldlds = loads
+__global__ void __launch_bounds__(kRedThreads)
+k_checon(const double *__restrict__ loads, double *__restrict__ oldlds, long long n, double *part, State *st) {
+  __shared__ double sh[8];
+  __shared__ int flag;
+  const long long nchunks = (n + kChunk - 1) / kChunk;
+  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    double ml = 0.0, md = 0.0;
+    for (int k = 0; k < 8; ++k) {
+      const long long i = c * kChunk + 256 * k + threadIdx.x;
+      if (i < n) {
+        const double v = loads[i], o = oldlds[i];
+        ml = fmax(ml, fabs(v)); md = fmax(md, fabs(v - o));
+        oldlds[i] = v;
+      }
+    }
+    const double a = block_max(ml, sh);
+    const double b = block_max(md, sh);
+    if (threadIdx.x == 0) { part[c] = a; part[nchunks + c] = b; }
+  }
+  if (last_block(&st->ticket[0], &flag)) {
+    const double m1 = final_max(part, nchunks, sh);
+    const double m2 = final_max(part + nchunks, nchunks, sh);
+    if (threadIdx.x == 0) { st->loc[0] = 0.0; st->loc[1] = m1; st->loc[2] = m2; st->loc[3] = 0.0; }
   }
 }
 

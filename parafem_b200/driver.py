@@ -154,6 +154,49 @@ XX3_SECTIONS = ("Setup", "Read element steering array", "Convert Abaqus to S&G n
                 "Get starting r", "Solve equations", "Output results")
 
 
+def run_p122(prob, s, out_base=None, decimals=4):
+    """Program p122 (p122.f90) for one rank: setup, then the load-increment loop -- every increment one device call
+    (plastic iterations, each a PCG solve restarted from the current x plus the Gauss-point stress update).  With
+    `out_base` the displacement files <out_base>.ensi.DISPL-NNNNNN are written after every increment (p122.f90:215-228;
+    single rank).  -> dict(rows = [(totd(1), sigma z, sigma x, sigma y, cjtot, plasiters)], totd, dt, solve_s, setup_s)."""
+    from . import host
+    t0 = time.time()
+    _solver.setup_problem(s, prob)
+    t_setup = time.time() - t0
+    rows, ms_total = [], 0.0
+    ld0 = prob.r_pp if getattr(prob, "loaded_nodes", 0) else None
+    for iy, q in enumerate(prob.qinc, 1):
+        plasiters, cjtot, ms = s.plastic_increment(q, prob.plasits, prob.plastol, prob.cjits, prob.cjtol, ld0_pp=ld0,
+                                                   valf_pp=prob.val_f if prob.no_f.size else None)
+        ms_total += ms
+        totd = s.plastic_totd()
+        t = s.plastic_tensor(0, 0) if prob.numpe == 1 else np.zeros(6)
+        rows.append((float(totd[0]) if prob.numpe == 1 else None, t[2], t[0], t[1], cjtot, plasiters))
+        if out_base and prob.npes == 1:
+            host.write_ensi(f"{out_base}.ensi.DISPL-{iy:06d}", host.nodal_values(prob, totd), decimals=decimals)
+        if plasiters == prob.plasits:
+            break
+    return dict(rows=rows, totd=totd, dt=prob.dt, solve_s=ms_total / 1e3, setup_s=t_setup)
+
+
+def write_res_p122(path, prob, res, t_total=0.0):
+    """<job>.res as p122.f90:59-64,93,117,206-214,230 writes it."""
+    with open(path, "w") as f:
+        f.write(f"This job ran on {prob.npes:5d}  processes\n")
+        f.write(f"There are {prob.nn:7d} nodes{prob.nr:7d} restrained and   {prob.neq:7d} equations\n")
+        f.write(f"Time after setup is:{res['setup_s']:10.4f}\n")
+        f.write(f"The critical timestep is   {_fe(res['dt'])}\n")
+        for iy, (d1, sz, sx, sy, cjtot, plasiters) in enumerate(res["rows"], 1):
+            f.write(f"\nLoad Increment   {iy:5d}\n")
+            f.write(f"The displacement is  {_fe(d1)}\n")
+            f.write("  sigma z    sigma x     sigma y\n")
+            f.write(f"{_fe(sz)}{_fe(sx)}{_fe(sy)}\n")
+            f.write(f"The total number of cj iterations was  {cjtot:12d}\n")
+            f.write(f"The number of plastic iterations was  {plasiters:12d}\n")
+            f.write(f"cj iterations per plastic iteration were {cjtot / plasiters:11.2f}\n")
+        f.write(f"This analysis took: {t_total:10.4f}\n")
+
+
 def write_res_xx3(path, prob, res, loaded_nodes, seconds, kernels=None):
     """<job>.res in the layout of the reference's GPU driver xx3 (programs/dev/xx3/xx3.f90, golden
     examples/dev/xx3/demo/xx3-tiny.res): BASIC JOB DATA, then the 'section / seconds / %total' table -- SURVEY 5.1's

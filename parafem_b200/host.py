@@ -324,6 +324,61 @@ def read_deck_p123(job, npes=1, numpe=1, program=123):
     return p
 
 
+def read_deck_p122(job, npes=1, numpe=1):
+    """Input section of p122.f90:36-57,97-114 for one rank: read_p122 (element, meshgen, partitioner / nels nn nr nip
+    nod fixed_freedoms loaded_nodes / phi c psi e v / incs plasits cjits plastol cjtol), read_qinc, the mesh and
+    restraint readers of p121, read_loads + load (ld0_pp) and read_fixed + find_no + reindex (this rank's fixed
+    equations and their values).  -> Problem(program 122) with phi, c, psi, qinc, plasits, cjits, plastol, cjtol."""
+    L = lib()
+    tk = open(job + ".dat").read().split()
+    if len(tk) < 20:
+        raise PfError(f"{job}.dat: too few values for read_p122")
+    meshgen, partitioner = int(tk[1]), int(tk[2])
+    nels, nn, nr, nip, nod, fixed, loaded = (int(v) for v in tk[3:10])
+    phi, c, psi, e, v = (float(t.replace("D", "E").replace("d", "e")) for t in tk[10:15])
+    incs, plasits, cjits = (int(t) for t in tk[15:18])
+    plastol, cjtol = float(tk[18]), float(tk[19])
+    qinc = [float(t) for t in tk[20:20 + incs]]
+    if min(nels, nn) < 1 or nr < 0 or nr > nn or nod not in (8, 20) or nip != 8 or len(qinc) != incs or fixed < 0 or loaded < 0:
+        raise PfError(f"{job}.dat: sizes outside what p122 takes (hexahedra with 8 or 20 nodes, nip = 8)")
+    g_coord = np.empty((nn, 3), np.float64)
+    g_num = np.empty((nels, nod), np.int32)
+    check(L.pf_read_d(job.encode(), nn, nels, nod, ptr(g_coord), ptr(g_num)), what="pf_read_d")
+    if meshgen == 2:
+        check(L.pf_abaqus2sg(nod, nels, ptr(g_num)), what="pf_abaqus2sg")
+    nels_pp, iel_start = read_psize(job, npes, numpe) if partitioner == 2 else calc_nels_pp(nels, npes, numpe)
+    g_num_pp = np.ascontiguousarray(g_num[iel_start - 1:iel_start - 1 + nels_pp])
+    g_coord_pp = np.empty((nels_pp, 3, nod), np.float64)
+    check(L.pf_coords_pp(nod, nels_pp, nn, ptr(g_num_pp), ptr(g_coord), ptr(g_coord_pp)), what="pf_coords_pp")
+    rest = np.zeros((4, nr), np.int32)
+    check(L.pf_read_bnd(job.encode(), nr, 3, ptr(rest)), what="pf_read_bnd")
+    nf, g_g, neq = _steer(nn, 3, rest, g_num_pp, nod)
+    neq_pp, ieq_start = calc_neq_pp(neq, npes, numpe)
+    r = np.zeros(neq_pp, np.float64)
+    if loaded:
+        node = np.empty(loaded, np.int32)
+        val = np.empty((loaded, 3), np.float64)
+        check(L.pf_read_lds(job.encode(), loaded, 3, ptr(node), ptr(val)), what="pf_read_lds")
+        check(L.pf_load(3, loaded, nn, ptr(node), ptr(val), ptr(nf), ieq_start, neq_pp, ptr(r)), what="pf_load")
+    no_f, val_f = np.zeros(0, np.int32), np.zeros(0, np.float64)
+    if fixed:
+        node = np.empty(fixed, np.int32)
+        sense = np.empty(fixed, np.int32)
+        valf = np.empty(fixed, np.float64)
+        check(L.pf_read_fix(job.encode(), fixed, ptr(node), ptr(sense), ptr(valf)), what="pf_read_fix")
+        if node.min() < 1 or node.max() > nn or sense.min() < 1 or sense.max() > 3:
+            raise PfError(f"{job}.fix names a node outside 1..{nn} or a freedom outside 1..3")
+        eq = nf[node - 1, sense - 1]            # find_no (new_library.f90): the equation of (node, sense)
+        mine = (eq >= ieq_start) & (eq < ieq_start + neq_pp)
+        no_f, val_f = np.ascontiguousarray(eq[mine]), np.ascontiguousarray(valf[mine])
+    p = Problem(122, nod, 3, nip, nels, nn, nr, neq, npes, numpe, nels_pp, iel_start, neq_pp, ieq_start,
+                g_num_pp, g_coord_pp, g_g, nf, r, e=e, v=v, tol=cjtol, limit=cjits, no_f=no_f, val_f=val_f)
+    p.phi, p.c, p.psi, p.qinc, p.plasits, p.cjits, p.plastol, p.cjtol = phi, c, psi, qinc, plasits, cjits, plastol, cjtol
+    p.loaded_nodes = loaded
+    p.g_coord, p.rest = g_coord, rest
+    return p
+
+
 def read_deck_xx2(job, npes=1, numpe=1):
     """Input section of programs/dev/xx2/xx2.f90:60-160 for one rank: read_xx2, read_elements (connectivity +
     material number of every element), abaqus2sg, read_g_coord_pp, read_rest, read_materialValue, steering,

@@ -181,6 +181,32 @@ class Solver:
         self._ck(lib().pf_explicit_steps(self._h, nsteps, C.byref(ms)), "pf_explicit_steps")
         return ms.value
 
+    # -- p122: elasto-plasticity ---------------------------------------------------------------
+    def plastic_begin(self, phi, c, psi, e, v):
+        """p122.f90:88-93 after form_km_elastic + build_precon. -> the critical time step dt"""
+        dt = C.c_double()
+        self._ck(lib().pf_plastic_begin(self._h, phi, c, psi, e, v, C.byref(dt)), "pf_plastic_begin")
+        return dt.value
+
+    def plastic_increment(self, qinc, plasits, plastol, cjits, cjtol, ld0_pp=None, valf_pp=None):
+        """One load increment (p122.f90:115-205). -> (plasiters, cjtot, elapsed_ms)"""
+        pl, cj, ms = C.c_int(), C.c_int(), C.c_double()
+        l0 = f64(ld0_pp) if ld0_pp is not None else None
+        vf = f64(valf_pp) if valf_pp is not None and len(valf_pp) else None
+        self._ck(lib().pf_plastic_increment(self._h, qinc, ptr(l0), ptr(vf), plasits, plastol, cjits, cjtol, C.byref(pl),
+                                            C.byref(cj), C.byref(ms)), "pf_plastic_increment")
+        return pl.value, cj.value, ms.value
+
+    def plastic_totd(self):
+        out = np.empty(self.prob.neq_pp)
+        self._ck(lib().pf_plastic_get(self._h, ptr(out), 0, 0, None), "pf_plastic_get")
+        return out
+
+    def plastic_tensor(self, iel=0, ig=0):
+        out = np.empty(6)
+        self._ck(lib().pf_plastic_get(self._h, None, iel, ig, ptr(out)), "pf_plastic_get")
+        return out
+
     # -- fine-grained -----------------------------------------------------------------
     def gather(self, p_pp):
         out = np.empty((self.prob.nels_pp, self.prob.ntot))
@@ -271,6 +297,11 @@ def setup_problem(solver, prob, matrix_free=False, layout=0):
         if prob.no_f.size:
             # r_pp(j) = store_pp(i)*valf(k)   (xx2.f90:294-300)
             prob.r_pp[prob.no_f - prob.ieq_start] = solver.store() * prob.val_f
+    elif prob.program == 122:
+        # p122.f90:94-114: storkm_pp, the preconditioner with the penalty on this rank's fixed freedoms, zero stresses
+        solver.form_km_elastic(prob.e, prob.v)
+        solver.build_precon(prob.no_f if prob.no_f.size else None, 1e20)
+        prob.dt = solver.plastic_begin(prob.phi, prob.c, prob.psi, prob.e, prob.v)
     elif prob.program == 125:
         solver.form_k_explicit(prob.kx, prob.ky, prob.kz, prob.dtim)
     elif prob.program == 124:
