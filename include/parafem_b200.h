@@ -141,6 +141,12 @@ int pf_pcg_run(pf_handle h, double tol, int limit, int *iters, int *converged,
                double *elapsed_ms);
 int pf_pcg_get_x(pf_handle h, double *xnew_pp);
 /* checon_par ratio max|xnew-x|/max|xnew| of every iteration of the last run */
+/* PCG_KM (maths.f90:1152-1323), SURVEY 8a row a14: the solver for meshes of congruent elements -- one
+ * km(ntot,ntot) for every element (utemp_pp = MATMUL(km,pmul_pp)), the inverted diagonal preconditioner
+ * diag_precon_pp(neq_pp) supplied by the caller as in the Fortran argument list; r_pp in, xnew_pp out.  The element
+ * matrix lives in registers on the device: no storkm stream at all.                                          */
+int pf_pcg_km(pf_handle h, const double *km, const double *diag_precon_pp, const double *r_pp, double tol, int limit,
+              double *xnew_pp, int *iters, int *converged);
 int pf_get_ratio_history(pf_handle h, double *out, int maxn, int *n);
 
 /* --- transient conduction: program p124 ---------------
@@ -370,6 +376,15 @@ int pf_write_ensi(const char *path, int numvar, int64_t nn, const double *values
 int pf_make_ggl(int ntot, int64_t nels_pp, const int32_t *g_g_pp, int64_t neq,
                 int npes, int numpe, int32_t *ggl_pp, int64_t cap,
                 int32_t *halo_eq, int64_t *halo_cnt, int64_t *nhalo);
+
+/* binary decks: <job>.bin.ensi.geo = the EnSight Gold "C Binary" geometry file written by
+ * p12meshgenbin (mesh_ensi_geo_bin, input.f90:7986-8164) and read by read_g_coord_pp_be (input.f90:632-790) and
+ * read_g_num_pp_be (:1254-1420).  Coordinates are single precision in the file; the connectivity is in EnSight's
+ * node order (for 8-node bricks the order abaqus2sg expects; pf_ensi2sg restores S&G order for 8 / 20 / 4 nodes). */
+int pf_write_geo_bin(const char *job, int nod, int64_t nn, int64_t nels, const double *g_coord, const int32_t *g_num_sg);
+int pf_geo_bin_sizes(const char *job, int64_t *nn, int64_t *nels, int *nod);
+int pf_read_geo_bin(const char *job, int64_t nn, int64_t nels, int nod, double *g_coord, int32_t *g_num);
+int pf_ensi2sg(int nod, int64_t nels, int32_t *g_num);
 
 /* Tables of the halo exchanges fused into the PCG kernels (peer transport, device.cu).  Forward: which owned
  * equations peers gather (one bit each in `bits`, the equations ascending in `slot0`, per equation its

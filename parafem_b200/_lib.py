@@ -57,6 +57,7 @@ SIGNATURES = {
     "pf_pcg_load_rhs": (c_int, [vp, vp]),
     "pf_pcg_run": (c_int, [vp, c_dbl, c_int, P(c_int), P(c_int), P(c_dbl)]),
     "pf_pcg_get_x": (c_int, [vp, vp]),
+    "pf_pcg_km": (c_int, [vp, vp, vp, vp, c_dbl, c_int, vp, P(c_int), P(c_int)]),
     "pf_get_ratio_history": (c_int, [vp, vp, c_int, P(c_int)]),
     "pf_form_k_transient": (c_int, [vp, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl]),
     "pf_get_storkb": (c_int, [vp, c_i64, c_i64, vp]),
@@ -114,6 +115,10 @@ SIGNATURES = {
     "pf_nodal_values": (c_int, [c_int, c_i64, vp, c_i64, c_i64, vp, c_i64, c_i64, vp]),
     "pf_write_ensi": (c_int, [C.c_char_p, c_int, c_i64, vp, c_int]),
     "pf_make_ggl": (c_int, [c_int, c_i64, vp, c_i64, c_int, c_int, vp, c_i64, vp, vp, P(c_i64)]),
+    "pf_write_geo_bin": (c_int, [C.c_char_p, c_int, c_i64, c_i64, vp, vp]),
+    "pf_geo_bin_sizes": (c_int, [C.c_char_p, P(c_i64), P(c_i64), P(c_int)]),
+    "pf_read_geo_bin": (c_int, [C.c_char_p, c_i64, c_i64, c_int, vp, vp]),
+    "pf_ensi2sg": (c_int, [c_int, c_i64, vp]),
     "pf_make_put_tables": (c_int, [c_int, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, P(c_i64)]),
     "pf_make_acc_chunks": (c_int, [c_i64, c_int, c_i64, vp, vp]),
 }

@@ -83,6 +83,9 @@ struct pf_ctx {
   int64_t nels = 0, neq = 0, ieq_start = 0, neq_pp = 0, nhalo = 0, nslots = 0;
   bool have_mesh = false, have_km = false, have_precon = false, matrix_free = false;
   DevBuf<double> coord, km, utemp, diag_tmp, geom;
+  // pcg_km (maths.f90:1152-1323): one element matrix shared by every element
+  DevBuf<double> km1;
+  bool one_km = false;
   // p124 (transient conduction): km holds storka_pp (the PCG matrix), kb holds storkb_pp; mat_override
   // selects the matrix set of the next operator product (nullptr = km)
   DevBuf<double> kb, val_f;
@@ -384,9 +387,29 @@ int launch_mf_t(pf_handle h, const double *pvec, const State *st, PeerTable *T =
   return 0;
 }
 
+template <int NTOT, bool GATHER>
+int launch_matvec_km_t(pf_handle h, const double *pvec, const State *st, PeerTable *T) {
+  const int64_t npass = (h->nels + (64 / NTOT) - 1) / (64 / NTOT);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(npass, (int64_t)h->sm_count * 8));
+  k_matvec_km<NTOT, GATHER><<<grid, 64, 0, h->stream>>>(h->km1.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st, T);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
 template <bool GATHER>
 int launch_matvec(pf_handle h, const double *pvec, const State *st, PeerTable *T = nullptr) {
   Scope sc(h, K_MATVEC);
+  if (h->one_km) {
+    switch (h->ntot) {
+      case 60: return launch_matvec_km_t<60, GATHER>(h, pvec, st, T);
+      case 24: return launch_matvec_km_t<24, GATHER>(h, pvec, st, T);
+      case 12: return launch_matvec_km_t<12, GATHER>(h, pvec, st, T);
+      case 8: return launch_matvec_km_t<8, GATHER>(h, pvec, st, T);
+      case 4: return launch_matvec_km_t<4, GATHER>(h, pvec, st, T);
+    }
+    return fail(h, 3, "unsupported ntot %d", h->ntot);
+  }
   if (h->matrix_free) {
     if (h->mf_mode == 2) {
       // PF_TUNE: unroll factor of the node-pair loops (default 2; measured in profiles/r01_mf_kernel_history.md)
@@ -958,7 +981,7 @@ int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp, con
     h->nels = nels_pp; h->neq = neq; h->ieq_start = ieq_start; h->neq_pp = neq_pp;
     h->have_mesh = false; h->have_km = h->have_precon = false;
     h->transient = h->transient_first = false; h->mat_override = nullptr; h->kb.release();
-    h->explicit_ = false; h->plastic = false; h->fixed_mode = 0;
+    h->explicit_ = false; h->plastic = false; h->fixed_mode = 0; h->one_km = false;
     h->epoch++;                                   // a captured iteration graph of the previous mesh is stale
 
     // gather table (make_ggl rebuilt from g_g_pp)
@@ -1103,6 +1126,7 @@ static int alloc_km(pf_handle h) {
 
 int pf_form_km_elastic(pf_handle h, double e, double v) {
   int rc = need_device(h); if (rc) return rc;
+  h->one_km = false;
   h->transient = false; h->explicit_ = false; h->kb.release();
   NEED(h->have_mesh && h->nodof == 3, "needs pf_setup_mesh with nodof = 3");
   NEED(h->nod != 4 || (h->km_layout == 0 && !h->matrix_free), "tetrahedra: reference storkm layout, stored matrices only");
@@ -1155,6 +1179,7 @@ int pf_form_km_elastic(pf_handle h, double e, double v) {
 // xx2.f90:169-193: as pf_form_km_elastic with e, v = prop(:,etype_pp(iel)) per element
 int pf_form_km_elastic_mat(pf_handle h, int np_types, const double *prop, const int32_t *etype_pp) {
   int rc = need_device(h); if (rc) return rc;
+  h->one_km = false;
   NEED(h->have_mesh && h->nodof == 3, "needs pf_setup_mesh with nodof = 3");
   NEED(!h->matrix_free, "the matrix-free variant takes one material (pf_form_km_elastic)");
   NEED(np_types >= 1 && prop && etype_pp, "np_types >= 1, prop(2,np_types) and etype_pp(nels_pp) are required");
@@ -1189,6 +1214,7 @@ int pf_form_km_elastic_mat(pf_handle h, int np_types, const double *prop, const 
 
 int pf_form_kc_laplace(pf_handle h, double kx, double ky, double kz) {
   int rc = need_device(h); if (rc) return rc;
+  h->one_km = false;
   h->transient = false; h->explicit_ = false; h->kb.release();
   NEED(h->have_mesh && h->nodof == 1 && (h->nod == 8 || h->nod == 4), "needs pf_setup_mesh with nod = 8 or 4, nodof = 1");
   NEED(h->nod != 4 || h->km_layout == 0, "tetrahedra: reference storkm layout only");
@@ -1209,6 +1235,7 @@ int pf_form_kc_laplace(pf_handle h, double kx, double ky, double kz) {
 // ---- p124: transient heat conduction, implicit theta method ----
 int pf_form_k_transient(pf_handle h, double kx, double ky, double kz, double rho, double cp, double theta, double dtim) {
   int rc = need_device(h); if (rc) return rc;
+  h->one_km = false;
   NEED(h->have_mesh && h->nodof == 1 && h->nod == 8, "needs pf_setup_mesh with nod = 8, nodof = 1");
   NEED(h->km_layout == 0 && !h->matrix_free, "the transient matrices use the reference storkm layout");
   ElemTables T;
@@ -1305,6 +1332,7 @@ int pf_transient_step(pf_handle h, const double *loads_pp, double tol, int limit
 // ---- p125: explicit transient conduction (forward Euler with a lumped mass) ----
 int pf_form_k_explicit(pf_handle h, double kx, double ky, double kz, double dtim) {
   int rc = need_device(h); if (rc) return rc;
+  h->one_km = false;
   NEED(h->have_mesh && h->nodof == 1 && h->nod == 8, "needs pf_setup_mesh with nod = 8, nodof = 1");
   NEED(h->km_layout == 0 && !h->matrix_free, "store_pm_pp uses the reference storkm layout");
   h->transient = false; h->kb.release();
@@ -1519,6 +1547,7 @@ int pf_plastic_get(pf_handle h, double *totd_pp, int64_t iel, int ig, double *te
 
 int pf_set_storkm(pf_handle h, const double *storkm_pp) {
   int rc = need_device(h); if (rc) return rc;
+  h->one_km = false;
   NEED(h->have_mesh && storkm_pp, "needs pf_setup_mesh");
   NEED(!h->matrix_free, "matrix-free variant: storkm is not stored");
   h->transient = false; h->explicit_ = false; h->kb.release();
@@ -1769,6 +1798,25 @@ int pf_pcg_solve(pf_handle h, const double *r_pp, double tol, int limit, double 
   if ((rc = pf_pcg_load_rhs(h, r_pp))) return rc;
   if ((rc = pf_pcg_run(h, tol, limit, iters, converged, nullptr))) return rc;
   return pf_pcg_get_x(h, xnew_pp);
+}
+
+// PCG_KM (maths.f90:1152-1323): every element shares km(ntot,ntot); the caller supplies the inverted diagonal
+// preconditioner of its own equations, as the Fortran routine's argument list does.
+int pf_pcg_km(pf_handle h, const double *km, const double *diag_precon_pp, const double *r_pp, double tol, int limit,
+              double *xnew_pp, int *iters, int *converged) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_mesh && km && diag_precon_pp && r_pp && xnew_pp, "needs pf_setup_mesh and km, diag_precon_pp, r_pp, xnew_pp");
+  NEED(!h->matrix_free && h->km_layout == 0, "pcg_km takes the stored path in the reference layout");
+  const size_t nk = (size_t)h->ntot * h->ntot;
+  CU(h->km1.alloc(nk));
+  CU(cudaMemcpyAsync(h->km1.p, km, nk * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->diag_ext.p + 1, diag_precon_pp, (size_t)h->neq_pp * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->km.release();
+  h->one_km = true; h->have_km = true; h->have_precon = true; h->nfixed = 0; h->fixed_mode = 0;
+  h->transient = false; h->explicit_ = false; h->plastic = false;
+  h->epoch++;
+  return pf_pcg_solve(h, r_pp, tol, limit, xnew_pp, iters, converged);
 }
 
 int pf_get_ratio_history(pf_handle h, double *out, int maxn, int *n) {

@@ -1031,6 +1031,118 @@ int pf_make_ggl(int ntot, int64_t nels_pp, const int32_t *g_g_pp, int64_t neq, i
 }
 
 
+/* ---- binary decks: <job>.bin.ensi.geo, the EnSight Gold "C Binary" geometry file that
+ * p12meshgenbin writes (mesh_ensi_geo_bin, input.f90:7986-8164) and read_g_coord_pp_be / read_g_num_pp_be
+ * (input.f90:632-790, 1254-1420) read: nine 80-character records and two C ints of header, nn, the coordinates as
+ * C floats component by component, the element type record, nels and the connectivity as C ints in EnSight's node
+ * order.  Single-precision coordinates are what the format holds. ---- */
+static const int kEnsi8[8] = {1, 4, 8, 5, 2, 3, 7, 6};                 /* input.f90:8099-8103 (S&G positions, 1-based) */
+static const int kEnsi20[20] = {1, 7, 19, 13, 3, 5, 17, 15, 8, 12, 20, 9, 4, 11, 16, 10, 2, 6, 18, 14};   /* :8109-8119 */
+static const int kEnsi4[4] = {1, 3, 2, 4};                             /* :8131-8132 */
+static const int *ensi_order(int nod) { return nod == 8 ? kEnsi8 : nod == 20 ? kEnsi20 : nod == 4 ? kEnsi4 : nullptr; }
+
+static void put80(FILE *f, const std::string &text) {
+  char rec[80];
+  memset(rec, ' ', sizeof rec);                                        /* Fortran CHARACTER(LEN=80): blank padded */
+  memcpy(rec, text.data(), std::min<size_t>(text.size(), 80));
+  fwrite(rec, 1, 80, f);
+}
+
+int pf_write_geo_bin(const char *job, int nod, int64_t nn, int64_t nels, const double *g_coord /*(3,nn)*/,
+                     const int32_t *g_num_sg /*(nod,nels), S&G order*/) {
+  const int *ord = ensi_order(nod);
+  if (!ord || nn < 1 || nels < 1 || nn > 2147483647LL || nels > 2147483647LL) return 2;
+  FILE *f = fopen((std::string(job) + ".bin.ensi.geo").c_str(), "wb");
+  if (!f) return 1;
+  std::string name(job);
+  const size_t slash = name.find_last_of('/');
+  if (slash != std::string::npos) name = name.substr(slash + 1);
+  put80(f, "C Binary"); put80(f, "Problem name: " + name); put80(f, "Geometry files");
+  put80(f, "node id off"); put80(f, "element id off"); put80(f, "part");
+  const int32_t one = 1, nn32 = (int32_t)nn, nels32 = (int32_t)nels;
+  fwrite(&one, 4, 1, f);
+  put80(f, "Volume"); put80(f, "coordinates");
+  fwrite(&nn32, 4, 1, f);
+  std::vector<float> ordn((size_t)nn);
+  for (int j = 0; j < 3; ++j) {
+    for (int64_t i = 0; i < nn; ++i) ordn[(size_t)i] = (float)g_coord[i * 3 + j];
+    fwrite(ordn.data(), 4, (size_t)nn, f);
+  }
+  put80(f, nod == 8 ? "hexa8" : nod == 20 ? "hexa20" : "tetra4");
+  fwrite(&nels32, 4, 1, f);
+  std::vector<int32_t> row((size_t)nod);
+  for (int64_t e = 0; e < nels; ++e) {
+    for (int m = 0; m < nod; ++m) row[(size_t)m] = g_num_sg[e * nod + ord[m] - 1];
+    fwrite(row.data(), 4, (size_t)nod, f);
+  }
+  const bool ok = !ferror(f);
+  fclose(f);
+  return ok ? 0 : 3;
+}
+
+/* sizes in the header of a binary geometry file: nn, nels, nod (from the element type record) */
+int pf_geo_bin_sizes(const char *job, int64_t *nn, int64_t *nels, int *nod) {
+  FILE *f = fopen((std::string(job) + ".bin.ensi.geo").c_str(), "rb");
+  if (!f) return 1;
+  char rec[81]; rec[80] = 0;
+  int32_t part = 0, nn32 = 0, nels32 = 0;
+  int rc = 0;
+  if (fread(rec, 1, 80, f) != 80 || strncmp(rec, "C Binary", 8) != 0) rc = 2;
+  for (int k = 0; k < 5 && !rc; ++k) if (fread(rec, 1, 80, f) != 80) rc = 2;
+  if (!rc && fread(&part, 4, 1, f) != 1) rc = 2;
+  for (int k = 0; k < 2 && !rc; ++k) if (fread(rec, 1, 80, f) != 80) rc = 2;
+  if (!rc && (fread(&nn32, 4, 1, f) != 1 || nn32 < 1)) rc = 2;
+  if (!rc && fseek(f, (long)nn32 * 12, SEEK_CUR) != 0) rc = 2;
+  if (!rc && fread(rec, 1, 80, f) != 80) rc = 2;
+  if (!rc) {
+    if (!strncmp(rec, "hexa20", 6)) *nod = 20;
+    else if (!strncmp(rec, "hexa8", 5)) *nod = 8;
+    else if (!strncmp(rec, "tetra4", 6)) *nod = 4;
+    else rc = 3;
+  }
+  if (!rc && (fread(&nels32, 4, 1, f) != 1 || nels32 < 1)) rc = 2;
+  fclose(f);
+  if (!rc) { *nn = nn32; *nels = nels32; }
+  return rc;
+}
+
+/* read_g_coord_pp_be + read_g_num_pp_be on global arrays: g_coord(3,nn) widened to double, g_num(nod,nels) in the
+ * file's (EnSight) node order -- for 8-node bricks that is the order abaqus2sg expects (the drivers that use the
+ * binary readers, xx12 / xx12_b, call it with meshgen = 2); pf_ensi2sg undoes it for every element type.  Node
+ * numbers outside 1..nn are status 8. */
+int pf_read_geo_bin(const char *job, int64_t nn, int64_t nels, int nod, double *g_coord, int32_t *g_num) {
+  int64_t nn_f = 0, nels_f = 0; int nod_f = 0;
+  int rc = pf_geo_bin_sizes(job, &nn_f, &nels_f, &nod_f);
+  if (rc) return rc;
+  if (nn_f != nn || nels_f != nels || nod_f != nod) return 4;
+  FILE *f = fopen((std::string(job) + ".bin.ensi.geo").c_str(), "rb");
+  if (!f) return 1;
+  if (fseek(f, 6 * 80 + 4 + 2 * 80 + 4, SEEK_SET) != 0) { fclose(f); return 2; }
+  std::vector<float> ordn((size_t)nn);
+  for (int j = 0; j < 3 && !rc; ++j) {
+    if (fread(ordn.data(), 4, (size_t)nn, f) != (size_t)nn) { rc = 2; break; }
+    for (int64_t i = 0; i < nn; ++i) g_coord[i * 3 + j] = (double)ordn[(size_t)i];
+  }
+  if (!rc && fseek(f, 80 + 4, SEEK_CUR) != 0) rc = 2;
+  if (!rc && fread(g_num, 4, (size_t)(nels * nod), f) != (size_t)(nels * nod)) rc = 2;
+  fclose(f);
+  if (!rc)
+    for (int64_t i = 0; i < nels * nod; ++i) if (g_num[i] < 1 || g_num[i] > nn) return 8;
+  return rc;
+}
+
+/* EnSight node order -> Smith & Griffiths order, in place (the inverse of mesh_ensi_geo_bin's permutation) */
+int pf_ensi2sg(int nod, int64_t nels, int32_t *g_num) {
+  const int *ord = ensi_order(nod);
+  if (!ord) return 1;
+  for (int64_t e = 0; e < nels; ++e) {
+    int32_t t[20];
+    for (int m = 0; m < nod; ++m) t[m] = g_num[e * nod + m];
+    for (int m = 0; m < nod; ++m) g_num[e * nod + ord[m] - 1] = t[m];
+  }
+  return 0;
+}
+
 /* Tables of the exchanges fused into the PCG kernels of the peer transport (device.cu: k_pupdate stores every new p
  * value a peer's elements gather straight into that peer's halo segment; k_dot adds the received partial sums
  * chunk by chunk).  Pure index work on the halo tables of pf_setup_mesh, kept here so that it is testable on CPU. */

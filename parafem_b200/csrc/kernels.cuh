@@ -281,6 +281,47 @@ k_matvec_sym(const double *__restrict__ kp, const int *__restrict__ ggl, const d
   }
 }
 
+// ----------------------------------------------------------------------------
+// a14: pcg_km (maths.f90:1152-1323) -- ONE element matrix km(ntot,ntot) shared by every element
+// (utemp_pp = MATMUL(km,pmul_pp)).  Nothing streams from HBM but the gather indices and the vectors: thread
+// (element slot, row) keeps its row of km in registers, the right-hand sides of the block's elements are staged in
+// shared memory, every product is the j-ascending sum from 0.0 with separate multiply and add -- the same bits as
+// MATMUL on a replicated storkm_pp.  FP64-pipe bound.
+// ----------------------------------------------------------------------------
+template <int NTOT, bool GATHER>
+__global__ void __launch_bounds__(64)
+k_matvec_km(const double *__restrict__ km1, const int *__restrict__ ggl, const double *__restrict__ pvec,
+            double *__restrict__ utemp, long long nels, const State *st, PeerTable *T) {
+  constexpr int THREADS = 64, EPB = THREADS / NTOT;        // elements per block pass
+  static_assert(NTOT <= THREADS, "one thread per row");
+  if (st && *(volatile const int *)&st->done) return;
+  __shared__ double pm[EPB * NTOT];
+  const int t = threadIdx.x, el = t / NTOT, row = t - el * NTOT;
+  const bool on = el < EPB;
+  double K[NTOT];
+#pragma unroll
+  for (int j = 0; j < NTOT; ++j) K[j] = on ? km1[j * NTOT + row] : 0.0;
+  if (GATHER && T) { if (t < 32) warp_wait_fwd(T, st); __syncthreads(); }
+  const long long npass = (nels + EPB - 1) / EPB;
+  for (long long b = blockIdx.x; b < npass; b += gridDim.x) {
+    const long long e0 = b * EPB;
+    const int ne = (int)((nels - e0) < EPB ? (nels - e0) : EPB);
+    __syncthreads();
+    for (int q = t; q < ne * NTOT; q += THREADS) {
+      if (GATHER) pm[q] = T ? __ldcg(pvec + ggl[e0 * NTOT + q]) : pvec[ggl[e0 * NTOT + q]];
+      else pm[q] = pvec[e0 * NTOT + q];
+    }
+    __syncthreads();
+    if (on && el < ne) {
+      const double *pv = pm + el * NTOT;
+      double a = 0.0;
+#pragma unroll
+      for (int j = 0; j < NTOT; ++j) a = a + K[j] * pv[j];
+      utemp[(e0 + el) * NTOT + row] = a;
+    }
+  }
+}
+
 // pmul materialised (pf_gather only; the solver never does this)
 __global__ void k_gather(const int *__restrict__ ggl, const double *__restrict__ p_ext,
                          double *__restrict__ pmul, long long n) {

@@ -210,18 +210,37 @@ def cube_p125(nxe, nye, nze, aa=None, bb=None, cc=None, kx=1.0, ky=1.0, kz=1.0, 
     return p
 
 
-def read_deck_p121(job, npes=1, numpe=1):
+def write_geo_bin(job, g_coord, g_num_sg):
+    """mesh_ensi_geo_bin (input.f90:7986-8164), what p12meshgenbin writes beside the ASCII deck: <job>.bin.ensi.geo,
+    EnSight Gold "C Binary" geometry -- single-precision coordinates, connectivity in EnSight's node order."""
+    gc, gn = f64(g_coord), i32(g_num_sg)
+    check(lib().pf_write_geo_bin(job.encode(), gn.shape[1], gc.shape[0], gn.shape[0], ptr(gc), ptr(gn)), what="pf_write_geo_bin")
+
+
+def _read_mesh(job, nn, nels, nod, meshgen, binary):
+    """g_coord (nn,3), g_num (nels,nod) in S&G order: read_g_num_pp + abaqus2sg + read_g_coord_pp from <job>.d, or
+    their _be variants (input.f90:632-790, 1254-1420) from <job>.bin.ensi.geo when ``binary``."""
+    L = lib()
+    g_coord = np.empty((nn, 3), np.float64)
+    g_num = np.empty((nels, nod), np.int32)
+    if binary:
+        check(L.pf_read_geo_bin(job.encode(), nn, nels, nod, ptr(g_coord), ptr(g_num)), what="pf_read_geo_bin")
+        check(L.pf_ensi2sg(nod, nels, ptr(g_num)), what="pf_ensi2sg")     # for 8-node bricks == abaqus2sg (xx12.f90:118-121)
+    else:
+        check(L.pf_read_d(job.encode(), nn, nels, nod, ptr(g_coord), ptr(g_num)), what="pf_read_d")
+        if meshgen == 2:
+            check(L.pf_abaqus2sg(nod, nels, ptr(g_num)), what="pf_abaqus2sg")
+    return g_coord, g_num
+
+
+def read_deck_p121(job, npes=1, numpe=1, binary=False):
     """read_p121 + read_g_num_pp + abaqus2sg + read_g_coord_pp + read_rest + steering +
-    read_loads + load (p121.f90:28-49, 79-85) for one rank."""
+    read_loads + load (p121.f90:28-49, 79-85) for one rank.  binary: mesh from <job>.bin.ensi.geo."""
     L = lib()
     info = DeckInfo()
     check(L.pf_read_dat(job.encode(), 121, C.byref(info)), what="pf_read_dat")
     nod, nn, nels, nr, loaded = info.nod, info.nn, info.nels, info.nr, info.loaded
-    g_coord = np.empty((nn, 3), np.float64)
-    g_num = np.empty((nels, nod), np.int32)
-    check(L.pf_read_d(job.encode(), nn, nels, nod, ptr(g_coord), ptr(g_num)), what="pf_read_d")
-    if info.meshgen == 2:
-        check(L.pf_abaqus2sg(nod, nels, ptr(g_num)), what="pf_abaqus2sg")
+    g_coord, g_num = _read_mesh(job, nn, nels, nod, info.meshgen, binary)
     if info.partitioner == 2:      # external partition: <job>.psize, elements pre-sorted by rank
         nels_pp, iel_start = read_psize(job, npes, numpe)
     elif info.partitioner == 1:
@@ -260,7 +279,7 @@ def read_deck_p125(job, npes=1, numpe=1):
     return read_deck_p123(job, npes, numpe, program=125)
 
 
-def read_deck_p123(job, npes=1, numpe=1, program=123):
+def read_deck_p123(job, npes=1, numpe=1, program=123, binary=False):
     """Input section of p123.f90:27-55,94-131 (and of programs/dev/xx11/xx11.f90, which shares its deck format)
     for one rank: read_p123, read_g_num_pp, abaqus2sg, read_g_coord_pp, read_rest + rearrange_2/find_g4 -- or
     g_g_pp = g_num_pp when nr = 0 (p123.f90:54) --, read_loads (first column = global equation number,
@@ -271,11 +290,7 @@ def read_deck_p123(job, npes=1, numpe=1, program=123):
     nod, nn, nels, nr = info.nod, info.nn, info.nels, info.nr
     if nod not in (8, 4):
         raise PfError("p123 decks hold 8-node bricks (or, for xx11, 4-node tetrahedra)")
-    g_coord = np.empty((nn, 3), np.float64)
-    g_num = np.empty((nels, nod), np.int32)
-    check(L.pf_read_d(job.encode(), nn, nels, nod, ptr(g_coord), ptr(g_num)), what="pf_read_d")
-    if info.meshgen == 2:
-        check(L.pf_abaqus2sg(nod, nels, ptr(g_num)), what="pf_abaqus2sg")
+    g_coord, g_num = _read_mesh(job, nn, nels, nod, info.meshgen, binary)
     nels_pp, iel_start = read_psize(job, npes, numpe) if info.partitioner == 2 else calc_nels_pp(nels, npes, numpe)
     g_num_pp = np.ascontiguousarray(g_num[iel_start - 1:iel_start - 1 + nels_pp])
     g_coord_pp = np.empty((nels_pp, 3, nod), np.float64)

@@ -2,6 +2,7 @@
 and writes the ParaFEM input deck <job>.d / .bnd / .lds / .dat (/ .mat) in the reference's formats.
 
   python -m parafem_b200.meshgen <job>          # <job>.mg -> deck, iotype 'parafem'
+  python -m parafem_b200.meshgen --bin <job>    # p12meshgenbin: the deck plus <job>.bin.ensi.geo (binary geometry)
 
 .mg layouts (tokens may be spread over lines arbitrarily):
   'p121' / iotype nels nxe nze nod nip / aa bb cc e v / tol limit                       (p12meshgen.f90:118-127)
@@ -32,8 +33,16 @@ def _global_coords(p):
     return g
 
 
-def generate(job):
-    """<job>.mg -> deck files; returns the host.Problem that was written."""
+def generate(job, binary=False):
+    """<job>.mg -> deck files; returns the host.Problem that was written.  binary: also <job>.bin.ensi.geo, as
+    tools/preprocessing/p12meshgenbin does (mesh_ensi_geo_bin)."""
+    p = _generate(job)
+    if binary:
+        host.write_geo_bin(job, _global_coords(p), p.g_num_pp)
+    return p
+
+
+def _generate(job):
     prog, iotype, v = read_mg(job + ".mg")
     if iotype != "parafem":
         raise PfError(f"iotype '{iotype}': only 'parafem' decks are written (the 'paraview' branch is a viewer export)")
@@ -77,10 +86,12 @@ def generate(job):
 
 def main(argv=None):
     argv = sys.argv[1:] if argv is None else argv
+    binary = "--bin" in argv
+    argv = [a for a in argv if a != "--bin"]
     if len(argv) != 1:
         print(__doc__)
         return 2
-    p = generate(argv[0])
+    p = generate(argv[0], binary=binary)
     print(f"{argv[0]}: program p{p.program}, {p.nels} elements, {p.nn} nodes, {p.nr} restrained, {p.neq} equations")
     return 0
 

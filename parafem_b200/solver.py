@@ -123,6 +123,15 @@ class Solver:
         self._ck(lib().pf_pcg_solve(self._h, ptr(r), tol, limit, ptr(x), C.byref(it), C.byref(cv)), "pf_pcg_solve")
         return x, it.value, bool(cv.value)
 
+    def pcg_km(self, km, diag_precon_pp, r_pp, tol, limit):
+        """PCG_KM (maths.f90:1152-1323): one km(ntot,ntot) for every element. -> (xnew_pp, iters, converged)"""
+        k, dg, r = f64(km), f64(diag_precon_pp), f64(r_pp)
+        assert k.shape == (self.prob.ntot, self.prob.ntot) and dg.size == r.size == self.prob.neq_pp
+        x = np.empty(self.prob.neq_pp)
+        it, cv = C.c_int(), C.c_int()
+        self._ck(lib().pf_pcg_km(self._h, ptr(k), ptr(dg), ptr(r), tol, limit, ptr(x), C.byref(it), C.byref(cv)), "pf_pcg_km")
+        return x, it.value, bool(cv.value)
+
     def pcg_load_rhs(self, r_pp):
         self._ck(lib().pf_pcg_load_rhs(self._h, ptr(f64(r_pp))), "pf_pcg_load_rhs")
 

@@ -237,3 +237,23 @@ def test_errors_are_codes_not_exits(gpu):
         s.prob = PROBLEMS["tiny_hex20"]()
         s.build_precon()          # no mesh yet -> status > 0 + message, never exit()
     s.close()
+
+
+@pytest.mark.parametrize("name", ["tiny_hex20", "hex8_elastic", "p123_box"])
+def test_pcg_km_shared_element_matrix(gpu, name):
+    """PCG_KM (maths.f90:1152-1323): one km for every element, the caller's inverted diagonal.
+    On a p12meshgen box all elements are congruent, so the routine applies; == the oracle's solve on the replicated
+    matrix, bit for bit (x, iteration count, every checon ratio)."""
+    p = PROBLEMS[name]()
+    km = km_oracle(p)
+    shared = np.ascontiguousarray(np.broadcast_to(km[0], km.shape))
+    ref = oracle.pcg(shared, p.g_g_pp, p.neq, p.r_pp, p.tol, p.limit, npes=1, red_mode=1)
+    gpu.setup_mesh(p)
+    x, iters, conv = gpu.pcg_km(km[0], ref["diag"], p.r_pp, p.tol, p.limit)
+    assert conv and iters == ref["iters"] and np.array_equal(x, ref["x"])
+    assert np.array_equal(gpu.ratio_history(), ref["ratio"])
+    # the per-element path is back after the next formation call
+    solver.setup_problem(gpu, p)
+    x2, it2, _ = gpu.pcg_solve(p.r_pp, p.tol, p.limit)
+    full = oracle.pcg(km, p.g_g_pp, p.neq, p.r_pp, p.tol, p.limit, npes=1, red_mode=1)
+    assert it2 == full["iters"] and np.array_equal(x2, full["x"])

@@ -63,7 +63,7 @@ def test_p122_demo_golden_log_and_field(deck, golden, tmp_path):
         out = driver.run_p122(p, s, out_base=str(tmp_path / "p122_demo"))
     rows = out["rows"]
     assert len(rows) == len(gold_d) == 10
-    assert f"{out['dt']:.4E}" == "1.0400E-04"                        # "The critical timestep is    0.1040E-03"
+    assert f"{out['dt']:.3E}" == "5.200E-04"                         # "The critical timestep is     0.5200E-03"
     for (d1, sz, sx, sy, cjtot, plasiters), d, sg, cj, pl in zip(rows, gold_d, gold_s, gold_cj, gold_pl):
         assert (cjtot, plasiters) == (cj, pl)
         assert abs(d1 - d) <= 6e-4 * abs(d)

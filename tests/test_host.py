@@ -451,3 +451,46 @@ def test_deck_node_numbers_are_range_checked(tmp_path, tiny, golden):
     assert lib().pf_coords_pp(20, good.nels_pp, nn, ptr(g_num), ptr(np.zeros((nn, 3))), ptr(out)) == 5
     r = np.empty(good.neq_pp)
     assert lib().pf_load(3, 1, nn, ptr(np.array([nn + 1], np.int32)), ptr(np.ones(3)), ptr(good.nf), 1, good.neq_pp, ptr(r)) == 5
+
+
+@pytest.mark.parametrize("prog,nod", [("p121", 20), ("p121", 8), ("p123", 8)])
+def test_binary_geometry_deck_round_trip(tmp_path, prog, nod):
+    """<job>.bin.ensi.geo as p12meshgenbin writes it (mesh_ensi_geo_bin, input.f90:7986-8164) and
+    read_g_coord_pp_be / read_g_num_pp_be read it (input.f90:632-790, 1254-1420), against the ASCII deck of the same
+    mesh: identical steering (connectivity, g_g_pp, loads), coordinates equal after the trip through the file's
+    C floats, and the byte layout of the header (nine 80-character records, part number, nn)."""
+    import struct
+    from parafem_b200 import meshgen
+    job = str(tmp_path / "box")
+    if prog == "p121":
+        open(job + ".mg", "w").write(f"'p121'\n'parafem'\n{6 * 5 * 4} 6 4 {nod} 8\n0.5 0.4 0.25 100.0 0.3\n1.0e-5 300\n")
+    else:
+        open(job + ".mg", "w").write("'p123'\n'parafem'\n120 6 4 8\n0.5 0.4 0.25 2.0 2.0 2.0\n1.0e-5 300\n1 0\n")
+    written = meshgen.generate(job, binary=True)
+    raw = open(job + ".bin.ensi.geo", "rb").read()
+    recs = [raw[80 * k:80 * k + 80].decode().rstrip() for k in range(6)]
+    assert recs == ["C Binary", "Problem name: box", "Geometry files", "node id off", "element id off", "part"]
+    assert struct.unpack("<i", raw[480:484])[0] == 1 and raw[484:564].decode().rstrip() == "Volume"
+    assert raw[564:644].decode().rstrip() == "coordinates" and struct.unpack("<i", raw[644:648])[0] == written.nn
+    off = 648 + 12 * written.nn
+    assert raw[off:off + 80].decode().rstrip() == ("hexa20" if nod == 20 else "hexa8")
+    assert struct.unpack("<i", raw[off + 80:off + 84])[0] == written.nels and len(raw) == off + 84 + 4 * nod * written.nels
+    read = host.read_deck_p121 if prog == "p121" else host.read_deck_p123
+    a, b = read(job), read(job, binary=True)
+    assert np.array_equal(a.g_num_pp, b.g_num_pp) and np.array_equal(a.g_g_pp, b.g_g_pp) and np.array_equal(a.r_pp, b.r_pp)
+    assert np.array_equal(b.g_coord_pp, a.g_coord_pp.astype(np.float32).astype(np.float64))
+    assert np.abs(a.g_coord_pp - b.g_coord_pp).max() <= 2e-7 * np.abs(a.g_coord_pp).max()
+    # the first element's connectivity in the file is EnSight's order of the S&G numbering (input.f90:8099-8119)
+    first = struct.unpack(f"<{nod}i", raw[off + 84:off + 84 + 4 * nod])
+    order = [1, 4, 8, 5, 2, 3, 7, 6] if nod == 8 else [1, 7, 19, 13, 3, 5, 17, 15, 8, 12, 20, 9, 4, 11, 16, 10, 2, 6, 18, 14]
+    assert list(first) == [int(written.g_num_pp[0, k - 1]) for k in order]
+    # a truncated file and a node number out of range are status codes
+    from parafem_b200 import PfError
+    open(job + ".bin.ensi.geo", "wb").write(raw[:-8])
+    with pytest.raises(PfError):
+        read(job, binary=True)
+    bad = bytearray(raw)
+    bad[off + 84:off + 88] = struct.pack("<i", written.nn + 3)
+    open(job + ".bin.ensi.geo", "wb").write(bytes(bad))
+    with pytest.raises(PfError):
+        read(job, binary=True)
