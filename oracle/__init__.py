@@ -337,6 +337,11 @@ def find_g4(g_num, rest):
     return g
 
 
+def set_mf_order(order):
+    """1 (default): the summation order of k_apply_mf2; 0: that of the round-1 kernel k_apply_mf (PF_MF=1lane)."""
+    lib().orc_set_mf_order(int(order))
+
+
 def apply_mf(g_coord_pp, nod, nip, e, v, pmul):
     """Matrix-free element products (config E): utemp = sum_gp B^T D B p det w, oracle order."""
     g, pm = _f64(g_coord_pp), _f64(pmul)

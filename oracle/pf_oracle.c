@@ -82,12 +82,41 @@ int orc_sample_hex(int nip, double *points, double *weights) {
   return 1;
 }
 
-/* sample('tetrahedron'), nip = 1 (new_library.f90:1329-1341): the centroid, weight 1/6.  The 4- and 5-point
- * rules are written with single-precision literals there and are not restated. */
+/* sample('tetrahedron') (new_library.f90:1328-1378), weights already multiplied by 1/6: nip = 1 the centroid;
+ * nip = 4 and 5 are written there with DEFAULT-REAL (single-precision) literals -- .58541020, .13819660, .25/6.,
+ * 1./6., -.8, 9./20. -- which Fortran evaluates in single precision and then widens: restated with floats. */
 int orc_sample_tet(int nip, double *points, double *weights) {
-  if (nip != 1) return 1;
-  points[0] = points[1] = points[2] = 0.25; weights[0] = 1.0 / 6.0;
-  return 0;
+#define S(i, j) points[((j)-1) * nip + ((i)-1)]
+  if (nip == 1) {
+    S(1, 1) = S(1, 2) = S(1, 3) = 0.25; weights[0] = 1.0 / 6.0;
+    return 0;
+  }
+  for (int q = 0; q < 3 * nip; ++q) points[q] = 0.0;
+  if (nip == 4) {
+    const double a = (double).58541020f, b = (double).13819660f;
+    S(1, 1) = a; S(1, 2) = b; S(1, 3) = b;
+    S(2, 2) = a; S(2, 3) = b; S(2, 1) = b;
+    S(3, 3) = a; S(3, 1) = b; S(3, 2) = b;
+    S(4, 1) = b; S(4, 2) = b; S(4, 3) = b;
+    const float w = .25f / 6.f;
+    for (int i = 0; i < 4; ++i) weights[i] = (double)w;
+    return 0;
+  }
+  if (nip == 5) {
+    const float sixth = 1.f / 6.f;
+    S(1, 1) = (double).25f; S(1, 2) = (double).25f; S(1, 3) = (double).25f;
+    S(2, 1) = (double).5f; S(2, 2) = (double)sixth; S(2, 3) = S(2, 2);
+    S(3, 2) = (double).5f; S(3, 3) = (double)sixth; S(3, 1) = S(3, 3);
+    S(4, 3) = (double).5f; S(4, 1) = (double)sixth; S(4, 2) = S(4, 1);
+    S(5, 1) = (double)sixth; S(5, 2) = S(5, 1); S(5, 3) = S(5, 1);
+    weights[0] = (double)(-.8f);
+    weights[1] = (double)(9.f / 20.f);
+    weights[2] = weights[3] = weights[4] = weights[1];
+    for (int i = 0; i < 5; ++i) weights[i] = weights[i] / (double)6.f;      /* wt = wt/6. : REAL(iwp) / default real */
+    return 0;
+  }
+#undef S
+  return 1;
 }
 /* the rule of an element with nod nodes: tetrahedron for nod = 4, hexahedron otherwise */
 static int sample_for(int nod, int nip, double *points, double *weights) {
@@ -234,7 +263,7 @@ static double gauss_point(int nod, const double *points, int nip, int ig, const 
  * g_coord_pp(nod,3,nels), storkm_pp(ntot,ntot,nels), ntot = 3*nod. */
 int orc_form_km_elastic(int64_t nels, int nod, int nip, const double *g_coord_pp, double e,
                         double v, double *storkm_pp) {
-  if ((nod != 4 && nod != 8 && nod != 20) || (nip != 1 && nip != 8) || (nod == 4 && nip != 1)) return 1;
+  if ((nod != 4 && nod != 8 && nod != 20) || (nod != 4 && nip != 1 && nip != 8) || (nod == 4 && nip != 1 && nip != 4 && nip != 5)) return 1;
   const int ntot = 3 * nod;
   double points[24], weights[8], dee[36];
   sample_for(nod, nip, points, weights);
@@ -275,7 +304,7 @@ int orc_form_km_elastic(int64_t nels, int nod, int nip, const double *g_coord_pp
 /* elements_1 of p123.f90:70-84: kcx,kcy,kcz outer products; storkc_pp(8,8,nels) */
 int orc_form_kc_laplace(int64_t nels, int nod, int nip, const double *g_coord_pp, double kx,
                         double ky, double kz, double *storkc_pp) {
-  if ((nod != 8 && nod != 4) || (nip != 1 && nip != 8) || (nod == 4 && nip != 1)) return 1;
+  if ((nod != 8 && nod != 4) || (nod == 8 && nip != 1 && nip != 8) || (nod == 4 && nip != 1 && nip != 4 && nip != 5)) return 1;
   double points[24], weights[8];
   sample_for(nod, nip, points, weights);
   const int nn2 = nod * nod;
@@ -811,12 +840,17 @@ void orc_matvec(int ntot, int64_t nels, const double *storkm, const double *pmul
  *   eps    = (G00, G11, G22, G10+G01, G21+G12, G20+G02)      beemat's row order
  *   sigma  = D eps                          product + c-ascending fmas per row, then * det*w
  *   T(b,c) = sum_a inv(a,b) S(a,c)          S = symmetric stress tensor; product, two fmas
- * and then per dof ONE chain over (Gauss point ascending, b ascending):
- *   u_c(m) = sum_gp sum_b der_gp(b,m) T_gp(b,c)      first term a product, then 23 fmas.
- * This is the operation order of k_apply_mf in parafem_b200/csrc/kernels.cuh.  It is a
+ * and then per dof one chain over (Gauss point ascending, b ascending) for each HALF of the points, the two added:
+ *   u_c(m) = [sum_{gp<4} sum_b der_gp(b,m) T_gp(b,c)] + [sum_{gp>=4} ...]   each: first term a product, then 11 fmas
+ * (orc_set_mf_order(0): ONE 24-term chain, the round-1 kernel).
+ * This is the operation order of k_apply_mf2 in parafem_b200/csrc/kernels.cuh.  It is a
  * different rounding of the same operator as MATMUL(storkm,pmul) (p121.f90:94), hence its
  * own oracle.
  */
+/* 1: the order of k_apply_mf2 (two lanes per element, the default kernel); 0: the order of the round-1 kernel
+ * k_apply_mf (PF_MF=1lane) */
+static int g_mf_order = 1;
+void orc_set_mf_order(int order) { g_mf_order = order ? 1 : 0; }
 static void mf_element(int nod, double der[8][60] /*[ig][a*20+m]*/, const double *coord, const double *dee,
                        const double *weights, const double *pm, double *ut) {
   double T[8][9];
@@ -862,13 +896,27 @@ static void mf_element(int nod, double der[8][60] /*[ig][a*20+m]*/, const double
   }
   for (int m = 0; m < nod; ++m)
     for (int c = 0; c < 3; ++c) {
-      double s = der[0][m] * T[0][c];
-      for (int ig = 0; ig < 8; ++ig)
-        for (int b = 0; b < 3; ++b) {
-          if (ig == 0 && b == 0) continue;
-          s = fma(der[ig][b * 20 + m], T[ig][b * 3 + c], s);
+      if (g_mf_order == 0) {            /* k_apply_mf (round 1): one 24-term chain */
+        double s = der[0][m] * T[0][c];
+        for (int ig = 0; ig < 8; ++ig)
+          for (int b = 0; b < 3; ++b) {
+            if (ig == 0 && b == 0) continue;
+            s = fma(der[ig][b * 20 + m], T[ig][b * 3 + c], s);
+          }
+        ut[3 * m + c] = s;
+      } else {                          /* k_apply_mf2: a 12-term chain per half of the points, then one add */
+        double part[2];
+        for (int hf = 0; hf < 2; ++hf) {
+          double s = der[4 * hf][m] * T[4 * hf][c];
+          for (int ig = 4 * hf; ig < 4 * hf + 4; ++ig)
+            for (int b = 0; b < 3; ++b) {
+              if (ig == 4 * hf && b == 0) continue;
+              s = fma(der[ig][b * 20 + m], T[ig][b * 3 + c], s);
+            }
+          part[hf] = s;
         }
-      ut[3 * m + c] = s;
+        ut[3 * m + c] = part[0] + part[1];
+      }
     }
 }
 

@@ -314,9 +314,23 @@ int shape_der_at(int nod, double xi, double eta, double zeta, double *D, double 
 int fill_tables(int nod, int nip, double e, double v, double kx, double ky, double kz, ElemTables &T) {
   memset(&T, 0, sizeof T);
   double pts[8][3];
-  if (nod == 4) {          // sample('tetrahedron'), nip = 1 (new_library.f90:1329-1341): centroid, weight 1/6
-    if (nip != 1) return 1;
-    pts[0][0] = pts[0][1] = pts[0][2] = 0.25; T.weights[0] = 1.0 / 6.0;
+  if (nod == 4) {          // sample('tetrahedron') (new_library.f90:1328-1378): nip = 1 centroid, weight 1/6;
+    // nip = 4 / 5 are written with default-real (single-precision) literals there: restated with floats
+    for (int i = 0; i < 8; ++i) pts[i][0] = pts[i][1] = pts[i][2] = 0.0;
+    if (nip == 1) { pts[0][0] = pts[0][1] = pts[0][2] = 0.25; T.weights[0] = 1.0 / 6.0; }
+    else if (nip == 4) {
+      const double a = (double).58541020f, b = (double).13819660f;
+      for (int i = 0; i < 4; ++i) { pts[i][0] = pts[i][1] = pts[i][2] = b; T.weights[i] = (double)(.25f / 6.f); }
+      pts[0][0] = a; pts[1][1] = a; pts[2][2] = a;
+    } else if (nip == 5) {
+      const double q = (double).25f, hf = (double).5f, sx = (double)(1.f / 6.f);
+      pts[0][0] = pts[0][1] = pts[0][2] = q;
+      for (int i = 1; i < 5; ++i) pts[i][0] = pts[i][1] = pts[i][2] = sx;
+      pts[1][0] = hf; pts[2][1] = hf; pts[3][2] = hf;
+      T.weights[0] = (double)(-.8f);
+      for (int i = 1; i < 5; ++i) T.weights[i] = (double)(9.f / 20.f);
+      for (int i = 0; i < 5; ++i) T.weights[i] = T.weights[i] / (double)6.f;
+    } else return 1;
   } else if (nip == 1) { pts[0][0] = pts[0][1] = pts[0][2] = 0.0; T.weights[0] = 8.0; }
   else if (nip == 8) {
     const double r3 = 1.0 / std::sqrt(3.0);
@@ -397,6 +411,28 @@ int launch_matvec_km_t(pf_handle h, const double *pvec, const State *st, PeerTab
   return 0;
 }
 
+// k_apply_mf2: two lanes per element, 16 warps per SM (the default; PF_MF=1lane selects k_apply_mf)
+constexpr int kMf2Warps = 16;
+bool mf_two_lanes() {
+  static const bool on = !(getenv("PF_MF") && !strcmp(getenv("PF_MF"), "1lane"));
+  return on;
+}
+int mf2_grid(pf_handle h) {
+  const int64_t nhg = (h->nels + 15) / 16;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (nhg + kMf2Warps - 1) / kMf2Warps));
+}
+template <int NOD, bool GATHER, int GEOM>
+int launch_mf2_t(pf_handle h, const double *pvec, const State *st, PeerTable *T = nullptr) {
+  using Cfg = Mf2Cfg<NOD>;
+  auto kern = k_apply_mf2<NOD, GATHER, GEOM, kMf2Warps>;
+  if (int rc_ = ensure_smem(h, kern, Cfg::smem(kMf2Warps))) return rc_;
+  kern<<<mf2_grid(h), kMf2Warps * 32, Cfg::smem(kMf2Warps), h->stream>>>(h->coord.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st,
+                                                                          h->geom.p, T);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
 template <bool GATHER>
 int launch_matvec(pf_handle h, const double *pvec, const State *st, PeerTable *T = nullptr) {
   Scope sc(h, K_MATVEC);
@@ -409,6 +445,10 @@ int launch_matvec(pf_handle h, const double *pvec, const State *st, PeerTable *T
       case 4: return launch_matvec_km_t<4, GATHER>(h, pvec, st, T);
     }
     return fail(h, 3, "unsupported ntot %d", h->ntot);
+  }
+  if (h->matrix_free && mf_two_lanes()) {
+    if (h->mf_mode == 2) return h->nod == 20 ? launch_mf2_t<20, GATHER, 2>(h, pvec, st, T) : launch_mf2_t<8, GATHER, 2>(h, pvec, st, T);
+    return h->nod == 20 ? launch_mf2_t<20, GATHER, 0>(h, pvec, st, T) : launch_mf2_t<8, GATHER, 0>(h, pvec, st, T);
   }
   if (h->matrix_free) {
     if (h->mf_mode == 2) {
@@ -952,8 +992,8 @@ int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp, con
   // nobody enters the collectives below unless every rank got through (agree) ----
   auto local_a = [&]() -> int {
     NEED((nod == 4 || nod == 8 || nod == 20) && (nodof == 1 || nodof == 3), "nod must be 4 (tetrahedra), 8 or 20 (hexahedra), nodof 1 or 3");
-    NEED(nip == 1 || nip == 8, "nip must be 1 or 8");
-    NEED(nod != 4 || nip == 1, "4-node tetrahedra take nip = 1");
+    NEED(nip == 1 || nip == 8 || (nod == 4 && (nip == 4 || nip == 5)), "nip must be 1 or 8 (hexahedra), 1, 4 or 5 (tetrahedra)");
+    NEED(nod != 4 || nip != 8, "4-node tetrahedra take nip = 1, 4 or 5");
     NEED(nels_pp >= 1 && neq >= 1 && neq_pp >= 0 && ieq_start >= 1, "bad sizes");
     NEED(ntot == 60 || ntot == 24 || ntot == 8 || ntot == 12 || ntot == 4,
          "supported element types: hex20 / hex8 / tet4 elastic, hex8 / tet4 scalar");
@@ -1143,12 +1183,13 @@ int pf_form_km_elastic(pf_handle h, double e, double v) {
     if (h->mf_mode == 2) {
       // geometric factors: inverse Jacobian (9) + det*w (1) per element and Gauss point
       CU(h->geom.alloc((size_t)((h->nels + 31) / 32) * 32 * 80));   // [group][point][word][lane], padded to whole groups
-      if (h->nod == 20) rc = launch_mf_t<20, false, 1>(h, nullptr, nullptr);
+      if (mf_two_lanes()) rc = h->nod == 20 ? launch_mf2_t<20, false, 1>(h, nullptr, nullptr) : launch_mf2_t<8, false, 1>(h, nullptr, nullptr);
+      else if (h->nod == 20) rc = launch_mf_t<20, false, 1>(h, nullptr, nullptr);
       else rc = launch_mf_t<8, false, 1>(h, nullptr, nullptr);
       if (rc) return rc;
     } else {
-      // mode 1: the factors are rebuilt every call; one 640 B scratch line per resident thread
-      CU(h->geom.alloc((size_t)mf_grid(h) * kMfWarps * 32 * 80));
+      // mode 1: the factors are rebuilt every call; one 640 B scratch line per resident element slot
+      CU(h->geom.alloc((size_t)std::max(mf_grid(h) * kMfWarps, mf2_grid(h) * kMf2Warps) * 32 * 80));
     }
   } else if ((rc = alloc_km(h))) return rc;
   const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 16);

@@ -1561,6 +1561,246 @@ k_apply_mf(const double *__restrict__ g_coord, const int *__restrict__ ggl, cons
 }
 
 // ----------------------------------------------------------------------------
+// k_apply_mf2: the same operator with TWO LANES PER ELEMENT (round 2).  k_apply_mf above keeps 72 T values, 36 H
+// accumulators and the factors of three points in one thread: ~254 registers, 8 warps per SM, and ncu showed the
+// FP64 pipe 49 % active with nothing saturated -- a latency problem.  Here lane `half` of an element's lane pair owns
+// the Gauss points 4*half .. 4*half+3: 36 H accumulators -> 36 T values per lane, <= 128 registers, 16 warps per SM
+// with the same number of elements in flight and the same FP64 work per element.  Phase 2 forms, per freedom, one chain
+// over the lane's four points (first term a product, then 11 fma) and the two chains are added with one shuffle:
+//   u_c(m) = [sum_{g<4} sum_b der_g(b,m) T_g(b,c)] + [sum_{g>=4} sum_b der_g(b,m) T_g(b,c)]
+// (orc_apply_mf mirrors exactly this).  A warp owns 16 consecutive elements; shared-memory rows, the bulk-copied
+// gather indices and the factor layout [group of 32][point][word][lane] are those of k_apply_mf.
+// ----------------------------------------------------------------------------
+template <int NOD>
+struct Mf2Cfg {
+  static constexpr int NTOT = 3 * NOD, kRow = NTOT + 2, EPW = 16;   // elements per warp
+  static constexpr int kIdxBytes = EPW * NTOT * 4;
+  static constexpr int kDerBytes = NOD * 24 * 8;
+  static constexpr size_t smem(int warps) { return (size_t)kDerBytes + (size_t)warps * (EPW * kRow * 8 + kIdxBytes + 16); }
+};
+
+template <int NOD, bool GATHER, int GEOM, int WARPS, int UNR = 2>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_apply_mf2(const double *__restrict__ g_coord, const int *__restrict__ ggl, const double *__restrict__ pvec,
+            double *__restrict__ utemp, long long nels, const State *st, double *geom, PeerTable *T) {
+  using Cfg = Mf2Cfg<NOD>;
+  constexpr int NTOT = Cfg::NTOT, ROW = Cfg::kRow, KP = (NTOT + 31) / 32, EPW = Cfg::EPW;
+  constexpr long long kGroupGeom = 32LL * 80;               // doubles per group of 32 elements (MfCfg::kGroupGeom)
+  static_assert(NOD % 2 == 0, "nodes are processed in pairs");
+  if (st && *(volatile const int *)&st->done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int el = lane >> 1, half = lane & 1;                 // this lane's element of the warp's 16 and its half of the points
+  double *s_der = reinterpret_cast<double *>(smem_raw);                                   // [m][g][b]
+  double *rows = reinterpret_cast<double *>(smem_raw + Cfg::kDerBytes) + (size_t)w * EPW * ROW;
+  int *idxbuf = reinterpret_cast<int *>(smem_raw + Cfg::kDerBytes + (size_t)WARPS * EPW * ROW * 8) + (size_t)w * EPW * NTOT;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + Cfg::kDerBytes + (size_t)WARPS * (EPW * ROW * 8 + Cfg::kIdxBytes));
+  const uint32_t bar = smem_u32(&bars[w]);
+  const uint32_t row_s = smem_u32(rows + el * ROW);          // this lane pair's element row
+  for (int q = threadIdx.x; q < NOD * 24; q += blockDim.x) {
+    const int m = q / 24, r = q - m * 24, g = r / 3, b = r - g * 3;
+    s_der[q] = c_tab.der[g * 60 + b * 20 + m];
+  }
+  __syncthreads();
+  const long long nhg = (nels + EPW - 1) / EPW;              // half-groups of 16 elements
+  const long long hstride = (long long)gridDim.x * WARPS;
+  uint64_t policy = 0;
+  uint32_t phase = 0;
+  auto issue_idx = [&](long long hg) {                       // lane 0 only
+    const long long e0 = hg * EPW;
+    const int ne = (int)((nels - e0) < EPW ? (nels - e0) : EPW);
+    const uint32_t bytes = (uint32_t)ne * NTOT * 4;
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(smem_u32(idxbuf), ggl + e0 * NTOT, bytes, bar, policy);
+  };
+  long long hg = (long long)blockIdx.x * WARPS + w;
+  if (GATHER && GEOM != 1) {
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+      policy = policy_evict_first();
+      if (hg < nhg) issue_idx(hg);
+    }
+    __syncwarp();
+    if (T) warp_wait_fwd(T, st);
+  }
+  for (; hg < nhg; hg += hstride) {
+    const long long e0 = hg * EPW;
+    const int ne = (int)((nels - e0) < EPW ? (nels - e0) : EPW);
+    const unsigned int pairmask = ne >= EPW ? 0xffffffffu : ((1u << (2 * ne)) - 1u);
+    // this lane pair's 16-byte words of the factors: word (g*5+j) of the element at gfl[(g*5+j)*32]
+    double2 *gfl = reinterpret_cast<double2 *>(geom + (GEOM == 0 ? (long long)blockIdx.x * WARPS + w : (hg >> 1)) * kGroupGeom) +
+                   (GEOM == 0 ? el : (int)(hg & 1) * 16 + el);
+    if (GEOM == 2 && lane == 0 && hg + hstride < nhg) {
+      const long long nh = hg + hstride;                     // next half-group's factors towards L2
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(geom + (nh >> 1) * kGroupGeom),
+                   "r"((uint32_t)(kGroupGeom * 8)) : "memory");
+    }
+    if (GEOM != 2) {
+      // coordinates g_coord_pp(nod,3,nels) -> the elements' rows, [b*NOD+m]
+      for (int e2 = 0; e2 < ne; ++e2)
+#pragma unroll
+        for (int kp = 0; kp < KP; ++kp) {
+          const int k = lane + 32 * kp;
+          if (k < NTOT) rows[e2 * ROW + k] = g_coord[(e0 + e2) * NTOT + k];
+        }
+      __syncwarp();
+      if (el < ne) {
+        double J[4][9];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int z = 0; z < 9; ++z) J[g][z] = 0.0;
+#pragma unroll UNR
+        for (int t = 0; t < NOD / 2; ++t) {
+          double cx[2], cy[2], cz[2];
+          lds128(row_s + (2 * t) * 8, cx[0], cx[1]);
+          lds128(row_s + (NOD + 2 * t) * 8, cy[0], cy[1]);
+          lds128(row_s + (2 * NOD + 2 * t) * 8, cz[0], cz[1]);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const double *der = s_der + (2 * t + h) * 24 + half * 12;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const double d0 = der[3 * g], d1 = der[3 * g + 1], d2 = der[3 * g + 2];
+              J[g][0] = fma(d0, cx[h], J[g][0]); J[g][1] = fma(d1, cx[h], J[g][1]); J[g][2] = fma(d2, cx[h], J[g][2]);
+              J[g][3] = fma(d0, cy[h], J[g][3]); J[g][4] = fma(d1, cy[h], J[g][4]); J[g][5] = fma(d2, cy[h], J[g][5]);
+              J[g][6] = fma(d0, cz[h], J[g][6]); J[g][7] = fma(d1, cz[h], J[g][7]); J[g][8] = fma(d2, cz[h], J[g][8]);
+            }
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          double inv[9];
+          const double det = det3(J[g]);
+          inv3(J[g], det, inv);
+          const double f = det * c_tab.weights[4 * half + g];
+          double2 *o = gfl + (4 * half + g) * 5 * 32;
+          o[0] = make_double2(inv[0], inv[1]); o[32] = make_double2(inv[2], inv[3]);
+          o[64] = make_double2(inv[4], inv[5]); o[96] = make_double2(inv[6], inv[7]);
+          o[128] = make_double2(inv[8], f);
+        }
+      }
+      __syncwarp();
+      asm volatile("" ::: "memory");  // GEOM 0 re-reads its scratch line below
+    }
+    if (GEOM != 1) {
+      if (GATHER) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+      }
+      if (ne == EPW) {
+        double val[EPW][KP];
+#pragma unroll
+        for (int e2 = 0; e2 < EPW; ++e2)
+#pragma unroll
+          for (int kp = 0; kp < KP; ++kp) {
+            const int k = lane + 32 * kp;
+            if (GATHER) {
+              const int idx = (k < NTOT) ? idxbuf[e2 * NTOT + k] : 0;
+              val[e2][kp] = T ? __ldca(pvec + idx) : pvec[idx];
+            } else val[e2][kp] = (k < NTOT) ? pvec[(e0 + e2) * NTOT + k] : 0.0;
+          }
+#pragma unroll
+        for (int e2 = 0; e2 < EPW; ++e2)
+#pragma unroll
+          for (int kp = 0; kp < KP; ++kp) {
+            const int k = lane + 32 * kp;
+            if (k < NTOT) rows[e2 * ROW + k] = val[e2][kp];
+          }
+      } else {
+        for (int e2 = 0; e2 < ne; ++e2)
+          for (int k = lane; k < NTOT; k += 32)
+            rows[e2 * ROW + k] = GATHER ? (T ? __ldca(pvec + idxbuf[e2 * NTOT + k]) : pvec[idxbuf[e2 * NTOT + k]]) : pvec[(e0 + e2) * NTOT + k];
+      }
+      __syncwarp();
+      if (GATHER && lane == 0 && hg + hstride < nhg) {
+        fence_proxy_async();  // the warp's generic reads of idxbuf are ordered before the async overwrite
+        issue_idx(hg + hstride);
+      }
+      if (el < ne) {
+        double Tm[4][9];
+        double gq[2][10];                                     // factors of the current point and the next one
+        auto load_gq = [&](int g4, double *dst) {
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const double2 *src = gfl + ((4 * half + g4) * 5 + j) * 32;
+            const double2 v = (GEOM == 2) ? __ldg(src) : *src;
+            dst[2 * j] = v.x; dst[2 * j + 1] = v.y;
+          }
+        };
+        load_gq(0, gq[0]);                                    // in flight during the 4 x 9 x NOD fma below
+        double H[4][9];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int z = 0; z < 9; ++z) H[g][z] = 0.0;
+#pragma unroll UNR
+        for (int t = 0; t < NOD / 2; ++t) {
+          double v[6];
+          lds128(row_s + (6 * t) * 8, v[0], v[1]);
+          lds128(row_s + (6 * t + 2) * 8, v[2], v[3]);
+          lds128(row_s + (6 * t + 4) * 8, v[4], v[5]);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const double px = v[3 * h], py = v[3 * h + 1], pz = v[3 * h + 2];
+            const double *der = s_der + (2 * t + h) * 24 + half * 12;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const double d0 = der[3 * g], d1 = der[3 * g + 1], d2 = der[3 * g + 2];
+              H[g][0] = fma(d0, px, H[g][0]); H[g][1] = fma(d0, py, H[g][1]); H[g][2] = fma(d0, pz, H[g][2]);
+              H[g][3] = fma(d1, px, H[g][3]); H[g][4] = fma(d1, py, H[g][4]); H[g][5] = fma(d1, pz, H[g][5]);
+              H[g][6] = fma(d2, px, H[g][6]); H[g][7] = fma(d2, py, H[g][7]); H[g][8] = fma(d2, pz, H[g][8]);
+            }
+          }
+        }
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {
+          if (g4 + 1 < 4) load_gq(g4 + 1, gq[(g4 + 1) & 1]);  // one point ahead
+          mf_point_mid(H[g4], gq[g4 & 1], gq[g4 & 1][9], Tm[g4]);
+        }
+        // every lane has read its row of right-hand sides: the pair may now overwrite it with the products
+        __syncwarp(pairmask);
+        // phase 2: per freedom one 12-term chain over this lane's four points, then the partner's chain is added
+#pragma unroll UNR
+        for (int t = 0; t < NOD / 2; ++t) {
+          double o[6];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const double *der = s_der + (2 * t + h) * 24 + half * 12;
+            double ox = der[0] * Tm[0][0], oy = der[0] * Tm[0][1], oz = der[0] * Tm[0][2];
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+              for (int b = 0; b < 3; ++b) {
+                if (g == 0 && b == 0) continue;
+                const double d = der[g * 3 + b];
+                ox = fma(d, Tm[g][b * 3], ox); oy = fma(d, Tm[g][b * 3 + 1], oy); oz = fma(d, Tm[g][b * 3 + 2], oz);
+              }
+            o[3 * h] = ox; o[3 * h + 1] = oy; o[3 * h + 2] = oz;
+          }
+#pragma unroll
+          for (int q = 0; q < 6; ++q) o[q] = o[q] + __shfl_xor_sync(pairmask, o[q], 1);   // (points 0-3) + (points 4-7)
+          if ((t & 1) == half) {
+            sts128(row_s + (6 * t) * 8, o[0], o[1]);
+            sts128(row_s + (6 * t + 2) * 8, o[2], o[3]);
+            sts128(row_s + (6 * t + 4) * 8, o[4], o[5]);
+          }
+        }
+      }
+      __syncwarp();
+      for (int e2 = 0; e2 < ne; ++e2)
+#pragma unroll
+        for (int kp = 0; kp < KP; ++kp) {
+          const int k = lane + 32 * kp;
+          if (k < NTOT) utemp[(e0 + e2) * NTOT + k] = rows[e2 * ROW + k];
+        }
+      __syncwarp();
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
 // p122 (programs/5th_ed/p122/p122.f90): elasto-plasticity, Mohr-Coulomb, viscoplastic strain method
 // ----------------------------------------------------------------------------
 // The Gauss-point update of elements_4 (p122.f90:197-231): strain increment from the displacement increment,

@@ -92,5 +92,29 @@ def test_tetrahedra_limits_are_reported(gpu):
     gpu.set_storkm_layout(0)
     bad = tet_problem(host.cube_p121(3, 3, 3, 8, aa=1., bb=1., cc=1.))
     bad.nip = 8
-    with pytest.raises(PfError, match="nip = 1"):
+    with pytest.raises(PfError, match="nip = 1, 4 or 5"):
         gpu.setup_mesh(bad)
+
+
+@pytest.mark.parametrize("nip", [4, 5])
+def test_tetrahedron_four_and_five_point_rules(gpu, nip):
+    """sample('tetrahedron') nip = 4 and 5 (new_library.f90:1343-1378; written there with single-precision literals,
+    restated as floats widened to double): element matrices bit-equal to the oracle for the elastic and the scalar
+    element, and -- the derivatives of a 4-node tetrahedron being constant -- equal to the one-point rule's to the
+    single-precision accuracy of the rule's weights; the solve converges to the same field."""
+    for base in (host.cube_p121(4, 3, 3, 8, aa=1., bb=1., cc=1., limit=3000), host.cube_p123(5, 4, 4, limit=800)):
+        p1 = tet_problem(base)
+        p = tet_problem(base)
+        p.nip = nip
+        solver.setup_problem(gpu, p)
+        km = gpu.get_storkm()
+        ref = (oracle.form_km_elastic(p.g_coord_pp, 4, nip, p.e, p.v) if p.program == 121
+               else oracle.form_kc_laplace(p.g_coord_pp, nip, p.kx, p.ky, p.kz))
+        assert np.array_equal(km, ref)
+        x, iters, conv = gpu.pcg_solve(p.r_pp, p.tol, p.limit)
+        solver.setup_problem(gpu, p1)
+        km1 = gpu.get_storkm()
+        x1, it1, conv1 = gpu.pcg_solve(p1.r_pp, p1.tol, p1.limit)
+        assert conv and conv1 and abs(iters - it1) <= 1
+        assert np.abs(km - km1).max() <= 2e-7 * np.abs(km1).max()
+        assert np.linalg.norm(x - x1) <= 1e-5 * np.linalg.norm(x1)
