@@ -446,10 +446,12 @@ int launch_matvec(pf_handle h, const double *pvec, const State *st, PeerTable *T
     }
     return fail(h, 3, "unsupported ntot %d", h->ntot);
   }
-  if (h->matrix_free && mf_two_lanes()) {
-    if (h->mf_mode == 2) return h->nod == 20 ? launch_mf2_t<20, GATHER, 2>(h, pvec, st, T) : launch_mf2_t<8, GATHER, 2>(h, pvec, st, T);
-    return h->nod == 20 ? launch_mf2_t<20, GATHER, 0>(h, pvec, st, T) : launch_mf2_t<8, GATHER, 0>(h, pvec, st, T);
-  }
+  // mode 2 (stored geometric factors): two lanes per element (k_apply_mf2, measured 0.848 against 0.867 ms at config C);
+  // mode 1 (factors rebuilt from the coordinates every call) keeps the one-lane kernel: its Jacobian pass spills at
+  // 128 registers (1.52 against 1.37 ms).  The two kernels add the points' contributions in different orders; the
+  // oracle mirrors each (orc_apply_mf, order by mode).
+  if (h->matrix_free && h->mf_mode == 2 && mf_two_lanes())
+    return h->nod == 20 ? launch_mf2_t<20, GATHER, 2>(h, pvec, st, T) : launch_mf2_t<8, GATHER, 2>(h, pvec, st, T);
   if (h->matrix_free) {
     if (h->mf_mode == 2) {
       // PF_TUNE: unroll factor of the node-pair loops (default 2; measured in profiles/r01_mf_kernel_history.md)

@@ -126,11 +126,11 @@ def main():
                   else oracle.form_kc_laplace(full.g_coord_pp, full.nip, full.kx, full.ky, full.kz))
         if variant == "sym":      # K(i,j) = L(max,min): the oracle on the symmetrised matrices
             km = np.triu(km) + np.triu(km, 1).transpose(0, 2, 1)
-        mf = dict(g_coord_pp=full.g_coord_pp, nod=full.nod, nip=full.nip, e=full.e, v=full.v) if mf_mode else None
+        mf = dict(g_coord_pp=full.g_coord_pp, nod=full.nod, nip=full.nip, e=full.e, v=full.v, mode=mf_mode) if mf_mode else None
         pm_ref = oracle.gather(full.g_g_pp, pv)
         e0 = p.iel_start - 1
         ok_g = np.array_equal(s.gather(pv[lo:lo + p.neq_pp]), pm_ref[e0:e0 + p.nels_pp])
-        ut_ref = oracle.apply_mf(full.g_coord_pp, full.nod, full.nip, full.e, full.v, pm_ref) if mf_mode else oracle.matvec(km, pm_ref)
+        ut_ref = oracle.apply_mf(full.g_coord_pp, full.nod, full.nip, full.e, full.v, pm_ref, mode=mf_mode) if mf_mode else oracle.matvec(km, pm_ref)
         u_ref = oracle.scatter(full.g_g_pp, ut_ref, p.neq, npes=world)
         s.nfixed_saved = None
         u = s.apply(pv[lo:lo + p.neq_pp])

@@ -31,7 +31,7 @@ def test_matrix_free_products_equal_oracle(gpu, name, mode):
     rng = np.random.RandomState(2)
     pm = rng.randn(p.nels, p.ntot)
     ut = gpu.matvec(pm)
-    ref = oracle.apply_mf(p.g_coord_pp, p.nod, p.nip, p.e, p.v, pm)
+    ref = oracle.apply_mf(p.g_coord_pp, p.nod, p.nip, p.e, p.v, pm, mode=mode)
     assert np.array_equal(ut, ref)
     # and it is the same operator as the stored matrices, to rounding
     km = oracle.form_km_elastic(p.g_coord_pp, p.nod, p.nip, p.e, p.v)
@@ -51,7 +51,7 @@ def test_matrix_free_pcg_equals_oracle(gpu, name, mode):
     solver.setup_problem(gpu, p, matrix_free=mode)
     x, iters, conv = gpu.pcg_solve(p.r_pp, p.tol, p.limit)
     km = oracle.form_km_elastic(p.g_coord_pp, p.nod, p.nip, p.e, p.v)
-    mf = dict(g_coord_pp=p.g_coord_pp, nod=p.nod, nip=p.nip, e=p.e, v=p.v)
+    mf = dict(g_coord_pp=p.g_coord_pp, nod=p.nod, nip=p.nip, e=p.e, v=p.v, mode=mode)
     ref = oracle.pcg(km, p.g_g_pp, p.neq, p.r_pp, p.tol, p.limit, npes=1, red_mode=1, mf=mf)
     assert conv and iters == ref["iters"]
     assert np.array_equal(x, ref["x"])
