@@ -141,6 +141,39 @@ MODULE parafem_gpu
       REAL(c_double),VALUE :: e,v; REAL(c_double) :: sigma(6)
     END FUNCTION
 
+    ! the same at a local point (xi,eta,zeta) of the element (the 2013 build behind p121/book/p121.res
+    ! printed the stress at the last Gauss point)
+    INTEGER(c_int) FUNCTION pf_point_stress(h,iel,xi,eta,zeta,e,v,sigma) BIND(C,name='pf_point_stress')
+      IMPORT; TYPE(c_ptr),VALUE :: h; INTEGER(c_int64_t),VALUE :: iel
+      REAL(c_double),VALUE :: xi,eta,zeta,e,v; REAL(c_double) :: sigma(6)
+    END FUNCTION
+
+    ! PCG_KM (maths.f90:1152-1323): one km(ntot,ntot) for every element, the caller's inverted preconditioner
+    INTEGER(c_int) FUNCTION pf_pcg_km(h,km,diag_precon_pp,r_pp,tol,limit,xnew_pp,iters,converged)  &
+                                      BIND(C,name='pf_pcg_km')
+      IMPORT; TYPE(c_ptr),VALUE :: h; REAL(c_double) :: km(*),diag_precon_pp(*),r_pp(*),xnew_pp(*)
+      REAL(c_double),VALUE :: tol; INTEGER(c_int),VALUE :: limit; INTEGER(c_int) :: iters,converged
+    END FUNCTION
+
+    ! p122.f90:88-93 (after pf_form_km_elastic + pf_build_precon), :115-205 (one load increment), :206-214
+    INTEGER(c_int) FUNCTION pf_plastic_begin(h,phi,c,psi,e,v,dt) BIND(C,name='pf_plastic_begin')
+      IMPORT; TYPE(c_ptr),VALUE :: h; REAL(c_double),VALUE :: phi,c,psi,e,v; REAL(c_double) :: dt
+    END FUNCTION
+    INTEGER(c_int) FUNCTION pf_plastic_increment(h,qinc,ld0_pp,valf_pp,plasits,plastol,cjits,cjtol,  &
+                                                 plasiters,cjtot,elapsed_ms) BIND(C,name='pf_plastic_increment')
+      IMPORT; TYPE(c_ptr),VALUE :: h; REAL(c_double),VALUE :: qinc,plastol,cjtol
+      TYPE(c_ptr),VALUE :: ld0_pp,valf_pp        ! C_LOC(ld0_pp) / C_LOC(valf) or C_NULL_PTR
+      INTEGER(c_int),VALUE :: plasits,cjits; INTEGER(c_int) :: plasiters,cjtot; REAL(c_double) :: elapsed_ms
+    END FUNCTION
+    INTEGER(c_int) FUNCTION pf_plastic_get(h,totd_pp,iel,ig,tensor6) BIND(C,name='pf_plastic_get')
+      IMPORT; TYPE(c_ptr),VALUE :: h,totd_pp,tensor6; INTEGER(c_int64_t),VALUE :: iel; INTEGER(c_int),VALUE :: ig
+    END FUNCTION
+
+    ! 0: one rank, 1: NCCL send/recv, 2: peer memory over NVLink
+    INTEGER(c_int) FUNCTION pf_halo_transport(h) BIND(C,name='pf_halo_transport')
+      IMPORT; TYPE(c_ptr),VALUE :: h
+    END FUNCTION
+
   END INTERFACE
 
 CONTAINS

@@ -1674,27 +1674,35 @@ int pf_build_precon(pf_handle h, int64_t nfixed_pp, const int32_t *no_f_pp, doub
     h->launches++;
   } else if ((rc = launch_scatter(h, nullptr, true, h->diag_ext.p))) return rc;
   if ((rc = halo_reverse(h, h->diag_ext.p, nullptr))) return rc;
-  h->nfixed = (int)nfixed_pp;
-  if (h->nfixed > 0) {
-    std::vector<int> slots((size_t)h->nfixed);
-    for (int i = 0; i < h->nfixed; ++i) {
-      const int64_t g = no_f_pp[i];
-      NEED(g >= h->ieq_start && g < h->ieq_start + h->neq_pp, "fixed equation not owned by this rank");
-      slots[(size_t)i] = (int)(g - h->ieq_start + 1);
+  // the rest is local to this rank; several ranks agree on the outcome before any of them goes on to a solve
+  // (a rank that returned alone would leave the others waiting in the first exchange of the PCG loop)
+  auto local = [&]() -> int {
+    h->nfixed = (int)nfixed_pp;
+    if (h->nfixed > 0) {
+      NEED(no_f_pp, "nfixed_pp > 0 needs no_f_pp");
+      std::vector<int> slots((size_t)h->nfixed);
+      for (int i = 0; i < h->nfixed; ++i) {
+        const int64_t g = no_f_pp[i];
+        NEED(g >= h->ieq_start && g < h->ieq_start + h->neq_pp, "fixed equation not owned by this rank");
+        slots[(size_t)i] = (int)(g - h->ieq_start + 1);
+      }
+      CU(h->fix_slot.alloc(slots.size())); CU(h->store.alloc(slots.size()));
+      CU(cudaMemcpy(h->fix_slot.p, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice));
+      k_fixed_penalty<<<(h->nfixed + 255) / 256, 256, 0, h->stream>>>(h->fix_slot.p, h->diag_ext.p, h->store.p, penalty, h->nfixed);
+      h->launches++;
     }
-    CU(h->fix_slot.alloc(slots.size())); CU(h->store.alloc(slots.size()));
-    CU(cudaMemcpy(h->fix_slot.p, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice));
-    k_fixed_penalty<<<(h->nfixed + 255) / 256, 256, 0, h->stream>>>(h->fix_slot.p, h->diag_ext.p, h->store.p, penalty, h->nfixed);
-    h->launches++;
-  }
-  if (h->neq_pp > 0) {
-    k_invert<<<grid_for(h, h->neq_pp, 256), 256, 0, h->stream>>>(h->diag_ext.p + 1, (long long)h->neq_pp);
-    h->launches++;
-  }
-  CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(h->stream));
+    if (h->neq_pp > 0) {
+      k_invert<<<grid_for(h, h->neq_pp, 256), 256, 0, h->stream>>>(h->diag_ext.p + 1, (long long)h->neq_pp);
+      h->launches++;
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+  };
+  if ((rc = agree(h, local()))) { h->nfixed = 0; return rc; }
   h->diag_tmp.release();
   h->have_precon = true;
+  h->fixed_mode = 0;
   h->epoch++;
   return 0;
 }
