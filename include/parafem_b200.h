@@ -184,6 +184,22 @@ int pf_form_k_explicit(pf_handle h, double kx, double ky, double kz, double dtim
 int pf_explicit_start(pf_handle h, double val0);
 int pf_explicit_steps(pf_handle h, int nsteps, double *elapsed_ms);
 
+/* --- p129: forced vibration, implicit theta method, consistent mass ----------
+ * programs/5th_ed/p129/p129.f90.  The driver keeps its input section, the harmonic load factor and its output.
+ *   pf_form_dynamic   elements_2 (p129.f90:83-98): store_km_pp and the consistent store_mm_pp (ecmat, shape_fun; 20-node
+ *                     bricks with nip = 8 or the 27-point rule, 8-node bricks with nip = 8), combined once into the three
+ *                     matrix sets the time loop uses: store_mm*c3 + store_km*c4 (PCG, :128), store_km*c2 + store_mm*c3
+ *                     (:114) and store_mm/theta (:120), c1..c4 as :80-82.  Then pf_build_precon (:99-105).
+ *   pf_dynamic_start  fext_pp (load, :106-111); x0 = d1x0 = d2x0 = 0 (:112).
+ *   pf_dynamic_step   one pass of timesteps (:113-149): both right-hand-side products, loads = u + vu + fext*load_factor
+ *                     with load_factor = theta*dtim*cos(omega*t) + c1*cos(omega*(t-dtim)) from the caller, the PCG solve
+ *                     from x = 0, and the displacement / velocity / acceleration update.
+ *   pf_dynamic_get    x1_pp, d1x1_pp, d2x1_pp of the last step (any pointer may be NULL).                         */
+int pf_form_dynamic(pf_handle h, double e, double v, double rho, double alpha1, double beta1, double theta, double dtim);
+int pf_dynamic_start(pf_handle h, const double *fext_pp);
+int pf_dynamic_step(pf_handle h, double load_factor, double tol, int limit, int *iters, int *converged, double *elapsed_ms);
+int pf_dynamic_get(pf_handle h, double *x_pp, double *d1x_pp, double *d2x_pp);
+
 /* --- p122: 3-D elasto-plasticity ------------------------
  * programs/5th_ed/p122/p122.f90: Mohr-Coulomb solid, viscoplastic strain method.  The driver keeps its input
  * section and output; the device holds storkm_pp, evpt_pp / tensor_pp (nst,nip,nels_pp) and every vector of the

@@ -86,6 +86,7 @@ def lib():
         L.orc_form_k_transient.argtypes = [i64, cint, cint, vp, dbl, dbl, dbl, dbl, dbl, dbl, dbl, vp, vp, vp, vp]
         L.orc_apply.argtypes = [cint, i64, vp, vp, i64, cint, vp, vp]
         L.orc_p122_elements.argtypes = [i64, cint, cint, vp, dbl, dbl, dbl, dbl, dbl, dbl, cint, vp, vp, vp, vp]
+        L.orc_form_mass.argtypes = [i64, cint, cint, vp, dbl, vp]
         L.orc_cube_elements.argtypes = [cint, cint, cint, dbl, dbl, dbl, i64, i64, vp, vp]
         L.orc_cube_rest.argtypes = [cint, cint, cint, cint, i64, vp]
         L.orc_cube_rest.restype = i64
@@ -432,6 +433,91 @@ def p124(storka, storkb, g_g, neq, val0, nstep, tol, limit, npes=1, red_mode=0, 
         if j in keep:
             fields[j] = x.copy()
     return dict(iters=iters, converged=conv, x=x, fields=fields)
+
+
+def form_mass(g_coord_pp, nod, nip, rho):
+    """p129.f90:85-98, consistent mass: store_mm_pp (nels, ntot, ntot)."""
+    g = _f64(g_coord_pp)
+    out = np.empty((g.shape[0], 3 * nod, 3 * nod))
+    assert lib().orc_form_mass(g.shape[0], nod, nip, _p(g), rho, _p(out)) == 0
+    return out
+
+
+def p129(km, mm, g_g, neq, fext, theta, omega, alpha1, beta1, nstep, tol, limit, npes=1, red_mode=1, keep=()):
+    """The time-stepping loop of p129.f90:60-69,99-150 (forced vibration, theta method, consistent mass, Rayleigh
+    damping alpha1 / beta1; dtim = period/20): per step the two right-hand-side products, the harmonic load, one PCG
+    solve from x = 0 on store_mm_pp*c3 + store_km_pp*c4, then the velocity / acceleration updates.
+    -> dict(rows [(time, cos(omega t), iters)], x (last), d1x, d2x, fields {step: x})."""
+    import math
+    pi = math.acos(-1.0)
+    period = 2.0 * pi / omega
+    dtim = period / 20.0
+    c1 = (1.0 - theta) * dtim
+    c2 = beta1 - c1
+    c3 = alpha1 + 1.0 / (theta * dtim)
+    c4 = beta1 + theta * dtim
+    a_mat = mm * c3 + km * c4                 # temp_pp of the iterations loop (p129.f90:128)
+    b_mat = km * c2 + mm * c3                 # temp_pp of elements_3 (:114)
+    m_th = mm / theta                         # :120
+    ntot = km.shape[1]
+    diag_tmp = np.ascontiguousarray(mm[:, np.arange(ntot), np.arange(ntot)] * c3 + km[:, np.arange(ntot), np.arange(ntot)] * c4)
+    x0 = np.zeros(neq); d1x0 = np.zeros(neq); d2x0 = np.zeros(neq)
+    real_time, rows, fields = 0.0, [], {}
+    for j in range(1, nstep + 1):
+        real_time = real_time + dtim
+        u = apply(b_mat, g_g, neq, x0, npes)
+        vu = apply(m_th, g_g, neq, d1x0, npes)
+        loads = fext * (theta * dtim * math.cos(omega * real_time) + c1 * math.cos(omega * (real_time - dtim)))
+        loads = u + vu + loads
+        res = pcg(a_mat, g_g, neq, loads, tol, limit, npes=npes, red_mode=red_mode)
+        assert np.array_equal(res["diag"], 1.0 / scatter(g_g, diag_tmp, neq, npes))     # :99-105
+        x1 = res["x"]
+        d1x1 = (x1 - x0) / (theta * dtim) - d1x0 * (1.0 - theta) / theta
+        d2x1 = (d1x1 - d1x0) / (theta * dtim) - d2x0 * (1.0 - theta) / theta
+        x0, d1x0, d2x0 = x1, d1x1, d2x1
+        rows.append((real_time, math.cos(omega * real_time), res["iters"]))
+        if j in keep:
+            fields[j] = x1.copy()
+    return dict(rows=rows, x=x0, d1x=d1x0, d2x=d2x0, fields=fields, dtim=dtim)
+
+
+def cube_p129(nxe, nye, nze, aa, bb, cc, rho=2000.0, e=1.0e5, v=0.3, alpha1=0.0008, beta1=0.5, nstep=40, npri=1, theta=1.0,
+              omega=0.01, tol=1e-4, limit=3000, nip=27, deck_rounding=False):
+    """p12meshgen's p129 cantilever (p12meshgen.f90, CASE('p129')): geometry_20bxz bricks, the first nr nodes (the plane
+    y = 0) fully fixed, 2*nxe+1 loaded nodes on the last line of the mesh, nres the monitored equation."""
+    L = lib()
+    nels = nxe * nye * nze
+    nr = 3 * nxe * nze + 2 * nxe + 2 * nze + 1
+    nn = ((2 * nxe + 1) * (nze + 1) + (nxe + 1) * nze) * (nye + 1) + (nxe + 1) * (nze + 1) * nye
+    m = Mesh()
+    m.program, m.nod, m.nodof, m.nip, m.nels, m.nn, m.nr = 129, 20, 3, nip, nels, nn, nr
+    m.rho, m.e, m.v, m.alpha1, m.beta1, m.nstep, m.npri, m.theta, m.omega, m.tol, m.limit = rho, e, v, alpha1, beta1, nstep, npri, theta, omega, tol, limit
+    m.nres = 3 * (nye * (nxe + 1) * (nze + 1) + nr * (nye - 1) + (nxe + 1))
+    m.g_num_pp = np.empty((nels, 20), np.int32)
+    m.g_coord_pp = np.empty((nels, 3, 20))
+    assert L.orc_cube_elements(20, nxe, nze, aa, bb, cc, 0, nels, _p(m.g_num_pp), _p(m.g_coord_pp)) == 0
+    if deck_rounding:                             # the deck holds the coordinates as F12.4
+        m.g_coord_pp = np.round(m.g_coord_pp, 4)
+    rest = np.zeros((4, nr), np.int32)
+    rest[0] = np.arange(1, nr + 1)
+    m.rest = rest.copy()
+    L.orc_rearrange(nr, 3, _p(rest))
+    m.g_g_pp = np.zeros((nels, 60), np.int32)
+    L.orc_find_g_all(20, 3, nels, _p(m.g_num_pp), _p(m.g_g_pp), nr, _p(rest))
+    m.neq = int(m.g_g_pp.max())
+    loaded = 2 * nxe + 1
+    node = nn - loaded + np.arange(1, loaded + 1)
+    val = np.where((np.arange(1, loaded + 1) == 1) | (np.arange(1, loaded + 1) == loaded), 25.0 / 12.0,
+                   np.where(np.arange(1, loaded + 1) % 2 == 0, 25.0 / 3.0, 25.0 / 6.0))
+    if deck_rounding:
+        val = _round_sig(val, 8)
+    nf_z = np.zeros(nn + 1, np.int32)
+    nf_z[m.g_num_pp.ravel()] = m.g_g_pp.reshape(nels, 20, 3)[:, :, 2].ravel()
+    m.r_pp = np.zeros(m.neq)
+    eq = nf_z[node]
+    m.r_pp[eq[eq > 0] - 1] = val[eq > 0]
+    m.loaded_nodes, m.load_node, m.load_val, m.total_load = loaded, node.astype(np.int32), val, float(val.sum())
+    return m
 
 
 def form_k_explicit(g_coord_pp, nip, kx, ky, kz, dtim):

@@ -79,6 +79,26 @@ int orc_sample_hex(int nip, double *points, double *weights) {
     }
     return 0;
   }
+  if (nip == 27) {
+    /* new_library.f90:1491-1517.  wt = (/5./9.*v,8./9.*v,5./9.*v/): the outer factors are DEFAULT-REAL literals
+     * (single-precision quotients, widened), v(9) = (/5/9*w,8/9*w,5/9*w/) with w = (5/9,8/9,5/9) in REAL(iwp) (:1053-1054) */
+    const double r15 = 0.2 * sqrt(15.0);
+    const double w[3] = {5.0 / 9.0, 8.0 / 9.0, 5.0 / 9.0};
+    const double f59 = (double)(5.f / 9.f), f89 = (double)(8.f / 9.f);
+    double v[9];
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) v[3 * a + b] = w[a] * w[b];   /* (5/9*w, 8/9*w, 5/9*w) */
+    for (int blk = 0; blk < 3; ++blk) {
+      const double fy = blk == 0 ? -r15 : blk == 1 ? 0.0 : r15, fw = blk == 1 ? f89 : f59;
+      for (int q = 0; q < 9; ++q) {
+        const int i = 9 * blk + q;                 /* 0-based point */
+        points[0 * 27 + i] = (q % 3 == 0) ? -r15 : (q % 3 == 1) ? 0.0 : r15;      /* s(1:7:3,1), s(2:8:3,1), s(3:9:3,1) */
+        points[2 * 27 + i] = (q / 3 == 0) ? r15 : (q / 3 == 1) ? 0.0 : -r15;      /* s(1:3,3), s(4:6,3), s(7:9,3) */
+        points[1 * 27 + i] = fy;
+        weights[i] = fw * v[q];
+      }
+    }
+    return 0;
+  }
   return 1;
 }
 
@@ -263,9 +283,9 @@ static double gauss_point(int nod, const double *points, int nip, int ig, const 
  * g_coord_pp(nod,3,nels), storkm_pp(ntot,ntot,nels), ntot = 3*nod. */
 int orc_form_km_elastic(int64_t nels, int nod, int nip, const double *g_coord_pp, double e,
                         double v, double *storkm_pp) {
-  if ((nod != 4 && nod != 8 && nod != 20) || (nod != 4 && nip != 1 && nip != 8) || (nod == 4 && nip != 1 && nip != 4 && nip != 5)) return 1;
+  if ((nod != 4 && nod != 8 && nod != 20) || (nod != 4 && nip != 1 && nip != 8 && nip != 27) || (nod == 4 && nip != 1 && nip != 4 && nip != 5)) return 1;
   const int ntot = 3 * nod;
-  double points[24], weights[8], dee[36];
+  double points[81], weights[27], dee[36];
   sample_for(nod, nip, points, weights);
   orc_deemat6(dee, e, v);
 #pragma omp parallel
@@ -305,7 +325,7 @@ int orc_form_km_elastic(int64_t nels, int nod, int nip, const double *g_coord_pp
 int orc_form_kc_laplace(int64_t nels, int nod, int nip, const double *g_coord_pp, double kx,
                         double ky, double kz, double *storkc_pp) {
   if ((nod != 8 && nod != 4) || (nod == 8 && nip != 1 && nip != 8) || (nod == 4 && nip != 1 && nip != 4 && nip != 5)) return 1;
-  double points[24], weights[8];
+  double points[81], weights[27];
   sample_for(nod, nip, points, weights);
   const int nn2 = nod * nod;
 #pragma omp parallel for schedule(static)
@@ -327,8 +347,21 @@ int orc_form_kc_laplace(int64_t nels, int nod, int nip, const double *g_coord_pp
 
 /* shape_fun, 3-D nod = 8 (new_library.f90:397-422) at Gauss point i (0-based) */
 int orc_shape_fun(int nod, const double *points, int nip, int i, double *fun) {
-  if (nod != 8) return 1;
+  if (nod != 8 && nod != 20) return 1;
   const double xi = points[0 * nip + i], eta = points[1 * nip + i], zeta = points[2 * nip + i];
+  if (nod == 20) {   /* new_library.f90:449-468 */
+    static const int xii[20] = {-1, -1, -1, 0, 1, 1, 1, 0, -1, -1, 1, 1, -1, -1, -1, 0, 1, 1, 1, 0};
+    static const int etai[20] = {-1, -1, -1, -1, -1, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1};
+    static const int zetai[20] = {-1, 0, 1, 1, 1, 0, -1, -1, -1, 1, 1, -1, -1, 0, 1, 1, 1, 0, -1, -1};
+    for (int l = 1; l <= 20; ++l) {
+      const double xi0 = xi * xii[l - 1], eta0 = eta * etai[l - 1], zeta0 = zeta * zetai[l - 1];
+      if (l == 4 || l == 8 || l == 16 || l == 20) fun[l - 1] = .25 * (1. - xi * xi) * (1. + eta0) * (1. + zeta0);
+      else if (l >= 9 && l <= 12) fun[l - 1] = .25 * (1. + xi0) * (1. - eta * eta) * (1. + zeta0);
+      else if (l == 2 || l == 6 || l == 14 || l == 18) fun[l - 1] = .25 * (1. + xi0) * (1. + eta0) * (1. - zeta * zeta);
+      else fun[l - 1] = .125 * (1. + xi0) * (1. + eta0) * (1. + zeta0) * (xi0 + eta0 + zeta0 - 2);
+    }
+    return 0;
+  }
   const double etam = 1.0 - eta, xim = 1.0 - xi, zetam = 1.0 - zeta;
   const double etap = eta + 1.0, xip = xi + 1.0, zetap = zeta + 1.0;
   fun[0] = 0.125 * xim * etam * zetam; fun[1] = 0.125 * xim * etam * zetap;
@@ -348,7 +381,7 @@ int orc_form_k_transient(int64_t nels, int nod, int nip, const double *g_coord_p
                          double ky, double kz, double rho, double cp, double theta, double dtim,
                          double *storka_pp, double *storkb_pp, double *kc_out, double *pm_out) {
   if (nod != 8 || (nip != 1 && nip != 8)) return 1;
-  double points[24], weights[8], kay[9] = {0};
+  double points[81], weights[27], kay[9] = {0};
   orc_sample_hex(nip, points, weights);
   kay[0] = kx; kay[4] = ky; kay[8] = kz;                       /* kay(a,b) at [b*3+a] */
   const double omt = 1.0 - theta;
@@ -380,6 +413,37 @@ int orc_form_k_transient(int64_t nels, int nod, int nip, const double *g_coord_p
       if (storkb_pp) storkb_pp[iel * 64 + q] = pm[q] - kc[q] * omt * dtim;
       if (kc_out) kc_out[iel * 64 + q] = kc[q];
       if (pm_out) pm_out[iel * 64 + q] = pm[q];
+    }
+  }
+  return 0;
+}
+
+/* elements_2 of p129.f90:85-98, consistent mass: emm = sum_gp ecmat(fun)*det*w*rho with ecmat = MATMUL(nt,tn)
+ * (new_library.f90:1536-1563: nt((i-1)*nodof+j,j) = fun(i)), i.e. emm(3i+j,3i'+j') = fun(i)*fun(i') for j == j'.
+ * store_mm_pp(ntot,ntot,nels). */
+int orc_form_mass(int64_t nels, int nod, int nip, const double *g_coord_pp, double rho, double *store_mm_pp) {
+  if ((nod != 8 && nod != 20) || (nip != 8 && nip != 27)) return 1;
+  const int ntot = 3 * nod;
+  double points[81], weights[27];
+  orc_sample_hex(nip, points, weights);
+#pragma omp parallel for schedule(static)
+  for (int64_t iel = 0; iel < nels; ++iel) {
+    double der[60], deriv[60], fun[20];
+    double *mm = store_mm_pp + iel * ntot * ntot;
+    for (int q = 0; q < ntot * ntot; ++q) mm[q] = 0.0;
+    for (int ig = 0; ig < nip; ++ig) {
+      const double det = gauss_point(nod, points, nip, ig, g_coord_pp + iel * nod * 3, der, deriv);
+      orc_shape_fun(nod, points, nip, ig, fun);
+      for (int b = 0; b < ntot; ++b)
+        for (int a = 0; a < ntot; ++a) {
+          double ecm = 0.0;                              /* MATMUL(nt,tn): k ascending, separate multiply and add */
+          for (int k = 0; k < 3; ++k) {
+            const double nt = (a % 3 == k) ? fun[a / 3] : 0.0, tn = (b % 3 == k) ? fun[b / 3] : 0.0;
+            ecm = ecm + nt * tn;
+          }
+          ecm = ecm * det * weights[ig] * rho;
+          mm[b * ntot + a] = mm[b * ntot + a] + ecm;
+        }
     }
   }
   return 0;
@@ -492,7 +556,7 @@ int orc_p122_elements(int64_t nels, int nod, int nip, const double *g_coord_pp, 
                       double *utemp) {
   if ((nod != 8 && nod != 20) || nip != 8) return 1;
   const int ntot = 3 * nod;
-  double points[24], weights[8], dee[36];
+  double points[81], weights[27], dee[36];
   orc_sample_hex(nip, points, weights);
   orc_deemat6(dee, e, v);
 #pragma omp parallel for schedule(static)
@@ -661,7 +725,7 @@ int orc_cube_elements(int nod, int nxe, int nze, double aa, double bb, double cc
       num[6] = num[5] - nxe - 1; num[7] = num[6] + 1; num[8] = num[5] + 1;
       const double x0 = (double)(ip - 1) * aa, x1 = (double)ip * aa;
       const double y0 = (double)(iq - 1) * bb, y1 = (double)iq * bb;
-      const double z0 = (double)(-is) * cc, z1 = (double)(-(is - 1)) * cc;
+      const double z0 = -((double)is * cc), z1 = -((double)(is - 1) * cc);   /* -is*cc = -(is*cc): -0.0 on the top plane */
       x[1] = x[2] = x[5] = x[6] = x0; x[3] = x[4] = x[7] = x[8] = x1;
       y[1] = y[2] = y[3] = y[4] = y0; y[5] = y[6] = y[7] = y[8] = y1;
       z[1] = z[4] = z[5] = z[8] = z0; z[2] = z[3] = z[6] = z[7] = z1;
@@ -686,7 +750,7 @@ int orc_cube_elements(int nod, int nxe, int nze, double aa, double bb, double cc
       for (int m = 1; m <= 8; ++m) y[m] = y0;
       for (int m = 13; m <= 20; ++m) y[m] = y1;
       y[9] = .5 * (y[1] + y[13]); y[10] = .5 * (y[3] + y[15]); y[11] = .5 * (y[5] + y[17]); y[12] = .5 * (y[7] + y[19]);
-      const double z0 = (double)(-is) * cc, z1 = (double)(-(is - 1)) * cc;
+      const double z0 = -((double)is * cc), z1 = -((double)(is - 1) * cc);   /* -is*cc = -(is*cc): -0.0 on the top plane */
       z[1] = z[7] = z[8] = z[9] = z[12] = z[13] = z[19] = z[20] = z0;
       z[3] = z[4] = z[5] = z[10] = z[11] = z[15] = z[16] = z[17] = z1;
       z[2] = .5 * (z[1] + z[3]); z[6] = .5 * (z[5] + z[7]); z[14] = .5 * (z[13] + z[15]); z[18] = .5 * (z[17] + z[19]);
@@ -924,7 +988,7 @@ int orc_apply_mf(int64_t nels, int nod, int nip, const double *g_coord_pp, doubl
                  const double *pmul, double *utemp) {
   if ((nod != 8 && nod != 20) || nip != 8) return 1;
   const int ntot = 3 * nod;
-  double points[24], weights[8], dee[36], der[8][60], d3[60];
+  double points[81], weights[27], dee[36], der[8][60], d3[60];
   orc_sample_hex(nip, points, weights);
   orc_deemat6(dee, e, v);
   for (int ig = 0; ig < nip; ++ig) {

@@ -66,6 +66,10 @@ SIGNATURES = {
     "pf_form_k_explicit": (c_int, [vp, c_dbl, c_dbl, c_dbl, c_dbl]),
     "pf_explicit_start": (c_int, [vp, c_dbl]),
     "pf_explicit_steps": (c_int, [vp, c_int, P(c_dbl)]),
+    "pf_form_dynamic": (c_int, [vp, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl]),
+    "pf_dynamic_start": (c_int, [vp, vp]),
+    "pf_dynamic_step": (c_int, [vp, c_dbl, c_dbl, c_int, P(c_int), P(c_int), P(c_dbl)]),
+    "pf_dynamic_get": (c_int, [vp, vp, vp, vp]),
     "pf_plastic_begin": (c_int, [vp, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, P(c_dbl)]),
     "pf_plastic_increment": (c_int, [vp, c_dbl, vp, vp, c_int, c_dbl, c_int, c_dbl, P(c_int), P(c_int), P(c_dbl)]),
     "pf_plastic_get": (c_int, [vp, vp, c_i64, c_int, vp]),

@@ -83,6 +83,11 @@ struct pf_ctx {
   int64_t nels = 0, neq = 0, ieq_start = 0, neq_pp = 0, nhalo = 0, nslots = 0;
   bool have_mesh = false, have_km = false, have_precon = false, matrix_free = false;
   DevBuf<double> coord, km, utemp, diag_tmp, geom;
+  // p129 (forced vibration, theta method): km holds store_mm*c3 + store_km*c4 (the PCG matrix), kb store_km*c2 +
+  // store_mm*c3 and kc store_mm/theta (the two right-hand-side products); displacement / velocity / acceleration
+  bool dynamic = false;
+  double dyn_theta = 0.0, dyn_dtim = 0.0;
+  DevBuf<double> kc, fext, x0, d1x0, d2x0;
   // pcg_km (maths.f90:1152-1323): one element matrix shared by every element
   DevBuf<double> km1;
   bool one_km = false;
@@ -313,7 +318,7 @@ int shape_der_at(int nod, double xi, double eta, double zeta, double *D, double 
 // sample('hexahedron') new_library.f90:1397-1433; shape_der :745-794, :865-896; deemat :1671-1686
 int fill_tables(int nod, int nip, double e, double v, double kx, double ky, double kz, ElemTables &T) {
   memset(&T, 0, sizeof T);
-  double pts[8][3];
+  double pts[27][3];
   if (nod == 4) {          // sample('tetrahedron') (new_library.f90:1328-1378): nip = 1 centroid, weight 1/6;
     // nip = 4 / 5 are written with default-real (single-precision) literals there: restated with floats
     for (int i = 0; i < 8; ++i) pts[i][0] = pts[i][1] = pts[i][2] = 0.0;
@@ -340,10 +345,40 @@ int fill_tables(int nod, int nip, double e, double v, double kx, double ky, doub
       pts[i][2] = (i == 0 || i == 2 || i == 4 || i == 5) ? r3 : -r3;
       T.weights[i] = 1.0;
     }
+  } else if (nip == 27 && nod != 4) {
+    // sample('hexahedron'), nip = 27 (new_library.f90:1491-1517): wt = (/5./9.*v,8./9.*v,5./9.*v/) with DEFAULT-REAL
+    // outer factors (single-precision quotients, widened) and v(9) = w (x) w, w = (5/9,8/9,5/9) in REAL(iwp) (:1053-1054)
+    const double r15 = 0.2 * std::sqrt(15.0);
+    const double w[3] = {5.0 / 9.0, 8.0 / 9.0, 5.0 / 9.0};
+    const double f59 = (double)(5.f / 9.f), f89 = (double)(8.f / 9.f);
+    for (int blk = 0; blk < 3; ++blk)
+      for (int q = 0; q < 9; ++q) {
+        const int i = 9 * blk + q;
+        pts[i][0] = (q % 3 == 0) ? -r15 : (q % 3 == 1) ? 0.0 : r15;
+        pts[i][2] = (q / 3 == 0) ? r15 : (q / 3 == 1) ? 0.0 : -r15;
+        pts[i][1] = blk == 0 ? -r15 : blk == 1 ? 0.0 : r15;
+        T.weights[i] = (blk == 1 ? f89 : f59) * (w[q / 3] * w[q % 3]);
+      }
   } else return 1;
   T.nip = nip;
   for (int ig = 0; ig < nip; ++ig)
-    if (shape_der_at(nod, pts[ig][0], pts[ig][1], pts[ig][2], T.der + ig * 60, nod == 8 ? T.fun + ig * 8 : nullptr)) return 2;
+    if (shape_der_at(nod, pts[ig][0], pts[ig][1], pts[ig][2], T.der + ig * 60, (nod == 8 && ig < 8) ? T.fun + ig * 8 : nullptr)) return 2;
+  if (nod == 20)           // shape_fun, 3-D nod = 20 (new_library.f90:449-468)
+    for (int ig = 0; ig < nip; ++ig) {
+      static const int xii[20] = {-1, -1, -1, 0, 1, 1, 1, 0, -1, -1, 1, 1, -1, -1, -1, 0, 1, 1, 1, 0};
+      static const int etai[20] = {-1, -1, -1, -1, -1, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1};
+      static const int zetai[20] = {-1, 0, 1, 1, 1, 0, -1, -1, -1, 1, 1, -1, -1, 0, 1, 1, 1, 0, -1, -1};
+      const double xi = pts[ig][0], eta = pts[ig][1], zeta = pts[ig][2];
+      for (int l = 1; l <= 20; ++l) {
+        const double xi0 = xi * xii[l - 1], eta0 = eta * etai[l - 1], zeta0 = zeta * zetai[l - 1];
+        double f;
+        if (l == 4 || l == 8 || l == 16 || l == 20) f = .25 * (1. - xi * xi) * (1. + eta0) * (1. + zeta0);
+        else if (l >= 9 && l <= 12) f = .25 * (1. + xi0) * (1. - eta * eta) * (1. + zeta0);
+        else if (l == 2 || l == 6 || l == 14 || l == 18) f = .25 * (1. + xi0) * (1. + eta0) * (1. - zeta * zeta);
+        else f = .125 * (1. + xi0) * (1. + eta0) * (1. + zeta0) * (xi0 + eta0 + zeta0 - 2);
+        T.fun20[ig * 20 + l - 1] = f;
+      }
+    }
   // deemat, 6x6
   const double v2 = v / (1.0 - v), vv = (1.0 - 2.0 * v) / (1.0 - v) * 0.5;
   for (int i = 0; i < 3; ++i) T.dee[i * 6 + i] = 1.0;
@@ -870,6 +905,7 @@ int pf_finalize(pf_handle h) {
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->snap_pinned) cudaFreeHost(h->snap_pinned);
   for (auto e : h->snap_ev) if (e) cudaEventDestroy(e);
+  h->kc.release(); h->fext.release(); h->x0.release(); h->d1x0.release(); h->d2x0.release();
   h->evpt.release(); h->tensor.release(); h->bdylds.release(); h->oldis.release(); h->totd.release(); h->loads.release(); h->ld0.release(); h->valf.release();
   h->put_bits.release(); h->pk_ptr.release(); h->acc_chunk_ptr.release(); h->pk_slot0.release(); h->pk_rank.release(); h->pk_dst.release();
   close_imports(h);
@@ -994,7 +1030,8 @@ int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp, con
   // nobody enters the collectives below unless every rank got through (agree) ----
   auto local_a = [&]() -> int {
     NEED((nod == 4 || nod == 8 || nod == 20) && (nodof == 1 || nodof == 3), "nod must be 4 (tetrahedra), 8 or 20 (hexahedra), nodof 1 or 3");
-    NEED(nip == 1 || nip == 8 || (nod == 4 && (nip == 4 || nip == 5)), "nip must be 1 or 8 (hexahedra), 1, 4 or 5 (tetrahedra)");
+    NEED(nip == 1 || nip == 8 || (nod == 4 && (nip == 4 || nip == 5)) || (nod == 20 && nip == 27),
+         "nip must be 1 or 8 (hexahedra; 27 for 20-node bricks), 1, 4 or 5 (tetrahedra)");
     NEED(nod != 4 || nip != 8, "4-node tetrahedra take nip = 1, 4 or 5");
     NEED(nels_pp >= 1 && neq >= 1 && neq_pp >= 0 && ieq_start >= 1, "bad sizes");
     NEED(ntot == 60 || ntot == 24 || ntot == 8 || ntot == 12 || ntot == 4,
@@ -1023,7 +1060,7 @@ int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp, con
     h->nels = nels_pp; h->neq = neq; h->ieq_start = ieq_start; h->neq_pp = neq_pp;
     h->have_mesh = false; h->have_km = h->have_precon = false;
     h->transient = h->transient_first = false; h->mat_override = nullptr; h->kb.release();
-    h->explicit_ = false; h->plastic = false; h->fixed_mode = 0; h->one_km = false;
+    h->explicit_ = false; h->plastic = false; h->fixed_mode = 0; h->one_km = false; h->dynamic = false; h->kc.release();
     h->epoch++;                                   // a captured iteration graph of the previous mesh is stale
 
     // gather table (make_ggl rebuilt from g_g_pp)
@@ -1169,7 +1206,7 @@ static int alloc_km(pf_handle h) {
 int pf_form_km_elastic(pf_handle h, double e, double v) {
   int rc = need_device(h); if (rc) return rc;
   h->one_km = false;
-  h->transient = false; h->explicit_ = false; h->kb.release();
+  h->transient = false; h->explicit_ = false; h->dynamic = false; h->kb.release();
   NEED(h->have_mesh && h->nodof == 3, "needs pf_setup_mesh with nodof = 3");
   NEED(h->nod != 4 || (h->km_layout == 0 && !h->matrix_free), "tetrahedra: reference storkm layout, stored matrices only");
   ElemTables T;
@@ -1200,6 +1237,9 @@ int pf_form_km_elastic(pf_handle h, double e, double v) {
   if (h->nod == 4) {
     NEED(!diag_only, "the matrix-free variant exists for the hexahedra only");
     k_form_km_elastic<4, 64><<<grid, 64, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, nullptr, h->km_layout);
+  } else if (h->nip == 27) {
+    NEED(!diag_only && h->nod == 20, "the 27-point rule is built for stored matrices of 20-node bricks");
+    k_form_km_elastic<20, 128><<<grid, 128, 0, h->stream>>>(h->coord.p, h->km.p, (long long)h->nels, nullptr, h->km_layout);
   } else if (diag_only && !old_form) {
     if (h->nod == 20) k_form_km_tiled<20, 2, 2, 128, false, true><<<grid, 128, 0, h->stream>>>(h->coord.p, diag_only, (long long)h->nels, 0, nullptr, nullptr);
     else k_form_km_tiled<8, 1, 1, 64, false, true><<<grid, 64, 0, h->stream>>>(h->coord.p, diag_only, (long long)h->nels, 0, nullptr, nullptr);
@@ -1230,7 +1270,7 @@ int pf_form_km_elastic_mat(pf_handle h, int np_types, const double *prop, const 
   for (int64_t e = 0; e < h->nels; ++e)
     if (etype_pp[e] < 1 || etype_pp[e] > np_types) return fail(h, 4, "pf_form_km_elastic_mat: etype_pp(%lld) = %d outside 1..%d",
                                                                (long long)e + 1, etype_pp[e], np_types);
-  h->transient = false; h->explicit_ = false; h->kb.release();
+  h->transient = false; h->explicit_ = false; h->dynamic = false; h->kb.release();
   ElemTables T;
   std::vector<double> dees((size_t)np_types * 36);
   for (int m = 0; m < np_types; ++m) {           // deemat(e,v,dee) per material (xx2.f90:176-180)
@@ -1258,7 +1298,7 @@ int pf_form_km_elastic_mat(pf_handle h, int np_types, const double *prop, const 
 int pf_form_kc_laplace(pf_handle h, double kx, double ky, double kz) {
   int rc = need_device(h); if (rc) return rc;
   h->one_km = false;
-  h->transient = false; h->explicit_ = false; h->kb.release();
+  h->transient = false; h->explicit_ = false; h->dynamic = false; h->kb.release();
   NEED(h->have_mesh && h->nodof == 1 && (h->nod == 8 || h->nod == 4), "needs pf_setup_mesh with nod = 8 or 4, nodof = 1");
   NEED(h->nod != 4 || h->km_layout == 0, "tetrahedra: reference storkm layout only");
   ElemTables T;
@@ -1298,7 +1338,8 @@ int pf_form_k_transient(pf_handle h, double kx, double ky, double kz, double rho
 
 int pf_get_storkb(pf_handle h, int64_t iel0, int64_t n, double *out) {
   int rc = need_device(h); if (rc) return rc;
-  NEED(h->transient && h->have_km && iel0 >= 0 && n >= 0 && iel0 + n <= h->nels, "needs pf_form_k_transient and a local element range");
+  NEED((h->transient || h->dynamic) && h->have_km && iel0 >= 0 && n >= 0 && iel0 + n <= h->nels,
+       "needs pf_form_k_transient (storkb_pp) or pf_form_dynamic (store_km*c2 + store_mm*c3) and a local element range");
   const size_t per = (size_t)h->ntot * h->ntot;
   CU(cudaMemcpy(out, h->kb.p + (size_t)iel0 * per, (size_t)n * per * 8, cudaMemcpyDeviceToHost));
   return 0;
@@ -1588,12 +1629,101 @@ int pf_plastic_get(pf_handle h, double *totd_pp, int64_t iel, int ig, double *te
   return 0;
 }
 
+// ---- p129: forced vibration of an elastic solid, implicit theta method, consistent mass ----
+int pf_form_dynamic(pf_handle h, double e, double v, double rho, double alpha1, double beta1, double theta, double dtim) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_mesh && h->nodof == 3 && (h->nod == 20 || h->nod == 8) && !h->matrix_free && h->km_layout == 0,
+       "needs pf_setup_mesh with hexahedra, nodof = 3, the stored path and the reference layout");
+  NEED(theta > 0.0 && dtim > 0.0, "theta and dtim must be positive");
+  // store_km_pp (p129.f90:85-89) through the stiffness kernels, store_mm_pp (:90-93) through k_form_mass
+  if ((rc = pf_form_km_elastic(h, e, v))) return rc;
+  const size_t n = h->km.n;
+  DevBuf<double> mm;
+  CU(mm.alloc(n)); CU(h->kb.alloc(n)); CU(h->kc.alloc(n));
+  const int grid = (int)std::min<int64_t>(h->nels, (int64_t)h->sm_count * 16);
+  if (h->nod == 20) k_form_mass<20><<<grid, 128, 0, h->stream>>>(h->coord.p, mm.p, (long long)h->nels, rho);
+  else k_form_mass<8><<<grid, 128, 0, h->stream>>>(h->coord.p, mm.p, (long long)h->nels, rho);
+  // c1..c4 (p129.f90:80-82)
+  const double c1 = (1.0 - theta) * dtim, c2 = beta1 - c1, c3 = alpha1 + 1.0 / (theta * dtim), c4 = beta1 + theta * dtim;
+  const int g = grid_for(h, (int64_t)n, 256);
+  k_lincomb<<<g, 256, 0, h->stream>>>(h->kb.p, h->km.p, c2, mm.p, c3, (long long)n);      // store_km*c2 + store_mm*c3   (:114)
+  k_divide<<<g, 256, 0, h->stream>>>(h->kc.p, mm.p, theta, (long long)n);                  // store_mm/theta           (:120)
+  k_lincomb<<<g, 256, 0, h->stream>>>(h->km.p, mm.p, c3, h->km.p, c4, (long long)n);      // store_mm*c3 + store_km*c4   (:128)
+  h->launches += 4;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  h->dynamic = true; h->dyn_theta = theta; h->dyn_dtim = dtim;
+  h->have_km = true; h->have_precon = false;
+  return 0;
+}
+
+int pf_dynamic_start(pf_handle h, const double *fext_pp) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->dynamic && h->have_precon && fext_pp, "needs pf_form_dynamic, pf_build_precon and fext_pp");
+  const size_t nq = (size_t)std::max<int64_t>(h->neq_pp, 1);
+  CU(h->fext.alloc(nq)); CU(h->x0.alloc(nq)); CU(h->d1x0.alloc(nq)); CU(h->d2x0.alloc(nq));
+  CU(cudaMemcpyAsync(h->fext.p, fext_pp, (size_t)h->neq_pp * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemsetAsync(h->x0.p, 0, nq * 8, h->stream)); CU(cudaMemsetAsync(h->d1x0.p, 0, nq * 8, h->stream));
+  CU(cudaMemsetAsync(h->d2x0.p, 0, nq * 8, h->stream));                                   // p129.f90:112
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// One pass of `timesteps` (p129.f90:113-149); load_factor = theta*dtim*cos(omega*t) + c1*cos(omega*(t-dtim)) (:124-125)
+int pf_dynamic_step(pf_handle h, double load_factor, double tol, int limit, int *iters, int *converged, double *elapsed_ms) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->dynamic && h->have_precon && h->fext.p, "needs pf_form_dynamic, pf_build_precon and pf_dynamic_start");
+  const long long n = h->neq_pp;
+  const int g = grid_for(h, std::max<long long>(n, 1), 256);
+  EventPair ev;
+  CU(ev.create());
+  CU(cudaEventRecord(ev.a, h->stream));
+  const int nfixed = h->nfixed;
+  h->nfixed = 0;
+  // u = (store_km*c2 + store_mm*c3) x0 ; vu = (store_mm/theta) d1x0   (:114-123)
+  CU(cudaMemcpyAsync(h->p_ext.p + 1, h->x0.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+  h->mat_override = h->kb.p;
+  rc = apply_operator(h, nullptr);
+  if (!rc) {
+    cudaMemcpyAsync(h->d.p, h->u_ext.p + 1, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream);
+    cudaMemcpyAsync(h->p_ext.p + 1, h->d1x0.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream);
+    h->mat_override = h->kc.p;
+    rc = apply_operator(h, nullptr);
+  }
+  h->mat_override = nullptr;
+  h->nfixed = nfixed;
+  if (rc) return rc;
+  k_dyn_rhs<<<g, 256, 0, h->stream>>>(h->r.p, h->d.p, h->u_ext.p + 1, h->fext.p, load_factor, n);
+  h->launches++;
+  CU(cudaGetLastError());
+  // d = M^-1 loads, p = d, x = 0 and the PCG loop on store_mm*c3 + store_km*c4   (:127-144)
+  if ((rc = pcg_run_impl(h, tol, limit, iters, converged, nullptr, 0))) return rc;
+  k_dyn_update<<<g, 256, 0, h->stream>>>(h->x.p, h->x0.p, h->d1x0.p, h->d2x0.p, h->dyn_theta, h->dyn_dtim, n);
+  h->launches++;
+  CU(cudaEventRecord(ev.b, h->stream));
+  CU(cudaEventSynchronize(ev.b));
+  CU(cudaGetLastError());
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, ev.a, ev.b));
+  if (elapsed_ms) *elapsed_ms = ms;
+  return 0;
+}
+
+int pf_dynamic_get(pf_handle h, double *x_pp, double *d1x_pp, double *d2x_pp) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->dynamic && h->x0.p, "needs pf_dynamic_start");
+  if (x_pp) CU(cudaMemcpy(x_pp, h->x0.p, (size_t)h->neq_pp * 8, cudaMemcpyDeviceToHost));
+  if (d1x_pp) CU(cudaMemcpy(d1x_pp, h->d1x0.p, (size_t)h->neq_pp * 8, cudaMemcpyDeviceToHost));
+  if (d2x_pp) CU(cudaMemcpy(d2x_pp, h->d2x0.p, (size_t)h->neq_pp * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int pf_set_storkm(pf_handle h, const double *storkm_pp) {
   int rc = need_device(h); if (rc) return rc;
   h->one_km = false;
   NEED(h->have_mesh && storkm_pp, "needs pf_setup_mesh");
   NEED(!h->matrix_free, "matrix-free variant: storkm is not stored");
-  h->transient = false; h->explicit_ = false; h->kb.release();
+  h->transient = false; h->explicit_ = false; h->dynamic = false; h->kb.release();
   if ((rc = alloc_km(h))) return rc;
   if (h->km_layout == 0) {
     CU(cudaMemcpy(h->km.p, storkm_pp, h->km.bytes(), cudaMemcpyHostToDevice));

@@ -925,11 +925,12 @@ __global__ void k_invert(double *__restrict__ v, long long n) {
 // computed on the host with the reference's formulas and held in constant memory.
 // ----------------------------------------------------------------------------
 struct ElemTables {
-  double der[8 * 3 * 20];  // [ig][a][m]  = der(a,m) at Gauss point ig   (shape_der)
-  double weights[8];       // sample
+  double der[27 * 3 * 20]; // [ig][a][m]  = der(a,m) at Gauss point ig   (shape_der); up to the 27-point rule (p129)
+  double weights[27];      // sample
   double dee[36];          // dee(l,k) at [k*6+l]                        (deemat)
   double kxyz[3];          // p123 / p124 conductivities (diagonal of kay)
   double fun[8 * 8];       // [ig][m] = fun(m) at Gauss point ig, 8-node brick   (shape_fun)
+  double fun20[27 * 20];   // the same for the 20-node brick (new_library.f90:449-468), p129's consistent mass
   double trans[4];         // p124: rho, cp, theta, dtim
   int nip;
 };
@@ -2047,6 +2048,80 @@ k_checon(const double *__restrict__ loads, double *__restrict__ oldlds, long lon
     const double m1 = final_max(part, nchunks, sh);
     const double m2 = final_max(part + nchunks, nchunks, sh);
     if (threadIdx.x == 0) { st->loc[0] = 0.0; st->loc[1] = m1; st->loc[2] = m2; st->loc[3] = 0.0; }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// p129 (programs/5th_ed/p129/p129.f90): forced vibration, implicit theta method, consistent mass
+// ----------------------------------------------------------------------------
+// elements_2, mass part (p129.f90:90-93): emm += ecmat(fun)*det*w*rho per Gauss point, ecmat = MATMUL(nt,tn)
+// (new_library.f90:1536-1563), i.e. emm(3i+j,3i'+j') += fun(i)*fun(i')*det*w*rho for j == j' and +0.0 otherwise.
+// One CTA of 128 threads per element, every thread a strided share of the ntot x ntot entries.
+template <int NOD>
+__global__ void __launch_bounds__(128)
+k_form_mass(const double *__restrict__ g_coord, double *__restrict__ mm, long long nels, double rho) {
+  constexpr int NTOT = 3 * NOD, NENT = NTOT * NTOT, THREADS = 128, PER = (NENT + THREADS - 1) / THREADS;
+  __shared__ double s_coord[NOD * 3], s_jac[9], s_deriv[NOD * 3];
+  for (long long e = blockIdx.x; e < nels; e += gridDim.x) {
+    __syncthreads();
+    for (int q = threadIdx.x; q < NOD * 3; q += THREADS) s_coord[q] = g_coord[e * NOD * 3 + q];
+    double acc[PER];
+#pragma unroll
+    for (int n = 0; n < PER; ++n) acc[n] = 0.0;
+    __syncthreads();
+    for (int ig = 0; ig < c_tab.nip; ++ig) {
+      const double det = gauss_point<NOD>(ig, s_coord, s_jac, s_deriv);
+      const double wt = c_tab.weights[ig];
+      const double *fun = NOD == 20 ? c_tab.fun20 + ig * 20 : c_tab.fun + ig * 8;
+#pragma unroll
+      for (int n = 0; n < PER; ++n) {
+        const int idx = threadIdx.x + n * THREADS;
+        if (idx < NENT) {
+          const int b = idx / NTOT, a = idx - b * NTOT;
+          const double ecm = (a % 3 == b % 3) ? fun[a / 3] * fun[b / 3] : 0.0;
+          acc[n] = acc[n] + ecm * det * wt * rho;
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int n = 0; n < PER; ++n) {
+      const int idx = threadIdx.x + n * THREADS;
+      if (idx < NENT) mm[e * (long long)NENT + idx] = acc[n];
+    }
+  }
+}
+// out = a*ca + b*cb, entry by entry (p129.f90:114 temp_pp = store_km_pp*c2 + store_mm_pp*c3, :128 the PCG matrix);
+// out may be b
+__global__ void k_lincomb(double *out, const double *__restrict__ a, double ca, const double *b, double cb, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = a[i] * ca + b[i] * cb;
+}
+__global__ void k_divide(double *__restrict__ out, const double *__restrict__ a, double s, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = a[i] / s;
+}
+// loads = u + vu + fext*factor   (p129.f90:124-126; factor = theta*dtim*cos(omega t) + c1*cos(omega (t - dtim)))
+__global__ void k_dyn_rhs(double *__restrict__ r, const double *__restrict__ u, const double *__restrict__ vu,
+                          const double *__restrict__ fext, double factor, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) r[i] = u[i] + vu[i] + fext[i] * factor;
+}
+// x1 = xnew; d1x1 = (x1-x0)/(theta*dtim) - d1x0*(1-theta)/theta; d2x1 = (d1x1-d1x0)/(theta*dtim) - d2x0*(1-theta)/theta;
+// x0 = x1; d1x0 = d1x1; d2x0 = d2x1   (p129.f90:146-149)
+__global__ void k_dyn_update(const double *__restrict__ x1, double *__restrict__ x0, double *__restrict__ d1x0,
+                             double *__restrict__ d2x0, double theta, double dtim, long long n) {
+  const double td = theta * dtim, omt = 1.0 - theta;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const double a = x1[i], v0 = d1x0[i];
+    const double v1 = (a - x0[i]) / td - v0 * omt / theta;
+    const double w1 = (v1 - v0) / td - d2x0[i] * omt / theta;
+    x0[i] = a; d1x0[i] = v1; d2x0[i] = w1;
   }
 }
 

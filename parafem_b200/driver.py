@@ -154,6 +154,48 @@ XX3_SECTIONS = ("Setup", "Read element steering array", "Convert Abaqus to S&G n
                 "Get starting r", "Solve equations", "Output results")
 
 
+def run_p129(prob, s, out_base=None, decimals=4, nstep=None):
+    """Program p129 (p129.f90) for one rank: setup, then the time loop -- per step the harmonic load factor on the host
+    (p129.f90:124-125) and one device call.  With `out_base` the displacement files <out_base>.ensi.DISPL-NNNNNN are
+    written every npri steps (single rank).  -> dict(rows = [(time, cos(omega t), x1(nres), iters)], x, d1x, d2x, dtim,
+    solve_s, setup_s)."""
+    import math
+    from . import host
+    t0 = time.time()
+    _solver.setup_problem(s, prob)
+    t_setup = time.time() - t0
+    dtim, theta, omega = prob.dtim, prob.theta, prob.omega
+    c1 = (1.0 - theta) * dtim
+    lo = prob.ieq_start
+    owns = lo <= prob.nres < lo + prob.neq_pp
+    rows, ms_total, real_time = [], 0.0, 0.0
+    for j in range(1, (nstep or prob.nstep) + 1):
+        real_time = real_time + dtim
+        factor = theta * dtim * math.cos(omega * real_time) + c1 * math.cos(omega * (real_time - dtim))
+        it, _, ms = s.dynamic_step(factor, prob.tol, prob.limit)
+        ms_total += ms
+        if j // prob.npri * prob.npri == j:
+            x1, _, _ = s.dynamic_get()
+            if owns:
+                rows.append((real_time, math.cos(omega * real_time), float(x1[prob.nres - lo]), it))
+            if out_base and prob.npes == 1:
+                host.write_ensi(f"{out_base}.ensi.DISPL-{j:06d}", host.nodal_values(prob, x1), decimals=decimals)
+    x, d1x, d2x = s.dynamic_get()
+    return dict(rows=rows, x=x, d1x=d1x, d2x=d2x, dtim=dtim, solve_s=ms_total / 1e3, setup_s=t_setup)
+
+
+def write_res_p129(path, prob, res, t_total=0.0):
+    """<job>.res as p129.f90:50-56,113,150-152,176-178 writes it."""
+    with open(path, "w") as f:
+        f.write(f"This job ran on {prob.npes:6d} processes\n")
+        f.write(f"There are {prob.nn:12d} nodes {prob.nr:12d} restrained and {prob.neq:12d} equations\n")
+        f.write(f"Time after setup was:{res['setup_s']:10.4f}\n")
+        f.write("   Time t  cos(omega*t) Displacement Iterations\n")
+        for t, c, x, it in res["rows"]:
+            f.write(f"{_fe(t)}{_fe(c)}{_fe(x)}{it:10d}\n")
+        f.write(f"This analysis took:{t_total:10.4f}\n")
+
+
 def run_p122(prob, s, out_base=None, decimals=4):
     """Program p122 (p122.f90) for one rank: setup, then the load-increment loop -- every increment one device call
     (plastic iterations, each a PCG solve restarted from the current x plus the Gauss-point stress update).  With

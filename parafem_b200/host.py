@@ -394,6 +394,76 @@ def read_deck_p122(job, npes=1, numpe=1):
     return p
 
 
+def cube_p129(nxe, nye, nze, aa, bb, cc, rho=2000.0, e=1.0e5, v=0.3, alpha1=0.0008, beta1=0.5, nstep=40, npri=1, theta=1.0,
+              omega=0.01, tol=1e-4, limit=3000, nip=27, npes=1, numpe=1):
+    """In-memory p12meshgen cantilever for p129 (p12meshgen.f90 CASE('p129')): 20-node bricks, the nodes of the plane
+    y = 0 (the first nr node numbers) fully fixed, 2*nxe+1 loaded nodes at the far end, nres the monitored equation."""
+    L = lib()
+    nels = nxe * nye * nze
+    nr = 3 * nxe * nze + 2 * nxe + 2 * nze + 1
+    nn = ((2 * nxe + 1) * (nze + 1) + (nxe + 1) * nze) * (nye + 1) + (nxe + 1) * (nze + 1) * nye
+    nels_pp, iel_start = calc_nels_pp(nels, npes, numpe)
+    g_num = np.empty((nels_pp, 20), np.int32)
+    g_coord = np.empty((nels_pp, 3, 20), np.float64)
+    check(L.pf_cube_elements(nxe, nze, 20, aa, bb, cc, iel_start, nels_pp, 0, ptr(g_num), ptr(g_coord)), what="pf_cube_elements")
+    rest = np.zeros((4, nr), np.int32)
+    rest[0] = np.arange(1, nr + 1)
+    nf, g_g, neq = _steer(nn, 3, rest, g_num, 20)
+    neq_pp, ieq_start = calc_neq_pp(neq, npes, numpe)
+    loaded = 2 * nxe + 1
+    k = np.arange(1, loaded + 1)
+    node = (nn - loaded + k).astype(np.int32)
+    val = np.zeros((loaded, 3))
+    val[:, 2] = np.where((k == 1) | (k == loaded), 25.0 / 12.0, np.where(k % 2 == 0, 25.0 / 3.0, 25.0 / 6.0))
+    r = np.empty(neq_pp, np.float64)
+    check(L.pf_load(3, loaded, nn, ptr(node), ptr(val), ptr(nf), ieq_start, neq_pp, ptr(r)), what="pf_load")
+    p = Problem(129, 20, 3, nip, nels, nn, nr, neq, npes, numpe, nels_pp, iel_start, neq_pp, ieq_start, g_num, g_coord, g_g,
+                nf, r, e=e, v=v, tol=tol, limit=limit, rho=rho, theta=theta, nstep=nstep, npri=npri,
+                nres=3 * (nye * (nxe + 1) * (nze + 1) + nr * (nye - 1) + (nxe + 1)), total_load=float(val.sum()))
+    p.alpha1, p.beta1, p.omega, p.rest = alpha1, beta1, omega, rest
+    return p
+
+
+def read_deck_p129(job, npes=1, numpe=1):
+    """Input section of p129.f90:27-44,106-111 for one rank: read_p129 (input.f90:4968-4970: element, mesh, partitioner,
+    nels nn nr nip nod loaded_nodes nres / rho e v alpha1 beta1 / nstep npri theta omega tol limit), the mesh and
+    restraint readers of p121, read_loads + load (fext_pp)."""
+    L = lib()
+    tk = open(job + ".dat").read().split()
+    if len(tk) < 21:
+        raise PfError(f"{job}.dat: too few values for read_p129")
+    meshgen, partitioner = int(tk[1]), int(tk[2])
+    nels, nn, nr, nip, nod, loaded, nres = (int(v) for v in tk[3:10])
+    rho, e, v, alpha1, beta1 = (float(t.replace("D", "E").replace("d", "e")) for t in tk[10:15])
+    nstep, npri = int(tk[15]), int(tk[16])
+    theta, omega, tol = (float(t.replace("D", "E").replace("d", "e")) for t in tk[17:20])
+    limit = int(tk[20])
+    if min(nels, nn) < 1 or nr < 0 or nr > nn or nod != 20 or nip not in (8, 27) or loaded < 0 or loaded > nn:
+        raise PfError(f"{job}.dat: sizes outside what p129 takes (20-node hexahedra, nip = 8 or 27)")
+    g_coord, g_num = _read_mesh(job, nn, nels, nod, meshgen, False)
+    nels_pp, iel_start = read_psize(job, npes, numpe) if partitioner == 2 else calc_nels_pp(nels, npes, numpe)
+    g_num_pp = np.ascontiguousarray(g_num[iel_start - 1:iel_start - 1 + nels_pp])
+    g_coord_pp = np.empty((nels_pp, 3, nod), np.float64)
+    check(L.pf_coords_pp(nod, nels_pp, nn, ptr(g_num_pp), ptr(g_coord), ptr(g_coord_pp)), what="pf_coords_pp")
+    rest = np.zeros((4, nr), np.int32)
+    check(L.pf_read_bnd(job.encode(), nr, 3, ptr(rest)), what="pf_read_bnd")
+    nf, g_g, neq = _steer(nn, 3, rest, g_num_pp, nod)
+    neq_pp, ieq_start = calc_neq_pp(neq, npes, numpe)
+    r = np.zeros(neq_pp, np.float64)
+    total = 0.0
+    if loaded:
+        node = np.empty(loaded, np.int32)
+        val = np.empty((loaded, 3), np.float64)
+        check(L.pf_read_lds(job.encode(), loaded, 3, ptr(node), ptr(val)), what="pf_read_lds")
+        check(L.pf_load(3, loaded, nn, ptr(node), ptr(val), ptr(nf), ieq_start, neq_pp, ptr(r)), what="pf_load")
+        total = float(val.sum())
+    p = Problem(129, nod, 3, nip, nels, nn, nr, neq, npes, numpe, nels_pp, iel_start, neq_pp, ieq_start, g_num_pp, g_coord_pp,
+                g_g, nf, r, e=e, v=v, tol=tol, limit=limit, rho=rho, theta=theta, nstep=nstep, npri=npri, nres=nres,
+                total_load=total)
+    p.alpha1, p.beta1, p.omega, p.rest, p.g_coord = alpha1, beta1, omega, rest, g_coord
+    return p
+
+
 def read_deck_xx2(job, npes=1, numpe=1):
     """Input section of programs/dev/xx2/xx2.f90:60-160 for one rank: read_xx2, read_elements (connectivity +
     material number of every element), abaqus2sg, read_g_coord_pp, read_rest, read_materialValue, steering,

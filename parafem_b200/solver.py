@@ -190,6 +190,26 @@ class Solver:
         self._ck(lib().pf_explicit_steps(self._h, nsteps, C.byref(ms)), "pf_explicit_steps")
         return ms.value
 
+    # -- p129: forced vibration, theta method ---------------------------------------------------
+    def form_dynamic(self, e, v, rho, alpha1, beta1, theta, dtim):
+        """p129.f90:80-98: store_km_pp, consistent store_mm_pp and the three matrix sets of the time loop."""
+        self._ck(lib().pf_form_dynamic(self._h, e, v, rho, alpha1, beta1, theta, dtim), "pf_form_dynamic")
+
+    def dynamic_start(self, fext_pp):
+        self._ck(lib().pf_dynamic_start(self._h, ptr(f64(fext_pp))), "pf_dynamic_start")
+
+    def dynamic_step(self, load_factor, tol, limit):
+        """One time step (p129.f90:113-149). -> (iters, converged, elapsed_ms)"""
+        it, cv, ms = C.c_int(), C.c_int(), C.c_double()
+        self._ck(lib().pf_dynamic_step(self._h, load_factor, tol, limit, C.byref(it), C.byref(cv), C.byref(ms)), "pf_dynamic_step")
+        return it.value, bool(cv.value), ms.value
+
+    def dynamic_get(self):
+        """-> (x1_pp, d1x1_pp, d2x1_pp) of the last step"""
+        out = [np.empty(self.prob.neq_pp) for _ in range(3)]
+        self._ck(lib().pf_dynamic_get(self._h, ptr(out[0]), ptr(out[1]), ptr(out[2])), "pf_dynamic_get")
+        return tuple(out)
+
     # -- p122: elasto-plasticity ---------------------------------------------------------------
     def plastic_begin(self, phi, c, psi, e, v):
         """p122.f90:88-93 after form_km_elastic + build_precon. -> the critical time step dt"""
@@ -306,6 +326,13 @@ def setup_problem(solver, prob, matrix_free=False, layout=0):
         if prob.no_f.size:
             # r_pp(j) = store_pp(i)*valf(k)   (xx2.f90:294-300)
             prob.r_pp[prob.no_f - prob.ieq_start] = solver.store() * prob.val_f
+    elif prob.program == 129:
+        # p129.f90:78-105: period / 20 time step, the matrix sets, the preconditioner of store_mm*c3 + store_km*c4
+        import math
+        prob.dtim = 2.0 * math.acos(-1.0) / prob.omega / 20.0
+        solver.form_dynamic(prob.e, prob.v, prob.rho, prob.alpha1, prob.beta1, prob.theta, prob.dtim)
+        solver.build_precon(None, 1e20)
+        solver.dynamic_start(prob.r_pp)
     elif prob.program == 122:
         # p122.f90:94-114: storkm_pp, the preconditioner with the penalty on this rank's fixed freedoms, zero stresses
         solver.form_km_elastic(prob.e, prob.v)

@@ -144,5 +144,23 @@ def main():
     print("golden fixtures written to", HERE)
 
 
+def p129_digests():
+    """p129_tiny (examples/5th_ed/p129: a deck without outputs -- 2560 20-node bricks, 12 465 nodes, nip = 27): SHA-256 of
+    the parsed arrays and the control values of its .dat; the in-memory generators (host.cube_p129, oracle.cube_p129)
+    must reproduce them.  Written alone: `python tests/golden/make_golden.py p129`."""
+    from parafem_b200 import host
+    d = host.read_deck_p129(f"{REF}/5th_ed/p129/p129_tiny")
+    out = dict(g_num_sg=sha(d.g_num_pp), g_coord_pp=sha(d.g_coord_pp + 0.0), rest=sha(d.rest), g_g=sha(d.g_g_pp), r=sha(d.r_pp),
+               nn=int(d.nn), nr=int(d.nr), neq=int(d.neq), nels=int(d.nels), nres=int(d.nres), nip=int(d.nip),
+               dat=dict(rho=d.rho, e=d.e, v=d.v, alpha1=d.alpha1, beta1=d.beta1, nstep=d.nstep, npri=d.npri, theta=d.theta,
+                        omega=d.omega, tol=d.tol, limit=d.limit), total_load=d.total_load)
+    json.dump(out, open(f"{HERE}/p129_tiny_digests.json", "w"), indent=1)
+    print("p129_tiny digests written")
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["p129"]:
+        p129_digests()
+    else:
+        main()
+        p129_digests()

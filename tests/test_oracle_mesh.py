@@ -65,3 +65,22 @@ def test_reference_arm_maps_only_the_oracle_and_uses_every_core():
     line = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][0])
     assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) == line["host"]["cores"]
     assert line["config"]["nels"] == 216 and line["same_workload_as_gpu_arm"] is False
+
+
+def test_p129_cantilever_reproduces_the_shipped_deck():
+    """examples/5th_ed/p129/p129_tiny.{d,bnd,lds,dat} (the reference ships this deck without outputs): both in-memory
+    generators -- the product's host.cube_p129 and the oracle's cube_p129 -- reproduce its connectivity, coordinates,
+    restraints, steering array and (after the deck's E16.8) its loads: digests of the parsed reference files,
+    tests/golden/make_golden.py."""
+    import hashlib
+    d = json.load(open(os.path.join(ROOT, "tests", "golden", "p129_tiny_digests.json")))
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    h = host.cube_p129(8, 40, 8, .125, .125, .125)
+    o = oracle.cube_p129(8, 40, 8, .125, .125, .125, deck_rounding=True)
+    assert (h.nn, h.nr, h.neq, h.nels, h.nres) == (o.nn, o.nr, o.neq, o.nels, o.nres) == (d["nn"], d["nr"], d["neq"], d["nels"], d["nres"])
+    assert (d["nn"], d["nr"], d["neq"], d["nels"], d["nres"], d["nip"]) == (12465, 225, 36720, 2560, 36072, 27)
+    for m in (h, o):
+        assert sha(m.g_num_pp) == d["g_num_sg"] and sha(m.g_coord_pp + 0.0) == d["g_coord_pp"] and sha(m.g_g_pp) == d["g_g"]   # (+ 0.0: the deck prints -0.0 as 0.0000)
+        assert sha(m.rest) == d["rest"]
+    assert sha(o.r_pp) == d["r"]                                        # loads through E16.8
+    assert np.abs(h.r_pp - o.r_pp).max() <= 5e-8 and abs(h.total_load - 100.0) < 1e-12
