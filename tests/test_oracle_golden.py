@@ -440,3 +440,44 @@ def test_p122_demo_log_and_displacements(golden, c_elements):
     field = np.where(nf > 0, totd[np.maximum(nf, 1) - 1], 0.0)
     gold_f = a["p122_displ_010"].astype(np.float64).reshape(3, nn).T
     assert np.abs(field - gold_f).max() <= 6e-4 * np.abs(gold_f).max()
+
+
+# ---- p129: forced vibration (no output ships with the reference's deck: the restatement is checked against physics) ----
+
+def test_p129_quasi_static_limit_and_free_vibration_period():
+    """oracle.p129 (p129.f90:78-149) on a short cantilever.  (i) omega -> 0: the time step period/20 becomes huge, inertia
+    and damping vanish against K*theta*dtim, and every step's displacement must equal the STATIC solution K x = fext
+    times the load's cosine (theta = 1: the load is evaluated at the new time).  (ii) Undamped free vibration after a
+    static preload: the tip keeps oscillating about zero with the period of the first bending mode -- checked against the
+    Rayleigh quotient of the static shape, omega1^2 <= x'Kx / x'Mx (within 10 %: the static shape is close to the mode)."""
+    m = oracle.cube_p129(2, 6, 2, .25, .25, .25, rho=2000.0, e=1.0e4, v=0.3, alpha1=0.0, beta1=0.0, theta=1.0, omega=1e-7,
+                         tol=1e-10, limit=4000, nip=8)
+    km = oracle.form_km_elastic(m.g_coord_pp, 20, 8, m.e, m.v)
+    mm = oracle.form_mass(m.g_coord_pp, 20, 8, m.rho)
+    assert np.abs(mm - mm.transpose(0, 2, 1)).max() == 0.0
+    assert abs(mm[0].sum() / 3.0 - m.rho * .25 ** 3) < 1e-9 * m.rho          # consistent mass: each direction carries rho*V
+    static = oracle.pcg(km, m.g_g_pp, m.neq, m.r_pp, 1e-12, 6000, npes=1, red_mode=1)
+    assert static["converged"]
+    r = oracle.p129(km, mm, m.g_g_pp, m.neq, m.r_pp, m.theta, m.omega, 0.0, 0.0, 3, m.tol, m.limit, keep=(1, 2, 3))
+    for j, (t, c, it) in enumerate(r["rows"], 1):
+        assert np.linalg.norm(r["fields"][j] - static["x"] * c) <= 1e-6 * np.linalg.norm(static["x"])
+    # (ii) free vibration: start from the static shape at rest, no load (theta = 1/2: no algorithmic damping)
+    xs = static["x"]
+    Kx = oracle.apply(km, m.g_g_pp, m.neq, xs)
+    Mx = oracle.apply(mm, m.g_g_pp, m.neq, xs)
+    w1 = np.sqrt(np.dot(xs, Kx) / np.dot(xs, Mx))
+    dt = 2.0 * np.pi / w1 / 40.0
+    theta = 0.5
+    c3, c4, c2 = 1.0 / (theta * dt), theta * dt, -(1.0 - theta) * dt
+    a_mat, b_mat, m_th = mm * c3 + km * c4, km * c2 + mm * c3, mm / theta
+    x0, v0 = xs.copy(), np.zeros(m.neq)
+    tip, k = [], m.nres - 1
+    for _ in range(60):
+        rhs = oracle.apply(b_mat, m.g_g_pp, m.neq, x0) + oracle.apply(m_th, m.g_g_pp, m.neq, v0)
+        x1 = oracle.pcg(a_mat, m.g_g_pp, m.neq, rhs, 1e-12, 6000, npes=1, red_mode=1)["x"]
+        v0 = (x1 - x0) / (theta * dt) - v0 * (1.0 - theta) / theta
+        x0 = x1
+        tip.append(x0[k])
+    tip = np.array(tip) / xs[k]
+    first_zero = int(np.argmax(tip < 0.0)) + 1                             # a quarter period after release
+    assert 8 <= first_zero <= 12 and tip.min() < -0.85                     # period ~ 40 steps, amplitude kept
