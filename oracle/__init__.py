@@ -339,17 +339,18 @@ def find_g4(g_num, rest):
 
 
 def set_mf_order(order):
-    """1: the summation order of k_apply_mf2 (matrix-free mode 2, two lanes per element); 0: that of k_apply_mf
-    (mode 1, one 24-term chain per freedom)."""
+    """1: the summation order of k_apply_mf2 (20-node bricks: two lanes per element, two 12-term chains added); 0: that
+    of k_apply_mf (8-node bricks: one 24-term chain per freedom)."""
     lib().orc_set_mf_order(int(order))
 
 
 def apply_mf(g_coord_pp, nod, nip, e, v, pmul, mode=2):
     """Matrix-free element products (config E): utemp = sum_gp B^T D B p det w in the operation order of the device
-    kernel of matrix-free mode ``mode`` (1: rebuilt from coordinates, k_apply_mf; 2: stored factors, k_apply_mf2)."""
+    kernel of that element type (20-node bricks: k_apply_mf2; 8-node bricks: k_apply_mf; both matrix-free modes of a
+    kernel give the same bits, ``mode`` is accepted for symmetry with the device call)."""
     g, pm = _f64(g_coord_pp), _f64(pmul)
     out = np.empty(pm.shape)
-    set_mf_order(0 if mode == 1 else 1)
+    set_mf_order(1 if nod == 20 else 0)
     rc = lib().orc_apply_mf(g.shape[0], nod, nip, _p(g), e, v, _p(pm), _p(out))
     assert rc == 0
     return out
@@ -369,7 +370,7 @@ def pcg(storkm, g_g, neq, r, tol, limit, npes=1, red_mode=0, no_f=None, val_f=No
     it, conv, secs = cint(), cint(), dbl()
     mfc = _f64(mf["g_coord_pp"]) if mf else None     # mf = dict(g_coord_pp, nod, nip, e, v[, mode]): matrix-free products
     if mf:
-        set_mf_order(0 if mf.get("mode", 2) == 1 else 1)
+        set_mf_order(1 if mf["nod"] == 20 else 0)
     rc = lib().orc_pcg(ntot, nels, _p(g), _p(k), neq, _p(r), nfixed, _p(no_f), _p(val_f), penalty, npes,
                        red_mode, tol, limit, _p(x), C.byref(it), C.byref(conv), _p(ratio), _p(diag),
                        C.byref(secs), _p(mfc), mf["nod"] if mf else 0, mf["nip"] if mf else 0,

@@ -446,8 +446,9 @@ int launch_matvec_km_t(pf_handle h, const double *pvec, const State *st, PeerTab
   return 0;
 }
 
-// k_apply_mf2: two lanes per element, 16 warps per SM (the default; PF_MF=1lane selects k_apply_mf)
-constexpr int kMf2Warps = 16;
+// k_apply_mf2: two lanes per element; 12 warps per SM (3 per scheduler, 168 registers, no spills) with the two halves
+// of an element on the two half-warps measured best (profiles/r02_mf_kernel_round2.md); PF_MF=1lane selects k_apply_mf
+constexpr int kMf2Warps = 12;
 bool mf_two_lanes() {
   static const bool on = !(getenv("PF_MF") && !strcmp(getenv("PF_MF"), "1lane"));
   return on;
@@ -456,16 +457,30 @@ int mf2_grid(pf_handle h) {
   const int64_t nhg = (h->nels + 15) / 16;
   return (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (nhg + kMf2Warps - 1) / kMf2Warps));
 }
-template <int NOD, bool GATHER, int GEOM>
-int launch_mf2_t(pf_handle h, const double *pvec, const State *st, PeerTable *T = nullptr) {
+template <int NOD, bool GATHER, int GEOM, int WARPS, int PAIR>
+int launch_mf2_tt(pf_handle h, const double *pvec, const State *st, PeerTable *T) {
   using Cfg = Mf2Cfg<NOD>;
-  auto kern = k_apply_mf2<NOD, GATHER, GEOM, kMf2Warps>;
-  if (int rc_ = ensure_smem(h, kern, Cfg::smem(kMf2Warps))) return rc_;
-  kern<<<mf2_grid(h), kMf2Warps * 32, Cfg::smem(kMf2Warps), h->stream>>>(h->coord.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st,
-                                                                          h->geom.p, T);
+  auto kern = k_apply_mf2<NOD, GATHER, GEOM, WARPS, 2, PAIR>;
+  if (int rc_ = ensure_smem(h, kern, Cfg::smem(WARPS))) return rc_;
+  const int64_t nhg = (h->nels + 15) / 16;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (nhg + WARPS - 1) / WARPS));
+  kern<<<grid, WARPS * 32, Cfg::smem(WARPS), h->stream>>>(h->coord.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st, h->geom.p, T);
   h->launches++;
   CU(cudaGetLastError());
   return 0;
+}
+// PF_MF2=1 (adjacent-lane pairs) / PF_MF2W=8|16 select the other measured variants for A/B runs
+template <int NOD, bool GATHER, int GEOM>
+int launch_mf2_t(pf_handle h, const double *pvec, const State *st, PeerTable *T = nullptr) {
+  static const int pair = getenv("PF_MF2") ? atoi(getenv("PF_MF2")) : 16;
+  static const int warps = getenv("PF_MF2W") ? atoi(getenv("PF_MF2W")) : kMf2Warps;
+  if (GEOM == 2 && GATHER && NOD == 20) {
+    if (pair == 1 && warps == 16) return launch_mf2_tt<NOD, GATHER, GEOM, 16, 1>(h, pvec, st, T);
+    if (pair == 1) return launch_mf2_tt<NOD, GATHER, GEOM, kMf2Warps, 1>(h, pvec, st, T);
+    if (warps == 16) return launch_mf2_tt<NOD, GATHER, GEOM, 16, 16>(h, pvec, st, T);
+    if (warps == 8) return launch_mf2_tt<NOD, GATHER, GEOM, 8, 16>(h, pvec, st, T);
+  }
+  return launch_mf2_tt<NOD, GATHER, GEOM, kMf2Warps, 16>(h, pvec, st, T);
 }
 
 template <bool GATHER>
@@ -481,12 +496,12 @@ int launch_matvec(pf_handle h, const double *pvec, const State *st, PeerTable *T
     }
     return fail(h, 3, "unsupported ntot %d", h->ntot);
   }
-  // mode 2 (stored geometric factors): two lanes per element (k_apply_mf2, measured 0.848 against 0.867 ms at config C);
-  // mode 1 (factors rebuilt from the coordinates every call) keeps the one-lane kernel: its Jacobian pass spills at
-  // 128 registers (1.52 against 1.37 ms).  The two kernels add the points' contributions in different orders; the
-  // oracle mirrors each (orc_apply_mf, order by mode).
-  if (h->matrix_free && h->mf_mode == 2 && mf_two_lanes())
-    return h->nod == 20 ? launch_mf2_t<20, GATHER, 2>(h, pvec, st, T) : launch_mf2_t<8, GATHER, 2>(h, pvec, st, T);
+  // 20-node bricks: two lanes per element (k_apply_mf2; config C: mode 2 0.754 against 0.867 ms, mode 1 1.30 against 1.37 ms);
+  // 8-node bricks keep the one-lane kernel (200^3: 1.79 against 2.17 ms -- too little arithmetic per element to pay for
+  // the pairing).  The two kernels add the Gauss points' contributions in different orders; the oracle mirrors each
+  // (orc_apply_mf: order by element type).
+  if (h->matrix_free && h->nod == 20 && mf_two_lanes())
+    return h->mf_mode == 2 ? launch_mf2_t<20, GATHER, 2>(h, pvec, st, T) : launch_mf2_t<20, GATHER, 0>(h, pvec, st, T);
   if (h->matrix_free) {
     if (h->mf_mode == 2) {
       // PF_TUNE: unroll factor of the node-pair loops (default 2; measured in profiles/r01_mf_kernel_history.md)
@@ -1222,7 +1237,7 @@ int pf_form_km_elastic(pf_handle h, double e, double v) {
     if (h->mf_mode == 2) {
       // geometric factors: inverse Jacobian (9) + det*w (1) per element and Gauss point
       CU(h->geom.alloc((size_t)((h->nels + 31) / 32) * 32 * 80));   // [group][point][word][lane], padded to whole groups
-      if (mf_two_lanes()) rc = h->nod == 20 ? launch_mf2_t<20, false, 1>(h, nullptr, nullptr) : launch_mf2_t<8, false, 1>(h, nullptr, nullptr);
+      if (h->nod == 20 && mf_two_lanes()) rc = launch_mf2_t<20, false, 1>(h, nullptr, nullptr);
       else if (h->nod == 20) rc = launch_mf_t<20, false, 1>(h, nullptr, nullptr);
       else rc = launch_mf_t<8, false, 1>(h, nullptr, nullptr);
       if (rc) return rc;

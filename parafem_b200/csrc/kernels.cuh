@@ -1580,7 +1580,7 @@ struct Mf2Cfg {
   static constexpr size_t smem(int warps) { return (size_t)kDerBytes + (size_t)warps * (EPW * kRow * 8 + kIdxBytes + 16); }
 };
 
-template <int NOD, bool GATHER, int GEOM, int WARPS, int UNR = 2>
+template <int NOD, bool GATHER, int GEOM, int WARPS, int UNR = 2, int PAIR = 1>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 k_apply_mf2(const double *__restrict__ g_coord, const int *__restrict__ ggl, const double *__restrict__ pvec,
             double *__restrict__ utemp, long long nels, const State *st, double *geom, PeerTable *T) {
@@ -1591,7 +1591,9 @@ k_apply_mf2(const double *__restrict__ g_coord, const int *__restrict__ ggl, con
   if (st && *(volatile const int *)&st->done) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int el = lane >> 1, half = lane & 1;                 // this lane's element of the warp's 16 and its half of the points
+  // this lane's element of the warp's 16 and its half of the points: partner lane = lane ^ PAIR (PAIR 1: adjacent lanes,
+  // PAIR 16: the two half-warps -- every quarter-warp then reads ONE der address)
+  const int el = PAIR == 1 ? lane >> 1 : lane & 15, half = PAIR == 1 ? lane & 1 : lane >> 4;
   double *s_der = reinterpret_cast<double *>(smem_raw);                                   // [m][g][b]
   double *rows = reinterpret_cast<double *>(smem_raw + Cfg::kDerBytes) + (size_t)w * EPW * ROW;
   int *idxbuf = reinterpret_cast<int *>(smem_raw + Cfg::kDerBytes + (size_t)WARPS * EPW * ROW * 8) + (size_t)w * EPW * NTOT;
@@ -1628,7 +1630,7 @@ k_apply_mf2(const double *__restrict__ g_coord, const int *__restrict__ ggl, con
   for (; hg < nhg; hg += hstride) {
     const long long e0 = hg * EPW;
     const int ne = (int)((nels - e0) < EPW ? (nels - e0) : EPW);
-    const unsigned int pairmask = ne >= EPW ? 0xffffffffu : ((1u << (2 * ne)) - 1u);
+    const unsigned int pairmask = ne >= EPW ? 0xffffffffu : (PAIR == 1 ? ((1u << (2 * ne)) - 1u) : (((1u << ne) - 1u) * 0x10001u));
     // this lane pair's 16-byte words of the factors: word (g*5+j) of the element at gfl[(g*5+j)*32]
     double2 *gfl = reinterpret_cast<double2 *>(geom + (GEOM == 0 ? (long long)blockIdx.x * WARPS + w : (hg >> 1)) * kGroupGeom) +
                    (GEOM == 0 ? el : (int)(hg & 1) * 16 + el);
@@ -1763,6 +1765,8 @@ k_apply_mf2(const double *__restrict__ g_coord, const int *__restrict__ ggl, con
         // every lane has read its row of right-hand sides: the pair may now overwrite it with the products
         __syncwarp(pairmask);
         // phase 2: per freedom one 12-term chain over this lane's four points, then the partner's chain is added
+        // (exchanging only the six sums each lane needs -- two node pairs per shuffle round -- was measured SLOWER:
+        // 0.804 against 0.754 ms, the longer loop body loses more overlap than the 60 shuffles cost)
 #pragma unroll UNR
         for (int t = 0; t < NOD / 2; ++t) {
           double o[6];
@@ -1781,7 +1785,7 @@ k_apply_mf2(const double *__restrict__ g_coord, const int *__restrict__ ggl, con
             o[3 * h] = ox; o[3 * h + 1] = oy; o[3 * h + 2] = oz;
           }
 #pragma unroll
-          for (int q = 0; q < 6; ++q) o[q] = o[q] + __shfl_xor_sync(pairmask, o[q], 1);   // (points 0-3) + (points 4-7)
+          for (int q = 0; q < 6; ++q) o[q] = o[q] + __shfl_xor_sync(pairmask, o[q], PAIR);   // (points 0-3) + (points 4-7)
           if ((t & 1) == half) {
             sts128(row_s + (6 * t) * 8, o[0], o[1]);
             sts128(row_s + (6 * t + 2) * 8, o[2], o[3]);

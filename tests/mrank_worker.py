@@ -46,6 +46,13 @@ def problem(name, npes, numpe):
         return host.cube_p124(9, 11, 8, aa=.1, bb=.1, cc=.1, nstep=6, npes=npes, numpe=numpe, fixed=name.endswith("fixed"))
     if name == "p125":                   # explicit transient conduction
         return host.cube_p125(9, 11, 8, aa=.1, bb=.1, cc=.1, dtim=1e-4, nstep=30, npes=npes, numpe=numpe)
+    if name == "p129":                   # forced vibration: three matrix sets, one PCG solve per step
+        return host.cube_p129(3, 6, 2, .25, .25, .25, e=1.0e4, nip=8, nstep=4, npes=npes, numpe=numpe)
+    if name == "p122":                   # elasto-plasticity, loaded-nodes branch
+        p = host.cube_p121(4, 5, 3, 8, aa=1., bb=1., cc=1., e=100.0, v=0.3, npes=npes, numpe=numpe)
+        p.program, p.phi, p.c, p.psi = 122, 20.0, 4.0, 0.0
+        p.qinc, p.plasits, p.cjits, p.plastol, p.cjtol, p.loaded_nodes = [0.5, 0.3], 12, 80, 1e-4, 1e-6, 1
+        return p
     if name == "tet4":                   # 4-node tetrahedra, elastic (12x12 element matrices)
         from tet_util import tet_problem
         return tet_problem(host.cube_p121(5, 6, 3, 8, aa=1., bb=1., cc=1., limit=3000), npes, numpe)
@@ -90,6 +97,36 @@ def transient_specs(s, name, p, full, world):
     return ok, f"iters={its}/{ref['iters']}"
 
 
+def driver_specs(s, name, p, full, world):
+    """p129 / p122 on N ranks == the oracle emulating the same N ranks."""
+    from parafem_b200 import driver
+    lo = p.ieq_start - 1
+    if name == "p129":
+        km = oracle.form_km_elastic(full.g_coord_pp, 20, full.nip, full.e, full.v)
+        mm = oracle.form_mass(full.g_coord_pp, 20, full.nip, full.rho)
+        ref = oracle.p129(km, mm, full.g_g_pp, full.neq, full.r_pp, full.theta, full.omega, full.alpha1, full.beta1, full.nstep,
+                          full.tol, full.limit, npes=world, red_mode=1)
+        out = driver.run_p129(p, s)
+        ok = (np.array_equal(out["x"], ref["x"][lo:lo + p.neq_pp]) and np.array_equal(out["d1x"], ref["d1x"][lo:lo + p.neq_pp])
+              and np.array_equal(out["d2x"], ref["d2x"][lo:lo + p.neq_pp]))
+        if out["rows"]:                                    # the rank that owns nres
+            ok = ok and [r[3] for r in out["rows"]] == [r[2] for r in ref["rows"]]
+        return ok, f"iters={[r[2] for r in ref['rows']]}"
+    from oracle import p122_oracle
+    ref_rows, ref_totd = p122_oracle.p122(full.g_coord_pp, full.g_g_pp, full.neq, full.phi, full.c, full.psi, full.e, full.v,
+                                          full.qinc, full.plasits, full.cjits, full.plastol, full.cjtol, ld0=full.r_pp, npes=world,
+                                          red_mode=1)
+    out = driver.run_p122(p, s)
+    # the Lode-angle functions are CUDA's on the device and glibc's in the oracle: counts equal or within a few cj
+    # iterations, fields to the cj tolerance (tests/test_gpu_plastic.py)
+    ok = len(out["rows"]) == len(ref_rows)
+    for r, o in zip(out["rows"], ref_rows):
+        ok = ok and r[5] == o["plasiters"] and abs(r[4] - o["cjtot"]) <= max(2, 0.02 * o["cjtot"])
+    mine = ref_totd[lo:lo + p.neq_pp]
+    err = np.linalg.norm(out["totd"] - mine) / max(np.linalg.norm(ref_totd), 1e-300)
+    return ok and err <= 1e-6, f"plas={[o['plasiters'] for o in ref_rows]} cj={[r[4] for r in out['rows']]}/{[o['cjtot'] for o in ref_rows]} err={err:.1e}"
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dist.init_process_group(backend="gloo", rank=rank, world_size=world)
@@ -102,9 +139,9 @@ def main():
         name, _, variant = spec.partition(":")
         p = problem(name, world, rank + 1)
         full = problem(name, 1, 1)
-        if name in ("p124", "p124_fixed", "p125"):
+        if name in ("p124", "p124_fixed", "p125", "p129", "p122"):
             oracle.set_element_partition(None)
-            ok, info = transient_specs(s, name, p, full, world)
+            ok, info = (driver_specs if name in ("p129", "p122") else transient_specs)(s, name, p, full, world)
             line = f"[rank {rank}] {spec}: equal={ok} {info}"
             print(line, flush=True)
             if not ok:
