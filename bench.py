@@ -402,15 +402,29 @@ def mf_flops(mode, nodn):
     return fl
 
 
-def mf_roofline(prob, mode, m, peak):
+def mf_kernel_name():
+    sel = os.environ.get("PF_MF", "")
+    return {"1lane": "k_apply_mf", "2lane": "k_apply_mf2"}.get(sel, "k_apply_mf3")
+
+
+def mf_roofline(prob, mode, m, peaks):
+    """peaks = (DFMA loop, DMMA loop) TFLOP/s measured on this device.  k_apply_mf3 runs its two node sums on the FP64
+    tensor pipe, so its denominator is the tensor figure (the higher one); the DFMA figure stays in the line."""
+    dfma, dmma = peaks
     mv_ms_, mv_n_ = m["kernel_ms"]["matvec"]
     avg = mv_ms_ / max(mv_n_, 1)
     fl = prob.nels_pp * mf_flops(mode, prob.nod)
-    return {"bound": "fp64", "achieved": fl / (avg / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-            "frac": fl / (avg / 1e3) / 1e12 / peak, "traffic": None,
-            "kernel": "k_apply_mf (matrix-free operator form, gather fused)",
-            "peak_kind": "DFMA micro-benchmark on this device (pf_measure_fp64), fma = 2 flop",
+    tensor = mf_kernel_name() == "k_apply_mf3"
+    peak = dmma if tensor else dfma
+    ach = fl / (avg / 1e3) / 1e12
+    return {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+            "frac": ach / peak, "traffic": None,
+            "kernel": mf_kernel_name() + " (matrix-free operator form, gather fused)",
+            "peak_kind": ("mma.sync.m8n8k4.f64 micro-benchmark on this device (pf_measure_fp64_tensor), 512 flop per warp "
+                          "instruction" if tensor else "DFMA micro-benchmark on this device (pf_measure_fp64), fma = 2 flop"),
+            "peak_dfma": dfma, "peak_fp64_tensor": dmma, "frac_of_dfma_peak": ach / dfma,
             "algorithmic_flops_per_launch": fl, "flops_per_element": mf_flops(mode, prob.nod),
+            "flops_note": "algorithmic flops of the operator form (padding of the node tiles to 24 not counted)",
             "avg_launch_ms": avg, "launches_timed": int(mv_n_)}
 
 
@@ -614,7 +628,7 @@ def main():
     solver.setup_problem(s, prob, matrix_free=args.matrix_free, layout=args.layout)
     ctx.barrier()
     t_dev_setup = time.time() - t0
-    fp64_tflops = s.measure_fp64() if args.matrix_free else None
+    fp64_tflops = (s.measure_fp64(), s.measure_fp64_tensor()) if args.matrix_free else None
     hbm_read_gbs = s.measure_hbm_read() if not args.matrix_free else None   # read-only stream ceiling (informational)
     m = measure(ctx, prob)
     tts = None if args.no_solve else solve_to_convergence(ctx, prob)
@@ -640,7 +654,7 @@ def main():
         peak = None
         for mode, name in ((2, "matrix_free_geometric_factors"), (1, "matrix_free_rebuilt_from_coordinates")):
             solver.setup_problem(s, prob, matrix_free=mode)
-            peak = peak or s.measure_fp64()
+            peak = peak or (s.measure_fp64(), s.measure_fp64_tensor())
             mm = measure(ctx, prob)
             variants[name] = block(ctx, prob, mm, mf_roofline(prob, mode, mm, peak),
                                    solve_to_convergence(ctx, prob) if (mode == 2 and not args.no_solve) else None)

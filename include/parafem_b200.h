@@ -262,6 +262,9 @@ int64_t pf_kernel_launches(pf_handle h); /* all kernel launches since pf_init */
 /* DFMA micro-benchmark on this device: the FP64 roofline denominator of the
  * matrix-free variant ("FP64 peak is not in MEASURED_PEAKS.json").  */
 int pf_measure_fp64(pf_handle h, double *tflops);
+/* The same for the FP64 tensor pipe (mma.sync.m8n8k4.f64, 512 flop per warp instruction): the roofline
+ * denominator of the tensor-core matrix-free kernel (k_apply_mf3).                              */
+int pf_measure_fp64_tensor(pf_handle h, double *tflops);
 /* Read-only HBM stream through the same bulk-copy ring as the mat-vec, no arithmetic (GB/s):
  * MEASURED_PEAKS.json's hbm_gbs is a copy (read + write); this is the read-stream ceiling.     */
 int pf_measure_hbm_read(pf_handle h, double *gbs);

@@ -339,18 +339,30 @@ def find_g4(g_num, rest):
 
 
 def set_mf_order(order):
-    """1: the summation order of k_apply_mf2 (20-node bricks: two lanes per element, two 12-term chains added); 0: that
-    of k_apply_mf (8-node bricks: one 24-term chain per freedom)."""
+    """2: the summation order of k_apply_mf3 (FP64 tensor-core kernel, the default for both bricks: one fma chain in the
+    k order of its mma instructions); 1: k_apply_mf2 (PF_MF=2lane: two 12-term chains added); 0: k_apply_mf
+    (PF_MF=1lane: one 24-term chain, Gauss points ascending)."""
     lib().orc_set_mf_order(int(order))
+
+
+def default_mf_order(nod):
+    """The order of the kernel the library launches for this element type (PF_MF in the environment selects the older
+    kernels for A/B runs; the tests follow it)."""
+    sel = os.environ.get("PF_MF", "")
+    if sel == "1lane":
+        return 0
+    if sel == "2lane":
+        return 1 if nod == 20 else 0
+    return 2
 
 
 def apply_mf(g_coord_pp, nod, nip, e, v, pmul, mode=2):
     """Matrix-free element products (config E): utemp = sum_gp B^T D B p det w in the operation order of the device
-    kernel of that element type (20-node bricks: k_apply_mf2; 8-node bricks: k_apply_mf; both matrix-free modes of a
+    kernel in use (k_apply_mf3 unless PF_MF selects an older one; both matrix-free modes of a
     kernel give the same bits, ``mode`` is accepted for symmetry with the device call)."""
     g, pm = _f64(g_coord_pp), _f64(pmul)
     out = np.empty(pm.shape)
-    set_mf_order(1 if nod == 20 else 0)
+    set_mf_order(default_mf_order(nod))
     rc = lib().orc_apply_mf(g.shape[0], nod, nip, _p(g), e, v, _p(pm), _p(out))
     assert rc == 0
     return out
@@ -370,7 +382,7 @@ def pcg(storkm, g_g, neq, r, tol, limit, npes=1, red_mode=0, no_f=None, val_f=No
     it, conv, secs = cint(), cint(), dbl()
     mfc = _f64(mf["g_coord_pp"]) if mf else None     # mf = dict(g_coord_pp, nod, nip, e, v[, mode]): matrix-free products
     if mf:
-        set_mf_order(1 if mf["nod"] == 20 else 0)
+        set_mf_order(default_mf_order(mf["nod"]))
     rc = lib().orc_pcg(ntot, nels, _p(g), _p(k), neq, _p(r), nfixed, _p(no_f), _p(val_f), penalty, npes,
                        red_mode, tol, limit, _p(x), C.byref(it), C.byref(conv), _p(ratio), _p(diag),
                        C.byref(secs), _p(mfc), mf["nod"] if mf else 0, mf["nip"] if mf else 0,

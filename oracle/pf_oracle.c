@@ -904,17 +904,22 @@ void orc_matvec(int ntot, int64_t nels, const double *storkm, const double *pmul
  *   eps    = (G00, G11, G22, G10+G01, G21+G12, G20+G02)      beemat's row order
  *   sigma  = D eps                          product + c-ascending fmas per row, then * det*w
  *   T(b,c) = sum_a inv(a,b) S(a,c)          S = symmetric stress tensor; product, two fmas
- * and then per dof one chain over (Gauss point ascending, b ascending) for each HALF of the points, the two added:
- *   u_c(m) = [sum_{gp<4} sum_b der_gp(b,m) T_gp(b,c)] + [sum_{gp>=4} ...]   each: first term a product, then 11 fmas
- * (orc_set_mf_order(0): ONE 24-term chain, the round-1 kernel).
- * This is the operation order of k_apply_mf2 in parafem_b200/csrc/kernels.cuh.  It is a
+ * and then per dof the sum over (Gauss point, b) in the order of the device kernel in use (g_mf_order below):
+ *   order 2 (k_apply_mf3)  u_c(m) = one fma chain from 0.0 over (h | b | q), Gauss point 2q+h
+ *   order 1 (k_apply_mf2)  u_c(m) = [sum_{gp<4} sum_b der_gp(b,m) T_gp(b,c)] + [sum_{gp>=4} ...], each: a product, then 11 fmas
+ *   order 0 (k_apply_mf)   ONE 24-term chain, Gauss point ascending, b ascending
+ * These are the operation orders of the kernels in parafem_b200/csrc/kernels.cuh.  Each is a
  * different rounding of the same operator as MATMUL(storkm,pmul) (p121.f90:94), hence its
  * own oracle.
  */
-/* 1: the order of k_apply_mf2 (two lanes per element, the default kernel); 0: the order of the round-1 kernel
- * k_apply_mf (PF_MF=1lane) */
-static int g_mf_order = 1;
-void orc_set_mf_order(int order) { g_mf_order = order ? 1 : 0; }
+/* 2: the order of k_apply_mf3 (FP64 tensor-core kernel, the default for both bricks): per freedom ONE 24-term fma chain
+ *    from 0.0 over (h = 0,1 | b = 0,1,2 | q = 0..3) with Gauss point 2q+h -- the k order of its mma.sync.m8n8k4.f64
+ *    instructions, each of which is a k-ascending fma chain on the accumulator (measured on the B200 bit for bit,
+ *    scripts/probe/dmma_probe.cu);
+ * 1: the order of k_apply_mf2 (two lanes per element, PF_MF=2lane); 0: the order of the round-1 kernel k_apply_mf
+ *    (PF_MF=1lane) */
+static int g_mf_order = 2;
+void orc_set_mf_order(int order) { g_mf_order = (order >= 0 && order <= 2) ? order : 2; }
 static void mf_element(int nod, double der[8][60] /*[ig][a*20+m]*/, const double *coord, const double *dee,
                        const double *weights, const double *pm, double *ut) {
   double T[8][9];
@@ -944,6 +949,15 @@ static void mf_element(int nod, double der[8][60] /*[ig][a*20+m]*/, const double
         G[a * 3 + c] = s;
       }
     const double eps[6] = {G[0], G[4], G[8], G[3] + G[1], G[7] + G[5], G[6] + G[2]};
+    if (g_mf_order == 2) {              /* k_apply_mf3 leaves deemat's structural zeros out (mf_point_mid_iso) */
+      for (int r = 0; r < 3; ++r) {
+        double s = dee[r] * eps[0];
+        s = fma(dee[6 + r], eps[1], s);
+        s = fma(dee[12 + r], eps[2], s);
+        sig[r] = s * f;
+      }
+      for (int r = 3; r < 6; ++r) sig[r] = (dee[r * 6 + r] * eps[r]) * f;
+    } else
     for (int r = 0; r < 6; ++r) {
       double s = dee[r] * eps[0];
       for (int c = 1; c < 6; ++c) s = fma(dee[c * 6 + r], eps[c], s);
@@ -960,7 +974,13 @@ static void mf_element(int nod, double der[8][60] /*[ig][a*20+m]*/, const double
   }
   for (int m = 0; m < nod; ++m)
     for (int c = 0; c < 3; ++c) {
-      if (g_mf_order == 0) {            /* k_apply_mf (round 1): one 24-term chain */
+      if (g_mf_order == 2) {            /* k_apply_mf3: the k order of its phase-3 mma instructions */
+        double s = 0.0;
+        for (int h = 0; h < 2; ++h)
+          for (int b = 0; b < 3; ++b)
+            for (int q = 0; q < 4; ++q) s = fma(T[2 * q + h][b * 3 + c], der[2 * q + h][b * 20 + m], s);
+        ut[3 * m + c] = s;
+      } else if (g_mf_order == 0) {     /* k_apply_mf (round 1): one 24-term chain */
         double s = der[0][m] * T[0][c];
         for (int ig = 0; ig < 8; ++ig)
           for (int b = 0; b < 3; ++b) {

@@ -449,10 +449,7 @@ int launch_matvec_km_t(pf_handle h, const double *pvec, const State *st, PeerTab
 // k_apply_mf2: two lanes per element; 12 warps per SM (3 per scheduler, 168 registers, no spills) with the two halves
 // of an element on the two half-warps measured best (profiles/r02_mf_kernel_round2.md); PF_MF=1lane selects k_apply_mf
 constexpr int kMf2Warps = 12;
-bool mf_two_lanes() {
-  static const bool on = !(getenv("PF_MF") && !strcmp(getenv("PF_MF"), "1lane"));
-  return on;
-}
+bool mf_two_lanes();
 int mf2_grid(pf_handle h) {
   const int64_t nhg = (h->nels + 15) / 16;
   return (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (nhg + kMf2Warps - 1) / kMf2Warps));
@@ -483,6 +480,65 @@ int launch_mf2_t(pf_handle h, const double *pvec, const State *st, PeerTable *T 
   return launch_mf2_tt<NOD, GATHER, GEOM, kMf2Warps, 16>(h, pvec, st, T);
 }
 
+// k_apply_mf4 / k_apply_mf3: the FP64 tensor-core kernels (mma.sync.m8n8k4.f64); the warp-specialised k_apply_mf4 is the
+// default for both bricks and both matrix-free modes, PF_MF=3 selects the first build (every warp moves its own data).
+// PF_MF=2lane / 1lane select the round-2 / round-1 DFMA kernels for A/B runs (each has its own summation order, mirrored
+// by the oracle: orc_set_mf_order).
+int mf_kernel_choice() {
+  static const int c = [] {
+    const char *e = getenv("PF_MF");
+    if (e && !strcmp(e, "1lane")) return 1;
+    if (e && !strcmp(e, "2lane")) return 2;
+    if (e && !strcmp(e, "3")) return 3;
+    return 4;
+  }();
+  return c;
+}
+bool mf_two_lanes() { return mf_kernel_choice() != 1; }
+constexpr int kMf3Warps = 12;
+template <int NOD, bool GATHER, int GEOM, int WARPS, int BREG>
+int launch_mf3_tt(pf_handle h, const double *pvec, const State *st, PeerTable *T) {
+  using Cfg = Mf3Cfg<NOD>;
+  auto kern = k_apply_mf3<NOD, GATHER, GEOM, WARPS, BREG>;
+  if (int rc_ = ensure_smem(h, kern, Cfg::smem(WARPS, GEOM))) return rc_;
+  const int64_t npass = (h->nels + Cfg::EPP - 1) / Cfg::EPP;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (npass + WARPS - 1) / WARPS));
+  kern<<<grid, WARPS * 32, Cfg::smem(WARPS, GEOM), h->stream>>>(h->coord.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st, h->geom.p, T);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+// PF_MF3W = 16 | 12h (12 warps, phase-1 fragments in registers) | default 12 warps, fragments from the shared-memory table
+template <int NOD, bool GATHER, int GEOM>
+int launch_mf3_t(pf_handle h, const double *pvec, const State *st, PeerTable *T = nullptr) {
+  static const char *sel = getenv("PF_MF3W") ? getenv("PF_MF3W") : "";
+  if (!strcmp(sel, "12h")) return launch_mf3_tt<NOD, GATHER, GEOM, 12, 1>(h, pvec, st, T);
+  if (!strcmp(sel, "16")) return launch_mf3_tt<NOD, GATHER, GEOM, 16, 0>(h, pvec, st, T);
+  return launch_mf3_tt<NOD, GATHER, GEOM, kMf3Warps, 0>(h, pvec, st, T);
+}
+
+// k_apply_mf4: the warp-specialised build of the tensor-core kernel (PF_MF=3 selects k_apply_mf3 for A/B runs);
+// PF_MF4C = consumer warps per SM (8 or 12)
+constexpr int kMf4Cons = 12;
+template <int NOD, bool GATHER, int GEOM, int NCW>
+int launch_mf4_tt(pf_handle h, const double *pvec, const State *st, PeerTable *T) {
+  using Cfg = Mf4Cfg<NOD, NCW>;
+  auto kern = k_apply_mf4<NOD, GATHER, GEOM, NCW>;
+  if (int rc_ = ensure_smem(h, kern, Cfg::kSmem)) return rc_;
+  const int64_t npass = (h->nels + Cfg::EPP - 1) / Cfg::EPP;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (npass + Cfg::NCONS - 1) / Cfg::NCONS));
+  kern<<<grid, Cfg::kThreads, Cfg::kSmem, h->stream>>>(h->coord.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st, h->geom.p, T);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+template <int NOD, bool GATHER, int GEOM>
+int launch_mf4_t(pf_handle h, const double *pvec, const State *st, PeerTable *T = nullptr) {
+  static const int ncw = getenv("PF_MF4C") ? atoi(getenv("PF_MF4C")) : kMf4Cons;
+  if (ncw == 8) return launch_mf4_tt<NOD, GATHER, GEOM, 8>(h, pvec, st, T);
+  return launch_mf4_tt<NOD, GATHER, GEOM, kMf4Cons>(h, pvec, st, T);
+}
+
 template <bool GATHER>
 int launch_matvec(pf_handle h, const double *pvec, const State *st, PeerTable *T = nullptr) {
   Scope sc(h, K_MATVEC);
@@ -500,6 +556,14 @@ int launch_matvec(pf_handle h, const double *pvec, const State *st, PeerTable *T
   // 8-node bricks keep the one-lane kernel (200^3: 1.79 against 2.17 ms -- too little arithmetic per element to pay for
   // the pairing).  The two kernels add the Gauss points' contributions in different orders; the oracle mirrors each
   // (orc_apply_mf: order by element type).
+  if (h->matrix_free && mf_kernel_choice() == 4) {
+    if (h->nod == 20) return h->mf_mode == 2 ? launch_mf4_t<20, GATHER, 2>(h, pvec, st, T) : launch_mf4_t<20, GATHER, 0>(h, pvec, st, T);
+    return h->mf_mode == 2 ? launch_mf4_t<8, GATHER, 2>(h, pvec, st, T) : launch_mf4_t<8, GATHER, 0>(h, pvec, st, T);
+  }
+  if (h->matrix_free && mf_kernel_choice() == 3) {
+    if (h->nod == 20) return h->mf_mode == 2 ? launch_mf3_t<20, GATHER, 2>(h, pvec, st, T) : launch_mf3_t<20, GATHER, 0>(h, pvec, st, T);
+    return h->mf_mode == 2 ? launch_mf3_t<8, GATHER, 2>(h, pvec, st, T) : launch_mf3_t<8, GATHER, 0>(h, pvec, st, T);
+  }
   if (h->matrix_free && h->nod == 20 && mf_two_lanes())
     return h->mf_mode == 2 ? launch_mf2_t<20, GATHER, 2>(h, pvec, st, T) : launch_mf2_t<20, GATHER, 0>(h, pvec, st, T);
   if (h->matrix_free) {
@@ -973,6 +1037,26 @@ int pf_measure_fp64(pf_handle h, double *tflops) {
   }
   h->launches += 4;
   cudaEventDestroy(e0); cudaEventDestroy(e1); out.release();
+  *tflops = best;
+  return 0;
+}
+
+int pf_measure_fp64_tensor(pf_handle h, double *tflops) {
+  int rc = need_device(h); if (rc) return rc;
+  DevBuf<double> out; CU(out.alloc(1));
+  const int iters = 4000, threads = 256, blocks = h->sm_count * 2;
+  EventPair ev; CU(ev.create());
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CU(cudaEventRecord(ev.a, h->stream));
+    k_fp64_tensor_peak<<<blocks, threads, 0, h->stream>>>(out.p, iters, 1.0000001, 1e-9);
+    CU(cudaEventRecord(ev.b, h->stream));
+    CU(cudaEventSynchronize(ev.b));
+    float ms = 0.f; CU(cudaEventElapsedTime(&ms, ev.a, ev.b));
+    const double tf = 2.0 * 256.0 * 9.0 * iters * (double)(threads / 32) * blocks / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  h->launches += 4;
   *tflops = best;
   return 0;
 }

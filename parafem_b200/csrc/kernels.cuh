@@ -1310,6 +1310,43 @@ __device__ __forceinline__ void mf_point_mid(const double *H, const double *inv,
     }
 }
 
+// The same with deemat's structural zeros left out (isotropic dee, new_library.f90:905-930: a 3x3 block and a diagonal):
+// the normal stresses are 3-term chains, the shear stresses single products -- 18 instead of 42 FP64 instructions.
+// The left-out terms are products with an exact 0.0.  k_apply_mf3 and the oracle's order 2 use this form.
+__device__ __forceinline__ void mf_point_mid_iso(const double *H, const double *inv, double f, double *T) {
+  double G[9];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double s = inv[a] * H[c];
+      s = fma(inv[3 + a], H[3 + c], s);
+      s = fma(inv[6 + a], H[6 + c], s);
+      G[a * 3 + c] = s;
+    }
+  const double eps[6] = {G[0], G[4], G[8], G[3] + G[1], G[7] + G[5], G[6] + G[2]};
+  double sig[6];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    double s = c_tab.dee[r] * eps[0];
+    s = fma(c_tab.dee[6 + r], eps[1], s);
+    s = fma(c_tab.dee[12 + r], eps[2], s);
+    sig[r] = s * f;
+  }
+#pragma unroll
+  for (int r = 3; r < 6; ++r) sig[r] = (c_tab.dee[r * 6 + r] * eps[r]) * f;
+  const double S[9] = {sig[0], sig[3], sig[5], sig[3], sig[1], sig[4], sig[5], sig[4], sig[2]};
+#pragma unroll
+  for (int b = 0; b < 3; ++b)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double s = inv[b * 3] * S[c];
+      s = fma(inv[b * 3 + 1], S[3 + c], s);
+      s = fma(inv[b * 3 + 2], S[6 + c], s);
+      T[b * 3 + c] = s;
+    }
+}
+
 // GEOM 0: rebuild jac / inverse / det at every point from the coordinates every call (config E as
 //         named); the 80 factors of an element pass through a per-thread scratch line in `geom`
 //         (L2-resident, never re-read by another thread);
@@ -1802,6 +1839,625 @@ k_apply_mf2(const double *__restrict__ g_coord, const int *__restrict__ ggl, con
         }
       __syncwarp();
     }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// k_apply_mf3: the same operator on the FP64 TENSOR pipe (round 2, second build).  The two node sums of the matrix-free
+// product are small GEMMs with a CONSTANT operand (der is the same for every element):
+//   phase 1   H_e,g(b,c) = sum_m der_g(b,m) p_e,c(m)       [8 elements x 3] x [NOD] x [8 points x 3]
+//   phase 3   u_e,c(m)   = sum_(g,b) T_e,g(b,c) der_g(b,m)  [8 elements x 3] x [8 points x 3] x [NOD]
+// issued as mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; measured on the B200, scripts/probe/dmma_probe.cu: 37.2 TFLOP/s
+// against 33.9 of the DFMA loop, and D = fma(a3,b3,fma(a2,b2,fma(a1,b1,fma(a0,b0,c)))) bit for bit, i.e. a k-ascending
+// fma chain -- which is how the oracle states it).  A warp pass is 8 elements: lane (r = lane/4, q = lane%4) feeds
+// element r.  The fragment layouts are chosen so that NOTHING is transposed between the phases:
+//   phase 1: rows (M) = (component c | element r), k = node, columns (N) = (b | point g): the accumulator fragment of
+//            lane (r,q) is the complete 3x3 H of element r at the points 2q and 2q+1 -> mf_point_mid in registers;
+//   phase 3: rows = (c | element r), k = (h, b | q) <-> point 2q+h, columns = node: the A fragments are exactly the
+//            T values the lane has just formed.
+// der lives in registers as the B fragments of both phases (33 doubles per lane for 20-node bricks), so the shared-memory
+// der table and its 30 LDS wavefronts per element of k_apply_mf / k_apply_mf2 are gone; shared memory only stages the
+// gathered right-hand sides (coalesced gather -> rows -> A fragments) and the products (fragments -> rows -> coalesced
+// store).  Chain orders (orc_apply_mf, order 2): H and jac node-ascending from 0.0 as before; u_c(m) ONE 24-term fma
+// chain from 0.0 over (h = 0,1 | b = 0,1,2 | q = 0..3), point g = 2q+h.
+// GEOM 0: jac comes from the same phase-1 product on the coordinates, det / inverse stay in registers (no scratch);
+// GEOM 2: reads the factors k_apply_mf2<GEOM 1> stored ([group of 32][point][word][lane]).  Same bits in both modes.
+// ----------------------------------------------------------------------------
+template <int NOD>
+struct Mf3Cfg {
+  static constexpr int NTOT = 3 * NOD, EPP = 8;                       // elements per warp pass
+  static constexpr int KS1 = NOD / 4, NT3 = (NOD + 7) / 8;            // k-steps of phase 1, node tiles of phase 3
+  static constexpr int NF = KS1 * 3 + 6 * NT3;                        // der fragments per lane (33 / 12)
+  // row stride (doubles) == 4 or 12 mod 16: the A-fragment reads rows[r][3(4s+q)+c] of a half-warp hit 16 distinct
+  // 8-byte bank pairs (20-node: 60, 8-node: 28)
+  static constexpr int kRow = (NTOT % 16 == 4 || NTOT % 16 == 12) ? NTOT : NTOT + ((12 - NTOT % 16) + 16) % 16;
+  static constexpr int kIdxBytes = EPP * NTOT * 4;
+  static constexpr int kFragBytes = NF * 32 * 8;
+  // per warp: two row buffers (pass n is computed while pass n+1 lands), with GEOM 0 one coordinate buffer, the indices
+  __host__ __device__ static constexpr size_t per_warp(int geom) { return (size_t)(geom == 0 ? 3 : 2) * EPP * kRow * 8 + kIdxBytes; }
+  static constexpr size_t smem(int warps, int geom) { return (size_t)kFragBytes + (size_t)warps * (per_warp(geom) + 16); }
+};
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// BREG 2: all der fragments live in registers for the whole kernel; 1: those of phase 1 (and the Jacobian product);
+// 0: every fragment is read from a conflict-free shared-memory table [fragment][lane] at its use.
+// The products leave through ONE bulk async store per pass (shared -> global, no LSU wavefronts).
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int NOD, bool GATHER, int GEOM, int WARPS, int BREG>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_apply_mf3(const double *__restrict__ g_coord, const int *__restrict__ ggl, const double *__restrict__ pvec,
+            double *__restrict__ utemp, long long nels, const State *st, const double *__restrict__ geom, PeerTable *T) {
+  using Cfg = Mf3Cfg<NOD>;
+  constexpr int NTOT = Cfg::NTOT, ROW = Cfg::kRow, EPP = Cfg::EPP, KS1 = Cfg::KS1, NT3 = Cfg::NT3, NF = Cfg::NF;
+  constexpr int KP = (EPP * NTOT + 31) / 32;                 // flat (element, freedom) words of a pass per lane
+  constexpr long long kGroupGeom = 32LL * 80;                // doubles per group of 32 elements (MfCfg::kGroupGeom)
+  static_assert(NOD % 4 == 0, "phase 1 takes the nodes four at a time");
+  static_assert(GEOM == 0 || GEOM == 2, "the factors of mode 2 are written by k_apply_mf2<GEOM 1>");
+  if (st && *(volatile const int *)&st->done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, q = lane & 3;
+  double *s_frag = reinterpret_cast<double *>(smem_raw);
+  unsigned char *mine = smem_raw + Cfg::kFragBytes + (size_t)w * Cfg::per_warp(GEOM);
+  double *rows2 = reinterpret_cast<double *>(mine);                                        // [2][EPP*ROW]
+  double *cbuf = rows2 + 2 * EPP * ROW;                                                    // GEOM 0 only
+  int *idxbuf = reinterpret_cast<int *>(mine + (size_t)(GEOM == 0 ? 3 : 2) * EPP * ROW * 8);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + Cfg::kFragBytes + (size_t)WARPS * Cfg::per_warp(GEOM));
+  const uint32_t bar = smem_u32(&bars[w]);
+  // der as B fragments (lane holds B[k = q][n = r]):
+  //   fragment s*3+b            phase 1, k-step s, column tile b:   der_{g=r}(b, m = 4s+q)
+  //   fragment 3 KS1 + (3h+b) NT3 + nt   phase 3, k-step 3h+b, node tile nt: der_{g=2q+h}(b, m = 8nt+r), 0 beyond the last node
+  for (int i = threadIdx.x; i < NF * 32; i += blockDim.x) {
+    const int f = i >> 5, l = i & 31, rr = l >> 2, qq = l & 3;
+    double v;
+    if (f < 3 * KS1) {
+      const int s = f / 3, b = f - 3 * s;
+      v = c_tab.der[rr * 60 + b * 20 + 4 * s + qq];
+    } else {
+      const int f3 = f - 3 * KS1, sb = f3 / NT3, nt = f3 - sb * NT3, h = sb / 3, b = sb - 3 * h;
+      v = (8 * nt + rr < NOD) ? c_tab.der[(2 * qq + h) * 60 + b * 20 + 8 * nt + rr] : 0.0;
+    }
+    s_frag[i] = v;
+  }
+  __syncthreads();
+  constexpr int NREG = BREG == 2 ? NF : (BREG == 1 ? 3 * KS1 : 0);
+  double Breg[NREG > 0 ? NREG : 1];
+#pragma unroll
+  for (int f = 0; f < NREG; ++f) {
+    Breg[f] = s_frag[f * 32 + lane];
+    asm volatile("" : "+d"(Breg[f]));                        // opaque: kept in a register, not re-read
+  }
+  auto fragB = [&](int f) -> double { return f < NREG ? Breg[f] : s_frag[f * 32 + lane]; };
+  const long long npass = (nels + EPP - 1) / EPP;
+  const long long pstride = (long long)gridDim.x * WARPS;
+  uint64_t policy = 0;
+  uint32_t phase = 0;
+  auto issue_idx = [&](long long ps) {                       // lane 0 only
+    const long long e0 = ps * EPP;
+    const int ne = (int)((nels - e0) < EPP ? (nels - e0) : EPP);
+    const uint32_t bytes = (uint32_t)ne * NTOT * 4;
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(smem_u32(idxbuf), ggl + e0 * NTOT, bytes, bar, policy);
+  };
+  // right-hand sides (and with GEOM 0 the coordinates) of pass ps: asynchronous 8-byte copies straight into shared
+  // memory, coalesced over the pass's (element, freedom) words; nothing is held in registers while they fly
+  auto issue_data = [&](long long ps, double *dst) {
+    const long long e0 = ps * EPP;
+    const int ne = (int)((nels - e0) < EPP ? (nels - e0) : EPP);
+    const int nw = ne * NTOT;
+#pragma unroll
+    for (int kp = 0; kp < KP; ++kp) {
+      const int f = lane + 32 * kp;
+      if (f < EPP * NTOT) {
+        double *d = dst + (f / NTOT) * ROW + (f % NTOT);
+        if (f < nw) cp_async8(smem_u32(d), GATHER ? pvec + idxbuf[f] : pvec + e0 * NTOT + f);
+        else *d = 0.0;
+      }
+    }
+    if (GEOM == 0) {
+#pragma unroll
+      for (int kp = 0; kp < KP; ++kp) {
+        const int f = lane + 32 * kp;
+        if (f < EPP * NTOT) {
+          double *d = cbuf + (f / NTOT) * ROW + (f % NTOT);
+          if (f < nw) cp_async8(smem_u32(d), g_coord + e0 * NTOT + f);
+          else *d = 0.0;
+        }
+      }
+    }
+    cp_async_commit();
+  };
+  long long ps = (long long)blockIdx.x * WARPS + w;
+  if (ps >= npass) return;
+  if (GATHER) {
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+      policy = policy_evict_first();
+      issue_idx(ps);
+    }
+    __syncwarp();
+    // N ranks, peer transport: the owners' values are in my halo segment of pvec; nothing of pvec is read before this
+    if (T) warp_wait_fwd(T, st);
+    mbar_wait(bar, phase);
+    phase ^= 1;
+  }
+  issue_data(ps, rows2);
+  __syncwarp();
+  if (GATHER && lane == 0 && ps + pstride < npass) {
+    fence_proxy_async();                                     // generic reads of idxbuf before the async overwrite
+    issue_idx(ps + pstride);
+  }
+  int buf = 0;
+  for (; ps < npass; ps += pstride, buf ^= 1) {
+    const long long e0 = ps * EPP;
+    const int ne = (int)((nels - e0) < EPP ? (nels - e0) : EPP);
+    const int nw = ne * NTOT;                                // words of this pass
+    double *rows = rows2 + buf * EPP * ROW;
+    double gq[2][10];                                        // jac^-1 (9) and det*w of the lane's two points
+    if (GEOM == 2) {
+      // word (g*5+j) of element i of a group at [(g*5+j)*32 + i] (16-byte words); in flight during phase 1
+      const double2 *gfl = reinterpret_cast<const double2 *>(geom + (e0 >> 5) * kGroupGeom) + ((int)(e0 & 31) + r);
+      if (r < ne) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const double2 v = __ldg(gfl + ((2 * q + h) * 5 + j) * 32);
+            gq[h][2 * j] = v.x; gq[h][2 * j + 1] = v.y;
+          }
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int j = 0; j < 10; ++j) gq[h][j] = 0.0;
+      }
+      const long long en = (ps + pstride) * EPP;             // next pass: its 40 lines of factors towards L2
+      if (r == 0 && en < nels) {
+        const double2 *gn = reinterpret_cast<const double2 *>(geom + (en >> 5) * kGroupGeom) + (int)(en & 31);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int j = 0; j < 5; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + ((2 * q + h) * 5 + j) * 32));
+      }
+    }
+    cp_async_wait_all();
+    __syncwarp();                                            // this pass's rows (and coordinates) have landed
+    if (GEOM == 0) {
+      double J[3][3][2];                                     // [b: x,y,z][a][h] = jac(a,b) at point 2q+h
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) J[b][a][0] = J[b][a][1] = 0.0;
+#pragma unroll
+      for (int s = 0; s < KS1; ++s) {
+        double a3[3];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) a3[b] = cbuf[r * ROW + b * NOD + 4 * s + q];
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+          for (int a = 0; a < 3; ++a) dmma884(J[b][a][0], J[b][a][1], a3[b], fragB(s * 3 + a));
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double Jm[9];
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+          for (int a = 0; a < 3; ++a) Jm[b * 3 + a] = J[b][a][h];
+        const double det = det3(Jm);
+        inv3(Jm, det, gq[h]);
+        gq[h][9] = det * c_tab.weights[2 * q + h];
+      }
+      __syncwarp();                                          // the coordinate buffer is free for the next pass
+    }
+    // the next pass's data starts to move now and lands during this pass's arithmetic
+    if (ps + pstride < npass) {
+      if (GATHER) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+      }
+      bulk_wait_read_all();                                  // the previous pass's products have left the other buffer
+      __syncwarp();
+      issue_data(ps + pstride, rows2 + (buf ^ 1) * EPP * ROW);
+      __syncwarp();
+      if (GATHER && lane == 0 && ps + 2 * pstride < npass) {
+        fence_proxy_async();
+        issue_idx(ps + 2 * pstride);
+      }
+    }
+    // phase 1: H[c][b][h] = H_{element r, point 2q+h}(b,c)
+    double H[3][3][2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) H[c][b][0] = H[c][b][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < KS1; ++s) {
+      double a3[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a3[c] = rows[r * ROW + 3 * (4 * s + q) + c];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) dmma884(H[c][b][0], H[c][b][1], a3[c], fragB(s * 3 + b));
+    }
+    double Tm[2][9];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double Hm[9];
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Hm[b * 3 + c] = H[c][b][h];
+      mf_point_mid_iso(Hm, gq[h], gq[h][9], Tm[h]);
+    }
+    // phase 3: U[c][nt][h'] = u_c(m = 8nt + 2q + h') of element r
+    double U[3][NT3][2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int nt = 0; nt < NT3; ++nt) U[c][nt][0] = U[c][nt][1] = 0.0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int nt = 0; nt < NT3; ++nt) dmma884(U[c][nt][0], U[c][nt][1], Tm[h][b * 3 + c], fragB(3 * KS1 + (3 * h + b) * NT3 + nt));
+    // every lane's A-fragment reads of the rows precede the warp-wide mma above: the rows may take the products
+#pragma unroll
+    for (int nt = 0; nt < NT3; ++nt)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int m = 8 * nt + 2 * q + hh;
+        if (m < NOD) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) rows[r * ROW + 3 * m + c] = U[c][nt][hh];
+        }
+      }
+    fence_proxy_async();                                     // my generic stores before the async proxy reads them
+    __syncwarp();
+    if (ROW == NTOT) {
+      if (lane == 0) { bulk_s2g(utemp + e0 * NTOT, smem_u32(rows), (uint32_t)nw * 8); bulk_commit(); }
+    } else if (lane < ne) {
+      bulk_s2g(utemp + (e0 + lane) * NTOT, smem_u32(rows + lane * ROW), NTOT * 8);
+      bulk_commit();
+    }
+  }
+  bulk_wait_all();                                           // shared memory must outlive the stores
+}
+
+// ----------------------------------------------------------------------------
+// k_apply_mf4: k_apply_mf3's arithmetic, WARP-SPECIALISED.  ncu of k_apply_mf3 (profiles/r02_mf_tensor_kernel.md): every
+// warp alternates between moving data (index loads -> gathers -> staging, LSU-bound, no FP64) and arithmetic, the DMMA
+// pipe is busy 48 % of the time and the der-fragment table costs as many shared-memory wavefronts as the gather.  Here
+// a CTA of 384 threads is one producer warpgroup (4 warps, 56 registers) and two consumer warpgroups (8 warps, 224
+// registers, setmaxnreg):
+//   producer warp j (scheduler j) feeds consumer warps j and j+4 (same scheduler): per pass of 8 elements it waits for a
+//     free ring stage, reads the pass's gather indices (bulk-copied two passes ahead), issues the asynchronous 8-byte
+//     gathers straight into the stage (cp.async, completion counted on the stage's `full` mbarrier), with GEOM 0 one bulk
+//     copy of the coordinates, and prefetches the pass's geometric factors into L2;
+//   consumer warp: waits for `full`, runs the two tensor-pipe products and the Gauss-point arithmetic with ALL der
+//     fragments in registers, writes the products over the stage, sends them off with one bulk async store and hands
+//     the previous stage back (`empty`) once its store has been read.
+// Three ring stages per consumer.  Same bits as k_apply_mf3 (order 2 of the oracle).
+// ----------------------------------------------------------------------------
+template <int NOD, int NCW>
+struct Mf4Cfg {
+  static constexpr int NTOT = 3 * NOD, EPP = 8, KS1 = NOD / 4, NT3 = (NOD + 7) / 8, NF = KS1 * 3 + 6 * NT3;
+  static constexpr int kRow = Mf3Cfg<NOD>::kRow;
+  // NCW consumer warps (12: three per scheduler, 152 registers, the phase-3 fragments from a shared-memory table -- the
+  // default, measured 0.505 against 0.602 ms at config C; 8: two per scheduler, 224 registers, every der fragment in
+  // registers) + 4 producer warps.
+  // Ring stages per consumer (a stage is handed back one pass after its store was issued, so the producer runs S-2
+  // passes ahead of the arithmetic) and index buffers per consumer (bulk-copied NIDX passes ahead).
+  static constexpr int S = NCW == 8 ? (NOD == 20 ? 4 : 6) : (NOD == 20 ? 3 : 4), NIDX = NCW == 8 ? 4 : 2;
+  static constexpr int NCONS = NCW, NPROD = 4, KPW = NCW / NPROD, kThreads = 32 * (NCONS + NPROD);
+  static constexpr int kConsRegs = NCW == 8 ? 224 : 152, kProdRegs = 56;
+  static constexpr bool kAllFragsInRegs = NCW == 8;
+  static constexpr int kStageBytes = EPP * kRow * 8, kIdxBytes = EPP * NTOT * 4;
+  static constexpr int kBarsPer = 2 * S + NIDX;
+  static constexpr int kFragBytes = kAllFragsInRegs ? 0 : 6 * NT3 * 32 * 8;
+  static constexpr size_t kSmem = (size_t)NCONS * S * kStageBytes + (size_t)NCONS * NIDX * kIdxBytes + kFragBytes + (size_t)NCONS * kBarsPer * 8;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+template <int NOD, bool GATHER, int GEOM, int NCW>
+__global__ void __launch_bounds__(Mf4Cfg<NOD, NCW>::kThreads, 1)
+k_apply_mf4(const double *__restrict__ g_coord, const int *__restrict__ ggl, const double *__restrict__ pvec,
+            double *__restrict__ utemp, long long nels, const State *st, const double *__restrict__ geom, PeerTable *T) {
+  using Cfg = Mf4Cfg<NOD, NCW>;
+  constexpr int NTOT = Cfg::NTOT, ROW = Cfg::kRow, EPP = Cfg::EPP, KS1 = Cfg::KS1, NT3 = Cfg::NT3, NF = Cfg::NF, S = Cfg::S;
+  constexpr int NCONS = Cfg::NCONS, NPROD = Cfg::NPROD, NIDX = Cfg::NIDX, BP = Cfg::kBarsPer, KPW = Cfg::KPW;
+  constexpr bool ALLREG = Cfg::kAllFragsInRegs;
+  constexpr int KP = (EPP * NTOT + 31) / 32;
+  constexpr long long kGroupGeom = 32LL * 80;
+  static_assert(NOD % 4 == 0 && (EPP * NTOT) % 32 == 0, "a pass is a whole number of warp-wide words");
+  static_assert(GEOM == 0 || GEOM == 2, "the factors of mode 2 are written by k_apply_mf2<GEOM 1>");
+  static_assert((NIDX & (NIDX - 1)) == 0, "index ring: power of two");
+  if (st && *(volatile const int *)&st->done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *stage0 = smem_raw;                                                         // [NCONS][S] rows
+  unsigned char *idx0 = smem_raw + (size_t)NCONS * S * Cfg::kStageBytes;                    // [NCONS][NIDX]
+  double *s_frag = reinterpret_cast<double *>(idx0 + (size_t)NCONS * NIDX * Cfg::kIdxBytes);   // phase-3 fragments [f][lane]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(idx0 + (size_t)NCONS * NIDX * Cfg::kIdxBytes + Cfg::kFragBytes);
+  auto full_bar = [&](int c, int s) { return smem_u32(&bars[c * BP + s]); };
+  auto empty_bar = [&](int c, int s) { return smem_u32(&bars[c * BP + S + s]); };
+  auto idx_bar = [&](int c, int b) { return smem_u32(&bars[c * BP + 2 * S + b]); };
+  if (threadIdx.x < NCONS) {
+    const int c = threadIdx.x;
+    for (int s2 = 0; s2 < S; ++s2) {
+      mbar_init(full_bar(c, s2), 32);                          // the producer's 32 lanes, each when its copies have landed
+      mbar_init(empty_bar(c, s2), 1);
+    }
+    for (int b = 0; b < NIDX; ++b) mbar_init(idx_bar(c, b), 1);
+    fence_mbar_init();
+  }
+  if (!ALLREG) {
+    for (int i = threadIdx.x; i < 6 * NT3 * 32; i += blockDim.x) {
+      const int f3 = i >> 5, l = i & 31, rr = l >> 2, qq = l & 3, sb = f3 / NT3, nt = f3 - sb * NT3, h = sb / 3, b = sb - 3 * h;
+      s_frag[i] = (8 * nt + rr < NOD) ? c_tab.der[(2 * qq + h) * 60 + b * 20 + 8 * nt + rr] : 0.0;
+    }
+  }
+  __syncthreads();
+  const long long npass = (nels + EPP - 1) / EPP;
+  const long long stride = (long long)gridDim.x * NCONS;
+
+  if (w < NPROD) {
+    // ------------------------------------------------ producer ------------------------------------------------
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::kProdRegs));
+    const uint64_t policy = policy_evict_first();
+    auto issue_idx = [&](int c, int b, long long ps) {         // lane 0 only
+      const long long e0 = ps * EPP;
+      const int ne = (int)((nels - e0) < EPP ? (nels - e0) : EPP);
+      const uint32_t bytes = (uint32_t)ne * NTOT * 4;
+      mbar_expect_tx(idx_bar(c, b), bytes);
+      bulk_g2s(smem_u32(idx0 + (size_t)(c * NIDX + b) * Cfg::kIdxBytes), ggl + e0 * NTOT, bytes, idx_bar(c, b), policy);
+    };
+    if (GATHER && lane == 0) {
+      for (int it0 = 0; it0 < NIDX; ++it0)
+#pragma unroll
+        for (int k = 0; k < KPW; ++k) {
+          const int c = w + NPROD * k;
+          const long long ps = (long long)blockIdx.x * NCONS + c + it0 * stride;
+          if (ps < npass) issue_idx(c, it0, ps);
+        }
+    }
+    __syncwarp();
+    // N ranks, peer transport: the owners' values are in my halo segment of pvec; nothing of pvec is read before this
+    if (GATHER && T) warp_wait_fwd(T, st);
+    int s2 = 0, sph = 1;                                       // ring stage and the parity of its `empty` barrier to wait for
+    for (int it = 0;; ++it) {
+      bool any = false;
+#pragma unroll
+      for (int k = 0; k < KPW; ++k) {
+        const int c = w + NPROD * k;
+        const long long ps = (long long)blockIdx.x * NCONS + c + (long long)it * stride;
+        if (ps >= npass) continue;
+        any = true;
+        const int b = it & (NIDX - 1);
+        const long long e0 = ps * EPP;
+        const int ne = (int)((nels - e0) < EPP ? (nels - e0) : EPP);
+        const int nw = ne * NTOT;
+        mbar_wait(empty_bar(c, s2), sph);                      // the consumer's store out of this stage has been read
+        double *rows = reinterpret_cast<double *>(stage0 + (size_t)(c * S + s2) * Cfg::kStageBytes);
+        const int *idxbuf = reinterpret_cast<const int *>(idx0 + (size_t)(c * NIDX + b) * Cfg::kIdxBytes);
+        if (GATHER) mbar_wait(idx_bar(c, b), (it / NIDX) & 1);
+        if (ne == EPP) {
+          int idx[KP];
+          if (GATHER) {
+#pragma unroll
+            for (int kp = 0; kp < KP; ++kp) idx[kp] = idxbuf[lane + 32 * kp];
+          }
+#pragma unroll
+          for (int kp = 0; kp < KP; ++kp) {
+            const int f = lane + 32 * kp;
+            const int d = (ROW == NTOT) ? f : (f / NTOT) * ROW + (f % NTOT);
+            cp_async8(smem_u32(rows + d), GATHER ? pvec + idx[kp] : pvec + e0 * NTOT + f);
+          }
+        } else {
+          for (int f = lane; f < nw; f += 32)
+            cp_async8(smem_u32(rows + (f / NTOT) * ROW + (f % NTOT)), GATHER ? pvec + idxbuf[f] : pvec + e0 * NTOT + f);
+        }
+        cp_async_arrive_noinc(full_bar(c, s2));                // fires when this lane's copies have landed
+        __syncwarp();
+        if (GATHER && lane == 0 && ps + NIDX * stride < npass) {
+          fence_proxy_async();                                 // the warp's reads of this index buffer before the async overwrite
+          issue_idx(c, b, ps + NIDX * stride);
+        }
+        if (GEOM == 2) {
+          // this pass's 40 lines of geometric factors towards L2 (the consumer loads them one pass ahead of their use)
+          const double2 *gn = reinterpret_cast<const double2 *>(geom + (e0 >> 5) * kGroupGeom) + (int)(e0 & 31);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + lane * 32));
+          if (lane < 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + (lane + 32) * 32));
+        }
+      }
+      if (!any) break;
+      if (++s2 == S) { s2 = 0; sph ^= 1; }
+    }
+    cp_async_wait_all();
+  } else {
+    // ------------------------------------------------ consumer ------------------------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::kConsRegs));
+    const int c = w - NPROD, r = lane >> 2, q = lane & 3;
+    // der as B fragments (lane holds B[k = q][n = r]), in registers for the whole kernel:
+    //   [s*3+b]                      phase 1, k-step s, column tile b:   der_{g=r}(b, m = 4s+q)
+    //   [3 KS1 + (3h+b) NT3 + nt]    phase 3, k-step 3h+b, node tile nt: der_{g=2q+h}(b, m = 8nt+r), 0 beyond the last node
+    constexpr int NREG = ALLREG ? NF : 3 * KS1;
+    double Bf[NREG];
+#pragma unroll
+    for (int s3 = 0; s3 < KS1; ++s3)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) Bf[s3 * 3 + b] = c_tab.der[r * 60 + b * 20 + 4 * s3 + q];
+    if (ALLREG) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+          for (int nt = 0; nt < NT3; ++nt)
+            Bf[(3 * KS1 + (3 * h + b) * NT3 + nt) % NREG] = (8 * nt + r < NOD) ? c_tab.der[(2 * q + h) * 60 + b * 20 + 8 * nt + r] : 0.0;
+    }
+#pragma unroll
+    for (int f = 0; f < NREG; ++f) asm volatile("" : "+d"(Bf[f]));   // opaque: kept in registers, never re-read
+    auto frag3 = [&](int f3) -> double { return ALLREG ? Bf[(3 * KS1 + f3) % NREG] : s_frag[f3 * 32 + lane]; };
+    // loaded straight into registers as soon as the previous pass no longer needs them (after ITS Gauss-point
+    // arithmetic: no extra registers, and phase 3 + the store + the next phase 1 cover the latency): GEOM 2 the lane's
+    // two points' factors (jac^-1, det*w), GEOM 0 the lane's coordinates as the A fragments of the Jacobian product
+    // (x,y,z of nodes 4s+q of element r)
+    constexpr int NPRE = GEOM == 2 ? 20 : 3 * KS1;
+    double pre[NPRE];
+    auto load_pre = [&](long long ps) {
+      const long long e0 = ps * EPP;
+      const int ne = (int)((nels - e0) < EPP ? (nels - e0) : EPP);
+      if (r < ne) {
+        if (GEOM == 2) {
+          // word (g*5+j) of element i of a group at [(g*5+j)*32 + i] (16-byte words)
+          const double2 *gfl = reinterpret_cast<const double2 *>(geom + (e0 >> 5) * kGroupGeom) + ((int)(e0 & 31) + r);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+              const double2 v = __ldg(gfl + ((2 * q + h) * 5 + j) * 32);
+              pre[h * 10 + 2 * j] = v.x; pre[h * 10 + 2 * j + 1] = v.y;
+            }
+        } else {
+          const double *cr = g_coord + (e0 + r) * NTOT;        // g_coord_pp(nod,3,iel): [b*NOD+m]
+#pragma unroll
+          for (int s3 = 0; s3 < KS1; ++s3)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) pre[s3 * 3 + b] = __ldg(cr + b * NOD + 4 * s3 + q);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NPRE; ++j) pre[j] = 0.0;
+      }
+    };
+    long long ps = (long long)blockIdx.x * NCONS + c;
+    if (ps < npass) load_pre(ps);
+    int s2 = 0, sph = 0, it = 0;
+    for (; ps < npass; ps += stride, ++it) {
+      const long long e0 = ps * EPP;
+      const int ne = (int)((nels - e0) < EPP ? (nels - e0) : EPP);
+      double *rows = reinterpret_cast<double *>(stage0 + (size_t)(c * S + s2) * Cfg::kStageBytes);
+      double gq0[GEOM == 0 ? 20 : 1];                          // GEOM 0: jac^-1 (9) and det*w of the lane's two points
+      if (GEOM == 0) {
+        double J[3][3][2];                                     // [b: x,y,z][a][h] = jac(a,b) at point 2q+h
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+          for (int a = 0; a < 3; ++a) J[b][a][0] = J[b][a][1] = 0.0;
+#pragma unroll
+        for (int s3 = 0; s3 < KS1; ++s3)
+#pragma unroll
+          for (int b = 0; b < 3; ++b)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) dmma884(J[b][a][0], J[b][a][1], pre[s3 * 3 + b], Bf[s3 * 3 + a]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          double Jm[9];
+#pragma unroll
+          for (int b = 0; b < 3; ++b)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) Jm[b * 3 + a] = J[b][a][h];
+          const double det = det3(Jm);
+          inv3(Jm, det, gq0 + (GEOM == 0 ? 10 * h : 0));
+          gq0[GEOM == 0 ? 10 * h + 9 : 0] = det * c_tab.weights[2 * q + h];
+        }
+      }
+      const double *gq = GEOM == 0 ? gq0 : pre;                // [h*10 + j]
+      mbar_wait(full_bar(c, s2), sph);                         // the pass's right-hand sides have landed
+      // phase 1: H[c2][b][h] = H_{element r, point 2q+h}(b,c2)
+      double H[3][3][2];
+#pragma unroll
+      for (int c2 = 0; c2 < 3; ++c2)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) H[c2][b][0] = H[c2][b][1] = 0.0;
+#pragma unroll
+      for (int s3 = 0; s3 < KS1; ++s3) {
+        double a3[3];
+#pragma unroll
+        for (int c2 = 0; c2 < 3; ++c2) a3[c2] = rows[r * ROW + 3 * (4 * s3 + q) + c2];
+#pragma unroll
+        for (int c2 = 0; c2 < 3; ++c2)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) dmma884(H[c2][b][0], H[c2][b][1], a3[c2], Bf[s3 * 3 + b]);
+      }
+      double Tm[2][9];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double Hm[9];
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+          for (int c2 = 0; c2 < 3; ++c2) Hm[b * 3 + c2] = H[c2][b][h];
+        mf_point_mid_iso(Hm, gq + 10 * h, gq[10 * h + 9], Tm[h]);
+      }
+      if (ps + stride < npass) load_pre(ps + stride);          // the next pass's factors / coordinates
+      // phase 3: U[c2][nt][h'] = u_c2(m = 8nt + 2q + h') of element r
+      double U[3][NT3][2];
+#pragma unroll
+      for (int c2 = 0; c2 < 3; ++c2)
+#pragma unroll
+        for (int nt = 0; nt < NT3; ++nt) U[c2][nt][0] = U[c2][nt][1] = 0.0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+          for (int c2 = 0; c2 < 3; ++c2)
+#pragma unroll
+            for (int nt = 0; nt < NT3; ++nt) dmma884(U[c2][nt][0], U[c2][nt][1], Tm[h][b * 3 + c2], frag3((3 * h + b) * NT3 + nt));
+      // every lane's A-fragment reads of the stage precede the warp-wide mma above: the stage may take the products
+#pragma unroll
+      for (int nt = 0; nt < NT3; ++nt)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int m = 8 * nt + 2 * q + hh;
+          if (m < NOD) {
+#pragma unroll
+            for (int c2 = 0; c2 < 3; ++c2) rows[r * ROW + 3 * m + c2] = U[c2][nt][hh];
+          }
+        }
+      fence_proxy_async();                                     // my generic stores before the async proxy reads them
+      __syncwarp();
+      if (lane == 0) {
+        if (ROW == NTOT) bulk_s2g(utemp + e0 * NTOT, smem_u32(rows), (uint32_t)(ne * NTOT) * 8);
+        else
+          for (int e2 = 0; e2 < ne; ++e2) bulk_s2g(utemp + (e0 + e2) * NTOT, smem_u32(rows + e2 * ROW), NTOT * 8);
+        bulk_commit();
+        if (it > 0) {
+          bulk_wait_read_1();                                  // the PREVIOUS pass's store has read its stage
+          mbar_arrive(empty_bar(c, s2 == 0 ? S - 1 : s2 - 1));
+        }
+      }
+      if (++s2 == S) { s2 = 0; sph ^= 1; }
+    }
+    if (lane == 0) bulk_wait_all();                            // shared memory must outlive the stores
   }
 }
 
@@ -2363,6 +3019,21 @@ __global__ void k_fp64_peak(double *out, int iters, double a, double b) {
   }
   const double s = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
   if (s == 12345.678) out[0] = s;  // keep the chains alive
+}
+
+// The same for the FP64 tensor pipe (mma.sync.m8n8k4.f64 = DMMA.8x8x4, 256 fma per warp instruction): the denominator
+// of k_apply_mf3.  9 independent accumulator fragments per warp, as in the kernel's phases.
+__global__ void k_fp64_tensor_peak(double *out, int iters, double a, double b) {
+  double acc[9][2];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) acc[i][0] = acc[i][1] = threadIdx.x * 1e-9 + i;
+  for (int it = 0; it < iters; ++it)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) dmma884(acc[i][0], acc[i][1], a, b);
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) s += acc[i][0] + acc[i][1];
+  if (s == 12345.678) out[0] = s;
 }
 
 }  // namespace pf

@@ -85,6 +85,12 @@ class Solver:
         self._ck(lib().pf_measure_fp64(self._h, C.byref(t)), "pf_measure_fp64")
         return t.value
 
+    def measure_fp64_tensor(self):
+        """TFLOP/s of the FP64 tensor pipe (DMMA.8x8x4), the denominator of the tensor-core matrix-free kernel."""
+        t = C.c_double()
+        self._ck(lib().pf_measure_fp64_tensor(self._h, C.byref(t)), "pf_measure_fp64_tensor")
+        return t.value
+
     def measure_hbm_read(self):
         """GB/s of a read-only stream through the mat-vec's bulk-copy ring (no arithmetic)."""
         t = C.c_double()
