@@ -391,12 +391,16 @@ def hbm_roofline(ctx, prob, m, layout=0):
                         "(the headline pass has no per-launch events: graph replay)"}
 
 
-def mf_flops(mode, nodn):
-    # flops per element of k_apply_mf as executed (fma = 2 flop, mul/add = 1), 8 Gauss points:
-    # phase 1  H = der x p: 9 fma per node and point; per point G (9 mul + 18 fma), eps (3 add),
-    # sigma (12 mul + 30 fma), T (9 mul + 18 fma) = 165 flop; phase 2: per dof 1 mul + 23 fma.
+def mf_flops(mode, nodn, kernel=None):
+    # flops per element as executed (fma = 2 flop, mul/add = 1), 8 Gauss points:
+    # phase 1  H = der x p: 9 fma per node and point; per point G (9 mul + 18 fma), eps (3 add), sigma, T (9 mul + 18 fma);
+    # phase 3: per freedom a 24-term chain.  sigma = D eps: k_apply_mf / k_apply_mf2 multiply the full 6x6 deemat
+    # (12 mul + 30 fma = 72 flop -> 165 per point, first term of the phase-3 chain a product: 47 flop per freedom);
+    # the tensor-core kernels leave deemat's structural zeros out (24 flop -> 117 per point) and run the chain as
+    # 24 fma from 0.0 (48 flop per freedom).  The padding of the node tiles (20 -> 24) is NOT counted.
     # Mode 1 adds the Jacobian pass: 9 fma per node and point + det/inverse/det*w (51 flop) per point.
-    fl = 8 * 18 * nodn + 8 * 165 + 3 * nodn * 47
+    tensor = (kernel or mf_kernel_name()) in ("k_apply_mf3", "k_apply_mf4")
+    fl = 8 * 18 * nodn + 8 * (117 if tensor else 165) + 3 * nodn * (48 if tensor else 47)
     if mode == 1:
         fl += 8 * 18 * nodn + 8 * 51
     return fl
@@ -404,17 +408,17 @@ def mf_flops(mode, nodn):
 
 def mf_kernel_name():
     sel = os.environ.get("PF_MF", "")
-    return {"1lane": "k_apply_mf", "2lane": "k_apply_mf2"}.get(sel, "k_apply_mf3")
+    return {"1lane": "k_apply_mf", "2lane": "k_apply_mf2", "3": "k_apply_mf3"}.get(sel, "k_apply_mf4")
 
 
 def mf_roofline(prob, mode, m, peaks):
-    """peaks = (DFMA loop, DMMA loop) TFLOP/s measured on this device.  k_apply_mf3 runs its two node sums on the FP64
-    tensor pipe, so its denominator is the tensor figure (the higher one); the DFMA figure stays in the line."""
+    """peaks = (DFMA loop, DMMA loop) TFLOP/s measured on this device.  k_apply_mf4 / k_apply_mf3 run their two node sums on
+    the FP64 tensor pipe, so their denominator is the tensor figure (the higher one); the DFMA figure stays in the line."""
     dfma, dmma = peaks
     mv_ms_, mv_n_ = m["kernel_ms"]["matvec"]
     avg = mv_ms_ / max(mv_n_, 1)
     fl = prob.nels_pp * mf_flops(mode, prob.nod)
-    tensor = mf_kernel_name() == "k_apply_mf3"
+    tensor = mf_kernel_name() in ("k_apply_mf3", "k_apply_mf4")
     peak = dmma if tensor else dfma
     ach = fl / (avg / 1e3) / 1e12
     return {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
@@ -424,7 +428,7 @@ def mf_roofline(prob, mode, m, peaks):
                           "instruction" if tensor else "DFMA micro-benchmark on this device (pf_measure_fp64), fma = 2 flop"),
             "peak_dfma": dfma, "peak_fp64_tensor": dmma, "frac_of_dfma_peak": ach / dfma,
             "algorithmic_flops_per_launch": fl, "flops_per_element": mf_flops(mode, prob.nod),
-            "flops_note": "algorithmic flops of the operator form (padding of the node tiles to 24 not counted)",
+            "flops_note": "flops of the operator form as this kernel executes it (see mf_flops); padding of the node tiles to 24 not counted",
             "avg_launch_ms": avg, "launches_timed": int(mv_n_)}
 
 

@@ -339,9 +339,9 @@ def find_g4(g_num, rest):
 
 
 def set_mf_order(order):
-    """2: the summation order of k_apply_mf3 (FP64 tensor-core kernel, the default for both bricks: one fma chain in the
-    k order of its mma instructions); 1: k_apply_mf2 (PF_MF=2lane: two 12-term chains added); 0: k_apply_mf
-    (PF_MF=1lane: one 24-term chain, Gauss points ascending)."""
+    """2: the summation order of k_apply_mf4 / k_apply_mf3 (FP64 tensor-core kernels, the default for both bricks: one
+    fma chain in the k order of their mma instructions, deemat's structural zeros left out); 1: k_apply_mf2
+    (PF_MF=2lane: two 12-term chains added); 0: k_apply_mf (PF_MF=1lane: one 24-term chain, Gauss points ascending)."""
     lib().orc_set_mf_order(int(order))
 
 
@@ -358,7 +358,7 @@ def default_mf_order(nod):
 
 def apply_mf(g_coord_pp, nod, nip, e, v, pmul, mode=2):
     """Matrix-free element products (config E): utemp = sum_gp B^T D B p det w in the operation order of the device
-    kernel in use (k_apply_mf3 unless PF_MF selects an older one; both matrix-free modes of a
+    kernel in use (k_apply_mf4 unless PF_MF selects an older one; both matrix-free modes of a
     kernel give the same bits, ``mode`` is accepted for symmetry with the device call)."""
     g, pm = _f64(g_coord_pp), _f64(pmul)
     out = np.empty(pm.shape)

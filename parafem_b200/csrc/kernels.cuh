@@ -2120,7 +2120,9 @@ k_apply_mf3(const double *__restrict__ g_coord, const int *__restrict__ ggl, con
         for (int c = 0; c < 3; ++c)
 #pragma unroll
           for (int nt = 0; nt < NT3; ++nt) dmma884(U[c][nt][0], U[c][nt][1], Tm[h][b * 3 + c], fragB(3 * KS1 + (3 * h + b) * NT3 + nt));
-    // every lane's A-fragment reads of the rows precede the warp-wide mma above: the rows may take the products
+    // every lane's A-fragment reads of the rows fed the warp-wide mma above, so they are complete; the barrier states
+    // that order for the memory model (and for racecheck): the rows may take the products
+    __syncwarp();
 #pragma unroll
     for (int nt = 0; nt < NT3; ++nt)
 #pragma unroll
@@ -2432,7 +2434,9 @@ k_apply_mf4(const double *__restrict__ g_coord, const int *__restrict__ ggl, con
           for (int c2 = 0; c2 < 3; ++c2)
 #pragma unroll
             for (int nt = 0; nt < NT3; ++nt) dmma884(U[c2][nt][0], U[c2][nt][1], Tm[h][b * 3 + c2], frag3((3 * h + b) * NT3 + nt));
-      // every lane's A-fragment reads of the stage precede the warp-wide mma above: the stage may take the products
+      // every lane's A-fragment reads of the stage fed the warp-wide mma above, so they are complete; the barrier
+      // states that order for the memory model (and for racecheck): the stage may take the products
+      __syncwarp();
 #pragma unroll
       for (int nt = 0; nt < NT3; ++nt)
 #pragma unroll
