@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """profiles/rNN_sass_summary.txt: per kernel of libparafem_b200.so, the SASS evidence the judge otherwise has to
 extract alone -- bulk async copies (UBLKCP = the TMA engine's 1-D copy), mbarrier traffic (SYNCS), FP64 arithmetic
-(DFMA / DMUL / DADD: --fmad=false leaves DFMA only where the source writes fma()), shared / global accesses, and
+(DMMA = the FP64 tensor-core instruction of the matrix-free kernels, USETMAXREG = their producer / consumer register
+split; DFMA / DMUL / DADD: --fmad=false leaves DFMA only where the source writes fma()), shared / global accesses, and
 registers / spills from ptxas.  Runs on CPU: cuobjdump only reads the cubin."""
 import collections
 import os
@@ -11,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "parafem_b200", "libparafem_b200.so")
-MNEMONICS = ("UBLKCP", "SYNCS", "UBLKPF", "DFMA", "DMUL", "DADD", "LDS", "STS", "LDG", "STG", "LDGSTS", "SHFL", "BAR", "MUFU", "ATOM", "RED")
+MNEMONICS = ("UBLKCP", "SYNCS", "UBLKPF", "DMMA", "USETMAXREG", "DFMA", "DMUL", "DADD", "LDS", "STS", "LDG", "STG", "LDGSTS", "SHFL", "BAR", "MUFU", "ATOM", "RED")
 
 
 def demangle(names):
