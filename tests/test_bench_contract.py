@@ -6,6 +6,7 @@ import os
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEFAULT_LINE = "r02_bench_default_n125_tensor.json"     # the default run after the tensor-core matrix-free kernel landed
 
 
 def last_line(name):
@@ -15,7 +16,7 @@ def last_line(name):
 
 
 def test_default_line_has_every_contract_key():
-    d = last_line("r02_bench_default_n125.json")
+    d = last_line(DEFAULT_LINE)
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
         assert k in d, k
@@ -47,7 +48,7 @@ def test_default_line_has_every_contract_key():
 def test_default_line_carries_parity_configs_weak_and_reference_kernel():
     """Round 2: the driver-run line itself holds the N-rank parity self-check, the named
     configurations B and D, the weak-scaling block and the reference's own CUDA kernel timed beside this library's."""
-    d = last_line("r02_bench_default_n125.json")
+    d = last_line(DEFAULT_LINE)
     pc = d["parity_check"]
     assert pc["bit_equal"] is True and pc["nranks"] == d["n_gpus"] and len(pc["specs"]) == 2
     assert all(s["bit_equal"] and s["iters"] == s["oracle_iters"] for s in pc["specs"])
@@ -85,17 +86,25 @@ def test_reference_arm_line():
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == "port" and d["gpu_launches"] == 0
     assert d["host"]["cores"] == d["cpu_baseline"]["cores"] >= 1 and d["same_workload_as_gpu_arm"] is False
     # both arms describe the linear system with the same function: same keys as the GPU arm's config
-    assert set(d["config"]) == set(last_line("r02_bench_default_n125.json")["config"])
+    assert set(d["config"]) == set(last_line(DEFAULT_LINE)["config"])
 
 
 def test_variant_lines_carry_their_own_roofline():
-    d = last_line("r02_bench_default_n125.json")
+    d = last_line(DEFAULT_LINE)
     v = d["variants"]
     assert set(v) == {"stored_symmetric_packed", "matrix_free_geometric_factors", "matrix_free_rebuilt_from_coordinates"}
     assert v["stored_symmetric_packed"]["roofline"]["bound"] == "hbm"
     for name in ("matrix_free_geometric_factors", "matrix_free_rebuilt_from_coordinates"):
         r = v[name]["roofline"]
         assert r["bound"] == "fp64" and r["unit"] == "TFLOP/s" and 0 < r["frac"] < 1
+        # the tensor-core kernel is judged against the (higher) measured tensor peak; the DFMA figure stays in the line
+        assert r["kernel"].startswith("k_apply_mf4") and r["peak"] == r["peak_fp64_tensor"] > r["peak_dfma"] > 25
+        assert r["frac"] == pytest.approx(r["achieved"] / r["peak"], rel=1e-12)
+        assert r["frac_of_dfma_peak"] == pytest.approx(r["achieved"] / r["peak_dfma"], rel=1e-12)
+        assert r["achieved"] == pytest.approx(r["algorithmic_flops_per_launch"] / (r["avg_launch_ms"] * 1e-3) / 1e12, rel=1e-9)
+    assert v["matrix_free_geometric_factors"]["roofline"]["flops_per_element"] == 6696      # as executed, padding not counted
+    assert v["matrix_free_geometric_factors"]["roofline"]["frac"] >= 0.65
+    assert v["matrix_free_geometric_factors"]["value"] >= 19000
 
 
 def test_reference_arm_runs_on_cpu_and_under_torchrun():
