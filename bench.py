@@ -411,7 +411,24 @@ def mf_kernel_name():
     return {"1lane": "k_apply_mf", "2lane": "k_apply_mf2", "3": "k_apply_mf3"}.get(sel, "k_apply_mf4")
 
 
-def mf_roofline(prob, mode, m, peaks):
+def mf_hbm_side(ctx, prob, mode, avg_ms):
+    """The matrix-free kernel's OTHER roofline.  It streams, per element, the geometric factors (mode 2: 8 x (jac^-1, det*w)
+    = 640 B) or the coordinates (mode 1: 24 x nod B), the gather indices (4 x ntot B), writes utemp (8 x ntot B) and reads
+    every right-hand side at least once (8 B per equation): with the tensor-core kernel that is no longer negligible."""
+    per_el = (640 if mode == 2 else 24 * prob.nod) + 12 * prob.ntot
+    alg = prob.nels_pp * per_el + prob.neq_pp * 8
+    traffic, src = None, None
+    cands = [c for c in ctx.traffic.get("captures", []) if c.get("elem") == f"p{prob.program}_hex{prob.nod}" and c.get("layout") == f"mf{mode}"]
+    if cands:
+        ent = min(cands, key=lambda c: abs(c["nels_pp"] - prob.nels_pp))
+        traffic = ent["dram_bytes_per_launch"] / ent["nels_pp"] * prob.nels_pp
+        src = ent.get("source", "") + ("" if ent["nels_pp"] == prob.nels_pp else f", scaled per element to this rank's {prob.nels_pp}")
+    ach = alg / (avg_ms / 1e3) / 1e9
+    return {"bound": "hbm", "algorithmic_bytes_per_launch": alg, "bytes_per_element": per_el, "achieved": ach, "unit": "GB/s",
+            "peak": ctx.pk["hbm_gbs"], "frac": ach / ctx.pk["hbm_gbs"], "traffic": traffic, "traffic_source": src}
+
+
+def mf_roofline(ctx, prob, mode, m, peaks):
     """peaks = (DFMA loop, DMMA loop) TFLOP/s measured on this device.  k_apply_mf4 / k_apply_mf3 run their two node sums on
     the FP64 tensor pipe, so their denominator is the tensor figure (the higher one); the DFMA figure stays in the line."""
     dfma, dmma = peaks
@@ -429,7 +446,8 @@ def mf_roofline(prob, mode, m, peaks):
             "peak_dfma": dfma, "peak_fp64_tensor": dmma, "frac_of_dfma_peak": ach / dfma,
             "algorithmic_flops_per_launch": fl, "flops_per_element": mf_flops(mode, prob.nod),
             "flops_note": "flops of the operator form as this kernel executes it (see mf_flops); padding of the node tiles to 24 not counted",
-            "avg_launch_ms": avg, "launches_timed": int(mv_n_)}
+            "avg_launch_ms": avg, "launches_timed": int(mv_n_),
+            "hbm_side": mf_hbm_side(ctx, prob, mode, avg)}
 
 
 def block(ctx, prob, m, roofline, tts=None):
@@ -637,7 +655,7 @@ def main():
     m = measure(ctx, prob)
     tts = None if args.no_solve else solve_to_convergence(ctx, prob)
     if args.matrix_free:
-        roof = mf_roofline(prob, args.matrix_free, m, fp64_tflops)
+        roof = mf_roofline(ctx, prob, args.matrix_free, m, fp64_tflops)
     else:
         roof = hbm_roofline(ctx, prob, m, args.layout)
         roof["read_only_stream_gbs"] = hbm_read_gbs
@@ -660,7 +678,7 @@ def main():
             solver.setup_problem(s, prob, matrix_free=mode)
             peak = peak or (s.measure_fp64(), s.measure_fp64_tensor())
             mm = measure(ctx, prob)
-            variants[name] = block(ctx, prob, mm, mf_roofline(prob, mode, mm, peak),
+            variants[name] = block(ctx, prob, mm, mf_roofline(ctx, prob, mode, mm, peak),
                                    solve_to_convergence(ctx, prob) if (mode == 2 and not args.no_solve) else None)
 
     # ---- the other named configurations, and weak scaling ---------------------------------------------

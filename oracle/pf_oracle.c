@@ -898,7 +898,8 @@ void orc_matvec(int ntot, int64_t nels, const double *storkm, const double *pmul
 /*
  * Operator form of elements_3 without storkm.  With deriv = jac^-1 * der the element product
  * factors through two 3x3 matrices per Gauss point (ascending):
- *   jac, det, jac^-1 as in gauss_point() but with fused multiply-adds (fma chains from 0.0)
+ *   jac, det, jac^-1 as in gauss_point() but with fused multiply-adds (fma chains from 0.0); order 2: the inverse is the
+ *   adjugate times ONE reciprocal of det instead of nine divisions
  *   H(b,c) = sum_m der(b,m) p_c(m)          node-ascending fma chains from 0.0
  *   G(a,c) = sum_b inv(a,b) H(b,c)          product, then two fmas, b ascending
  *   eps    = (G00, G11, G22, G10+G01, G21+G12, G20+G02)      beemat's row order
@@ -920,6 +921,23 @@ void orc_matvec(int ntot, int64_t nels, const double *storkm, const double *pmul
  *    (PF_MF=1lane) */
 static int g_mf_order = 2;
 void orc_set_mf_order(int order) { g_mf_order = (order >= 0 && order <= 2) ? order : 2; }
+/* orc_invert3 with the nine divisions by det replaced by products with 1/det (the tensor-core kernels' inv3_recip) */
+static void invert3_recip(double *m) {
+  const double rd = 1.0 / orc_determinant3(m);
+  double j11 = M3(m, 2, 2) * M3(m, 3, 3) - M3(m, 3, 2) * M3(m, 2, 3);
+  double j21 = -(M3(m, 2, 1) * M3(m, 3, 3)) + M3(m, 3, 1) * M3(m, 2, 3);
+  double j31 = M3(m, 2, 1) * M3(m, 3, 2) - M3(m, 3, 1) * M3(m, 2, 2);
+  double j12 = -(M3(m, 1, 2) * M3(m, 3, 3)) + M3(m, 3, 2) * M3(m, 1, 3);
+  double j22 = M3(m, 1, 1) * M3(m, 3, 3) - M3(m, 3, 1) * M3(m, 1, 3);
+  double j32 = -(M3(m, 1, 1) * M3(m, 3, 2)) + M3(m, 3, 1) * M3(m, 1, 2);
+  double j13 = M3(m, 1, 2) * M3(m, 2, 3) - M3(m, 2, 2) * M3(m, 1, 3);
+  double j23 = -(M3(m, 1, 1) * M3(m, 2, 3)) + M3(m, 2, 1) * M3(m, 1, 3);
+  double j33 = M3(m, 1, 1) * M3(m, 2, 2) - M3(m, 2, 1) * M3(m, 1, 2);
+  M3(m, 1, 1) = j11 * rd; M3(m, 1, 2) = j12 * rd; M3(m, 1, 3) = j13 * rd;
+  M3(m, 2, 1) = j21 * rd; M3(m, 2, 2) = j22 * rd; M3(m, 2, 3) = j23 * rd;
+  M3(m, 3, 1) = j31 * rd; M3(m, 3, 2) = j32 * rd; M3(m, 3, 3) = j33 * rd;
+}
+
 static void mf_element(int nod, double der[8][60] /*[ig][a*20+m]*/, const double *coord, const double *dee,
                        const double *weights, const double *pm, double *ut) {
   double T[8][9];
@@ -933,7 +951,8 @@ static void mf_element(int nod, double der[8][60] /*[ig][a*20+m]*/, const double
       }
     const double det = orc_determinant3(jac);
     memcpy(inv, jac, sizeof inv);
-    orc_invert3(inv);
+    if (g_mf_order == 2) invert3_recip(inv);   /* k_apply_mf3 / k_apply_mf4: adjugate times ONE reciprocal (inv3_recip) */
+    else orc_invert3(inv);
     const double f = det * weights[ig];
     for (int b = 0; b < 3; ++b)
       for (int c = 0; c < 3; ++c) {

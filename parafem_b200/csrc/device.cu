@@ -1321,7 +1321,9 @@ int pf_form_km_elastic(pf_handle h, double e, double v) {
     if (h->mf_mode == 2) {
       // geometric factors: inverse Jacobian (9) + det*w (1) per element and Gauss point
       CU(h->geom.alloc((size_t)((h->nels + 31) / 32) * 32 * 80));   // [group][point][word][lane], padded to whole groups
-      if (h->nod == 20 && mf_two_lanes()) rc = launch_mf2_t<20, false, 1>(h, nullptr, nullptr);
+      // each kernel family writes the factors it reads: the tensor-core kernels invert with one reciprocal per point
+      if (mf_kernel_choice() >= 3) rc = h->nod == 20 ? launch_mf3_t<20, false, 1>(h, nullptr, nullptr) : launch_mf3_t<8, false, 1>(h, nullptr, nullptr);
+      else if (h->nod == 20 && mf_two_lanes()) rc = launch_mf2_t<20, false, 1>(h, nullptr, nullptr);
       else if (h->nod == 20) rc = launch_mf_t<20, false, 1>(h, nullptr, nullptr);
       else rc = launch_mf_t<8, false, 1>(h, nullptr, nullptr);
       if (rc) return rc;

@@ -955,6 +955,20 @@ __device__ __forceinline__ void inv3(const double *m, double det, double *o) {
   o[6] = (A(1, 2) * A(2, 3) - A(2, 2) * A(1, 3)) / det;      // (1,3)
   o[7] = (-(A(1, 1) * A(2, 3)) + A(2, 1) * A(1, 3)) / det;   // (2,3)
   o[8] = (A(1, 1) * A(2, 2) - A(2, 1) * A(1, 2)) / det;      // (3,3)
+}
+// the tensor-core matrix-free kernels (order 2 of the oracle): ONE IEEE division per Gauss point instead of nine -- the
+// adjugate entries with the operation order above, times 1/det
+__device__ __forceinline__ void inv3_recip(const double *m, double det, double *o) {
+  const double rd = 1.0 / det;
+  o[0] = (A(2, 2) * A(3, 3) - A(3, 2) * A(2, 3)) * rd;
+  o[1] = (-(A(2, 1) * A(3, 3)) + A(3, 1) * A(2, 3)) * rd;
+  o[2] = (A(2, 1) * A(3, 2) - A(3, 1) * A(2, 2)) * rd;
+  o[3] = (-(A(1, 2) * A(3, 3)) + A(3, 2) * A(1, 3)) * rd;
+  o[4] = (A(1, 1) * A(3, 3) - A(3, 1) * A(1, 3)) * rd;
+  o[5] = (-(A(1, 1) * A(3, 2)) + A(3, 1) * A(1, 2)) * rd;
+  o[6] = (A(1, 2) * A(2, 3) - A(2, 2) * A(1, 3)) * rd;
+  o[7] = (-(A(1, 1) * A(2, 3)) + A(2, 1) * A(1, 3)) * rd;
+  o[8] = (A(1, 1) * A(2, 2) - A(2, 1) * A(1, 2)) * rd;
 #undef A
 }
 
@@ -1860,8 +1874,11 @@ k_apply_mf2(const double *__restrict__ g_coord, const int *__restrict__ ggl, con
 // gathered right-hand sides (coalesced gather -> rows -> A fragments) and the products (fragments -> rows -> coalesced
 // store).  Chain orders (orc_apply_mf, order 2): H and jac node-ascending from 0.0 as before; u_c(m) ONE 24-term fma
 // chain from 0.0 over (h = 0,1 | b = 0,1,2 | q = 0..3), point g = 2q+h.
-// GEOM 0: jac comes from the same phase-1 product on the coordinates, det / inverse stay in registers (no scratch);
-// GEOM 2: reads the factors k_apply_mf2<GEOM 1> stored ([group of 32][point][word][lane]).  Same bits in both modes.
+// GEOM 0: jac comes from the same phase-1 product on the coordinates, det / inverse (adjugate times ONE reciprocal per
+//         point, inv3_recip) stay in registers (no scratch);
+// GEOM 1: only writes those factors ([group of 32][point][word][lane]: the layout of k_apply_mf / k_apply_mf2) -- the
+//         setup of mode 2 for this kernel family;
+// GEOM 2: reads them.  Same bits in modes 0 and 2.
 // ----------------------------------------------------------------------------
 template <int NOD>
 struct Mf3Cfg {
@@ -1873,8 +1890,8 @@ struct Mf3Cfg {
   static constexpr int kRow = (NTOT % 16 == 4 || NTOT % 16 == 12) ? NTOT : NTOT + ((12 - NTOT % 16) + 16) % 16;
   static constexpr int kIdxBytes = EPP * NTOT * 4;
   static constexpr int kFragBytes = NF * 32 * 8;
-  // per warp: two row buffers (pass n is computed while pass n+1 lands), with GEOM 0 one coordinate buffer, the indices
-  __host__ __device__ static constexpr size_t per_warp(int geom) { return (size_t)(geom == 0 ? 3 : 2) * EPP * kRow * 8 + kIdxBytes; }
+  // per warp: two row buffers (pass n is computed while pass n+1 lands), with GEOM 0 / 1 one coordinate buffer, the indices
+  __host__ __device__ static constexpr size_t per_warp(int geom) { return (size_t)(geom != 2 ? 3 : 2) * EPP * kRow * 8 + kIdxBytes; }
   static constexpr size_t smem(int warps, int geom) { return (size_t)kFragBytes + (size_t)warps * (per_warp(geom) + 16); }
 };
 
@@ -1900,21 +1917,21 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 template <int NOD, bool GATHER, int GEOM, int WARPS, int BREG>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 k_apply_mf3(const double *__restrict__ g_coord, const int *__restrict__ ggl, const double *__restrict__ pvec,
-            double *__restrict__ utemp, long long nels, const State *st, const double *__restrict__ geom, PeerTable *T) {
+            double *__restrict__ utemp, long long nels, const State *st, double *geom, PeerTable *T) {
   using Cfg = Mf3Cfg<NOD>;
   constexpr int NTOT = Cfg::NTOT, ROW = Cfg::kRow, EPP = Cfg::EPP, KS1 = Cfg::KS1, NT3 = Cfg::NT3, NF = Cfg::NF;
   constexpr int KP = (EPP * NTOT + 31) / 32;                 // flat (element, freedom) words of a pass per lane
   constexpr long long kGroupGeom = 32LL * 80;                // doubles per group of 32 elements (MfCfg::kGroupGeom)
   static_assert(NOD % 4 == 0, "phase 1 takes the nodes four at a time");
-  static_assert(GEOM == 0 || GEOM == 2, "the factors of mode 2 are written by k_apply_mf2<GEOM 1>");
+  static_assert(GEOM >= 0 && GEOM <= 2, "0: rebuild the factors every call, 1: only write them (setup of mode 2), 2: read them");
   if (st && *(volatile const int *)&st->done) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, q = lane & 3;
   double *s_frag = reinterpret_cast<double *>(smem_raw);
   unsigned char *mine = smem_raw + Cfg::kFragBytes + (size_t)w * Cfg::per_warp(GEOM);
   double *rows2 = reinterpret_cast<double *>(mine);                                        // [2][EPP*ROW]
-  double *cbuf = rows2 + 2 * EPP * ROW;                                                    // GEOM 0 only
-  int *idxbuf = reinterpret_cast<int *>(mine + (size_t)(GEOM == 0 ? 3 : 2) * EPP * ROW * 8);
+  double *cbuf = rows2 + 2 * EPP * ROW;                                                    // GEOM 0 / 1 only
+  int *idxbuf = reinterpret_cast<int *>(mine + (size_t)(GEOM != 2 ? 3 : 2) * EPP * ROW * 8);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + Cfg::kFragBytes + (size_t)WARPS * Cfg::per_warp(GEOM));
   const uint32_t bar = smem_u32(&bars[w]);
   // der as B fragments (lane holds B[k = q][n = r]):
@@ -1958,16 +1975,18 @@ k_apply_mf3(const double *__restrict__ g_coord, const int *__restrict__ ggl, con
     const long long e0 = ps * EPP;
     const int ne = (int)((nels - e0) < EPP ? (nels - e0) : EPP);
     const int nw = ne * NTOT;
+    if (GEOM != 1) {
 #pragma unroll
-    for (int kp = 0; kp < KP; ++kp) {
-      const int f = lane + 32 * kp;
-      if (f < EPP * NTOT) {
-        double *d = dst + (f / NTOT) * ROW + (f % NTOT);
-        if (f < nw) cp_async8(smem_u32(d), GATHER ? pvec + idxbuf[f] : pvec + e0 * NTOT + f);
-        else *d = 0.0;
+      for (int kp = 0; kp < KP; ++kp) {
+        const int f = lane + 32 * kp;
+        if (f < EPP * NTOT) {
+          double *d = dst + (f / NTOT) * ROW + (f % NTOT);
+          if (f < nw) cp_async8(smem_u32(d), GATHER ? pvec + idxbuf[f] : pvec + e0 * NTOT + f);
+          else *d = 0.0;
+        }
       }
     }
-    if (GEOM == 0) {
+    if (GEOM != 2) {
 #pragma unroll
       for (int kp = 0; kp < KP; ++kp) {
         const int f = lane + 32 * kp;
@@ -2036,7 +2055,7 @@ k_apply_mf3(const double *__restrict__ g_coord, const int *__restrict__ ggl, con
     }
     cp_async_wait_all();
     __syncwarp();                                            // this pass's rows (and coordinates) have landed
-    if (GEOM == 0) {
+    if (GEOM != 2) {
       double J[3][3][2];                                     // [b: x,y,z][a][h] = jac(a,b) at point 2q+h
 #pragma unroll
       for (int b = 0; b < 3; ++b)
@@ -2060,10 +2079,22 @@ k_apply_mf3(const double *__restrict__ g_coord, const int *__restrict__ ggl, con
 #pragma unroll
           for (int a = 0; a < 3; ++a) Jm[b * 3 + a] = J[b][a][h];
         const double det = det3(Jm);
-        inv3(Jm, det, gq[h]);
+        inv3_recip(Jm, det, gq[h]);
         gq[h][9] = det * c_tab.weights[2 * q + h];
       }
       __syncwarp();                                          // the coordinate buffer is free for the next pass
+    }
+    if (GEOM == 1) {
+      // setup of mode 2: word (g*5+j) of element i of a group of 32 at [(g*5+j)*32 + i] (16-byte words)
+      double2 *gfl = reinterpret_cast<double2 *>(geom + (e0 >> 5) * kGroupGeom) + ((int)(e0 & 31) + r);
+      if (r < ne) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int j = 0; j < 5; ++j) gfl[((2 * q + h) * 5 + j) * 32] = make_double2(gq[h][2 * j], gq[h][2 * j + 1]);
+      }
+      if (ps + pstride < npass) issue_data(ps + pstride, rows2);
+      continue;
     }
     // the next pass's data starts to move now and lands during this pass's arithmetic
     if (ps + pstride < npass) {
@@ -2198,7 +2229,7 @@ k_apply_mf4(const double *__restrict__ g_coord, const int *__restrict__ ggl, con
   constexpr int KP = (EPP * NTOT + 31) / 32;
   constexpr long long kGroupGeom = 32LL * 80;
   static_assert(NOD % 4 == 0 && (EPP * NTOT) % 32 == 0, "a pass is a whole number of warp-wide words");
-  static_assert(GEOM == 0 || GEOM == 2, "the factors of mode 2 are written by k_apply_mf2<GEOM 1>");
+  static_assert(GEOM == 0 || GEOM == 2, "the factors of mode 2 are written by k_apply_mf3<GEOM 1>");
   static_assert((NIDX & (NIDX - 1)) == 0, "index ring: power of two");
   if (st && *(volatile const int *)&st->done) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -2387,7 +2418,7 @@ k_apply_mf4(const double *__restrict__ g_coord, const int *__restrict__ ggl, con
 #pragma unroll
             for (int a = 0; a < 3; ++a) Jm[b * 3 + a] = J[b][a][h];
           const double det = det3(Jm);
-          inv3(Jm, det, gq0 + (GEOM == 0 ? 10 * h : 0));
+          inv3_recip(Jm, det, gq0 + (GEOM == 0 ? 10 * h : 0));
           gq0[GEOM == 0 ? 10 * h + 9 : 0] = det * c_tab.weights[2 * q + h];
         }
       }
