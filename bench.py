@@ -325,6 +325,10 @@ def measure(ctx, prob):
     ms_prof = ctx.maxf(ms_prof)
     km = {name: s.kernel_ms(i) for i, name in enumerate(KERNEL_KINDS)}
     s.set_profile(False)
+    # the mat-vec kernel alone, max(K, 20) launches back to back between ONE pair of events: what a launch costs without
+    # the two event records around it (they add ~10 us -- nothing at config C, 10 % at config B's 0.1 ms launches)
+    ctx.barrier()
+    mv_b2b = ctx.maxf(s.measure_matvec(max(K, 20)))
 
     def e2e_once(k):
         ctx.barrier()
@@ -337,7 +341,7 @@ def measure(ctx, prob):
     e2e_once(W)
     e2e_s, _ = e2e_once(K)
     return {"ms": ms, "ms_profiled": ms_prof, "value": prob.neq * K / (ms / 1e3) / 1e6,
-            "launches": launches, "clocks": clocks, "kernel_ms": km, "e2e_s": e2e_s,
+            "launches": launches, "clocks": clocks, "kernel_ms": km, "matvec_back_to_back_ms": mv_b2b, "e2e_s": e2e_s,
             "e2e_value": prob.neq * K / e2e_s / 1e6}
 
 
@@ -360,6 +364,17 @@ def solve_to_convergence(ctx, prob):
             "mdof_iters_per_s": prob.neq * it_c.value / (ms_full / 1e3) / 1e6,
             "e2e_mdof_iters_per_s": prob.neq * it_c.value / wall / 1e6,
             "x1": x1 if ctx.rank == 0 else None, "tol": prob.tol}
+
+
+def _b2b(work, m, peak, scale):
+    """The same kernel, same work, timed as max(K, 20) launches back to back between one pair of events."""
+    ms = m.get("matvec_back_to_back_ms")
+    if not ms:
+        return None
+    ach = work / (ms / 1e3) / scale
+    return {"avg_launch_ms": ms, "achieved": ach, "frac": ach / peak,
+            "note": "pf_measure_matvec: the kernel alone, launches back to back between ONE pair of events (right-hand sides "
+                    "resident, no per-launch event records)"}
 
 
 def hbm_roofline(ctx, prob, m, layout=0):
@@ -388,7 +403,8 @@ def hbm_roofline(ctx, prob, m, layout=0):
             "peak_kind": ctx.pk_kind, "algorithmic_bytes_per_launch": bytes_pp, "avg_launch_ms": avg,
             "launches_timed": int(mv_n),
             "timed_in": "a second pass of the same K steps with CUDA events on the solver stream around every launch "
-                        "(the headline pass has no per-launch events: graph replay)"}
+                        "(the headline pass has no per-launch events: graph replay)",
+            "back_to_back": _b2b(bytes_pp, m, ctx.pk["hbm_gbs"], 1e9)}
 
 
 def mf_flops(mode, nodn, kernel=None):
@@ -447,6 +463,7 @@ def mf_roofline(ctx, prob, mode, m, peaks):
             "algorithmic_flops_per_launch": fl, "flops_per_element": mf_flops(mode, prob.nod),
             "flops_note": "flops of the operator form as this kernel executes it (see mf_flops); padding of the node tiles to 24 not counted",
             "avg_launch_ms": avg, "launches_timed": int(mv_n_),
+            "back_to_back": _b2b(fl, m, peak, 1e12),
             "hbm_side": mf_hbm_side(ctx, prob, mode, avg)}
 
 

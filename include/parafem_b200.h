@@ -95,6 +95,9 @@ int pf_setup_mesh(pf_handle h, int nod, int nodof, int nip, int64_t nels_pp,
  * Gauss point (10 doubles, 640 B per element) are stored at setup and read
  * back instead of being rebuilt -- same bits as mode 1, no FP64 divisions
  * in the loop ("partial assembly").
+ * Both modes run on the FP64 tensor cores (k_apply_mf4: the two node sums as
+ * mma.sync.m8n8k4.f64 with der as constant register fragments; a DMMA is a
+ * k-ascending fma chain bit for bit, which is how the oracle states it).
  * pf_set_storkm_layout(h, 1) (call before forming / uploading the matrices):
  * keep only the lower triangle of every element matrix, packed by columns
  * (ntot(ntot+1)/2 doubles: 14 640 B instead of 28 800 B per 20-node brick),
@@ -263,8 +266,11 @@ int64_t pf_kernel_launches(pf_handle h); /* all kernel launches since pf_init */
  * matrix-free variant ("FP64 peak is not in MEASURED_PEAKS.json").  */
 int pf_measure_fp64(pf_handle h, double *tflops);
 /* The same for the FP64 tensor pipe (mma.sync.m8n8k4.f64, 512 flop per warp instruction): the roofline
- * denominator of the tensor-core matrix-free kernel (k_apply_mf3).                              */
+ * denominator of the tensor-core matrix-free kernels (k_apply_mf4 / k_apply_mf3).              */
 int pf_measure_fp64_tensor(pf_handle h, double *tflops);
+/* The mat-vec kernel of the current problem, `reps` launches back to back between one pair of events
+ * (ms per launch): the kernel time without per-launch event records, for launches of ~0.1 ms.   */
+int pf_measure_matvec(pf_handle h, int reps, double *ms_per_launch);
 /* Read-only HBM stream through the same bulk-copy ring as the mat-vec, no arithmetic (GB/s):
  * MEASURED_PEAKS.json's hbm_gbs is a copy (read + write); this is the read-stream ceiling.     */
 int pf_measure_hbm_read(pf_handle h, double *gbs);

@@ -90,6 +90,7 @@ SIGNATURES = {
     "pf_kernel_launches": (c_i64, [vp]),
     "pf_measure_fp64": (c_int, [vp, P(c_dbl)]),
     "pf_measure_fp64_tensor": (c_int, [vp, P(c_dbl)]),
+    "pf_measure_matvec": (c_int, [vp, c_int, P(c_dbl)]),
     "pf_measure_hbm_read": (c_int, [vp, P(c_dbl)]),
     "pf_device_info": (c_int, [vp, P(c_int), P(c_i64), P(c_i64)]),
     # B. host helpers

@@ -404,6 +404,20 @@ int launch_matvec_t(pf_handle h, const double *pvec, const State *st, PeerTable 
   return 0;
 }
 
+template <int NTOT, int EPT, int WARPS, int NBUF, bool GATHER>
+int launch_matvec2_t(pf_handle h, const double *pvec, const State *st, PeerTable *T) {
+  using Cfg = Matvec2Cfg<NTOT, EPT, WARPS, NBUF>;
+  auto kern = k_matvec2<NTOT, EPT, WARPS, NBUF, GATHER>;
+  if (int rc_ = ensure_smem(h, kern, Cfg::kSmem)) return rc_;
+  const int64_t ntiles = (h->nels + EPT - 1) / EPT;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, ntiles));
+  kern<<<grid, Cfg::kThreads, Cfg::kSmem, h->stream>>>(h->mat_override ? h->mat_override : h->km.p, h->ggl.p, pvec, h->utemp.p,
+                                                       (long long)h->nels, st, T);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
 constexpr int kMfWarps = 8;   // 256 threads = 256 elements in flight per SM; ~190 registers per thread
 
 int mf_grid(pf_handle h) {
@@ -604,8 +618,15 @@ int launch_matvec(pf_handle h, const double *pvec, const State *st, PeerTable *T
       if (tune == 2) return launch_matvec_t<24, 2, 16, GATHER>(h, pvec, st, T);
       return launch_matvec_t<24, 1, 32, GATHER>(h, pvec, st, T);
     case 8:
-      if (tune == 1) return launch_matvec_t<8, 64, 6, GATHER>(h, pvec, st, T);
-      return launch_matvec_t<8, 16, 16, GATHER>(h, pvec, st, T);
+      // 8x8 matrices (p123 / p124 / p125).  Side traffic (indices 32 B, gathered right-hand sides, utemp 64 B per 512 B
+      // matrix) is a fifth of the stream, so ~0.83 of the HBM peak on the matrix bytes is the ceiling.  Measured at config
+      // B / at 200^3 (scripts/gpu_r2_15.sh, back to back): one slot per warp 16 elements x 16 warps 0.755 / 0.814;
+      // k_matvec2 two slots per warp: 12 x 16 0.775 / 0.834, 8 x 24 0.784 / 0.845 (default), 16 x 12 0.783; three slots:
+      // 8 x 16 0.718, 4 x 32 0.715
+      if (tune == 1) return launch_matvec_t<8, 16, 16, GATHER>(h, pvec, st, T);
+      if (tune == 2) return launch_matvec2_t<8, 12, 16, 2, GATHER>(h, pvec, st, T);
+      if (tune == 5) return launch_matvec2_t<8, 16, 12, 2, GATHER>(h, pvec, st, T);
+      return launch_matvec2_t<8, 8, 24, 2, GATHER>(h, pvec, st, T);
     case 12: return launch_matvec_t<12, 8, 16, GATHER>(h, pvec, st, T);    // 4-node tetrahedra, elastic: 9 KB tiles
     case 4: return launch_matvec_t<4, 64, 16, GATHER>(h, pvec, st, T);     // 4-node tetrahedra, scalar: 8 KB tiles
   }
@@ -1039,6 +1060,29 @@ int pf_measure_fp64(pf_handle h, double *tflops) {
   cudaEventDestroy(e0); cudaEventDestroy(e1); out.release();
   *tflops = best;
   return 0;
+}
+
+// The mat-vec kernel of the current problem launched `reps` times back to back between ONE pair of events: the kernel
+// time without the ~10 us a pair of per-launch event records adds to a 0.1 ms launch (config B).  The right-hand sides
+// are whatever p_ext holds (local values; no halo wait, no stopping flag): timing only, utemp is overwritten.
+int pf_measure_matvec(pf_handle h, int reps, double *ms_per_launch) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_km && h->have_mesh && reps > 0, "needs pf_setup_mesh, element matrices and reps > 0");
+  if (h->matrix_free && (rc = ensure_tables(h))) return rc;
+  const bool prof = h->profile;
+  h->profile = false;
+  EventPair ev; CU(ev.create());
+  for (int warm = 0; warm < 2 && !rc; ++warm) rc = launch_matvec<true>(h, h->p_ext.p, nullptr);
+  if (!rc) {
+    CU(cudaEventRecord(ev.a, h->stream));
+    for (int i = 0; i < reps && !rc; ++i) rc = launch_matvec<true>(h, h->p_ext.p, nullptr);
+    CU(cudaEventRecord(ev.b, h->stream));
+    CU(cudaEventSynchronize(ev.b));
+    float ms = 0.f; CU(cudaEventElapsedTime(&ms, ev.a, ev.b));
+    *ms_per_launch = (double)ms / reps;
+  }
+  h->profile = prof;
+  return rc;
 }
 
 int pf_measure_fp64_tensor(pf_handle h, double *tflops) {

@@ -171,6 +171,113 @@ k_matvec(const double *__restrict__ km, const int *__restrict__ ggl, const doubl
   }
 }
 
+// k_matvec2: the same product with NBUF ring slots PER WARP (round 2).  k_matvec re-arms a warp's only slot after the
+// tile has been multiplied, so the slot carries no bytes while the warp computes; with 8x8 matrices (p123 / p124 / p125:
+// 8 KB tiles) the copy latency is most of a warp's cycle and the 16 slots of an SM hold ~94 KB in flight on average --
+// measured 0.104 ms = 0.755 of the HBM peak at config B.  Here the copy of tile t+NBUF*WARPS is issued into the slot tile
+// t has just left, NBUF-1 copies per warp are always in flight while it gathers and multiplies.  Same arithmetic, same bits.
+template <int NTOT, int EPT, int WARPS, int NBUF>
+struct Matvec2Cfg {
+  static constexpr int kTileDoubles = EPT * NTOT * NTOT, kTileBytes = kTileDoubles * 8, kPmDoubles = EPT * NTOT;
+  static constexpr int kThreads = WARPS * 32;
+  static constexpr size_t kSmem = (size_t)WARPS * NBUF * kTileBytes + (size_t)WARPS * kPmDoubles * 8 + (size_t)WARPS * NBUF * 8;
+};
+
+template <int NTOT, int EPT, int WARPS, int NBUF, bool GATHER>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_matvec2(const double *__restrict__ km, const int *__restrict__ ggl, const double *__restrict__ pvec,
+          double *__restrict__ utemp, long long nels, const State *st, PeerTable *T) {
+  using Cfg = Matvec2Cfg<NTOT, EPT, WARPS, NBUF>;
+  constexpr int KP = (EPT * NTOT + 31) / 32, RP = NTOT / 2;
+  if (st && *(volatile const int *)&st->done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *tiles = reinterpret_cast<double *>(smem_raw);
+  double *pm_all = tiles + (size_t)WARPS * NBUF * Cfg::kTileDoubles;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(pm_all + WARPS * Cfg::kPmDoubles);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ntiles = (nels + EPT - 1) / EPT;
+  const long long t0 = ntiles * blockIdx.x / gridDim.x, t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
+  double *mytiles = tiles + (size_t)w * NBUF * Cfg::kTileDoubles;
+  double *pm = pm_all + w * Cfg::kPmDoubles;
+  uint64_t policy = 0;
+  if (lane == 0) {
+    for (int b = 0; b < NBUF; ++b) mbar_init(smem_u32(&bars[w * NBUF + b]), 1);
+    fence_mbar_init();
+    policy = policy_evict_first();
+  }
+  __syncwarp();
+  auto issue = [&](int b, long long t) {                       // lane 0 only
+    const long long e0 = t * EPT;
+    const int ne = (int)((nels - e0) < EPT ? (nels - e0) : EPT);
+    const uint32_t bytes = (uint32_t)ne * NTOT * NTOT * 8, bar = smem_u32(&bars[w * NBUF + b]);
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(smem_u32(mytiles + (size_t)b * Cfg::kTileDoubles), km + e0 * (long long)(NTOT * NTOT), bytes, bar, policy);
+  };
+  long long t = t0 + w;
+  if (lane == 0)
+    for (int b = 0; b < NBUF; ++b)
+      if (t + (long long)b * WARPS < t1) issue(b, t + (long long)b * WARPS);
+  // N ranks, peer transport: the owners' values must have landed before the first gather; the first tiles are on their way
+  if (GATHER && T) warp_wait_fwd(T, st);
+  int b = 0;
+  uint32_t phase = 0;
+  for (; t < t1; t += WARPS) {
+    const long long e0 = t * EPT;
+    const int ne = (int)((nels - e0) < EPT ? (nels - e0) : EPT);
+    const double *tile = mytiles + (size_t)b * Cfg::kTileDoubles;
+    // the tile's right-hand sides: every index first, then every value (two dependent loads per word, all in flight)
+    if (ne == EPT) {
+      int idx[KP];
+      double val[KP];
+#pragma unroll
+      for (int kp = 0; kp < KP; ++kp) {
+        const int s = lane + 32 * kp;
+        idx[kp] = (GATHER && s < EPT * NTOT) ? ggl[e0 * NTOT + s] : 0;
+      }
+#pragma unroll
+      for (int kp = 0; kp < KP; ++kp) {
+        const int s = lane + 32 * kp;
+        if (GATHER) val[kp] = T ? __ldcg(pvec + idx[kp]) : pvec[idx[kp]];
+        else val[kp] = (s < EPT * NTOT) ? pvec[e0 * NTOT + s] : 0.0;
+      }
+#pragma unroll
+      for (int kp = 0; kp < KP; ++kp) {
+        const int s = lane + 32 * kp;
+        if (s < EPT * NTOT) pm[s] = val[kp];
+      }
+    } else {
+      for (int s = lane; s < ne * NTOT; s += 32) {
+        if (GATHER) pm[s] = T ? __ldcg(pvec + ggl[e0 * NTOT + s]) : pvec[ggl[e0 * NTOT + s]];
+        else pm[s] = pvec[e0 * NTOT + s];
+      }
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&bars[w * NBUF + b]), phase);
+    for (int s = lane; s < ne * RP; s += 32) {
+      const int el = s / RP, rp = s - el * RP;
+      const double *K = tile + el * (NTOT * NTOT) + 2 * rp;
+      const double *pv = pm + el * NTOT;
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < NTOT; j += 2) {
+        const double2 pj = *reinterpret_cast<const double2 *>(pv + j);
+        const double2 k0 = *reinterpret_cast<const double2 *>(K + j * NTOT);
+        const double2 k1 = *reinterpret_cast<const double2 *>(K + (j + 1) * NTOT);
+        a0 = a0 + k0.x * pj.x; a1 = a1 + k0.y * pj.x;
+        a0 = a0 + k1.x * pj.y; a1 = a1 + k1.y * pj.y;
+      }
+      *reinterpret_cast<double2 *>(utemp + (e0 + el) * NTOT + 2 * rp) = make_double2(a0, a1);
+    }
+    __syncwarp();
+    const long long tn = t + (long long)NBUF * WARPS;
+    if (tn < t1 && lane == 0) {
+      fence_proxy_async();  // order this warp's generic reads of the slot before the async overwrite
+      issue(b, tn);
+    }
+    if (++b == NBUF) { b = 0; phase ^= 1; }
+  }
+}
+
 // ----------------------------------------------------------------------------
 // a8 on the symmetric-packed layout (pf_set_storkm_layout(h, 1)): half the storkm stream.
 // ----------------------------------------------------------------------------

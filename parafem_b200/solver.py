@@ -91,6 +91,12 @@ class Solver:
         self._ck(lib().pf_measure_fp64_tensor(self._h, C.byref(t)), "pf_measure_fp64_tensor")
         return t.value
 
+    def measure_matvec(self, reps=50):
+        """ms per launch of the current problem's mat-vec kernel, ``reps`` launches back to back between one event pair."""
+        t = C.c_double()
+        self._ck(lib().pf_measure_matvec(self._h, int(reps), C.byref(t)), "pf_measure_matvec")
+        return t.value
+
     def measure_hbm_read(self):
         """GB/s of a read-only stream through the mat-vec's bulk-copy ring (no arithmetic)."""
         t = C.c_double()
