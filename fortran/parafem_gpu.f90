@@ -169,6 +169,17 @@ MODULE parafem_gpu
       IMPORT; TYPE(c_ptr),VALUE :: h,totd_pp,tensor6; INTEGER(c_int64_t),VALUE :: iel; INTEGER(c_int),VALUE :: ig
     END FUNCTION
 
+    ! p1210 (explicit elasto-plastic von Mises dynamics, lumped mass): begin after pf_setup_mesh, npri steps per call
+    INTEGER(c_int) FUNCTION pf_vm_explicit_begin(h,e,v,sbary,rho,dtim,pload,fext_pp) BIND(C,name='pf_vm_explicit_begin')
+      IMPORT; TYPE(c_ptr),VALUE :: h,fext_pp; REAL(c_double),VALUE :: e,v,sbary,rho,dtim,pload
+    END FUNCTION
+    INTEGER(c_int) FUNCTION pf_vm_explicit_steps(h,nsteps,elapsed_ms) BIND(C,name='pf_vm_explicit_steps')
+      IMPORT; TYPE(c_ptr),VALUE :: h; INTEGER(c_int),VALUE :: nsteps; REAL(c_double) :: elapsed_ms
+    END FUNCTION
+    INTEGER(c_int) FUNCTION pf_vm_explicit_get(h,x1_pp,d1x1_pp,d2x1_pp,mm_pp) BIND(C,name='pf_vm_explicit_get')
+      IMPORT; TYPE(c_ptr),VALUE :: h,x1_pp,d1x1_pp,d2x1_pp,mm_pp       ! C_LOC(...) or C_NULL_PTR
+    END FUNCTION
+
     ! 0: one rank, 1: NCCL send/recv, 2: peer memory over NVLink
     INTEGER(c_int) FUNCTION pf_halo_transport(h) BIND(C,name='pf_halo_transport')
       IMPORT; TYPE(c_ptr),VALUE :: h

@@ -187,6 +187,18 @@ int pf_form_k_explicit(pf_handle h, double kx, double ky, double kz, double dtim
 int pf_explicit_start(pf_handle h, double val0);
 int pf_explicit_steps(pf_handle h, int nsteps, double *elapsed_ms);
 
+/* p1210 (programs/5th_ed/p1210/p1210.f90: forced vibration of an elastic-plastic von Mises solid, lumped mass,
+ * explicit integration).  No element matrices, no PCG: after pf_setup_mesh (20-node bricks, nip 8)
+ *   pf_vm_explicit_begin : element tables for (e, v), the diagonal mass matrix mm_pp (p1210.f90:93-104, scattered with
+ *                          the reverse halo exchange), fext_pp(neq_pp) from load() (:106-111), zero state (:112);
+ *   pf_vm_explicit_steps : nsteps passes of time_steps (:114-150) on the device: x1 += dtim*d1x1 + dtim**2/2*d2x1,
+ *                          gather, the Gauss-point stress update (invar / vmpl, tensor_pp / etensor_pp resident),
+ *                          scatter of -bload, bdylds = (bdylds + fext*pload)/mm, velocity and acceleration updates;
+ *   pf_vm_explicit_get   : x1_pp, d1x1_pp, d2x1_pp, mm_pp (any may be NULL).                                      */
+int pf_vm_explicit_begin(pf_handle h, double e, double v, double sbary, double rho, double dtim, double pload,
+                         const double *fext_pp);
+int pf_vm_explicit_steps(pf_handle h, int nsteps, double *elapsed_ms);
+int pf_vm_explicit_get(pf_handle h, double *x1_pp, double *d1x1_pp, double *d2x1_pp, double *mm_pp);
 /* --- p129: forced vibration, implicit theta method, consistent mass ----------
  * programs/5th_ed/p129/p129.f90.  The driver keeps its input section, the harmonic load factor and its output.
  *   pf_form_dynamic   elements_2 (p129.f90:83-98): store_km_pp and the consistent store_mm_pp (ecmat, shape_fun; 20-node

@@ -494,6 +494,22 @@ def p129(km, mm, g_g, neq, fext, theta, omega, alpha1, beta1, nstep, tol, limit,
     return dict(rows=rows, x=x0, d1x=d1x0, d2x=d2x0, fields=fields, dtim=dtim)
 
 
+def p1210(g_coord_pp, g_g, neq, fext, e, v, sbary, rho, dtim, pload, nstep, npri, npes=1):
+    """p1210.f90 on global arrays (orc_p1210_run): explicit elasto-plastic (von Mises) dynamics with the lumped mass of
+    :93-104.  -> dict(mm, snaps = [(step, x1, d1x1, d2x1)] every npri steps)."""
+    g, gg, fe = _f64(g_coord_pp), _i32(g_g), _f64(fext)
+    nels, nod = g.shape[0], g.shape[2]
+    nout = nstep // npri
+    snap = np.zeros((max(nout, 1), 3, neq))
+    mm = np.zeros(neq)
+    L = lib()
+    rc = L.orc_p1210_run(C.c_int64(nels), nod, 8, _p(g), _p(gg), C.c_int64(neq), _p(fe), C.c_double(e), C.c_double(v),
+                         C.c_double(sbary), C.c_double(rho), C.c_double(dtim), C.c_double(pload), int(nstep), int(npri),
+                         int(npes), _p(mm), _p(snap))
+    assert rc == 0
+    return dict(mm=mm, snaps=[((k + 1) * npri, snap[k, 0], snap[k, 1], snap[k, 2]) for k in range(nout)])
+
+
 def cube_p129(nxe, nye, nze, aa, bb, cc, rho=2000.0, e=1.0e5, v=0.3, alpha1=0.0008, beta1=0.5, nstep=40, npri=1, theta=1.0,
               omega=0.01, tol=1e-4, limit=3000, nip=27, deck_rounding=False):
     """p12meshgen's p129 cantilever (p12meshgen.f90, CASE('p129')): geometry_20bxz bricks, the first nr nodes (the plane

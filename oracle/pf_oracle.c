@@ -23,6 +23,8 @@
  *   programs/5th_ed/p121/p121.f90 (whole), programs/5th_ed/p123/p123.f90 (whole)
  *   programs/5th_ed/p122/p122.f90:197-231 (orc_p122_elements; the load-increment loop around it is in
  *   oracle/p122_oracle.py), new_library.f90: formm :85-198, invar :1813-1916, mocouf :2364-2417, mocouq :2423-2490
+ *   programs/5th_ed/p1210/p1210.f90:93-104 (orc_p1210_mass), :113-150 (orc_p1210_elements, orc_p1210_run),
+ *   new_library.f90: vmpl :2196-2286
  *   programs/5th_ed/p124/p124.f90:81-95,139-232, programs/5th_ed/p125/p125.f90:66-99,
  *   programs/dev/xx2/xx2.f90:169-193 (the time loops / material loop are composed from
  *   these C functions in oracle/__init__.py: p124(), p125(), form_km_elastic_mat())
@@ -1314,6 +1316,149 @@ int orc_pcg(int ntot, int64_t nels, const int32_t *g_g, const double *storkm, in
   *iters_out = iters; *converged_out = converged;
   free(pmul); free(utemp); free(diag); free(p); free(r); free(x); free(xnew); free(u); free(d); free(store);
   ranks_free(R);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* p1210 (programs/5th_ed/p1210/p1210.f90): forced vibration of an elastic-plastic (von Mises) solid,   */
+/* lumped mass, explicit integration.  20-node bricks (the lumping pattern of :100-103 is theirs).      */
+/* ------------------------------------------------------------------------- */
+/* elements_1 (p1210.f90:93-104): mm_tmp(:,iel) = emm, emm = volume/13 on the mid-side freedoms, an eighth of that on
+ * the corner freedoms (1:19:6, 2:20:6, 3:21:6, 37:55:6, 38:56:6, 39:57:6), volume = sum_gp det*w*rho */
+int orc_p1210_mass(int64_t nels, int nod, int nip, const double *g_coord_pp, double rho, double *mm_tmp) {
+  if (nod != 20 || nip != 8) return 1;
+  double points[81], weights[27];
+  orc_sample_hex(nip, points, weights);
+  for (int64_t iel = 0; iel < nels; ++iel) {
+    double der[60], deriv[60], volume = 0.0;
+    for (int ig = 0; ig < nip; ++ig) {
+      const double det = gauss_point(nod, points, nip, ig, g_coord_pp + iel * nod * 3, der, deriv);
+      volume = volume + det * weights[ig] * rho;
+    }
+    double *emm = mm_tmp + iel * 60;
+    const double mid = volume / 13.0;
+    for (int q = 0; q < 60; ++q) emm[q] = mid;
+    for (int c = 0; c < 3; ++c)
+      for (int q = c; q <= 18 + c; q += 6) { emm[q] = mid * .125; emm[36 + q] = mid * .125; }
+  }
+  return 0;
+}
+
+/* vmpl, nst = 6 (new_library.f90:2262-2284): pl(i,j) = term(i)*term(j)*ee */
+static void vmpl6(double e, double v, const double *s, double *pl) {
+  const double sx = s[0], sy = s[1], sz = s[2], txy = s[3], tyz = s[4], tzx = s[5];
+  const double dsbar = sqrt((sx - sy) * (sx - sy) + (sy - sz) * (sy - sz) + (sz - sx) * (sz - sx) + 6.0 * (txy * txy) +
+                            6.0 * (tyz * tyz) + 6.0 * (tzx * tzx)) / sqrt(2.0);
+  const double ee = 1.5 * e / ((1.0 + v) * dsbar * dsbar);
+  const double term[6] = {(2.0 * sx - sy - sz) / 3.0, (2.0 * sy - sz - sx) / 3.0, (2.0 * sz - sx - sy) / 3.0, txy, tyz, tzx};
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) pl[j * 6 + i] = term[i] * term[j] * ee;
+}
+/* the second invariant of invar (new_library.f90:1891-1897): dsbar = sqrt(3)*sqrt(d2); p1210 uses nothing else of it */
+static double dsbar6(const double *s) {
+  const double d2 = ((s[0] - s[1]) * (s[0] - s[1]) + (s[1] - s[2]) * (s[1] - s[2]) + (s[2] - s[0]) * (s[2] - s[0])) / 6.0 +
+                    s[3] * s[3] + s[4] * s[4] + s[5] * s[5];
+  return sqrt(3.0) * sqrt(d2);
+}
+
+/* elements_2 (p1210.f90:120-147) over all elements: pmul = gathered displacements, etensor / tensor (6,nip,nels) updated
+ * in place, utemp = -bload.  Every MATMUL: k ascending from 0.0, separate multiply and add. */
+int orc_p1210_elements(int64_t nels, int nod, int nip, const double *g_coord_pp, double e, double v, double sbary,
+                       const double *pmul, double *etensor, double *tensor, double *utemp) {
+  if (nod != 20 || nip != 8) return 1;
+  const int ntot = 3 * nod;
+  double points[81], weights[27], dee0[36];
+  orc_sample_hex(nip, points, weights);
+  orc_deemat6(dee0, e, v);
+#pragma omp parallel for schedule(static) if (nels > 256)
+  for (int64_t iel = 0; iel < nels; ++iel) {
+    double der[60], deriv[60], bee[6 * 60], bload[60], eps[6], sigma[6], stressv[6], dee[36], pl[36];
+    const double *eld = pmul + iel * ntot;
+    for (int q = 0; q < ntot; ++q) bload[q] = 0.0;
+    for (int ig = 0; ig < nip; ++ig) {
+      double *et = etensor + (iel * nip + ig) * 6, *te = tensor + (iel * nip + ig) * 6;
+      memcpy(dee, dee0, sizeof dee);
+      const double det = gauss_point(nod, points, nip, ig, g_coord_pp + iel * nod * 3, der, deriv);
+      orc_beemat6(bee, deriv, nod);
+      for (int r = 0; r < 6; ++r) {
+        double s = 0.0;
+        for (int q = 0; q < ntot; ++q) s += bee[q * 6 + r] * eld[q];
+        eps[r] = s - et[r];
+      }
+      for (int r = 0; r < 6; ++r) {
+        double s = 0.0;
+        for (int q = 0; q < 6; ++q) s += dee[q * 6 + r] * eps[q];
+        sigma[r] = s;
+        stressv[r] = s + te[r];
+      }
+      const double fnew = dsbar6(stressv) - sbary;
+      if (fnew >= 0.0) {                 /* yield is violated: scale back to the surface, elasto-plastic dee */
+        const double f = dsbar6(te) - sbary, fac = fnew / (fnew - f);
+        for (int r = 0; r < 6; ++r) stressv[r] = te[r] + (1.0 - fac) * sigma[r];
+        vmpl6(e, v, stressv, pl);
+        for (int q = 0; q < 36; ++q) dee[q] = dee[q] - fac * pl[q];
+      }
+      for (int r = 0; r < 6; ++r) {
+        double s = 0.0;
+        for (int q = 0; q < 6; ++q) s += dee[q * 6 + r] * eps[q];
+        sigma[r] = s + te[r];
+      }
+      for (int q = 0; q < ntot; ++q) {   /* eload = MATMUL(sigma,bee); bload = bload + eload*det*weights(i) */
+        double s = 0.0;
+        for (int r = 0; r < 6; ++r) s += sigma[r] * bee[q * 6 + r];
+        bload[q] = bload[q] + s * det * weights[ig];
+      }
+      for (int r = 0; r < 6; ++r) { te[r] = sigma[r]; et[r] = et[r] + eps[r]; }
+    }
+    for (int q = 0; q < ntot; ++q) utemp[iel * ntot + q] = 0.0 - bload[q];
+  }
+  return 0;
+}
+
+/* The whole program on global arrays over npes emulated ranks (the partition only orders the scatter's sums).
+ * mm_out (neq) = the assembled lumped mass; snap holds, for every npri-th step, x1 / d1x1 / d2x1 (3 x neq doubles). */
+int orc_p1210_run(int64_t nels, int nod, int nip, const double *g_coord_pp, const int32_t *g_g, int64_t neq,
+                  const double *fext, double e, double v, double sbary, double rho, double dtim, double pload, int nstep,
+                  int npri, int npes, double *mm_out, double *snap) {
+  if (nod != 20 || nip != 8 || npri < 1) return 1;
+  const int ntot = 3 * nod;
+#ifdef _OPENMP
+  /* a handful of elements and hundreds of thousands of steps: opening parallel regions would be all the time there is */
+  const int threads_before = omp_get_max_threads();
+  if (nels <= 256) omp_set_num_threads(1);
+#endif
+  orc_ranks *R = ranks_new(npes, ntot, nels, g_g, neq);
+  double *pmul = malloc(sizeof(double) * (size_t)(nels * ntot)), *utemp = malloc(sizeof(double) * (size_t)(nels * ntot));
+  double *x1 = calloc((size_t)neq, 8), *d1 = calloc((size_t)neq, 8), *d2 = calloc((size_t)neq, 8);
+  double *mm = calloc((size_t)neq, 8), *bdy = calloc((size_t)neq, 8);
+  double *et = calloc((size_t)(nels * nip * 6), 8), *te = calloc((size_t)(nels * nip * 6), 8);
+  orc_p1210_mass(nels, nod, nip, g_coord_pp, rho, utemp);
+  ranks_scatter(R, ntot, g_g, utemp, mm);
+  if (mm_out) memcpy(mm_out, mm, sizeof(double) * (size_t)neq);
+  int64_t nout = 0;
+  for (int jj = 1; jj <= nstep; ++jj) {
+    for (int64_t i = 0; i < neq; ++i) x1[i] = x1[i] + (dtim * d1[i]) + (0.5 * (dtim * dtim) * d2[i]);   /* p1210.f90:117 */
+    orc_gather(ntot, nels, g_g, x1, pmul);
+    orc_p1210_elements(nels, nod, nip, g_coord_pp, e, v, sbary, pmul, et, te, utemp);
+    ranks_scatter(R, ntot, g_g, utemp, bdy);
+    for (int64_t i = 0; i < neq; ++i) {                       /* :148-150 */
+      double b = bdy[i] + fext[i] * pload;
+      b = b / mm[i];
+      d1[i] = d1[i] + (d2[i] + b) * .5 * dtim;
+      d2[i] = b;
+    }
+    if (jj % npri == 0 && snap) {
+      memcpy(snap + nout * 3 * neq, x1, sizeof(double) * (size_t)neq);
+      memcpy(snap + nout * 3 * neq + neq, d1, sizeof(double) * (size_t)neq);
+      memcpy(snap + nout * 3 * neq + 2 * neq, d2, sizeof(double) * (size_t)neq);
+      nout = nout + 1;
+    }
+  }
+  free(pmul); free(utemp); free(x1); free(d1); free(d2); free(mm); free(bdy); free(et); free(te);
+  ranks_free(R);
+#ifdef _OPENMP
+  omp_set_num_threads(threads_before);
+#endif
   return 0;
 }
 

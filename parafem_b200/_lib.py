@@ -88,6 +88,9 @@ SIGNATURES = {
     "pf_reset_profile": (c_int, [vp]),
     "pf_get_kernel_ms": (c_int, [vp, c_int, P(c_dbl), P(c_i64)]),
     "pf_kernel_launches": (c_i64, [vp]),
+    "pf_vm_explicit_begin": (c_int, [vp, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, vp]),
+    "pf_vm_explicit_steps": (c_int, [vp, c_int, P(c_dbl)]),
+    "pf_vm_explicit_get": (c_int, [vp, vp, vp, vp, vp]),
     "pf_measure_fp64": (c_int, [vp, P(c_dbl)]),
     "pf_measure_fp64_tensor": (c_int, [vp, P(c_dbl)]),
     "pf_measure_matvec": (c_int, [vp, c_int, P(c_dbl)]),

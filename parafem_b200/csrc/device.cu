@@ -145,6 +145,13 @@ struct pf_ctx {
   PlasticParams pl_par;
   DevBuf<double> evpt, tensor, bdylds, oldis, totd, loads, ld0, valf;
 
+  // p1210 (explicit elasto-plastic dynamics): strains / stresses of every Gauss point, lumped mass, external loads,
+  // velocity and acceleration; the displacement lives in the owned part of p_ext
+  bool vm_explicit = false;
+  VmParams vm_par;
+  double vm_dtim = 0.0, vm_pload = 0.0;
+  DevBuf<double> vm_eten, vm_ten, vm_mm, vm_fext, vm_d1, vm_d2;
+
   // one PCG iteration captured as a CUDA graph (single rank; re-captured when the problem changes)
   cudaGraphExec_t graph_exec = nullptr;
   int64_t epoch = 0, graph_epoch = -1, graph_launches = 0;
@@ -1771,6 +1778,94 @@ int pf_plastic_get(pf_handle h, double *totd_pp, int64_t iel, int ig, double *te
     NEED(iel >= 0 && iel < h->nels && ig >= 0 && ig < h->nip, "element / Gauss point outside the local range");
     CU(cudaMemcpy(tensor6, h->tensor.p + ((size_t)iel * h->nip + ig) * 6, 48, cudaMemcpyDeviceToHost));
   }
+  return 0;
+}
+
+// ---- p1210: forced vibration of an elastic-plastic (von Mises) solid, lumped mass, explicit integration ----
+// (programs/5th_ed/p1210/p1210.f90).  No element matrices and no PCG: pf_setup_mesh, then
+// pf_vm_explicit_begin (element tables, lumped mass :93-104, zero state :112), pf_vm_explicit_steps (:114-150).
+int pf_vm_explicit_begin(pf_handle h, double e, double v, double sbary, double rho, double dtim, double pload, const double *fext_pp) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->have_mesh && h->nodof == 3 && h->nod == 20 && h->nip == 8, "needs pf_setup_mesh with 20-node hexahedra, nodof = 3, nip = 8");
+  NEED(dtim > 0.0 && rho > 0.0, "dtim and rho must be positive");
+  ElemTables T;
+  if (fill_tables(h->nod, h->nip, e, v, 0, 0, 0, T)) return fail(h, 3, "unsupported nod/nip");
+  if ((rc = upload_tables(h, T))) return rc;
+  h->vm_par = VmParams{e, v, sbary};
+  h->vm_dtim = dtim; h->vm_pload = pload;
+  const size_t ng = (size_t)std::max<int64_t>(h->nels * h->nip * 6, 1), nq = (size_t)std::max<int64_t>(h->neq_pp, 1);
+  CU(h->vm_eten.alloc(ng)); CU(h->vm_ten.alloc(ng));
+  CU(h->vm_mm.alloc(nq)); CU(h->vm_fext.alloc(nq)); CU(h->vm_d1.alloc(nq)); CU(h->vm_d2.alloc(nq));
+  CU(cudaMemsetAsync(h->vm_eten.p, 0, ng * 8, h->stream)); CU(cudaMemsetAsync(h->vm_ten.p, 0, ng * 8, h->stream));
+  CU(cudaMemsetAsync(h->vm_d1.p, 0, nq * 8, h->stream)); CU(cudaMemsetAsync(h->vm_d2.p, 0, nq * 8, h->stream));
+  CU(cudaMemsetAsync(h->vm_fext.p, 0, nq * 8, h->stream));
+  CU(cudaMemsetAsync(h->p_ext.p, 0, h->p_ext.n * 8, h->stream));
+  if (fext_pp && h->neq_pp > 0) CU(cudaMemcpyAsync(h->vm_fext.p, fext_pp, (size_t)h->neq_pp * 8, cudaMemcpyHostToDevice, h->stream));
+  // diagonal mass matrix: mm_tmp -> scatter (with the reverse halo exchange) -> mm_pp
+  if (h->nels > 0) {
+    k_p1210_mass<<<grid_for(h, h->nels, 128), 128, 0, h->stream>>>(h->coord.p, h->utemp.p, (long long)h->nels, rho);
+    h->launches++;
+  }
+  if ((rc = launch_scatter(h, nullptr, false, h->u_ext.p))) return rc;
+  if ((rc = halo_reverse(h, h->u_ext.p, nullptr))) return rc;
+  CU(cudaMemcpyAsync(h->vm_mm.p, h->u_ext.p + 1, (size_t)h->neq_pp * 8, cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  h->have_km = false; h->have_precon = false; h->plastic = false; h->dynamic = false; h->transient = false; h->explicit_ = false;
+  h->vm_explicit = true;
+  return 0;
+}
+
+int pf_vm_explicit_steps(pf_handle h, int nsteps, double *elapsed_ms) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->vm_explicit && nsteps >= 0, "needs pf_vm_explicit_begin and nsteps >= 0");
+  if ((rc = ensure_tables(h))) return rc;
+  EventPair ev;
+  CU(ev.create());
+  CU(cudaEventRecord(ev.a, h->stream));
+  const long long n = h->neq_pp;
+  const int vgrid = grid_for(h, std::max<int64_t>(n, 1), 256);
+  const int egrid = (int)std::max<int64_t>(1, std::min<int64_t>(h->nels, (int64_t)h->sm_count * 16));
+  for (int j = 0; j < nsteps; ++j) {
+    if (n > 0) {
+      Scope sc(h, K_VECTOR);
+      k_p1210_predict<<<vgrid, 256, 0, h->stream>>>(h->p_ext.p + 1, h->vm_d1.p, h->vm_d2.p, h->vm_dtim, n);
+      h->launches++;
+    }
+    if ((rc = halo_forward(h, h->p_ext.p, nullptr))) return rc;
+    if (h->nels > 0) {
+      Scope sc(h, K_MATVEC);
+      k_p1210_elements<20><<<egrid, 64, 0, h->stream>>>(h->coord.p, h->ggl.p, h->p_ext.p, h->vm_eten.p, h->vm_ten.p, h->utemp.p,
+                                                        (long long)h->nels, h->vm_par);
+      h->launches++;
+    }
+    if ((rc = launch_scatter(h, nullptr, false, h->u_ext.p))) return rc;
+    if ((rc = halo_reverse(h, h->u_ext.p, nullptr))) return rc;
+    if (n > 0) {
+      Scope sc(h, K_VECTOR);
+      k_p1210_update<<<vgrid, 256, 0, h->stream>>>(h->u_ext.p + 1, h->vm_fext.p, h->vm_mm.p, h->vm_d1.p, h->vm_d2.p, h->vm_pload,
+                                                   h->vm_dtim, n);
+      h->launches++;
+    }
+  }
+  CU(cudaEventRecord(ev.b, h->stream));
+  CU(cudaEventSynchronize(ev.b));
+  CU(cudaGetLastError());
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, ev.a, ev.b));
+  collect_spans(h);
+  if (elapsed_ms) *elapsed_ms = ms;
+  return 0;
+}
+
+int pf_vm_explicit_get(pf_handle h, double *x1_pp, double *d1x1_pp, double *d2x1_pp, double *mm_pp) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(h->vm_explicit, "needs pf_vm_explicit_begin");
+  const size_t nb = (size_t)h->neq_pp * 8;
+  if (x1_pp) CU(cudaMemcpy(x1_pp, h->p_ext.p + 1, nb, cudaMemcpyDeviceToHost));
+  if (d1x1_pp) CU(cudaMemcpy(d1x1_pp, h->vm_d1.p, nb, cudaMemcpyDeviceToHost));
+  if (d2x1_pp) CU(cudaMemcpy(d2x1_pp, h->vm_d2.p, nb, cudaMemcpyDeviceToHost));
+  if (mm_pp) CU(cudaMemcpy(mm_pp, h->vm_mm.p, nb, cudaMemcpyDeviceToHost));
   return 0;
 }
 

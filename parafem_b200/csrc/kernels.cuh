@@ -2795,6 +2795,181 @@ k_p122_elements(const double *__restrict__ g_coord, const int *__restrict__ ggl,
   }
 }
 
+// ----------------------------------------------------------------------------
+// p1210 (programs/5th_ed/p1210/p1210.f90): forced vibration of an elastic-plastic (von Mises) solid, lumped mass,
+// explicit integration.  No PCG: a time step is gather -> Gauss-point stress update -> scatter -> three vector updates.
+// ----------------------------------------------------------------------------
+struct VmParams {
+  double e, v, sbary;
+};
+// second invariant as invar forms it (new_library.f90:1891-1897): dsbar = sqrt(3)*sqrt(d2)
+__device__ __forceinline__ double vm_dsbar(const double *s) {
+  const double d2 = ((s[0] - s[1]) * (s[0] - s[1]) + (s[1] - s[2]) * (s[1] - s[2]) + (s[2] - s[0]) * (s[2] - s[0])) / 6.0 +
+                    s[3] * s[3] + s[4] * s[4] + s[5] * s[5];
+  return sqrt(3.0) * sqrt(d2);
+}
+// elements_1 (p1210.f90:93-104): one thread per element, emm(ntot) -> utemp (mm_tmp)
+__global__ void k_p1210_mass(const double *__restrict__ g_coord, double *__restrict__ utemp, long long nels, double rho) {
+  constexpr int NOD = 20;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nels; e += (long long)gridDim.x * blockDim.x) {
+    const double *c = g_coord + e * NOD * 3;
+    double volume = 0.0;
+    for (int ig = 0; ig < 8; ++ig) {
+      const double *der = c_tab.der + ig * 60;
+      double jac[9];
+      for (int b = 0; b < 3; ++b)
+        for (int a = 0; a < 3; ++a) {
+          double sum = 0.0;
+          for (int m = 0; m < NOD; ++m) sum = sum + der[a * 20 + m] * c[b * NOD + m];
+          jac[b * 3 + a] = sum;
+        }
+      volume = volume + det3(jac) * c_tab.weights[ig] * rho;
+    }
+    const double mid = volume / 13.0, corner = mid * .125;
+    double *o = utemp + e * 60;
+    for (int m = 0; m < NOD; ++m) {
+      const bool is_corner = (m < 8 || m >= 12) && (m % 2 == 0);     // freedoms 1:19:6 .. 3:21:6 and 37:55:6 .. 39:57:6
+      o[3 * m] = o[3 * m + 1] = o[3 * m + 2] = is_corner ? corner : mid;
+    }
+  }
+}
+// elements_2 (p1210.f90:120-147): geometry of every Gauss point as in k_p122_elements; thread ig updates point ig (strain
+// from the gathered displacements minus etensor, elastic trial stress, on yield the scaled-back stress -> vmpl ->
+// dee - fac*pl, stress, tensor / etensor update); thread q adds the points' sigma*bee*det*w to bload(q) in point order;
+// utemp = 0 - bload.  Summation orders as orc_p1210_elements (products with a structural zero of bee left out).
+template <int NOD>
+__global__ void __launch_bounds__(64)
+k_p1210_elements(const double *__restrict__ g_coord, const int *__restrict__ ggl, const double *__restrict__ x_ext,
+                 double *__restrict__ etensor, double *__restrict__ tensor, double *__restrict__ utemp, long long nels, VmParams P) {
+  constexpr int NTOT = 3 * NOD, MAXIP = 8, THREADS = 64;
+  static_assert(NTOT <= THREADS, "one thread per element freedom");
+  __shared__ double s_coord[NOD * 3], s_jac[MAXIP * 9], s_det[MAXIP], s_deriv[MAXIP * NOD * 3], s_eld[NTOT], s_sig[MAXIP * 6];
+  const int nip = c_tab.nip, t = threadIdx.x;
+  for (long long e = blockIdx.x; e < nels; e += gridDim.x) {
+    __syncthreads();
+    for (int q = t; q < NOD * 3; q += THREADS) s_coord[q] = g_coord[e * NOD * 3 + q];
+    if (t < NTOT) s_eld[t] = x_ext[ggl[e * NTOT + t]];                // gather(x1_pp,pmul_pp): slot 0 holds 0.0
+    __syncthreads();
+    for (int q = t; q < nip * 9; q += THREADS) {                      // jac = MATMUL(der,coord), every point
+      const int ig = q / 9, r = q - 9 * ig, a = r % 3, b = r / 3;
+      const double *der = c_tab.der + ig * 60;
+      double sum = 0.0;
+#pragma unroll
+      for (int m = 0; m < NOD; ++m) sum = sum + der[a * 20 + m] * s_coord[b * NOD + m];
+      s_jac[ig * 9 + b * 3 + a] = sum;
+    }
+    __syncthreads();
+    if (t < nip) {
+      double jac[9], inv[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) jac[q] = s_jac[t * 9 + q];
+      const double det = det3(jac);
+      inv3(jac, det, inv);
+#pragma unroll
+      for (int q = 0; q < 9; ++q) s_jac[t * 9 + q] = inv[q];
+      s_det[t] = det;
+    }
+    __syncthreads();
+    for (int q = t; q < nip * NOD * 3; q += THREADS) {                // deriv = MATMUL(jac^-1,der)
+      const int ig = q / (NOD * 3), r = q - ig * (NOD * 3), m = r / 3, a = r - 3 * m;
+      const double *der = c_tab.der + ig * 60, *inv = s_jac + ig * 9;
+      double sum = 0.0;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) sum = sum + inv[b * 3 + a] * der[b * 20 + m];
+      s_deriv[q] = sum;
+    }
+    __syncthreads();
+    if (t < nip) {
+      const double *dv = s_deriv + t * (NOD * 3);
+      double *et = etensor + (e * nip + t) * 6, *te = tensor + (e * nip + t) * 6;
+      double eps[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, sigma[6], stressv[6], ten[6], dee[36];
+      for (int m = 0; m < NOD; ++m) {                                 // eps = MATMUL(bee,eld), q ascending
+        const double x = dv[m * 3], y = dv[m * 3 + 1], z = dv[m * 3 + 2];
+        const double e0 = s_eld[3 * m], e1 = s_eld[3 * m + 1], e2 = s_eld[3 * m + 2];
+        eps[0] = eps[0] + x * e0; eps[3] = eps[3] + y * e0; eps[5] = eps[5] + z * e0;     // column 3m
+        eps[1] = eps[1] + y * e1; eps[3] = eps[3] + x * e1; eps[4] = eps[4] + z * e1;     // column 3m+1
+        eps[2] = eps[2] + z * e2; eps[4] = eps[4] + y * e2; eps[5] = eps[5] + x * e2;     // column 3m+2
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) { eps[r] = eps[r] - et[r]; ten[r] = te[r]; }
+#pragma unroll
+      for (int q = 0; q < 36; ++q) dee[q] = c_tab.dee[q];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {                                   // sigma = MATMUL(dee,eps); stressv = sigma + tensor
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) sum = sum + dee[q * 6 + r] * eps[q];
+        sigma[r] = sum;
+        stressv[r] = sum + ten[r];
+      }
+      const double fnew = vm_dsbar(stressv) - P.sbary;
+      if (fnew >= 0.0) {                                              // yield is violated
+        const double f = vm_dsbar(ten) - P.sbary, fac = fnew / (fnew - f);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) stressv[r] = ten[r] + (1.0 - fac) * sigma[r];
+        // vmpl (new_library.f90:2262-2284)
+        const double sx = stressv[0], sy = stressv[1], sz = stressv[2], txy = stressv[3], tyz = stressv[4], tzx = stressv[5];
+        const double dsb = sqrt((sx - sy) * (sx - sy) + (sy - sz) * (sy - sz) + (sz - sx) * (sz - sx) + 6.0 * (txy * txy) +
+                                6.0 * (tyz * tyz) + 6.0 * (tzx * tzx)) / sqrt(2.0);
+        const double ee = 1.5 * P.e / ((1.0 + P.v) * dsb * dsb);
+        const double term[6] = {(2.0 * sx - sy - sz) / 3.0, (2.0 * sy - sz - sx) / 3.0, (2.0 * sz - sx - sy) / 3.0, txy, tyz, tzx};
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j < 6; ++j) dee[j * 6 + i] = dee[j * 6 + i] - fac * (term[i] * term[j] * ee);
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {                                   // sigma = MATMUL(dee,eps) + tensor
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) sum = sum + dee[q * 6 + r] * eps[q];
+        sigma[r] = sum + ten[r];
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        s_sig[t * 6 + r] = sigma[r];
+        te[r] = sigma[r];
+        et[r] = et[r] + eps[r];
+      }
+    }
+    __syncthreads();
+    if (t < NTOT) {                                                   // bload = bload + MATMUL(sigma,bee)*det*w
+      const int m = t / 3, comp = t - 3 * m;
+      double bl = 0.0;
+      for (int ig = 0; ig < nip; ++ig) {
+        const double *dv = s_deriv + ig * (NOD * 3), *sg = s_sig + ig * 6;
+        const double x = dv[m * 3], y = dv[m * 3 + 1], z = dv[m * 3 + 2];
+        double sum = 0.0;
+        if (comp == 0) { sum = sum + sg[0] * x; sum = sum + sg[3] * y; sum = sum + sg[5] * z; }
+        else if (comp == 1) { sum = sum + sg[1] * y; sum = sum + sg[3] * x; sum = sum + sg[4] * z; }
+        else { sum = sum + sg[2] * z; sum = sum + sg[4] * y; sum = sum + sg[5] * x; }
+        bl = bl + sum * s_det[ig] * c_tab.weights[ig];
+      }
+      utemp[e * NTOT + t] = 0.0 - bl;
+    }
+  }
+}
+// x1 = x1 + dtim*d1x1 + 0.5*dtim**2*d2x1   (p1210.f90:117); x1 lives in the owned part of p_ext
+__global__ void k_p1210_predict(double *__restrict__ x1, const double *__restrict__ d1, const double *__restrict__ d2, double dtim,
+                                long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const double c = 0.5 * (dtim * dtim);
+  for (; i < n; i += stride) x1[i] = x1[i] + (dtim * d1[i]) + (c * d2[i]);
+}
+// bdylds = (bdylds + fext*pload)/mm; d1x1 = d1x1 + (d2x1 + bdylds)*.5*dtim; d2x1 = bdylds   (p1210.f90:148-150)
+__global__ void k_p1210_update(const double *__restrict__ bdy, const double *__restrict__ fext, const double *__restrict__ mm,
+                               double *__restrict__ d1, double *__restrict__ d2, double pload, double dtim, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    double b = bdy[i] + fext[i] * pload;
+    b = b / mm[i];
+    d1[i] = d1[i] + (d2[i] + b) * .5 * dtim;
+    d2[i] = b;
+  }
+}
+
 // loads = ld0*q (or 0) [+ bdylds]   (p122.f90:127-137)
 __global__ void k_plastic_loads(double *__restrict__ loads, const double *__restrict__ ld0, const double *__restrict__ bdylds,
                                 double q, int add_bdy, long long n) {

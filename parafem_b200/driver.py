@@ -196,6 +196,52 @@ def write_res_p129(path, prob, res, t_total=0.0):
         f.write(f"This analysis took:{t_total:10.4f}\n")
 
 
+def run_p1210(prob, s, out_base=None, decimals=4, nstep=None):
+    """Program p1210 (p1210.f90) for one rank: setup (lumped mass, loads), then the explicit loop -- npri steps per
+    device call.  With `out_base` the displacement files <out_base>.ensi.DISPL-NNNNNN are written every npri steps
+    (single rank).  -> dict(rows = [(time, x1(nres), d1x1(nres), d2x1(nres))] starting with the t = 0 row, x, d1x, d2x,
+    fields = {step: x1_pp}, solve_s, setup_s)."""
+    from . import host
+    t0 = time.time()
+    _solver.setup_problem(s, prob)
+    t_setup = time.time() - t0
+    lo = prob.ieq_start
+    owns = lo <= prob.nres < lo + prob.neq_pp
+    k = prob.nres - lo
+    rows, fields, ms_total = [], {}, 0.0
+    if owns:
+        rows.append((0.0, 0.0, 0.0, 0.0))
+    nstep = prob.nstep if nstep is None else nstep
+    real_time, done = 0.0, 0
+    while done + prob.npri <= nstep:
+        ms_total += s.vm_explicit_steps(prob.npri)
+        done += prob.npri
+        for _ in range(prob.npri):
+            real_time = real_time + prob.dtim                 # real_time=real_time+dtim, step by step (p1210.f90:115)
+        x1, d1, d2 = s.vm_explicit_get()
+        fields[done] = x1
+        if owns:
+            rows.append((real_time, float(x1[k]), float(d1[k]), float(d2[k])))
+        if out_base and prob.npes == 1:
+            host.write_ensi(f"{out_base}.ensi.DISPL-{done:06d}", host.nodal_values(prob, x1), decimals=decimals)
+    if done < nstep:
+        ms_total += s.vm_explicit_steps(nstep - done)
+    x, d1x, d2x = s.vm_explicit_get()
+    return dict(rows=rows, x=x, d1x=d1x, d2x=d2x, fields=fields, solve_s=ms_total / 1e3, setup_s=t_setup)
+
+
+def write_res_p1210(path, prob, res, t_total=0.0):
+    """<job>.res as p1210.f90:55-60,113-114,152-153 writes it."""
+    with open(path, "w") as f:
+        f.write(f"This job ran on {prob.npes:6d} processes\n")
+        f.write(f"There are {prob.nn:12d} nodes {prob.nr:12d} restrained and {prob.neq:12d} equations\n")
+        f.write(f"Time after setup was:{res['setup_s']:10.4f}\n")
+        f.write("  Time      Displacement  Velocity   Acceleration \n")
+        for t, x, v, a in res["rows"]:
+            f.write(f"{_fe(t)}{_fe(x)}{_fe(v)}{_fe(a)}\n")
+        f.write(f"This analysis took:{t_total:10.4f}\n")
+
+
 def run_p122(prob, s, out_base=None, decimals=4):
     """Program p122 (p122.f90) for one rank: setup, then the load-increment loop -- every increment one device call
     (plastic iterations, each a PCG solve restarted from the current x plus the Gauss-point stress update).  With

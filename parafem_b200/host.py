@@ -464,6 +464,52 @@ def read_deck_p129(job, npes=1, numpe=1):
     return p
 
 
+def read_deck_p1210(job, npes=1, numpe=1):
+    """Input section of p1210.f90:27-52,106-111 for one rank.  read_p1210 (input.f90:5107-5109) reads
+    element, meshgen, partitioner, nels nip nn nr nod loaded_nodes nres, rho e v sbary, dtim nstep npri pload;
+    the one deck the reference ships (examples/5th_ed/p1210/p1210_tiny.dat, written for the program's 2010 form
+    "p1210_5") has no nres and ends `pload dtim nstep npri` with the counts written as reals (3.e+5 3.e+3): both
+    layouts are taken, told apart by the token after loaded_nodes (an integer nres or the real rho)."""
+    L = lib()
+    tk = open(job + ".dat").read().split()
+    num = lambda t: float(t.replace("D", "E").replace("d", "e"))
+    meshgen, partitioner = int(tk[1]), int(tk[2])
+    nels, nip, nn, nr, nod, loaded = (int(v) for v in tk[3:9])
+    if len(tk) >= 18 and tk[9].lstrip("+-").isdigit():
+        nres = int(tk[9])
+        rho, e, v, sbary, dtim = (num(t) for t in tk[10:15])
+        nstep, npri, pload = int(tk[15]), int(tk[16]), num(tk[17])
+    elif len(tk) >= 17:
+        nres = 1                                               # p1210.f90:13 default
+        rho, e, v, sbary, pload, dtim = (num(t) for t in tk[9:15])
+        nstep, npri = int(round(num(tk[15]))), int(round(num(tk[16])))
+    else:
+        raise PfError(f"{job}.dat: too few values for read_p1210")
+    if min(nels, nn) < 1 or nr < 0 or nr > nn or nod != 20 or nip != 8 or loaded < 0 or loaded > nn or nstep < 0 or npri < 1:
+        raise PfError(f"{job}.dat: sizes outside what p1210 takes (20-node hexahedra, nip = 8)")
+    g_coord, g_num = _read_mesh(job, nn, nels, nod, meshgen, False)
+    nels_pp, iel_start = read_psize(job, npes, numpe) if partitioner == 2 else calc_nels_pp(nels, npes, numpe)
+    g_num_pp = np.ascontiguousarray(g_num[iel_start - 1:iel_start - 1 + nels_pp])
+    g_coord_pp = np.empty((nels_pp, 3, nod), np.float64)
+    check(L.pf_coords_pp(nod, nels_pp, nn, ptr(g_num_pp), ptr(g_coord), ptr(g_coord_pp)), what="pf_coords_pp")
+    rest = np.zeros((4, nr), np.int32)
+    check(L.pf_read_bnd(job.encode(), nr, 3, ptr(rest)), what="pf_read_bnd")
+    nf, g_g, neq = _steer(nn, 3, rest, g_num_pp, nod)
+    neq_pp, ieq_start = calc_neq_pp(neq, npes, numpe)
+    r = np.zeros(neq_pp, np.float64)
+    total = 0.0
+    if loaded:
+        node = np.empty(loaded, np.int32)
+        val = np.empty((loaded, 3), np.float64)
+        check(L.pf_read_lds(job.encode(), loaded, 3, ptr(node), ptr(val)), what="pf_read_lds")
+        check(L.pf_load(3, loaded, nn, ptr(node), ptr(val), ptr(nf), ieq_start, neq_pp, ptr(r)), what="pf_load")
+        total = float(val.sum())
+    p = Problem(1210, nod, 3, nip, nels, nn, nr, neq, npes, numpe, nels_pp, iel_start, neq_pp, ieq_start, g_num_pp, g_coord_pp,
+                g_g, nf, r, e=e, v=v, rho=rho, nstep=nstep, npri=npri, nres=nres, total_load=total)
+    p.sbary, p.dtim, p.pload, p.rest, p.g_coord = sbary, dtim, pload, rest, g_coord
+    return p
+
+
 def read_deck_xx2(job, npes=1, numpe=1):
     """Input section of programs/dev/xx2/xx2.f90:60-160 for one rank: read_xx2, read_elements (connectivity +
     material number of every element), abaqus2sg, read_g_coord_pp, read_rest, read_materialValue, steering,

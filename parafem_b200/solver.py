@@ -222,6 +222,24 @@ class Solver:
         self._ck(lib().pf_dynamic_get(self._h, ptr(out[0]), ptr(out[1]), ptr(out[2])), "pf_dynamic_get")
         return tuple(out)
 
+    # -- p1210: explicit elasto-plastic (von Mises) dynamics -------------------------------------
+    def vm_explicit_begin(self, e, v, sbary, rho, dtim, pload, fext_pp):
+        """p1210.f90:93-112 after setup_mesh: element tables, lumped mass, external loads, zero state."""
+        self._ck(lib().pf_vm_explicit_begin(self._h, e, v, sbary, rho, dtim, pload, ptr(f64(fext_pp))), "pf_vm_explicit_begin")
+
+    def vm_explicit_steps(self, nsteps):
+        """nsteps passes of time_steps (p1210.f90:114-150) on the device. -> elapsed_ms"""
+        ms = C.c_double()
+        self._ck(lib().pf_vm_explicit_steps(self._h, int(nsteps), C.byref(ms)), "pf_vm_explicit_steps")
+        return ms.value
+
+    def vm_explicit_get(self, mass=False):
+        """-> (x1_pp, d1x1_pp, d2x1_pp[, mm_pp])"""
+        out = [np.empty(self.prob.neq_pp) for _ in range(4 if mass else 3)]
+        self._ck(lib().pf_vm_explicit_get(self._h, ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]) if mass else None),
+                 "pf_vm_explicit_get")
+        return tuple(out)
+
     # -- p122: elasto-plasticity ---------------------------------------------------------------
     def plastic_begin(self, phi, c, psi, e, v):
         """p122.f90:88-93 after form_km_elastic + build_precon. -> the critical time step dt"""
@@ -345,6 +363,9 @@ def setup_problem(solver, prob, matrix_free=False, layout=0):
         solver.form_dynamic(prob.e, prob.v, prob.rho, prob.alpha1, prob.beta1, prob.theta, prob.dtim)
         solver.build_precon(None, 1e20)
         solver.dynamic_start(prob.r_pp)
+    elif prob.program == 1210:
+        # p1210.f90:93-112: no element matrices, no preconditioner
+        solver.vm_explicit_begin(prob.e, prob.v, prob.sbary, prob.rho, prob.dtim, prob.pload, prob.r_pp)
     elif prob.program == 122:
         # p122.f90:94-114: storkm_pp, the preconditioner with the penalty on this rank's fixed freedoms, zero stresses
         solver.form_km_elastic(prob.e, prob.v)

@@ -15,6 +15,8 @@ are parsed and packed:
   p124_demo_digests.json   SHA-256 of the parsed p124_demo.d / .bnd arrays (25^3 8-node bricks); arrays.npz
                   also holds three of the sixteen golden nodal temperature files (steps 10, 80, 150;
                   float32 of the 5-digit values) and fixtures.json the p124 logs / control files
+  p1210_tiny.json / p1210_tiny_dis.npz   the p1210 deck files and log as lines; eight of its hundred golden
+                  displacement fields (p1210_tiny.dis)
 tests/conftest.py materialises decks and logs from these into a temporary directory with the
 repo's own deck writer (pf_write_deck_p121), which reproduces xx3-tiny.d byte for byte.
 """
@@ -158,9 +160,36 @@ def p129_digests():
     print("p129_tiny digests written")
 
 
+def p1210_golden():
+    """p1210_tiny (examples/5th_ed/p1210: five 20-node bricks, a cantilever; the only p1210 deck the reference ships,
+    with the displacement fields of 100 output steps of a 300 000-step elasto-plastic run in p1210_tiny.dis): the four
+    small deck files and the log as lists of lines, and the golden fields of eight of the hundred steps (float64 of the
+    5-digit values).  Written alone: `python tests/golden/make_golden.py p1210`."""
+    job = f"{REF}/5th_ed/p1210/p1210_tiny"
+    txt = {ext: lines(f"{job}.{ext}") for ext in ("dat", "d", "bnd", "lds", "res")}
+    json.dump(txt, open(f"{HERE}/p1210_tiny.json", "w"), indent=0)
+    dis = lines(job + ".dis")
+    nn, keep, fields = 68, (3000, 6000, 9000, 30000, 60000, 150000, 240000, 300000), {}
+    i = 0
+    while i < len(dis):
+        if dis[i].startswith("*DISPLACEMENT"):
+            step = int(dis[i + 1])
+            if step in keep:
+                fields[str(step)] = np.array([[float(x) for x in l.split()[1:]] for l in dis[i + 2:i + 2 + nn]])
+            i += 2 + nn
+        else:
+            i += 1
+    assert len(fields) == len(keep)
+    np.savez_compressed(f"{HERE}/p1210_tiny_dis.npz", **fields)
+    print("p1210_tiny golden written")
+
+
 if __name__ == "__main__":
     if sys.argv[1:] == ["p129"]:
         p129_digests()
+    elif sys.argv[1:] == ["p1210"]:
+        p1210_golden()
     else:
         main()
         p129_digests()
+        p1210_golden()

@@ -48,6 +48,9 @@ def problem(name, npes, numpe):
         return host.cube_p125(9, 11, 8, aa=.1, bb=.1, cc=.1, dtim=1e-4, nstep=30, npes=npes, numpe=numpe)
     if name == "p129":                   # forced vibration: three matrix sets, one PCG solve per step
         return host.cube_p129(3, 6, 2, .25, .25, .25, e=1.0e4, nip=8, nstep=4, npes=npes, numpe=numpe)
+    if name == "p1210":                  # explicit elasto-plastic dynamics: no PCG, halo exchanges around the element kernel
+        from p1210_util import synthetic
+        return synthetic(host, 4, 9, 3, npes=npes, numpe=numpe)
     if name == "p122":                   # elasto-plasticity, loaded-nodes branch
         p = host.cube_p121(4, 5, 3, 8, aa=1., bb=1., cc=1., e=100.0, v=0.3, npes=npes, numpe=numpe)
         p.program, p.phi, p.c, p.psi = 122, 20.0, 4.0, 0.0
@@ -98,9 +101,16 @@ def transient_specs(s, name, p, full, world):
 
 
 def driver_specs(s, name, p, full, world):
-    """p129 / p122 on N ranks == the oracle emulating the same N ranks."""
+    """p129 / p122 / p1210 on N ranks == the oracle emulating the same N ranks."""
     from parafem_b200 import driver
     lo = p.ieq_start - 1
+    if name == "p1210":
+        ref = oracle.p1210(full.g_coord_pp, full.g_g_pp, full.neq, full.r_pp, full.e, full.v, full.sbary, full.rho, full.dtim,
+                           full.pload, full.nstep, full.npri, npes=world)
+        out = driver.run_p1210(p, s)
+        ok = all(np.array_equal(out["fields"][step], x1[lo:lo + p.neq_pp]) for step, x1, _, _ in ref["snaps"])
+        ok = ok and np.array_equal(out["d2x"], ref["snaps"][-1][3][lo:lo + p.neq_pp])
+        return ok, f"steps={full.nstep}"
     if name == "p129":
         km = oracle.form_km_elastic(full.g_coord_pp, 20, full.nip, full.e, full.v)
         mm = oracle.form_mass(full.g_coord_pp, 20, full.nip, full.rho)
@@ -139,9 +149,9 @@ def main():
         name, _, variant = spec.partition(":")
         p = problem(name, world, rank + 1)
         full = problem(name, 1, 1)
-        if name in ("p124", "p124_fixed", "p125", "p129", "p122"):
+        if name in ("p124", "p124_fixed", "p125", "p129", "p122", "p1210"):
             oracle.set_element_partition(None)
-            ok, info = (driver_specs if name in ("p129", "p122") else transient_specs)(s, name, p, full, world)
+            ok, info = (driver_specs if name in ("p129", "p122", "p1210") else transient_specs)(s, name, p, full, world)
             line = f"[rank {rank}] {spec}: equal={ok} {info}"
             print(line, flush=True)
             if not ok:

@@ -1,0 +1,58 @@
+"""p1210 test helpers: the reference's one p1210 deck materialised from tests/golden/p1210_tiny.json, its golden
+displacement fields, the printed-digit comparison, and a synthetic cantilever that yields within a few hundred steps."""
+import json
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+# The shipped deck (examples/5th_ed/p1210/p1210_tiny.dat) was written for the program's 2010 form: no nres, and its last
+# line `-.003 1.e-6 3.e+5 3.e+3` holds a value that is NOT the load multiplier of today's p1210.f90 (:148,
+# bdylds = bdylds + fext*pload).  dtim / nstep / npri are identified by the golden's own step numbers; the multiplier
+# that reproduces ALL 100 golden fields of the 300 000-step elasto-plastic run to the five digits printed is 2.0.
+GOLDEN_PLOAD = 2.0
+
+
+def write_tiny_deck(dirpath, current_layout=False):
+    txt = json.load(open(os.path.join(HERE, "golden", "p1210_tiny.json")))
+    job = os.path.join(str(dirpath), "p1210_tiny")
+    for ext in ("d", "bnd", "lds"):
+        open(f"{job}.{ext}", "w").write("\n".join(txt[ext]) + "\n")
+    if current_layout:      # read_p1210 as it stands (input.f90:5107-5109)
+        open(job + ".dat", "w").write("'hexahedron'\n2\n1\n5 8 68 8 20 8 1\n1.E-2 4.E+4 .3 3.5E+2\n1.e-6 300000 3000 2.0\n")
+    else:
+        open(job + ".dat", "w").write("\n".join(txt["dat"]) + "\n")
+    return job
+
+
+def golden_fields():
+    z = np.load(os.path.join(HERE, "golden", "p1210_tiny_dis.npz"))
+    return {int(k): z[k] for k in z.files}
+
+
+def nodal(prob, x):
+    """(nn,3) displacements from the global equation vector (0 on restrained freedoms)."""
+    out = np.zeros((prob.nn, 3))
+    m = prob.nf > 0
+    out[m] = x[prob.nf[m] - 1]
+    return out
+
+
+def equal_to_printed_digits(ours, gold, digits=5):
+    """|ours - gold| within one unit of the last of `digits` significant digits of every golden value (it was printed
+    rounded, and the 2010 build's last bits are not ours; measured: <= 0.56 units, except one value of 300 x 204 that
+    sits on a rounding boundary)."""
+    g = np.abs(gold)
+    unit = np.where(g > 0, 10.0 ** (np.floor(np.log10(np.where(g > 0, g, 1.0))) - (digits - 1)), 0.0)
+    # freedoms on the symmetry plane are zero up to rounding noise in both runs (golden -1.9659E-18, here -3.4e-19)
+    floor = 1e-9 * g.max()
+    return bool(np.all(np.abs(ours - gold) <= np.maximum(unit, floor)))
+
+
+def synthetic(host, nxe=4, nye=5, nze=3, npes=1, numpe=1, nstep=240, npri=80):
+    """p12meshgen's p121 cube (20-node bricks, restrained sides and base, 100 units of load on the top patch) run as a
+    p1210 problem: density and time step inside the explicit stability limit, a yield stress the Gauss points under the
+    load exceed within the first hundred steps (so the vmpl branch is exercised)."""
+    p = host.cube_p121(nxe, nye, nze, 20, aa=1., bb=1., cc=1., e=100.0, v=0.3, npes=npes, numpe=numpe)
+    p.program, p.rho, p.sbary, p.dtim, p.pload, p.nstep, p.npri, p.nres = 1210, 1.0, 4.0, 2.0e-3, 1.0, nstep, npri, 1
+    return p

@@ -1,0 +1,62 @@
+"""p1210 on the device (pf_vm_explicit_begin / _steps / _get): explicit elasto-plastic (von Mises) dynamics with a lumped
+mass.  No transcendental function but sqrt, no reduction: the device is compared with the oracle BIT FOR BIT, and with the
+reference's golden displacement fields (p1210_tiny.dis) to the digits printed."""
+import numpy as np
+import pytest
+
+import oracle
+from parafem_b200 import driver, host, solver
+from p1210_util import GOLDEN_PLOAD, equal_to_printed_digits, golden_fields, nodal, synthetic, write_tiny_deck
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    s = solver.Solver(0, 1, 0)
+    yield s
+    s.close()
+
+
+def test_tiny_deck_equals_oracle_and_golden(gpu, tmp_path):
+    p = host.read_deck_p1210(write_tiny_deck(tmp_path))
+    p.pload = GOLDEN_PLOAD                       # tests/p1210_util.py: what the deck's last line does not say
+    nstep = 60000                                # 20 of the golden's 100 output steps; yield starts before step 30000
+    res = driver.run_p1210(p, gpu, nstep=nstep)
+    ref = oracle.p1210(p.g_coord_pp, p.g_g_pp, p.neq, p.r_pp, p.e, p.v, p.sbary, p.rho, p.dtim, p.pload, nstep, p.npri)
+    assert np.array_equal(gpu.vm_explicit_get(mass=True)[3], ref["mm"])
+    assert len(res["fields"]) == 20
+    for step, x1, d1, d2 in ref["snaps"]:
+        assert np.array_equal(res["fields"][step], x1), step
+    assert np.array_equal(res["x"], ref["snaps"][-1][1]) and np.array_equal(res["d1x"], ref["snaps"][-1][2])
+    assert np.array_equal(res["d2x"], ref["snaps"][-1][3])
+    gold = golden_fields()
+    for step in (3000, 6000, 9000, 30000, 60000):
+        assert equal_to_printed_digits(nodal(p, res["fields"][step]), gold[step]), step
+    # the log: header, the t = 0 row and one row per output step, in the reference's E12.4
+    out = tmp_path / "p1210_tiny.res"
+    driver.write_res_p1210(str(out), p, res)
+    lines = out.read_text().splitlines()
+    assert lines[1] == "There are           68 nodes            8 restrained and          180 equations"
+    assert lines[3] == "  Time      Displacement  Velocity   Acceleration " and lines[4].split() == ["0.0000E+00"] * 4
+    assert len(lines) == 4 + 1 + 20 + 1 and lines[5].startswith("  0.3000E-02")
+
+
+@pytest.mark.parametrize("shape", [(4, 5, 3), (3, 7, 2)])
+def test_synthetic_yielding_case_equals_oracle(gpu, shape):
+    p = synthetic(host, *shape)
+    res = driver.run_p1210(p, gpu)
+    ref = oracle.p1210(p.g_coord_pp, p.g_g_pp, p.neq, p.r_pp, p.e, p.v, p.sbary, p.rho, p.dtim, p.pload, p.nstep, p.npri)
+    for step, x1, d1, d2 in ref["snaps"]:
+        assert np.array_equal(res["fields"][step], x1), step
+    assert np.array_equal(res["d1x"], ref["snaps"][-1][2]) and np.array_equal(res["d2x"], ref["snaps"][-1][3])
+    el = oracle.p1210(p.g_coord_pp, p.g_g_pp, p.neq, p.r_pp, p.e, p.v, 1e30, p.rho, p.dtim, p.pload, p.nstep, p.npri)
+    assert np.abs(el["snaps"][-1][1] - res["x"]).max() > 1e-3 * np.abs(res["x"]).max()      # it did yield
+
+
+def test_needs_twenty_node_bricks(gpu):
+    from parafem_b200 import PfError
+    p = host.cube_p121(3, 3, 3, 8, aa=1., bb=1., cc=1.)
+    p.program, p.rho, p.sbary, p.dtim, p.pload = 1210, 1.0, 4.0, 1e-3, 1.0
+    with pytest.raises(PfError):
+        solver.setup_problem(gpu, p)
