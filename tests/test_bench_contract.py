@@ -6,7 +6,7 @@ import os
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DEFAULT_LINE = "r02_bench_default_n125_tensor.json"     # the default run after the tensor-core matrix-free kernel landed
+DEFAULT_LINE = "r02_bench_default_n125_final.json"      # the default run of the last GPU visit (scripts/gpu_r2_16.sh)
 
 
 def last_line(name):
@@ -35,6 +35,7 @@ def test_default_line_has_every_contract_key():
     assert r["achieved"] == pytest.approx(r["algorithmic_bytes_per_launch"] / (r["avg_launch_ms"] * 1e-3) / 1e9, rel=1e-9)
     assert r["algorithmic_bytes_per_launch"] == 1953125 * 3600 * 8 and r["launches_timed"] == d["steps"]
     assert r["traffic"] >= r["algorithmic_bytes_per_launch"]                # ncu dram bytes per launch
+    assert abs(r["back_to_back"]["frac"] / r["frac"] - 1.0) < 0.05          # K launches between one pair of events agree
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["unit"] == d["unit"] and c["value"] > 0 and c["sample"]
     k = d["clocks"]
@@ -102,6 +103,13 @@ def test_variant_lines_carry_their_own_roofline():
         assert r["frac"] == pytest.approx(r["achieved"] / r["peak"], rel=1e-12)
         assert r["frac_of_dfma_peak"] == pytest.approx(r["achieved"] / r["peak_dfma"], rel=1e-12)
         assert r["achieved"] == pytest.approx(r["algorithmic_flops_per_launch"] / (r["avg_launch_ms"] * 1e-3) / 1e12, rel=1e-9)
+        # the same kernel timed back to back, and its HBM side (factors / coordinates, indices, products, right-hand sides)
+        assert abs(r["back_to_back"]["avg_launch_ms"] / r["avg_launch_ms"] - 1.0) < 0.1
+        hs = r["hbm_side"]
+        assert hs["bound"] == "hbm" and 0.3 < hs["frac"] < 1.0 and hs["frac"] == pytest.approx(hs["achieved"] / hs["peak"], rel=1e-12)
+    hs = v["matrix_free_geometric_factors"]["roofline"]["hbm_side"]
+    assert hs["bytes_per_element"] == 640 + 720 and abs(hs["traffic"] / hs["algorithmic_bytes_per_launch"] - 1.0) < 0.05
+    assert v["matrix_free_rebuilt_from_coordinates"]["value"] >= 15000                     # config E as named
     assert v["matrix_free_geometric_factors"]["roofline"]["flops_per_element"] == 6696      # as executed, padding not counted
     assert v["matrix_free_geometric_factors"]["roofline"]["frac"] >= 0.65
     assert v["matrix_free_geometric_factors"]["value"] >= 19000
