@@ -173,6 +173,9 @@ MODULE parafem_gpu
     INTEGER(c_int) FUNCTION pf_vm_explicit_begin(h,e,v,sbary,rho,dtim,pload,fext_pp) BIND(C,name='pf_vm_explicit_begin')
       IMPORT; TYPE(c_ptr),VALUE :: h,fext_pp; REAL(c_double),VALUE :: e,v,sbary,rho,dtim,pload
     END FUNCTION
+    INTEGER(c_int) FUNCTION pf_vm_explicit_set_form(h,form) BIND(C,name='pf_vm_explicit_set_form')
+      IMPORT; TYPE(c_ptr),VALUE :: h; INTEGER(c_int),VALUE :: form    ! 0: elements_2 as written, 1: tensor-core operator form
+    END FUNCTION
     INTEGER(c_int) FUNCTION pf_vm_explicit_steps(h,nsteps,elapsed_ms) BIND(C,name='pf_vm_explicit_steps')
       IMPORT; TYPE(c_ptr),VALUE :: h; INTEGER(c_int),VALUE :: nsteps; REAL(c_double) :: elapsed_ms
     END FUNCTION

@@ -197,6 +197,10 @@ int pf_explicit_steps(pf_handle h, int nsteps, double *elapsed_ms);
  *   pf_vm_explicit_get   : x1_pp, d1x1_pp, d2x1_pp, mm_pp (any may be NULL).                                      */
 int pf_vm_explicit_begin(pf_handle h, double e, double v, double sbary, double rho, double dtim, double pload,
                          const double *fext_pp);
+/* form 0 (default): the Gauss-point loop as p1210.f90:120-147 writes it, bit for bit (k_p1210_elements); form 1: the
+ * same update in operator form on the FP64 tensor cores (the matrix-free kernel's pipeline with the elasto-plastic
+ * point update in the middle) -- another rounding (1e-15), ~20x faster, pinned to the same golden fields.        */
+int pf_vm_explicit_set_form(pf_handle h, int form);
 int pf_vm_explicit_steps(pf_handle h, int nsteps, double *elapsed_ms);
 int pf_vm_explicit_get(pf_handle h, double *x1_pp, double *d1x1_pp, double *d2x1_pp, double *mm_pp);
 /* --- p129: forced vibration, implicit theta method, consistent mass ----------

@@ -494,9 +494,12 @@ def p129(km, mm, g_g, neq, fext, theta, omega, alpha1, beta1, nstep, tol, limit,
     return dict(rows=rows, x=x0, d1x=d1x0, d2x=d2x0, fields=fields, dtim=dtim)
 
 
-def p1210(g_coord_pp, g_g, neq, fext, e, v, sbary, rho, dtim, pload, nstep, npri, npes=1):
+def p1210(g_coord_pp, g_g, neq, fext, e, v, sbary, rho, dtim, pload, nstep, npri, npes=1, form=0):
     """p1210.f90 on global arrays (orc_p1210_run): explicit elasto-plastic (von Mises) dynamics with the lumped mass of
-    :93-104.  -> dict(mm, snaps = [(step, x1, d1x1, d2x1)] every npri steps)."""
+    :93-104.  form 0: elements_2 as the reference writes it (the arithmetic of k_p1210_elements); form 1: the operator
+    form of the tensor-core kernel k_p1210_mf (another rounding).  -> dict(mm, snaps = [(step, x1, d1x1, d2x1)] every
+    npri steps)."""
+    lib().orc_set_p1210_form(int(form))
     g, gg, fe = _f64(g_coord_pp), _i32(g_g), _f64(fext)
     nels, nod = g.shape[0], g.shape[2]
     nout = nstep // npri

@@ -1415,6 +1415,109 @@ int orc_p1210_elements(int64_t nels, int nod, int nip, const double *g_coord_pp,
   return 0;
 }
 
+/* The same update in OPERATOR FORM -- the arithmetic of the tensor-core kernel k_p1210_mf (the matrix-free kernel
+ * k_apply_mf4 with p1210's Gauss-point update in the middle), stated as plain C:
+ *   jac / H: node-ascending fma chains from 0.0; inverse = adjugate x ONE reciprocal (invert3_recip); f = det*w
+ *   G = inv H (product + two fma), eps = beemat's rows of G minus etensor
+ *   sigma_el = D eps with deemat's structural zeros left out (3-term chains, single products), stressv = sigma_el + tensor
+ *   yield (dsbar - sbary >= 0): fac, the scaled-back stress, vmpl and dee - fac*pl exactly as elements_2; then
+ *       sigma(r) = dee'(r,0)*eps(0) + fma chain over q = 1..5, + tensor;   no yield: sigma = stressv
+ *   tensor = sigma, etensor += eps;  S = sigma*f;  T = inv^T S (product + two fma)
+ *   u_c(m) = ONE fma chain from 0.0 over (h | b | q), Gauss point 2q+h (the k order of the phase-3 mma);  utemp = 0 - u
+ * A different rounding of elements_2 (p1210.f90:120-147), pinned to the same golden fields. */
+int orc_p1210_elements_mf(int64_t nels, int nod, int nip, const double *g_coord_pp, double e, double v, double sbary,
+                          const double *pmul, double *etensor, double *tensor, double *utemp) {
+  if (nod != 20 || nip != 8) return 1;
+  const int ntot = 3 * nod;
+  double points[81], weights[27], dee0[36], der[8][60], d3[60];
+  orc_sample_hex(nip, points, weights);
+  orc_deemat6(dee0, e, v);
+  for (int ig = 0; ig < nip; ++ig) {
+    orc_shape_der(nod, points, nip, ig, d3);
+    for (int m = 0; m < nod; ++m)
+      for (int a = 0; a < 3; ++a) der[ig][a * 20 + m] = d3[m * 3 + a];
+  }
+#pragma omp parallel for schedule(static) if (nels > 256)
+  for (int64_t iel = 0; iel < nels; ++iel) {
+    const double *coord = g_coord_pp + iel * nod * 3, *pm = pmul + iel * ntot;
+    double T[8][9];
+    for (int ig = 0; ig < 8; ++ig) {
+      double *et = etensor + (iel * nip + ig) * 6, *te = tensor + (iel * nip + ig) * 6;
+      double jac[9], inv[9], H[9], G[9], sigma[6], stressv[6], dee[36], pl[36];
+      for (int b = 0; b < 3; ++b)
+        for (int a = 0; a < 3; ++a) {
+          double s = 0.0;
+          for (int m = 0; m < nod; ++m) s = fma(der[ig][a * 20 + m], coord[b * nod + m], s);
+          jac[b * 3 + a] = s;
+        }
+      const double det = orc_determinant3(jac);
+      memcpy(inv, jac, sizeof inv);
+      invert3_recip(inv);
+      const double f = det * weights[ig];
+      for (int b = 0; b < 3; ++b)
+        for (int c = 0; c < 3; ++c) {
+          double s = 0.0;
+          for (int m = 0; m < nod; ++m) s = fma(der[ig][b * 20 + m], pm[3 * m + c], s);
+          H[b * 3 + c] = s;
+        }
+      for (int a = 0; a < 3; ++a)
+        for (int c = 0; c < 3; ++c) {
+          double s = inv[a] * H[c];
+          s = fma(inv[3 + a], H[3 + c], s);
+          s = fma(inv[6 + a], H[6 + c], s);
+          G[a * 3 + c] = s;
+        }
+      double eps[6] = {G[0], G[4], G[8], G[3] + G[1], G[7] + G[5], G[6] + G[2]};
+      for (int r = 0; r < 6; ++r) eps[r] = eps[r] - et[r];
+      for (int r = 0; r < 3; ++r) {
+        double s = dee0[r] * eps[0];
+        s = fma(dee0[6 + r], eps[1], s);
+        s = fma(dee0[12 + r], eps[2], s);
+        sigma[r] = s;
+      }
+      for (int r = 3; r < 6; ++r) sigma[r] = dee0[r * 6 + r] * eps[r];
+      for (int r = 0; r < 6; ++r) stressv[r] = sigma[r] + te[r];
+      const double fnew = dsbar6(stressv) - sbary;
+      if (fnew >= 0.0) {
+        const double fy = dsbar6(te) - sbary, fac = fnew / (fnew - fy);
+        for (int r = 0; r < 6; ++r) stressv[r] = te[r] + (1.0 - fac) * sigma[r];
+        vmpl6(e, v, stressv, pl);
+        for (int q = 0; q < 36; ++q) dee[q] = dee0[q] - fac * pl[q];
+        for (int r = 0; r < 6; ++r) {
+          double s = dee[r] * eps[0];
+          for (int q = 1; q < 6; ++q) s = fma(dee[q * 6 + r], eps[q], s);
+          sigma[r] = s + te[r];
+        }
+      } else {
+        for (int r = 0; r < 6; ++r) sigma[r] = stressv[r];
+      }
+      for (int r = 0; r < 6; ++r) { te[r] = sigma[r]; et[r] = et[r] + eps[r]; }
+      double sg[6];
+      for (int r = 0; r < 6; ++r) sg[r] = sigma[r] * f;
+      const double S[9] = {sg[0], sg[3], sg[5], sg[3], sg[1], sg[4], sg[5], sg[4], sg[2]};
+      for (int b = 0; b < 3; ++b)
+        for (int c = 0; c < 3; ++c) {
+          double s = inv[b * 3] * S[c];
+          s = fma(inv[b * 3 + 1], S[3 + c], s);
+          s = fma(inv[b * 3 + 2], S[6 + c], s);
+          T[ig][b * 3 + c] = s;
+        }
+    }
+    for (int m = 0; m < nod; ++m)
+      for (int c = 0; c < 3; ++c) {
+        double s = 0.0;
+        for (int h = 0; h < 2; ++h)
+          for (int b = 0; b < 3; ++b)
+            for (int q = 0; q < 4; ++q) s = fma(T[2 * q + h][b * 3 + c], der[2 * q + h][b * 20 + m], s);
+        utemp[iel * ntot + 3 * m + c] = 0.0 - s;
+      }
+  }
+  return 0;
+}
+
+static int g_p1210_form = 0;   /* 0: elements_2 as written (orc_p1210_elements); 1: operator form (orc_p1210_elements_mf) */
+void orc_set_p1210_form(int form) { g_p1210_form = form ? 1 : 0; }
+
 /* The whole program on global arrays over npes emulated ranks (the partition only orders the scatter's sums).
  * mm_out (neq) = the assembled lumped mass; snap holds, for every npri-th step, x1 / d1x1 / d2x1 (3 x neq doubles). */
 int orc_p1210_run(int64_t nels, int nod, int nip, const double *g_coord_pp, const int32_t *g_g, int64_t neq,
@@ -1439,7 +1542,8 @@ int orc_p1210_run(int64_t nels, int nod, int nip, const double *g_coord_pp, cons
   for (int jj = 1; jj <= nstep; ++jj) {
     for (int64_t i = 0; i < neq; ++i) x1[i] = x1[i] + (dtim * d1[i]) + (0.5 * (dtim * dtim) * d2[i]);   /* p1210.f90:117 */
     orc_gather(ntot, nels, g_g, x1, pmul);
-    orc_p1210_elements(nels, nod, nip, g_coord_pp, e, v, sbary, pmul, et, te, utemp);
+    if (g_p1210_form) orc_p1210_elements_mf(nels, nod, nip, g_coord_pp, e, v, sbary, pmul, et, te, utemp);
+    else orc_p1210_elements(nels, nod, nip, g_coord_pp, e, v, sbary, pmul, et, te, utemp);
     ranks_scatter(R, ntot, g_g, utemp, bdy);
     for (int64_t i = 0; i < neq; ++i) {                       /* :148-150 */
       double b = bdy[i] + fext[i] * pload;

@@ -89,6 +89,7 @@ SIGNATURES = {
     "pf_get_kernel_ms": (c_int, [vp, c_int, P(c_dbl), P(c_i64)]),
     "pf_kernel_launches": (c_i64, [vp]),
     "pf_vm_explicit_begin": (c_int, [vp, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, vp]),
+    "pf_vm_explicit_set_form": (c_int, [vp, c_int]),
     "pf_vm_explicit_steps": (c_int, [vp, c_int, P(c_dbl)]),
     "pf_vm_explicit_get": (c_int, [vp, vp, vp, vp, vp]),
     "pf_measure_fp64": (c_int, [vp, P(c_dbl)]),

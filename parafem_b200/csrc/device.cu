@@ -148,6 +148,7 @@ struct pf_ctx {
   // p1210 (explicit elasto-plastic dynamics): strains / stresses of every Gauss point, lumped mass, external loads,
   // velocity and acceleration; the displacement lives in the owned part of p_ext
   bool vm_explicit = false;
+  int vm_form = 0;          // 0: elements_2 as written (k_p1210_elements); 1: operator form on the tensor cores (k_p1210_mf)
   VmParams vm_par;
   double vm_dtim = 0.0, vm_pload = 0.0;
   DevBuf<double> vm_eten, vm_ten, vm_mm, vm_fext, vm_d1, vm_d2;
@@ -548,7 +549,8 @@ int launch_mf4_tt(pf_handle h, const double *pvec, const State *st, PeerTable *T
   if (int rc_ = ensure_smem(h, kern, Cfg::kSmem)) return rc_;
   const int64_t npass = (h->nels + Cfg::EPP - 1) / Cfg::EPP;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (npass + Cfg::NCONS - 1) / Cfg::NCONS));
-  kern<<<grid, Cfg::kThreads, Cfg::kSmem, h->stream>>>(h->coord.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st, h->geom.p, T);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmem, h->stream>>>(h->coord.p, h->ggl.p, pvec, h->utemp.p, (long long)h->nels, st, h->geom.p, T,
+                                                       nullptr, nullptr, VmParams{0.0, 0.0, 0.0});
   h->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -1816,6 +1818,13 @@ int pf_vm_explicit_begin(pf_handle h, double e, double v, double sbary, double r
   return 0;
 }
 
+int pf_vm_explicit_set_form(pf_handle h, int form) {
+  int rc = need_device(h); if (rc) return rc;
+  NEED(form == 0 || form == 1, "form must be 0 (elements_2 as written) or 1 (operator form, FP64 tensor cores)");
+  h->vm_form = form;
+  return 0;
+}
+
 int pf_vm_explicit_steps(pf_handle h, int nsteps, double *elapsed_ms) {
   int rc = need_device(h); if (rc) return rc;
   NEED(h->vm_explicit && nsteps >= 0, "needs pf_vm_explicit_begin and nsteps >= 0");
@@ -1835,8 +1844,20 @@ int pf_vm_explicit_steps(pf_handle h, int nsteps, double *elapsed_ms) {
     if ((rc = halo_forward(h, h->p_ext.p, nullptr))) return rc;
     if (h->nels > 0) {
       Scope sc(h, K_MATVEC);
-      k_p1210_elements<20><<<egrid, 64, 0, h->stream>>>(h->coord.p, h->ggl.p, h->p_ext.p, h->vm_eten.p, h->vm_ten.p, h->utemp.p,
-                                                        (long long)h->nels, h->vm_par);
+      if (h->vm_form == 1) {
+        // operator form on the FP64 tensor cores: k_apply_mf4's pipeline with p1210's Gauss-point update (8 consumer warps
+        // of 224 registers; coordinates -> Jacobian every step, as the reference recomputes it)
+        using Cfg = Mf4Cfg<20, 8>;
+        auto kern = k_apply_mf4<20, true, 0, 8, 1>;
+        if ((rc = ensure_smem(h, kern, Cfg::kSmem))) return rc;
+        const int64_t npass = (h->nels + Cfg::EPP - 1) / Cfg::EPP;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (npass + Cfg::NCONS - 1) / Cfg::NCONS));
+        kern<<<grid, Cfg::kThreads, Cfg::kSmem, h->stream>>>(h->coord.p, h->ggl.p, h->p_ext.p, h->utemp.p, (long long)h->nels, nullptr,
+                                                             nullptr, nullptr, h->vm_eten.p, h->vm_ten.p, h->vm_par);
+      } else {
+        k_p1210_elements<20><<<egrid, 64, 0, h->stream>>>(h->coord.p, h->ggl.p, h->p_ext.p, h->vm_eten.p, h->vm_ten.p, h->utemp.p,
+                                                          (long long)h->nels, h->vm_par);
+      }
       h->launches++;
     }
     if ((rc = launch_scatter(h, nullptr, false, h->u_ext.p))) return rc;

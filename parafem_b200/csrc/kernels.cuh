@@ -2283,6 +2283,84 @@ k_apply_mf3(const double *__restrict__ g_coord, const int *__restrict__ ggl, con
   bulk_wait_all();                                           // shared memory must outlive the stores
 }
 
+// p1210's Gauss-point update in operator form (orc_p1210_elements_mf): H(b,c) at [b*3+c], inv = jac^-1, f = det*w, the
+// point's etensor / tensor (6 doubles each, updated in place) -> T(b,c).  Strain from the displacement gradient minus
+// etensor, elastic trial stress (deemat's zeros left out), on yield the scaled-back stress -> vmpl -> dee - fac*pl formed
+// entry by entry inside the stress sum, stress * det*w -> T = jac^-T S.
+struct VmParams {
+  double e, v, sbary;
+};
+// second invariant as invar forms it (new_library.f90:1891-1897): dsbar = sqrt(3)*sqrt(d2)
+__device__ __forceinline__ double vm_dsbar(const double *s) {
+  const double d2 = ((s[0] - s[1]) * (s[0] - s[1]) + (s[1] - s[2]) * (s[1] - s[2]) + (s[2] - s[0]) * (s[2] - s[0])) / 6.0 +
+                    s[3] * s[3] + s[4] * s[4] + s[5] * s[5];
+  return sqrt(3.0) * sqrt(d2);
+}
+__device__ __forceinline__ void vm_point_mid(const double *H, const double *inv, double f, double *et, double *te,
+                                             const VmParams &P, double *T) {
+  double G[9];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double s = inv[a] * H[c];
+      s = fma(inv[3 + a], H[3 + c], s);
+      s = fma(inv[6 + a], H[6 + c], s);
+      G[a * 3 + c] = s;
+    }
+  double eps[6] = {G[0], G[4], G[8], G[3] + G[1], G[7] + G[5], G[6] + G[2]};
+  double sigma[6], stressv[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) eps[r] = eps[r] - et[r];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    double s = c_tab.dee[r] * eps[0];
+    s = fma(c_tab.dee[6 + r], eps[1], s);
+    s = fma(c_tab.dee[12 + r], eps[2], s);
+    sigma[r] = s;
+  }
+#pragma unroll
+  for (int r = 3; r < 6; ++r) sigma[r] = c_tab.dee[r * 6 + r] * eps[r];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) stressv[r] = sigma[r] + te[r];
+  const double fnew = vm_dsbar(stressv) - P.sbary;
+  if (fnew >= 0.0) {                                              // yield is violated
+    const double fy = vm_dsbar(te) - P.sbary, fac = fnew / (fnew - fy);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) stressv[r] = te[r] + (1.0 - fac) * sigma[r];
+    const double sx = stressv[0], sy = stressv[1], sz = stressv[2], txy = stressv[3], tyz = stressv[4], tzx = stressv[5];
+    const double dsb = sqrt((sx - sy) * (sx - sy) + (sy - sz) * (sy - sz) + (sz - sx) * (sz - sx) + 6.0 * (txy * txy) +
+                            6.0 * (tyz * tyz) + 6.0 * (tzx * tzx)) / sqrt(2.0);
+    const double ee = 1.5 * P.e / ((1.0 + P.v) * dsb * dsb);
+    const double term[6] = {(2.0 * sx - sy - sz) / 3.0, (2.0 * sy - sz - sx) / 3.0, (2.0 * sz - sx - sy) / 3.0, txy, tyz, tzx};
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      double s = (c_tab.dee[r] - fac * (term[r] * term[0] * ee)) * eps[0];
+#pragma unroll
+      for (int q = 1; q < 6; ++q) s = fma(c_tab.dee[q * 6 + r] - fac * (term[r] * term[q] * ee), eps[q], s);
+      sigma[r] = s + te[r];
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) sigma[r] = stressv[r];
+  }
+#pragma unroll
+  for (int r = 0; r < 6; ++r) { te[r] = sigma[r]; et[r] = et[r] + eps[r]; }
+  double sg[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) sg[r] = sigma[r] * f;
+  const double S[9] = {sg[0], sg[3], sg[5], sg[3], sg[1], sg[4], sg[5], sg[4], sg[2]};
+#pragma unroll
+  for (int b = 0; b < 3; ++b)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double s = inv[b * 3] * S[c];
+      s = fma(inv[b * 3 + 1], S[3 + c], s);
+      s = fma(inv[b * 3 + 2], S[6 + c], s);
+      T[b * 3 + c] = s;
+    }
+}
+
 // ----------------------------------------------------------------------------
 // k_apply_mf4: k_apply_mf3's arithmetic, WARP-SPECIALISED.  ncu of k_apply_mf3 (profiles/r02_mf_tensor_kernel.md): every
 // warp alternates between moving data (index loads -> gathers -> staging, LSU-bound, no FP64) and arithmetic, the DMMA
@@ -2325,10 +2403,13 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
 }
 __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
-template <int NOD, bool GATHER, int GEOM, int NCW>
+// MID 1 (k_p1210_mf): p1210's elasto-plastic Gauss-point update (vm_point_mid) instead of the elastic one, the points'
+// etensor_pp / tensor_pp (6, nip, nels) read and written in place, and utemp = 0 - products (elements_2 of p1210.f90).
+template <int NOD, bool GATHER, int GEOM, int NCW, int MID = 0>
 __global__ void __launch_bounds__(Mf4Cfg<NOD, NCW>::kThreads, 1)
 k_apply_mf4(const double *__restrict__ g_coord, const int *__restrict__ ggl, const double *__restrict__ pvec,
-            double *__restrict__ utemp, long long nels, const State *st, const double *__restrict__ geom, PeerTable *T) {
+            double *__restrict__ utemp, long long nels, const State *st, const double *__restrict__ geom, PeerTable *T,
+            double *etensor = nullptr, double *tensor = nullptr, VmParams vmp = VmParams{0.0, 0.0, 0.0}) {
   using Cfg = Mf4Cfg<NOD, NCW>;
   constexpr int NTOT = Cfg::NTOT, ROW = Cfg::kRow, EPP = Cfg::EPP, KS1 = Cfg::KS1, NT3 = Cfg::NT3, NF = Cfg::NF, S = Cfg::S;
   constexpr int NCONS = Cfg::NCONS, NPROD = Cfg::NPROD, NIDX = Cfg::NIDX, BP = Cfg::kBarsPer, KPW = Cfg::KPW;
@@ -2555,7 +2636,30 @@ k_apply_mf4(const double *__restrict__ g_coord, const int *__restrict__ ggl, con
         for (int b = 0; b < 3; ++b)
 #pragma unroll
           for (int c2 = 0; c2 < 3; ++c2) Hm[b * 3 + c2] = H[c2][b][h];
-        mf_point_mid_iso(Hm, gq + 10 * h, gq[10 * h + 9], Tm[h]);
+        if (MID == 1) {
+          if (r < ne) {
+            // the point's 2 x 48 contiguous bytes of state: three 16-byte words each way
+            double2 *ep = reinterpret_cast<double2 *>(etensor + ((e0 + r) * 8 + (2 * q + h)) * 6);
+            double2 *tp = reinterpret_cast<double2 *>(tensor + ((e0 + r) * 8 + (2 * q + h)) * 6);
+            double et[6], te[6];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const double2 a = ep[j], b2 = tp[j];
+              et[2 * j] = a.x; et[2 * j + 1] = a.y; te[2 * j] = b2.x; te[2 * j + 1] = b2.y;
+            }
+            vm_point_mid(Hm, gq + 10 * h, gq[10 * h + 9], et, te, vmp, Tm[h]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              ep[j] = make_double2(et[2 * j], et[2 * j + 1]);
+              tp[j] = make_double2(te[2 * j], te[2 * j + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int z = 0; z < 9; ++z) Tm[h][z] = 0.0;
+          }
+        } else {
+          mf_point_mid_iso(Hm, gq + 10 * h, gq[10 * h + 9], Tm[h]);
+        }
       }
       if (ps + stride < npass) load_pre(ps + stride);          // the next pass's factors / coordinates
       // phase 3: U[c2][nt][h'] = u_c2(m = 8nt + 2q + h') of element r
@@ -2582,7 +2686,7 @@ k_apply_mf4(const double *__restrict__ g_coord, const int *__restrict__ ggl, con
           const int m = 8 * nt + 2 * q + hh;
           if (m < NOD) {
 #pragma unroll
-            for (int c2 = 0; c2 < 3; ++c2) rows[r * ROW + 3 * m + c2] = U[c2][nt][hh];
+            for (int c2 = 0; c2 < 3; ++c2) rows[r * ROW + 3 * m + c2] = MID == 1 ? 0.0 - U[c2][nt][hh] : U[c2][nt][hh];
           }
         }
       fence_proxy_async();                                     // my generic stores before the async proxy reads them
@@ -2799,15 +2903,6 @@ k_p122_elements(const double *__restrict__ g_coord, const int *__restrict__ ggl,
 // p1210 (programs/5th_ed/p1210/p1210.f90): forced vibration of an elastic-plastic (von Mises) solid, lumped mass,
 // explicit integration.  No PCG: a time step is gather -> Gauss-point stress update -> scatter -> three vector updates.
 // ----------------------------------------------------------------------------
-struct VmParams {
-  double e, v, sbary;
-};
-// second invariant as invar forms it (new_library.f90:1891-1897): dsbar = sqrt(3)*sqrt(d2)
-__device__ __forceinline__ double vm_dsbar(const double *s) {
-  const double d2 = ((s[0] - s[1]) * (s[0] - s[1]) + (s[1] - s[2]) * (s[1] - s[2]) + (s[2] - s[0]) * (s[2] - s[0])) / 6.0 +
-                    s[3] * s[3] + s[4] * s[4] + s[5] * s[5];
-  return sqrt(3.0) * sqrt(d2);
-}
 // elements_1 (p1210.f90:93-104): one thread per element, emm(ntot) -> utemp (mm_tmp)
 __global__ void k_p1210_mass(const double *__restrict__ g_coord, double *__restrict__ utemp, long long nels, double rho) {
   constexpr int NOD = 20;

@@ -227,6 +227,10 @@ class Solver:
         """p1210.f90:93-112 after setup_mesh: element tables, lumped mass, external loads, zero state."""
         self._ck(lib().pf_vm_explicit_begin(self._h, e, v, sbary, rho, dtim, pload, ptr(f64(fext_pp))), "pf_vm_explicit_begin")
 
+    def vm_explicit_set_form(self, form):
+        """0: elements_2 as the reference writes it; 1: operator form on the FP64 tensor cores."""
+        self._ck(lib().pf_vm_explicit_set_form(self._h, int(form)), "pf_vm_explicit_set_form")
+
     def vm_explicit_steps(self, nsteps):
         """nsteps passes of time_steps (p1210.f90:114-150) on the device. -> elapsed_ms"""
         ms = C.c_double()
@@ -366,6 +370,7 @@ def setup_problem(solver, prob, matrix_free=False, layout=0):
     elif prob.program == 1210:
         # p1210.f90:93-112: no element matrices, no preconditioner
         solver.vm_explicit_begin(prob.e, prob.v, prob.sbary, prob.rho, prob.dtim, prob.pload, prob.r_pp)
+        solver.vm_explicit_set_form(getattr(prob, "form", 0))
     elif prob.program == 122:
         # p122.f90:94-114: storkm_pp, the preconditioner with the penalty on this rank's fixed freedoms, zero stresses
         solver.form_km_elastic(prob.e, prob.v)

@@ -105,8 +105,9 @@ def driver_specs(s, name, p, full, world):
     from parafem_b200 import driver
     lo = p.ieq_start - 1
     if name == "p1210":
+        form = getattr(p, "form", 0)             # "p1210:mf" = the operator form on the tensor cores
         ref = oracle.p1210(full.g_coord_pp, full.g_g_pp, full.neq, full.r_pp, full.e, full.v, full.sbary, full.rho, full.dtim,
-                           full.pload, full.nstep, full.npri, npes=world)
+                           full.pload, full.nstep, full.npri, npes=world, form=form)
         out = driver.run_p1210(p, s)
         ok = all(np.array_equal(out["fields"][step], x1[lo:lo + p.neq_pp]) for step, x1, _, _ in ref["snaps"])
         ok = ok and np.array_equal(out["d2x"], ref["snaps"][-1][3][lo:lo + p.neq_pp])
@@ -151,6 +152,8 @@ def main():
         full = problem(name, 1, 1)
         if name in ("p124", "p124_fixed", "p125", "p129", "p122", "p1210"):
             oracle.set_element_partition(None)
+            if name == "p1210" and variant == "mf":
+                p.form = 1
             ok, info = (driver_specs if name in ("p129", "p122", "p1210") else transient_specs)(s, name, p, full, world)
             line = f"[rank {rank}] {spec}: equal={ok} {info}"
             print(line, flush=True)

@@ -36,6 +36,6 @@ def test_multirank_equals_oracle(n, transport):
            "hex20:sym", "hex8:sym", "p123:sym", "hex20_thin:mf2", "hex20:mf1", "hex8:mf2",
            "hex20_psize", "hex20_psize:sym", "p124", "p124_fixed", "p125", "hex20_mat",
            "hex20_shuffled", "hex20_shuffled:sym", "hex20_shuffled:mf2", "p123_fixed_shuffled", "tet4", "tet4_scalar",
-           "p129", "p122", "p1210"]
+           "p129", "p122", "p1210", "p1210:mf"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     assert res.returncode == 0 and "MRANK_OK" in res.stdout, res.stdout[-4000:] + res.stderr[-4000:]

@@ -54,6 +54,36 @@ def test_synthetic_yielding_case_equals_oracle(gpu, shape):
     assert np.abs(el["snaps"][-1][1] - res["x"]).max() > 1e-3 * np.abs(res["x"]).max()      # it did yield
 
 
+def test_operator_form_on_the_tensor_cores(gpu, tmp_path):
+    """pf_vm_explicit_set_form(1): the Gauss-point update inside the matrix-free tensor-core pipeline (k_apply_mf4<MID 1>).
+    Another rounding of elements_2 -- bit-equal to ITS oracle mirror (orc_p1210_elements_mf), 1e-12 from the form the
+    reference writes, and the golden fields to the digits printed."""
+    p = host.read_deck_p1210(write_tiny_deck(tmp_path))
+    p.pload, p.form = GOLDEN_PLOAD, 1
+    nstep = 60000
+    res = driver.run_p1210(p, gpu, nstep=nstep)
+    ref = oracle.p1210(p.g_coord_pp, p.g_g_pp, p.neq, p.r_pp, p.e, p.v, p.sbary, p.rho, p.dtim, p.pload, nstep, p.npri, form=1)
+    for step, x1, d1, d2 in ref["snaps"]:
+        assert np.array_equal(res["fields"][step], x1), step
+    assert np.array_equal(res["d1x"], ref["snaps"][-1][2]) and np.array_equal(res["d2x"], ref["snaps"][-1][3])
+    gold = golden_fields()
+    for step in (3000, 6000, 9000, 30000, 60000):
+        assert equal_to_printed_digits(nodal(p, res["fields"][step]), gold[step]), step
+    ref0 = oracle.p1210(p.g_coord_pp, p.g_g_pp, p.neq, p.r_pp, p.e, p.v, p.sbary, p.rho, p.dtim, p.pload, 9000, p.npri, form=0)
+    for step, x1, _, _ in ref0["snaps"]:
+        assert np.abs(res["fields"][step] - x1).max() <= 1e-12 * np.abs(x1).max()
+    # a mesh with ragged passes (60 and 42 elements: not multiples of 8) that yields
+    for shape in ((4, 5, 3), (3, 7, 2)):
+        q = synthetic(host, *shape)
+        q.form = 1
+        res = driver.run_p1210(q, gpu)
+        ref = oracle.p1210(q.g_coord_pp, q.g_g_pp, q.neq, q.r_pp, q.e, q.v, q.sbary, q.rho, q.dtim, q.pload, q.nstep, q.npri, form=1)
+        for step, x1, d1, d2 in ref["snaps"]:
+            assert np.array_equal(res["fields"][step], x1), (shape, step)
+        el = oracle.p1210(q.g_coord_pp, q.g_g_pp, q.neq, q.r_pp, q.e, q.v, 1e30, q.rho, q.dtim, q.pload, q.nstep, q.npri, form=1)
+        assert np.abs(el["snaps"][-1][1] - res["x"]).max() > 1e-3 * np.abs(res["x"]).max()
+
+
 def test_needs_twenty_node_bricks(gpu):
     from parafem_b200 import PfError
     p = host.cube_p121(3, 3, 3, 8, aa=1., bb=1., cc=1.)
