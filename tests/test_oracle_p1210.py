@@ -56,6 +56,19 @@ def test_all_golden_fields_of_the_300000_step_run(tiny):
         assert np.abs(x - by_step[step]).max() <= 1e-12 * np.abs(x).max()
 
 
+def test_operator_form_is_another_rounding_of_the_same_update(tiny):
+    """orc_p1210_elements_mf (what the tensor-core kernel computes) against elements_2 as written, and against the golden
+    fields through first yield (the full 300 000 steps were checked once: all 100 fields, 23 s)."""
+    p = tiny
+    a = oracle.p1210(p.g_coord_pp, p.g_g_pp, p.neq, p.r_pp, p.e, p.v, p.sbary, p.rho, p.dtim, GOLDEN_PLOAD, 30000, 3000, form=1)
+    b = oracle.p1210(p.g_coord_pp, p.g_g_pp, p.neq, p.r_pp, p.e, p.v, p.sbary, p.rho, p.dtim, GOLDEN_PLOAD, 30000, 3000, form=0)
+    gold = golden_fields()
+    for (step, x, _, _), (_, y, _, _) in zip(a["snaps"], b["snaps"]):
+        assert not np.array_equal(x, y) and np.abs(x - y).max() <= 1e-12 * np.abs(y).max()
+        if step in gold:
+            assert equal_to_printed_digits(nodal(p, x), gold[step]), step
+
+
 def test_the_written_load_factor_is_not_the_golden_one(tiny):
     p = tiny
     out = oracle.p1210(p.g_coord_pp, p.g_g_pp, p.neq, p.r_pp, p.e, p.v, p.sbary, p.rho, p.dtim, p.pload, 3000, 3000)
