@@ -1078,20 +1078,22 @@ int pf_measure_matvec(pf_handle h, int reps, double *ms_per_launch) {
   int rc = need_device(h); if (rc) return rc;
   NEED(h->have_km && h->have_mesh && reps > 0, "needs pf_setup_mesh, element matrices and reps > 0");
   if (h->matrix_free && (rc = ensure_tables(h))) return rc;
-  const bool prof = h->profile;
-  h->profile = false;
+  struct NoProfile {                       // per-launch events off for the duration, restored on every return path
+    pf_handle h; bool was;
+    explicit NoProfile(pf_handle h_) : h(h_), was(h_->profile) { h->profile = false; }
+    ~NoProfile() { h->profile = was; }
+  } guard(h);
   EventPair ev; CU(ev.create());
   for (int warm = 0; warm < 2 && !rc; ++warm) rc = launch_matvec<true>(h, h->p_ext.p, nullptr);
-  if (!rc) {
-    CU(cudaEventRecord(ev.a, h->stream));
-    for (int i = 0; i < reps && !rc; ++i) rc = launch_matvec<true>(h, h->p_ext.p, nullptr);
-    CU(cudaEventRecord(ev.b, h->stream));
-    CU(cudaEventSynchronize(ev.b));
-    float ms = 0.f; CU(cudaEventElapsedTime(&ms, ev.a, ev.b));
-    *ms_per_launch = (double)ms / reps;
-  }
-  h->profile = prof;
-  return rc;
+  if (rc) return rc;
+  CU(cudaEventRecord(ev.a, h->stream));
+  for (int i = 0; i < reps && !rc; ++i) rc = launch_matvec<true>(h, h->p_ext.p, nullptr);
+  CU(cudaEventRecord(ev.b, h->stream));
+  CU(cudaEventSynchronize(ev.b));
+  if (rc) return rc;
+  float ms = 0.f; CU(cudaEventElapsedTime(&ms, ev.a, ev.b));
+  *ms_per_launch = (double)ms / reps;
+  return 0;
 }
 
 int pf_measure_fp64_tensor(pf_handle h, double *tflops) {
