@@ -45,7 +45,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed building libparafem_b200.so")
         with open(os.path.join(_HERE, "ptxas_info.txt"), "w") as f:
             f.write(res.stdout)
-    for name in ("p121_b200", "p12x_b200"):          # host drivers above the C-ABI (no Fortran compiler here)
+    for name in ("p121_b200", "p12x_b200", "p1210_b200"):          # host drivers above the C-ABI (no Fortran compiler here)
         drv_src, exe = os.path.join(CSRC, name + ".cpp"), os.path.join(_HERE, name)
         if os.path.exists(drv_src) and (force or _stale(exe, [drv_src, LIB])):
             cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), drv_src,

@@ -65,6 +65,22 @@ def test_matrix_free_pcg_equals_oracle(gpu, name, mode):
     assert np.linalg.norm(x - stored["x"]) <= 1e-4 * np.linalg.norm(stored["x"])
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("dims,nod", [((1, 1, 2), 20), ((2, 1, 1), 8), ((1, 3, 3), 20)])
+def test_fewer_elements_than_one_warp_pass(gpu, dims, nod, mode):
+    """2, 2 and 9 elements: the tensor-core kernel's passes of 8 elements are ragged or nearly empty, most consumer warps
+    have nothing to do and the producers' index / ring prologues are longer than the work."""
+    p = host.cube_p121(*dims, nod, aa=1., bb=.5, cc=2., limit=100)
+    solver.setup_problem(gpu, p, matrix_free=mode)
+    pm = np.random.RandomState(5).randn(p.nels, p.ntot)
+    assert np.array_equal(gpu.matvec(pm), oracle.apply_mf(p.g_coord_pp, p.nod, p.nip, p.e, p.v, pm, mode=mode))
+    x, iters, conv = gpu.pcg_solve(p.r_pp, p.tol, p.limit)
+    km = oracle.form_km_elastic(p.g_coord_pp, p.nod, p.nip, p.e, p.v)
+    mf = dict(g_coord_pp=p.g_coord_pp, nod=p.nod, nip=p.nip, e=p.e, v=p.v, mode=mode)
+    ref = oracle.pcg(km, p.g_g_pp, p.neq, p.r_pp, p.tol, p.limit, npes=1, red_mode=1, mf=mf)
+    assert iters == ref["iters"] and np.array_equal(x, ref["x"])
+
+
 def test_matrix_free_tight_tolerance_matches_stored_path(gpu):
     """Driven to tol 1e-13 the two operator roundings land on the same field within 1e-9."""
     p = CASES["hex20"]()

@@ -84,6 +84,31 @@ def test_operator_form_on_the_tensor_cores(gpu, tmp_path):
         assert np.abs(el["snaps"][-1][1] - res["x"]).max() > 1e-3 * np.abs(res["x"]).max()
 
 
+@pytest.mark.parametrize("form", [0, 1])
+def test_cpp_driver_writes_the_golden_displacement_file(tmp_path, form):
+    """p1210_b200 (C++ host code above the C-ABI) on the shipped deck: its <job>.b200.dis, in the layout of the reference's
+    p1210_tiny.dis, holds the golden fields to the digits printed; the log has the reference's lines."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    job = write_tiny_deck(tmp_path)
+    run = subprocess.run([os.path.join(root, "parafem_b200", "p1210_b200"), job, str(GOLDEN_PLOAD), str(form), "30000"],
+                         capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stdout + run.stderr
+    lines = open(job + ".b200.dis").read().splitlines()
+    assert len(lines) == 10 * 70 and lines[0].startswith("*DISPLACEMENT") and lines[1].split() == ["3000"]
+    gold = golden_fields()
+    for k, step in enumerate(range(3000, 30001, 3000)):
+        blk = lines[70 * k:70 * (k + 1)]
+        assert int(blk[1]) == step
+        if step in gold:
+            ours = np.array([[float(x) for x in l.split()[1:]] for l in blk[2:]])
+            assert equal_to_printed_digits(ours, gold[step]), step
+    res = open(job + ".b200.res").read().splitlines()
+    assert res[1] == "There are           68 nodes            8 restrained and          180 equations"
+    assert res[3] == "  Time      Displacement  Velocity   Acceleration " and len(res) == 4 + 1 + 10 + 1
+
+
 def test_needs_twenty_node_bricks(gpu):
     from parafem_b200 import PfError
     p = host.cube_p121(3, 3, 3, 8, aa=1., bb=1., cc=1.)
