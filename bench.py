@@ -53,7 +53,7 @@ def parse():
     #  rejects e.g. --n / --nod even after the script name)
     ap.add_argument("--cube", dest="n", type=int, default=125, help="cube edge in elements (125 = BASELINE config C)")
     ap.add_argument("--hex", dest="nod", type=int, default=20, choices=[8, 20], help="nodes per brick")
-    ap.add_argument("--program", default="p121", choices=["p121", "p123", "p124", "p125"],
+    ap.add_argument("--program", default="p121", choices=["p121", "p123", "p124", "p125", "p1210"],
                     help="p123 = steady heat conduction, 8-node bricks (BASELINE config B at --cube 100); p124 = transient "
                          "conduction, one PCG solve per time step (a step = one time step); p125 = explicit transient "
                          "conduction (a step = one pass of gather / mat-vec / scatter)")
@@ -572,8 +572,12 @@ def transient_bench(ctx):
     args, rank, nranks, s = ctx.args, ctx.rank, ctx.nranks, ctx.s
     n, K, W = args.n, ctx.K, ctx.W
     nye = n * nranks if args.weak else n
-    make = host.cube_p124 if args.program == "p124" else host.cube_p125
-    prob = make(n, nye, n, npes=nranks, numpe=rank + 1)
+    if args.program == "p1210":
+        # explicit elasto-plastic dynamics on 20-node bricks; --matrix-free 1 selects the tensor-core operator form
+        prob = host.cube_p1210(n, nye, n, dtim=2.0e-3 * 4.0 / n, npes=nranks, numpe=rank + 1, form=1 if args.matrix_free else 0)
+    else:
+        make = host.cube_p124 if args.program == "p124" else host.cube_p125
+        prob = make(n, nye, n, npes=nranks, numpe=rank + 1)
     solver.setup_problem(s, prob)
     sampler = ClockSampler(ctx.local)
 
@@ -581,6 +585,8 @@ def transient_bench(ctx):
         """k steps -> (device ms, PCG iterations or steps)."""
         if args.program == "p125":
             return s.explicit_steps(k), k
+        if args.program == "p1210":
+            return s.vm_explicit_steps(k), k
         ms_, its_ = 0.0, 0
         for _ in range(k):
             it, _, m = s.transient_step(prob.tol, prob.limit)
@@ -590,7 +596,7 @@ def transient_bench(ctx):
 
     if args.program == "p124":
         s.transient_start(prob.val0)
-    else:
+    elif args.program == "p125":
         s.explicit_start(prob.val0)
     run(W)
     ctx.barrier()
@@ -604,7 +610,8 @@ def transient_bench(ctx):
     ms = ctx.maxf(ms)
     t = time.perf_counter()
     _, e_units = run(K)
-    x = s.pcg_get_x()                        # e2e: the same through the C-ABI + the field read back to the host
+    # e2e: the same through the C-ABI + the field read back to the host
+    x = s.vm_explicit_get()[0] if args.program == "p1210" else s.pcg_get_x()
     e2e_s = ctx.maxf(time.perf_counter() - t)
     s.set_profile(True); s.reset_profile()   # a third pass with CUDA events around every launch: kernel shares
     run(K)
@@ -636,6 +643,28 @@ def transient_bench(ctx):
                              "algorithmic_bytes_per_launch": bytes_pp, "launches_timed": int(mv_n)},
                 "kernel_ms_per_step": {k: v[0] / K for k, v in km.items()},
                 "clocks": clocks, "x_checksum": float(x.sum())}
+        if args.program == "p1210":
+            # no element matrices: the element kernel is judged by its flops (form 1: FP64 tensor cores, the matrix-free
+            # operator with the Jacobian rebuilt + ~80 flop per Gauss point of plasticity) and by its bytes (coordinates
+            # 480, indices 240, products 480, Gauss-point state 8 x 96 read + written per element)
+            avg = mv_ms / max(mv_n, 1)
+            form = 1 if args.matrix_free else 0
+            per_el = 480 + 240 + 480 + 2 * 8 * 96
+            alg = prob.nels_pp * per_el + prob.neq_pp * 8
+            fl = prob.nels_pp * (mf_flops(1, 20, "k_apply_mf4") + 8 * 80)
+            line["config"]["workload"] = (f"p1210 {n}x{nye}x{n} 20-node bricks (p12meshgen's p121 cube run as explicit elasto-plastic "
+                                          f"dynamics): {prob.nels} elements, {prob.neq} equations, dtim {prob.dtim}, form {form}")
+            line["config"]["step"] = "one explicit step (predictor, gather, Gauss-point stress update, scatter, velocity / acceleration update)"
+            line["config"]["l2"] = f"Gauss-point state per rank {prob.nels_pp * 8 * 96 / 1e6:.0f} MB"
+            dfma, dmma = s.measure_fp64(), s.measure_fp64_tensor()
+            line["roofline"] = {"bound": "fp64" if form else "fp64 (one CTA per element, not tuned)", "unit": "TFLOP/s",
+                                "achieved": fl / (avg / 1e3) / 1e12, "peak": dmma if form else dfma,
+                                "frac": fl / (avg / 1e3) / 1e12 / (dmma if form else dfma), "traffic": None,
+                                "kernel": "k_apply_mf4<MID 1> (operator form, FP64 tensor cores)" if form else "k_p1210_elements (elements_2 as written)",
+                                "flops_per_element_operator_form": fl // max(prob.nels_pp, 1), "avg_launch_ms": avg, "launches_timed": int(mv_n),
+                                "hbm_side": {"bytes_per_element": per_el, "algorithmic_bytes_per_launch": alg,
+                                             "achieved": alg / (avg / 1e3) / 1e9, "peak": pk["hbm_gbs"],
+                                             "frac": alg / (avg / 1e3) / 1e9 / pk["hbm_gbs"]}}
         print(json.dumps(line), flush=True)
 
 
@@ -648,7 +677,7 @@ def main():
     from parafem_b200 import solver
     ctx = Ctx(args)
     rank, nranks, s, K, W = ctx.rank, ctx.nranks, ctx.s, ctx.K, ctx.W
-    if args.program in ("p124", "p125"):
+    if args.program in ("p124", "p125", "p1210"):
         transient_bench(ctx)
         ctx.close()
         return

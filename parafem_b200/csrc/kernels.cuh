@@ -2510,6 +2510,11 @@ k_apply_mf4(const double *__restrict__ g_coord, const int *__restrict__ ggl, con
           fence_proxy_async();                                 // the warp's reads of this index buffer before the async overwrite
           issue_idx(c, b, ps + NIDX * stride);
         }
+        if (MID == 1 && lane < 2) {
+          // p1210: the pass's Gauss-point state (8 elements x 8 points x 48 B, contiguous in each array) towards L2
+          const double *sp = (lane == 0 ? etensor : tensor) + e0 * 48;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(sp), "r"((uint32_t)ne * 384u) : "memory");
+        }
         if (GEOM == 2) {
           // this pass's 40 lines of geometric factors towards L2 (the consumer loads them one pass ahead of their use)
           const double2 *gn = reinterpret_cast<const double2 *>(geom + (e0 >> 5) * kGroupGeom) + (int)(e0 & 31);

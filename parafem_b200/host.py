@@ -464,6 +464,17 @@ def read_deck_p129(job, npes=1, numpe=1):
     return p
 
 
+def cube_p1210(nxe, nye, nze, aa=1.0, bb=1.0, cc=1.0, e=100.0, v=0.3, rho=1.0, sbary=4.0, dtim=2.0e-3, pload=1.0,
+               nstep=240, npri=80, npes=1, numpe=1, form=0):
+    """A p1210 problem on p12meshgen's p121 cube of 20-node bricks (restrained sides and base, 100 units of load on the
+    top patch): the reference ships only the five-element p1210_tiny deck, this is the synthetic workload for sizes
+    beyond it.  Defaults: inside the explicit stability limit for unit bricks, and a yield stress the Gauss points under
+    the load exceed within the first hundred steps.  form: pf_vm_explicit_set_form."""
+    p = cube_p121(nxe, nye, nze, 20, aa=aa, bb=bb, cc=cc, e=e, v=v, npes=npes, numpe=numpe)
+    p.program, p.rho, p.sbary, p.dtim, p.pload, p.nstep, p.npri, p.nres, p.form = 1210, rho, sbary, dtim, pload, nstep, npri, 1, form
+    return p
+
+
 def read_deck_p1210(job, npes=1, numpe=1):
     """Input section of p1210.f90:27-52,106-111 for one rank.  read_p1210 (input.f90:5107-5109) reads
     element, meshgen, partitioner, nels nip nn nr nod loaded_nodes nres, rho e v sbary, dtim nstep npri pload;

@@ -50,9 +50,6 @@ def equal_to_printed_digits(ours, gold, digits=5):
 
 
 def synthetic(host, nxe=4, nye=5, nze=3, npes=1, numpe=1, nstep=240, npri=80):
-    """p12meshgen's p121 cube (20-node bricks, restrained sides and base, 100 units of load on the top patch) run as a
-    p1210 problem: density and time step inside the explicit stability limit, a yield stress the Gauss points under the
-    load exceed within the first hundred steps (so the vmpl branch is exercised)."""
-    p = host.cube_p121(nxe, nye, nze, 20, aa=1., bb=1., cc=1., e=100.0, v=0.3, npes=npes, numpe=numpe)
-    p.program, p.rho, p.sbary, p.dtim, p.pload, p.nstep, p.npri, p.nres = 1210, 1.0, 4.0, 2.0e-3, 1.0, nstep, npri, 1
-    return p
+    """host.cube_p1210 with its defaults: a yield stress the Gauss points under the load exceed within the first
+    hundred steps (so the vmpl branch is exercised)."""
+    return host.cube_p1210(nxe, nye, nze, npes=npes, numpe=numpe, nstep=nstep, npri=npri)
