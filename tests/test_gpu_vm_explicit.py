@@ -84,6 +84,19 @@ def test_operator_form_on_the_tensor_cores(gpu, tmp_path):
         assert np.abs(el["snaps"][-1][1] - res["x"]).max() > 1e-3 * np.abs(res["x"]).max()
 
 
+def test_all_300000_steps_on_the_device_in_the_tensor_core_form(gpu, tmp_path):
+    """The whole golden run on the device (form 1): every kept output step of p1210_tiny.dis, first yield, plastic cycling
+    and the last step, to the digits printed.  (Form 0 equals its oracle bit for bit, and that oracle is checked over the
+    300 000 steps on CPU in tests/test_oracle_p1210.py.)"""
+    p = host.read_deck_p1210(write_tiny_deck(tmp_path))
+    p.pload, p.form = GOLDEN_PLOAD, 1
+    res = driver.run_p1210(p, gpu)
+    gold = golden_fields()
+    assert len(res["fields"]) == 100
+    for step, g in gold.items():
+        assert equal_to_printed_digits(nodal(p, res["fields"][step]), g), step
+
+
 @pytest.mark.parametrize("form", [0, 1])
 def test_cpp_driver_writes_the_golden_displacement_file(tmp_path, form):
     """p1210_b200 (C++ host code above the C-ABI) on the shipped deck: its <job>.b200.dis, in the layout of the reference's
