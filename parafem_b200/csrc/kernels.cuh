@@ -1,13 +1,17 @@
 // kernels.cuh -- sm_100a kernels of the EBE-PCG hot path.
 //
-// Everything here is FP64 and HBM-bound; nothing is tensor-core work.  The file
-// is compiled with --fmad=false so that every a*b+c is a separate IEEE multiply
+// The stored-storkm path (the reference's path, the headline) is FP64 and HBM-bound; nothing of it is
+// tensor-core work.  The file is compiled with --fmad=false so that every a*b+c is a separate IEEE multiply
 // and add: the kernels then produce the same bits as oracle/pf_oracle.c
 // (-ffp-contract=off) because they also use the same summation orders:
 //   mat-vec     u_i = sum_j K(i,j) p_j, j ascending        (p121.f90:93-97)
 //   scatter     contributions in ascending element order    (gather_scatter.f90:759-761)
 //   reductions  the fixed blocked tree described at block_tree() below
 // The kernels are bandwidth-bound, so the lost FMA throughput costs nothing.
+// The MATRIX-FREE variant (BASELINE config E: k_apply_mf / k_apply_mf2 / k_apply_mf3 / k_apply_mf4, and p1210's
+// operator form) is the exception: it is FP64-flop-bound, uses explicit fma() chains and -- k_apply_mf3 / k_apply_mf4 --
+// the FP64 tensor instruction mma.sync.m8n8k4.f64, which is a k-ascending fma chain bit for bit; the oracle mirrors
+// those chains (orc_apply_mf, orc_p1210_elements_mf).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
