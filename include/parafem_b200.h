@@ -403,6 +403,9 @@ int pf_write_deck_scalar(const char *job, const pf_deck_info *info, const double
  * one per line, Fortran e12.<decimals> (5 in the current source, 4 in the shipped
  * p121_demo.ensi.DISPL-000001).                                               */
 void pf_calc_nodes_pp(int64_t nn, int npes, int numpe, int64_t *nodes_pp, int64_t *node_start);
+/* calc_npes_pp (gather_scatter.f90:349-394): the reference's overestimate of a rank's neighbour count (dimensions of
+ * toget / toput before make_ggl).  Not needed by pf_setup_mesh, which counts the neighbours exactly.             */
+int pf_calc_npes_pp(int npes);
 int pf_nodal_values(int nodof, int64_t nn, const int32_t *nf, int64_t ieq_start, int64_t neq_pp,
                     const double *x_pp, int64_t node_start, int64_t nodes_pp, double *out);
 int pf_write_ensi(const char *path, int numvar, int64_t nn, const double *values, int decimals);

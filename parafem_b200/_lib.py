@@ -122,6 +122,7 @@ SIGNATURES = {
                                    vp, vp, vp, vp, vp]),
     "pf_write_deck_scalar": (c_int, [C.c_char_p, P(DeckInfo), vp, vp, vp]),
     "pf_calc_nodes_pp": (None, [c_i64, c_int, c_int, P(c_i64), P(c_i64)]),
+    "pf_calc_npes_pp": (c_int, [c_int]),
     "pf_nodal_values": (c_int, [c_int, c_i64, vp, c_i64, c_i64, vp, c_i64, c_i64, vp]),
     "pf_write_ensi": (c_int, [C.c_char_p, c_int, c_i64, vp, c_int]),
     "pf_make_ggl": (c_int, [c_int, c_i64, vp, c_i64, c_int, c_int, vp, c_i64, vp, vp, P(c_i64)]),

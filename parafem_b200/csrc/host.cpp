@@ -814,6 +814,19 @@ void pf_calc_nodes_pp(int64_t nn, int npes, int numpe, int64_t *nodes_pp, int64_
   even_split(nn, npes, numpe, nodes_pp, node_start);
 }
 
+// calc_npes_pp (gather_scatter.f90:349-394): the reference's rough bound on the number of ranks a rank exchanges with,
+// used to dimension toget / toput BEFORE make_ggl knows the answer ("causes the most execution failures, particularly
+// for pathological cases", :371-372).  This library never needs it -- pf_setup_mesh counts the neighbours exactly
+// (all-gather of the wanted-equation counts) -- but a driver that keeps its own make_ggl call still asks for it.
+int pf_calc_npes_pp(int npes) {
+  if (npes < 1) return 0;
+  if (npes <= 15) return npes;
+  if (npes <= 32) return npes / 2;
+  if (npes <= 256) return npes / 4;
+  if (npes <= 1024) return npes / 7;
+  return npes / 12;
+}
+
 int pf_nodal_values(int nodof, int64_t nn, const int32_t *nf, int64_t ieq_start, int64_t neq_pp,
                     const double *x_pp, int64_t node_start, int64_t nodes_pp, double *out) {
   if (node_start < 1 || node_start + nodes_pp - 1 > nn) return 1;

@@ -494,3 +494,11 @@ def test_binary_geometry_deck_round_trip(tmp_path, prog, nod):
     open(job + ".bin.ensi.geo", "wb").write(bytes(bad))
     with pytest.raises(PfError):
         read(job, binary=True)
+
+
+def test_calc_npes_pp_is_the_reference_table():
+    """gather_scatter.f90:376-389: npes for up to 15 ranks, then /2, /4, /7, /12."""
+    from parafem_b200._lib import lib
+    L = lib()
+    assert [L.pf_calc_npes_pp(n) for n in (1, 8, 15, 16, 32, 33, 256, 257, 1024, 1025, 12000)] == [1, 8, 15, 8, 16, 8, 64, 36, 146, 85, 1000]
+    assert L.pf_calc_npes_pp(0) == 0
